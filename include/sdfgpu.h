@@ -1,0 +1,225 @@
+/*
+ * sdfgpu.h -- C ABI of libsdfgpu.so: the B200 (sm_100a) grid-fill and
+ * sphere-trace hot path of sdf-viewer, behind plain pointers and sizes.
+ *
+ * Each entry point cites the reference interface it replaces; paths are
+ * relative to /root/reference.  The library plugs in at the seam between
+ * `SDFViewerAppScene::render` (src/app/scene/mod.rs:158-225) and
+ * `SDFViewer` / `SDFViewerMaterial` (src/app/scene/sdf/{mod,material}.rs).
+ *
+ * Conventions
+ *  - every function returns SDFGPU_OK (0) or a negative sdfgpu_status; it
+ *    never aborts or throws (reference: a failing guest is logged and a benign
+ *    value returned, src/sdf/wasm/native.rs:196-203).  The message is kept per
+ *    handle (sdfgpu_last_error) or per thread when there is no handle.
+ *  - volumes are `[f32;4]` texels, x fastest, then y, then z
+ *    (flat = (z*H + y)*W + x, src/app/scene/sdf/mod.rs:177).
+ *  - compute entry points enqueue on the handle's CUDA stream and return;
+ *    entry points that fill HOST memory synchronise that stream first.
+ *  - a handle is used from one thread at a time; distinct handles are independent.
+ *  - there is NO CPU fallback: without a CUDA device every call fails with
+ *    SDFGPU_ERR_CUDA.
+ */
+#ifndef SDFGPU_H
+#define SDFGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sdfgpu_ctx sdfgpu_ctx;
+
+typedef enum sdfgpu_status {
+    SDFGPU_OK = 0,
+    SDFGPU_ERR_INVALID = -1, /* bad argument                                  */
+    SDFGPU_ERR_CUDA = -2,    /* CUDA runtime/driver error, or no device       */
+    SDFGPU_ERR_TAPE = -3,    /* malformed tape                                */
+    SDFGPU_ERR_STATE = -4    /* call order (e.g. update before set_tape)      */
+} sdfgpu_status;
+
+/* Uncomputed-voxel marker, f32(0.1) + f32(0.001234) (src/app/scene/sdf/mod.rs:42). */
+float sdfgpu_air_dist(void);
+
+/* ------------------------------------------------------------------ create */
+
+/* SDFViewer::from_bb (src/app/scene/sdf/mod.rs:46-72): the longest bbox axis
+ * gets `max_voxels_side` voxels, the others `(max * size_i / size_max) as usize`.
+ * bb = {min.x,min.y,min.z,max.x,max.y,max.z}.  Both volumes start as AIR_DIST
+ * in all four channels (:76-77). */
+int sdfgpu_create(const float bb[6], uint32_t max_voxels_side, uint32_t loading_passes,
+                  int device, sdfgpu_ctx** out);
+
+/* The voxel-count rule of from_bb alone (src/app/scene/sdf/mod.rs:47-68); no device needed. */
+int sdfgpu_dims_from_bb(const float bb[6], uint32_t max_voxels_side, uint32_t out_voxels[3]);
+
+/* SDFViewer::new_voxels (src/app/scene/sdf/mod.rs:75-101). */
+int sdfgpu_create_voxels(const float bb[6], const uint32_t voxels[3], uint32_t loading_passes,
+                         int device, sdfgpu_ctx** out);
+
+/* Multi-GPU: this handle owns only z in [z_begin, z_end) of the global grid
+ * `voxels`, plus one halo slice on each interior face.  Not in the reference
+ * (single process, src/app/scene/sdf/mod.rs:174 "TODO: parallel iteration"). */
+int sdfgpu_create_slab(const float bb[6], const uint32_t voxels[3], uint32_t loading_passes,
+                       int device, uint32_t z_begin, uint32_t z_end, sdfgpu_ctx** out);
+
+/* Dropping the SDFViewer (scene/mod.rs:154-155 rebuilds it on every set_sdf). */
+void sdfgpu_destroy(sdfgpu_ctx* ctx);
+
+const char* sdfgpu_last_error(const sdfgpu_ctx* ctx); /* ctx may be NULL: per-thread message */
+
+/* tex0.width/height/depth (read by scene/mod.rs:149-150). */
+int sdfgpu_dims(const sdfgpu_ctx* ctx, uint32_t out_voxels[3]);
+/* Stored z range of this handle including halo slices: [z_lo, z_hi). */
+int sdfgpu_slab(const sdfgpu_ctx* ctx, uint32_t* z_begin, uint32_t* z_end,
+                uint32_t* z_lo, uint32_t* z_hi);
+
+/* -------------------------------------------------------------------- fill */
+
+/* Replaces the `sdf: impl SDFSurface` argument of SDFViewer::update
+ * (src/app/scene/sdf/mod.rs:128): the SDF as a tape (sdfgpu_tape.h).  Copies
+ * the bytes; may be called again when a parameter changes
+ * (SDFSurface::set_parameter, src/sdf/mod.rs:73). */
+int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes);
+
+/* SDFViewer::update (src/app/scene/sdf/mod.rs:128-217).
+ *   changed_box : result of sdf.changed() this frame ({min,max}), or NULL for None;
+ *                 merged into the pending box as :131-139 does.
+ *   max_passes  : how many LoadingManager passes to run at most (0 = all that
+ *                 are pending); replaces max_delta_time -- a pass is one kernel.
+ *   iterations  : out, LoadingManager iterations performed (the return value of update).
+ * State machine (pending box, 3-pass re-sample, changed_box_while_loading)
+ * follows :141-154.  A voxel is (re)sampled iff tex0.r == AIR_DIST or its
+ * position lies in the pending box (:184-190); stored values follow :196-208. */
+int sdfgpu_update(sdfgpu_ctx* ctx, const float* changed_box, uint32_t max_passes,
+                  uint64_t* iterations);
+
+/* One-kernel full fill: the state the reference reaches once its
+ * LoadingManager is exhausted on a fresh SDFViewer, without the per-pass
+ * AIR_DIST reads.  Marks loading as finished. */
+int sdfgpu_fill_all(sdfgpu_ctx* ctx);
+
+/* Re-sample only the voxels whose position lies in `box` (closed interval,
+ * float compare, src/app/scene/sdf/mod.rs:187-189): the 60 Hz parameter-sweep
+ * path.  Launches over the index AABB of the box only. */
+int sdfgpu_resample_box(sdfgpu_ctx* ctx, const float box[6], uint64_t* voxels_touched);
+
+/* SDFViewer::commit (src/app/scene/sdf/mod.rs:220-239): no upload is needed
+ * (the volumes already live in HBM); latches
+ * lod_dist_between_samples = 2^passes_left for the tracer (:226). */
+int sdfgpu_commit(sdfgpu_ctx* ctx);
+
+/* loading_mgr.{len(), total_iterations(), passes_left(), passes}
+ * (src/app/scene/sdf/loading.rs:80-105; read by scene/mod.rs:153,229-239). */
+int sdfgpu_loading_state(const sdfgpu_ctx* ctx, uint64_t* len, uint64_t* total_iterations,
+                         uint32_t* passes_left, uint32_t* passes);
+
+/* Reset both volumes to AIR_DIST and restart loading with `loading_passes`
+ * (what set_sdf does by rebuilding the viewer, scene/mod.rs:154-155). */
+int sdfgpu_reset(sdfgpu_ctx* ctx, uint32_t loading_passes);
+
+/* The CPU-side `tex0` / `tex1` Vec<[f32;4]> (src/app/scene/sdf/mod.rs:23-25).
+ * Each buffer holds W*H*(z_end-z_begin) texels of 4 floats (owned slices, no
+ * halo); either pointer may be NULL. */
+int sdfgpu_download(sdfgpu_ctx* ctx, float* tex0, float* tex1);
+
+/* Device pointers of the stored slab (including halo slices, z_lo first), for
+ * CUDA/GL interop and for the NCCL halo exchange done by the host side. */
+int sdfgpu_device_ptrs(sdfgpu_ctx* ctx, void** tex0, void** tex1);
+
+/* ------------------------------------------------------------------- trace */
+
+/* Uniform contract of the tracer: SDFViewerMaterial::use_uniforms
+ * (src/app/scene/sdf/material.rs:50-73) plus the camera of scene/mod.rs:82-95.
+ * Matrices are column-major (cgmath / GLSL). */
+typedef struct sdfgpu_camera {
+    float position[3];     /* cameraPosition                                       */
+    float view[16];        /* camera.view()                                        */
+    float projection[16];  /* camera.projection()                                  */
+    float tint[4];         /* surfaceColorTint, linear (material.rs:64); white     */
+    uint32_t tone_mapping; /* three-d ToneMapping: 0 none 1 reinhard 2 aces 3 filmic */
+    uint32_t color_mapping;/* three-d ColorMapping: 0 none 1 compute-to-sRGB       */
+    float gamma;           /* GAMMA_CORRECTION define (material.rs:39-41); 0 = off */
+    float ambient[3];      /* AmbientLight colour * intensity (scene/mod.rs:106)   */
+} sdfgpu_camera;
+
+/* The camera of SDFViewerAppScene::new (src/app/scene/mod.rs:82-95): eye (2.5,3,5) looking at the
+ * origin, up +Y, fovy 45 deg, near 0.1, far 1000; three-d defaults ACES tone mapping + sRGB colour
+ * mapping; one white ambient light of intensity 1 (scene/mod.rs:106). */
+void sdfgpu_camera_default(sdfgpu_camera* cam, uint32_t width, uint32_t height);
+
+/* cgmath 0.18 Matrix4::look_at_rh / perspective, column-major (what three-d's Camera stores). */
+void sdfgpu_look_at_rh(const float eye[3], const float center[3], const float up[3], float m[16]);
+void sdfgpu_perspective(float fovy_rad, float aspect, float z_near, float z_far, float m[16]);
+
+/* Lower-level ray description derived from the camera (kept public so the
+ * parity tests can hand identical numbers to the oracle):
+ *   unnormalised direction of pixel (i,j), j = 0 at the BOTTOM row (GL window
+ *   coordinates):  base + (i + 0.5) * dx + (j + 0.5) * dy
+ *   bvp = bias * projection * view (material.rs:89-97), column-major. */
+typedef struct sdfgpu_rays {
+    float origin[3];
+    float base[3];
+    float dx[3];
+    float dy[3];
+    float bvp[16];
+} sdfgpu_rays;
+
+int sdfgpu_camera_rays(const sdfgpu_camera* cam, uint32_t width, uint32_t height,
+                       sdfgpu_rays* out);
+
+/* G-buffer record per pixel, SDFGPU_GBUF_FLOATS floats:
+ *  [0..2] hit position  [3] t (distance from ray origin; -1 out of steps,
+ *  -2 out of bounds, -3 ray misses the bounding box => no fragment)
+ *  [4..7] raw tex0 at hit  [8..11] raw tex1 at hit  [12..14] normal  [15] steps */
+#define SDFGPU_GBUF_FLOATS 16
+
+/* material.frag main() (src/app/scene/sdf/material.frag:130-182) for every
+ * pixel whose ray enters the bounding box.  Outputs (any may be NULL):
+ *   rgba  : width*height*4 floats, outColor as the shader writes it
+ *   depth : width*height floats, gl_FragDepth (1.0 on miss)
+ *   gbuf  : width*height*SDFGPU_GBUF_FLOATS floats
+ * Host pointers; the frame is traced on the device and copied back. */
+int sdfgpu_trace(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width, uint32_t height,
+                 float* rgba, float* depth, float* gbuf);
+
+/* Same, but leaves the frame in device memory owned by the handle (valid until
+ * the next trace with a different size, or destroy) and does not synchronise. */
+int sdfgpu_trace_device(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width,
+                        uint32_t height, int want_gbuf, void** rgba_dev, void** depth_dev,
+                        void** gbuf_dev);
+
+/* What the next trace would use: the clip box (the bounding box, or with slab_clip != 0 this
+ * handle's slab sub-box), the lod latched by sdfgpu_commit and the texture filter state
+ * (0 NEAREST until the first commit at lod == 1, then LINEAR; scene/sdf/mod.rs:110-111,226-238).
+ * Any output may be NULL.  For tests that hand the same numbers to the oracle. */
+int sdfgpu_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width, uint32_t height,
+                        int slab_clip, float clip_min[3], float clip_max[3], float* lod,
+                        uint32_t* filter_linear);
+
+/* Trace only this handle's slab (multi-GPU sort-last): rays are clipped to the
+ * slab's own sub-box; per pixel a 64-bit key = (depth bits << 32) | RGBA8 is
+ * written so that an element-wise MIN over ranks composites the frame. */
+int sdfgpu_trace_slab_keys(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width,
+                           uint32_t height, void** keys_dev);
+
+/* Pack / unpack helpers for the composited keys (device -> host RGBA8 + depth). */
+int sdfgpu_keys_download(sdfgpu_ctx* ctx, const void* keys_dev, uint32_t width,
+                         uint32_t height, uint8_t* rgba8, float* depth);
+
+/* ------------------------------------------------------------------ stream */
+
+int sdfgpu_sync(sdfgpu_ctx* ctx);
+/* cudaStream_t of the handle, as void* (for CUDA events on the launching stream). */
+void* sdfgpu_stream(sdfgpu_ctx* ctx);
+/* Kernels launched by this handle so far (bench.py's gpu_launches claim). */
+uint64_t sdfgpu_launch_count(const sdfgpu_ctx* ctx);
+/* Fill-kernel variant knobs (0 = library default); used by the benchmarks. */
+int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFGPU_H */

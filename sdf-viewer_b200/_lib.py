@@ -1,0 +1,120 @@
+"""ctypes binding of libsdfgpu.so (include/sdfgpu.h).
+
+This is the binding a host in another language would write (cgo / JNI / Rust
+`extern "C"`): plain pointers and sizes, no torch types.  The library is
+loaded from this directory; if it is missing the import of the compute API
+fails loudly -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsdfgpu.so")
+
+SDFGPU_OK = 0
+SDFGPU_ERR_INVALID = -1
+SDFGPU_ERR_CUDA = -2
+SDFGPU_ERR_TAPE = -3
+SDFGPU_ERR_STATE = -4
+GBUF_FLOATS = 16
+
+
+class SdfGpuError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"sdfgpu error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+class Camera(C.Structure):  # sdfgpu_camera
+    _fields_ = [
+        ("position", C.c_float * 3),
+        ("view", C.c_float * 16),
+        ("projection", C.c_float * 16),
+        ("tint", C.c_float * 4),
+        ("tone_mapping", C.c_uint32),
+        ("color_mapping", C.c_uint32),
+        ("gamma", C.c_float),
+        ("ambient", C.c_float * 3),
+    ]
+
+
+class Rays(C.Structure):  # sdfgpu_rays
+    _fields_ = [
+        ("origin", C.c_float * 3),
+        ("base", C.c_float * 3),
+        ("dx", C.c_float * 3),
+        ("dy", C.c_float * 3),
+        ("bvp", C.c_float * 16),
+    ]
+
+
+_vp = C.c_void_p
+_u32 = C.c_uint32
+_u64 = C.c_uint64
+_fp = C.POINTER(C.c_float)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+_vpp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); must list every function include/sdfgpu.h declares
+SIGNATURES = {
+    "sdfgpu_air_dist": (C.c_float, []),
+    "sdfgpu_dims_from_bb": (C.c_int, [_fp, _u32, _u32p]),
+    "sdfgpu_create": (C.c_int, [_fp, _u32, _u32, C.c_int, _vpp]),
+    "sdfgpu_create_voxels": (C.c_int, [_fp, _u32p, _u32, C.c_int, _vpp]),
+    "sdfgpu_create_slab": (C.c_int, [_fp, _u32p, _u32, C.c_int, _u32, _u32, _vpp]),
+    "sdfgpu_destroy": (None, [_vp]),
+    "sdfgpu_last_error": (C.c_char_p, [_vp]),
+    "sdfgpu_dims": (C.c_int, [_vp, _u32p]),
+    "sdfgpu_slab": (C.c_int, [_vp, _u32p, _u32p, _u32p, _u32p]),
+    "sdfgpu_set_tape": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "sdfgpu_update": (C.c_int, [_vp, _fp, _u32, _u64p]),
+    "sdfgpu_fill_all": (C.c_int, [_vp]),
+    "sdfgpu_resample_box": (C.c_int, [_vp, _fp, _u64p]),
+    "sdfgpu_commit": (C.c_int, [_vp]),
+    "sdfgpu_loading_state": (C.c_int, [_vp, _u64p, _u64p, _u32p, _u32p]),
+    "sdfgpu_reset": (C.c_int, [_vp, _u32]),
+    "sdfgpu_download": (C.c_int, [_vp, _vp, _vp]),
+    "sdfgpu_device_ptrs": (C.c_int, [_vp, _vpp, _vpp]),
+    "sdfgpu_camera_default": (None, [C.POINTER(Camera), _u32, _u32]),
+    "sdfgpu_look_at_rh": (None, [_fp, _fp, _fp, _fp]),
+    "sdfgpu_perspective": (None, [C.c_float, C.c_float, C.c_float, C.c_float, _fp]),
+    "sdfgpu_camera_rays": (C.c_int, [C.POINTER(Camera), _u32, _u32, C.POINTER(Rays)]),
+    "sdfgpu_trace": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, _vp, _vp, _vp]),
+    "sdfgpu_trace_device": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, C.c_int, _vpp, _vpp, _vpp]),
+    "sdfgpu_trace_params": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, C.c_int, _fp, _fp, _fp, _u32p]),
+    "sdfgpu_trace_slab_keys": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, _vpp]),
+    "sdfgpu_keys_download": (C.c_int, [_vp, _vp, _u32, _u32, _vp, _vp]),
+    "sdfgpu_sync": (C.c_int, [_vp]),
+    "sdfgpu_stream": (_vp, [_vp]),
+    "sdfgpu_launch_count": (_u64, [_vp]),
+    "sdfgpu_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libsdfgpu.so and attach the signatures.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  sdf-viewer_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, ctx=None):
+    if rc != SDFGPU_OK:
+        msg = load().sdfgpu_last_error(ctx)
+        raise SdfGpuError(rc, msg.decode("utf-8", "replace") if msg else "")

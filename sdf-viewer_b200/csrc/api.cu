@@ -1,0 +1,920 @@
+// api.cu -- host side of libsdfgpu.so: the C ABI of include/sdfgpu.h.
+//
+// Holds what `SDFViewer` holds in the reference
+// (/root/reference/src/app/scene/sdf/mod.rs:21-38): the two volumes (here in
+// HBM only), the LoadingManager counters (src/app/scene/sdf/loading.rs:5-19),
+// the pending changed box and the lod latched by commit().  A LoadingManager
+// pass is one launch of the fill kernel (fill.cu); the tracer is trace.cu.
+// There is no CPU fallback: every compute entry point fails with
+// SDFGPU_ERR_CUDA when no device is usable.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sdfgpu_internal.h"
+
+using namespace sdfgpu;
+
+#define SDFGPU_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local std::string g_thread_error;
+
+// src/app/scene/sdf/loading.rs:108-115
+uint32_t prev_power_of_2(uint32_t x) {
+    x |= x >> 1; x |= x >> 2; x |= x >> 4; x |= x >> 8; x |= x >> 16;
+    return x - (x >> 1);
+}
+
+struct LoadingState {  // LoadingManager at pass granularity, loading.rs:5-19
+    uint64_t limits[3] = {0, 0, 0};
+    uint64_t passes = 0;
+    uint64_t step_size = 0;
+    uint64_t iterations = 0;  // always 0 between passes
+    uint64_t total_iterations = 0;
+
+    void reset(uint64_t p) {  // :37-43
+        passes = p;
+        const uint32_t e = (uint32_t)(p > 1 ? p : 1) - 1;
+        step_size = e < 63 ? (uint64_t)1 << e : (uint64_t)1 << 62;
+        iterations = 0;
+        total_iterations = 0;
+    }
+    uint64_t pass_items(uint64_t s) const {
+        return ((limits[0] + s - 1) / s) * ((limits[1] + s - 1) / s) * ((limits[2] + s - 1) / s);
+    }
+    uint64_t len() const {  // :80-89
+        uint64_t s = step_size, it = 0;
+        while (s > 0) {
+            it += pass_items(s);
+            s = prev_power_of_2((uint32_t)(s - 1));
+        }
+        return it - iterations;
+    }
+    uint32_t passes_left() const {  // :99-105
+        if (step_size == 0) return 0;
+        return (uint32_t)log2f((float)step_size) + 1;
+    }
+    void finish_pass() {  // the tail of next(), :67-71
+        total_iterations += pass_items(step_size);
+        step_size = prev_power_of_2((uint32_t)(step_size - 1));
+        iterations = 0;
+    }
+};
+
+}  // namespace
+
+struct sdfgpu_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    float bb[6];
+    uint32_t dims[3];
+    uint32_t z_begin = 0, z_end = 0, z_lo = 0, z_hi = 0;
+    float4* tex0 = nullptr;
+    float4* tex1 = nullptr;
+    size_t stored_texels = 0;
+    LoadingState lm;
+    bool has_changed_box = false;
+    float changed_box[6];
+    bool changed_box_while_loading = false;
+    float lod = 1.0f;            // SDFViewerMaterial::lod_dist_between_samples, material.rs:27
+    bool filter_linear = false;  // GL filter state: NEAREST until a commit at lod == 1 (mod.rs:110-111,227-238)
+    // tape
+    bool has_tape = false;
+    std::vector<unsigned char> img_host;
+    unsigned char* img_dev = nullptr;
+    size_t img_dev_cap = 0;
+    TapeImageHeader hdr;
+    std::vector<float> px, py, pz;  // host copies of the position tables
+    float lut[256];
+    // frame
+    uint32_t fw = 0, fh = 0;
+    float4* rgba_dev = nullptr;
+    float* depth_dev = nullptr;
+    float* gbuf_dev = nullptr;
+    unsigned long long* keys_dev = nullptr;
+    unsigned long long* touched_dev = nullptr;
+    // options
+    int opt_vpt = 0;        // voxels per thread (0 = default)
+    int opt_ctas = 0;       // CTAs per SM (0 = as many as fit)
+    int opt_streaming = 1;  // st.global.cs
+    int opt_fill_halo = 1;  // compute the halo slices locally (0: the host exchanges them)
+    size_t smem_prepared = 0;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(sdfgpu_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_thread_error = buf;
+    return code;
+}
+
+#define CK(ctx, call)                                                                                  \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            (void)cudaGetLastError();                                                                  \
+            return fail((ctx), SDFGPU_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));      \
+        }                                                                                              \
+    } while (0)
+
+float air_dist_value() {  // src/app/scene/sdf/mod.rs:42
+    volatile float a = 1e-1f, b = 0.001234f;
+    return a + b;
+}
+
+// three-d-asset Srgba::to_linear_srgb on one u8 channel (call site scene/sdf/mod.rs:201)
+float srgb_u8_to_linear(unsigned v) {
+    volatile float c = (float)v / 255.0f;
+    if (c < 0.04045f) return c / 12.92f;
+    volatile float t = (c + 0.055f) / 1.055f;
+    return powf(t, 2.4f);
+}
+
+void build_pos_table(std::vector<float>& t, uint32_t n, float lo, float hi) {  // scene/sdf/mod.rs:160-161,179-182
+    t.resize(n);
+    volatile float size = hi - lo;
+    volatile float nm1 = (float)n - 1.0f;
+    for (uint32_t i = 0; i < n; ++i) {
+        volatile float p = (float)i;
+        p = p / nm1;
+        p = p * size;
+        p = p + lo;
+        t[i] = p;
+    }
+}
+
+uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+void set_device(sdfgpu_ctx* ctx) { (void)cudaSetDevice(ctx->device); }
+
+int default_vpt(const sdfgpu_ctx* ctx) { return ctx->opt_vpt ? ctx->opt_vpt : ((ctx->hdr.flags & TAPE_FLAG_CULL) ? 8 : 2); }
+
+// one fill launch over lattice {r0 + i*step} restricted to the index box [lo, hi) per axis
+int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_t hi[3], bool conditional,
+             unsigned long long* touched) {
+    if (!ctx->has_tape) return fail(ctx, SDFGPU_ERR_STATE, "no tape set (call sdfgpu_set_tape first)");
+    FillParams p;
+    memset(&p, 0, sizeof p);
+    uint32_t r0[3], n[3];
+    for (int a = 0; a < 3; ++a) {
+        if (hi[a] <= lo[a]) return SDFGPU_OK;
+        r0[a] = ((lo[a] + step - 1) / step) * step;
+        if (r0[a] >= hi[a]) return SDFGPU_OK;
+        n[a] = (hi[a] - r0[a] + step - 1) / step;
+    }
+    const int V = default_vpt(ctx);
+    p.tex0 = ctx->tex0; p.tex1 = ctx->tex1;
+    p.tape_img = ctx->img_dev; p.tape_img_bytes = (uint32_t)ctx->img_host.size();
+    p.W = ctx->dims[0]; p.H = ctx->dims[1]; p.D = ctx->dims[2];
+    p.z_lo = ctx->z_lo;
+    p.rx0 = r0[0]; p.ry0 = r0[1]; p.rz0 = r0[2];
+    p.nx = n[0]; p.ny = n[1]; p.nz = n[2];
+    p.step = step;
+    p.tiles_x = (n[0] + FILL_TILE_X - 1) / FILL_TILE_X;
+    p.tiles_y = (n[1] + FILL_TILE_Y - 1) / FILL_TILE_Y;
+    p.tiles_z = (n[2] + V - 1) / V;
+    p.conditional = conditional ? 1u : 0u;
+    p.has_box = ctx->has_changed_box ? 1u : 0u;
+    if (ctx->has_changed_box) memcpy(p.box, ctx->changed_box, sizeof p.box);
+    p.air_dist = air_dist_value();
+    p.streaming_stores = ctx->opt_streaming ? 1u : 0u;
+    p.touched = touched;
+    const uint32_t n_cull = (ctx->hdr.flags & TAPE_FLAG_CULL) ? ctx->hdr.cull_count : 0u;
+    const size_t smem = fill_smem_bytes(p.tape_img_bytes, n_cull, ctx->hdr.max_stack, V, &p.stack_floats);
+    if (smem > 227u * 1024u)
+        return fail(ctx, SDFGPU_ERR_TAPE, "tape needs %zu bytes of shared memory per CTA (limit 232448)", smem);
+    if (smem > ctx->smem_prepared) {
+        CK(ctx, fill_prepare(smem));
+        ctx->smem_prepared = smem;
+    }
+    int per_sm = fill_max_ctas_per_sm(V, smem);
+    if (per_sm < 1) return fail(ctx, SDFGPU_ERR_CUDA, "fill kernel does not fit on an SM (smem %zu)", smem);
+    if (ctx->opt_ctas > 0 && ctx->opt_ctas < per_sm) per_sm = ctx->opt_ctas;
+    const uint64_t n_tiles = (uint64_t)p.tiles_x * p.tiles_y * p.tiles_z;
+    if (n_tiles > 0xffffffffull) return fail(ctx, SDFGPU_ERR_INVALID, "grid too large for one launch");
+    uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    CK(ctx, launch_fill(p, V, (int)grid, smem, ctx->stream));
+    ctx->launches++;
+    return SDFGPU_OK;
+}
+
+void fill_z_range(const sdfgpu_ctx* ctx, uint32_t* za, uint32_t* zb) {
+    if (ctx->opt_fill_halo) { *za = ctx->z_lo; *zb = ctx->z_hi; }
+    else { *za = ctx->z_begin; *zb = ctx->z_end; }
+}
+
+int alloc_volumes(sdfgpu_ctx* ctx) {
+    ctx->stored_texels = (size_t)ctx->dims[0] * ctx->dims[1] * (ctx->z_hi - ctx->z_lo);
+    if (ctx->stored_texels) {
+        CK(ctx, cudaMalloc(&ctx->tex0, ctx->stored_texels * sizeof(float4)));
+        CK(ctx, cudaMalloc(&ctx->tex1, ctx->stored_texels * sizeof(float4)));
+    }
+    CK(ctx, cudaMalloc(&ctx->touched_dev, sizeof(unsigned long long)));
+    return SDFGPU_OK;
+}
+
+int reset_volumes(sdfgpu_ctx* ctx) {  // new_voxels, scene/sdf/mod.rs:76-77: AIR_DIST in all 4 channels of both
+    const int grid = ctx->sm_count * 8;
+    CK(ctx, launch_set_const(ctx->tex0, ctx->stored_texels, air_dist_value(), grid, ctx->stream));
+    CK(ctx, launch_set_const(ctx->tex1, ctx->stored_texels, air_dist_value(), grid, ctx->stream));
+    if (ctx->stored_texels) ctx->launches += 2;
+    return SDFGPU_OK;
+}
+
+int create_common(const float bb[6], const uint32_t voxels[3], uint32_t passes, int device, uint32_t z_begin,
+                  uint32_t z_end, sdfgpu_ctx** out) {
+    if (!out) return fail(nullptr, SDFGPU_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!bb || !voxels) return fail(nullptr, SDFGPU_ERR_INVALID, "bb / voxels is NULL");
+    if (z_begin > z_end || z_end > voxels[2]) return fail(nullptr, SDFGPU_ERR_INVALID, "bad slab range");
+    if (voxels[0] > 65535u || voxels[1] > 65535u || voxels[2] > 65535u)
+        return fail(nullptr, SDFGPU_ERR_INVALID, "more than 65535 voxels on a side");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        (void)cudaGetLastError();
+        return fail(nullptr, SDFGPU_ERR_CUDA, "no CUDA device (%s); libsdfgpu has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= n_dev) return fail(nullptr, SDFGPU_ERR_INVALID, "device %d out of range", device);
+    sdfgpu_ctx* ctx = new (std::nothrow) sdfgpu_ctx();
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "out of host memory");
+    ctx->device = device;
+    memcpy(ctx->bb, bb, sizeof ctx->bb);
+    memcpy(ctx->dims, voxels, sizeof ctx->dims);
+    ctx->z_begin = z_begin; ctx->z_end = z_end;
+    ctx->z_lo = z_begin > 0 ? z_begin - 1 : 0;
+    ctx->z_hi = z_end < voxels[2] ? z_end + 1 : voxels[2];
+    if (z_begin == z_end) { ctx->z_lo = z_begin; ctx->z_hi = z_end; }
+    ctx->lm.limits[0] = voxels[0]; ctx->lm.limits[1] = voxels[1]; ctx->lm.limits[2] = voxels[2];
+    ctx->lm.reset(passes);
+    for (unsigned i = 0; i < 256; ++i) ctx->lut[i] = srgb_u8_to_linear(i);
+    build_pos_table(ctx->px, voxels[0], bb[0], bb[3]);
+    build_pos_table(ctx->py, voxels[1], bb[1], bb[4]);
+    build_pos_table(ctx->pz, voxels[2], bb[2], bb[5]);
+    int rc = SDFGPU_OK;
+    do {
+        cudaError_t ce;
+        if ((ce = cudaSetDevice(device)) != cudaSuccess ||
+            (ce = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
+            (ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            rc = fail(nullptr, SDFGPU_ERR_CUDA, "device setup failed: %s", cudaGetErrorString(ce));
+            break;
+        }
+        if ((rc = alloc_volumes(ctx)) != SDFGPU_OK) break;
+        if ((rc = reset_volumes(ctx)) != SDFGPU_OK) break;
+    } while (0);
+    if (rc != SDFGPU_OK) {
+        g_thread_error = ctx->err.empty() ? g_thread_error : ctx->err;
+        sdfgpu_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return SDFGPU_OK;
+}
+
+// Rust `as usize` on f32: saturating, NaN -> 0
+uint32_t f32_as_usize(float f) {
+    if (!(f == f) || f <= 0.0f) return 0u;
+    if (f >= 4294967296.0f) return 0xffffffffu;
+    return (uint32_t)f;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ create
+
+SDFGPU_API float sdfgpu_air_dist(void) { return air_dist_value(); }
+
+SDFGPU_API int sdfgpu_dims_from_bb(const float bb[6], uint32_t max_voxels_side, uint32_t out[3]) {
+    if (!bb || !out) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL argument");
+    // SDFViewer::from_bb, scene/sdf/mod.rs:47-68.  Iterator::max_by keeps the LAST maximum.
+    volatile float sz[3] = {bb[3] - bb[0], bb[4] - bb[1], bb[5] - bb[2]};
+    int max_dim = 0;
+    for (int i = 1; i < 3; ++i)
+        if (sz[i] >= sz[max_dim]) max_dim = i;
+    for (int i = 0; i < 3; ++i) {
+        if (i == max_dim) {
+            out[i] = max_voxels_side;
+        } else {
+            volatile float f = (float)max_voxels_side * sz[i];
+            f = f / sz[max_dim];
+            out[i] = f32_as_usize(f);
+        }
+    }
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_create(const float bb[6], uint32_t max_voxels_side, uint32_t loading_passes, int device,
+                             sdfgpu_ctx** out) {
+    uint32_t dims[3];
+    int rc = sdfgpu_dims_from_bb(bb, max_voxels_side, dims);
+    if (rc != SDFGPU_OK) return rc;
+    return create_common(bb, dims, loading_passes, device, 0, dims[2], out);
+}
+
+SDFGPU_API int sdfgpu_create_voxels(const float bb[6], const uint32_t voxels[3], uint32_t loading_passes, int device,
+                                    sdfgpu_ctx** out) {
+    if (!voxels) return fail(nullptr, SDFGPU_ERR_INVALID, "voxels is NULL");
+    return create_common(bb, voxels, loading_passes, device, 0, voxels[2], out);
+}
+
+SDFGPU_API int sdfgpu_create_slab(const float bb[6], const uint32_t voxels[3], uint32_t loading_passes, int device,
+                                  uint32_t z_begin, uint32_t z_end, sdfgpu_ctx** out) {
+    return create_common(bb, voxels, loading_passes, device, z_begin, z_end, out);
+}
+
+SDFGPU_API void sdfgpu_destroy(sdfgpu_ctx* ctx) {
+    if (!ctx) return;
+    set_device(ctx);
+    if (ctx->stream) (void)cudaStreamSynchronize(ctx->stream);
+    (void)cudaFree(ctx->tex0); (void)cudaFree(ctx->tex1); (void)cudaFree(ctx->img_dev);
+    (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
+    (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->touched_dev);
+    if (ctx->stream) (void)cudaStreamDestroy(ctx->stream);
+    (void)cudaGetLastError();
+    delete ctx;
+}
+
+SDFGPU_API const char* sdfgpu_last_error(const sdfgpu_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_thread_error.c_str();
+}
+
+SDFGPU_API int sdfgpu_dims(const sdfgpu_ctx* ctx, uint32_t out_voxels[3]) {
+    if (!ctx || !out_voxels) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL argument");
+    memcpy(out_voxels, ctx->dims, sizeof ctx->dims);
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_slab(const sdfgpu_ctx* ctx, uint32_t* z_begin, uint32_t* z_end, uint32_t* z_lo, uint32_t* z_hi) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (z_begin) *z_begin = ctx->z_begin;
+    if (z_end) *z_end = ctx->z_end;
+    if (z_lo) *z_lo = ctx->z_lo;
+    if (z_hi) *z_hi = ctx->z_hi;
+    return SDFGPU_OK;
+}
+
+// -------------------------------------------------------------------- tape
+
+SDFGPU_API int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (!tape) return fail(ctx, SDFGPU_ERR_INVALID, "tape is NULL");
+    if (tape_bytes < sizeof(sdft_header)) return fail(ctx, SDFGPU_ERR_TAPE, "tape shorter than its header");
+    sdft_header h;
+    memcpy(&h, tape, sizeof h);
+    if (h.magic != SDFT_MAGIC) return fail(ctx, SDFGPU_ERR_TAPE, "bad tape magic 0x%08x", h.magic);
+    if (h.version != SDFT_VERSION) return fail(ctx, SDFGPU_ERR_TAPE, "unsupported tape version %u", h.version);
+    if (h.n_instr > SDFT_MAX_INSTR || h.n_prims > SDFT_MAX_PRIMS || h.n_consts > SDFT_MAX_CONSTS)
+        return fail(ctx, SDFGPU_ERR_TAPE, "tape exceeds limits (%u instr, %u prims, %u consts)", h.n_instr, h.n_prims,
+                    h.n_consts);
+    const size_t need = sizeof(sdft_header) + (size_t)h.n_instr * sizeof(sdft_instr) +
+                        (size_t)h.n_prims * sizeof(sdft_prim) + (size_t)h.n_consts * 4;
+    if (need > tape_bytes) return fail(ctx, SDFGPU_ERR_TAPE, "tape truncated: %zu bytes needed, %zu given", need, tape_bytes);
+    std::vector<sdft_instr> instr(h.n_instr);
+    std::vector<sdft_prim> prims(h.n_prims);
+    std::vector<float> consts(h.n_consts);
+    const unsigned char* b = (const unsigned char*)tape + sizeof h;
+    if (h.n_instr) memcpy(instr.data(), b, instr.size() * sizeof(sdft_instr));
+    b += instr.size() * sizeof(sdft_instr);
+    if (h.n_prims) memcpy(prims.data(), b, prims.size() * sizeof(sdft_prim));
+    b += prims.size() * sizeof(sdft_prim);
+    if (h.n_consts) memcpy(consts.data(), b, consts.size() * 4);
+
+    // ---- validate: operands in range, stack balanced
+    uint32_t sp = 0, max_sp = 0, n_ranges = 0, cull_first = 0, cull_count = 0;
+    bool p_clean = true, cull_ok = false;
+    for (uint32_t pc = 0; pc < h.n_instr; ++pc) {
+        const sdft_instr& I = instr[pc];
+        bool end = false;
+        switch (I.op) {
+            case SDFT_OP_END: end = true; break;
+            case SDFT_OP_PRIM: case SDFT_OP_UNION_PRIM: case SDFT_OP_INTER_PRIM:
+                if (I.a >= h.n_prims) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: primitive %u out of range", pc, I.a);
+                break;
+            case SDFT_OP_UNION_RANGE:
+                if (I.b < 1 || (uint64_t)I.a + I.b > h.n_prims)
+                    return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: primitive range [%u,+%u) out of range", pc, I.a, I.b);
+                ++n_ranges;
+                cull_first = I.a; cull_count = I.b; cull_ok = p_clean;
+                break;
+            case SDFT_OP_PUSH:
+                if (sp >= SDFT_MAX_STACK) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: stack overflow", pc);
+                ++sp; if (sp > max_sp) max_sp = sp;
+                break;
+            case SDFT_OP_POP_UNION: case SDFT_OP_POP_INTER:
+                if (sp == 0) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: stack underflow", pc);
+                --sp;
+                break;
+            case SDFT_OP_POP_DEMO_DIFF:
+                if (sp == 0) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: stack underflow", pc);
+                if ((uint64_t)I.a + 7 > h.n_consts) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: constants out of range", pc);
+                --sp;
+                break;
+            case SDFT_OP_D_NEG: case SDFT_OP_D_ABS: case SDFT_OP_D_ADD: case SDFT_OP_D_MUL: case SDFT_OP_D_MAX:
+            case SDFT_OP_D_MIN: break;
+            case SDFT_OP_M_SET:
+                if ((uint64_t)I.a + 6 > h.n_consts) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: constants out of range", pc);
+                break;
+            case SDFT_OP_P_RESET: p_clean = true; break;
+            case SDFT_OP_P_SUB:
+                if ((uint64_t)I.a + 3 > h.n_consts) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: constants out of range", pc);
+                p_clean = false;
+                break;
+            case SDFT_OP_P_MUL: case SDFT_OP_P_ABS: p_clean = false; break;
+            default: return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: unknown op %u", pc, I.op);
+        }
+        if (end) break;
+    }
+    for (uint32_t k = 0; k < h.n_prims; ++k) {
+        const uint32_t shape = prims[k].kind & 0xffu, mat = (prims[k].kind >> 8) & 0xffu;
+        if (shape > SDFT_SHAPE_BOX_LINF || mat > SDFT_MAT_NORMAL || (prims[k].kind >> 16) != 0)
+            return fail(ctx, SDFGPU_ERR_TAPE, "primitive %u: unknown kind 0x%x", k, prims[k].kind);
+    }
+
+    // ---- build the shared-memory image
+    TapeImageHeader ih;
+    memset(&ih, 0, sizeof ih);
+    ih.n_instr = h.n_instr; ih.n_prims = h.n_prims; ih.n_consts = h.n_consts;
+    ih.max_stack = max_sp;
+    if (n_ranges == 1 && cull_ok && cull_count >= 16) {
+        ih.flags |= TAPE_FLAG_CULL;
+        ih.cull_first = cull_first; ih.cull_count = cull_count;
+    }
+    uint32_t off = sizeof(TapeImageHeader);
+    ih.off_instr = off; off += align16(h.n_instr * 16u);
+    ih.off_geom = off; off += h.n_prims * 16u;
+    ih.off_mat0 = off; off += h.n_prims * 16u;
+    ih.off_mat1 = off; off += h.n_prims * 16u;
+    ih.off_consts = off; off += align16(h.n_consts * 4u);
+    ih.off_lut = off; off += 1024u;
+    ih.off_px = off; off += align16(ctx->dims[0] * 4u);
+    ih.off_py = off; off += align16(ctx->dims[1] * 4u);
+    ih.off_pz = off; off += align16(ctx->dims[2] * 4u);
+    if (off > 200u * 1024u)
+        return fail(ctx, SDFGPU_ERR_TAPE, "tape image is %u bytes; the fill kernel stages at most 204800 in shared memory", off);
+    std::vector<unsigned char> img(off, 0);
+    memcpy(img.data(), &ih, sizeof ih);
+    if (h.n_instr) memcpy(img.data() + ih.off_instr, instr.data(), h.n_instr * 16u);
+    for (uint32_t k = 0; k < h.n_prims; ++k) {
+        const sdft_prim& pr = prims[k];
+        const float g[4] = {pr.center[0], pr.center[1], pr.center[2], pr.size};
+        const float m0[4] = {pr.color[0], pr.color[1], pr.color[2], pr.metallic};
+        float m1[4] = {pr.roughness, pr.occlusion, pr.air_skip, 0.0f};
+        memcpy(&m1[3], &pr.kind, 4);
+        memcpy(img.data() + ih.off_geom + 16u * k, g, 16);
+        memcpy(img.data() + ih.off_mat0 + 16u * k, m0, 16);
+        memcpy(img.data() + ih.off_mat1 + 16u * k, m1, 16);
+    }
+    if (h.n_consts) memcpy(img.data() + ih.off_consts, consts.data(), h.n_consts * 4u);
+    memcpy(img.data() + ih.off_lut, ctx->lut, 1024);
+    if (ctx->dims[0]) memcpy(img.data() + ih.off_px, ctx->px.data(), ctx->dims[0] * 4u);
+    if (ctx->dims[1]) memcpy(img.data() + ih.off_py, ctx->py.data(), ctx->dims[1] * 4u);
+    if (ctx->dims[2]) memcpy(img.data() + ih.off_pz, ctx->pz.data(), ctx->dims[2] * 4u);
+
+    set_device(ctx);
+    if (img.size() > ctx->img_dev_cap) {
+        // the previous image may still be read by a fill in flight
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        (void)cudaFree(ctx->img_dev);
+        ctx->img_dev = nullptr; ctx->img_dev_cap = 0;
+        CK(ctx, cudaMalloc(&ctx->img_dev, img.size()));
+        ctx->img_dev_cap = img.size();
+    }
+    // stream-ordered after earlier fills; the source is pageable, so this call returns once it is staged
+    CK(ctx, cudaMemcpyAsync(ctx->img_dev, img.data(), img.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->img_host.swap(img);
+    ctx->hdr = ih;
+    ctx->has_tape = true;
+    return SDFGPU_OK;
+}
+
+// -------------------------------------------------------------------- fill
+
+SDFGPU_API int sdfgpu_update(sdfgpu_ctx* ctx, const float* changed_box, uint32_t max_passes, uint64_t* iterations) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (iterations) *iterations = 0;
+    if (!ctx->has_tape) return fail(ctx, SDFGPU_ERR_STATE, "no tape set (call sdfgpu_set_tape first)");
+    set_device(ctx);
+    bool just_changed_box = false;
+    if (changed_box) {  // scene/sdf/mod.rs:131-139; merge_bounding_boxes, src/sdf/defaults.rs:59-72
+        if (ctx->has_changed_box) {
+            for (int i = 0; i < 3; ++i) {
+                ctx->changed_box[i] = fminf(ctx->changed_box[i], changed_box[i]);
+                ctx->changed_box[3 + i] = fmaxf(ctx->changed_box[3 + i], changed_box[3 + i]);
+            }
+        } else {
+            memcpy(ctx->changed_box, changed_box, sizeof ctx->changed_box);
+            ctx->has_changed_box = true;
+        }
+        ctx->changed_box_while_loading = ctx->lm.len() > 0 || ctx->changed_box_while_loading;
+        just_changed_box = true;
+    }
+    if (ctx->has_changed_box && ctx->lm.len() == 0) {  // :144-154
+        ctx->lm.reset(3);
+        if (!just_changed_box) {
+            if (!ctx->changed_box_while_loading) ctx->has_changed_box = false;
+            ctx->changed_box_while_loading = false;
+        }
+    }
+    const uint64_t start_iter = ctx->lm.total_iterations;
+    uint32_t za, zb;
+    fill_z_range(ctx, &za, &zb);
+    uint32_t done = 0;
+    while (ctx->lm.step_size != 0 && (max_passes == 0 || done < max_passes)) {  // :173-215, one pass per launch
+        const uint32_t lo[3] = {0, 0, za}, hi[3] = {ctx->dims[0], ctx->dims[1], zb};
+        const int rc = run_fill(ctx, (uint32_t)ctx->lm.step_size, lo, hi, true, nullptr);
+        if (rc != SDFGPU_OK) return rc;
+        ctx->lm.finish_pass();
+        ++done;
+    }
+    if (iterations) *iterations = ctx->lm.total_iterations - start_iter;  // :216
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_fill_all(sdfgpu_ctx* ctx) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    set_device(ctx);
+    uint32_t za, zb;
+    fill_z_range(ctx, &za, &zb);
+    const uint32_t lo[3] = {0, 0, za}, hi[3] = {ctx->dims[0], ctx->dims[1], zb};
+    const int rc = run_fill(ctx, 1, lo, hi, false, nullptr);
+    if (rc != SDFGPU_OK) return rc;
+    while (ctx->lm.step_size != 0) ctx->lm.finish_pass();
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_resample_box(sdfgpu_ctx* ctx, const float box[6], uint64_t* voxels_touched) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (voxels_touched) *voxels_touched = 0;
+    if (!box) return fail(ctx, SDFGPU_ERR_INVALID, "box is NULL");
+    if (!ctx->has_tape) return fail(ctx, SDFGPU_ERR_STATE, "no tape set (call sdfgpu_set_tape first)");
+    set_device(ctx);
+    // index AABB of the voxels whose position lies in the closed box (float compare, :187-189)
+    uint32_t lo[3], hi[3];
+    const std::vector<float>* tab[3] = {&ctx->px, &ctx->py, &ctx->pz};
+    for (int a = 0; a < 3; ++a) {
+        uint32_t first = 0xffffffffu, last = 0;
+        const std::vector<float>& t = *tab[a];
+        for (uint32_t i = 0; i < t.size(); ++i)
+            if (t[i] >= box[a] && t[i] <= box[3 + a]) {
+                if (first == 0xffffffffu) first = i;
+                last = i;
+            }
+        if (first == 0xffffffffu) return SDFGPU_OK;  // nothing inside
+        lo[a] = first; hi[a] = last + 1;
+    }
+    uint32_t za, zb;
+    fill_z_range(ctx, &za, &zb);
+    if (lo[2] < za) lo[2] = za;
+    if (hi[2] > zb) hi[2] = zb;
+    // temporarily present `box` as the pending box of a conditional pass
+    const bool saved_has = ctx->has_changed_box;
+    float saved[6];
+    memcpy(saved, ctx->changed_box, sizeof saved);
+    ctx->has_changed_box = true;
+    memcpy(ctx->changed_box, box, sizeof saved);
+    int rc = SDFGPU_OK;
+    if (voxels_touched) {
+        cudaError_t e = cudaMemsetAsync(ctx->touched_dev, 0, sizeof(unsigned long long), ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, SDFGPU_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == SDFGPU_OK) rc = run_fill(ctx, 1, lo, hi, true, voxels_touched ? ctx->touched_dev : nullptr);
+    ctx->has_changed_box = saved_has;
+    memcpy(ctx->changed_box, saved, sizeof saved);
+    if (rc != SDFGPU_OK) return rc;
+    if (voxels_touched) {
+        unsigned long long n = 0;
+        CK(ctx, cudaMemcpyAsync(&n, ctx->touched_dev, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        *voxels_touched = n;
+    }
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_commit(sdfgpu_ctx* ctx) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    ctx->lod = exp2f((float)(uint8_t)ctx->lm.passes_left());  // scene/sdf/mod.rs:226
+    if (ctx->lod == 1.0f) ctx->filter_linear = true;         // :227-230, never switched back
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_loading_state(const sdfgpu_ctx* ctx, uint64_t* len, uint64_t* total_iterations,
+                                    uint32_t* passes_left, uint32_t* passes) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (len) *len = ctx->lm.len();
+    if (total_iterations) *total_iterations = ctx->lm.total_iterations;
+    if (passes_left) *passes_left = ctx->lm.passes_left();
+    if (passes) *passes = (uint32_t)ctx->lm.passes;
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_reset(sdfgpu_ctx* ctx, uint32_t loading_passes) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    set_device(ctx);
+    const int rc = reset_volumes(ctx);
+    if (rc != SDFGPU_OK) return rc;
+    ctx->lm.reset(loading_passes);
+    ctx->has_changed_box = false;
+    ctx->changed_box_while_loading = false;
+    ctx->lod = 1.0f;
+    ctx->filter_linear = false;
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_download(sdfgpu_ctx* ctx, float* tex0, float* tex1) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    set_device(ctx);
+    const size_t slice = (size_t)ctx->dims[0] * ctx->dims[1];
+    const size_t off = (size_t)(ctx->z_begin - ctx->z_lo) * slice;
+    const size_t n = (size_t)(ctx->z_end - ctx->z_begin) * slice;
+    if (n) {
+        if (tex0) CK(ctx, cudaMemcpyAsync(tex0, ctx->tex0 + off, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+        if (tex1) CK(ctx, cudaMemcpyAsync(tex1, ctx->tex1 + off, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_device_ptrs(sdfgpu_ctx* ctx, void** tex0, void** tex1) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (tex0) *tex0 = ctx->tex0;
+    if (tex1) *tex1 = ctx->tex1;
+    return SDFGPU_OK;
+}
+
+// ------------------------------------------------------------------- trace
+
+namespace {
+
+void mat4_mul(const float* a, const float* b, float* out) {  // column-major out = a * b
+    float r[16];
+    for (int c = 0; c < 4; ++c)
+        for (int rr = 0; rr < 4; ++rr) {
+            volatile float s = 0.0f;
+            for (int k = 0; k < 4; ++k) {
+                volatile float t = a[k * 4 + rr] * b[c * 4 + k];
+                s = s + t;
+            }
+            r[c * 4 + rr] = s;
+        }
+    memcpy(out, r, sizeof r);
+}
+
+void normalize3(float v[3]) {  // cgmath: v * (1 / |v|)
+    volatile float m = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    volatile float inv = 1.0f / m;
+    v[0] *= inv; v[1] *= inv; v[2] *= inv;
+}
+
+int ensure_frame(sdfgpu_ctx* ctx, uint32_t w, uint32_t h, bool want_gbuf, bool want_keys) {
+    const size_t n = (size_t)w * h;
+    if (w != ctx->fw || h != ctx->fh) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
+        (void)cudaFree(ctx->keys_dev);
+        ctx->rgba_dev = nullptr; ctx->depth_dev = nullptr; ctx->gbuf_dev = nullptr; ctx->keys_dev = nullptr;
+        ctx->fw = ctx->fh = 0;
+        if (n) {
+            CK(ctx, cudaMalloc(&ctx->rgba_dev, n * sizeof(float4)));
+            CK(ctx, cudaMalloc(&ctx->depth_dev, n * sizeof(float)));
+        }
+        ctx->fw = w; ctx->fh = h;
+    }
+    if (want_gbuf && !ctx->gbuf_dev && n) CK(ctx, cudaMalloc(&ctx->gbuf_dev, n * SDFGPU_GBUF_FLOATS * sizeof(float)));
+    if (want_keys && !ctx->keys_dev && n) CK(ctx, cudaMalloc(&ctx->keys_dev, n * sizeof(unsigned long long)));
+    return SDFGPU_OK;
+}
+
+int fill_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t w, uint32_t h, bool slab_clip, TraceParams* tp) {
+    sdfgpu_rays rays;
+    int rc = sdfgpu_camera_rays(cam, w, h, &rays);
+    if (rc != SDFGPU_OK) return fail(ctx, rc, "%s", g_thread_error.c_str());
+    memset(tp, 0, sizeof *tp);
+    tp->tex0 = ctx->tex0; tp->tex1 = ctx->tex1;
+    memcpy(tp->origin, rays.origin, 12); memcpy(tp->base, rays.base, 12);
+    memcpy(tp->dx, rays.dx, 12); memcpy(tp->dy, rays.dy, 12); memcpy(tp->bvp, rays.bvp, 64);
+    for (int a = 0; a < 3; ++a) {
+        tp->bmin[a] = tp->clip_min[a] = ctx->bb[a];
+        tp->bmax[a] = tp->clip_max[a] = ctx->bb[3 + a];
+    }
+    if (slab_clip) {  // texel slices [z_begin, z_end) <=> p01.z * D in [z_begin, z_end)
+        volatile float size = ctx->bb[5] - ctx->bb[2];
+        volatile float a0 = (float)ctx->z_begin / (float)ctx->dims[2], a1 = (float)ctx->z_end / (float)ctx->dims[2];
+        if (ctx->z_begin > 0) { volatile float t = a0 * size; tp->clip_min[2] = ctx->bb[2] + t; }
+        if (ctx->z_end < ctx->dims[2]) { volatile float t = a1 * size; tp->clip_max[2] = ctx->bb[2] + t; }
+    }
+    tp->W = ctx->dims[0]; tp->H = ctx->dims[1]; tp->D = ctx->dims[2];
+    tp->z_lo = ctx->z_lo; tp->z_hi = ctx->z_hi;
+    tp->lod = ctx->lod;
+    tp->filter_linear = ctx->filter_linear ? 1u : 0u;
+    memcpy(tp->tint, cam->tint, 16);
+    tp->tone_mapping = cam->tone_mapping; tp->color_mapping = cam->color_mapping;
+    tp->gamma = cam->gamma;
+    memcpy(tp->ambient, cam->ambient, 12);
+    tp->width = w; tp->height = h;
+    return SDFGPU_OK;
+}
+
+}  // namespace
+
+SDFGPU_API void sdfgpu_look_at_rh(const float eye[3], const float center[3], const float up[3], float m[16]) {
+    // cgmath 0.18 Matrix4::look_to_rh (three-d Camera::set_view; call site scene/mod.rs:82-95)
+    float f[3] = {center[0] - eye[0], center[1] - eye[1], center[2] - eye[2]};
+    normalize3(f);
+    float s[3] = {f[1] * up[2] - f[2] * up[1], f[2] * up[0] - f[0] * up[2], f[0] * up[1] - f[1] * up[0]};
+    normalize3(s);
+    const float u[3] = {s[1] * f[2] - s[2] * f[1], s[2] * f[0] - s[0] * f[2], s[0] * f[1] - s[1] * f[0]};
+    const float es = eye[0] * s[0] + eye[1] * s[1] + eye[2] * s[2];
+    const float eu = eye[0] * u[0] + eye[1] * u[1] + eye[2] * u[2];
+    const float ef = eye[0] * f[0] + eye[1] * f[1] + eye[2] * f[2];
+    const float r[16] = {s[0], u[0], -f[0], 0.f, s[1], u[1], -f[1], 0.f, s[2], u[2], -f[2], 0.f, -es, -eu, ef, 1.f};
+    memcpy(m, r, sizeof r);
+}
+
+SDFGPU_API void sdfgpu_perspective(float fovy_rad, float aspect, float z_near, float z_far, float m[16]) {
+    const float f = 1.0f / tanf(fovy_rad / 2.0f);  // cgmath PerspectiveFov -> Matrix4
+    const float r[16] = {f / aspect, 0, 0, 0, 0, f, 0, 0, 0, 0, (z_far + z_near) / (z_near - z_far), -1.f,
+                         0, 0, (2.f * z_far * z_near) / (z_near - z_far), 0};
+    memcpy(m, r, sizeof r);
+}
+
+SDFGPU_API void sdfgpu_camera_default(sdfgpu_camera* cam, uint32_t width, uint32_t height) {
+    if (!cam) return;
+    memset(cam, 0, sizeof *cam);
+    const float eye[3] = {2.5f, 3.0f, 5.0f}, center[3] = {0.f, 0.f, 0.f}, up[3] = {0.f, 1.f, 0.f};  // scene/mod.rs:89-91
+    memcpy(cam->position, eye, 12);
+    sdfgpu_look_at_rh(eye, center, up, cam->view);
+    const float aspect = height ? (float)width / (float)height : 1.0f;
+    sdfgpu_perspective(45.0f * 3.14159265358979323846f / 180.0f, aspect, 0.1f, 1000.0f, cam->projection);  // :92-94
+    cam->tint[0] = cam->tint[1] = cam->tint[2] = cam->tint[3] = 1.0f;  // Srgba::WHITE, material.rs:29
+    cam->tone_mapping = 2;   // three-d Camera default: ToneMapping::Aces
+    cam->color_mapping = 1;  // ColorMapping::ComputeToSrgb
+    cam->gamma = 0.0f;       // env "gamma" unset, material.rs:39
+    cam->ambient[0] = cam->ambient[1] = cam->ambient[2] = 1.0f;  // AmbientLight(1.0, WHITE), scene/mod.rs:106
+}
+
+SDFGPU_API int sdfgpu_camera_rays(const sdfgpu_camera* cam, uint32_t width, uint32_t height, sdfgpu_rays* out) {
+    if (!cam || !out) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL argument");
+    if (width == 0 || height == 0) return fail(nullptr, SDFGPU_ERR_INVALID, "empty frame");
+    const float* V = cam->view;
+    const float* P = cam->projection;
+    if (P[0] == 0.0f || P[5] == 0.0f) return fail(nullptr, SDFGPU_ERR_INVALID, "singular projection");
+    // rows of the view rotation: side, up, -forward
+    const float s[3] = {V[0], V[4], V[8]}, u[3] = {V[1], V[5], V[9]}, f[3] = {-V[2], -V[6], -V[10]};
+    const float sx = 1.0f / P[0], sy = 1.0f / P[5];
+    for (int a = 0; a < 3; ++a) {
+        out->origin[a] = cam->position[a];
+        out->base[a] = f[a] - s[a] * sx - u[a] * sy;
+        out->dx[a] = s[a] * (2.0f * sx / (float)width);
+        out->dy[a] = u[a] * (2.0f * sy / (float)height);
+    }
+    const float bias[16] = {0.5f, 0, 0, 0, 0, 0.5f, 0, 0, 0, 0, 0.5f, 0, 0.5f, 0.5f, 0.5f, 1.0f};  // material.rs:90-95
+    float pv[16];
+    mat4_mul(P, V, pv);
+    mat4_mul(bias, pv, out->bvp);
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_trace_device(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width, uint32_t height,
+                                   int want_gbuf, void** rgba_dev, void** depth_dev, void** gbuf_dev) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (!cam) return fail(ctx, SDFGPU_ERR_INVALID, "cam is NULL");
+    if (width == 0 || height == 0) return fail(ctx, SDFGPU_ERR_INVALID, "empty frame");
+    set_device(ctx);
+    int rc = ensure_frame(ctx, width, height, want_gbuf != 0, false);
+    if (rc != SDFGPU_OK) return rc;
+    TraceParams tp;
+    if ((rc = fill_trace_params(ctx, cam, width, height, false, &tp)) != SDFGPU_OK) return rc;
+    tp.rgba = ctx->rgba_dev; tp.depth = ctx->depth_dev;
+    tp.gbuf = want_gbuf ? ctx->gbuf_dev : nullptr;
+    CK(ctx, launch_trace(tp, 0, ctx->stream));
+    ctx->launches++;
+    if (rgba_dev) *rgba_dev = ctx->rgba_dev;
+    if (depth_dev) *depth_dev = ctx->depth_dev;
+    if (gbuf_dev) *gbuf_dev = want_gbuf ? ctx->gbuf_dev : nullptr;
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_trace(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width, uint32_t height, float* rgba,
+                            float* depth, float* gbuf) {
+    void *r = nullptr, *d = nullptr, *g = nullptr;
+    const int rc = sdfgpu_trace_device(ctx, cam, width, height, gbuf != nullptr, &r, &d, &g);
+    if (rc != SDFGPU_OK) return rc;
+    const size_t n = (size_t)width * height;
+    if (rgba) CK(ctx, cudaMemcpyAsync(rgba, r, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (depth) CK(ctx, cudaMemcpyAsync(depth, d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (gbuf) CK(ctx, cudaMemcpyAsync(gbuf, g, n * SDFGPU_GBUF_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width, uint32_t height,
+                                   int slab_clip, float clip_min[3], float clip_max[3], float* lod,
+                                   uint32_t* filter_linear) {
+    if (!ctx || !cam) return fail(ctx, SDFGPU_ERR_INVALID, "NULL argument");
+    TraceParams tp;
+    const int rc = fill_trace_params(ctx, cam, width, height, slab_clip != 0, &tp);
+    if (rc != SDFGPU_OK) return rc;
+    if (clip_min) memcpy(clip_min, tp.clip_min, 12);
+    if (clip_max) memcpy(clip_max, tp.clip_max, 12);
+    if (lod) *lod = tp.lod;
+    if (filter_linear) *filter_linear = tp.filter_linear;
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_trace_slab_keys(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width, uint32_t height,
+                                      void** keys_dev) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (!cam || !keys_dev) return fail(ctx, SDFGPU_ERR_INVALID, "NULL argument");
+    if (width == 0 || height == 0) return fail(ctx, SDFGPU_ERR_INVALID, "empty frame");
+    set_device(ctx);
+    int rc = ensure_frame(ctx, width, height, false, true);
+    if (rc != SDFGPU_OK) return rc;
+    TraceParams tp;
+    if ((rc = fill_trace_params(ctx, cam, width, height, true, &tp)) != SDFGPU_OK) return rc;
+    tp.keys = ctx->keys_dev;
+    CK(ctx, launch_trace(tp, 0, ctx->stream));
+    ctx->launches++;
+    *keys_dev = ctx->keys_dev;
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_keys_download(sdfgpu_ctx* ctx, const void* keys_dev, uint32_t width, uint32_t height,
+                                    uint8_t* rgba8, float* depth) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (!keys_dev) return fail(ctx, SDFGPU_ERR_INVALID, "keys_dev is NULL");
+    set_device(ctx);
+    const size_t n = (size_t)width * height;
+    if (n == 0 || n > 0xffffffffull) return fail(ctx, SDFGPU_ERR_INVALID, "bad frame size");
+    uint8_t* r_dev = nullptr;
+    float* d_dev = nullptr;
+    int rc = SDFGPU_OK;
+    cudaError_t e = cudaSuccess;
+    do {
+        if (rgba8 && (e = cudaMalloc(&r_dev, n * 4)) != cudaSuccess) break;
+        if (depth && (e = cudaMalloc(&d_dev, n * 4)) != cudaSuccess) break;
+        if ((e = launch_keys_unpack((const unsigned long long*)keys_dev, (uint32_t)n, r_dev, d_dev, ctx->stream)) != cudaSuccess) break;
+        ctx->launches++;
+        if (rgba8 && (e = cudaMemcpyAsync(rgba8, r_dev, n * 4, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) break;
+        if (depth && (e = cudaMemcpyAsync(depth, d_dev, n * 4, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) break;
+        e = cudaStreamSynchronize(ctx->stream);
+    } while (0);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        rc = fail(ctx, SDFGPU_ERR_CUDA, "keys download failed: %s", cudaGetErrorString(e));
+    }
+    (void)cudaFree(r_dev); (void)cudaFree(d_dev);
+    return rc;
+}
+
+// ------------------------------------------------------------------ stream
+
+SDFGPU_API int sdfgpu_sync(sdfgpu_ctx* ctx) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    set_device(ctx);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SDFGPU_OK;
+}
+
+SDFGPU_API void* sdfgpu_stream(sdfgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+SDFGPU_API uint64_t sdfgpu_launch_count(const sdfgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+SDFGPU_API int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (!key) return fail(ctx, SDFGPU_ERR_INVALID, "key is NULL");
+    if (!strcmp(key, "fill_voxels_per_thread")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8)
+            return fail(ctx, SDFGPU_ERR_INVALID, "fill_voxels_per_thread must be 0, 1, 2, 4 or 8");
+        ctx->opt_vpt = (int)value;
+    } else if (!strcmp(key, "fill_ctas_per_sm")) {
+        if (value < 0 || value > 32) return fail(ctx, SDFGPU_ERR_INVALID, "fill_ctas_per_sm out of range");
+        ctx->opt_ctas = (int)value;
+    } else if (!strcmp(key, "streaming_stores")) {
+        ctx->opt_streaming = value != 0;
+    } else if (!strcmp(key, "fill_halo")) {
+        ctx->opt_fill_halo = value != 0;
+    } else {
+        return fail(ctx, SDFGPU_ERR_INVALID, "unknown option '%s'", key);
+    }
+    return SDFGPU_OK;
+}

@@ -1,0 +1,317 @@
+// trace.cu -- the sphere tracer: material.frag main() + sdfRaycast
+// (/root/reference/src/app/scene/sdf/material.frag:92-182), one ray per thread.
+//
+// The rasterised bounding cube that produces the fragments in the reference
+// (src/app/scene/sdf/mod.rs:254-282, Cull::None material.rs:75-81) is replaced
+// by a ray / AABB slab test per pixel.  The two RGBA32F volumes are read as
+// linear [f32;4] arrays (x fastest) through the read-only L1/TEX path
+// (ld.global.nc); filtering is point fetch + exact fp32 trilinear with GL
+// texel-centre addressing and MIRRORED_REPEAT (scene/sdf/mod.rs:113-115) --
+// hardware LINEAR filtering has ~8-bit weights and cannot meet 1e-5.  While
+// marching only the distance lane (.r, 4 B) of each texel is fetched; the full
+// texel is fetched once at the hit.
+//
+// A warp owns an 8 x 4 pixel tile so neighbouring rays share texels; finished
+// lanes drop out and the warp leaves the loop as soon as its ballot is empty.
+//
+// Compiled with -fmad=false -prec-div=true -prec-sqrt=true (GLSL highp f32
+// without contraction is what the oracle restates).
+#include "sdfgpu_internal.h"
+
+namespace sdfgpu {
+namespace {
+
+struct Vol {
+    const float4* tex;
+    int W, H, D, z_lo, z_hi;
+};
+
+// GL MIRRORED_REPEAT on an integer texel index
+__device__ __forceinline__ int mirror_idx(int i, int n) {
+    if ((unsigned)i < (unsigned)n) return i;
+    int m = i % (2 * n);
+    if (m < 0) m += 2 * n;
+    return m < n ? m : 2 * n - 1 - m;
+}
+
+__device__ __forceinline__ size_t texel_index(const Vol& v, int x, int y, int z) {
+    x = mirror_idx(x, v.W); y = mirror_idx(y, v.H); z = mirror_idx(z, v.D);
+    z = max(z, v.z_lo); z = min(z, v.z_hi - 1);  // slab storage: taps stay within the halo
+    return ((size_t)(z - v.z_lo) * v.H + (size_t)y) * v.W + (size_t)x;
+}
+
+__device__ __forceinline__ float lerp1(float a, float b, float f) { return a + f * (b - a); }
+
+struct Taps {
+    size_t i000, i100, i010, i110, i001, i101, i011, i111;
+    float fx, fy, fz;
+};
+
+// texture(sampler3D, p01) with GL_LINEAR: texel centres at (i + 0.5) / N
+__device__ __forceinline__ Taps linear_taps(const Vol& v, float ax, float ay, float az) {
+    const float ux = ax * (float)v.W - 0.5f, uy = ay * (float)v.H - 0.5f, uz = az * (float)v.D - 0.5f;
+    const float fx0 = floorf(ux), fy0 = floorf(uy), fz0 = floorf(uz);
+    Taps t;
+    t.fx = ux - fx0; t.fy = uy - fy0; t.fz = uz - fz0;
+    const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
+    const int xa = mirror_idx(x0, v.W), xb = mirror_idx(x0 + 1, v.W);
+    const int ya = mirror_idx(y0, v.H), yb = mirror_idx(y0 + 1, v.H);
+    int za = mirror_idx(z0, v.D), zb = mirror_idx(z0 + 1, v.D);
+    za = min(max(za, v.z_lo), v.z_hi - 1) - v.z_lo;
+    zb = min(max(zb, v.z_lo), v.z_hi - 1) - v.z_lo;
+    const size_t ra = ((size_t)za * v.H + ya) * v.W, rb = ((size_t)za * v.H + yb) * v.W;
+    const size_t rc = ((size_t)zb * v.H + ya) * v.W, rd = ((size_t)zb * v.H + yb) * v.W;
+    t.i000 = ra + xa; t.i100 = ra + xb; t.i010 = rb + xa; t.i110 = rb + xb;
+    t.i001 = rc + xa; t.i101 = rc + xb; t.i011 = rd + xa; t.i111 = rd + xb;
+    return t;
+}
+
+__device__ __forceinline__ float trilerp(float c000, float c100, float c010, float c110, float c001, float c101,
+                                         float c011, float c111, float fx, float fy, float fz) {
+    const float a = lerp1(c000, c100, fx), b = lerp1(c010, c110, fx);
+    const float e = lerp1(c001, c101, fx), f = lerp1(c011, c111, fx);
+    return lerp1(lerp1(a, b, fy), lerp1(e, f, fy), fz);
+}
+
+__device__ __forceinline__ float ldx(const float4* t, size_t i) { return __ldg(reinterpret_cast<const float*>(t + i)); }
+
+// sdfSampleRawInterp / sdfSampleRawNearest (material.frag:27-53): while loading (lod != 1) the
+// coordinate is first rounded to the lod lattice (:33-34); the fetch then uses whatever GL filter
+// the texture currently has (NEAREST until the first commit at lod == 1, LINEAR afterwards).
+template <bool SNAP>
+__device__ __forceinline__ void tex_coord(const TraceParams& P, const Vol& v, float px, float py, float pz, float& ax,
+                                          float& ay, float& az) {
+    ax = (px - P.bmin[0]) / (P.bmax[0] - P.bmin[0]);  // :30, :44
+    ay = (py - P.bmin[1]) / (P.bmax[1] - P.bmin[1]);
+    az = (pz - P.bmin[2]) / (P.bmax[2] - P.bmin[2]);
+    if (SNAP) {
+        const float rx = (float)v.W / P.lod, ry = (float)v.H / P.lod, rz = (float)v.D / P.lod;  // :33
+        ax = floorf(ax * rx + 0.5f) / rx; ay = floorf(ay * ry + 0.5f) / ry; az = floorf(az * rz + 0.5f) / rz;  // :34
+    }
+}
+
+// distance lane only
+template <bool SNAP, bool LINEAR>
+__device__ __forceinline__ float sample_dist(const TraceParams& P, const Vol& v, float px, float py, float pz) {
+    float ax, ay, az;
+    tex_coord<SNAP>(P, v, px, py, pz, ax, ay, az);
+    if (LINEAR) {
+        const Taps t = linear_taps(v, ax, ay, az);
+        return trilerp(ldx(v.tex, t.i000), ldx(v.tex, t.i100), ldx(v.tex, t.i010), ldx(v.tex, t.i110),
+                       ldx(v.tex, t.i001), ldx(v.tex, t.i101), ldx(v.tex, t.i011), ldx(v.tex, t.i111), t.fx, t.fy,
+                       t.fz);
+    } else {  // GL_NEAREST: texel floor(p01 * N)
+        const int x = (int)floorf(ax * (float)v.W), y = (int)floorf(ay * (float)v.H), z = (int)floorf(az * (float)v.D);
+        return ldx(v.tex, texel_index(v, x, y, z));
+    }
+}
+
+template <bool SNAP, bool LINEAR>
+__device__ __forceinline__ float4 sample_full(const TraceParams& P, const Vol& v, float px, float py, float pz) {
+    float ax, ay, az;
+    tex_coord<SNAP>(P, v, px, py, pz, ax, ay, az);
+    if (LINEAR) {
+        const Taps t = linear_taps(v, ax, ay, az);
+        const float4 c000 = __ldg(v.tex + t.i000), c100 = __ldg(v.tex + t.i100), c010 = __ldg(v.tex + t.i010),
+                     c110 = __ldg(v.tex + t.i110), c001 = __ldg(v.tex + t.i001), c101 = __ldg(v.tex + t.i101),
+                     c011 = __ldg(v.tex + t.i011), c111 = __ldg(v.tex + t.i111);
+        float4 r;
+        r.x = trilerp(c000.x, c100.x, c010.x, c110.x, c001.x, c101.x, c011.x, c111.x, t.fx, t.fy, t.fz);
+        r.y = trilerp(c000.y, c100.y, c010.y, c110.y, c001.y, c101.y, c011.y, c111.y, t.fx, t.fy, t.fz);
+        r.z = trilerp(c000.z, c100.z, c010.z, c110.z, c001.z, c101.z, c011.z, c111.z, t.fx, t.fy, t.fz);
+        r.w = trilerp(c000.w, c100.w, c010.w, c110.w, c001.w, c101.w, c011.w, c111.w, t.fx, t.fy, t.fz);
+        return r;
+    } else {
+        const int x = (int)floorf(ax * (float)v.W), y = (int)floorf(ay * (float)v.H), z = (int)floorf(az * (float)v.D);
+        return __ldg(v.tex + texel_index(v, x, y, z));
+    }
+}
+
+// sdfOutOfBoundsDist, material.frag:83-88
+__device__ __forceinline__ float oob_dist(const float* bmin, const float* bmax, float x, float y, float z) {
+    const float ox = fmaxf(bmin[0] - x, x - bmax[0]);
+    const float oy = fmaxf(bmin[1] - y, y - bmax[1]);
+    const float oz = fmaxf(bmin[2] - z, z - bmax[2]);
+    return fmaxf(ox, fmaxf(oy, oz));
+}
+
+// three-d ToneMapping / ColorMapping shader chunks (material.rs:37-38); see the oracle header
+__device__ __forceinline__ float tone_mapping(uint32_t type, float c) {
+    if (type == 1u) {
+        c = c / (c + 1.0f);
+    } else if (type == 2u) {
+        c = c * (2.51f * c + 0.03f) / (c * (2.43f * c + 0.59f) + 0.14f);
+    } else if (type == 3u) {
+        c = fmaxf(0.0f, c - 0.004f);
+        c = (c * (6.2f * c + 0.5f)) / (c * (6.2f * c + 1.7f) + 0.06f);
+        c = powf(c, 2.2f);
+    } else {
+        return c;
+    }
+    return fminf(fmaxf(c, 0.0f), 1.0f);
+}
+__device__ __forceinline__ float color_mapping(uint32_t type, float c) {
+    if (type == 1u) {
+        const float lo = c * 12.92f;
+        const float hi = 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+        return (c < 0.0031308f) ? lo : hi;
+    }
+    return c;
+}
+
+__device__ __forceinline__ unsigned long long pack_key(float depth, float r, float g, float b, float a) {
+    const uint32_t R = min(__float2uint_rn(fminf(fmaxf(r, 0.f), 1.f) * 255.0f), 255u);
+    const uint32_t G = min(__float2uint_rn(fminf(fmaxf(g, 0.f), 1.f) * 255.0f), 255u);
+    const uint32_t B = min(__float2uint_rn(fminf(fmaxf(b, 0.f), 1.f) * 255.0f), 255u);
+    const uint32_t A = min(__float2uint_rn(fminf(fmaxf(a, 0.f), 1.f) * 255.0f), 255u);
+    const uint32_t rgba = R | (G << 8) | (B << 16) | (A << 24);
+    const float dc = fminf(fmaxf(depth, 0.0f), 1.0f);
+    return ((unsigned long long)__float_as_uint(dc) << 32) | rgba;
+}
+
+template <bool SNAP, bool LINEAR>
+__global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceParams P) {
+    // 8 warps per CTA, each an 8 x 4 pixel tile; CTA tile = 32 x 8 pixels
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * 32u + (warp & 3) * 8u + (lane & 7);
+    const uint32_t j = blockIdx.y * 8u + (warp >> 2) * 4u + (lane >> 3);
+    if (i >= P.width || j >= P.height) return;
+    const size_t px = (size_t)j * P.width + i;
+
+    const Vol v0{P.tex0, (int)P.W, (int)P.H, (int)P.D, (int)P.z_lo, (int)P.z_hi};
+    const Vol v1{P.tex1, (int)P.W, (int)P.H, (int)P.D, (int)P.z_lo, (int)P.z_hi};
+
+    float g[SDFGPU_GBUF_FLOATS];
+#pragma unroll
+    for (int k = 0; k < SDFGPU_GBUF_FLOATS; ++k) g[k] = 0.0f;
+    float code;
+    float hx = 0.f, hy = 0.f, hz = 0.f;
+    int steps = 0;
+    float s0x = 0.f;
+    bool hit = false;
+    float rdx = 0.f, rdy = 0.f, rdz = 0.f;
+
+    const float fx = (float)i + 0.5f, fy = (float)j + 0.5f;
+    const float camx = P.origin[0], camy = P.origin[1], camz = P.origin[2];
+    const float dux = (P.base[0] + P.dx[0] * fx) + P.dy[0] * fy;
+    const float duy = (P.base[1] + P.dx[1] * fx) + P.dy[1] * fy;
+    const float duz = (P.base[2] + P.dx[2] * fx) + P.dy[2] * fy;
+    // fragment coverage: ray / AABB slab test
+    const float ix = 1.0f / dux, iy = 1.0f / duy, iz = 1.0f / duz;
+    const float t1x = (P.clip_min[0] - camx) * ix, t2x = (P.clip_max[0] - camx) * ix;
+    const float t1y = (P.clip_min[1] - camy) * iy, t2y = (P.clip_max[1] - camy) * iy;
+    const float t1z = (P.clip_min[2] - camz) * iz, t2z = (P.clip_max[2] - camz) * iz;
+    const float tmin = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
+    const float tmax = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
+    if (!(tmax >= fmaxf(tmin, 0.0f))) {
+        code = -3.0f;
+    } else {
+        const float tf = (tmin < 0.0f) ? tmax : tmin;
+        const float posx = camx + dux * tf, posy = camy + duy * tf, posz = camz + duz * tf;
+        // material.frag:133-139
+        rdx = posx - camx; rdy = posy - camy; rdz = posz - camz;
+        const float inv = 1.0f / sqrtf(rdx * rdx + rdy * rdy + rdz * rdz);
+        rdx *= inv; rdy *= inv; rdz *= inv;
+        float rox = posx, roy = posy, roz = posz;
+        if (oob_dist(P.clip_min, P.clip_max, rox + rdx * 0.2f, roy + rdy * 0.2f, roz + rdz * 0.2f) > 0.0f) {
+            rox = camx + rdx * 0.2f; roy = camy + rdy * 0.2f; roz = camz + rdz * 0.2f;
+        }
+        // sdfRaycast, material.frag:92-128, maxSteps = 256 (:142)
+        float t = 0.0f;
+        hx = rox; hy = roy; hz = roz;
+        code = -1.0f;
+        for (int it = 0; it < 256; ++it) {
+            steps = it;
+            if (it >= 255) { code = -1.0f; break; }                                          // :99-102
+            if (oob_dist(P.clip_min, P.clip_max, hx, hy, hz) > 1e-4f) { code = -2.0f; break; }  // :106-109
+            s0x = sample_dist<SNAP, LINEAR>(P, v0, hx, hy, hz);                                    // :112
+            const float dist = s0x - 1e-1f;                                                  // :59
+            if (dist < 1e-5f) { code = t; hit = true; break; }                               // :117-121
+            t += dist;                                                                       // :124
+            hx += rdx * dist; hy += rdy * dist; hz += rdz * dist;                            // :125
+        }
+    }
+
+    g[0] = hx; g[1] = hy; g[2] = hz; g[3] = code; g[15] = (float)steps;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    float depth = 1.0f;
+    if (hit) {
+        const float4 s0 = sample_full<SNAP, LINEAR>(P, v0, hx, hy, hz);
+        const float4 s1 = sample_full<SNAP, LINEAR>(P, v1, hx, hy, hz);  // :154
+        g[4] = s0.x; g[5] = s0.y; g[6] = s0.z; g[7] = s0.w;
+        g[8] = s1.x; g[9] = s1.y; g[10] = s1.z; g[11] = s1.w;
+        if (P.gbuf) {  // sdfNormal, :73-80 (dead for the ambient-only light set, kept for the G-buffer)
+            const float lx = (float)P.W / P.lod, ly = (float)P.H / P.lod, lz = (float)P.D / P.lod;
+            const float h = 1.0f / sqrtf(lx * lx + ly * ly + lz * lz);
+            const float kx[4] = {1.f, -1.f, -1.f, 1.f}, ky[4] = {-1.f, -1.f, 1.f, 1.f}, kz[4] = {-1.f, 1.f, -1.f, 1.f};
+            float nx = 0.f, ny = 0.f, nz = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float dq = sample_dist<SNAP, LINEAR>(P, v0, hx + kx[q] * h, hy + ky[q] * h, hz + kz[q] * h) - 1e-1f;
+                nx += kx[q] * dq; ny += ky[q] * dq; nz += kz[q] * dq;
+            }
+            const float ninv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+            g[12] = nx * ninv; g[13] = ny * ninv; g[14] = nz * ninv;
+        }
+        // :158-173
+        const float al[3] = {s0.y * P.tint[0], s0.z * P.tint[1], s0.w * P.tint[2]};
+        float col[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            // calculate_lighting with one ambient light: occlusion * ambient * mix(albedo, 0, metallic)
+            const float mixv = al[c] * (1.0f - s1.x) + 0.0f * s1.x;
+            float x = 0.0f + (s1.z * P.ambient[c]) * mixv;
+            x = tone_mapping(P.tone_mapping, x);
+            x = color_mapping(P.color_mapping, x);
+            if (P.gamma != 0.0f) x = powf(x, P.gamma);
+            col[c] = x;
+        }
+        out = make_float4(col[0], col[1], col[2], P.tint[3]);
+        // :180-181
+        const float* m = P.bvp;
+        const float z = ((m[2] * hx + m[6] * hy) + m[10] * hz) + m[14];
+        const float w = ((m[3] * hx + m[7] * hy) + m[11] * hz) + m[15];
+        depth = z / w;
+    }
+    if (P.rgba) P.rgba[px] = out;
+    if (P.depth) P.depth[px] = depth;
+    if (P.gbuf) {
+        float4* gp = reinterpret_cast<float4*>(P.gbuf + px * SDFGPU_GBUF_FLOATS);
+        gp[0] = make_float4(g[0], g[1], g[2], g[3]);
+        gp[1] = make_float4(g[4], g[5], g[6], g[7]);
+        gp[2] = make_float4(g[8], g[9], g[10], g[11]);
+        gp[3] = make_float4(g[12], g[13], g[14], g[15]);
+    }
+    if (P.keys) P.keys[px] = pack_key(depth, out.x, out.y, out.z, out.w);
+}
+
+__global__ void keys_unpack_kernel(const unsigned long long* __restrict__ keys, uint32_t n, uint8_t* __restrict__ rgba8,
+                                   float* __restrict__ depth) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = keys[i];
+    if (rgba8) reinterpret_cast<uint32_t*>(rgba8)[i] = (uint32_t)(k & 0xffffffffull);
+    if (depth) depth[i] = __uint_as_float((uint32_t)(k >> 32));
+}
+
+}  // namespace
+
+cudaError_t launch_trace(const TraceParams& p, int /*variant*/, cudaStream_t s) {
+    if (p.width == 0 || p.height == 0) return cudaSuccess;
+    const dim3 grid((p.width + 31) / 32, (p.height + 7) / 8);
+    const bool snap = p.lod != 1.0f, lin = p.filter_linear != 0;
+    if (!snap && lin) trace_kernel<false, true><<<grid, 256, 0, s>>>(p);
+    else if (!snap && !lin) trace_kernel<false, false><<<grid, 256, 0, s>>>(p);
+    else if (snap && lin) trace_kernel<true, true><<<grid, 256, 0, s>>>(p);
+    else trace_kernel<true, false><<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_keys_unpack(const unsigned long long* keys, uint32_t n, uint8_t* rgba8, float* depth,
+                               cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    keys_unpack_kernel<<<(n + 255) / 256, 256, 0, s>>>(keys, n, rgba8, depth);
+    return cudaGetLastError();
+}
+
+}  // namespace sdfgpu

@@ -1,0 +1,146 @@
+"""Z-slab sharding of the grid across GPUs, one process per GPU (torch.distributed / NCCL).
+
+The fill is a pure map over voxels (`sample` depends only on the position,
+/root/reference/src/sdf/mod.rs:43), and the flat index is z-major
+(src/app/scene/sdf/mod.rs:177), so rank g owns the contiguous slices
+[g*D/G, (g+1)*D/G) and no collective is needed to fill them.  The one exchange step is the
+halo: the trilinear / normal taps of the tracer at a slab face read one slice of the neighbour,
+so after a fill each rank sends its first and last owned slice (both textures) to its
+neighbours with NCCL send/recv over NVLink.  The trace is sort-last: every rank traces its own
+sub-box into 64-bit (depth, RGBA8) keys and an all-reduce(MIN) composites the frame.
+
+`torch` is used for the process group, streams and as a view on the library's device memory.
+"""
+import numpy as np
+
+from .viewer import SDFViewer
+
+
+def slab_range(depth, rank, world):
+    """Owned z slices of `rank`: contiguous, balanced, covering [0, depth)."""
+    return (rank * depth) // world, ((rank + 1) * depth) // world
+
+
+def stored_range(depth, z_begin, z_end):
+    """Stored slices = owned slices plus one halo slice on each interior face (include/sdfgpu.h)."""
+    if z_begin == z_end:
+        return z_begin, z_end
+    return max(z_begin - 1, 0), min(z_end + 1, depth)
+
+
+def halo_plan(depth, rank, world):
+    """The send/recv list of one rank: (kind, peer, z) with kind in {"send", "recv"}; z is the global
+    slice index moved.  Ranks with empty slabs take no part; neighbours are the nearest non-empty ranks."""
+    zb, ze = slab_range(depth, rank, world)
+    if zb == ze:
+        return []
+    ops = []
+    lo = rank - 1
+    while lo >= 0 and slab_range(depth, lo, world)[0] == slab_range(depth, lo, world)[1]:
+        lo -= 1
+    hi = rank + 1
+    while hi < world and slab_range(depth, hi, world)[0] == slab_range(depth, hi, world)[1]:
+        hi += 1
+    if lo >= 0:
+        ops += [("send", lo, zb), ("recv", lo, zb - 1)]
+    if hi < world:
+        ops += [("send", hi, ze - 1), ("recv", hi, ze)]
+    return ops
+
+
+def exchange_halos(dist, textures, dims, rank, world, group=None):
+    """Exchange the boundary slices of every tensor in `textures` (each a flat float32 tensor holding
+    the stored slices [z_lo, z_hi) of a W*H*4-float-per-slice volume).  Device agnostic (NCCL on GPU,
+    gloo in the CPU tests)."""
+    W, H, D = dims
+    zb, ze = slab_range(D, rank, world)
+    z_lo, _ = stored_range(D, zb, ze)
+    n = W * H * 4
+    ops = []
+    for kind, peer, z in halo_plan(D, rank, world):
+        for t in textures:
+            view = t[(z - z_lo) * n:(z - z_lo + 1) * n]
+            ops.append(dist.P2POp(dist.isend if kind == "send" else dist.irecv, view, peer, group))
+    if not ops:
+        return 0
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    return len(ops)
+
+
+class _DevMem:
+    """A __cuda_array_interface__ view of library-owned device memory."""
+
+    def __init__(self, ptr, n_items, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n_items),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class ShardedViewer:
+    """One rank's part of a Z-sharded SDFViewer.  With world == 1 it is a plain SDFViewer."""
+
+    def __init__(self, dims, bb, loading_passes, rank=0, world=1, device=0, group=None):
+        self.dims, self.bb, self.rank, self.world, self.device = tuple(dims), bb, rank, world, device
+        self.dist = group  # the torch.distributed module (None when world == 1)
+        if world > 1:
+            zr = slab_range(dims[2], rank, world)
+            self.viewer = SDFViewer.new_voxels(dims, bb, loading_passes, device=device, z_range=zr)
+            self.viewer.set_option("fill_halo", 0)
+            import torch
+            self._torch = torch
+            self._stream = torch.cuda.ExternalStream(self.viewer.stream, device=torch.device("cuda", device))
+            p0, p1 = self.viewer.device_ptrs()
+            n = dims[0] * dims[1] * (self.viewer.z_hi - self.viewer.z_lo) * 4
+            self._tex = [torch.as_tensor(_DevMem(p, n, "<f4"), device=torch.device("cuda", device)) for p in (p0, p1)]
+        else:
+            self.viewer = SDFViewer.new_voxels(dims, bb, loading_passes, device=device)
+
+    def close(self):
+        self.viewer.close()
+
+    def _exchange(self):
+        if self.world > 1:
+            with self._torch.cuda.stream(self._stream):  # NCCL orders itself after / before this stream
+                exchange_halos(self.dist, self._tex, self.dims, self.rank, self.world)
+
+    def fill_all(self):
+        self.viewer.fill_all()
+        self._exchange()
+
+    def update(self, sdf, max_passes=0):
+        it = self.viewer.update(sdf, max_passes)
+        self._exchange()
+        return it
+
+    def commit(self):
+        self.viewer.commit()
+
+    def _composite(self, cam, width, height):
+        t = self._torch
+        keys = self.viewer.trace_slab_keys(cam, width, height)
+        kt = t.as_tensor(_DevMem(keys, width * height, "<i8"), device=t.device("cuda", self.device))
+        with t.cuda.stream(self._stream):
+            self.dist.all_reduce(kt, op=self.dist.ReduceOp.MIN)  # keys are < 2^62: signed MIN == unsigned MIN
+        return keys
+
+    def trace_device(self, cam, width, height):
+        if self.world == 1:
+            return self.viewer.trace_device(cam, width, height)
+        return self._composite(cam, width, height)
+
+    def trace_host(self, cam, width, height, rgba_out=None, depth_out=None):
+        """Frame to host memory.  One GPU: RGBA32F + depth (the shader's outputs).  Sharded: the
+        composited RGBA8 + depth (what the keys carry); returned on every rank."""
+        if self.world == 1:
+            out = {}
+            if rgba_out is not None:
+                out["rgba"] = rgba_out
+            if depth_out is not None:
+                out["depth"] = depth_out
+            r, d, _ = self.viewer.trace(cam, width, height, out=out)
+            return r, d
+        keys = self._composite(cam, width, height)
+        rgba8, depth = self.viewer.keys_download(keys, width, height)
+        if depth_out is not None:
+            np.copyto(depth_out, depth)
+        return rgba8, depth

@@ -1,0 +1,118 @@
+"""Builders for the SDF instruction tape (include/sdfgpu_tape.h).
+
+The reference has no op tree -- an SDF is an opaque `SDFSurface::sample(p)`
+callback (/root/reference/src/sdf/mod.rs:33-43) -- so the tape is this build's
+GPU-side stand-in for it.  `demo_tape` is the hand lowering of the reference's
+built-in `SDFDemo` (src/sdf/demo/mod.rs:51-75, cube.rs:79-89, sphere.rs:37-47).
+"""
+import struct
+
+import numpy as np
+
+SDFT_MAGIC = 0x54464453
+SDFT_VERSION = 1
+SDFT_MAX_STACK = 8
+
+SHAPE_SPHERE, SHAPE_BOX_LINF = 0, 1
+MAT_FLAT, MAT_BRICK, MAT_NORMAL = 0, 1, 2
+
+OP_END = 0
+OP_PRIM, OP_UNION_PRIM, OP_INTER_PRIM, OP_UNION_RANGE = 1, 2, 3, 4
+OP_PUSH, OP_POP_UNION, OP_POP_INTER, OP_POP_DEMO_DIFF = 8, 9, 10, 11
+OP_D_NEG, OP_D_ABS, OP_D_ADD, OP_D_MUL, OP_D_MAX, OP_D_MIN = 16, 17, 18, 19, 20, 21
+OP_M_SET = 24
+OP_P_RESET, OP_P_SUB, OP_P_MUL, OP_P_ABS = 32, 33, 34, 35
+
+INSTR_DTYPE = np.dtype([("op", "<u4"), ("a", "<u4"), ("b", "<u4"), ("imm", "<f4")])
+PRIM_DTYPE = np.dtype(
+    [("center", "<f4", 3), ("size", "<f4"), ("color", "<f4", 3), ("metallic", "<f4"), ("roughness", "<f4"),
+     ("occlusion", "<f4"), ("air_skip", "<f4"), ("kind", "<u4")]
+)
+assert INSTR_DTYPE.itemsize == 16 and PRIM_DTYPE.itemsize == 48
+
+
+class TapeBuilder:
+    """Accumulates instructions, primitives and constants; `build()` returns the tape bytes."""
+
+    def __init__(self):
+        self.instr = []
+        self.prims = []
+        self.consts = []
+
+    # -- tables
+    def prim(self, shape, center, size, material=MAT_FLAT, color=(0.0, 0.0, 0.0), metallic=0.0, roughness=0.0,
+             occlusion=0.0, air_skip=float("inf")):
+        self.prims.append((tuple(center), size, tuple(color), metallic, roughness, occlusion, air_skip,
+                           shape | (material << 8)))
+        return len(self.prims) - 1
+
+    def prims_from_array(self, arr):
+        """Append a PRIM_DTYPE array; returns the index of its first element."""
+        first = len(self.prims)
+        for r in np.asarray(arr, dtype=PRIM_DTYPE):
+            self.prims.append((tuple(r["center"]), r["size"], tuple(r["color"]), r["metallic"], r["roughness"],
+                               r["occlusion"], r["air_skip"], int(r["kind"])))
+        return first
+
+    def const(self, values):
+        first = len(self.consts)
+        self.consts.extend(float(v) for v in values)
+        return first
+
+    # -- instructions
+    def emit(self, op, a=0, b=0, imm=0.0):
+        self.instr.append((op, a, b, imm))
+        return self
+
+    def build(self):
+        ins = np.array(self.instr, dtype=INSTR_DTYPE) if self.instr else np.zeros(0, INSTR_DTYPE)
+        prims = np.array(self.prims, dtype=PRIM_DTYPE) if self.prims else np.zeros(0, PRIM_DTYPE)
+        consts = np.array(self.consts, dtype="<f4")
+        hdr = struct.pack("<8I", SDFT_MAGIC, SDFT_VERSION, len(ins), len(prims), len(consts), 0, 0, 0)
+        return hdr + ins.tobytes() + prims.tobytes() + consts.tobytes()
+
+
+def demo_tape(cube_half_side=0.95, cube_material=MAT_BRICK, sphere_radius=1.05, sphere_material=MAT_NORMAL,
+              max_distance_custom_material=0.05, disable_sphere=False):
+    """`SDFDemo` (src/sdf/demo/mod.rs:20-32 for the defaults) lowered to the tape."""
+    t = TapeBuilder()
+    # "the air has no texture": material skipped when the distance exceeds 0.1 (cube.rs:83, sphere.rs:41)
+    box = t.prim(SHAPE_BOX_LINF, (0.0, 0.0, 0.0), cube_half_side, cube_material, air_skip=0.1)
+    t.emit(OP_PRIM, box)
+    if not disable_sphere:  # demo/mod.rs:54-55
+        sph = t.prim(SHAPE_SPHERE, (0.0, 0.0, 0.0), sphere_radius, sphere_material, air_skip=0.1)
+        # seam threshold, then the forced seam material of demo/mod.rs:66-69
+        c = t.const([max_distance_custom_material, 0.5, 0.6, 0.7, 0.5, 0.0, 0.0])
+        t.emit(OP_PUSH).emit(OP_PRIM, sph).emit(OP_POP_DEMO_DIFF, c)
+    t.emit(OP_END)
+    return t.build()
+
+
+def csg_primitive_table(n=1000, seed=1234):
+    """The CSG stress workload of BASELINE.json configs[2]: n random spheres /
+    L-inf boxes with flat materials.  Deterministic; the same table feeds the oracle and the kernel."""
+    rng = np.random.default_rng(seed)
+    arr = np.zeros(n, PRIM_DTYPE)
+    shape = (rng.random(n) < 0.5).astype(np.uint32)  # 1 = box
+    arr["center"] = rng.uniform(-0.8, 0.8, (n, 3)).astype(np.float32)
+    arr["size"] = rng.uniform(0.03, 0.12, n).astype(np.float32)
+    arr["color"] = rng.uniform(0.1, 1.0, (n, 3)).astype(np.float32)
+    arr["metallic"] = rng.uniform(0.0, 1.0, n).astype(np.float32)
+    arr["roughness"] = rng.uniform(0.0, 1.0, n).astype(np.float32)
+    arr["occlusion"] = 1.0
+    arr["air_skip"] = np.inf
+    arr["kind"] = shape | (MAT_FLAT << 8)
+    return arr
+
+
+def csg_tape(table=None, clip_radius=0.98):
+    """intersect(union(table[0..n)), sphere(0, clip_radius)); union / intersect carry the winning
+    child's whole sample, ties keep the first (include/sdfgpu_tape.h)."""
+    if table is None:
+        table = csg_primitive_table()
+    t = TapeBuilder()
+    first = t.prims_from_array(table)
+    clip = t.prim(SHAPE_SPHERE, (0.0, 0.0, 0.0), clip_radius, MAT_FLAT, color=(0.8, 0.8, 0.8), metallic=0.1,
+                  roughness=0.6, occlusion=1.0)
+    t.emit(OP_UNION_RANGE, first, len(table)).emit(OP_INTER_PRIM, clip).emit(OP_END)
+    return t.build()

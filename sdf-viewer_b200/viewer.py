@@ -1,0 +1,252 @@
+"""Host mirror of `SDFViewer` (/root/reference/src/app/scene/sdf/mod.rs:21-251) over the C ABI
+of include/sdfgpu.h: same constructor names, `update` / `commit`, `loading_mgr` fields read by the
+scene (`src/app/scene/mod.rs:149-153,229-239`), plus `trace`, which stands where the scene calls
+`volume.render(&camera, lights)` (`scene/mod.rs:213-215`) with `SDFViewerMaterial`.
+
+Everything here is a thin call into libsdfgpu.so; no arithmetic of the hot path happens in Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Camera, Rays, GBUF_FLOATS, SdfGpuError, check  # noqa: F401
+
+
+def _f6(bb):
+    flat = [float(v) for v in (list(bb[0]) + list(bb[1]) if len(bb) == 2 else list(bb))]
+    if len(flat) != 6:
+        raise ValueError("bounding box must be ((minx,miny,minz),(maxx,maxy,maxz)) or 6 floats")
+    return (C.c_float * 6)(*flat)
+
+
+def _host_ptr(arr):
+    return arr.ctypes.data_as(C.c_void_p) if arr is not None else None
+
+
+def dims_from_bb(bb, max_voxels_side):
+    """SDFViewer::from_bb's voxel-count rule (scene/sdf/mod.rs:47-68)."""
+    out = (C.c_uint32 * 3)()
+    check(_lib.load().sdfgpu_dims_from_bb(_f6(bb), int(max_voxels_side), out))
+    return tuple(out)
+
+
+def default_camera(width, height):
+    cam = Camera()
+    _lib.load().sdfgpu_camera_default(C.byref(cam), int(width), int(height))
+    return cam
+
+
+def look_at_camera(eye, target, width, height, up=(0.0, 1.0, 0.0), fovy_deg=45.0, z_near=0.1, z_far=1000.0):
+    """A camera like the scene's (scene/mod.rs:82-95) at another pose (CameraController output)."""
+    lib = _lib.load()
+    cam = default_camera(width, height)
+    e, t, u = ((C.c_float * 3)(*[float(x) for x in v]) for v in (eye, target, up))
+    cam.position[:] = list(e)
+    lib.sdfgpu_look_at_rh(e, t, u, cam.view)
+    lib.sdfgpu_perspective(C.c_float(np.float32(fovy_deg) * np.float32(np.pi) / np.float32(180.0)),
+                           C.c_float(float(width) / float(height)), z_near, z_far, cam.projection)
+    return cam
+
+
+def camera_rays(cam, width, height):
+    rays = Rays()
+    check(_lib.load().sdfgpu_camera_rays(C.byref(cam), int(width), int(height), C.byref(rays)))
+    return rays
+
+
+class _LoadingView:
+    """`viewer.loading_mgr` as the scene reads it (scene/mod.rs:153,229-239)."""
+
+    def __init__(self, viewer):
+        self._v = viewer
+
+    def _state(self):
+        ln, tot = C.c_uint64(), C.c_uint64()
+        left, passes = C.c_uint32(), C.c_uint32()
+        check(self._v._lib.sdfgpu_loading_state(self._v._h, C.byref(ln), C.byref(tot), C.byref(left), C.byref(passes)),
+              self._v._h)
+        return ln.value, tot.value, left.value, passes.value
+
+    def __len__(self):
+        return self._state()[0]
+
+    def total_iterations(self):
+        return self._state()[1]
+
+    def passes_left(self):
+        return self._state()[2]
+
+    @property
+    def passes(self):
+        return self._state()[3]
+
+    @property
+    def limits(self):
+        return self._v.dims
+
+
+class SDFViewer:
+    def __init__(self, handle, bounding_box):
+        self._lib = _lib.load()
+        self._h = handle
+        self.bounding_box = bounding_box
+        d = (C.c_uint32 * 3)()
+        check(self._lib.sdfgpu_dims(self._h, d), self._h)
+        self.dims = tuple(d)
+        zb, ze, zl, zh = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(self._lib.sdfgpu_slab(self._h, C.byref(zb), C.byref(ze), C.byref(zl), C.byref(zh)), self._h)
+        self.z_begin, self.z_end, self.z_lo, self.z_hi = zb.value, ze.value, zl.value, zh.value
+        self.loading_mgr = _LoadingView(self)
+        self._tape = None
+
+    # ---- constructors (scene/sdf/mod.rs:46-101)
+    @classmethod
+    def from_bb(cls, bb, max_voxels_side, loading_passes, device=0):
+        lib = _lib.load()
+        h = C.c_void_p()
+        check(lib.sdfgpu_create(_f6(bb), int(max_voxels_side), int(loading_passes), int(device), C.byref(h)))
+        return cls(h, bb)
+
+    @classmethod
+    def new_voxels(cls, voxels, bb, loading_passes, device=0, z_range=None):
+        lib = _lib.load()
+        h = C.c_void_p()
+        v = (C.c_uint32 * 3)(*[int(x) for x in voxels])
+        if z_range is None:
+            check(lib.sdfgpu_create_voxels(_f6(bb), v, int(loading_passes), int(device), C.byref(h)))
+        else:
+            check(lib.sdfgpu_create_slab(_f6(bb), v, int(loading_passes), int(device), int(z_range[0]),
+                                         int(z_range[1]), C.byref(h)))
+        return cls(h, bb)
+
+    def close(self):
+        if self._h:
+            self._lib.sdfgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- tex0.width/height/depth (scene/mod.rs:149-150)
+    @property
+    def width(self):
+        return self.dims[0]
+
+    @property
+    def height(self):
+        return self.dims[1]
+
+    @property
+    def depth(self):
+        return self.dims[2]
+
+    # ---- fill
+    def set_tape(self, tape_bytes):
+        buf = (C.c_char * len(tape_bytes)).from_buffer_copy(tape_bytes)
+        check(self._lib.sdfgpu_set_tape(self._h, buf, len(tape_bytes)), self._h)
+        self._tape = tape_bytes
+
+    def update(self, sdf, max_passes=0):
+        """SDFViewer::update (scene/sdf/mod.rs:128-217).  `sdf` is an `sdf.SDFSurface` (its tape is
+        re-sent when it reports a change) or None to keep the current tape.  `max_passes` replaces
+        `max_delta_time`: a LoadingManager pass is one kernel launch.  Returns the iterations done."""
+        changed = None
+        if sdf is not None:
+            changed = sdf.changed()
+            if self._tape is None or changed is not None:
+                self.set_tape(sdf.tape())
+        it = C.c_uint64()
+        box = _f6(changed) if changed is not None else None
+        check(self._lib.sdfgpu_update(self._h, box, int(max_passes), C.byref(it)), self._h)
+        return it.value
+
+    def fill_all(self):
+        check(self._lib.sdfgpu_fill_all(self._h), self._h)
+
+    def resample_box(self, box, count=False):
+        n = C.c_uint64()
+        check(self._lib.sdfgpu_resample_box(self._h, _f6(box), C.byref(n) if count else None), self._h)
+        return n.value if count else None
+
+    def commit(self):  # scene/sdf/mod.rs:220-239
+        check(self._lib.sdfgpu_commit(self._h), self._h)
+
+    def reset(self, loading_passes):
+        check(self._lib.sdfgpu_reset(self._h, int(loading_passes)), self._h)
+
+    def download(self, tex0=True, tex1=True, out0=None, out1=None):
+        """The CPU-side `Vec<[f32;4]>` volumes (scene/sdf/mod.rs:23-25) of this handle's own slices,
+        shaped (depth, height, width, 4)."""
+        shape = (self.z_end - self.z_begin, self.dims[1], self.dims[0], 4)
+        a0 = (out0 if out0 is not None else np.empty(shape, np.float32)) if tex0 else None
+        a1 = (out1 if out1 is not None else np.empty(shape, np.float32)) if tex1 else None
+        check(self._lib.sdfgpu_download(self._h, _host_ptr(a0), _host_ptr(a1)), self._h)
+        return a0, a1
+
+    def device_ptrs(self):
+        p0, p1 = C.c_void_p(), C.c_void_p()
+        check(self._lib.sdfgpu_device_ptrs(self._h, C.byref(p0), C.byref(p1)), self._h)
+        return p0.value, p1.value
+
+    # ---- trace
+    def trace(self, cam, width, height, rgba=True, depth=True, gbuf=False, out=None):
+        """material.frag main() per pixel; returns (rgba[h,w,4], depth[h,w], gbuf[h,w,16]); row 0 is
+        the bottom row (GL window coordinates).  `out` may hold preallocated (pinned) arrays."""
+        out = out or {}
+        r = out.get("rgba", np.empty((height, width, 4), np.float32)) if rgba else None
+        d = out.get("depth", np.empty((height, width), np.float32)) if depth else None
+        g = out.get("gbuf", np.empty((height, width, GBUF_FLOATS), np.float32)) if gbuf else None
+        check(self._lib.sdfgpu_trace(self._h, C.byref(cam), int(width), int(height), _host_ptr(r), _host_ptr(d),
+                                     _host_ptr(g)), self._h)
+        return r, d, g
+
+    def trace_device(self, cam, width, height, want_gbuf=False):
+        """Enqueue the trace; the frame stays in HBM.  Returns device pointers (rgba, depth, gbuf)."""
+        r, d, g = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(self._lib.sdfgpu_trace_device(self._h, C.byref(cam), int(width), int(height), int(want_gbuf),
+                                            C.byref(r), C.byref(d), C.byref(g)), self._h)
+        return r.value, d.value, g.value
+
+    def trace_params(self, cam, width, height, slab_clip=False):
+        cmin, cmax = (C.c_float * 3)(), (C.c_float * 3)()
+        lod, lin = C.c_float(), C.c_uint32()
+        check(self._lib.sdfgpu_trace_params(self._h, C.byref(cam), int(width), int(height), int(slab_clip), cmin, cmax,
+                                            C.byref(lod), C.byref(lin)), self._h)
+        return list(cmin), list(cmax), lod.value, lin.value
+
+    def trace_slab_keys(self, cam, width, height):
+        k = C.c_void_p()
+        check(self._lib.sdfgpu_trace_slab_keys(self._h, C.byref(cam), int(width), int(height), C.byref(k)), self._h)
+        return k.value
+
+    def keys_download(self, keys_dev, width, height):
+        rgba8 = np.empty((height, width, 4), np.uint8)
+        depth = np.empty((height, width), np.float32)
+        check(self._lib.sdfgpu_keys_download(self._h, C.c_void_p(keys_dev), int(width), int(height), _host_ptr(rgba8),
+                                             _host_ptr(depth)), self._h)
+        return rgba8, depth
+
+    # ---- stream
+    def sync(self):
+        check(self._lib.sdfgpu_sync(self._h), self._h)
+
+    @property
+    def stream(self):
+        return self._lib.sdfgpu_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return self._lib.sdfgpu_launch_count(self._h)
+
+    def set_option(self, key, value):
+        check(self._lib.sdfgpu_set_option(self._h, key.encode(), int(value)), self._h)

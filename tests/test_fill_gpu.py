@@ -1,0 +1,258 @@
+"""GPU parity of the grid fill: the CUDA path through the C ABI against the CPU oracle,
+bit for bit (f32 compared as u32), on the same tape / grid / bounding box.
+
+Reference semantics: SDFViewer::update, /root/reference/src/app/scene/sdf/mod.rs:128-217."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BB = ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_same_volume(got0, got1, want0, want1):
+    for name, g, w in (("tex0", got0, want0), ("tex1", got1, want1)):
+        gb, wb = bits(g), bits(w)
+        if not np.array_equal(gb, wb):
+            bad = np.argwhere(gb != wb)
+            z, y, x, c = bad[0]
+            raise AssertionError(
+                f"{name}: {len(bad)} of {gb.size} lanes differ; first at voxel ({x},{y},{z}) lane {c}: "
+                f"got {g[z, y, x, c]!r} want {w[z, y, x, c]!r}")
+
+
+def oracle_full(oracle, tape, dims, bb=BB, passes=2):
+    v = oracle.Viewer(bb, dims, passes)
+    s = oracle.Sampler(tape=tape)
+    v.update(s)  # until the LoadingManager is exhausted, reference visit order
+    return v
+
+
+@pytest.mark.parametrize("vpt", [1, 2, 4, 8])
+def test_demo_fill_all_64(S, oracle, vpt):
+    tape = S.tape.demo_tape()
+    with S.SDFViewer.from_bb(BB, 64, 2) as v:
+        assert v.dims == (64, 64, 64)
+        v.set_option("fill_voxels_per_thread", vpt)
+        v.set_tape(tape)
+        v.fill_all()
+        t0, t1 = v.download()
+        assert len(v.loading_mgr) == 0 and v.loading_mgr.passes_left() == 0
+    o = oracle_full(oracle, tape, (64, 64, 64))
+    assert_same_volume(t0, t1, o.tex0, o.tex1)
+    # SURVEY 8c known answers (demo defaults, N = 64)
+    assert t0[0, 0, 0, 0] == np.float32(0.1) + (np.float32(1.0) - np.float32(0.95))
+    assert tuple(t1[0, 0, 0]) == (np.float32(0.4), np.float32(0.5), np.float32(1.0), np.float32(oracle.lib().orc_air_dist()))
+    assert t0[32, 32, 32, 0] == np.float32(1.0)
+
+
+@pytest.mark.parametrize("dims", [(2, 2, 2), (8, 8, 8), (11, 11, 11), (8, 11, 17), (33, 7, 5), (70, 9, 3)])
+@pytest.mark.parametrize("passes", [1, 3])
+def test_demo_update_passes_ragged(S, oracle, dims, passes):
+    """Pass-by-pass: after every LoadingManager pass the volume equals the oracle's after the same
+    number of iterations (loading.rs pass structure), including untouched AIR_DIST voxels."""
+    tape = S.tape.demo_tape()
+    o = oracle.Viewer(BB, dims, passes)
+    s = oracle.Sampler(tape=tape)
+    with S.SDFViewer.new_voxels(dims, BB, passes) as v:
+        v.set_tape(tape)
+        for step in S.loading.pass_steps(passes):
+            n = S.loading.pass_items(dims, step)
+            assert v.update(None, max_passes=1) == n
+            assert o.update(s, max_iterations=n) == n
+            t0, t1 = v.download()
+            assert_same_volume(t0, t1, o.tex0, o.tex1)
+            assert len(v.loading_mgr) == o.len()
+            assert v.loading_mgr.total_iterations() == o.total_iterations()
+            assert v.loading_mgr.passes_left() == o.passes_left()
+        assert v.update(None) == 0 and o.update(s) == 0
+
+
+def test_demo_params_and_disable_sphere(S, oracle):
+    for kw in (dict(cube_half_side=0.8, sphere_radius=0.9), dict(disable_sphere=True),
+               dict(cube_material=S.tape.MAT_NORMAL, sphere_material=S.tape.MAT_BRICK),
+               dict(max_distance_custom_material=0.2)):
+        tape = S.tape.demo_tape(**kw)
+        with S.SDFViewer.from_bb(BB, 48, 2) as v:
+            v.set_tape(tape)
+            v.fill_all()
+            t0, t1 = v.download()
+        o = oracle_full(oracle, tape, (48, 48, 48))
+        assert_same_volume(t0, t1, o.tex0, o.tex1)
+
+
+def test_nonuniform_bbox(S, oracle):
+    bb = ((-0.3, -1.1, 0.2), (1.7, 0.4, 0.9))
+    dims = S.dims_from_bb(bb, 50)
+    import ctypes as C
+    od = (C.c_uint32 * 3)()
+    oracle.lib().orc_dims_from_bb(oracle._bb6(bb), 50, od)
+    assert dims == tuple(od)
+    tape = S.tape.demo_tape()
+    with S.SDFViewer.from_bb(bb, 50, 2) as v:
+        assert v.dims == dims
+        v.set_tape(tape)
+        assert v.update(None) == sum(S.loading.pass_items(dims, s) for s in S.loading.pass_steps(2))
+        t0, t1 = v.download()
+    o = oracle_full(oracle, tape, dims, bb=bb)
+    assert_same_volume(t0, t1, o.tex0, o.tex1)
+
+
+@pytest.mark.parametrize("n_prims,vpt", [(5, 2), (40, 1), (40, 4), (300, 8), (1000, 8)])
+def test_csg_tape(S, oracle, n_prims, vpt):
+    """UNION_RANGE with per-tile culling (>= 16 primitives) and without: identical to the oracle's
+    plain left-to-right fold."""
+    table = S.tape.csg_primitive_table(n_prims, seed=7 + n_prims)
+    tape = S.tape.csg_tape(table)
+    dims = (64, 64, 32) if n_prims >= 300 else (40, 36, 24)
+    with S.SDFViewer.new_voxels(dims, BB, 1) as v:
+        v.set_option("fill_voxels_per_thread", vpt)
+        v.set_tape(tape)
+        v.fill_all()
+        t0, t1 = v.download()
+    o = oracle.Viewer(BB, dims, 1)
+    o.fill_all(oracle.Sampler(tape=tape))
+    assert_same_volume(t0, t1, o.tex0, o.tex1)
+
+
+def test_generic_ops_tape(S, oracle):
+    """Every opcode of include/sdfgpu_tape.h at least once."""
+    T = S.tape
+    t = T.TapeBuilder()
+    a = t.prim(T.SHAPE_SPHERE, (0.2, 0.1, -0.3), 0.5, T.MAT_NORMAL, air_skip=0.3)
+    b = t.prim(T.SHAPE_BOX_LINF, (-0.2, 0.0, 0.1), 0.4, T.MAT_BRICK, air_skip=float("inf"))
+    c = t.prim(T.SHAPE_BOX_LINF, (0.0, 0.0, 0.0), 0.9, T.MAT_FLAT, color=(0.2, 0.9, 0.1), metallic=0.3,
+               roughness=0.7, occlusion=0.5)
+    d = t.prim(T.SHAPE_SPHERE, (0.5, 0.5, 0.5), 0.3, T.MAT_FLAT, color=(1.5, -0.2, 0.0), occlusion=-1.0)
+    k0 = t.const([0.1, -0.05, 0.02])
+    k1 = t.const([0.9, 0.8, 0.7, 0.6, 0.5, 0.4])
+    (t.emit(T.OP_PRIM, a).emit(T.OP_UNION_PRIM, b).emit(T.OP_PUSH)
+      .emit(T.OP_P_SUB, k0).emit(T.OP_P_MUL, imm=1.5).emit(T.OP_P_ABS, 5)
+      .emit(T.OP_PRIM, d).emit(T.OP_D_MUL, imm=0.5).emit(T.OP_D_ADD, imm=-0.01).emit(T.OP_POP_UNION)
+      .emit(T.OP_PUSH).emit(T.OP_P_RESET).emit(T.OP_PRIM, c).emit(T.OP_D_NEG).emit(T.OP_D_ABS)
+      .emit(T.OP_D_MAX, imm=-0.2).emit(T.OP_D_MIN, imm=0.7).emit(T.OP_POP_INTER)
+      .emit(T.OP_PUSH).emit(T.OP_UNION_RANGE, 0, 4).emit(T.OP_INTER_PRIM, c).emit(T.OP_M_SET, k1)
+      .emit(T.OP_POP_UNION).emit(T.OP_END))
+    tape = t.build()
+    dims = (37, 29, 13)
+    with S.SDFViewer.new_voxels(dims, BB, 1) as v:
+        v.set_tape(tape)
+        v.fill_all()
+        t0, t1 = v.download()
+    o = oracle.Viewer(BB, dims, 1)
+    o.fill_all(oracle.Sampler(tape=tape))
+    assert_same_volume(t0, t1, o.tex0, o.tex1)
+
+
+def test_changed_box_state_machine(S, oracle):
+    """sdf.changed() -> merged pending box -> 3-pass re-sample of the voxels inside it
+    (scene/sdf/mod.rs:131-154,184-190), while and after loading.  The GPU runs whole passes; the
+    oracle is then given the same number of iterations, so both stop at the same pass boundary."""
+    import ctypes as C
+    dims = (24, 20, 16)
+    sdf = S.SDFDemo()
+    o = oracle.Viewer(BB, dims, 2)
+    with S.SDFViewer.new_voxels(dims, BB, 2) as v:
+        def step(changed, tape, max_passes):
+            v.set_tape(tape)
+            it = C.c_uint64()
+            box = (C.c_float * 6)(*changed) if changed is not None else None
+            S.viewer.check(v._lib.sdfgpu_update(v._h, box, max_passes, C.byref(it)), v._h)
+            s = oracle.Sampler(tape=tape)
+            want = o.update(s, changed=changed, max_iterations=it.value if it.value else 1)
+            assert it.value == want
+            t0, t1 = v.download()
+            assert_same_volume(t0, t1, o.tex0, o.tex1)
+            assert len(v.loading_mgr) == o.len()
+            assert v.loading_mgr.passes_left() == o.passes_left()
+            return it.value
+
+        tapeA = sdf.tape()
+        assert step(None, tapeA, 1) == S.loading.pass_items(dims, 2)   # coarse pass of the initial load
+        boxA = (-0.5, -0.25, -1.0, 0.25, 0.5, 0.1)
+        sdf.set_parameter("sphere_radius", 0.9)
+        tapeB = sdf.tape()
+        assert step(boxA, tapeB, 1) > 0            # change reported while loading
+        assert step(None, tapeB, 0) > 0            # queued 3-pass re-sample (changed_box_while_loading)
+        assert step(None, tapeB, 0) > 0            # one more 3-pass round, then the box is dropped
+        assert step(None, tapeB, 0) == 0
+        boxB = (0.1, 0.1, 0.1, 0.9, 0.6, 0.7)
+        sdf.set_parameter("cube_half_side", 0.7)
+        tapeC = sdf.tape()
+        assert step(boxB, tapeC, 2) > 0            # change after loading: new 3-pass manager
+        assert step(boxA, tapeC, 0) > 0            # merged boxes
+        step(None, tapeC, 0)
+        step(None, tapeC, 0)
+        assert step(None, tapeC, 0) == 0
+        assert len(v.loading_mgr) == 0
+
+
+def test_resample_box(S, oracle):
+    """The dirty-block path: only voxels whose position lies in the closed box change."""
+    dims = (48, 40, 32)
+    tapeA, tapeB = S.tape.demo_tape(), S.tape.demo_tape(sphere_radius=0.8, cube_half_side=0.9)
+    box = (-0.4, -0.35, -0.6, 0.31, 0.55, 0.2)
+    with S.SDFViewer.new_voxels(dims, BB, 2) as v:
+        v.set_tape(tapeA)
+        v.fill_all()
+        v.set_tape(tapeB)
+        n = v.resample_box(box, count=True)
+        t0, t1 = v.download()
+    a = oracle.Viewer(BB, dims, 1); a.fill_all(oracle.Sampler(tape=tapeA))
+    b = oracle.Viewer(BB, dims, 1); b.fill_all(oracle.Sampler(tape=tapeB))
+    xs = np.array([a.voxel_pos(i, 0, 0)[0] for i in range(dims[0])], np.float32)
+    ys = np.array([a.voxel_pos(0, i, 0)[1] for i in range(dims[1])], np.float32)
+    zs = np.array([a.voxel_pos(0, 0, i)[2] for i in range(dims[2])], np.float32)
+    f = np.float32
+    inside = ((zs >= f(box[2])) & (zs <= f(box[5])))[:, None, None] & ((ys >= f(box[1])) & (ys <= f(box[4])))[None, :, None] \
+        & ((xs >= f(box[0])) & (xs <= f(box[3])))[None, None, :]
+    want0 = np.where(inside[..., None], b.tex0, a.tex0)
+    want1 = np.where(inside[..., None], b.tex1, a.tex1)
+    assert_same_volume(t0, t1, want0, want1)
+    assert n >= inside.sum()  # AIR_DIST-valued voxels inside the index box are re-sampled too
+
+
+def test_slab_handles_cover_grid(S, oracle):
+    """Z-slab handles (multi-GPU sharding unit) each produce exactly their slices of the full grid,
+    and locally computed halo slices equal the neighbour's owned slices bit for bit."""
+    dims = (32, 24, 20)
+    tape = S.tape.demo_tape()
+    o = oracle_full(oracle, tape, dims)
+    cuts = [0, 7, 8, 15, 20]
+    for zb, ze in zip(cuts[:-1], cuts[1:]):
+        with S.SDFViewer.new_voxels(dims, BB, 2, z_range=(zb, ze)) as v:
+            assert (v.z_begin, v.z_end) == (zb, ze)
+            assert v.z_lo == max(zb - 1, 0) and v.z_hi == min(ze + 1, dims[2])
+            v.set_tape(tape)
+            v.update(None)
+            t0, t1 = v.download()
+            assert_same_volume(t0, t1, o.tex0[zb:ze], o.tex1[zb:ze])
+
+
+def test_errors(S):
+    import ctypes as C
+    lib = S.viewer._lib.load()
+    with S.SDFViewer.from_bb(BB, 16, 2) as v:
+        with pytest.raises(S.SdfGpuError) as e:
+            v.fill_all()
+        assert e.value.code == -4  # SDFGPU_ERR_STATE: no tape
+        with pytest.raises(S.SdfGpuError) as e:
+            v.set_tape(b"\0" * 64)
+        assert e.value.code == -3
+        bad = bytearray(S.tape.demo_tape())
+        bad[32 + 4] = 99  # instr 0 operand a -> primitive out of range
+        with pytest.raises(S.SdfGpuError) as e:
+            v.set_tape(bytes(bad))
+        assert e.value.code == -3 and "out of range" in e.value.message
+        t = S.tape.TapeBuilder()
+        t.emit(S.tape.OP_POP_UNION)
+        with pytest.raises(S.SdfGpuError):
+            v.set_tape(t.build())
+        with pytest.raises(S.SdfGpuError):
+            v.set_option("nope", 1)
+    h = C.c_void_p()
+    assert lib.sdfgpu_create((C.c_float * 6)(-1, -1, -1, 1, 1, 1), 16, 2, 999, C.byref(h)) == -1

@@ -1,0 +1,159 @@
+"""GPU parity of the sphere tracer against the CPU oracle's restatement of material.frag
+(/root/reference/src/app/scene/sdf/material.frag:92-182).  Both sides trace the SAME volume
+(downloaded from the GPU fill) with the SAME ray parameters (sdfgpu_camera_rays).
+
+Tolerances (BASELINE.json north_star: 1e-5 relative): hit/miss class and step count exact;
+hit position, t, raw tex0/tex1 at the hit, depth: 1e-5 relative (in practice bit-equal, the
+arithmetic is unfused f32 on both sides); final RGBA: 1e-5 relative + 1e-6 absolute, because
+device powf and glibc powf differ in the last ulp."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BB = ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))
+RTOL = 1e-5
+
+
+def fill(S, tape, dims, passes=2, bb=BB, max_passes=0, commit=True):
+    v = S.SDFViewer.new_voxels(dims, bb, passes)
+    v.set_tape(tape)
+    v.update(None, max_passes=max_passes)
+    if commit:
+        v.commit()
+    return v
+
+
+def compare(S, oracle, v, cam, w, h, bb=BB, frac_exact=0.999):
+    rg, dg, gg = v.trace(cam, w, h, gbuf=True)
+    t0, t1 = v.download()
+    rays = S.camera_rays(cam, w, h)
+    cmin, cmax, lod, lin = v.trace_params(cam, w, h)
+    P = oracle.trace_params(rays, bb, v.dims, lod=lod, filter_linear=lin, tone_mapping=cam.tone_mapping,
+                            color_mapping=cam.color_mapping, gamma=cam.gamma, tint=list(cam.tint),
+                            ambient=list(cam.ambient))
+    ro, do, go = oracle.trace(P, t0, t1, w, h)
+    # classification and step counts are exact
+    assert np.array_equal(gg[..., 3] < 0, go[..., 3] < 0), "hit mask differs"
+    miss = go[..., 3] < 0
+    assert np.array_equal(gg[..., 3][miss], go[..., 3][miss]), "miss codes differ"
+    assert np.array_equal(gg[..., 15], go[..., 15]), "step counts differ"
+    hit = ~miss
+    assert hit.sum() > 0.05 * w * h, "camera does not see the SDF"
+    np.testing.assert_allclose(gg[hit], go[hit], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(dg, do, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(rg, ro, rtol=RTOL, atol=1e-6)
+    assert np.all(rg[miss] == 0) and np.all(dg[miss] == 1.0)
+    # in practice the G-buffer is bit-equal
+    same = (gg.view(np.uint32) == go.view(np.uint32)).all(axis=-1)
+    assert same.mean() >= frac_exact, f"only {same.mean():.4f} of G-buffer records bit-equal"
+    return hit.mean()
+
+
+def test_default_camera_640x480(S, oracle):
+    """BASELINE config 1: demo SDF, 64^3, 2 passes, 640x480, default scene camera."""
+    with fill(S, S.tape.demo_tape(), (64, 64, 64)) as v:
+        cmin, cmax, lod, lin = v.trace_params(S.default_camera(640, 480), 640, 480)
+        assert lod == 1.0 and lin == 1
+        cov = compare(S, oracle, v, S.default_camera(640, 480), 640, 480)
+        assert 0.05 < cov < 0.5
+
+
+@pytest.mark.parametrize("eye,target", [((0.9, 1.1, 1.8), (0, 0, 0)), ((0.2, 0.1, 0.3), (1, 0.2, -0.4)),
+                                        ((-3.0, 0.4, 0.2), (0, 0, 0)), ((0.0, 4.0, 0.01), (0, 0, 0))])
+def test_other_cameras(S, oracle, eye, target):
+    """Close-up, camera INSIDE the box (origin = camera + 0.2 dir, material.frag:136-139), axis views."""
+    w, h = 320, 200
+    with fill(S, S.tape.demo_tape(), (48, 48, 48)) as v:
+        compare(S, oracle, v, S.look_at_camera(eye, target, w, h), w, h)
+
+
+def test_while_loading_lod(S, oracle):
+    """After the coarse pass only (lod = 2^passes_left = 4 or 2): nearest-snapped sampling
+    (material.frag:27-36) under the NEAREST filter, then under LINEAR once a lod-1 commit happened."""
+    w, h = 320, 240
+    cam = S.default_camera(w, h)
+    v = S.SDFViewer.new_voxels((64, 64, 64), BB, 3)
+    with v:
+        v.set_tape(S.tape.demo_tape())
+        v.update(None, max_passes=1)
+        v.commit()
+        assert v.trace_params(cam, w, h)[2:] == (4.0, 0)
+        compare(S, oracle, v, cam, w, h)
+        v.update(None, max_passes=1)
+        v.commit()
+        assert v.trace_params(cam, w, h)[2:] == (2.0, 0)
+        compare(S, oracle, v, cam, w, h)
+        v.update(None)
+        v.commit()
+        assert v.trace_params(cam, w, h)[2:] == (1.0, 1)
+        compare(S, oracle, v, cam, w, h)
+        # a later change starts a 3-pass re-sample: lod 4 again, but the filter stays LINEAR
+        import ctypes as C
+        it = C.c_uint64()
+        S.viewer.check(v._lib.sdfgpu_update(v._h, (C.c_float * 6)(-1, -1, -1, 1, 1, 1), 1, C.byref(it)), v._h)
+        v.commit()
+        assert v.trace_params(cam, w, h)[2:] == (4.0, 1)
+        compare(S, oracle, v, cam, w, h)
+
+
+def test_uncommitted_nearest(S, oracle):
+    """Before any commit lod stays 1 and the GL filter is NEAREST (scene/sdf/mod.rs:110-111)."""
+    w, h = 256, 192
+    with fill(S, S.tape.demo_tape(), (40, 40, 40), commit=False) as v:
+        cam = S.default_camera(w, h)
+        assert v.trace_params(cam, w, h)[2:] == (1.0, 0)
+        compare(S, oracle, v, cam, w, h)
+
+
+def test_nonuniform_volume_and_tone_modes(S, oracle):
+    bb = ((-0.8, -1.0, -0.6), (1.0, 0.7, 0.9))
+    w, h = 200, 160
+    v = S.SDFViewer.from_bb(bb, 56, 2)
+    with v:
+        v.set_tape(S.tape.csg_tape(S.tape.csg_primitive_table(60, seed=3)))
+        v.fill_all()
+        v.commit()
+        for tone, cmap, gamma in ((2, 1, 0.0), (1, 0, 0.0), (3, 1, 2.2), (0, 0, 0.0)):
+            cam = S.look_at_camera((2.0, 1.5, 2.5), (0.1, -0.1, 0.1), w, h)
+            cam.tone_mapping, cam.color_mapping, cam.gamma = tone, cmap, gamma
+            cam.tint[:] = [0.9, 0.8, 1.0, 0.75]
+            compare(S, oracle, v, cam, w, h, bb=bb)
+
+
+def test_slab_keys_composite(S, oracle):
+    """Sort-last multi-GPU trace: per-slab key images, MIN-composited, equal the oracle's per-slab
+    traces composited the same way; and match the single-volume frame except within 2/255."""
+    dims = (48, 48, 48)
+    w, h = 240, 180
+    tape = S.tape.demo_tape()
+    cam = S.default_camera(w, h)
+    cuts = [0, 16, 32, 48]
+    keys = []
+    with fill(S, tape, dims) as full:
+        rg, dg, _ = full.trace(cam, w, h)
+        t0, t1 = full.download()
+    for zb, ze in zip(cuts[:-1], cuts[1:]):
+        with S.SDFViewer.new_voxels(dims, BB, 2, z_range=(zb, ze)) as v:
+            v.set_tape(tape)
+            v.update(None)
+            v.commit()
+            k = v.trace_slab_keys(cam, w, h)
+            rgba8, depth = v.keys_download(k, w, h)
+            cmin, cmax, lod, lin = v.trace_params(cam, w, h, slab_clip=True)
+            P = oracle.trace_params(S.camera_rays(cam, w, h), BB, dims, lod=lod, filter_linear=lin, z_lo=v.z_lo,
+                                    z_hi=v.z_hi, clip_min=cmin, clip_max=cmax)
+            ro, do, _ = oracle.trace(P, t0[v.z_lo:v.z_hi], t1[v.z_lo:v.z_hi], w, h, gbuf=False)
+            np.testing.assert_allclose(depth, np.clip(do, 0, 1), rtol=RTOL)
+            want8 = np.rint(np.clip(ro, 0, 1) * 255).astype(np.uint8)
+            assert np.abs(rgba8.astype(int) - want8.astype(int)).max() <= 1
+            keys.append((depth.view(np.uint32).astype(np.uint64) << np.uint64(32)) | rgba8.view(np.uint32)[..., 0])
+    comp = np.minimum.reduce(keys)
+    comp_depth = (comp >> np.uint64(32)).astype(np.uint32).view(np.float32)
+    comp_rgba = (comp & np.uint64(0xffffffff)).astype(np.uint32).view(np.uint8).reshape(h, w, 4)
+    # sort-last restarts rays at slab faces: same surface, hit point may differ slightly
+    full8 = np.rint(np.clip(rg, 0, 1) * 255).astype(np.uint8)
+    agree = (np.abs(comp_rgba.astype(int) - full8.astype(int)).max(axis=-1) <= 2)
+    assert agree.mean() > 0.98
+    hit = dg < 1
+    assert np.median(np.abs(comp_depth[hit] - dg[hit])) < 1e-4
