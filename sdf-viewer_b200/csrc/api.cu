@@ -459,7 +459,7 @@ SDFGPU_API int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_by
         ih.cull_first = cull_first; ih.cull_count = cull_count;
     }
     uint32_t off = sizeof(TapeImageHeader);
-    ih.off_instr = off; off += align16(h.n_instr * 16u);
+    ih.off_instr = off; off += (h.n_instr + 1u) * 16u;  // + a terminating DOP_END
     ih.off_geom = off; off += h.n_prims * 16u;
     ih.off_mat0 = off; off += h.n_prims * 16u;
     ih.off_mat1 = off; off += h.n_prims * 16u;
@@ -472,7 +472,52 @@ SDFGPU_API int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_by
         return fail(ctx, SDFGPU_ERR_TAPE, "tape image is %u bytes; the fill kernel stages at most 204800 in shared memory", off);
     std::vector<unsigned char> img(off, 0);
     memcpy(img.data(), &ih, sizeof ih);
-    if (h.n_instr) memcpy(img.data() + ih.off_instr, instr.data(), h.n_instr * 16u);
+    {   // lower to the device opcodes (sdfgpu_internal.h DeviceOp): primitive ops specialised by shape and
+        // material, stack ops by (static) depth.  Operand fields keep their meaning; `b` of the
+        // stack ops becomes the shared-memory level to spill / reload.
+        std::vector<sdft_instr> low(instr);
+        uint32_t depth = 0;
+        for (uint32_t pc = 0; pc < h.n_instr; ++pc) {
+            sdft_instr& I = low[pc];
+            bool end = false;
+            switch (instr[pc].op) {
+                case SDFT_OP_END: I.op = DOP_END; end = true; break;
+                case SDFT_OP_PRIM: case SDFT_OP_UNION_PRIM: case SDFT_OP_INTER_PRIM: {
+                    const uint32_t mode = instr[pc].op - SDFT_OP_PRIM;
+                    const uint32_t shape = prims[I.a].kind & 0xffu, mat = (prims[I.a].kind >> 8) & 0xffu;
+                    I.op = DOP_PRIM + mode * 6 + shape * 3 + mat;
+                    break;
+                }
+                case SDFT_OP_UNION_RANGE: I.op = DOP_UNION_RANGE; break;
+                case SDFT_OP_PUSH:
+                    if (depth == 0) { I.op = DOP_PUSH_REG; I.b = 0; }
+                    else { I.op = DOP_PUSH_MEM; I.b = depth - 1; }
+                    ++depth;
+                    break;
+                case SDFT_OP_POP_UNION: case SDFT_OP_POP_INTER: case SDFT_OP_POP_DEMO_DIFF: {
+                    const uint32_t kind = instr[pc].op - SDFT_OP_POP_UNION;
+                    --depth;
+                    if (depth == 0) { I.op = DOP_POP_UNION + kind; I.b = 0; }
+                    else { I.op = DOP_POP_UNION_MEM + kind; I.b = depth - 1; }
+                    break;
+                }
+                case SDFT_OP_D_NEG: I.op = DOP_D_NEG; break;
+                case SDFT_OP_D_ABS: I.op = DOP_D_ABS; break;
+                case SDFT_OP_D_ADD: I.op = DOP_D_ADD; break;
+                case SDFT_OP_D_MUL: I.op = DOP_D_MUL; break;
+                case SDFT_OP_D_MAX: I.op = DOP_D_MAX; break;
+                case SDFT_OP_D_MIN: I.op = DOP_D_MIN; break;
+                case SDFT_OP_M_SET: I.op = DOP_M_SET; break;
+                case SDFT_OP_P_RESET: I.op = DOP_P_RESET; break;
+                case SDFT_OP_P_SUB: I.op = DOP_P_SUB; break;
+                case SDFT_OP_P_MUL: I.op = DOP_P_MUL; break;
+                case SDFT_OP_P_ABS: I.op = DOP_P_ABS; break;
+            }
+            if (end) break;
+        }
+        if (h.n_instr) memcpy(img.data() + ih.off_instr, low.data(), h.n_instr * 16u);
+        // the interpreter stops at DOP_END: one is always appended (the slot is zero-initialised = DOP_END)
+    }
     for (uint32_t k = 0; k < h.n_prims; ++k) {
         const sdft_prim& pr = prims[k];
         const float g[4] = {pr.center[0], pr.center[1], pr.center[2], pr.size};

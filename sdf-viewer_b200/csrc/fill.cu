@@ -106,29 +106,35 @@ __device__ __forceinline__ float prim_distance(uint32_t shape, float qx, float q
 }
 
 // One primitive with its material: SDFDemoCube::sample / SDFDemoSphere::sample
-// (cube.rs:79-89, sphere.rs:37-47) generalised by the record's fields.
+// (cube.rs:79-89, sphere.rs:37-47) generalised by the record's fields; shape and material are
+// compile-time here (the lowered opcode carries them).
+template <int SHAPE, int MAT>
 __device__ __forceinline__ Smp prim_sample(const float4 geom, const float4 m0, const float4 m1, float px, float py,
                                            float pz) {
-    const uint32_t kind = __float_as_uint(m1.w);
-    const uint32_t shape = kind & 0xffu, mat = (kind >> 8) & 0xffu;
     const float qx = px - geom.x, qy = py - geom.y, qz = pz - geom.z;
     Smp s;
-    s.d = prim_distance(shape, qx, qy, qz, geom.w);
+    float len = 0.0f;
+    if (SHAPE == SDFT_SHAPE_SPHERE) {
+        len = sqrtf(qx * qx + qy * qy + qz * qz);
+        s.d = len - geom.w;
+    } else {
+        s.d = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) - geom.w;
+    }
     s.r = s.g = s.b = s.m = s.ro = s.o = 0.0f;
     if (!(s.d > m1.z)) {  // "the air has no texture" shortcut, cube.rs:83-85
-        if (mat == SDFT_MAT_FLAT) {
+        if (MAT == SDFT_MAT_FLAT) {
             s.r = m0.x; s.g = m0.y; s.b = m0.z; s.m = m0.w; s.ro = m1.x; s.o = m1.y;
         } else {
             float nx, ny, nz;
-            if (shape == SDFT_SHAPE_SPHERE) {  // cgmath normalize = v * (1 / |v|), sphere.rs:123
-                const float inv = 1.0f / sqrtf(qx * qx + qy * qy + qz * qz);
+            if (SHAPE == SDFT_SHAPE_SPHERE) {  // cgmath normalize = v * (1 / |v|), sphere.rs:123
+                const float inv = 1.0f / len;
                 nx = qx * inv; ny = qy * inv; nz = qz * inv;
             } else {  // cube.rs:164-177
                 nx = fabsf(qx) > geom.w ? rust_signum(qx) : 0.0f;
                 ny = fabsf(qy) > geom.w ? rust_signum(qy) : 0.0f;
                 nz = fabsf(qz) > geom.w ? rust_signum(qz) : 0.0f;
             }
-            if (mat == SDFT_MAT_BRICK) {
+            if (MAT == SDFT_MAT_BRICK) {
                 brick_texture(qx, qy, qz, nx, ny, nz, s);
             } else {  // Material::Normal, cube.rs:56
                 s.r = fabsf(nx); s.g = fabsf(ny); s.b = fabsf(nz);
@@ -136,6 +142,33 @@ __device__ __forceinline__ Smp prim_sample(const float4 geom, const float4 m0, c
         }
     }
     return s;
+}
+
+// runtime (shape, material): used once per voxel after a UNION_RANGE fold
+__device__ __forceinline__ Smp prim_sample_rt(const float4 g, const float4 m0, const float4 m1, float px, float py,
+                                              float pz) {
+    const uint32_t kind = __float_as_uint(m1.w);
+    switch (((kind & 0xffu) ? 3u : 0u) + ((kind >> 8) & 0xffu)) {
+        case 0: return prim_sample<SDFT_SHAPE_SPHERE, SDFT_MAT_FLAT>(g, m0, m1, px, py, pz);
+        case 1: return prim_sample<SDFT_SHAPE_SPHERE, SDFT_MAT_BRICK>(g, m0, m1, px, py, pz);
+        case 2: return prim_sample<SDFT_SHAPE_SPHERE, SDFT_MAT_NORMAL>(g, m0, m1, px, py, pz);
+        case 3: return prim_sample<SDFT_SHAPE_BOX_LINF, SDFT_MAT_FLAT>(g, m0, m1, px, py, pz);
+        case 4: return prim_sample<SDFT_SHAPE_BOX_LINF, SDFT_MAT_BRICK>(g, m0, m1, px, py, pz);
+        default: return prim_sample<SDFT_SHAPE_BOX_LINF, SDFT_MAT_NORMAL>(g, m0, m1, px, py, pz);
+    }
+}
+
+// MODE 0: A = y;  1: A = union(A, y) = (y.d < A.d) ? y : A;  2: A = intersect(A, y) = (y.d > A.d) ? y : A
+template <int V, int MODE, int SHAPE, int MAT>
+__device__ __forceinline__ void op_prim(Smp (&A)[V], const float4 g, const float4 m0, const float4 m1,
+                                        const float (&qx)[V], const float (&qy)[V], const float (&qz)[V]) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const Smp y = prim_sample<SHAPE, MAT>(g, m0, m1, qx[v], qy[v], qz[v]);
+        if (MODE == 0) A[v] = y;
+        else if (MODE == 1) { if (y.d < A[v].d) A[v] = y; }
+        else { if (y.d > A[v].d) A[v] = y; }
+    }
 }
 
 // `Srgba::from(Vector3<f32>)`: (c * 255.0) as u8 -- saturating, NaN -> 0 (scene/sdf/mod.rs:201)
@@ -146,9 +179,39 @@ __device__ __forceinline__ void store_texel(float4* p, float4 v, bool streaming)
 }
 
 // ------------------------------------------------------------------ kernel
-// V = voxels per thread along z (lattice units).
-template <int V>
-__global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillParams P) {
+__device__ __forceinline__ void stack_store(float* st, const Smp& s) {
+    constexpr int NT = FILL_THREADS;
+    st[0 * NT] = s.d; st[1 * NT] = s.r; st[2 * NT] = s.g; st[3 * NT] = s.b;
+    st[4 * NT] = s.m; st[5 * NT] = s.ro; st[6 * NT] = s.o;
+}
+__device__ __forceinline__ void stack_load(const float* st, Smp& s) {
+    constexpr int NT = FILL_THREADS;
+    s.d = st[0 * NT]; s.r = st[1 * NT]; s.g = st[2 * NT]; s.b = st[3 * NT];
+    s.m = st[4 * NT]; s.ro = st[5 * NT]; s.o = st[6 * NT];
+}
+
+// B = popped sample (pushed first), A = accumulator.  KIND 0 union, 1 intersect, 2 SDFDemo combinator
+template <int KIND>
+__device__ __forceinline__ void op_pop(Smp& A, const Smp& B, const float* c) {
+    if (KIND == 0) {
+        if (!(A.d < B.d)) A = B;
+    } else if (KIND == 1) {
+        if (!(A.d > B.d)) A = B;
+    } else {  // SDFDemo::sample, demo/mod.rs:58-73; B = box, A = sphere
+        const float dist = fmaxf(B.d, -A.d);                 // :58
+        const float inter = fabsf(B.d) - fabsf(A.d);         // :60
+        Smp s = (inter < 0.0f) ? B : A;                      // :61
+        if (fabsf(inter) <= c[0]) {                          // :62
+            s.r = c[1]; s.g = c[2]; s.b = c[3]; s.m = c[4]; s.ro = c[5]; s.o = c[6];
+        }
+        s.d = dist;                                          // :72
+        A = s;
+    }
+}
+
+// V = voxels per thread along z (lattice units).  MINB = CTAs per SM the register budget aims at.
+template <int V, int MINB>
+__global__ void __launch_bounds__(FILL_THREADS, MINB) fill_kernel(const FillParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NT = FILL_THREADS;
 
@@ -168,33 +231,37 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillParams P) 
     __syncthreads();
     mbar_wait(bar, 0);
 
-    const TapeImageHeader hdr = *reinterpret_cast<const TapeImageHeader*>(smem);
-    const uint4* s_instr = reinterpret_cast<const uint4*>(smem + hdr.off_instr);
-    const float4* s_geom = reinterpret_cast<const float4*>(smem + hdr.off_geom);
-    const float4* s_mat0 = reinterpret_cast<const float4*>(smem + hdr.off_mat0);
-    const float4* s_mat1 = reinterpret_cast<const float4*>(smem + hdr.off_mat1);
-    const float* s_consts = reinterpret_cast<const float*>(smem + hdr.off_consts);
-    const float* s_lut = reinterpret_cast<const float*>(smem + hdr.off_lut);
-    const float* s_px = reinterpret_cast<const float*>(smem + hdr.off_px);
-    const float* s_py = reinterpret_cast<const float*>(smem + hdr.off_py);
-    const float* s_pz = reinterpret_cast<const float*>(smem + hdr.off_pz);
+    const TapeImageHeader* hdr = reinterpret_cast<const TapeImageHeader*>(smem);
+    const uint4* s_instr = reinterpret_cast<const uint4*>(smem + hdr->off_instr);
+    const float4* s_geom = reinterpret_cast<const float4*>(smem + hdr->off_geom);
+    const float4* s_mat0 = reinterpret_cast<const float4*>(smem + hdr->off_mat0);
+    const float4* s_mat1 = reinterpret_cast<const float4*>(smem + hdr->off_mat1);
+    const float* s_consts = reinterpret_cast<const float*>(smem + hdr->off_consts);
+    const float* s_lut = reinterpret_cast<const float*>(smem + hdr->off_lut);
+    const float* s_px = reinterpret_cast<const float*>(smem + hdr->off_px);
+    const float* s_py = reinterpret_cast<const float*>(smem + hdr->off_py);
+    const float* s_pz = reinterpret_cast<const float*>(smem + hdr->off_pz);
 
-    // scratch after the barrier: [16 B bar][64 B reduce][cull list u32 x n_cull][stack floats]
+    // scratch after the image: [16 B bar][32 B reduce][32 B counts][cull list u32 x n_cull][stack floats]
     float* s_red = reinterpret_cast<float*>(smem + img_bytes + 16);
-    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + img_bytes + 16 + 48);
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + img_bytes + 16 + 32);
     uint32_t* s_list = reinterpret_cast<uint32_t*>(smem + img_bytes + 16 + 64);
-    const uint32_t n_cull = (hdr.flags & TAPE_FLAG_CULL) ? hdr.cull_count : 0u;
-    float* s_stack = reinterpret_cast<float*>(smem + img_bytes + 16 + 64 + ((n_cull * 4u + 15u) & ~15u));
+    const uint32_t n_cull = (hdr->flags & TAPE_FLAG_CULL) ? hdr->cull_count : 0u;
+    const uint32_t cull_first = hdr->cull_first;
+    float* s_stack = reinterpret_cast<float*>(smem + img_bytes + 16 + 64 + ((n_cull * 4u + 15u) & ~15u)) + threadIdx.x;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_tiles = P.tiles_x * P.tiles_y * P.tiles_z;
     const size_t slice = (size_t)P.W * P.H;
-    unsigned long long touched_local = 0;
+    uint32_t touched_local = 0;
+
+    // tile -> (tx, ty, tz), x fastest; advanced incrementally by gridDim.x per iteration
+    uint32_t tx = blockIdx.x % P.tiles_x, ty = (blockIdx.x / P.tiles_x) % P.tiles_y,
+             tz = blockIdx.x / (P.tiles_x * P.tiles_y);
+    const uint32_t sx = gridDim.x % P.tiles_x, sy = (gridDim.x / P.tiles_x) % P.tiles_y,
+                   sz = gridDim.x / (P.tiles_x * P.tiles_y);
 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t tx = tile % P.tiles_x, tyz = tile / P.tiles_x;
-        const uint32_t ty = tyz % P.tiles_y, tz = tyz / P.tiles_y;
-
         // ---- per-tile culling of the UNION_RANGE (exact-safe: a primitive is dropped only if
         // its lower bound over the tile exceeds some other primitive's upper bound)
         uint32_t list_n = 0;
@@ -213,8 +280,8 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillParams P) 
             // pass 1: U = min over primitives of the upper bound
             float umin = __int_as_float(0x7f800000);
             for (uint32_t k = threadIdx.x; k < n_cull; k += NT) {
-                const float4 g = s_geom[hdr.cull_first + k];
-                const uint32_t shape = __float_as_uint(s_mat1[hdr.cull_first + k].w) & 0xffu;
+                const float4 g = s_geom[cull_first + k];
+                const uint32_t shape = __float_as_uint(s_mat1[cull_first + k].w) & 0xffu;
                 const float fx = fmaxf(fabsf(lox - g.x), fabsf(hix - g.x));
                 const float fy = fmaxf(fabsf(loy - g.y), fabsf(hiy - g.y));
                 const float fz = fmaxf(fabsf(loz - g.z), fabsf(hiz - g.z));
@@ -236,8 +303,8 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillParams P) 
                 const uint32_t k = k0 + threadIdx.x;
                 bool keep = false;
                 if (k < n_cull) {
-                    const float4 g = s_geom[hdr.cull_first + k];
-                    const uint32_t shape = __float_as_uint(s_mat1[hdr.cull_first + k].w) & 0xffu;
+                    const float4 g = s_geom[cull_first + k];
+                    const uint32_t shape = __float_as_uint(s_mat1[cull_first + k].w) & 0xffu;
                     const float nx_ = fmaxf(fmaxf(lox - g.x, g.x - hix), 0.0f);
                     const float ny_ = fmaxf(fmaxf(loy - g.y, g.y - hiy), 0.0f);
                     const float nz_ = fmaxf(fmaxf(loz - g.z, g.z - hiz), 0.0f);
@@ -257,7 +324,7 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillParams P) 
                     if (w < warp) wbase += c;
                     total += c;
                 }
-                if (keep) s_list[wbase + __popc(bal & ((1u << lane) - 1u))] = hdr.cull_first + k;
+                if (keep) s_list[wbase + __popc(bal & ((1u << lane) - 1u))] = cull_first + k;
                 base += total;
                 __syncthreads();
             }
@@ -266,26 +333,30 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillParams P) 
 
         const uint32_t lx = tx * FILL_TILE_X + lane;
         const uint32_t ly = ty * FILL_TILE_Y + warp;
+        const uint32_t lz0 = tz * V;
+        // advance to this CTA's next tile (mixed-radix add with carries)
+        tx += sx; ty += sy; tz += sz;
+        if (tx >= P.tiles_x) { tx -= P.tiles_x; ++ty; }
+        if (ty >= P.tiles_y) { ty -= P.tiles_y; ++tz; }
+
         const bool row_ok = lx < P.nx && ly < P.ny;
-        const uint32_t gx = P.rx0 + lx * P.step, gy = P.ry0 + ly * P.step;
+        const uint32_t gx = P.rx0 + lx * P.step, gy = P.ry0 + ly * P.step, gz0 = P.rz0 + lz0 * P.step;
         const float posx = row_ok ? s_px[gx] : 0.0f, posy = row_ok ? s_py[gy] : 0.0f;
+        const size_t flat0 = row_ok ? (size_t)(gz0 - P.z_lo) * slice + (size_t)gy * P.W + gx : 0;
+        const size_t vstride = (size_t)P.step * slice;
 
         bool act[V];
         float posz[V];
-        size_t flat[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            const uint32_t lz = tz * V + v;
-            act[v] = row_ok && lz < P.nz;
-            const uint32_t gz = P.rz0 + lz * P.step;
-            posz[v] = act[v] ? s_pz[gz] : 0.0f;
-            flat[v] = act[v] ? (size_t)(gz - P.z_lo) * slice + (size_t)gy * P.W + gx : 0;
+            act[v] = row_ok && lz0 + v < P.nz;
+            posz[v] = act[v] ? s_pz[gz0 + v * P.step] : 0.0f;
         }
         if (P.conditional) {  // scene/sdf/mod.rs:184-190
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 if (act[v]) {
-                    bool need = __ldg(reinterpret_cast<const float*>(P.tex0 + flat[v])) == P.air_dist;
+                    bool need = __ldg(reinterpret_cast<const float*>(P.tex0 + flat0 + v * vstride)) == P.air_dist;
                     if (P.has_box)
                         need = need || (posx >= P.box[0] && posx <= P.box[3] && posy >= P.box[1] && posy <= P.box[4] &&
                                         posz[v] >= P.box[2] && posz[v] <= P.box[5]);
@@ -293,7 +364,6 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillParams P) 
                 }
             }
         }
-
         {  // nothing to sample in this warp's row (conditional passes over an already loaded region)
             bool any = false;
 #pragma unroll
@@ -301,33 +371,31 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillParams P) 
             if (!__any_sync(0xffffffffu, any)) continue;
         }
 
-        // ---- interpret the tape (machine model: include/sdfgpu_tape.h)
-        Smp A[V];
+        // ---- interpret the lowered tape (machine model: include/sdfgpu_tape.h; A = accumulator,
+        // T = top of the sample stack in registers, deeper levels in shared memory)
+        Smp A[V], T[V];
         float qx[V], qy[V], qz[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             A[v].d = A[v].r = A[v].g = A[v].b = A[v].m = A[v].ro = A[v].o = 0.0f;
+            T[v] = A[v];
             qx[v] = posx; qy[v] = posy; qz[v] = posz[v];
         }
-        uint32_t sp = 0;
-        for (uint32_t pc = 0; pc < hdr.n_instr; ++pc) {
+        for (uint32_t pc = 0;; ++pc) {
             const uint4 I = s_instr[pc];
-            const uint32_t op = I.x;
-            if (op == SDFT_OP_END) break;
-            switch (op) {
-                case SDFT_OP_PRIM:
-                case SDFT_OP_UNION_PRIM:
-                case SDFT_OP_INTER_PRIM: {
-                    const float4 g = s_geom[I.y], m0 = s_mat0[I.y], m1 = s_mat1[I.y];
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        const Smp y = prim_sample(g, m0, m1, qx[v], qy[v], qz[v]);
-                        const bool take = op == SDFT_OP_PRIM || (op == SDFT_OP_UNION_PRIM ? y.d < A[v].d : y.d > A[v].d);
-                        if (take) A[v] = y;
-                    }
-                    break;
-                }
-                case SDFT_OP_UNION_RANGE: {
+            if (I.x == DOP_END) break;
+#define PRIM_CASE(MODE, SHAPE, MAT)                                                                    \
+    case DOP_PRIM + (MODE) * 6 + (SHAPE) * 3 + (MAT):                                                 \
+        op_prim<V, MODE, SHAPE, MAT>(A, s_geom[I.y], s_mat0[I.y], s_mat1[I.y], qx, qy, qz);           \
+        break;
+#define PRIM_CASES(MODE)                                                                               \
+    PRIM_CASE(MODE, 0, 0) PRIM_CASE(MODE, 0, 1) PRIM_CASE(MODE, 0, 2) PRIM_CASE(MODE, 1, 0) PRIM_CASE(MODE, 1, 1) \
+    PRIM_CASE(MODE, 1, 2)
+            switch (I.x) {
+                PRIM_CASES(0)
+                PRIM_CASES(1)
+                PRIM_CASES(2)
+                case DOP_UNION_RANGE: {
                     // fold == argmin with ties to the lowest index, then one material evaluation
                     const bool culled = n_cull != 0;
                     const uint32_t n = culled ? list_n : I.z;
@@ -356,73 +424,58 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillParams P) 
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
                         const uint32_t k = best_k[v];
-                        A[v] = prim_sample(s_geom[k], s_mat0[k], s_mat1[k], qx[v], qy[v], qz[v]);
+                        A[v] = prim_sample_rt(s_geom[k], s_mat0[k], s_mat1[k], qx[v], qy[v], qz[v]);
                     }
                     break;
                 }
-                case SDFT_OP_PUSH: {
+                case DOP_PUSH_MEM:
 #pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        float* st = s_stack + ((size_t)(sp * V + v) * 7) * NT + threadIdx.x;
-                        st[0 * NT] = A[v].d; st[1 * NT] = A[v].r; st[2 * NT] = A[v].g; st[3 * NT] = A[v].b;
-                        st[4 * NT] = A[v].m; st[5 * NT] = A[v].ro; st[6 * NT] = A[v].o;
-                    }
-                    ++sp;
-                    break;
-                }
-                case SDFT_OP_POP_UNION:
-                case SDFT_OP_POP_INTER:
-                case SDFT_OP_POP_DEMO_DIFF: {
-                    --sp;
+                    for (int v = 0; v < V; ++v) stack_store(s_stack + (size_t)((I.z * V + v) * 7) * NT, T[v]);
+                    // fall through
+                case DOP_PUSH_REG:
 #pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        const float* st = s_stack + ((size_t)(sp * V + v) * 7) * NT + threadIdx.x;
-                        Smp B;
-                        B.d = st[0 * NT]; B.r = st[1 * NT]; B.g = st[2 * NT]; B.b = st[3 * NT];
-                        B.m = st[4 * NT]; B.ro = st[5 * NT]; B.o = st[6 * NT];
-                        if (op == SDFT_OP_POP_UNION) {
-                            if (!(A[v].d < B.d)) A[v] = B;
-                        } else if (op == SDFT_OP_POP_INTER) {
-                            if (!(A[v].d > B.d)) A[v] = B;
-                        } else {  // SDFDemo::sample, demo/mod.rs:58-73; B = box, A = sphere
-                            const float* c = s_consts + I.y;
-                            const float dist = fmaxf(B.d, -A[v].d);
-                            const float inter = fabsf(B.d) - fabsf(A[v].d);
-                            Smp s = (inter < 0.0f) ? B : A[v];
-                            if (fabsf(inter) <= c[0]) {
-                                s.r = c[1]; s.g = c[2]; s.b = c[3]; s.m = c[4]; s.ro = c[5]; s.o = c[6];
-                            }
-                            s.d = dist;
-                            A[v] = s;
-                        }
-                    }
+                    for (int v = 0; v < V; ++v) T[v] = A[v];
                     break;
-                }
-                case SDFT_OP_D_NEG:
+                case DOP_POP_UNION:
+                case DOP_POP_UNION_MEM:
+#pragma unroll
+                    for (int v = 0; v < V; ++v) op_pop<0>(A[v], T[v], nullptr);
+                    break;
+                case DOP_POP_INTER:
+                case DOP_POP_INTER_MEM:
+#pragma unroll
+                    for (int v = 0; v < V; ++v) op_pop<1>(A[v], T[v], nullptr);
+                    break;
+                case DOP_POP_DEMO_DIFF:
+                case DOP_POP_DEMO_DIFF_MEM:
+#pragma unroll
+                    for (int v = 0; v < V; ++v) op_pop<2>(A[v], T[v], s_consts + I.y);
+                    break;
+                case DOP_D_NEG:
 #pragma unroll
                     for (int v = 0; v < V; ++v) A[v].d = -A[v].d;
                     break;
-                case SDFT_OP_D_ABS:
+                case DOP_D_ABS:
 #pragma unroll
                     for (int v = 0; v < V; ++v) A[v].d = fabsf(A[v].d);
                     break;
-                case SDFT_OP_D_ADD:
+                case DOP_D_ADD:
 #pragma unroll
                     for (int v = 0; v < V; ++v) A[v].d = A[v].d + __uint_as_float(I.w);
                     break;
-                case SDFT_OP_D_MUL:
+                case DOP_D_MUL:
 #pragma unroll
                     for (int v = 0; v < V; ++v) A[v].d = A[v].d * __uint_as_float(I.w);
                     break;
-                case SDFT_OP_D_MAX:
+                case DOP_D_MAX:
 #pragma unroll
                     for (int v = 0; v < V; ++v) A[v].d = fmaxf(A[v].d, __uint_as_float(I.w));
                     break;
-                case SDFT_OP_D_MIN:
+                case DOP_D_MIN:
 #pragma unroll
                     for (int v = 0; v < V; ++v) A[v].d = fminf(A[v].d, __uint_as_float(I.w));
                     break;
-                case SDFT_OP_M_SET: {
+                case DOP_M_SET: {
                     const float* c = s_consts + I.y;
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
@@ -430,24 +483,24 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillParams P) 
                     }
                     break;
                 }
-                case SDFT_OP_P_RESET:
+                case DOP_P_RESET:
 #pragma unroll
                     for (int v = 0; v < V; ++v) { qx[v] = posx; qy[v] = posy; qz[v] = posz[v]; }
                     break;
-                case SDFT_OP_P_SUB: {
+                case DOP_P_SUB: {
                     const float* c = s_consts + I.y;
 #pragma unroll
                     for (int v = 0; v < V; ++v) { qx[v] = qx[v] - c[0]; qy[v] = qy[v] - c[1]; qz[v] = qz[v] - c[2]; }
                     break;
                 }
-                case SDFT_OP_P_MUL:
+                case DOP_P_MUL:
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
                         qx[v] = qx[v] * __uint_as_float(I.w); qy[v] = qy[v] * __uint_as_float(I.w);
                         qz[v] = qz[v] * __uint_as_float(I.w);
                     }
                     break;
-                case SDFT_OP_P_ABS:
+                case DOP_P_ABS:
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
                         if (I.y & 1u) qx[v] = fabsf(qx[v]);
@@ -456,6 +509,12 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillParams P) 
                     }
                     break;
                 default: break;
+            }
+#undef PRIM_CASES
+#undef PRIM_CASE
+            if (I.x >= DOP_POP_UNION_MEM && I.x <= DOP_POP_DEMO_DIFF_MEM) {  // reload the new top of stack
+#pragma unroll
+                for (int v = 0; v < V; ++v) stack_load(s_stack + (size_t)((I.z * V + v) * 7) * NT, T[v]);
             }
         }
 
@@ -475,8 +534,8 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillParams P) 
                 t1.y = s.ro;
                 t1.z = (s.o <= 0.0f) ? 1.0f : s.o;
                 t1.w = P.air_dist;  // never written by the reference: keeps its initial value (:76)
-                store_texel(P.tex0 + flat[v], t0, P.streaming_stores != 0);
-                store_texel(P.tex1 + flat[v], t1, P.streaming_stores != 0);
+                store_texel(P.tex0 + flat0 + v * vstride, t0, P.streaming_stores != 0);
+                store_texel(P.tex1 + flat0 + v * vstride, t1, P.streaming_stores != 0);
                 ++touched_local;
             }
         }
@@ -485,7 +544,7 @@ __global__ void __launch_bounds__(FILL_THREADS) fill_kernel(const FillParams P) 
     if (P.touched) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) touched_local += __shfl_xor_sync(0xffffffffu, touched_local, o);
-        if (lane == 0 && touched_local) atomicAdd(P.touched, touched_local);
+        if (lane == 0 && touched_local) atomicAdd(P.touched, (unsigned long long)touched_local);
     }
 }
 
@@ -495,16 +554,20 @@ __global__ void __launch_bounds__(256) set_const_kernel(float4* __restrict__ dst
         dst[i] = val;
 }
 
-template <int V>
+template <int V, int MINB>
 cudaError_t launch_fill_v(const FillParams& p, int grid, size_t smem, cudaStream_t s) {
-    fill_kernel<V><<<grid, FILL_THREADS, smem, s>>>(p);
+    fill_kernel<V, MINB><<<grid, FILL_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
+#define FILL_K1 fill_kernel<1, 4>
+#define FILL_K2 fill_kernel<2, 3>
+#define FILL_K4 fill_kernel<4, 2>
+#define FILL_K8 fill_kernel<8, 1>
 
 }  // namespace
 
 size_t fill_smem_bytes(uint32_t tape_img_bytes, uint32_t n_cull, uint32_t max_stack, int V, uint32_t* stack_floats) {
-    const uint32_t sf = max_stack * 7u * (uint32_t)V * FILL_THREADS;
+    const uint32_t sf = (max_stack > 1 ? max_stack - 1 : 0) * 7u * (uint32_t)V * FILL_THREADS;  // top level lives in registers
     if (stack_floats) *stack_floats = sf;
     return (size_t)tape_img_bytes + 16 + 64 + ((n_cull * 4u + 15u) & ~15u) + (size_t)sf * 4u;
 }
@@ -512,10 +575,10 @@ size_t fill_smem_bytes(uint32_t tape_img_bytes, uint32_t n_cull, uint32_t max_st
 cudaError_t fill_prepare(size_t smem_bytes) {
     cudaError_t e;
     const int b = (int)smem_bytes;
-    if ((e = cudaFuncSetAttribute(fill_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(fill_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(fill_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(fill_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(FILL_K1, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(FILL_K2, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(FILL_K4, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(FILL_K8, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -523,10 +586,10 @@ int fill_max_ctas_per_sm(int V, size_t smem_bytes) {
     int n = 0;
     cudaError_t e;
     switch (V) {
-        case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<1>, FILL_THREADS, smem_bytes); break;
-        case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<2>, FILL_THREADS, smem_bytes); break;
-        case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<4>, FILL_THREADS, smem_bytes); break;
-        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fill_kernel<8>, FILL_THREADS, smem_bytes); break;
+        case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, FILL_K1, FILL_THREADS, smem_bytes); break;
+        case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, FILL_K2, FILL_THREADS, smem_bytes); break;
+        case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, FILL_K4, FILL_THREADS, smem_bytes); break;
+        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, FILL_K8, FILL_THREADS, smem_bytes); break;
     }
     if (e != cudaSuccess) { (void)cudaGetLastError(); return 0; }
     return n;
@@ -534,10 +597,10 @@ int fill_max_ctas_per_sm(int V, size_t smem_bytes) {
 
 cudaError_t launch_fill(const FillParams& p, int V, int grid, size_t smem, cudaStream_t s) {
     switch (V) {
-        case 1: return launch_fill_v<1>(p, grid, smem, s);
-        case 2: return launch_fill_v<2>(p, grid, smem, s);
-        case 4: return launch_fill_v<4>(p, grid, smem, s);
-        case 8: return launch_fill_v<8>(p, grid, smem, s);
+        case 1: return launch_fill_v<1, 4>(p, grid, smem, s);
+        case 2: return launch_fill_v<2, 3>(p, grid, smem, s);
+        case 4: return launch_fill_v<4, 2>(p, grid, smem, s);
+        case 8: return launch_fill_v<8, 1>(p, grid, smem, s);
         default: return cudaErrorInvalidValue;
     }
 }

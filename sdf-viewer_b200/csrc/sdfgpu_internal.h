@@ -33,6 +33,38 @@ enum : uint32_t {
     TAPE_FLAG_CULL = 1u  // the tape holds exactly one UNION_RANGE, reached with P == voxel position
 };
 
+// ---- lowered (device) opcodes.  sdfgpu_set_tape translates the public tape (sdfgpu_tape.h) into
+// this dense set so the interpreter dispatches through one jump table and each primitive op is
+// already specialised by shape and material:
+//   * PRIM / UNION_PRIM / INTER_PRIM a  ->  DOP_PRIM + mode*6 + shape*3 + material
+//   * the top of the sample stack lives in registers; PUSH / POP_* carry in their opcode whether
+//     a deeper level has to be spilled to / reloaded from shared memory (depth is static).
+enum DeviceOp : uint32_t {
+    DOP_END = 0,
+    DOP_PRIM = 1,  // 18 variants: mode (0 set, 1 union, 2 intersect) * 6 + shape * 3 + material
+    DOP_UNION_RANGE = 19,
+    DOP_PUSH_REG = 20,   // T = A                      (stack was empty)
+    DOP_PUSH_MEM = 21,   // spill T to level b, T = A   (b = depth before the push - 1)
+    DOP_POP_UNION = 22,  // +0 union, +1 intersect, +2 demo_diff; B = T
+    DOP_POP_INTER = 23,
+    DOP_POP_DEMO_DIFF = 24,
+    DOP_POP_UNION_MEM = 25,  // same, then reload T from level b (b = depth after the pop - 1)
+    DOP_POP_INTER_MEM = 26,
+    DOP_POP_DEMO_DIFF_MEM = 27,
+    DOP_D_NEG = 28,
+    DOP_D_ABS = 29,
+    DOP_D_ADD = 30,
+    DOP_D_MUL = 31,
+    DOP_D_MAX = 32,
+    DOP_D_MIN = 33,
+    DOP_M_SET = 34,
+    DOP_P_RESET = 35,
+    DOP_P_SUB = 36,
+    DOP_P_MUL = 37,
+    DOP_P_ABS = 38,
+    DOP_COUNT = 39
+};
+
 constexpr int FILL_THREADS = 256;  // 8 warps: a tile is 32 (x) x 8 (y) x V (z) lattice points
 constexpr int FILL_TILE_X = 32;
 constexpr int FILL_TILE_Y = 8;

@@ -1,0 +1,95 @@
+"""The drop-in boundary: libsdfgpu.so loads, exports every function include/sdfgpu.h declares,
+and the device-free entry points behave.  No compute is attempted without a GPU -- and the
+library must fail loudly (never fall back to a CPU path) when there is none."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "sdfgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sdfgpu_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(S):
+    from sdf_viewer_b200 import _lib
+    lib = _lib.load()
+    names = declared_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/sdfgpu.h but not exported by libsdfgpu.so"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in _lib.py"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes binding lists functions the header does not declare"
+
+
+def test_tape_header_layout_matches_python(S):
+    """sdft_instr is 16 bytes, sdft_prim 48, header 32 (include/sdfgpu_tape.h)."""
+    T = S.tape
+    t = T.demo_tape()
+    magic, version, n_instr, n_prims, n_consts = np.frombuffer(t[:20], "<u4")
+    assert magic == 0x54464453 and version == 1
+    assert (n_instr, n_prims, n_consts) == (5, 2, 7)
+    assert len(t) == 32 + 16 * n_instr + 48 * n_prims + 4 * n_consts
+    hdr = open(os.path.join(ROOT, "include", "sdfgpu_tape.h")).read()
+    for name in ("OP_END", "OP_PRIM", "OP_UNION_PRIM", "OP_INTER_PRIM", "OP_UNION_RANGE", "OP_PUSH", "OP_POP_UNION",
+                 "OP_POP_INTER", "OP_POP_DEMO_DIFF", "OP_D_NEG", "OP_D_ABS", "OP_D_ADD", "OP_D_MUL", "OP_D_MAX",
+                 "OP_D_MIN", "OP_M_SET", "OP_P_RESET", "OP_P_SUB", "OP_P_MUL", "OP_P_ABS"):
+        m = re.search(r"SDFT_%s\s*=\s*(\d+)" % name, hdr)
+        assert m and int(m.group(1)) == getattr(T, name), name
+
+
+def test_device_free_entry_points(S, oracle):
+    from sdf_viewer_b200 import _lib
+    lib = _lib.load()
+    assert lib.sdfgpu_air_dist() == oracle.lib().orc_air_dist() == np.float32(0.1) + np.float32(0.001234)
+    # from_bb's voxel rule (scene/sdf/mod.rs:47-68) against the oracle, incl. ties (last max wins) and truncation
+    for bb in [((-1, -1, -1), (1, 1, 1)), ((0, 0, 0), (1, 2, 3)), ((0, 0, 0), (3, 2, 1)), ((-1, 0, 0), (1, 2, 0.7)),
+               ((0, 0, 0), (2, 2, 1)), ((0, 0, 0), (1, 0.333, 0.9999))]:
+        for side in (1, 7, 64, 100, 512):
+            od = (C.c_uint32 * 3)()
+            oracle.lib().orc_dims_from_bb(oracle._bb6(bb), side, od)
+            assert S.dims_from_bb(bb, side) == tuple(od)
+    # camera: cgmath look_at_rh / perspective as the oracle restates them
+    cam = S.default_camera(640, 480)
+    v, p = (C.c_float * 16)(), (C.c_float * 16)()
+    oracle.lib().orc_look_at_rh(oracle._f([2.5, 3, 5]), oracle._f([0, 0, 0]), oracle._f([0, 1, 0]), v)
+    oracle.lib().orc_perspective(np.float32(45.0 * np.pi / 180.0), np.float32(640 / 480), 0.1, 1000.0, p)
+    np.testing.assert_allclose(list(cam.view), list(v), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(list(cam.projection), list(p), rtol=1e-6, atol=1e-7)
+    assert (cam.tone_mapping, cam.color_mapping, cam.gamma) == (2, 1, 0.0)
+    rays = S.camera_rays(cam, 640, 480)
+    # the centre ray looks at the origin: camera at (2.5,3,5) -> direction ~ -position
+    d = np.array(rays.base) + np.array(rays.dx) * 320 + np.array(rays.dy) * 240
+    pos = np.array(cam.position)
+    assert np.allclose(d / np.linalg.norm(d), -pos / np.linalg.norm(pos), atol=1e-5)
+    # unprojecting then projecting with BVP lands on the pixel (bias maps NDC to [0,1])
+    for (i, j) in ((0.5, 0.5), (100.5, 300.5), (639.5, 479.5)):
+        dd = np.array(rays.base) + np.array(rays.dx) * i + np.array(rays.dy) * j
+        q = np.array(rays.bvp).reshape(4, 4).T @ np.append(pos + 3.0 * dd, 1.0)
+        assert np.allclose(q[:2] / q[3], [i / 640, j / 480], atol=1e-4)
+
+
+def test_no_cpu_fallback_without_device(S):
+    """On a box without a CUDA device every constructor fails with SDFGPU_ERR_CUDA."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(S.SdfGpuError) as e:
+        S.SDFViewer.from_bb(((-1, -1, -1), (1, 1, 1)), 16, 2)
+    assert e.value.code == -2 and "no CPU fallback" in e.value.message
+
+
+def test_product_does_not_import_oracle():
+    """oracle/ is test infrastructure: nothing under sdf-viewer_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "sdf-viewer_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                text = open(os.path.join(d, f)).read()
+                assert "liboracle" not in text and "import orc" not in text and "sdf_oracle" not in text, f

@@ -1,0 +1,147 @@
+"""Pins the CPU oracle (oracle/sdf_oracle.cpp): hand-derived known answers from the reference's
+source lines, the committed golden fixtures, and internal consistency
+(tape interpreter == direct restatement; OpenMP fill == reference-order fill).
+
+The reference holds no value-level vectors for this path, and cannot be run here: "parity unpinned"."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+BB = ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))
+f32 = np.float32
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_constants(oracle):
+    L = oracle.lib()
+    assert L.orc_air_dist() == f32(0.1) + f32(0.001234)      # scene/sdf/mod.rs:42
+    assert abs(float(L.orc_air_dist()) - 0.101234004) < 1e-9
+    lut = (oracle.C.c_float * 256)()
+    L.orc_srgb_lut(lut)
+    lut = np.array(lut, np.float32)
+    assert lut[0] == 0 and lut[255] == 1 and np.all(np.diff(lut) > 0)
+    c = f32(10) / f32(255)
+    assert lut[10] == c / f32(12.92)                           # linear segment below 0.04045
+    assert abs(lut[128] - ((128 / 255 + 0.055) / 1.055) ** 2.4) < 1e-7
+    # `(c * 255.0) as u8`: truncation, saturation, NaN -> 0
+    for v, want in ((0.0, 0), (1.0, 255), (0.5, 127), (0.6, 153), (0.7, 178), (2.0, 255), (-1.0, 0), (float("nan"), 0),
+                    (150 / 255, 150), (24 / 255, 24), (10 / 255, 10), (56 / 255, 56), (70 / 255, 70), (60 / 255, 60)):
+        assert L.orc_f32_to_u8(f32(v)) == want, v
+
+
+def test_demo_known_answers(oracle):
+    """SURVEY 8c, derived by hand from demo/mod.rs:58-73, cube.rs:79-89,181-222, sphere.rs:37-47."""
+    d_box_corner = f32(1.0) - f32(0.95)
+    s = oracle.demo_sample([[1, 1, 1], [-1, -1, -1]])
+    for row in s:  # corner: box distance 0.05, sphere is air (d_sph = sqrt(3)-1.05 > 0.1), brick lands on cement
+        assert row[0] == d_box_corner
+        assert tuple(row[1:]) == (f32(56) / f32(255), f32(70) / f32(255), f32(60) / f32(255), f32(0.4), f32(0.5), f32(1.0))
+    # seam at p = (1,0,0): |d_box| ~ |d_sph| -> forced material (demo/mod.rs:62-70)
+    row = oracle.demo_sample([[1, 0, 0]])[0]
+    assert row[0] == max(f32(1) - f32(0.95), -(f32(1) - f32(1.05)))
+    assert tuple(row[1:]) == (f32(0.5), f32(0.6), f32(0.7), f32(0.5), f32(0.0), f32(0.0))
+    # centre region: deep inside the removed sphere -> distance = -d_sph
+    p = f32(0.015873075)
+    row = oracle.demo_sample([[p, p, p]])[0]
+    d_sph = np.sqrt(p * p + p * p + p * p, dtype=np.float32) - f32(1.05)
+    assert row[0] == -d_sph and abs(row[0] - 1.0225) < 1e-3
+    # distance_only skips every material
+    s = oracle.demo_sample(np.random.default_rng(1).uniform(-1, 1, (500, 3)), distance_only=True)
+    full = oracle.demo_sample(np.random.default_rng(1).uniform(-1, 1, (500, 3)))
+    assert np.array_equal(bits(s[:, 0]), bits(full[:, 0]))
+
+
+def test_voxel_positions_and_store_rules(oracle):
+    """scene/sdf/mod.rs:179-182 (three roundings) and :196-208 (clamp, grey, sRGB LUT, occlusion)."""
+    v = oracle.Viewer(BB, (64, 64, 64), 2)
+    for i, want in ((1, -0.96825397), (31, -0.015873015), (0, -1.0), (63, 1.0)):
+        x = v.voxel_pos(i, 0, 0)[0]
+        assert x == f32(f32(f32(i) / f32(63)) * f32(2)) + f32(-1)
+        assert abs(x - want) < 1e-7
+    its = v.update(oracle.Sampler())
+    assert its == 294912 and v.len() == 0                       # 32^3 + 64^3 (loading.rs:80-89)
+    t0, t1 = v.tex0, v.tex1
+    lut = (oracle.C.c_float * 256)(); oracle.lib().orc_srgb_lut(lut)
+    assert t0[0, 0, 0, 0] == f32(0.1) + (f32(1.0) - f32(0.95))
+    assert tuple(t0[0, 0, 0, 1:]) == (lut[56], lut[70], lut[60])
+    assert tuple(t1[0, 0, 0]) == (f32(0.4), f32(0.5), f32(1.0), f32(oracle.lib().orc_air_dist()))
+    assert t0[32, 32, 32, 0] == 1.0                             # clamp(0.1 + 1.02, 0, 1)
+    assert np.all(t1[..., 3] == f32(oracle.lib().orc_air_dist()))  # tex1.a is never written (:205-208)
+    assert t0[..., 0].min() >= 0 and t0[..., 0].max() <= 1
+    assert np.all(t1[..., 2] > 0)                               # occlusion <= 0 stored as 1 (:208)
+
+
+def test_tape_interpreter_equals_direct_demo(oracle, S):
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([rng.uniform(-1.2, 1.2, (20000, 3)), np.array([[0, 0, 0], [1, 1, 1], [0.95, 0, 0]])]).astype(f32)
+    for kw in ({}, dict(cube_half_side=0.7, sphere_radius=0.8), dict(disable_sphere=True),
+               dict(cube_material=S.tape.MAT_NORMAL, sphere_material=S.tape.MAT_BRICK), dict(max_distance_custom_material=0.3)):
+        P = oracle.demo_params(**{k: (int(v) if isinstance(v, bool) else v) for k, v in kw.items()})
+        with np.errstate(all="ignore"):
+            a, b = oracle.demo_sample(pts, P), oracle.tape_sample(S.tape.demo_tape(**kw), pts)
+        assert np.array_equal(bits(a), bits(b)), kw
+
+
+def test_parallel_fill_equals_reference_order(oracle, S):
+    tape = S.tape.csg_tape(S.tape.csg_primitive_table(25, seed=2))
+    a = oracle.Viewer(BB, (20, 17, 9), 3); a.update(oracle.Sampler(tape=tape))
+    b = oracle.Viewer(BB, (20, 17, 9), 3); b.fill_all(oracle.Sampler(tape=tape), threads=4)
+    assert np.array_equal(bits(a.tex0), bits(b.tex0)) and np.array_equal(bits(a.tex1), bits(b.tex1))
+
+
+def test_golden_demo_samples(oracle):
+    g = np.load(os.path.join(GOLD, "demo_samples.npz"))
+    with np.errstate(all="ignore"):
+        assert np.array_equal(bits(oracle.demo_sample(g["points"])), bits(g["samples"]))
+        assert np.array_equal(bits(oracle.demo_sample(g["points"], distance_only=True)), bits(g["samples_distance_only"]))
+
+
+def test_golden_volume_and_csg(oracle, S):
+    g = np.load(os.path.join(GOLD, "demo_volume_16.npz"))
+    v = oracle.Viewer(BB, (16, 16, 16), 2)
+    assert v.update(oracle.Sampler(tape=S.tape.demo_tape())) == int(g["iterations"])
+    assert np.array_equal(bits(v.tex0), bits(g["tex0"])) and np.array_equal(bits(v.tex1), bits(g["tex1"]))
+    g = np.load(os.path.join(GOLD, "csg_samples.npz"))
+    table = S.tape.csg_primitive_table(40, seed=11)
+    assert np.array_equal(table.tobytes(), g["table"].tobytes()), "csg_primitive_table is no longer deterministic"
+    assert np.array_equal(bits(oracle.tape_sample(S.tape.csg_tape(table), g["points"])), bits(g["samples"]))
+
+
+def test_golden_trace(oracle, S):
+    g = np.load(os.path.join(GOLD, "trace_32_160x120.npz"))
+    w, h = 160, 120
+    rays = S.camera_rays(S.default_camera(w, h), w, h)
+    for k in ("origin", "base", "dx", "dy", "bvp"):
+        assert np.array_equal(np.array(getattr(rays, k), f32), g[k].astype(f32)), k
+    v = oracle.Viewer(BB, (32, 32, 32), 2)
+    v.update(oracle.Sampler(tape=S.tape.demo_tape()))
+    P = oracle.trace_params(rays, BB, (32, 32, 32), lod=1.0, filter_linear=1)
+    rgba, depth, gbuf = oracle.trace(P, v.tex0, v.tex1, w, h, threads=4)
+    assert np.array_equal(bits(gbuf), bits(g["gbuf"]))
+    assert np.array_equal(bits(depth), bits(g["depth"]))
+    np.testing.assert_allclose(rgba, g["rgba"], rtol=1e-6, atol=1e-7)
+    hit = gbuf[..., 3] >= 0
+    assert 0.05 < hit.mean() < 0.5
+    # lighting with one ambient light: rgb = occlusion * albedo * (1 - metallic), then ACES + sRGB
+    s0, s1 = gbuf[hit][:, 4:8], gbuf[hit][:, 8:12]
+    lin = s1[:, 2:3] * s0[:, 1:4] * (1 - s1[:, 0:1])
+    aces = np.clip(lin * (2.51 * lin + 0.03) / (lin * (2.43 * lin + 0.59) + 0.14), 0, 1)
+    srgb = np.where(aces < 0.0031308, aces * 12.92, 1.055 * aces ** (1 / 2.4) - 0.055)
+    np.testing.assert_allclose(rgba[hit][:, :3], srgb, rtol=1e-4, atol=1e-6)
+    assert np.all(rgba[hit][:, 3] == 1) and np.all(rgba[~hit] == 0) and np.all(depth[~hit] == 1)
+
+
+def test_trace_edge_semantics(oracle, S):
+    """Rays that miss the box get code -3; rays whose entry point is within 0.2 of leaving start at
+    camera + 0.2 dir and go out of bounds at once (material.frag:136-139,106-109)."""
+    g = np.load(os.path.join(GOLD, "trace_32_160x120.npz"))
+    codes = g["gbuf"][..., 3]
+    assert (codes == -3).mean() > 0.5
+    assert (codes == -2).sum() > 0
+    assert np.all(g["gbuf"][..., 15][codes == -3] == 0)
+    assert g["gbuf"][..., 15].max() <= 255
