@@ -84,6 +84,12 @@ int sdfgpu_slab(const sdfgpu_ctx* ctx, uint32_t* z_begin, uint32_t* z_end,
  * (SDFSurface::set_parameter, src/sdf/mod.rs:73). */
 int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes);
 
+/* Device-free check of the specialiser: validates `tape`, lowers it and compiles the straight-line
+ * fill kernel for its structure with NVRTC for sm_100a (what sdfgpu_set_tape + the first fill do on
+ * a GPU box).  On success `log` receives the generated translation unit, on failure the compiler
+ * log.  Returns SDFGPU_ERR_CUDA when NVRTC is not installed. */
+int sdfgpu_jit_check(const void* tape, size_t tape_bytes, int voxels_per_thread, char* log, size_t log_cap);
+
 /* SDFViewer::update (src/app/scene/sdf/mod.rs:128-217).
  *   changed_box : result of sdf.changed() this frame ({min,max}), or NULL for None;
  *                 merged into the pending box as :131-139 does.
@@ -216,8 +222,16 @@ int sdfgpu_sync(sdfgpu_ctx* ctx);
 void* sdfgpu_stream(sdfgpu_ctx* ctx);
 /* Kernels launched by this handle so far (bench.py's gpu_launches claim). */
 uint64_t sdfgpu_launch_count(const sdfgpu_ctx* ctx);
-/* Fill-kernel variant knobs (0 = library default); used by the benchmarks. */
+/* Fill-kernel knobs (0 = library default); used by the benchmarks and tests:
+ *   "fill_voxels_per_thread" 0|1|2|4|8   "fill_ctas_per_sm" 0..32   "streaming_stores" 0|1
+ *   "fill_halo" 0|1 (compute halo slices locally; 0 when the host exchanges them)
+ *   "fill_program" 0 auto (kernel specialised for the tape structure, else built-in demo program,
+ *                  else interpreter) | 1 interpreter | 2 built-in or interpreter | 3 specialised or fail */
 int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value);
+/* Introspection: "last_fill_program" (0 interpreter, 1 specialised/JIT, 2 built-in demo),
+ * "last_fill_ctas_per_sm", "last_fill_voxels_per_thread", "sm_count", "tape_image_bytes",
+ * "tape_culled", "jit_available". */
+int sdfgpu_get_info(const sdfgpu_ctx* ctx, const char* key, int64_t* value);
 
 #ifdef __cplusplus
 }

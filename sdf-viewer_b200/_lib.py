@@ -69,6 +69,7 @@ SIGNATURES = {
     "sdfgpu_dims": (C.c_int, [_vp, _u32p]),
     "sdfgpu_slab": (C.c_int, [_vp, _u32p, _u32p, _u32p, _u32p]),
     "sdfgpu_set_tape": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "sdfgpu_jit_check": (C.c_int, [_vp, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]),
     "sdfgpu_update": (C.c_int, [_vp, _fp, _u32, _u64p]),
     "sdfgpu_fill_all": (C.c_int, [_vp]),
     "sdfgpu_resample_box": (C.c_int, [_vp, _fp, _u64p]),
@@ -90,6 +91,7 @@ SIGNATURES = {
     "sdfgpu_stream": (_vp, [_vp]),
     "sdfgpu_launch_count": (_u64, [_vp]),
     "sdfgpu_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
+    "sdfgpu_get_info": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int64)]),
 }
 
 _lib = None

@@ -91,6 +91,8 @@ struct sdfgpu_ctx {
     unsigned char* img_dev = nullptr;
     size_t img_dev_cap = 0;
     TapeImageHeader hdr;
+    std::vector<uint32_t> opcodes;  // lowered opcode sequence = the tape's structure (JIT cache key)
+    bool structure_is_demo = false; // matches the built-in PROG_DEMO kernel
     std::vector<float> px, py, pz;  // host copies of the position tables
     float lut[256];
     // frame
@@ -105,7 +107,11 @@ struct sdfgpu_ctx {
     int opt_ctas = 0;       // CTAs per SM (0 = as many as fit)
     int opt_streaming = 1;  // st.global.cs
     int opt_fill_halo = 1;  // compute the halo slices locally (0: the host exchanges them)
-    size_t smem_prepared = 0;
+    int opt_program = 0;    // 0 auto (JIT, else built-in, else interpreter), 1 interpreter, 2 built-in, 3 JIT or fail
+    int cc_major = 0, cc_minor = 0;
+    int last_program = -1, last_ctas = 0, last_vpt = 0;
+    std::string jit_note;   // why the JIT was not used (if it was not)
+    size_t smem_prepared[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [V][interpreter | demo]
     uint64_t launches = 0;
     std::string err;
 };
@@ -162,7 +168,7 @@ uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
 void set_device(sdfgpu_ctx* ctx) { (void)cudaSetDevice(ctx->device); }
 
-int default_vpt(const sdfgpu_ctx* ctx) { return ctx->opt_vpt ? ctx->opt_vpt : ((ctx->hdr.flags & TAPE_FLAG_CULL) ? 8 : 2); }
+int default_vpt(const sdfgpu_ctx* ctx) { return ctx->opt_vpt ? ctx->opt_vpt : ((ctx->hdr.flags & TAPE_FLAG_CULL) ? 8 : 4); }
 
 // one fill launch over lattice {r0 + i*step} restricted to the index box [lo, hi) per axis
 int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_t hi[3], bool conditional,
@@ -198,18 +204,42 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
     const size_t smem = fill_smem_bytes(p.tape_img_bytes, n_cull, ctx->hdr.max_stack, V, &p.stack_floats);
     if (smem > 227u * 1024u)
         return fail(ctx, SDFGPU_ERR_TAPE, "tape needs %zu bytes of shared memory per CTA (limit 232448)", smem);
-    if (smem > ctx->smem_prepared) {
-        CK(ctx, fill_prepare(smem));
-        ctx->smem_prepared = smem;
-    }
-    int per_sm = fill_max_ctas_per_sm(V, smem);
-    if (per_sm < 1) return fail(ctx, SDFGPU_ERR_CUDA, "fill kernel does not fit on an SM (smem %zu)", smem);
-    if (ctx->opt_ctas > 0 && ctx->opt_ctas < per_sm) per_sm = ctx->opt_ctas;
+    // ---- pick the program: a kernel specialised for this tape structure (NVRTC), the built-in
+    // demo program, or the interpreter
     const uint64_t n_tiles = (uint64_t)p.tiles_x * p.tiles_y * p.tiles_z;
     if (n_tiles > 0xffffffffull) return fail(ctx, SDFGPU_ERR_INVALID, "grid too large for one launch");
+    void* jit_fn = nullptr;
+    int per_sm = 0, program = dev::PROG_INTERPRET;
+    if (ctx->opt_program == 0 || ctx->opt_program == 3) {
+        std::string why;
+        if (ctx->opcodes.size() > 96) why = "tape longer than 96 instructions";
+        else if (jit_get(ctx->device, ctx->cc_major, ctx->cc_minor, ctx->opcodes, V, smem, &jit_fn, &per_sm, &why))
+            program = dev::PROG_JIT;
+        if (program != dev::PROG_JIT) {
+            ctx->jit_note = why;
+            if (ctx->opt_program == 3) return fail(ctx, SDFGPU_ERR_CUDA, "JIT kernel unavailable: %s", why.c_str());
+        }
+    }
+    if (program != dev::PROG_JIT) {
+        if ((ctx->opt_program == 0 || ctx->opt_program == 2) && ctx->structure_is_demo) program = dev::PROG_DEMO;
+        const size_t prepared_key = smem;
+        if (prepared_key > ctx->smem_prepared[V == 1 ? 0 : V == 2 ? 1 : V == 4 ? 2 : 3][program == dev::PROG_DEMO]) {
+            CK(ctx, fill_prepare(V, program, smem));
+            ctx->smem_prepared[V == 1 ? 0 : V == 2 ? 1 : V == 4 ? 2 : 3][program == dev::PROG_DEMO] = smem;
+        }
+        per_sm = fill_max_ctas_per_sm(V, program, smem);
+        if (per_sm < 1) return fail(ctx, SDFGPU_ERR_CUDA, "fill kernel does not fit on an SM (smem %zu)", smem);
+    }
+    if (ctx->opt_ctas > 0 && ctx->opt_ctas < per_sm) per_sm = ctx->opt_ctas;
     uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    CK(ctx, launch_fill(p, V, (int)grid, smem, ctx->stream));
+    if (program == dev::PROG_JIT) {
+        std::string why;
+        if (!jit_launch(jit_fn, p, (int)grid, smem, ctx->stream, &why)) return fail(ctx, SDFGPU_ERR_CUDA, "%s", why.c_str());
+    } else {
+        CK(ctx, launch_fill(p, V, program, (int)grid, smem, ctx->stream));
+    }
+    ctx->last_program = program; ctx->last_ctas = per_sm; ctx->last_vpt = V;
     ctx->launches++;
     return SDFGPU_OK;
 }
@@ -273,6 +303,8 @@ int create_common(const float bb[6], const uint32_t voxels[3], uint32_t passes, 
         cudaError_t ce;
         if ((ce = cudaSetDevice(device)) != cudaSuccess ||
             (ce = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess ||
+            (ce = cudaDeviceGetAttribute(&ctx->cc_major, cudaDevAttrComputeCapabilityMajor, device)) != cudaSuccess ||
+            (ce = cudaDeviceGetAttribute(&ctx->cc_minor, cudaDevAttrComputeCapabilityMinor, device)) != cudaSuccess ||
             (ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
             (void)cudaGetLastError();
             rc = fail(nullptr, SDFGPU_ERR_CUDA, "device setup failed: %s", cudaGetErrorString(ce));
@@ -374,11 +406,25 @@ SDFGPU_API int sdfgpu_slab(const sdfgpu_ctx* ctx, uint32_t* z_begin, uint32_t* z
 
 // -------------------------------------------------------------------- tape
 
-SDFGPU_API int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes) {
-    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+namespace {
+
+struct ParsedTape {
+    sdft_header h;
+    std::vector<sdft_instr> low;  // lowered instructions (DeviceOp), operands kept
+    std::vector<sdft_prim> prims;
+    std::vector<float> consts;
+    std::vector<uint32_t> opcodes;  // the structure: lowered opcodes up to and including DOP_END
+    uint32_t max_stack = 0;
+    bool cull = false;
+    uint32_t cull_first = 0, cull_count = 0;
+};
+
+// Validate a public tape (sdfgpu_tape.h) and lower it to the device opcodes (sdfgpu_device_types.h
+// DeviceOp): primitive ops specialised by shape and material, stack ops by their static depth.
+int parse_and_lower(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes, ParsedTape* out) {
     if (!tape) return fail(ctx, SDFGPU_ERR_INVALID, "tape is NULL");
     if (tape_bytes < sizeof(sdft_header)) return fail(ctx, SDFGPU_ERR_TAPE, "tape shorter than its header");
-    sdft_header h;
+    sdft_header& h = out->h;
     memcpy(&h, tape, sizeof h);
     if (h.magic != SDFT_MAGIC) return fail(ctx, SDFGPU_ERR_TAPE, "bad tape magic 0x%08x", h.magic);
     if (h.version != SDFT_VERSION) return fail(ctx, SDFGPU_ERR_TAPE, "unsupported tape version %u", h.version);
@@ -389,77 +435,109 @@ SDFGPU_API int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_by
                         (size_t)h.n_prims * sizeof(sdft_prim) + (size_t)h.n_consts * 4;
     if (need > tape_bytes) return fail(ctx, SDFGPU_ERR_TAPE, "tape truncated: %zu bytes needed, %zu given", need, tape_bytes);
     std::vector<sdft_instr> instr(h.n_instr);
-    std::vector<sdft_prim> prims(h.n_prims);
-    std::vector<float> consts(h.n_consts);
+    out->prims.resize(h.n_prims);
+    out->consts.resize(h.n_consts);
+    const std::vector<sdft_prim>& prims = out->prims;
     const unsigned char* b = (const unsigned char*)tape + sizeof h;
     if (h.n_instr) memcpy(instr.data(), b, instr.size() * sizeof(sdft_instr));
     b += instr.size() * sizeof(sdft_instr);
-    if (h.n_prims) memcpy(prims.data(), b, prims.size() * sizeof(sdft_prim));
+    if (h.n_prims) memcpy(out->prims.data(), b, prims.size() * sizeof(sdft_prim));
     b += prims.size() * sizeof(sdft_prim);
-    if (h.n_consts) memcpy(consts.data(), b, consts.size() * 4);
+    if (h.n_consts) memcpy(out->consts.data(), b, out->consts.size() * 4);
 
-    // ---- validate: operands in range, stack balanced
-    uint32_t sp = 0, max_sp = 0, n_ranges = 0, cull_first = 0, cull_count = 0;
-    bool p_clean = true, cull_ok = false;
-    for (uint32_t pc = 0; pc < h.n_instr; ++pc) {
-        const sdft_instr& I = instr[pc];
-        bool end = false;
-        switch (I.op) {
-            case SDFT_OP_END: end = true; break;
-            case SDFT_OP_PRIM: case SDFT_OP_UNION_PRIM: case SDFT_OP_INTER_PRIM:
-                if (I.a >= h.n_prims) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: primitive %u out of range", pc, I.a);
-                break;
-            case SDFT_OP_UNION_RANGE:
-                if (I.b < 1 || (uint64_t)I.a + I.b > h.n_prims)
-                    return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: primitive range [%u,+%u) out of range", pc, I.a, I.b);
-                ++n_ranges;
-                cull_first = I.a; cull_count = I.b; cull_ok = p_clean;
-                break;
-            case SDFT_OP_PUSH:
-                if (sp >= SDFT_MAX_STACK) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: stack overflow", pc);
-                ++sp; if (sp > max_sp) max_sp = sp;
-                break;
-            case SDFT_OP_POP_UNION: case SDFT_OP_POP_INTER:
-                if (sp == 0) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: stack underflow", pc);
-                --sp;
-                break;
-            case SDFT_OP_POP_DEMO_DIFF:
-                if (sp == 0) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: stack underflow", pc);
-                if ((uint64_t)I.a + 7 > h.n_consts) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: constants out of range", pc);
-                --sp;
-                break;
-            case SDFT_OP_D_NEG: case SDFT_OP_D_ABS: case SDFT_OP_D_ADD: case SDFT_OP_D_MUL: case SDFT_OP_D_MAX:
-            case SDFT_OP_D_MIN: break;
-            case SDFT_OP_M_SET:
-                if ((uint64_t)I.a + 6 > h.n_consts) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: constants out of range", pc);
-                break;
-            case SDFT_OP_P_RESET: p_clean = true; break;
-            case SDFT_OP_P_SUB:
-                if ((uint64_t)I.a + 3 > h.n_consts) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: constants out of range", pc);
-                p_clean = false;
-                break;
-            case SDFT_OP_P_MUL: case SDFT_OP_P_ABS: p_clean = false; break;
-            default: return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: unknown op %u", pc, I.op);
-        }
-        if (end) break;
-    }
     for (uint32_t k = 0; k < h.n_prims; ++k) {
         const uint32_t shape = prims[k].kind & 0xffu, mat = (prims[k].kind >> 8) & 0xffu;
         if (shape > SDFT_SHAPE_BOX_LINF || mat > SDFT_MAT_NORMAL || (prims[k].kind >> 16) != 0)
             return fail(ctx, SDFGPU_ERR_TAPE, "primitive %u: unknown kind 0x%x", k, prims[k].kind);
     }
 
+    // ---- validate (operands in range, stack balanced) and lower in one walk
+    out->low = instr;
+    uint32_t depth = 0, max_depth = 0, n_ranges = 0;
+    bool p_clean = true, cull_ok = false, ended = false;
+    for (uint32_t pc = 0; pc < h.n_instr && !ended; ++pc) {
+        const sdft_instr& S = instr[pc];
+        sdft_instr& I = out->low[pc];
+        switch (S.op) {
+            case SDFT_OP_END: I.op = DOP_END; ended = true; break;
+            case SDFT_OP_PRIM: case SDFT_OP_UNION_PRIM: case SDFT_OP_INTER_PRIM: {
+                if (S.a >= h.n_prims) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: primitive %u out of range", pc, S.a);
+                const uint32_t mode = S.op - SDFT_OP_PRIM;
+                const uint32_t shape = prims[S.a].kind & 0xffu, mat = (prims[S.a].kind >> 8) & 0xffu;
+                I.op = DOP_PRIM + mode * 6 + shape * 3 + mat;
+                break;
+            }
+            case SDFT_OP_UNION_RANGE:
+                if (S.b < 1 || (uint64_t)S.a + S.b > h.n_prims)
+                    return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: primitive range [%u,+%u) out of range", pc, S.a, S.b);
+                I.op = DOP_UNION_RANGE;
+                ++n_ranges;
+                out->cull_first = S.a; out->cull_count = S.b; cull_ok = p_clean;
+                break;
+            case SDFT_OP_PUSH:
+                if (depth >= SDFT_MAX_STACK) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: stack overflow", pc);
+                if (depth == 0) { I.op = DOP_PUSH_REG; I.b = 0; }
+                else { I.op = DOP_PUSH_MEM; I.b = depth - 1; }
+                ++depth;
+                if (depth > max_depth) max_depth = depth;
+                break;
+            case SDFT_OP_POP_UNION: case SDFT_OP_POP_INTER: case SDFT_OP_POP_DEMO_DIFF: {
+                if (depth == 0) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: stack underflow", pc);
+                if (S.op == SDFT_OP_POP_DEMO_DIFF && (uint64_t)S.a + 7 > h.n_consts)
+                    return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: constants out of range", pc);
+                const uint32_t kind = S.op - SDFT_OP_POP_UNION;
+                --depth;
+                if (depth == 0) { I.op = DOP_POP_UNION + kind; I.b = 0; }
+                else { I.op = DOP_POP_UNION_MEM + kind; I.b = depth - 1; }
+                break;
+            }
+            case SDFT_OP_D_NEG: I.op = DOP_D_NEG; break;
+            case SDFT_OP_D_ABS: I.op = DOP_D_ABS; break;
+            case SDFT_OP_D_ADD: I.op = DOP_D_ADD; break;
+            case SDFT_OP_D_MUL: I.op = DOP_D_MUL; break;
+            case SDFT_OP_D_MAX: I.op = DOP_D_MAX; break;
+            case SDFT_OP_D_MIN: I.op = DOP_D_MIN; break;
+            case SDFT_OP_M_SET:
+                if ((uint64_t)S.a + 6 > h.n_consts) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: constants out of range", pc);
+                I.op = DOP_M_SET;
+                break;
+            case SDFT_OP_P_RESET: I.op = DOP_P_RESET; p_clean = true; break;
+            case SDFT_OP_P_SUB:
+                if ((uint64_t)S.a + 3 > h.n_consts) return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: constants out of range", pc);
+                I.op = DOP_P_SUB; p_clean = false;
+                break;
+            case SDFT_OP_P_MUL: I.op = DOP_P_MUL; p_clean = false; break;
+            case SDFT_OP_P_ABS: I.op = DOP_P_ABS; p_clean = false; break;
+            default: return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: unknown op %u", pc, S.op);
+        }
+        out->opcodes.push_back(I.op);
+    }
+    if (!ended) out->opcodes.push_back(DOP_END);
+    out->max_stack = max_depth;
+    out->cull = n_ranges == 1 && cull_ok && out->cull_count >= 16;
+    return SDFGPU_OK;
+}
+
+}  // namespace
+
+SDFGPU_API int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    ParsedTape pt;
+    const int prc = parse_and_lower(ctx, tape, tape_bytes, &pt);
+    if (prc != SDFGPU_OK) return prc;
+    const sdft_header& h = pt.h;
+
     // ---- build the shared-memory image
     TapeImageHeader ih;
     memset(&ih, 0, sizeof ih);
     ih.n_instr = h.n_instr; ih.n_prims = h.n_prims; ih.n_consts = h.n_consts;
-    ih.max_stack = max_sp;
-    if (n_ranges == 1 && cull_ok && cull_count >= 16) {
+    ih.max_stack = pt.max_stack;
+    if (pt.cull) {
         ih.flags |= TAPE_FLAG_CULL;
-        ih.cull_first = cull_first; ih.cull_count = cull_count;
+        ih.cull_first = pt.cull_first; ih.cull_count = pt.cull_count;
     }
     uint32_t off = sizeof(TapeImageHeader);
-    ih.off_instr = off; off += (h.n_instr + 1u) * 16u;  // + a terminating DOP_END
+    ih.off_instr = off; off += (h.n_instr + 1u) * 16u;  // + a terminating DOP_END (zero-initialised slot)
     ih.off_geom = off; off += h.n_prims * 16u;
     ih.off_mat0 = off; off += h.n_prims * 16u;
     ih.off_mat1 = off; off += h.n_prims * 16u;
@@ -472,54 +550,9 @@ SDFGPU_API int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_by
         return fail(ctx, SDFGPU_ERR_TAPE, "tape image is %u bytes; the fill kernel stages at most 204800 in shared memory", off);
     std::vector<unsigned char> img(off, 0);
     memcpy(img.data(), &ih, sizeof ih);
-    {   // lower to the device opcodes (sdfgpu_internal.h DeviceOp): primitive ops specialised by shape and
-        // material, stack ops by (static) depth.  Operand fields keep their meaning; `b` of the
-        // stack ops becomes the shared-memory level to spill / reload.
-        std::vector<sdft_instr> low(instr);
-        uint32_t depth = 0;
-        for (uint32_t pc = 0; pc < h.n_instr; ++pc) {
-            sdft_instr& I = low[pc];
-            bool end = false;
-            switch (instr[pc].op) {
-                case SDFT_OP_END: I.op = DOP_END; end = true; break;
-                case SDFT_OP_PRIM: case SDFT_OP_UNION_PRIM: case SDFT_OP_INTER_PRIM: {
-                    const uint32_t mode = instr[pc].op - SDFT_OP_PRIM;
-                    const uint32_t shape = prims[I.a].kind & 0xffu, mat = (prims[I.a].kind >> 8) & 0xffu;
-                    I.op = DOP_PRIM + mode * 6 + shape * 3 + mat;
-                    break;
-                }
-                case SDFT_OP_UNION_RANGE: I.op = DOP_UNION_RANGE; break;
-                case SDFT_OP_PUSH:
-                    if (depth == 0) { I.op = DOP_PUSH_REG; I.b = 0; }
-                    else { I.op = DOP_PUSH_MEM; I.b = depth - 1; }
-                    ++depth;
-                    break;
-                case SDFT_OP_POP_UNION: case SDFT_OP_POP_INTER: case SDFT_OP_POP_DEMO_DIFF: {
-                    const uint32_t kind = instr[pc].op - SDFT_OP_POP_UNION;
-                    --depth;
-                    if (depth == 0) { I.op = DOP_POP_UNION + kind; I.b = 0; }
-                    else { I.op = DOP_POP_UNION_MEM + kind; I.b = depth - 1; }
-                    break;
-                }
-                case SDFT_OP_D_NEG: I.op = DOP_D_NEG; break;
-                case SDFT_OP_D_ABS: I.op = DOP_D_ABS; break;
-                case SDFT_OP_D_ADD: I.op = DOP_D_ADD; break;
-                case SDFT_OP_D_MUL: I.op = DOP_D_MUL; break;
-                case SDFT_OP_D_MAX: I.op = DOP_D_MAX; break;
-                case SDFT_OP_D_MIN: I.op = DOP_D_MIN; break;
-                case SDFT_OP_M_SET: I.op = DOP_M_SET; break;
-                case SDFT_OP_P_RESET: I.op = DOP_P_RESET; break;
-                case SDFT_OP_P_SUB: I.op = DOP_P_SUB; break;
-                case SDFT_OP_P_MUL: I.op = DOP_P_MUL; break;
-                case SDFT_OP_P_ABS: I.op = DOP_P_ABS; break;
-            }
-            if (end) break;
-        }
-        if (h.n_instr) memcpy(img.data() + ih.off_instr, low.data(), h.n_instr * 16u);
-        // the interpreter stops at DOP_END: one is always appended (the slot is zero-initialised = DOP_END)
-    }
+    if (h.n_instr) memcpy(img.data() + ih.off_instr, pt.low.data(), h.n_instr * 16u);
     for (uint32_t k = 0; k < h.n_prims; ++k) {
-        const sdft_prim& pr = prims[k];
+        const sdft_prim& pr = pt.prims[k];
         const float g[4] = {pr.center[0], pr.center[1], pr.center[2], pr.size};
         const float m0[4] = {pr.color[0], pr.color[1], pr.color[2], pr.metallic};
         float m1[4] = {pr.roughness, pr.occlusion, pr.air_skip, 0.0f};
@@ -528,7 +561,7 @@ SDFGPU_API int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_by
         memcpy(img.data() + ih.off_mat0 + 16u * k, m0, 16);
         memcpy(img.data() + ih.off_mat1 + 16u * k, m1, 16);
     }
-    if (h.n_consts) memcpy(img.data() + ih.off_consts, consts.data(), h.n_consts * 4u);
+    if (h.n_consts) memcpy(img.data() + ih.off_consts, pt.consts.data(), h.n_consts * 4u);
     memcpy(img.data() + ih.off_lut, ctx->lut, 1024);
     if (ctx->dims[0]) memcpy(img.data() + ih.off_px, ctx->px.data(), ctx->dims[0] * 4u);
     if (ctx->dims[1]) memcpy(img.data() + ih.off_py, ctx->py.data(), ctx->dims[1] * 4u);
@@ -548,8 +581,29 @@ SDFGPU_API int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_by
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->img_host.swap(img);
     ctx->hdr = ih;
+    ctx->opcodes.swap(pt.opcodes);
+    const uint32_t demo_ops[] = {DOP_PRIM + 0 * 6 + SDFT_SHAPE_BOX_LINF * 3 + SDFT_MAT_BRICK, DOP_PUSH_REG,
+                                 DOP_PRIM + 0 * 6 + SDFT_SHAPE_SPHERE * 3 + SDFT_MAT_NORMAL, DOP_POP_DEMO_DIFF, DOP_END};
+    ctx->structure_is_demo = ctx->opcodes.size() == 5 && !memcmp(ctx->opcodes.data(), demo_ops, sizeof demo_ops);
     ctx->has_tape = true;
     return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_jit_check(const void* tape, size_t tape_bytes, int voxels_per_thread, char* log, size_t log_cap) {
+    if (log && log_cap) log[0] = '\0';
+    ParsedTape pt;
+    const int prc = parse_and_lower(nullptr, tape, tape_bytes, &pt);
+    if (prc != SDFGPU_OK) return prc;
+    if (voxels_per_thread != 1 && voxels_per_thread != 2 && voxels_per_thread != 4 && voxels_per_thread != 8)
+        return fail(nullptr, SDFGPU_ERR_INVALID, "voxels_per_thread must be 1, 2, 4 or 8");
+    std::vector<char> cubin;
+    std::string err;
+    if (!jit_compile(pt.opcodes, voxels_per_thread, 10, 0, &cubin, &err)) {
+        if (log && log_cap) snprintf(log, log_cap, "%s", err.c_str());
+        return fail(nullptr, SDFGPU_ERR_CUDA, "%s", err.c_str());
+    }
+    if (log && log_cap) snprintf(log, log_cap, "%s", jit_source(pt.opcodes, voxels_per_thread).c_str());
+    return (int)cubin.size() > 0 ? SDFGPU_OK : SDFGPU_ERR_CUDA;
 }
 
 // -------------------------------------------------------------------- fill
@@ -958,8 +1012,24 @@ SDFGPU_API int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value
         ctx->opt_streaming = value != 0;
     } else if (!strcmp(key, "fill_halo")) {
         ctx->opt_fill_halo = value != 0;
+    } else if (!strcmp(key, "fill_program")) {
+        if (value < 0 || value > 3) return fail(ctx, SDFGPU_ERR_INVALID, "fill_program must be 0..3");
+        ctx->opt_program = (int)value;
     } else {
         return fail(ctx, SDFGPU_ERR_INVALID, "unknown option '%s'", key);
     }
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_get_info(const sdfgpu_ctx* ctx, const char* key, int64_t* value) {
+    if (!ctx || !key || !value) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL argument");
+    if (!strcmp(key, "last_fill_program")) *value = ctx->last_program;
+    else if (!strcmp(key, "last_fill_ctas_per_sm")) *value = ctx->last_ctas;
+    else if (!strcmp(key, "last_fill_voxels_per_thread")) *value = ctx->last_vpt;
+    else if (!strcmp(key, "sm_count")) *value = ctx->sm_count;
+    else if (!strcmp(key, "tape_image_bytes")) *value = (int64_t)ctx->img_host.size();
+    else if (!strcmp(key, "tape_culled")) *value = (ctx->hdr.flags & TAPE_FLAG_CULL) ? 1 : 0;
+    else if (!strcmp(key, "jit_available")) { std::string why; *value = jit_available(&why) ? 1 : 0; }
+    else return fail(nullptr, SDFGPU_ERR_INVALID, "unknown info key '%s'", key);
     return SDFGPU_OK;
 }

@@ -1,551 +1,17 @@
-// fill.cu -- the grid-fill kernel: SDFViewer::update's inner loop
-// (/root/reference/src/app/scene/sdf/mod.rs:173-215) for a whole LoadingManager
-// pass (src/app/scene/sdf/loading.rs:50-76) in one launch.
-//
-// Shape: persistent CTAs (grid = SMs x resident CTAs), 256 threads = 8 warps.
-// A tile is 32 (x) x 8 (y) x V (z) lattice points: a warp owns one x-row of 32
-// consecutive voxels, so each of its two stores per voxel (tex0, tex1: one
-// float4 each) is one 512-byte contiguous burst = four full 128-byte lines.
-// The tape image (instructions, primitive table, constants, sRGB LUT, per-axis
-// position tables) is staged into shared memory once per CTA with a TMA bulk
-// copy (cp.async.bulk + mbarrier).  Every warp walks the tape in lock step
-// (the tape is the same for all voxels, so instruction fetch never diverges).
-//
-// Arithmetic: IEEE binary32, one rounding per operation.  This file is
-// compiled with -fmad=false -prec-div=true -prec-sqrt=true -ftz=false: the
-// reference is Rust/WASM f32, which never fuses a multiply-add.
-//
-// Algorithmic bytes: 32 B written per sampled voxel (16 B tex0 + 16 B tex1);
-// conditional passes also read the 4-byte tex0.r of each visited voxel.
-#include <stdio.h>
-
+// fill.cu -- ahead-of-time instances of the grid-fill kernel (device code: fill_device.cuh):
+// the tape interpreter (any tape) and the built-in straight-line program for the structure of the
+// reference's own SDFDemo (/root/reference/src/sdf/demo/mod.rs:51-75).  Kernels specialised for
+// other tape structures are compiled from the same device source at set_tape time (jit.cu).
+#include "fill_device.cuh"
 #include "sdfgpu_internal.h"
 
 namespace sdfgpu {
 namespace {
 
-struct Smp {  // SDFSample, src/sdf/mod.rs:104-118
-    float d, r, g, b, m, ro, o;
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// ------------------------------------------------------------ TMA bulk copy
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
-// ------------------------------------------------------- exact f32 helpers
-// fmodf(x, 0.5) and fmodf(x, 0.25) for x >= 0 (`%` in cube.rs:192).  Exact: x*2 and
-// trunc()*0.5 are exact scalings and the final subtraction yields fmod's (always
-// representable) result.  Floats >= 2^24 are multiples of 0.5; inf/NaN give NaN.
-__device__ __forceinline__ float fmod_p5(float x) {
-    if (!(x < 16777216.0f)) return x * 0.0f;
-    return x - truncf(x * 2.0f) * 0.5f;
-}
-__device__ __forceinline__ float fmod_p25(float x) {
-    if (!(x < 8388608.0f)) return x * 0.0f;
-    return x - truncf(x * 4.0f) * 0.25f;
-}
-// f32::signum: +-1 with the sign bit of x, NaN for NaN (cube.rs:168)
-__device__ __forceinline__ float rust_signum(float x) { return (x != x) ? x : copysignf(1.0f, x); }
-
-// sample_brick_texture, src/sdf/demo/cube.rs:181-222
-__device__ __forceinline__ void brick_texture(float px, float py, float pz, float nx, float ny, float nz, Smp& s) {
-    float u, v;
-    const float ax = fabsf(nx), ay = fabsf(ny), az = fabsf(nz);
-    if (ax > ay) {  // :206
-        if (ax > az) { u = pz; v = py; } else { u = px; v = py; }
-    } else if (ay > az) {  // :214
-        u = pz; v = px;
-    } else {
-        u = px; v = py;
-    }
-    const float row_num = v * 4.0f;                    // v / BRICK_HEIGHT (0.25): exact either way
-    const float brick_offset = floorf(row_num) * 0.25f;  // / 4.
-    const float bx = fmod_p5(fabsf(u + brick_offset));
-    const float by = fmod_p25(fabsf(v));
-    const float max_cement = 0.2f / 2.0f * 0.25f;
-    const bool cement = bx < max_cement || bx > 0.5f - max_cement || by < max_cement || by > 0.25f - max_cement;
-    s.r = cement ? 56.f / 255.f : 150.f / 255.f;
-    s.g = cement ? 70.f / 255.f : 24.f / 255.f;
-    s.b = cement ? 60.f / 255.f : 10.f / 255.f;
-    s.m = cement ? 0.4f : 0.2f;
-    s.ro = cement ? 0.5f : 0.8f;
-    s.o = cement ? 1.0f : 0.0f;
-}
-
-// distance of one primitive; q = p - centre.  sphere.rs:39 (cgmath magnitude: x*x + y*y + z*z
-// summed left to right), cube.rs:81 (f32::max chain)
-__device__ __forceinline__ float prim_distance(uint32_t shape, float qx, float qy, float qz, float size) {
-    if (shape == SDFT_SHAPE_SPHERE) return sqrtf(qx * qx + qy * qy + qz * qz) - size;
-    return fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) - size;
-}
-
-// One primitive with its material: SDFDemoCube::sample / SDFDemoSphere::sample
-// (cube.rs:79-89, sphere.rs:37-47) generalised by the record's fields; shape and material are
-// compile-time here (the lowered opcode carries them).
-template <int SHAPE, int MAT>
-__device__ __forceinline__ Smp prim_sample(const float4 geom, const float4 m0, const float4 m1, float px, float py,
-                                           float pz) {
-    const float qx = px - geom.x, qy = py - geom.y, qz = pz - geom.z;
-    Smp s;
-    float len = 0.0f;
-    if (SHAPE == SDFT_SHAPE_SPHERE) {
-        len = sqrtf(qx * qx + qy * qy + qz * qz);
-        s.d = len - geom.w;
-    } else {
-        s.d = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) - geom.w;
-    }
-    s.r = s.g = s.b = s.m = s.ro = s.o = 0.0f;
-    if (!(s.d > m1.z)) {  // "the air has no texture" shortcut, cube.rs:83-85
-        if (MAT == SDFT_MAT_FLAT) {
-            s.r = m0.x; s.g = m0.y; s.b = m0.z; s.m = m0.w; s.ro = m1.x; s.o = m1.y;
-        } else {
-            float nx, ny, nz;
-            if (SHAPE == SDFT_SHAPE_SPHERE) {  // cgmath normalize = v * (1 / |v|), sphere.rs:123
-                const float inv = 1.0f / len;
-                nx = qx * inv; ny = qy * inv; nz = qz * inv;
-            } else {  // cube.rs:164-177
-                nx = fabsf(qx) > geom.w ? rust_signum(qx) : 0.0f;
-                ny = fabsf(qy) > geom.w ? rust_signum(qy) : 0.0f;
-                nz = fabsf(qz) > geom.w ? rust_signum(qz) : 0.0f;
-            }
-            if (MAT == SDFT_MAT_BRICK) {
-                brick_texture(qx, qy, qz, nx, ny, nz, s);
-            } else {  // Material::Normal, cube.rs:56
-                s.r = fabsf(nx); s.g = fabsf(ny); s.b = fabsf(nz);
-            }
-        }
-    }
-    return s;
-}
-
-// runtime (shape, material): used once per voxel after a UNION_RANGE fold
-__device__ __forceinline__ Smp prim_sample_rt(const float4 g, const float4 m0, const float4 m1, float px, float py,
-                                              float pz) {
-    const uint32_t kind = __float_as_uint(m1.w);
-    switch (((kind & 0xffu) ? 3u : 0u) + ((kind >> 8) & 0xffu)) {
-        case 0: return prim_sample<SDFT_SHAPE_SPHERE, SDFT_MAT_FLAT>(g, m0, m1, px, py, pz);
-        case 1: return prim_sample<SDFT_SHAPE_SPHERE, SDFT_MAT_BRICK>(g, m0, m1, px, py, pz);
-        case 2: return prim_sample<SDFT_SHAPE_SPHERE, SDFT_MAT_NORMAL>(g, m0, m1, px, py, pz);
-        case 3: return prim_sample<SDFT_SHAPE_BOX_LINF, SDFT_MAT_FLAT>(g, m0, m1, px, py, pz);
-        case 4: return prim_sample<SDFT_SHAPE_BOX_LINF, SDFT_MAT_BRICK>(g, m0, m1, px, py, pz);
-        default: return prim_sample<SDFT_SHAPE_BOX_LINF, SDFT_MAT_NORMAL>(g, m0, m1, px, py, pz);
-    }
-}
-
-// MODE 0: A = y;  1: A = union(A, y) = (y.d < A.d) ? y : A;  2: A = intersect(A, y) = (y.d > A.d) ? y : A
-template <int V, int MODE, int SHAPE, int MAT>
-__device__ __forceinline__ void op_prim(Smp (&A)[V], const float4 g, const float4 m0, const float4 m1,
-                                        const float (&qx)[V], const float (&qy)[V], const float (&qz)[V]) {
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        const Smp y = prim_sample<SHAPE, MAT>(g, m0, m1, qx[v], qy[v], qz[v]);
-        if (MODE == 0) A[v] = y;
-        else if (MODE == 1) { if (y.d < A[v].d) A[v] = y; }
-        else { if (y.d > A[v].d) A[v] = y; }
-    }
-}
-
-// `Srgba::from(Vector3<f32>)`: (c * 255.0) as u8 -- saturating, NaN -> 0 (scene/sdf/mod.rs:201)
-__device__ __forceinline__ uint32_t f32_to_u8_sat(float c) { return min(__float2uint_rz(c * 255.0f), 255u); }
-
-__device__ __forceinline__ void store_texel(float4* p, float4 v, bool streaming) {
-    if (streaming) __stcs(p, v); else *p = v;
-}
-
-// ------------------------------------------------------------------ kernel
-__device__ __forceinline__ void stack_store(float* st, const Smp& s) {
-    constexpr int NT = FILL_THREADS;
-    st[0 * NT] = s.d; st[1 * NT] = s.r; st[2 * NT] = s.g; st[3 * NT] = s.b;
-    st[4 * NT] = s.m; st[5 * NT] = s.ro; st[6 * NT] = s.o;
-}
-__device__ __forceinline__ void stack_load(const float* st, Smp& s) {
-    constexpr int NT = FILL_THREADS;
-    s.d = st[0 * NT]; s.r = st[1 * NT]; s.g = st[2 * NT]; s.b = st[3 * NT];
-    s.m = st[4 * NT]; s.ro = st[5 * NT]; s.o = st[6 * NT];
-}
-
-// B = popped sample (pushed first), A = accumulator.  KIND 0 union, 1 intersect, 2 SDFDemo combinator
-template <int KIND>
-__device__ __forceinline__ void op_pop(Smp& A, const Smp& B, const float* c) {
-    if (KIND == 0) {
-        if (!(A.d < B.d)) A = B;
-    } else if (KIND == 1) {
-        if (!(A.d > B.d)) A = B;
-    } else {  // SDFDemo::sample, demo/mod.rs:58-73; B = box, A = sphere
-        const float dist = fmaxf(B.d, -A.d);                 // :58
-        const float inter = fabsf(B.d) - fabsf(A.d);         // :60
-        Smp s = (inter < 0.0f) ? B : A;                      // :61
-        if (fabsf(inter) <= c[0]) {                          // :62
-            s.r = c[1]; s.g = c[2]; s.b = c[3]; s.m = c[4]; s.ro = c[5]; s.o = c[6];
-        }
-        s.d = dist;                                          // :72
-        A = s;
-    }
-}
-
-// V = voxels per thread along z (lattice units).  MINB = CTAs per SM the register budget aims at.
-template <int V, int MINB>
+// MINB = CTAs per SM the register allocation aims at (V voxels per thread need ~ 30 + 25 V registers)
+template <int V, int PROG, int MINB>
 __global__ void __launch_bounds__(FILL_THREADS, MINB) fill_kernel(const FillParams P) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int NT = FILL_THREADS;
-
-    // ---- stage the tape image: one elected thread issues the bulk copy
-    const uint32_t img_bytes = P.tape_img_bytes;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + img_bytes);  // img_bytes is a multiple of 16
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, img_bytes);
-        for (uint32_t off = 0; off < img_bytes; off += 32768u) {
-            const uint32_t n = min(32768u, img_bytes - off);
-            bulk_g2s(smem + off, P.tape_img + off, n, bar);
-        }
-    }
-    __syncthreads();
-    mbar_wait(bar, 0);
-
-    const TapeImageHeader* hdr = reinterpret_cast<const TapeImageHeader*>(smem);
-    const uint4* s_instr = reinterpret_cast<const uint4*>(smem + hdr->off_instr);
-    const float4* s_geom = reinterpret_cast<const float4*>(smem + hdr->off_geom);
-    const float4* s_mat0 = reinterpret_cast<const float4*>(smem + hdr->off_mat0);
-    const float4* s_mat1 = reinterpret_cast<const float4*>(smem + hdr->off_mat1);
-    const float* s_consts = reinterpret_cast<const float*>(smem + hdr->off_consts);
-    const float* s_lut = reinterpret_cast<const float*>(smem + hdr->off_lut);
-    const float* s_px = reinterpret_cast<const float*>(smem + hdr->off_px);
-    const float* s_py = reinterpret_cast<const float*>(smem + hdr->off_py);
-    const float* s_pz = reinterpret_cast<const float*>(smem + hdr->off_pz);
-
-    // scratch after the image: [16 B bar][32 B reduce][32 B counts][cull list u32 x n_cull][stack floats]
-    float* s_red = reinterpret_cast<float*>(smem + img_bytes + 16);
-    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem + img_bytes + 16 + 32);
-    uint32_t* s_list = reinterpret_cast<uint32_t*>(smem + img_bytes + 16 + 64);
-    const uint32_t n_cull = (hdr->flags & TAPE_FLAG_CULL) ? hdr->cull_count : 0u;
-    const uint32_t cull_first = hdr->cull_first;
-    float* s_stack = reinterpret_cast<float*>(smem + img_bytes + 16 + 64 + ((n_cull * 4u + 15u) & ~15u)) + threadIdx.x;
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t n_tiles = P.tiles_x * P.tiles_y * P.tiles_z;
-    const size_t slice = (size_t)P.W * P.H;
-    uint32_t touched_local = 0;
-
-    // tile -> (tx, ty, tz), x fastest; advanced incrementally by gridDim.x per iteration
-    uint32_t tx = blockIdx.x % P.tiles_x, ty = (blockIdx.x / P.tiles_x) % P.tiles_y,
-             tz = blockIdx.x / (P.tiles_x * P.tiles_y);
-    const uint32_t sx = gridDim.x % P.tiles_x, sy = (gridDim.x / P.tiles_x) % P.tiles_y,
-                   sz = gridDim.x / (P.tiles_x * P.tiles_y);
-
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- per-tile culling of the UNION_RANGE (exact-safe: a primitive is dropped only if
-        // its lower bound over the tile exceeds some other primitive's upper bound)
-        uint32_t list_n = 0;
-        if (n_cull) {
-            __syncthreads();  // previous tile's readers of s_list are done
-            const uint32_t lx0 = tx * FILL_TILE_X, ly0 = ty * FILL_TILE_Y, lz0 = tz * V;
-            const uint32_t lx1 = min(lx0 + FILL_TILE_X, P.nx) - 1, ly1 = min(ly0 + FILL_TILE_Y, P.ny) - 1,
-                           lz1 = min(lz0 + V, P.nz) - 1;
-            const float ax = s_px[P.rx0 + lx0 * P.step], bx = s_px[P.rx0 + lx1 * P.step];
-            const float ay = s_py[P.ry0 + ly0 * P.step], by = s_py[P.ry0 + ly1 * P.step];
-            const float az = s_pz[P.rz0 + lz0 * P.step], bz = s_pz[P.rz0 + lz1 * P.step];
-            const float lox = fminf(ax, bx), hix = fmaxf(ax, bx);
-            const float loy = fminf(ay, by), hiy = fmaxf(ay, by);
-            const float loz = fminf(az, bz), hiz = fmaxf(az, bz);
-            const float EPS = 1e-5f;
-            // pass 1: U = min over primitives of the upper bound
-            float umin = __int_as_float(0x7f800000);
-            for (uint32_t k = threadIdx.x; k < n_cull; k += NT) {
-                const float4 g = s_geom[cull_first + k];
-                const uint32_t shape = __float_as_uint(s_mat1[cull_first + k].w) & 0xffu;
-                const float fx = fmaxf(fabsf(lox - g.x), fabsf(hix - g.x));
-                const float fy = fmaxf(fabsf(loy - g.y), fabsf(hiy - g.y));
-                const float fz = fmaxf(fabsf(loz - g.z), fabsf(hiz - g.z));
-                float ub = (shape == SDFT_SHAPE_SPHERE) ? sqrtf(fx * fx + fy * fy + fz * fz) : fmaxf(fmaxf(fx, fy), fz);
-                ub = ub - g.w;
-                ub = ub + EPS * (1.0f + fabsf(ub));
-                umin = fminf(umin, ub);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-            if (lane == 0) s_red[warp] = umin;
-            __syncthreads();
-            float U = s_red[0];
-#pragma unroll
-            for (int w = 1; w < NT / 32; ++w) U = fminf(U, s_red[w]);
-            // pass 2: ordered compaction of the survivors (index order keeps the tie rule)
-            uint32_t base = 0;
-            for (uint32_t k0 = 0; k0 < n_cull; k0 += NT) {
-                const uint32_t k = k0 + threadIdx.x;
-                bool keep = false;
-                if (k < n_cull) {
-                    const float4 g = s_geom[cull_first + k];
-                    const uint32_t shape = __float_as_uint(s_mat1[cull_first + k].w) & 0xffu;
-                    const float nx_ = fmaxf(fmaxf(lox - g.x, g.x - hix), 0.0f);
-                    const float ny_ = fmaxf(fmaxf(loy - g.y, g.y - hiy), 0.0f);
-                    const float nz_ = fmaxf(fmaxf(loz - g.z, g.z - hiz), 0.0f);
-                    float lb = (shape == SDFT_SHAPE_SPHERE) ? sqrtf(nx_ * nx_ + ny_ * ny_ + nz_ * nz_)
-                                                            : fmaxf(fmaxf(nx_, ny_), nz_);
-                    lb = lb - g.w;
-                    lb = lb - EPS * (1.0f + fabsf(lb));
-                    keep = !(lb > U);  // NaN bounds keep the primitive
-                }
-                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-                if (lane == 0) s_cnt[warp] = __popc(bal);
-                __syncthreads();
-                uint32_t wbase = base, total = 0;
-#pragma unroll
-                for (int w = 0; w < NT / 32; ++w) {
-                    const uint32_t c = s_cnt[w];
-                    if (w < warp) wbase += c;
-                    total += c;
-                }
-                if (keep) s_list[wbase + __popc(bal & ((1u << lane) - 1u))] = cull_first + k;
-                base += total;
-                __syncthreads();
-            }
-            list_n = base;
-        }
-
-        const uint32_t lx = tx * FILL_TILE_X + lane;
-        const uint32_t ly = ty * FILL_TILE_Y + warp;
-        const uint32_t lz0 = tz * V;
-        // advance to this CTA's next tile (mixed-radix add with carries)
-        tx += sx; ty += sy; tz += sz;
-        if (tx >= P.tiles_x) { tx -= P.tiles_x; ++ty; }
-        if (ty >= P.tiles_y) { ty -= P.tiles_y; ++tz; }
-
-        const bool row_ok = lx < P.nx && ly < P.ny;
-        const uint32_t gx = P.rx0 + lx * P.step, gy = P.ry0 + ly * P.step, gz0 = P.rz0 + lz0 * P.step;
-        const float posx = row_ok ? s_px[gx] : 0.0f, posy = row_ok ? s_py[gy] : 0.0f;
-        const size_t flat0 = row_ok ? (size_t)(gz0 - P.z_lo) * slice + (size_t)gy * P.W + gx : 0;
-        const size_t vstride = (size_t)P.step * slice;
-
-        bool act[V];
-        float posz[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            act[v] = row_ok && lz0 + v < P.nz;
-            posz[v] = act[v] ? s_pz[gz0 + v * P.step] : 0.0f;
-        }
-        if (P.conditional) {  // scene/sdf/mod.rs:184-190
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                if (act[v]) {
-                    bool need = __ldg(reinterpret_cast<const float*>(P.tex0 + flat0 + v * vstride)) == P.air_dist;
-                    if (P.has_box)
-                        need = need || (posx >= P.box[0] && posx <= P.box[3] && posy >= P.box[1] && posy <= P.box[4] &&
-                                        posz[v] >= P.box[2] && posz[v] <= P.box[5]);
-                    act[v] = need;
-                }
-            }
-        }
-        {  // nothing to sample in this warp's row (conditional passes over an already loaded region)
-            bool any = false;
-#pragma unroll
-            for (int v = 0; v < V; ++v) any = any || act[v];
-            if (!__any_sync(0xffffffffu, any)) continue;
-        }
-
-        // ---- interpret the lowered tape (machine model: include/sdfgpu_tape.h; A = accumulator,
-        // T = top of the sample stack in registers, deeper levels in shared memory)
-        Smp A[V], T[V];
-        float qx[V], qy[V], qz[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            A[v].d = A[v].r = A[v].g = A[v].b = A[v].m = A[v].ro = A[v].o = 0.0f;
-            T[v] = A[v];
-            qx[v] = posx; qy[v] = posy; qz[v] = posz[v];
-        }
-        for (uint32_t pc = 0;; ++pc) {
-            const uint4 I = s_instr[pc];
-            if (I.x == DOP_END) break;
-#define PRIM_CASE(MODE, SHAPE, MAT)                                                                    \
-    case DOP_PRIM + (MODE) * 6 + (SHAPE) * 3 + (MAT):                                                 \
-        op_prim<V, MODE, SHAPE, MAT>(A, s_geom[I.y], s_mat0[I.y], s_mat1[I.y], qx, qy, qz);           \
-        break;
-#define PRIM_CASES(MODE)                                                                               \
-    PRIM_CASE(MODE, 0, 0) PRIM_CASE(MODE, 0, 1) PRIM_CASE(MODE, 0, 2) PRIM_CASE(MODE, 1, 0) PRIM_CASE(MODE, 1, 1) \
-    PRIM_CASE(MODE, 1, 2)
-            switch (I.x) {
-                PRIM_CASES(0)
-                PRIM_CASES(1)
-                PRIM_CASES(2)
-                case DOP_UNION_RANGE: {
-                    // fold == argmin with ties to the lowest index, then one material evaluation
-                    const bool culled = n_cull != 0;
-                    const uint32_t n = culled ? list_n : I.z;
-                    float best_d[V];
-                    uint32_t best_k[V];
-                    {
-                        const uint32_t k = culled ? s_list[0] : I.y;
-                        const float4 g = s_geom[k];
-                        const uint32_t shape = __float_as_uint(s_mat1[k].w) & 0xffu;
-#pragma unroll
-                        for (int v = 0; v < V; ++v) {
-                            best_d[v] = prim_distance(shape, qx[v] - g.x, qy[v] - g.y, qz[v] - g.z, g.w);
-                            best_k[v] = k;
-                        }
-                    }
-                    for (uint32_t j = 1; j < n; ++j) {
-                        const uint32_t k = culled ? s_list[j] : I.y + j;
-                        const float4 g = s_geom[k];
-                        const uint32_t shape = __float_as_uint(s_mat1[k].w) & 0xffu;
-#pragma unroll
-                        for (int v = 0; v < V; ++v) {
-                            const float d = prim_distance(shape, qx[v] - g.x, qy[v] - g.y, qz[v] - g.z, g.w);
-                            if (d < best_d[v]) { best_d[v] = d; best_k[v] = k; }
-                        }
-                    }
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        const uint32_t k = best_k[v];
-                        A[v] = prim_sample_rt(s_geom[k], s_mat0[k], s_mat1[k], qx[v], qy[v], qz[v]);
-                    }
-                    break;
-                }
-                case DOP_PUSH_MEM:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) stack_store(s_stack + (size_t)((I.z * V + v) * 7) * NT, T[v]);
-                    // fall through
-                case DOP_PUSH_REG:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) T[v] = A[v];
-                    break;
-                case DOP_POP_UNION:
-                case DOP_POP_UNION_MEM:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) op_pop<0>(A[v], T[v], nullptr);
-                    break;
-                case DOP_POP_INTER:
-                case DOP_POP_INTER_MEM:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) op_pop<1>(A[v], T[v], nullptr);
-                    break;
-                case DOP_POP_DEMO_DIFF:
-                case DOP_POP_DEMO_DIFF_MEM:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) op_pop<2>(A[v], T[v], s_consts + I.y);
-                    break;
-                case DOP_D_NEG:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) A[v].d = -A[v].d;
-                    break;
-                case DOP_D_ABS:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) A[v].d = fabsf(A[v].d);
-                    break;
-                case DOP_D_ADD:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) A[v].d = A[v].d + __uint_as_float(I.w);
-                    break;
-                case DOP_D_MUL:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) A[v].d = A[v].d * __uint_as_float(I.w);
-                    break;
-                case DOP_D_MAX:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) A[v].d = fmaxf(A[v].d, __uint_as_float(I.w));
-                    break;
-                case DOP_D_MIN:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) A[v].d = fminf(A[v].d, __uint_as_float(I.w));
-                    break;
-                case DOP_M_SET: {
-                    const float* c = s_consts + I.y;
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        A[v].r = c[0]; A[v].g = c[1]; A[v].b = c[2]; A[v].m = c[3]; A[v].ro = c[4]; A[v].o = c[5];
-                    }
-                    break;
-                }
-                case DOP_P_RESET:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) { qx[v] = posx; qy[v] = posy; qz[v] = posz[v]; }
-                    break;
-                case DOP_P_SUB: {
-                    const float* c = s_consts + I.y;
-#pragma unroll
-                    for (int v = 0; v < V; ++v) { qx[v] = qx[v] - c[0]; qy[v] = qy[v] - c[1]; qz[v] = qz[v] - c[2]; }
-                    break;
-                }
-                case DOP_P_MUL:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        qx[v] = qx[v] * __uint_as_float(I.w); qy[v] = qy[v] * __uint_as_float(I.w);
-                        qz[v] = qz[v] * __uint_as_float(I.w);
-                    }
-                    break;
-                case DOP_P_ABS:
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        if (I.y & 1u) qx[v] = fabsf(qx[v]);
-                        if (I.y & 2u) qy[v] = fabsf(qy[v]);
-                        if (I.y & 4u) qz[v] = fabsf(qz[v]);
-                    }
-                    break;
-                default: break;
-            }
-#undef PRIM_CASES
-#undef PRIM_CASE
-            if (I.x >= DOP_POP_UNION_MEM && I.x <= DOP_POP_DEMO_DIFF_MEM) {  // reload the new top of stack
-#pragma unroll
-                for (int v = 0; v < V; ++v) stack_load(s_stack + (size_t)((I.z * V + v) * 7) * NT, T[v]);
-            }
-        }
-
-        // ---- the stores of scene/sdf/mod.rs:196-208
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            if (act[v]) {
-                Smp s = A[v];
-                float4 t0, t1;
-                t0.x = fminf(fmaxf(1e-1f + s.d, 0.0f), 1.0f);  // f32::clamp; NaN stays NaN below
-                if (s.d != s.d) t0.x = s.d;
-                if (s.r == 0.0f && s.g == 0.0f && s.b == 0.0f) { s.r = 0.5f; s.g = 0.5f; s.b = 0.5f; }
-                t0.y = s_lut[f32_to_u8_sat(s.r)];
-                t0.z = s_lut[f32_to_u8_sat(s.g)];
-                t0.w = s_lut[f32_to_u8_sat(s.b)];
-                t1.x = s.m;
-                t1.y = s.ro;
-                t1.z = (s.o <= 0.0f) ? 1.0f : s.o;
-                t1.w = P.air_dist;  // never written by the reference: keeps its initial value (:76)
-                store_texel(P.tex0 + flat0 + v * vstride, t0, P.streaming_stores != 0);
-                store_texel(P.tex1 + flat0 + v * vstride, t1, P.streaming_stores != 0);
-                ++touched_local;
-            }
-        }
-    }
-
-    if (P.touched) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) touched_local += __shfl_xor_sync(0xffffffffu, touched_local, o);
-        if (lane == 0 && touched_local) atomicAdd(P.touched, (unsigned long long)touched_local);
-    }
+    dev::fill_body<V, PROG>(P);
 }
 
 __global__ void __launch_bounds__(256) set_const_kernel(float4* __restrict__ dst, size_t n, float v) {
@@ -554,55 +20,49 @@ __global__ void __launch_bounds__(256) set_const_kernel(float4* __restrict__ dst
         dst[i] = val;
 }
 
-template <int V, int MINB>
-cudaError_t launch_fill_v(const FillParams& p, int grid, size_t smem, cudaStream_t s) {
-    fill_kernel<V, MINB><<<grid, FILL_THREADS, smem, s>>>(p);
-    return cudaGetLastError();
+typedef void (*fill_fn)(const FillParams);
+
+fill_fn pick(int V, int program) {
+    const bool demo = program == dev::PROG_DEMO;
+    switch (V) {
+        case 1: return demo ? fill_kernel<1, dev::PROG_DEMO, 4> : fill_kernel<1, dev::PROG_INTERPRET, 4>;
+        case 2: return demo ? fill_kernel<2, dev::PROG_DEMO, 3> : fill_kernel<2, dev::PROG_INTERPRET, 3>;
+        case 4: return demo ? fill_kernel<4, dev::PROG_DEMO, 2> : fill_kernel<4, dev::PROG_INTERPRET, 2>;
+        case 8: return demo ? fill_kernel<8, dev::PROG_DEMO, 1> : fill_kernel<8, dev::PROG_INTERPRET, 1>;
+        default: return nullptr;
+    }
 }
-#define FILL_K1 fill_kernel<1, 4>
-#define FILL_K2 fill_kernel<2, 3>
-#define FILL_K4 fill_kernel<4, 2>
-#define FILL_K8 fill_kernel<8, 1>
 
 }  // namespace
 
 size_t fill_smem_bytes(uint32_t tape_img_bytes, uint32_t n_cull, uint32_t max_stack, int V, uint32_t* stack_floats) {
-    const uint32_t sf = (max_stack > 1 ? max_stack - 1 : 0) * 7u * (uint32_t)V * FILL_THREADS;  // top level lives in registers
+    // the top stack level lives in registers
+    const uint32_t sf = (max_stack > 1 ? max_stack - 1 : 0) * 7u * (uint32_t)V * FILL_THREADS;
     if (stack_floats) *stack_floats = sf;
     return (size_t)tape_img_bytes + 16 + 64 + ((n_cull * 4u + 15u) & ~15u) + (size_t)sf * 4u;
 }
 
-cudaError_t fill_prepare(size_t smem_bytes) {
-    cudaError_t e;
-    const int b = (int)smem_bytes;
-    if ((e = cudaFuncSetAttribute(FILL_K1, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(FILL_K2, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(FILL_K4, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(FILL_K8, cudaFuncAttributeMaxDynamicSharedMemorySize, b)) != cudaSuccess) return e;
-    return cudaSuccess;
+cudaError_t fill_prepare(int V, int program, size_t smem_bytes) {
+    fill_fn f = pick(V, program);
+    if (!f) return cudaErrorInvalidValue;
+    return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
 }
 
-int fill_max_ctas_per_sm(int V, size_t smem_bytes) {
+int fill_max_ctas_per_sm(int V, int program, size_t smem_bytes) {
+    fill_fn f = pick(V, program);
     int n = 0;
-    cudaError_t e;
-    switch (V) {
-        case 1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, FILL_K1, FILL_THREADS, smem_bytes); break;
-        case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, FILL_K2, FILL_THREADS, smem_bytes); break;
-        case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, FILL_K4, FILL_THREADS, smem_bytes); break;
-        default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, FILL_K8, FILL_THREADS, smem_bytes); break;
+    if (!f || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, f, FILL_THREADS, smem_bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
     }
-    if (e != cudaSuccess) { (void)cudaGetLastError(); return 0; }
     return n;
 }
 
-cudaError_t launch_fill(const FillParams& p, int V, int grid, size_t smem, cudaStream_t s) {
-    switch (V) {
-        case 1: return launch_fill_v<1, 4>(p, grid, smem, s);
-        case 2: return launch_fill_v<2, 3>(p, grid, smem, s);
-        case 4: return launch_fill_v<4, 2>(p, grid, smem, s);
-        case 8: return launch_fill_v<8, 1>(p, grid, smem, s);
-        default: return cudaErrorInvalidValue;
-    }
+cudaError_t launch_fill(const FillParams& p, int V, int program, int grid, size_t smem, cudaStream_t s) {
+    fill_fn f = pick(V, program);
+    if (!f) return cudaErrorInvalidValue;
+    f<<<grid, FILL_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_set_const(float4* dst, size_t n, float v, int grid, cudaStream_t s) {

@@ -248,5 +248,21 @@ class SDFViewer:
     def launch_count(self):
         return self._lib.sdfgpu_launch_count(self._h)
 
+    def get_info(self, key):
+        v = C.c_int64()
+        check(self._lib.sdfgpu_get_info(self._h, key.encode(), C.byref(v)), self._h)
+        return v.value
+
     def set_option(self, key, value):
         check(self._lib.sdfgpu_set_option(self._h, key.encode(), int(value)), self._h)
+
+
+def jit_check(tape_bytes, voxels_per_thread=2):
+    """Compile the specialised fill kernel for this tape's structure with NVRTC (no GPU needed).
+    Returns the generated translation unit; raises SdfGpuError with the compiler log on failure."""
+    buf = (C.c_char * len(tape_bytes)).from_buffer_copy(tape_bytes)
+    log = C.create_string_buffer(1 << 16)
+    rc = _lib.load().sdfgpu_jit_check(buf, len(tape_bytes), int(voxels_per_thread), log, len(log))
+    if rc != 0:
+        raise SdfGpuError(rc, log.value.decode("utf-8", "replace") or _lib.load().sdfgpu_last_error(None).decode())
+    return log.value.decode()

@@ -93,3 +93,16 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp")):
                 text = open(os.path.join(d, f)).read()
                 assert "liboracle" not in text and "import orc" not in text and "sdf_oracle" not in text, f
+
+
+def test_specialised_kernel_compiles_for_sm100a(S):
+    """sdfgpu_jit_check: the tape structure -> straight-line kernel source -> NVRTC cubin for sm_100a,
+    from the same device source as the ahead-of-time kernels.  Needs no GPU."""
+    src = S.jit_check(S.tape.demo_tape(), 2)
+    assert "SDFGPU_STEP(5, 0) SDFGPU_STEP(20, 1) SDFGPU_STEP(3, 2) SDFGPU_STEP(24, 3)" in src
+    assert "PROG_JIT" in src
+    src = S.jit_check(S.tape.csg_tape(S.tape.csg_primitive_table(20)), 8)
+    assert "SDFGPU_STEP(19, 0) SDFGPU_STEP(13, 1)" in src
+    with pytest.raises(S.SdfGpuError) as e:
+        S.jit_check(b"\0" * 40, 2)
+    assert e.value.code == -3

@@ -32,14 +32,23 @@ def oracle_full(oracle, tape, dims, bb=BB, passes=2):
     return v
 
 
+PROGRAMS = {"interpreter": (1, 0), "builtin_demo": (2, 2), "jit": (3, 1)}  # option value, last_fill_program
+
+
+@pytest.mark.parametrize("program", list(PROGRAMS))
 @pytest.mark.parametrize("vpt", [1, 2, 4, 8])
-def test_demo_fill_all_64(S, oracle, vpt):
+def test_demo_fill_all_64(S, oracle, vpt, program):
+    """All three ways of executing the lowered tape (interpreter, built-in demo program, NVRTC
+    kernel specialised for the tape structure) give the oracle's bits."""
     tape = S.tape.demo_tape()
     with S.SDFViewer.from_bb(BB, 64, 2) as v:
         assert v.dims == (64, 64, 64)
         v.set_option("fill_voxels_per_thread", vpt)
+        v.set_option("fill_program", PROGRAMS[program][0])
         v.set_tape(tape)
         v.fill_all()
+        assert v.get_info("last_fill_program") == PROGRAMS[program][1]
+        assert v.get_info("last_fill_voxels_per_thread") == vpt
         t0, t1 = v.download()
         assert len(v.loading_mgr) == 0 and v.loading_mgr.passes_left() == 0
     o = oracle_full(oracle, tape, (64, 64, 64))
@@ -102,8 +111,9 @@ def test_nonuniform_bbox(S, oracle):
     assert_same_volume(t0, t1, o.tex0, o.tex1)
 
 
+@pytest.mark.parametrize("program", ["interpreter", "jit"])
 @pytest.mark.parametrize("n_prims,vpt", [(5, 2), (40, 1), (40, 4), (300, 8), (1000, 8)])
-def test_csg_tape(S, oracle, n_prims, vpt):
+def test_csg_tape(S, oracle, n_prims, vpt, program):
     """UNION_RANGE with per-tile culling (>= 16 primitives) and without: identical to the oracle's
     plain left-to-right fold."""
     table = S.tape.csg_primitive_table(n_prims, seed=7 + n_prims)
@@ -111,15 +121,19 @@ def test_csg_tape(S, oracle, n_prims, vpt):
     dims = (64, 64, 32) if n_prims >= 300 else (40, 36, 24)
     with S.SDFViewer.new_voxels(dims, BB, 1) as v:
         v.set_option("fill_voxels_per_thread", vpt)
+        v.set_option("fill_program", PROGRAMS[program][0])
         v.set_tape(tape)
+        assert v.get_info("tape_culled") == (1 if n_prims >= 16 else 0)
         v.fill_all()
+        assert v.get_info("last_fill_program") == PROGRAMS[program][1]
         t0, t1 = v.download()
     o = oracle.Viewer(BB, dims, 1)
     o.fill_all(oracle.Sampler(tape=tape))
     assert_same_volume(t0, t1, o.tex0, o.tex1)
 
 
-def test_generic_ops_tape(S, oracle):
+@pytest.mark.parametrize("program", ["interpreter", "jit"])
+def test_generic_ops_tape(S, oracle, program):
     """Every opcode of include/sdfgpu_tape.h at least once."""
     T = S.tape
     t = T.TapeBuilder()
@@ -140,12 +154,43 @@ def test_generic_ops_tape(S, oracle):
     tape = t.build()
     dims = (37, 29, 13)
     with S.SDFViewer.new_voxels(dims, BB, 1) as v:
+        v.set_option("fill_program", PROGRAMS[program][0])
         v.set_tape(tape)
         v.fill_all()
+        assert v.get_info("last_fill_program") == PROGRAMS[program][1]
         t0, t1 = v.download()
     o = oracle.Viewer(BB, dims, 1)
     o.fill_all(oracle.Sampler(tape=tape))
     assert_same_volume(t0, t1, o.tex0, o.tex1)
+
+
+@pytest.mark.parametrize("program", ["interpreter", "jit"])
+def test_deep_stack_tape(S, oracle, program):
+    """Stack depth 8 (SDFT_MAX_STACK): levels below the top are spilled to shared memory."""
+    T = S.tape
+    t = T.TapeBuilder()
+    rng = np.random.default_rng(3)
+    prims = [t.prim(int(rng.integers(0, 2)), rng.uniform(-0.6, 0.6, 3), float(rng.uniform(0.2, 0.5)),
+                    int(rng.integers(0, 3)), color=rng.uniform(0, 1, 3), metallic=0.3, roughness=0.2, occlusion=0.9,
+                    air_skip=float(rng.choice([0.1, np.inf]))) for _ in range(9)]
+    for k in range(8):
+        t.emit(T.OP_PRIM, prims[k]).emit(T.OP_PUSH)
+    t.emit(T.OP_PRIM, prims[8])
+    for k in range(8):
+        t.emit(T.OP_POP_UNION if k % 2 == 0 else T.OP_POP_INTER)
+    t.emit(T.OP_END)
+    tape = t.build()
+    dims = (33, 17, 9)
+    for vpt in (1, 4):
+        with S.SDFViewer.new_voxels(dims, BB, 1) as v:
+            v.set_option("fill_program", PROGRAMS[program][0])
+            v.set_option("fill_voxels_per_thread", vpt)
+            v.set_tape(tape)
+            v.fill_all()
+            t0, t1 = v.download()
+        o = oracle.Viewer(BB, dims, 1)
+        o.fill_all(oracle.Sampler(tape=tape))
+        assert_same_volume(t0, t1, o.tex0, o.tex1)
 
 
 def test_changed_box_state_machine(S, oracle):
