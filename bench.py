@@ -146,7 +146,6 @@ def main():
     ap.add_argument("--workload", default="demo", choices=["demo", "csg"])
     ap.add_argument("--vpt", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
-    ap.add_argument("--streaming", type=int, default=-1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -180,8 +179,6 @@ def main():
         v.set_option("fill_voxels_per_thread", args.vpt)
     if args.ctas:
         v.set_option("fill_ctas_per_sm", args.ctas)
-    if args.streaming >= 0:
-        v.set_option("streaming_stores", args.streaming)
     v.set_tape(tape)
     stream = torch.cuda.ExternalStream(v.stream, device=torch.device("cuda", local))
     own_voxels = dims[0] * dims[1] * (v.z_end - v.z_begin)

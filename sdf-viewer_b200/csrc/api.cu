@@ -105,7 +105,6 @@ struct sdfgpu_ctx {
     // options
     int opt_vpt = 0;        // voxels per thread (0 = default)
     int opt_ctas = 0;       // CTAs per SM (0 = as many as fit)
-    int opt_streaming = 1;  // st.global.cs
     int opt_fill_halo = 1;  // compute the halo slices locally (0: the host exchanges them)
     int opt_program = 0;    // 0 auto (JIT, else built-in, else interpreter), 1 interpreter, 2 built-in, 3 JIT or fail
     int cc_major = 0, cc_minor = 0;
@@ -198,7 +197,6 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
     p.has_box = ctx->has_changed_box ? 1u : 0u;
     if (ctx->has_changed_box) memcpy(p.box, ctx->changed_box, sizeof p.box);
     p.air_dist = air_dist_value();
-    p.streaming_stores = ctx->opt_streaming ? 1u : 0u;
     p.touched = touched;
     const uint32_t n_cull = (ctx->hdr.flags & TAPE_FLAG_CULL) ? ctx->hdr.cull_count : 0u;
     const size_t smem = fill_smem_bytes(p.tape_img_bytes, n_cull, ctx->hdr.max_stack, V, &p.stack_floats);
@@ -1008,8 +1006,6 @@ SDFGPU_API int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value
     } else if (!strcmp(key, "fill_ctas_per_sm")) {
         if (value < 0 || value > 32) return fail(ctx, SDFGPU_ERR_INVALID, "fill_ctas_per_sm out of range");
         ctx->opt_ctas = (int)value;
-    } else if (!strcmp(key, "streaming_stores")) {
-        ctx->opt_streaming = value != 0;
     } else if (!strcmp(key, "fill_halo")) {
         ctx->opt_fill_halo = value != 0;
     } else if (!strcmp(key, "fill_program")) {

@@ -72,8 +72,9 @@ __device__ __forceinline__ float fmod_p25(float x) {
     if (!(x < 8388608.0f)) return x * 0.0f;
     return x - truncf(x * 4.0f) * 0.25f;
 }
-// f32::signum: +-1 with the sign bit of x, NaN for NaN (cube.rs:168)
-__device__ __forceinline__ float rust_signum(float x) { return (x != x) ? x : copysignf(1.0f, x); }
+// f32::signum (cube.rs:168) where it is reached: behind `x.abs() > side`, which is false for NaN,
+// so only the +-1-with-the-sign-of-x case remains
+__device__ __forceinline__ float signum_not_nan(float x) { return copysignf(1.0f, x); }
 
 // sample_brick_texture, src/sdf/demo/cube.rs:181-222
 __device__ __forceinline__ void brick_texture(float px, float py, float pz, float nx, float ny, float nz, Smp& s) {
@@ -122,27 +123,28 @@ __device__ __forceinline__ Smp prim_sample(const float4 geom, const float4 m0, c
     } else {
         s.d = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) - geom.w;
     }
-    s.r = s.g = s.b = s.m = s.ro = s.o = 0.0f;
-    if (!(s.d > m1.z)) {  // "the air has no texture" shortcut, cube.rs:83-85
-        if (MAT == SDFT_MAT_FLAT) {
-            s.r = m0.x; s.g = m0.y; s.b = m0.z; s.m = m0.w; s.ro = m1.x; s.o = m1.y;
-        } else {
-            float nx, ny, nz;
-            if (SHAPE == SDFT_SHAPE_SPHERE) {  // cgmath normalize = v * (1 / |v|), sphere.rs:123
-                const float inv = 1.0f / len;
-                nx = qx * inv; ny = qy * inv; nz = qz * inv;
-            } else {  // cube.rs:164-177
-                nx = fabsf(qx) > geom.w ? rust_signum(qx) : 0.0f;
-                ny = fabsf(qy) > geom.w ? rust_signum(qy) : 0.0f;
-                nz = fabsf(qz) > geom.w ? rust_signum(qz) : 0.0f;
-            }
-            if (MAT == SDFT_MAT_BRICK) {
-                brick_texture(qx, qy, qz, nx, ny, nz, s);
-            } else {  // Material::Normal, cube.rs:56
-                s.r = fabsf(nx); s.g = fabsf(ny); s.b = fabsf(nz);
-            }
+    // material evaluated unconditionally and dropped by selects when the sample is "air"
+    // (the reference's distance_only shortcut, cube.rs:83-85): no divergent branch in the warp
+    if (MAT == SDFT_MAT_FLAT) {
+        s.r = m0.x; s.g = m0.y; s.b = m0.z; s.m = m0.w; s.ro = m1.x; s.o = m1.y;
+    } else {
+        float nx, ny, nz;
+        if (SHAPE == SDFT_SHAPE_SPHERE) {  // cgmath normalize = v * (1 / |v|), sphere.rs:123
+            const float inv = 1.0f / len;
+            nx = qx * inv; ny = qy * inv; nz = qz * inv;
+        } else {  // cube.rs:164-177
+            nx = fabsf(qx) > geom.w ? signum_not_nan(qx) : 0.0f;
+            ny = fabsf(qy) > geom.w ? signum_not_nan(qy) : 0.0f;
+            nz = fabsf(qz) > geom.w ? signum_not_nan(qz) : 0.0f;
+        }
+        if (MAT == SDFT_MAT_BRICK) {
+            brick_texture(qx, qy, qz, nx, ny, nz, s);
+        } else {  // Material::Normal, cube.rs:56
+            s.r = fabsf(nx); s.g = fabsf(ny); s.b = fabsf(nz);
+            s.m = s.ro = s.o = 0.0f;
         }
     }
+    if (s.d > m1.z) s.r = s.g = s.b = s.m = s.ro = s.o = 0.0f;
     return s;
 }
 
@@ -161,11 +163,15 @@ __device__ __forceinline__ Smp prim_sample_rt(const float4 g, const float4 m0, c
 }
 
 // `Srgba::from(Vector3<f32>)`: (c * 255.0) as u8 -- saturating, NaN -> 0 (scene/sdf/mod.rs:201)
-__device__ __forceinline__ uint32_t f32_to_u8_sat(float c) { return min(__float2uint_rz(c * 255.0f), 255u); }
-
-__device__ __forceinline__ void store_texel(float4* p, float4 v, bool streaming) {
-    if (streaming) __stcs(p, v); else *p = v;
+// cvt.rzi.u8.f32 truncates, saturates to [0, 255] and maps NaN to 0 -- Rust's `as u8` -- in one instruction
+__device__ __forceinline__ uint32_t f32_to_u8_sat(float c) {
+    uint32_t r;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(c * 255.0f));
+    return r;
 }
+
+// st.global.cs: the volume is written once and is larger than L2 at the sizes that matter
+__device__ __forceinline__ void store_texel(float4* p, float4 v) { __stcs(p, v); }
 
 __device__ __forceinline__ void stack_store(float* st, const Smp& s) {
     constexpr int NT = FILL_THREADS;
@@ -464,13 +470,13 @@ __device__ __forceinline__ void fill_body(const FillParams& P) {
         const size_t flat0 = row_ok ? (size_t)(gz0 - P.z_lo) * slice + (size_t)gy * P.W + gx : 0;
 
         Machine<V> M;
-        M.posx = row_ok ? s_px[gx] : 0.0f;
-        M.posy = row_ok ? s_py[gy] : 0.0f;
+        M.posx = s_px[min(gx, P.W - 1u)];
+        M.posy = s_py[min(gy, P.H - 1u)];
         bool act[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             act[v] = row_ok && lz0 + v < P.nz;
-            M.posz[v] = act[v] ? s_pz[gz0 + v * P.step] : 0.0f;
+            M.posz[v] = s_pz[min(gz0 + v * P.step, P.D - 1u)];
         }
         if (P.conditional) {  // scene/sdf/mod.rs:184-190
 #pragma unroll
@@ -486,7 +492,7 @@ __device__ __forceinline__ void fill_body(const FillParams& P) {
             // nothing to sample in this warp's row (passes over an already loaded region)
             bool any = false;
 #pragma unroll
-            for (int v = 0; v < V; ++v) any = any || act[v];
+            for (int v = 0; v < V; ++v) { any = any || act[v]; touched_local += act[v] ? 1u : 0u; }
             if (!__any_sync(0xffffffffu, any)) continue;
         }
 
@@ -517,6 +523,8 @@ __device__ __forceinline__ void fill_body(const FillParams& P) {
         }
 
         // ---- the stores of scene/sdf/mod.rs:196-208
+        float4* const out0 = P.tex0 + flat0;
+        float4* const out1 = P.tex1 + flat0;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             if (act[v]) {
@@ -532,9 +540,8 @@ __device__ __forceinline__ void fill_body(const FillParams& P) {
                 t1.y = s.ro;
                 t1.z = (s.o <= 0.0f) ? 1.0f : s.o;
                 t1.w = P.air_dist;  // never written by the reference: keeps its initial value (:76)
-                store_texel(P.tex0 + flat0 + v * vstride, t0, P.streaming_stores != 0);
-                store_texel(P.tex1 + flat0 + v * vstride, t1, P.streaming_stores != 0);
-                ++touched_local;
+                store_texel(out0 + v * vstride, t0);
+                store_texel(out1 + v * vstride, t1);
             }
         }
     }

@@ -43,7 +43,7 @@ src_cache = {}
 def src(f, ln):
     if f not in src_cache:
         try:
-            src_cache[f] = open("/root/repo/sdf-viewer_b200/csrc/" + f).read().splitlines()
+            src_cache[f] = open("/root/repo/sdf-viewer_b200/csrc/" + f.replace("sdfgpu_fill_jit.cu","fill_device.cuh")).read().splitlines()
         except Exception:
             src_cache[f] = []
     s = src_cache[f]

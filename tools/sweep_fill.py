@@ -29,7 +29,7 @@ def main():
         stream = torch.cuda.ExternalStream(v.stream)
         v.set_tape(tape)
         nvox = side ** 3
-        for prog, vpt, ctas, streaming in [(p, a, b, c) for p in (1, 2, 3) for a in (1, 2, 4, 8) for b in (0, 1, 2, 3) for c in (1, 0)]:
+        for prog, vpt, ctas, streaming in [(p, a, b, c) for p in (1, 2, 3) for a in (1, 2, 4, 8) for b in (0, 1, 2, 3) for c in (1,)]:
             if workload != "demo" and prog == 2:
                 continue
             for _ in (0,):
@@ -37,7 +37,6 @@ def main():
                     v.set_option("fill_program", prog)
                     v.set_option("fill_voxels_per_thread", vpt)
                     v.set_option("fill_ctas_per_sm", ctas)
-                    v.set_option("streaming_stores", streaming)
                     try:
                         ms = time_fill(v, stream, reps=5 if workload == "demo" else 2)
                     except Exception as e:
@@ -47,7 +46,7 @@ def main():
         rows.sort()
         print("best:", rows[:5])
         ms, vpt, ctas, streaming, prog = rows[0]
-        v.set_option("fill_program", prog); v.set_option("fill_voxels_per_thread", vpt); v.set_option("fill_ctas_per_sm", ctas); v.set_option("streaming_stores", streaming)
+        v.set_option("fill_program", prog); v.set_option("fill_voxels_per_thread", vpt); v.set_option("fill_ctas_per_sm", ctas)
         v.fill_all(); v.commit()
         for (w, h) in ((640, 480), (1920, 1080), (3840, 2160)):
             for name, cam in (("default", S.default_camera(w, h)), ("closeup", S.look_at_camera((0.9, 1.1, 1.8), (0, 0, 0), w, h))):
