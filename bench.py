@@ -277,7 +277,11 @@ def main():
                 "what": "set_tape (H2D) + fill + trace + frame RGBA32F+depth D2H into pinned host memory"},
         "gpu_launches": int(launches), "clocks": clocks, "host_ms_per_step": wall_ms,
     }
-    if not args.no_cpu_baseline:
+    if n_gpus > 1:
+        out["e2e"]["d2h_bytes_per_step"] = W * H * 8
+        out["e2e"]["what"] = ("set_tape (H2D) + fill + NCCL halo exchange + slab trace + all-reduce(MIN) composite + "
+                              "frame RGBA8+depth D2H")
+    if not args.no_cpu_baseline and n_gpus == 1:
         import orc
         orc.build()
         threads = orc.lib().orc_max_threads()
