@@ -106,6 +106,8 @@ struct sdfgpu_ctx {
     int opt_vpt = 0;        // voxels per thread (0 = default)
     int opt_ctas = 0;       // CTAs per SM (0 = as many as fit)
     int opt_fill_halo = 1;  // compute the halo slices locally (0: the host exchanges them)
+    int opt_max_steps = 256;    // maxSteps of sdfRaycast (material.frag:142); other values are for experiments only
+    int opt_trace_variant = 0;  // 0: 8x8 tiles, heavy-first 1-D grid; 1: plain 2-D grid of 32x8 CTAs
     int opt_program = 0;    // 0 auto (JIT, else built-in, else interpreter), 1 interpreter, 2 built-in, 3 JIT or fail
     int cc_major = 0, cc_minor = 0;
     int last_program = -1, last_ctas = 0, last_vpt = 0;
@@ -167,7 +169,7 @@ uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
 void set_device(sdfgpu_ctx* ctx) { (void)cudaSetDevice(ctx->device); }
 
-int default_vpt(const sdfgpu_ctx* ctx) { return ctx->opt_vpt ? ctx->opt_vpt : ((ctx->hdr.flags & TAPE_FLAG_CULL) ? 8 : 4); }
+int default_vpt(const sdfgpu_ctx* ctx) { return ctx->opt_vpt ? ctx->opt_vpt : 4; }
 
 // one fill launch over lattice {r0 + i*step} restricted to the index box [lo, hi) per axis
 int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_t hi[3], bool conditional,
@@ -273,6 +275,11 @@ int create_common(const float bb[6], const uint32_t voxels[3], uint32_t passes, 
     if (z_begin > z_end || z_end > voxels[2]) return fail(nullptr, SDFGPU_ERR_INVALID, "bad slab range");
     if (voxels[0] > 65535u || voxels[1] > 65535u || voxels[2] > 65535u)
         return fail(nullptr, SDFGPU_ERR_INVALID, "more than 65535 voxels on a side");
+    {
+        const uint32_t zl = z_begin > 0 ? z_begin - 1 : 0, zh = z_end < voxels[2] ? z_end + 1 : voxels[2];
+        if ((uint64_t)voxels[0] * voxels[1] * (zh - zl) >= (1ull << 31))
+            return fail(nullptr, SDFGPU_ERR_INVALID, "a handle stores at most 2^31 texels per volume (32 GiB); shard along z");
+    }
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0) {
@@ -819,6 +826,15 @@ int fill_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t w, uin
         if (ctx->z_begin > 0) { volatile float t = a0 * size; tp->clip_min[2] = ctx->bb[2] + t; }
         if (ctx->z_end < ctx->dims[2]) { volatile float t = a1 * size; tp->clip_max[2] = ctx->bb[2] + t; }
     }
+    tp->size_pow2 = 1;
+    for (int a = 0; a < 3; ++a) {
+        volatile float size = tp->bmax[a] - tp->bmin[a];
+        int e = 0;
+        const float m = frexpf(size, &e);  // size = m * 2^e, m in [0.5, 1): a power of two has m == 0.5
+        // the reciprocal must be a normal float too (|e| small) for x / size == x * (1 / size) to hold bit for bit
+        if (!(m == 0.5f) || e < -60 || e > 60) tp->size_pow2 = 0;
+        tp->inv_size[a] = 1.0f / size;
+    }
     tp->W = ctx->dims[0]; tp->H = ctx->dims[1]; tp->D = ctx->dims[2];
     tp->z_lo = ctx->z_lo; tp->z_hi = ctx->z_hi;
     tp->lod = ctx->lod;
@@ -828,6 +844,35 @@ int fill_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t w, uin
     tp->gamma = cam->gamma;
     memcpy(tp->ambient, cam->ambient, 12);
     tp->width = w; tp->height = h;
+    tp->max_steps = (uint32_t)ctx->opt_max_steps;
+    // screen rectangle of the projected clip box (a convex box projects inside the bounding rectangle of
+    // its projected corners); +-2 pixels of slack; the whole frame if a corner is not in front of the camera
+    tp->tiles_x = (w + 7) / 8; tp->tiles_y = (h + 7) / 8;
+    double x0 = 1e30, y0 = 1e30, x1 = -1e30, y1 = -1e30;
+    bool full = false;
+    for (int c = 0; c < 8 && !full; ++c) {
+        const double p[3] = {(c & 1) ? tp->clip_max[0] : tp->clip_min[0], (c & 2) ? tp->clip_max[1] : tp->clip_min[1],
+                             (c & 4) ? tp->clip_max[2] : tp->clip_min[2]};
+        const float* m = tp->bvp;
+        const double X = m[0] * p[0] + m[4] * p[1] + m[8] * p[2] + m[12];
+        const double Y = m[1] * p[0] + m[5] * p[1] + m[9] * p[2] + m[13];
+        const double Wc = m[3] * p[0] + m[7] * p[1] + m[11] * p[2] + m[15];
+        if (!(Wc > 1e-4)) { full = true; break; }
+        const double sx = X / Wc * w, sy = Y / Wc * h;
+        if (!(sx == sx) || !(sy == sy)) { full = true; break; }
+        x0 = sx < x0 ? sx : x0; x1 = sx > x1 ? sx : x1;
+        y0 = sy < y0 ? sy : y0; y1 = sy > y1 ? sy : y1;
+    }
+    if (full) {
+        tp->rect[0] = tp->rect[1] = 0; tp->rect[2] = tp->tiles_x; tp->rect[3] = tp->tiles_y;
+    } else {
+        auto clampi = [](double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); };
+        const uint32_t px0 = (uint32_t)clampi(floor(x0) - 2, 0, w), px1 = (uint32_t)clampi(ceil(x1) + 2, 0, w);
+        const uint32_t py0 = (uint32_t)clampi(floor(y0) - 2, 0, h), py1 = (uint32_t)clampi(ceil(y1) + 2, 0, h);
+        tp->rect[0] = px0 / 8; tp->rect[1] = py0 / 8;
+        tp->rect[2] = (px1 + 7) / 8; tp->rect[3] = (py1 + 7) / 8;
+        if (tp->rect[2] <= tp->rect[0] || tp->rect[3] <= tp->rect[1]) tp->rect[0] = tp->rect[1] = tp->rect[2] = tp->rect[3] = 0;
+    }
     return SDFGPU_OK;
 }
 
@@ -903,7 +948,7 @@ SDFGPU_API int sdfgpu_trace_device(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, ui
     if ((rc = fill_trace_params(ctx, cam, width, height, false, &tp)) != SDFGPU_OK) return rc;
     tp.rgba = ctx->rgba_dev; tp.depth = ctx->depth_dev;
     tp.gbuf = want_gbuf ? ctx->gbuf_dev : nullptr;
-    CK(ctx, launch_trace(tp, 0, ctx->stream));
+    CK(ctx, launch_trace(tp, ctx->opt_trace_variant, ctx->stream));
     ctx->launches++;
     if (rgba_dev) *rgba_dev = ctx->rgba_dev;
     if (depth_dev) *depth_dev = ctx->depth_dev;
@@ -949,7 +994,7 @@ SDFGPU_API int sdfgpu_trace_slab_keys(sdfgpu_ctx* ctx, const sdfgpu_camera* cam,
     TraceParams tp;
     if ((rc = fill_trace_params(ctx, cam, width, height, true, &tp)) != SDFGPU_OK) return rc;
     tp.keys = ctx->keys_dev;
-    CK(ctx, launch_trace(tp, 0, ctx->stream));
+    CK(ctx, launch_trace(tp, ctx->opt_trace_variant, ctx->stream));
     ctx->launches++;
     *keys_dev = ctx->keys_dev;
     return SDFGPU_OK;
@@ -1008,6 +1053,12 @@ SDFGPU_API int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value
         ctx->opt_ctas = (int)value;
     } else if (!strcmp(key, "fill_halo")) {
         ctx->opt_fill_halo = value != 0;
+    } else if (!strcmp(key, "trace_max_steps")) {
+        if (value < 2 || value > 65536) return fail(ctx, SDFGPU_ERR_INVALID, "trace_max_steps out of range");
+        ctx->opt_max_steps = (int)value;
+    } else if (!strcmp(key, "trace_variant")) {
+        if (value < 0 || value > 1) return fail(ctx, SDFGPU_ERR_INVALID, "trace_variant must be 0 or 1");
+        ctx->opt_trace_variant = (int)value;
     } else if (!strcmp(key, "fill_program")) {
         if (value < 0 || value > 3) return fail(ctx, SDFGPU_ERR_INVALID, "fill_program must be 0..3");
         ctx->opt_program = (int)value;

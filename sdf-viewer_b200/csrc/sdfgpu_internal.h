@@ -18,6 +18,8 @@ struct TraceParams {
     float origin[3], base[3], dx[3], dy[3], bvp[16];
     float bmin[3], bmax[3];          // sdfBoundsMin/Max
     float clip_min[3], clip_max[3];  // == bounds on one GPU; the slab's sub-box for sort-last
+    float inv_size[3];               // exact 1 / (bmax - bmin), valid when size_pow2
+    uint32_t size_pow2;              // all three box sizes are powers of two: x / size == x * inv_size bit for bit
     uint32_t W, H, D;
     uint32_t z_lo, z_hi;  // stored slices
     float lod;
@@ -27,6 +29,9 @@ struct TraceParams {
     float gamma;
     float ambient[3];
     uint32_t width, height;
+    uint32_t max_steps;         // sdfRaycast's maxSteps: 256 (material.frag:142)
+    uint32_t tiles_x, tiles_y;  // 8 x 8 pixel tiles
+    uint32_t rect[4];           // tile rectangle [x0, y0, x1, y1) that contains every pixel whose ray can hit the clip box
     float4* rgba;              // may be null
     float* depth;              // may be null
     float* gbuf;               // may be null

@@ -13,6 +13,8 @@
 //
 // A warp owns an 8 x 4 pixel tile so neighbouring rays share texels; finished
 // lanes drop out and the warp leaves the loop as soon as its ballot is empty.
+// CTAs are 8 x 8 pixel tiles in a 1-D grid ordered heavy-first (tiles inside the
+// screen rectangle of the projected box), see trace_tiles_kernel.
 //
 // Compiled with -fmad=false -prec-div=true -prec-sqrt=true (GLSL highp f32
 // without contraction is what the oracle restates).
@@ -34,6 +36,17 @@ __device__ __forceinline__ int mirror_idx(int i, int n) {
     return m < n ? m : 2 * n - 1 - m;
 }
 
+// The two taps x0, x0 + 1 of a LINEAR fetch.  For x0 in [-1, n - 1] -- every position inside the
+// box -- MIRRORED_REPEAT of (x0, x0 + 1) is (max(x0, 0), min(x0 + 1, n - 1)); anything else takes
+// the general path.
+__device__ __forceinline__ void mirror_pair(int x0, int n, int& a, int& b) {
+    if ((unsigned)(x0 + 1) <= (unsigned)n) {
+        a = max(x0, 0); b = min(x0 + 1, n - 1);
+    } else {
+        a = mirror_idx(x0, n); b = mirror_idx(x0 + 1, n);
+    }
+}
+
 __device__ __forceinline__ size_t texel_index(const Vol& v, int x, int y, int z) {
     x = mirror_idx(x, v.W); y = mirror_idx(y, v.H); z = mirror_idx(z, v.D);
     z = max(z, v.z_lo); z = min(z, v.z_hi - 1);  // slab storage: taps stay within the halo
@@ -42,8 +55,8 @@ __device__ __forceinline__ size_t texel_index(const Vol& v, int x, int y, int z)
 
 __device__ __forceinline__ float lerp1(float a, float b, float f) { return a + f * (b - a); }
 
-struct Taps {
-    size_t i000, i100, i010, i110, i001, i101, i011, i111;
+struct Taps {  // texel indices fit 32 bits: sdfgpu_create rejects volumes of 2^32 texels or more per handle
+    uint32_t i000, i100, i010, i110, i001, i101, i011, i111;
     float fx, fy, fz;
 };
 
@@ -54,13 +67,14 @@ __device__ __forceinline__ Taps linear_taps(const Vol& v, float ax, float ay, fl
     Taps t;
     t.fx = ux - fx0; t.fy = uy - fy0; t.fz = uz - fz0;
     const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
-    const int xa = mirror_idx(x0, v.W), xb = mirror_idx(x0 + 1, v.W);
-    const int ya = mirror_idx(y0, v.H), yb = mirror_idx(y0 + 1, v.H);
-    int za = mirror_idx(z0, v.D), zb = mirror_idx(z0 + 1, v.D);
+    int xa, xb, ya, yb, za, zb;
+    mirror_pair(x0, v.W, xa, xb);
+    mirror_pair(y0, v.H, ya, yb);
+    mirror_pair(z0, v.D, za, zb);
     za = min(max(za, v.z_lo), v.z_hi - 1) - v.z_lo;
     zb = min(max(zb, v.z_lo), v.z_hi - 1) - v.z_lo;
-    const size_t ra = ((size_t)za * v.H + ya) * v.W, rb = ((size_t)za * v.H + yb) * v.W;
-    const size_t rc = ((size_t)zb * v.H + ya) * v.W, rd = ((size_t)zb * v.H + yb) * v.W;
+    const uint32_t ra = ((uint32_t)za * v.H + ya) * v.W, rb = ((uint32_t)za * v.H + yb) * v.W;
+    const uint32_t rc = ((uint32_t)zb * v.H + ya) * v.W, rd = ((uint32_t)zb * v.H + yb) * v.W;
     t.i000 = ra + xa; t.i100 = ra + xb; t.i010 = rb + xa; t.i110 = rb + xb;
     t.i001 = rc + xa; t.i101 = rc + xb; t.i011 = rd + xa; t.i111 = rd + xb;
     return t;
@@ -73,7 +87,7 @@ __device__ __forceinline__ float trilerp(float c000, float c100, float c010, flo
     return lerp1(lerp1(a, b, fy), lerp1(e, f, fy), fz);
 }
 
-__device__ __forceinline__ float ldx(const float4* t, size_t i) { return __ldg(reinterpret_cast<const float*>(t + i)); }
+__device__ __forceinline__ float ldx(const float4* t, uint32_t i) { return __ldg(reinterpret_cast<const float*>(t + i)); }
 
 // sdfSampleRawInterp / sdfSampleRawNearest (material.frag:27-53): while loading (lod != 1) the
 // coordinate is first rounded to the lod lattice (:33-34); the fetch then uses whatever GL filter
@@ -81,9 +95,15 @@ __device__ __forceinline__ float ldx(const float4* t, size_t i) { return __ldg(r
 template <bool SNAP>
 __device__ __forceinline__ void tex_coord(const TraceParams& P, const Vol& v, float px, float py, float pz, float& ax,
                                           float& ay, float& az) {
-    ax = (px - P.bmin[0]) / (P.bmax[0] - P.bmin[0]);  // :30, :44
-    ay = (py - P.bmin[1]) / (P.bmax[1] - P.bmin[1]);
-    az = (pz - P.bmin[2]) / (P.bmax[2] - P.bmin[2]);
+    // (p - min) / (max - min), :30, :44.  When the size is a power of two the host passes its exact
+    // reciprocal and the division becomes a multiplication with the same bits.
+    if (P.size_pow2) {
+        ax = (px - P.bmin[0]) * P.inv_size[0]; ay = (py - P.bmin[1]) * P.inv_size[1]; az = (pz - P.bmin[2]) * P.inv_size[2];
+    } else {
+        ax = (px - P.bmin[0]) / (P.bmax[0] - P.bmin[0]);
+        ay = (py - P.bmin[1]) / (P.bmax[1] - P.bmin[1]);
+        az = (pz - P.bmin[2]) / (P.bmax[2] - P.bmin[2]);
+    }
     if (SNAP) {
         const float rx = (float)v.W / P.lod, ry = (float)v.H / P.lod, rz = (float)v.D / P.lod;  // :33
         ax = floorf(ax * rx + 0.5f) / rx; ay = floorf(ay * ry + 0.5f) / ry; az = floorf(az * rz + 0.5f) / rz;  // :34
@@ -169,13 +189,21 @@ __device__ __forceinline__ unsigned long long pack_key(float depth, float r, flo
     return ((unsigned long long)__float_as_uint(dc) << 32) | rgba;
 }
 
+// A pixel the host proved to lie outside the screen rectangle of the projected clip box: its ray
+// misses the box (code -3), no ray arithmetic needed.
+__device__ __forceinline__ void write_outside(const TraceParams& P, size_t px) {
+    if (P.rgba) P.rgba[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (P.depth) P.depth[px] = 1.0f;
+    if (P.gbuf) {
+        float4* gp = reinterpret_cast<float4*>(P.gbuf + px * SDFGPU_GBUF_FLOATS);
+        gp[0] = make_float4(0.f, 0.f, 0.f, -3.0f);
+        gp[1] = gp[2] = gp[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (P.keys) P.keys[px] = pack_key(1.0f, 0.f, 0.f, 0.f, 0.f);
+}
+
 template <bool SNAP, bool LINEAR>
-__global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceParams P) {
-    // 8 warps per CTA, each an 8 x 4 pixel tile; CTA tile = 32 x 8 pixels
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t i = blockIdx.x * 32u + (warp & 3) * 8u + (lane & 7);
-    const uint32_t j = blockIdx.y * 8u + (warp >> 2) * 4u + (lane >> 3);
-    if (i >= P.width || j >= P.height) return;
+__device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, uint32_t j) {
     const size_t px = (size_t)j * P.width + i;
 
     const Vol v0{P.tex0, (int)P.W, (int)P.H, (int)P.D, (int)P.z_lo, (int)P.z_hi};
@@ -220,9 +248,10 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
         float t = 0.0f;
         hx = rox; hy = roy; hz = roz;
         code = -1.0f;
-        for (int it = 0; it < 256; ++it) {
+        const int max_steps = (int)P.max_steps;  // 256 in the reference (material.frag:142)
+        for (int it = 0; it < max_steps; ++it) {
             steps = it;
-            if (it >= 255) { code = -1.0f; break; }                                          // :99-102
+            if (it >= max_steps - 1) { code = -1.0f; break; }                                          // :99-102
             if (oob_dist(P.clip_min, P.clip_max, hx, hy, hz) > 1e-4f) { code = -2.0f; break; }  // :106-109
             s0x = sample_dist<SNAP, LINEAR>(P, v0, hx, hy, hz);                                    // :112
             const float dist = s0x - 1e-1f;                                                  // :59
@@ -285,6 +314,49 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
     if (P.keys) P.keys[px] = pack_key(depth, out.x, out.y, out.z, out.w);
 }
 
+// Variant 0 (default): 1-D grid of 8 x 8 pixel tiles (2 warps of 8 x 4), ordered so that the tiles
+// inside the screen rectangle of the projected clip box come first: the long marches start at
+// once and the cheap outside tiles fill in behind them.  Small CTAs release their SM slot as soon
+// as their own rays end instead of waiting for the slowest of 8 warps.
+template <bool SNAP, bool LINEAR>
+__global__ void __launch_bounds__(64) trace_tiles_kernel(const __grid_constant__ TraceParams P) {
+    const uint32_t rw = P.rect[2] - P.rect[0], rh = P.rect[3] - P.rect[1];
+    const uint32_t n_heavy = rw * rh;
+    uint32_t b = blockIdx.x, tx, ty;
+    bool outside = false;
+    if (b < n_heavy) {
+        tx = P.rect[0] + b % rw; ty = P.rect[1] + b / rw;
+    } else {
+        outside = true;
+        b -= n_heavy;
+        const uint32_t n_top = P.rect[1] * P.tiles_x, side = P.tiles_x - rw;
+        if (b < n_top) {
+            tx = b % P.tiles_x; ty = b / P.tiles_x;
+        } else if (b - n_top < rh * side) {
+            b -= n_top;
+            const uint32_t k = b % side;
+            ty = P.rect[1] + b / side; tx = k < P.rect[0] ? k : k + rw;
+        } else {
+            b -= n_top + rh * side;
+            tx = b % P.tiles_x; ty = P.rect[3] + b / P.tiles_x;
+        }
+    }
+    const uint32_t i = tx * 8u + (threadIdx.x & 7u), j = ty * 8u + (threadIdx.x >> 3);
+    if (i >= P.width || j >= P.height) return;
+    if (outside) write_outside(P, (size_t)j * P.width + i);
+    else trace_pixel<SNAP, LINEAR>(P, i, j);
+}
+
+// Variant 1: plain 2-D grid, 8 warps per CTA, each an 8 x 4 pixel tile; CTA tile = 32 x 8 pixels
+template <bool SNAP, bool LINEAR>
+__global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ TraceParams P) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * 32u + (warp & 3) * 8u + (lane & 7);
+    const uint32_t j = blockIdx.y * 8u + (warp >> 2) * 4u + (lane >> 3);
+    if (i >= P.width || j >= P.height) return;
+    trace_pixel<SNAP, LINEAR>(P, i, j);
+}
+
 __global__ void keys_unpack_kernel(const unsigned long long* __restrict__ keys, uint32_t n, uint8_t* __restrict__ rgba8,
                                    float* __restrict__ depth) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,14 +368,22 @@ __global__ void keys_unpack_kernel(const unsigned long long* __restrict__ keys, 
 
 }  // namespace
 
-cudaError_t launch_trace(const TraceParams& p, int /*variant*/, cudaStream_t s) {
+cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s) {
     if (p.width == 0 || p.height == 0) return cudaSuccess;
-    const dim3 grid((p.width + 31) / 32, (p.height + 7) / 8);
     const bool snap = p.lod != 1.0f, lin = p.filter_linear != 0;
-    if (!snap && lin) trace_kernel<false, true><<<grid, 256, 0, s>>>(p);
-    else if (!snap && !lin) trace_kernel<false, false><<<grid, 256, 0, s>>>(p);
-    else if (snap && lin) trace_kernel<true, true><<<grid, 256, 0, s>>>(p);
-    else trace_kernel<true, false><<<grid, 256, 0, s>>>(p);
+    if (variant == 0) {
+        const unsigned grid = p.tiles_x * p.tiles_y;
+        if (!snap && lin) trace_tiles_kernel<false, true><<<grid, 64, 0, s>>>(p);
+        else if (!snap && !lin) trace_tiles_kernel<false, false><<<grid, 64, 0, s>>>(p);
+        else if (snap && lin) trace_tiles_kernel<true, true><<<grid, 64, 0, s>>>(p);
+        else trace_tiles_kernel<true, false><<<grid, 64, 0, s>>>(p);
+    } else {
+        const dim3 grid((p.width + 31) / 32, (p.height + 7) / 8);
+        if (!snap && lin) trace_kernel<false, true><<<grid, 256, 0, s>>>(p);
+        else if (!snap && !lin) trace_kernel<false, false><<<grid, 256, 0, s>>>(p);
+        else if (snap && lin) trace_kernel<true, true><<<grid, 256, 0, s>>>(p);
+        else trace_kernel<true, false><<<grid, 256, 0, s>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -97,6 +97,22 @@ def test_while_loading_lod(S, oracle):
         compare(S, oracle, v, cam, w, h)
 
 
+def test_trace_variants_identical(S):
+    """The heavy-first 8x8-tile grid (default) and the plain 2-D grid trace the same frame, bit for bit,
+    including pixels outside the screen rectangle of the box, odd frame sizes and a camera inside the box."""
+    with fill(S, S.tape.demo_tape(), (64, 64, 64)) as v:
+        for (w, h, cam) in ((640, 480, None), (333, 211, None), (320, 200, ((0.2, 0.1, 0.3), (1, 0.2, -0.4))),
+                            (200, 300, ((4.0, 0.5, 0.2), (0, 3.0, 0)))):
+            c = S.default_camera(w, h) if cam is None else S.look_at_camera(cam[0], cam[1], w, h)
+            frames = []
+            for variant in (0, 1):
+                v.set_option("trace_variant", variant)
+                frames.append(v.trace(c, w, h, gbuf=True))
+            for a, b in zip(*frames):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        v.set_option("trace_variant", 0)
+
+
 def test_uncommitted_nearest(S, oracle):
     """Before any commit lod stays 1 and the GL filter is NEAREST (scene/sdf/mod.rs:110-111)."""
     w, h = 256, 192
