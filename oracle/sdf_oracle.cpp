@@ -696,6 +696,16 @@ ORC_API void* orc_viewer_new(const float bb[6], const uint32_t dims[3], uint64_t
     for (unsigned i = 0; i < 256; ++i) v->lut[i] = srgb_u8_to_linear(i);
     return v;
 }
+// Geometry only (no volumes): for point-wise checks of grids too large to hold twice on the host.
+ORC_API void* orc_viewer_new_noalloc(const float bb[6], const uint32_t dims[3], uint64_t passes) {
+    Viewer* v = new Viewer();
+    memcpy(v->dims, dims, 12);
+    memcpy(v->bb, bb, 24);
+    v->lm.limits[0] = dims[0]; v->lm.limits[1] = dims[1]; v->lm.limits[2] = dims[2];
+    v->lm.reset(passes);
+    for (unsigned i = 0; i < 256; ++i) v->lut[i] = srgb_u8_to_linear(i);
+    return v;
+}
 ORC_API void orc_viewer_free(void* h) { delete (Viewer*)h; }
 ORC_API float* orc_viewer_tex0(void* h) { return ((Viewer*)h)->tex0.data(); }
 ORC_API float* orc_viewer_tex1(void* h) { return ((Viewer*)h)->tex1.data(); }
@@ -790,6 +800,25 @@ ORC_API uint64_t orc_viewer_fill_all(void* h, void* sampler, uint32_t z0, uint32
                 store_sample(v, sdf.sample(voxel_pos(v, x, y, (uint64_t)z)), &v.tex0[4 * flat], &v.tex1[4 * flat]);
             }
     return (uint64_t)(z1 > z0 ? z1 - z0 : 0) * v.dims[1] * v.dims[0];
+}
+
+// What update() stores for the given voxels (idx = n x 3 voxel indices): out0 / out1 = n x 4 floats.
+// Lets the full-size GPU tests check a random subset of a 512^3 / 1024^3 volume point by point.
+ORC_API void orc_viewer_sample_voxels(void* h, void* sampler, const uint32_t* idx, uint64_t n, float* out0,
+                                      float* out1, int threads) {
+    Viewer& v = *(Viewer*)h;
+    const Sampler& sdf = *(const Sampler*)sampler;
+    const float AIR = air_dist();
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+        float* t0 = out0 + 4 * i;
+        float* t1 = out1 + 4 * i;
+        for (int c = 0; c < 4; ++c) t0[c] = t1[c] = AIR;  // new_voxels, :76-77
+        store_sample(v, sdf.sample(voxel_pos(v, idx[3 * i], idx[3 * i + 1], idx[3 * i + 2])), t0, t1);
+    }
 }
 
 ORC_API int orc_max_threads(void) {

@@ -110,6 +110,32 @@ __device__ __forceinline__ void tex_coord(const TraceParams& P, const Vol& v, fl
     }
 }
 
+// The distance lanes of the 8 texels around the last LINEAR fetch.  Near the surface a ray takes
+// many tiny steps inside one cell; those steps reuse the registers instead of re-fetching
+// (same values, same arithmetic: only the loads are skipped).
+struct CellCache {
+    float x0, y0, z0;  // floor() of the texel coordinates of the cached cell
+    float c000, c100, c010, c110, c001, c101, c011, c111;
+};
+
+template <bool SNAP>
+__device__ __forceinline__ float sample_dist_cached(const TraceParams& P, const Vol& v, float px, float py, float pz,
+                                                    CellCache& cc) {
+    float ax, ay, az;
+    tex_coord<SNAP>(P, v, px, py, pz, ax, ay, az);
+    const float ux = ax * (float)v.W - 0.5f, uy = ay * (float)v.H - 0.5f, uz = az * (float)v.D - 0.5f;
+    const float fx0 = floorf(ux), fy0 = floorf(uy), fz0 = floorf(uz);
+    if (fx0 != cc.x0 || fy0 != cc.y0 || fz0 != cc.z0) {
+        const Taps t = linear_taps(v, ax, ay, az);
+        cc.c000 = ldx(v.tex, t.i000); cc.c100 = ldx(v.tex, t.i100); cc.c010 = ldx(v.tex, t.i010);
+        cc.c110 = ldx(v.tex, t.i110); cc.c001 = ldx(v.tex, t.i001); cc.c101 = ldx(v.tex, t.i101);
+        cc.c011 = ldx(v.tex, t.i011); cc.c111 = ldx(v.tex, t.i111);
+        cc.x0 = fx0; cc.y0 = fy0; cc.z0 = fz0;
+    }
+    return trilerp(cc.c000, cc.c100, cc.c010, cc.c110, cc.c001, cc.c101, cc.c011, cc.c111, ux - fx0, uy - fy0,
+                   uz - fz0);
+}
+
 // distance lane only
 template <bool SNAP, bool LINEAR>
 __device__ __forceinline__ float sample_dist(const TraceParams& P, const Vol& v, float px, float py, float pz) {
@@ -249,11 +275,15 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, ui
         hx = rox; hy = roy; hz = roz;
         code = -1.0f;
         const int max_steps = (int)P.max_steps;  // 256 in the reference (material.frag:142)
+        CellCache cell;
+        cell.x0 = cell.y0 = cell.z0 = __int_as_float(0x7fc00000);  // NaN: never equal, first step always fetches
+        cell.c000 = cell.c100 = cell.c010 = cell.c110 = cell.c001 = cell.c101 = cell.c011 = cell.c111 = 0.0f;
         for (int it = 0; it < max_steps; ++it) {
             steps = it;
             if (it >= max_steps - 1) { code = -1.0f; break; }                                          // :99-102
             if (oob_dist(P.clip_min, P.clip_max, hx, hy, hz) > 1e-4f) { code = -2.0f; break; }  // :106-109
-            s0x = sample_dist<SNAP, LINEAR>(P, v0, hx, hy, hz);                                    // :112
+            if (LINEAR) s0x = sample_dist_cached<SNAP>(P, v0, hx, hy, hz, cell);                   // :112
+            else s0x = sample_dist<SNAP, LINEAR>(P, v0, hx, hy, hz);
             const float dist = s0x - 1e-1f;                                                  // :59
             if (dist < 1e-5f) { code = t; hit = true; break; }                               // :117-121
             t += dist;                                                                       // :124

@@ -66,6 +66,7 @@ def lib():
         "orc_prev_power_of_2": (u32, [u32]),
         "orc_dims_from_bb": (None, [fp, u32, C.POINTER(u32)]),
         "orc_viewer_new": (vp, [fp, C.POINTER(u32), u64]),
+        "orc_viewer_new_noalloc": (vp, [fp, C.POINTER(u32), u64]),
         "orc_viewer_free": (None, [vp]),
         "orc_viewer_tex0": (fp, [vp]),
         "orc_viewer_tex1": (fp, [vp]),
@@ -78,6 +79,7 @@ def lib():
         "orc_sampler_free": (None, [vp]),
         "orc_viewer_update": (u64, [vp, vp, fp, u64]),
         "orc_viewer_fill_all": (u64, [vp, vp, u32, u32, C.c_int]),
+        "orc_viewer_sample_voxels": (None, [vp, vp, vp, u64, vp, vp, C.c_int]),
         "orc_max_threads": (C.c_int, []),
         "orc_look_at_rh": (None, [fp, fp, fp, fp]),
         "orc_perspective": (None, [C.c_float, C.c_float, C.c_float, C.c_float, fp]),
@@ -147,9 +149,10 @@ class Sampler:
 class Viewer:
     """The oracle's SDFViewer (scene/sdf/mod.rs)."""
 
-    def __init__(self, bb, dims, passes):
+    def __init__(self, bb, dims, passes, alloc=True):
         self.bb, self.dims = bb, tuple(int(d) for d in dims)
-        self.h = lib().orc_viewer_new(_bb6(bb), (C.c_uint32 * 3)(*self.dims), int(passes))
+        new = lib().orc_viewer_new if alloc else lib().orc_viewer_new_noalloc
+        self.h = new(_bb6(bb), (C.c_uint32 * 3)(*self.dims), int(passes))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -177,6 +180,15 @@ class Viewer:
 
     def fill_all(self, sampler, z0=0, z1=None, threads=0):
         return lib().orc_viewer_fill_all(self.h, sampler.h, int(z0), int(self.dims[2] if z1 is None else z1), int(threads))
+
+    def sample_voxels(self, sampler, idx, threads=0):
+        """Stored texels (tex0, tex1) of the voxels idx[n,3] -- computed point by point, no volume needed."""
+        idx = np.ascontiguousarray(idx, np.uint32).reshape(-1, 3)
+        o0 = np.empty((len(idx), 4), np.float32)
+        o1 = np.empty((len(idx), 4), np.float32)
+        lib().orc_viewer_sample_voxels(self.h, sampler.h, idx.ctypes.data, len(idx), o0.ctypes.data, o1.ctypes.data,
+                                       int(threads))
+        return o0, o1
 
     def len(self):
         return lib().orc_viewer_len(self.h)

@@ -1,0 +1,113 @@
+"""Parity at BASELINE.json's full sizes, through properties that do not need the whole oracle volume:
+a random subset of voxels (plus corners / edges) of the GPU volume is compared, bit for bit, with
+the oracle evaluated point by point at those voxels; plus idempotence of the fill and the
+"nothing left to do" property of a conditional pass over a loaded grid."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+BB = ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))
+
+
+def gather_texels(S, v, idx):
+    """tex0 / tex1 texels of the voxels idx[n,3] (global indices inside the handle's stored slices),
+    read from HBM through a torch view of the library's memory (plumbing only)."""
+    import torch
+    from sdf_viewer_b200.sharded import _DevMem
+    W, H, D = v.dims
+    n = W * H * (v.z_hi - v.z_lo)
+    p0, p1 = v.device_ptrs()
+    flat = ((idx[:, 2].astype(np.int64) - v.z_lo) * H + idx[:, 1]) * W + idx[:, 0]
+    fi = torch.from_numpy(flat).cuda()
+    v.sync()
+    out = []
+    for p in (p0, p1):
+        t = torch.as_tensor(_DevMem(p, n * 4, "<f4"), device="cuda").view(n, 4)
+        out.append(t[fi].cpu().numpy())
+    return out
+
+
+def sample_indices(dims, n, rng, z_range=None):
+    z0, z1 = z_range or (0, dims[2])
+    idx = np.stack([rng.integers(0, dims[0], n), rng.integers(0, dims[1], n), rng.integers(z0, z1, n)], 1)
+    xs, ys, zs = [0, dims[0] - 1, dims[0] // 2], [0, dims[1] - 1, dims[1] // 2], [z0, z1 - 1, (z0 + z1) // 2]
+    special = np.array([(x, y, z) for x in xs for y in ys for z in zs])
+    return np.concatenate([idx, special]).astype(np.uint32)
+
+
+@pytest.mark.parametrize("workload,side", [("demo", 256), ("demo", 512), ("csg", 512)])
+def test_full_size_subset_parity(S, oracle, workload, side):
+    """BASELINE configs 2 / 3 and the bench workload: 256^3 and 512^3, default fill path (specialised kernel)."""
+    tape = S.tape.demo_tape() if workload == "demo" else S.tape.csg_tape()
+    dims = (side, side, side)
+    rng = np.random.default_rng(side)
+    idx = sample_indices(dims, 300_000, rng)
+    o = oracle.Viewer(BB, dims, 2, alloc=False)
+    want0, want1 = o.sample_voxels(oracle.Sampler(tape=tape), idx)
+    with S.SDFViewer.from_bb(BB, side, 2) as v:
+        v.set_tape(tape)
+        v.fill_all()
+        assert v.get_info("last_fill_program") in (1, 2)
+        got0, got1 = gather_texels(S, v, idx)
+        assert np.array_equal(got0.view(np.uint32), want0.view(np.uint32))
+        assert np.array_equal(got1.view(np.uint32), want1.view(np.uint32))
+        # idempotence: a second fill and a progressive conditional update change nothing
+        v.fill_all()
+        again0, again1 = gather_texels(S, v, idx)
+        assert np.array_equal(again0.view(np.uint32), got0.view(np.uint32))
+        v.reset(2)
+        its = v.update(None)
+        assert its == sum(S.loading.pass_items(dims, s) for s in S.loading.pass_steps(2))
+        upd0, upd1 = gather_texels(S, v, idx)
+        assert np.array_equal(upd0.view(np.uint32), want0.view(np.uint32))
+        assert np.array_equal(upd1.view(np.uint32), want1.view(np.uint32))
+        # a resample of a box with the same tape leaves the volume as it is and reports how many voxels it touched
+        n = v.resample_box((-0.25, -0.25, -0.25, 0.25, 0.25, 0.25), count=True)
+        k = len([i for i in range(side) if -0.25 <= o.voxel_pos(i, 0, 0)[0] <= 0.25])
+        assert n >= k ** 3
+        r0, _ = gather_texels(S, v, idx)
+        assert np.array_equal(r0.view(np.uint32), want0.view(np.uint32))
+
+
+def test_slab_of_1024_cubed(S, oracle):
+    """BASELINE config 4 geometry: one rank's slab (128 slices + halo) of the 1024^3 grid sharded 8 ways."""
+    dims = (1024, 1024, 1024)
+    rank = 3
+    zr = (rank * 128, (rank + 1) * 128)
+    tape = S.tape.demo_tape()
+    with S.SDFViewer.new_voxels(dims, BB, 2, z_range=zr) as v:
+        assert (v.z_lo, v.z_hi) == (zr[0] - 1, zr[1] + 1)
+        v.set_tape(tape)
+        v.fill_all()
+        rng = np.random.default_rng(4)
+        idx = sample_indices(dims, 200_000, rng, z_range=(v.z_lo, v.z_hi))  # includes both halo slices
+        o = oracle.Viewer(BB, dims, 2, alloc=False)
+        want0, want1 = o.sample_voxels(oracle.Sampler(tape=tape), idx)
+        got0, got1 = gather_texels(S, v, idx)
+        assert np.array_equal(got0.view(np.uint32), want0.view(np.uint32))
+        assert np.array_equal(got1.view(np.uint32), want1.view(np.uint32))
+
+
+def test_trace_1080p_rows_parity(S, oracle):
+    """BASELINE config 2: 256^3 grid, 1920x1080 trace; the oracle traces a band of rows (CPU time) of the
+    same frame from the downloaded volume."""
+    w, h = 1920, 1080
+    with S.SDFViewer.from_bb(BB, 256, 2) as v:
+        v.set_tape(S.tape.demo_tape())
+        v.update(None)
+        v.commit()
+        cam = S.default_camera(w, h)
+        rg, dg, gg = v.trace(cam, w, h, gbuf=True)
+        t0, t1 = v.download()
+        _, _, lod, lin = v.trace_params(cam, w, h)
+    rows = (500, 560)
+    P = oracle.trace_params(S.camera_rays(cam, w, h), BB, (256, 256, 256), lod=lod, filter_linear=lin)
+    ro, do, go = oracle.trace(P, t0, t1, w, h, rows=rows)
+    sl = slice(*rows)
+    assert np.array_equal(gg[sl][..., 3] < 0, go[sl][..., 3] < 0)
+    assert np.array_equal(gg[sl][..., 15], go[sl][..., 15])
+    hit = go[sl][..., 3] >= 0
+    assert hit.mean() > 0.1
+    np.testing.assert_allclose(gg[sl][hit], go[sl][hit], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(rg[sl], ro[sl], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dg[sl], do[sl], rtol=1e-5)
