@@ -169,7 +169,14 @@ uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
 void set_device(sdfgpu_ctx* ctx) { (void)cudaSetDevice(ctx->device); }
 
-int default_vpt(const sdfgpu_ctx* ctx) { return ctx->opt_vpt ? ctx->opt_vpt : 4; }
+// voxels per thread: 8 for the straight-line kernels (specialised / built in), 4 for the interpreter
+// (measured on B200, tools/sweep_minb.py)
+int default_vpt(const sdfgpu_ctx* ctx) {
+    if (ctx->opt_vpt) return ctx->opt_vpt;
+    if (ctx->opt_program == 1) return 4;
+    if (ctx->opt_program != 2 && ctx->opcodes.size() <= 96 && jit_available(nullptr)) return 8;
+    return ctx->structure_is_demo ? 8 : 4;
+}
 
 // one fill launch over lattice {r0 + i*step} restricted to the index box [lo, hi) per axis
 int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_t hi[3], bool conditional,

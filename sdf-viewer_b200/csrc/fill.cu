@@ -28,7 +28,7 @@ fill_fn pick(int V, int program) {
         case 1: return demo ? fill_kernel<1, dev::PROG_DEMO, 4> : fill_kernel<1, dev::PROG_INTERPRET, 4>;
         case 2: return demo ? fill_kernel<2, dev::PROG_DEMO, 3> : fill_kernel<2, dev::PROG_INTERPRET, 3>;
         case 4: return demo ? fill_kernel<4, dev::PROG_DEMO, 2> : fill_kernel<4, dev::PROG_INTERPRET, 2>;
-        case 8: return demo ? fill_kernel<8, dev::PROG_DEMO, 1> : fill_kernel<8, dev::PROG_INTERPRET, 1>;
+        case 8: return demo ? fill_kernel<8, dev::PROG_DEMO, 2> : fill_kernel<8, dev::PROG_INTERPRET, 1>;
         default: return nullptr;
     }
 }

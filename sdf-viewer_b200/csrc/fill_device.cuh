@@ -130,7 +130,7 @@ __device__ __forceinline__ Smp prim_sample(const float4 geom, const float4 m0, c
     } else {
         float nx, ny, nz;
         if (SHAPE == SDFT_SHAPE_SPHERE) {  // cgmath normalize = v * (1 / |v|), sphere.rs:123
-            const float inv = 1.0f / len;
+            const float inv = __frcp_rn(len);  // correctly rounded 1 / len == IEEE 1.0f / len
             nx = qx * inv; ny = qy * inv; nz = qz * inv;
         } else {  // cube.rs:164-177
             nx = fabsf(qx) > geom.w ? signum_not_nan(qx) : 0.0f;
