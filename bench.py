@@ -92,14 +92,16 @@ def peaks():
 
 
 def cpu_fill_sample(orc, tape, dims, threads, target_s=6.0):
-    """Oracle fill (OpenMP over z) on a bounded z-range of the same grid; returns samples/s."""
+    """Oracle fill (OpenMP over z, all host threads) on a bounded sample of the same grid; samples/s."""
     v = orc.Viewer(BB, dims, 1)
     s = orc.Sampler(tape=tape)
     mid = dims[2] // 2
-    t = time.perf_counter(); v.fill_all(s, mid, mid + 1, threads); per_slice = time.perf_counter() - t
-    nz = max(1, min(dims[2], int(target_s / max(per_slice, 1e-6))))
+    probe = min(dims[2], max(1, 2 * threads))  # enough slices to occupy every thread
+    z0 = max(0, mid - probe // 2)
+    t = time.perf_counter(); v.fill_all(s, z0, z0 + probe, threads); per_slice = (time.perf_counter() - t) / probe
+    nz = max(probe, min(dims[2], int(target_s / max(per_slice, 1e-9))))
+    reps = max(1, min(16, int(target_s / max(per_slice * nz, 1e-9))))
     z0 = max(0, mid - nz // 2)
-    reps = max(1, min(8, int(target_s / max(per_slice * nz, 1e-6))))
     t = time.perf_counter()
     n = sum(v.fill_all(s, z0, z0 + nz, threads) for _ in range(reps))
     dt = time.perf_counter() - t
