@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--vpt", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused-halo", action="store_true", help="exchange halos with NCCL send/recv instead of in-kernel peer stores")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -179,7 +180,7 @@ def main():
     cam = S.default_camera(W, H)
 
     from sdf_viewer_b200.sharded import ShardedViewer
-    sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist)
+    sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, fused=not args.no_fused_halo)
     v = sv.viewer
     if args.vpt:
         v.set_option("fill_voxels_per_thread", args.vpt)
@@ -266,7 +267,8 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{'demo_sdf' if args.workload == 'demo' else 'csg_1k'} {dims[0]}x{dims[1]}x{dims[2]} "
                                f"grid fill + {W}x{H} sphere trace, default scene camera",
-                   "sharding": f"z-slabs x{n_gpus}" if n_gpus > 1 else "single GPU",
+                   "sharding": (f"z-slabs x{n_gpus}, halo exchange: " + ("fused peer stores inside the fill kernel (CUDA IPC over NVLink)"
+                                if sv.fused else "NCCL send/recv after the fill")) if n_gpus > 1 else "single GPU",
                    "l2": "volume (32 B/voxel) exceeds the 126 MB L2, no flush needed" if own_voxels * 32 > 2.5e8 else "volume fits L2",
                    "step": "fill_all + commit + trace (lod 1, LINEAR filter, fp32 trilinear)"},
         "fill_ms": fill_ms, "trace_ms": trace_ms,
@@ -282,7 +284,7 @@ def main():
     if n_gpus > 1:
         out["e2e"]["d2h_bytes_per_step"] = W * H * 8
         out["e2e"]["what"] = ("set_tape (H2D) + fill + NCCL halo exchange + slab trace + all-reduce(MIN) composite + "
-                              "frame RGBA8+depth D2H")
+                              "frame RGBA8+depth D2H").replace("NCCL halo exchange", "fused halo exchange" if sv.fused else "NCCL halo exchange")
     if not args.no_cpu_baseline and n_gpus == 1:
         import orc
         orc.build()

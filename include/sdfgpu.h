@@ -65,6 +65,18 @@ int sdfgpu_create_voxels(const float bb[6], const uint32_t voxels[3], uint32_t l
 int sdfgpu_create_slab(const float bb[6], const uint32_t voxels[3], uint32_t loading_passes,
                        int device, uint32_t z_begin, uint32_t z_end, sdfgpu_ctx** out);
 
+/* Fused halo exchange between slab handles that live in different processes on one node (one
+ * process per GPU): a handle exports CUDA IPC handles of its two volumes (2 x 64 bytes:
+ * cudaIpcMemHandle_t of tex0, then of tex1); its neighbours attach them (side 0 = the neighbour
+ * below this handle, 1 = above; [peer_z_lo, peer_z_hi) = the neighbour's stored slices).  From
+ * then on every fill of this handle also stores its first / last owned slice straight into the
+ * neighbour's halo slice over NVLink, inside the fill kernel -- no separate exchange step.  The
+ * caller orders fills and traces across ranks (a stream-ordered barrier).  Not in the reference. */
+int sdfgpu_ipc_export(sdfgpu_ctx* ctx, void* handles, size_t handles_bytes);
+int sdfgpu_ipc_attach(sdfgpu_ctx* ctx, int side, const void* handles, size_t handles_bytes,
+                      uint32_t peer_z_lo, uint32_t peer_z_hi);
+int sdfgpu_ipc_detach(sdfgpu_ctx* ctx);
+
 /* Dropping the SDFViewer (scene/mod.rs:154-155 rebuilds it on every set_sdf). */
 void sdfgpu_destroy(sdfgpu_ctx* ctx);
 

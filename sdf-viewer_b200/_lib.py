@@ -64,6 +64,9 @@ SIGNATURES = {
     "sdfgpu_create": (C.c_int, [_fp, _u32, _u32, C.c_int, _vpp]),
     "sdfgpu_create_voxels": (C.c_int, [_fp, _u32p, _u32, C.c_int, _vpp]),
     "sdfgpu_create_slab": (C.c_int, [_fp, _u32p, _u32, C.c_int, _u32, _u32, _vpp]),
+    "sdfgpu_ipc_export": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "sdfgpu_ipc_attach": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _u32, _u32]),
+    "sdfgpu_ipc_detach": (C.c_int, [_vp]),
     "sdfgpu_destroy": (None, [_vp]),
     "sdfgpu_last_error": (C.c_char_p, [_vp]),
     "sdfgpu_dims": (C.c_int, [_vp, _u32p]),

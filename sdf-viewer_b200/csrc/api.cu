@@ -102,6 +102,10 @@ struct sdfgpu_ctx {
     float* gbuf_dev = nullptr;
     unsigned long long* keys_dev = nullptr;
     unsigned long long* touched_dev = nullptr;
+    // neighbours' volumes opened with cudaIpcOpenMemHandle (fused halo exchange)
+    float4* peer_tex0[2] = {nullptr, nullptr};
+    float4* peer_tex1[2] = {nullptr, nullptr};
+    uint32_t peer_z_lo[2] = {0, 0};
     // options
     int opt_vpt = 0;        // voxels per thread (0 = default)
     int opt_ctas = 0;       // CTAs per SM (0 = as many as fit)
@@ -207,6 +211,14 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
     if (ctx->has_changed_box) memcpy(p.box, ctx->changed_box, sizeof p.box);
     p.air_dist = air_dist_value();
     p.touched = touched;
+    for (int side = 0; side < 2; ++side) {
+        if (!ctx->peer_tex0[side]) continue;
+        p.peer_mask |= 1u << side;
+        p.peer_slice[side] = side == 0 ? ctx->z_begin : ctx->z_end - 1;
+        p.peer_z_lo[side] = ctx->peer_z_lo[side];
+        p.peer_tex0[side] = ctx->peer_tex0[side];
+        p.peer_tex1[side] = ctx->peer_tex1[side];
+    }
     const uint32_t n_cull = (ctx->hdr.flags & TAPE_FLAG_CULL) ? ctx->hdr.cull_count : 0u;
     const size_t smem = fill_smem_bytes(p.tape_img_bytes, n_cull, ctx->hdr.max_stack, V, &p.stack_floats);
     if (smem > 227u * 1024u)
@@ -385,10 +397,65 @@ SDFGPU_API int sdfgpu_create_slab(const float bb[6], const uint32_t voxels[3], u
     return create_common(bb, voxels, loading_passes, device, z_begin, z_end, out);
 }
 
+SDFGPU_API int sdfgpu_ipc_detach(sdfgpu_ctx* ctx) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    set_device(ctx);
+    if (ctx->stream) (void)cudaStreamSynchronize(ctx->stream);
+    for (int side = 0; side < 2; ++side) {
+        if (ctx->peer_tex0[side]) (void)cudaIpcCloseMemHandle(ctx->peer_tex0[side]);
+        if (ctx->peer_tex1[side]) (void)cudaIpcCloseMemHandle(ctx->peer_tex1[side]);
+        ctx->peer_tex0[side] = ctx->peer_tex1[side] = nullptr;
+    }
+    (void)cudaGetLastError();
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_ipc_export(sdfgpu_ctx* ctx, void* handles, size_t handles_bytes) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (!handles || handles_bytes < 2 * sizeof(cudaIpcMemHandle_t))
+        return fail(ctx, SDFGPU_ERR_INVALID, "handles buffer must hold 2 x %zu bytes", sizeof(cudaIpcMemHandle_t));
+    if (!ctx->tex0 || !ctx->tex1) return fail(ctx, SDFGPU_ERR_STATE, "handle stores no voxels");
+    set_device(ctx);
+    cudaIpcMemHandle_t h[2];
+    CK(ctx, cudaIpcGetMemHandle(&h[0], ctx->tex0));
+    CK(ctx, cudaIpcGetMemHandle(&h[1], ctx->tex1));
+    memcpy(handles, h, sizeof h);
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_ipc_attach(sdfgpu_ctx* ctx, int side, const void* handles, size_t handles_bytes,
+                                 uint32_t peer_z_lo, uint32_t peer_z_hi) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (side != 0 && side != 1) return fail(ctx, SDFGPU_ERR_INVALID, "side must be 0 (lower) or 1 (upper)");
+    if (!handles || handles_bytes < 2 * sizeof(cudaIpcMemHandle_t)) return fail(ctx, SDFGPU_ERR_INVALID, "bad handles buffer");
+    if (ctx->z_begin == ctx->z_end) return fail(ctx, SDFGPU_ERR_STATE, "this handle owns no slices");
+    // the slice this rank mirrors must be one the neighbour stores (its halo)
+    const uint32_t mirrored = side == 0 ? ctx->z_begin : ctx->z_end - 1;
+    if (!(mirrored >= peer_z_lo && mirrored < peer_z_hi))
+        return fail(ctx, SDFGPU_ERR_INVALID, "slice %u is not stored by the neighbour [%u,%u)", mirrored, peer_z_lo, peer_z_hi);
+    if (ctx->peer_tex0[side]) return fail(ctx, SDFGPU_ERR_STATE, "side %d already attached", side);
+    set_device(ctx);
+    cudaIpcMemHandle_t h[2];
+    memcpy(h, handles, sizeof h);
+    void *p0 = nullptr, *p1 = nullptr;
+    CK(ctx, cudaIpcOpenMemHandle(&p0, h[0], cudaIpcMemLazyEnablePeerAccess));
+    cudaError_t e = cudaIpcOpenMemHandle(&p1, h[1], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        (void)cudaIpcCloseMemHandle(p0);
+        (void)cudaGetLastError();
+        return fail(ctx, SDFGPU_ERR_CUDA, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    ctx->peer_tex0[side] = (float4*)p0;
+    ctx->peer_tex1[side] = (float4*)p1;
+    ctx->peer_z_lo[side] = peer_z_lo;
+    return SDFGPU_OK;
+}
+
 SDFGPU_API void sdfgpu_destroy(sdfgpu_ctx* ctx) {
     if (!ctx) return;
     set_device(ctx);
     if (ctx->stream) (void)cudaStreamSynchronize(ctx->stream);
+    (void)sdfgpu_ipc_detach(ctx);
     (void)cudaFree(ctx->tex0); (void)cudaFree(ctx->tex1); (void)cudaFree(ctx->img_dev);
     (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
     (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->touched_dev);

@@ -236,6 +236,19 @@ class SDFViewer:
                                              _host_ptr(depth)), self._h)
         return rgba8, depth
 
+    # ---- fused halo exchange (multi-GPU, one process per GPU)
+    def ipc_export(self):
+        buf = C.create_string_buffer(128)
+        check(self._lib.sdfgpu_ipc_export(self._h, buf, len(buf)), self._h)
+        return buf.raw
+
+    def ipc_attach(self, side, handles, peer_z_lo, peer_z_hi):
+        buf = C.create_string_buffer(bytes(handles), len(handles))
+        check(self._lib.sdfgpu_ipc_attach(self._h, int(side), buf, len(handles), int(peer_z_lo), int(peer_z_hi)), self._h)
+
+    def ipc_detach(self):
+        check(self._lib.sdfgpu_ipc_detach(self._h), self._h)
+
     # ---- stream
     def sync(self):
         check(self._lib.sdfgpu_sync(self._h), self._h)

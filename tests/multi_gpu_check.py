@@ -19,6 +19,15 @@ from sdf_viewer_b200.sharded import ShardedViewer  # noqa: E402
 BB = ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))
 
 
+def check_slab(sv, v, full, dims, rank):
+    """Owned slices and exchanged halo slices equal the oracle's full volume, bit for bit."""
+    v.sync(); torch.cuda.synchronize(); dist.barrier()
+    for t, want in zip(sv._tex, (full.tex0, full.tex1)):
+        got = t.cpu().numpy().reshape(v.z_hi - v.z_lo, dims[1], dims[0], 4)
+        assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(want[v.z_lo:v.z_hi]).view(np.uint32)), \
+            f"rank {rank}: stored slab [{v.z_lo},{v.z_hi}) differs from the oracle (halo exchange, fused={sv.fused})"
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -26,19 +35,23 @@ def main():
     dims = (48, 40, 36)
     w, h = 200, 150
     sdf = S.SDFDemo()
-    sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist)
-    v = sv.viewer
-    its = sv.update(sdf)                       # both passes + halo exchange over NCCL
-    sv.commit()
     full = orc.Viewer(BB, dims, 2)
-    assert full.update(orc.Sampler(tape=sdf.tape())) == its
-    v.sync(); torch.cuda.synchronize()
-    # owned slices and exchanged halo slices equal the oracle's full volume, bit for bit
+    want_its = full.update(orc.Sampler(tape=sdf.tape()))
+    fused_modes = []
+    for fused in (False, True):                # NCCL send/recv exchange, then the fused in-kernel P2P exchange
+        sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, fused=fused)
+        fused_modes.append(sv.fused)
+        v = sv.viewer
+        its = sv.update(S.SDFDemo())           # both passes + halo exchange
+        sv.commit()
+        assert its == want_its
+        check_slab(sv, v, full, dims, rank)
+        if not fused:
+            sv.close()
+    assert fused_modes[0] is False
+    if rank == 0:
+        print("fused halo exchange:", "CUDA IPC peer stores" if fused_modes[1] else "unavailable, NCCL send/recv used")
     n = dims[0] * dims[1] * 4
-    for t, want in zip(sv._tex, (full.tex0, full.tex1)):
-        got = t.cpu().numpy().reshape(v.z_hi - v.z_lo, dims[1], dims[0], 4)
-        assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(want[v.z_lo:v.z_hi]).view(np.uint32)), \
-            f"rank {rank}: stored slab [{v.z_lo},{v.z_hi}) differs from the oracle (halo exchange?)"
     # a locally recomputed halo equals the exchanged one (pure function of position)
     with S.SDFViewer.new_voxels(dims, BB, 2, device=local, z_range=(v.z_begin, v.z_end)) as v2:
         v2.set_tape(sdf.tape()); v2.fill_all(); v2.sync()
