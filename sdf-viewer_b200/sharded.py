@@ -87,6 +87,7 @@ class ShardedViewer:
         self.dims, self.bb, self.rank, self.world, self.device = tuple(dims), bb, rank, world, device
         self.dist = group  # the torch.distributed module (None when world == 1)
         self.fused = False
+        self._synced = True  # no rank can still be reading a halo slice (nothing has been traced yet)
         if world > 1:
             zr = slab_range(dims[2], rank, world)
             self.viewer = SDFViewer.new_voxels(dims, bb, loading_passes, device=device, z_range=zr)
@@ -140,14 +141,17 @@ class ShardedViewer:
             self.dist.all_reduce(self._flag)
 
     def _before_fill(self):
-        if self.world > 1 and self.fused:
-            self._barrier()  # neighbours have finished reading the halo slices this fill will overwrite
+        # a neighbour may still be reading the halo slices this fill overwrites -- unless the last thing
+        # every rank did was a collective that came after its reads (the compositing all-reduce)
+        if self.world > 1 and self.fused and not self._synced:
+            self._barrier()
 
     def _after_fill(self):
         if self.world == 1:
             return
         if self.fused:
             self._barrier()  # every rank's fill, and with it every halo slice, is complete
+            self._synced = True
         else:
             with self._torch.cuda.stream(self._stream):  # NCCL orders itself after / before this stream
                 exchange_halos(self.dist, self._tex, self.dims, self.rank, self.world)
@@ -172,6 +176,7 @@ class ShardedViewer:
         kt = t.as_tensor(_DevMem(keys, width * height, "<i8"), device=t.device("cuda", self.device))
         with t.cuda.stream(self._stream):
             self.dist.all_reduce(kt, op=self.dist.ReduceOp.MIN)  # keys are < 2^62: signed MIN == unsigned MIN
+        self._synced = True  # every rank's trace (its halo reads) precedes the completion of this all-reduce
         return keys
 
     def trace_device(self, cam, width, height):
