@@ -267,7 +267,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{'demo_sdf' if args.workload == 'demo' else 'csg_1k'} {dims[0]}x{dims[1]}x{dims[2]} "
                                f"grid fill + {W}x{H} sphere trace, default scene camera",
-                   "sharding": (f"z-slabs x{n_gpus}, halo exchange: " + ("fused peer stores inside the fill kernel (CUDA IPC over NVLink)"
+                   "sharding": (f"z-slabs x{n_gpus}, halo exchange: " + ("fused: boundary slices pushed by DMA over NVLink (CUDA IPC) while the interior fills"
                                 if sv.fused else "NCCL send/recv after the fill")) if n_gpus > 1 else "single GPU",
                    "l2": "volume (32 B/voxel) exceeds the 126 MB L2, no flush needed" if own_voxels * 32 > 2.5e8 else "volume fits L2",
                    "step": "fill_all + commit + trace (lod 1, LINEAR filter, fp32 trilinear)"},

@@ -68,10 +68,11 @@ int sdfgpu_create_slab(const float bb[6], const uint32_t voxels[3], uint32_t loa
 /* Fused halo exchange between slab handles that live in different processes on one node (one
  * process per GPU): a handle exports CUDA IPC handles of its two volumes (2 x 64 bytes:
  * cudaIpcMemHandle_t of tex0, then of tex1); its neighbours attach them (side 0 = the neighbour
- * below this handle, 1 = above; [peer_z_lo, peer_z_hi) = the neighbour's stored slices).  From
- * then on every fill of this handle also stores its first / last owned slice straight into the
- * neighbour's halo slice over NVLink, inside the fill kernel -- no separate exchange step.  The
- * caller orders fills and traces across ranks (a stream-ordered barrier).  Not in the reference. */
+ * below this handle, 1 = above; [peer_z_lo, peer_z_hi) = the neighbour's stored slices).  From then
+ * on sdfgpu_fill_all fills the two boundary slices first and lets the copy engines push them
+ * into the neighbours' halo slices over NVLink while the interior is being filled; update /
+ * resample_box push them after their last pass.  The caller orders fills and traces across ranks
+ * (a stream-ordered barrier).  Not in the reference. */
 int sdfgpu_ipc_export(sdfgpu_ctx* ctx, void* handles, size_t handles_bytes);
 int sdfgpu_ipc_attach(sdfgpu_ctx* ctx, int side, const void* handles, size_t handles_bytes,
                       uint32_t peer_z_lo, uint32_t peer_z_hi);

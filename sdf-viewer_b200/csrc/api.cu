@@ -106,6 +106,8 @@ struct sdfgpu_ctx {
     float4* peer_tex0[2] = {nullptr, nullptr};
     float4* peer_tex1[2] = {nullptr, nullptr};
     uint32_t peer_z_lo[2] = {0, 0};
+    cudaStream_t halo_stream = nullptr;  // DMA pushes of the boundary slices, overlapped with the interior fill
+    cudaEvent_t ev_boundary = nullptr, ev_pushed = nullptr;
     // options
     int opt_vpt = 0;        // voxels per thread (0 = default)
     int opt_ctas = 0;       // CTAs per SM (0 = as many as fit)
@@ -211,14 +213,6 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
     if (ctx->has_changed_box) memcpy(p.box, ctx->changed_box, sizeof p.box);
     p.air_dist = air_dist_value();
     p.touched = touched;
-    for (int side = 0; side < 2; ++side) {
-        if (!ctx->peer_tex0[side]) continue;
-        p.peer_mask |= 1u << side;
-        p.peer_slice[side] = side == 0 ? ctx->z_begin : ctx->z_end - 1;
-        p.peer_z_lo[side] = ctx->peer_z_lo[side];
-        p.peer_tex0[side] = ctx->peer_tex0[side];
-        p.peer_tex1[side] = ctx->peer_tex1[side];
-    }
     const uint32_t n_cull = (ctx->hdr.flags & TAPE_FLAG_CULL) ? ctx->hdr.cull_count : 0u;
     const size_t smem = fill_smem_bytes(p.tape_img_bytes, n_cull, ctx->hdr.max_stack, V, &p.stack_floats);
     if (smem > 227u * 1024u)
@@ -260,6 +254,22 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
     }
     ctx->last_program = program; ctx->last_ctas = per_sm; ctx->last_vpt = V;
     ctx->launches++;
+    return SDFGPU_OK;
+}
+
+bool has_peers(const sdfgpu_ctx* ctx) { return ctx->peer_tex0[0] || ctx->peer_tex0[1]; }
+
+// Copy this handle's first / last owned slice (both volumes) into the neighbours' halo slices:
+// device-to-device copies into the IPC-mapped peer volumes, i.e. NVLink DMA by the copy engines.
+int push_halos(sdfgpu_ctx* ctx, cudaStream_t s) {
+    const size_t slice = (size_t)ctx->dims[0] * ctx->dims[1];
+    for (int side = 0; side < 2; ++side) {
+        if (!ctx->peer_tex0[side]) continue;
+        const uint32_t z = side == 0 ? ctx->z_begin : ctx->z_end - 1;
+        const size_t src = (size_t)(z - ctx->z_lo) * slice, dst = (size_t)(z - ctx->peer_z_lo[side]) * slice;
+        CK(ctx, cudaMemcpyAsync(ctx->peer_tex0[side] + dst, ctx->tex0 + src, slice * sizeof(float4), cudaMemcpyDeviceToDevice, s));
+        CK(ctx, cudaMemcpyAsync(ctx->peer_tex1[side] + dst, ctx->tex1 + src, slice * sizeof(float4), cudaMemcpyDeviceToDevice, s));
+    }
     return SDFGPU_OK;
 }
 
@@ -401,6 +411,7 @@ SDFGPU_API int sdfgpu_ipc_detach(sdfgpu_ctx* ctx) {
     if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
     set_device(ctx);
     if (ctx->stream) (void)cudaStreamSynchronize(ctx->stream);
+    if (ctx->halo_stream) (void)cudaStreamSynchronize(ctx->halo_stream);
     for (int side = 0; side < 2; ++side) {
         if (ctx->peer_tex0[side]) (void)cudaIpcCloseMemHandle(ctx->peer_tex0[side]);
         if (ctx->peer_tex1[side]) (void)cudaIpcCloseMemHandle(ctx->peer_tex1[side]);
@@ -459,6 +470,9 @@ SDFGPU_API void sdfgpu_destroy(sdfgpu_ctx* ctx) {
     (void)cudaFree(ctx->tex0); (void)cudaFree(ctx->tex1); (void)cudaFree(ctx->img_dev);
     (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
     (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->touched_dev);
+    if (ctx->halo_stream) (void)cudaStreamDestroy(ctx->halo_stream);
+    if (ctx->ev_boundary) (void)cudaEventDestroy(ctx->ev_boundary);
+    if (ctx->ev_pushed) (void)cudaEventDestroy(ctx->ev_pushed);
     if (ctx->stream) (void)cudaStreamDestroy(ctx->stream);
     (void)cudaGetLastError();
     delete ctx;
@@ -724,6 +738,10 @@ SDFGPU_API int sdfgpu_update(sdfgpu_ctx* ctx, const float* changed_box, uint32_t
         ctx->lm.finish_pass();
         ++done;
     }
+    if (done && has_peers(ctx)) {
+        const int rc = push_halos(ctx, ctx->stream);
+        if (rc != SDFGPU_OK) return rc;
+    }
     if (iterations) *iterations = ctx->lm.total_iterations - start_iter;  // :216
     return SDFGPU_OK;
 }
@@ -733,9 +751,31 @@ SDFGPU_API int sdfgpu_fill_all(sdfgpu_ctx* ctx) {
     set_device(ctx);
     uint32_t za, zb;
     fill_z_range(ctx, &za, &zb);
-    const uint32_t lo[3] = {0, 0, za}, hi[3] = {ctx->dims[0], ctx->dims[1], zb};
-    const int rc = run_fill(ctx, 1, lo, hi, false, nullptr);
-    if (rc != SDFGPU_OK) return rc;
+    int rc;
+    if (has_peers(ctx) && ctx->z_end - ctx->z_begin >= 3) {
+        // fused halo exchange: fill the boundary slices first, then let the copy engines push them into
+        // the neighbours' halo slices over NVLink WHILE the interior is being filled
+        if (!ctx->halo_stream) {
+            CK(ctx, cudaStreamCreateWithFlags(&ctx->halo_stream, cudaStreamNonBlocking));
+            CK(ctx, cudaEventCreateWithFlags(&ctx->ev_boundary, cudaEventDisableTiming));
+            CK(ctx, cudaEventCreateWithFlags(&ctx->ev_pushed, cudaEventDisableTiming));
+        }
+        const uint32_t lo0[3] = {0, 0, ctx->z_begin}, hi0[3] = {ctx->dims[0], ctx->dims[1], ctx->z_begin + 1};
+        const uint32_t lo1[3] = {0, 0, ctx->z_end - 1}, hi1[3] = {ctx->dims[0], ctx->dims[1], ctx->z_end};
+        if ((rc = run_fill(ctx, 1, lo0, hi0, false, nullptr)) != SDFGPU_OK) return rc;
+        if ((rc = run_fill(ctx, 1, lo1, hi1, false, nullptr)) != SDFGPU_OK) return rc;
+        CK(ctx, cudaEventRecord(ctx->ev_boundary, ctx->stream));
+        CK(ctx, cudaStreamWaitEvent(ctx->halo_stream, ctx->ev_boundary, 0));
+        if ((rc = push_halos(ctx, ctx->halo_stream)) != SDFGPU_OK) return rc;
+        CK(ctx, cudaEventRecord(ctx->ev_pushed, ctx->halo_stream));
+        const uint32_t lo[3] = {0, 0, ctx->z_begin + 1}, hi[3] = {ctx->dims[0], ctx->dims[1], ctx->z_end - 1};
+        if ((rc = run_fill(ctx, 1, lo, hi, false, nullptr)) != SDFGPU_OK) return rc;
+        CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pushed, 0));
+    } else {
+        const uint32_t lo[3] = {0, 0, za}, hi[3] = {ctx->dims[0], ctx->dims[1], zb};
+        if ((rc = run_fill(ctx, 1, lo, hi, false, nullptr)) != SDFGPU_OK) return rc;
+        if (has_peers(ctx) && (rc = push_halos(ctx, ctx->stream)) != SDFGPU_OK) return rc;
+    }
     while (ctx->lm.step_size != 0) ctx->lm.finish_pass();
     return SDFGPU_OK;
 }
@@ -778,6 +818,7 @@ SDFGPU_API int sdfgpu_resample_box(sdfgpu_ctx* ctx, const float box[6], uint64_t
     if (rc == SDFGPU_OK) rc = run_fill(ctx, 1, lo, hi, true, voxels_touched ? ctx->touched_dev : nullptr);
     ctx->has_changed_box = saved_has;
     memcpy(ctx->changed_box, saved, sizeof saved);
+    if (rc == SDFGPU_OK && has_peers(ctx)) rc = push_halos(ctx, ctx->stream);
     if (rc != SDFGPU_OK) return rc;
     if (voxels_touched) {
         unsigned long long n = 0;

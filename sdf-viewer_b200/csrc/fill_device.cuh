@@ -542,20 +542,6 @@ __device__ __forceinline__ void fill_body(const FillParams& P) {
                 t1.w = P.air_dist;  // never written by the reference: keeps its initial value (:76)
                 store_texel(out0 + v * vstride, t0);
                 store_texel(out1 + v * vstride, t1);
-                // fused halo exchange: the first / last owned slice is also stored straight into the
-                // neighbouring rank's halo slice through its peer-mapped volumes (NVLink); the slice
-                // index is warp-uniform, so this branch does not diverge
-                if (P.peer_mask) {
-                    const uint32_t gz = gz0 + v * P.step;
-#pragma unroll
-                    for (int side = 0; side < 2; ++side) {
-                        if (P.peer_tex0[side] && gz == P.peer_slice[side]) {
-                            const size_t pi = (size_t)(gz - P.peer_z_lo[side]) * slice + (size_t)gy * P.W + gx;
-                            P.peer_tex0[side][pi] = t0;
-                            P.peer_tex1[side][pi] = t1;
-                        }
-                    }
-                }
             }
         }
     }
