@@ -83,6 +83,22 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+def ncu_traffic():
+    """dram bytes read + written per fill launch, from the committed `ncu --set full` capture."""
+    try:
+        rd = wr = None
+        for line in open(os.path.join(ROOT, "profiles", "r01_fill_ncu_summary.txt")):
+            k, _, v = line.partition(" = ")
+            if k.startswith("dram__bytes_"):
+                num, unit = v.split()[:2]
+                val = float(num) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+                if "read" in k: rd = val
+                else: wr = val
+        return rd + wr
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -231,7 +247,7 @@ def main():
         wall_ms = elapsed * 1e3 / args.steps
 
     # ---- end to end through the host-buffer ABI: tape H2D + fill + trace + frame D2H
-    rgba_h = torch.empty((H, W, 4), dtype=torch.float32).pin_memory().numpy()
+    rgba_h = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory().numpy()  # the reference presents an RGBA8 framebuffer
     depth_h = torch.empty((H, W), dtype=torch.float32).pin_memory().numpy()
     e2e_steps = max(3, min(args.steps, 30))
 
@@ -274,11 +290,12 @@ def main():
         "fill_ms": fill_ms, "trace_ms": trace_ms,
         "rays_per_sec": W * H / (trace_ms * 1e-3), "hit_fraction": hit_frac,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "fill_kernel",
+                     "traffic": ncu_traffic() if (n_gpus == 1 and args.grid == 512 and args.workload == "demo") else None,
+                     "traffic_source": "profiles/r01_fill_ncu_summary.txt (ncu --set full, same kernel and grid)", "peak_source": peak_src, "kernel": "fill_kernel",
                      "algorithmic_bytes_per_launch": own_voxels * BYTES_PER_SAMPLE},
         "e2e": {"value": total_voxels / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": len(tape) + 256, "d2h_bytes_per_step": W * H * 20,
-                "what": "set_tape (H2D) + fill + trace + frame RGBA32F+depth D2H into pinned host memory"},
+                "h2d_bytes_per_step": len(tape) + 256, "d2h_bytes_per_step": W * H * 8,
+                "what": "set_tape (H2D) + fill + commit + trace + frame RGBA8+depth D2H into pinned host memory"},
         "gpu_launches": int(launches), "clocks": clocks, "host_ms_per_step": wall_ms,
     }
     if n_gpus > 1:

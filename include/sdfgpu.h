@@ -204,6 +204,12 @@ int sdfgpu_camera_rays(const sdfgpu_camera* cam, uint32_t width, uint32_t height
 int sdfgpu_trace(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width, uint32_t height,
                  float* rgba, float* depth, float* gbuf);
 
+/* The frame as the reference's RGBA8 framebuffer receives it: rgba8 = width*height*4 bytes,
+ * round(clamp(outColor, 0, 1) * 255) per channel, plus gl_FragDepth; 8 bytes per pixel over PCIe
+ * instead of 20.  Either pointer may be NULL. */
+int sdfgpu_trace_rgba8(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width, uint32_t height,
+                       uint8_t* rgba8, float* depth);
+
 /* Same, but leaves the frame in device memory owned by the handle (valid until
  * the next trace with a different size, or destroy) and does not synchronise. */
 int sdfgpu_trace_device(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width,

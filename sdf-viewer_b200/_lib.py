@@ -86,6 +86,7 @@ SIGNATURES = {
     "sdfgpu_perspective": (None, [C.c_float, C.c_float, C.c_float, C.c_float, _fp]),
     "sdfgpu_camera_rays": (C.c_int, [C.POINTER(Camera), _u32, _u32, C.POINTER(Rays)]),
     "sdfgpu_trace": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, _vp, _vp, _vp]),
+    "sdfgpu_trace_rgba8": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, _vp, _vp]),
     "sdfgpu_trace_device": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, C.c_int, _vpp, _vpp, _vpp]),
     "sdfgpu_trace_params": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, C.c_int, _fp, _fp, _fp, _u32p]),
     "sdfgpu_trace_slab_keys": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, _vpp]),

@@ -101,6 +101,7 @@ struct sdfgpu_ctx {
     float* depth_dev = nullptr;
     float* gbuf_dev = nullptr;
     unsigned long long* keys_dev = nullptr;
+    uint32_t* rgba8_dev = nullptr;
     unsigned long long* touched_dev = nullptr;
     // neighbours' volumes opened with cudaIpcOpenMemHandle (fused halo exchange)
     float4* peer_tex0[2] = {nullptr, nullptr};
@@ -469,7 +470,7 @@ SDFGPU_API void sdfgpu_destroy(sdfgpu_ctx* ctx) {
     (void)sdfgpu_ipc_detach(ctx);
     (void)cudaFree(ctx->tex0); (void)cudaFree(ctx->tex1); (void)cudaFree(ctx->img_dev);
     (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
-    (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->touched_dev);
+    (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->rgba8_dev); (void)cudaFree(ctx->touched_dev);
     if (ctx->halo_stream) (void)cudaStreamDestroy(ctx->halo_stream);
     if (ctx->ev_boundary) (void)cudaEventDestroy(ctx->ev_boundary);
     if (ctx->ev_pushed) (void)cudaEventDestroy(ctx->ev_pushed);
@@ -909,8 +910,9 @@ int ensure_frame(sdfgpu_ctx* ctx, uint32_t w, uint32_t h, bool want_gbuf, bool w
     if (w != ctx->fw || h != ctx->fh) {
         CK(ctx, cudaStreamSynchronize(ctx->stream));
         (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
-        (void)cudaFree(ctx->keys_dev);
+        (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->rgba8_dev);
         ctx->rgba_dev = nullptr; ctx->depth_dev = nullptr; ctx->gbuf_dev = nullptr; ctx->keys_dev = nullptr;
+        ctx->rgba8_dev = nullptr;
         ctx->fw = ctx->fh = 0;
         if (n) {
             CK(ctx, cudaMalloc(&ctx->rgba_dev, n * sizeof(float4)));
@@ -978,7 +980,11 @@ int fill_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t w, uin
         x0 = sx < x0 ? sx : x0; x1 = sx > x1 ? sx : x1;
         y0 = sy < y0 ? sy : y0; y1 = sy > y1 ? sy : y1;
     }
-    if (full) {
+    if (ctx->stored_texels == 0) {
+        // an empty volume (a bounding box with a zero-size axis gives 0 voxels, scene/sdf/mod.rs:54-64):
+        // nothing can be sampled, every pixel is a miss
+        tp->rect[0] = tp->rect[1] = tp->rect[2] = tp->rect[3] = 0;
+    } else if (full) {
         tp->rect[0] = tp->rect[1] = 0; tp->rect[2] = tp->tiles_x; tp->rect[3] = tp->tiles_y;
     } else {
         auto clampi = [](double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); };
@@ -1063,7 +1069,7 @@ SDFGPU_API int sdfgpu_trace_device(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, ui
     if ((rc = fill_trace_params(ctx, cam, width, height, false, &tp)) != SDFGPU_OK) return rc;
     tp.rgba = ctx->rgba_dev; tp.depth = ctx->depth_dev;
     tp.gbuf = want_gbuf ? ctx->gbuf_dev : nullptr;
-    CK(ctx, launch_trace(tp, ctx->opt_trace_variant, ctx->stream));
+    CK(ctx, launch_trace(tp, ctx->stored_texels ? ctx->opt_trace_variant : 0, ctx->stream));
     ctx->launches++;
     if (rgba_dev) *rgba_dev = ctx->rgba_dev;
     if (depth_dev) *depth_dev = ctx->depth_dev;
@@ -1080,6 +1086,27 @@ SDFGPU_API int sdfgpu_trace(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t 
     if (rgba) CK(ctx, cudaMemcpyAsync(rgba, r, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     if (depth) CK(ctx, cudaMemcpyAsync(depth, d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (gbuf) CK(ctx, cudaMemcpyAsync(gbuf, g, n * SDFGPU_GBUF_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_trace_rgba8(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width, uint32_t height,
+                                  uint8_t* rgba8, float* depth) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (!cam) return fail(ctx, SDFGPU_ERR_INVALID, "cam is NULL");
+    if (width == 0 || height == 0) return fail(ctx, SDFGPU_ERR_INVALID, "empty frame");
+    set_device(ctx);
+    int rc = ensure_frame(ctx, width, height, false, false);
+    if (rc != SDFGPU_OK) return rc;
+    const size_t n = (size_t)width * height;
+    if (!ctx->rgba8_dev) CK(ctx, cudaMalloc(&ctx->rgba8_dev, n * sizeof(uint32_t)));
+    TraceParams tp;
+    if ((rc = fill_trace_params(ctx, cam, width, height, false, &tp)) != SDFGPU_OK) return rc;
+    tp.rgba8 = ctx->rgba8_dev; tp.depth = ctx->depth_dev;
+    CK(ctx, launch_trace(tp, ctx->stored_texels ? ctx->opt_trace_variant : 0, ctx->stream));
+    ctx->launches++;
+    if (rgba8) CK(ctx, cudaMemcpyAsync(rgba8, ctx->rgba8_dev, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (depth) CK(ctx, cudaMemcpyAsync(depth, ctx->depth_dev, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return SDFGPU_OK;
 }
@@ -1109,7 +1136,7 @@ SDFGPU_API int sdfgpu_trace_slab_keys(sdfgpu_ctx* ctx, const sdfgpu_camera* cam,
     TraceParams tp;
     if ((rc = fill_trace_params(ctx, cam, width, height, true, &tp)) != SDFGPU_OK) return rc;
     tp.keys = ctx->keys_dev;
-    CK(ctx, launch_trace(tp, ctx->opt_trace_variant, ctx->stream));
+    CK(ctx, launch_trace(tp, ctx->stored_texels ? ctx->opt_trace_variant : 0, ctx->stream));
     ctx->launches++;
     *keys_dev = ctx->keys_dev;
     return SDFGPU_OK;

@@ -36,6 +36,7 @@ struct TraceParams {
     float* depth;              // may be null
     float* gbuf;               // may be null
     unsigned long long* keys;  // may be null (sort-last compositing keys)
+    uint32_t* rgba8;           // may be null: the frame as an RGBA8 framebuffer would hold it (round(clamp(c) * 255))
 };
 
 // launchers (fill.cu / trace.cu).  `program`: dev::PROG_INTERPRET or dev::PROG_DEMO (built in)

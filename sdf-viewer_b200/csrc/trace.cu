@@ -226,6 +226,7 @@ __device__ __forceinline__ void write_outside(const TraceParams& P, size_t px) {
         gp[1] = gp[2] = gp[3] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (P.keys) P.keys[px] = pack_key(1.0f, 0.f, 0.f, 0.f, 0.f);
+    if (P.rgba8) P.rgba8[px] = 0u;
 }
 
 template <bool SNAP, bool LINEAR>
@@ -342,6 +343,7 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, ui
         gp[3] = make_float4(g[12], g[13], g[14], g[15]);
     }
     if (P.keys) P.keys[px] = pack_key(depth, out.x, out.y, out.z, out.w);
+    if (P.rgba8) P.rgba8[px] = (uint32_t)(pack_key(depth, out.x, out.y, out.z, out.w) & 0xffffffffull);
 }
 
 // Variant 0 (default): 1-D grid of 8 x 8 pixel tiles (2 warps of 8 x 4), ordered so that the tiles

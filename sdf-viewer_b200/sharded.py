@@ -191,6 +191,8 @@ class ShardedViewer:
         """Frame to host memory.  One GPU: RGBA32F + depth (the shader's outputs).  Sharded: the
         composited RGBA8 + depth (what the keys carry); returned on every rank."""
         if self.world == 1:
+            if rgba_out is not None and rgba_out.dtype == np.uint8:
+                return self.viewer.trace_rgba8(cam, width, height, rgba_out, depth_out)
             out = {}
             if rgba_out is not None:
                 out["rgba"] = rgba_out

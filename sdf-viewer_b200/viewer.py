@@ -210,6 +210,14 @@ class SDFViewer:
                                      _host_ptr(g)), self._h)
         return r, d, g
 
+    def trace_rgba8(self, cam, width, height, out_rgba8=None, out_depth=None):
+        """The frame as an RGBA8 framebuffer holds it (+ depth): (rgba8[h,w,4] uint8, depth[h,w])."""
+        r = out_rgba8 if out_rgba8 is not None else np.empty((height, width, 4), np.uint8)
+        d = out_depth if out_depth is not None else np.empty((height, width), np.float32)
+        check(self._lib.sdfgpu_trace_rgba8(self._h, C.byref(cam), int(width), int(height), _host_ptr(r), _host_ptr(d)),
+              self._h)
+        return r, d
+
     def trace_device(self, cam, width, height, want_gbuf=False):
         """Enqueue the trace; the frame stays in HBM.  Returns device pointers (rgba, depth, gbuf)."""
         r, d, g = C.c_void_p(), C.c_void_p(), C.c_void_p()

