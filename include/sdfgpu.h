@@ -125,6 +125,18 @@ int sdfgpu_fill_all(sdfgpu_ctx* ctx);
  * path.  Launches over the index AABB of the box only. */
 int sdfgpu_resample_box(sdfgpu_ctx* ctx, const float box[6], uint64_t* voxels_touched);
 
+/* Batched ingest for SDFs that have no tape (any existing .wasm SDFSurface; the reference's own
+ * "TODO: Batched sampling", src/sdf/mod.rs:39): the host evaluates sample(p, false) itself for a run
+ * of voxels and hands the raw results over; the GPU applies the store rules of
+ * src/app/scene/sdf/mod.rs:196-208 and writes both volumes.
+ *   sdfgpu_voxel_positions: positions of the voxels [first_flat, first_flat + count) in flat order
+ *     (flat = (z*H + y)*W + x, :177), computed exactly as :179-182 does; xyz = count * 3 floats.
+ *   sdfgpu_ingest_samples: `samples` = count SDFSample records (7 floats = 28 bytes each:
+ *     distance, r, g, b, metallic, roughness, occlusion; src/sdf/mod.rs:104-118 -- the bytes the host
+ *     reads out of WASM memory, src/sdf/wasm/native.rs:204-216) for the same voxels. */
+int sdfgpu_voxel_positions(const sdfgpu_ctx* ctx, uint64_t first_flat, uint64_t count, float* xyz);
+int sdfgpu_ingest_samples(sdfgpu_ctx* ctx, uint64_t first_flat, uint64_t count, const void* samples);
+
 /* SDFViewer::commit (src/app/scene/sdf/mod.rs:220-239): no upload is needed
  * (the volumes already live in HBM); latches
  * lod_dist_between_samples = 2^passes_left for the tracer (:226). */

@@ -76,6 +76,8 @@ SIGNATURES = {
     "sdfgpu_update": (C.c_int, [_vp, _fp, _u32, _u64p]),
     "sdfgpu_fill_all": (C.c_int, [_vp]),
     "sdfgpu_resample_box": (C.c_int, [_vp, _fp, _u64p]),
+    "sdfgpu_voxel_positions": (C.c_int, [_vp, _u64, _u64, _vp]),
+    "sdfgpu_ingest_samples": (C.c_int, [_vp, _u64, _u64, _vp]),
     "sdfgpu_commit": (C.c_int, [_vp]),
     "sdfgpu_loading_state": (C.c_int, [_vp, _u64p, _u64p, _u32p, _u32p]),
     "sdfgpu_reset": (C.c_int, [_vp, _u32]),

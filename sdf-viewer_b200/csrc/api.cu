@@ -102,6 +102,9 @@ struct sdfgpu_ctx {
     float* gbuf_dev = nullptr;
     unsigned long long* keys_dev = nullptr;
     uint32_t* rgba8_dev = nullptr;
+    float* ingest_dev = nullptr;  // staging for sdfgpu_ingest_samples: records, then the LUT
+    size_t ingest_cap = 0;
+    float* lut_dev = nullptr;
     unsigned long long* touched_dev = nullptr;
     // neighbours' volumes opened with cudaIpcOpenMemHandle (fused halo exchange)
     float4* peer_tex0[2] = {nullptr, nullptr};
@@ -471,6 +474,7 @@ SDFGPU_API void sdfgpu_destroy(sdfgpu_ctx* ctx) {
     (void)cudaFree(ctx->tex0); (void)cudaFree(ctx->tex1); (void)cudaFree(ctx->img_dev);
     (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
     (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->rgba8_dev); (void)cudaFree(ctx->touched_dev);
+    (void)cudaFree(ctx->ingest_dev); (void)cudaFree(ctx->lut_dev);
     if (ctx->halo_stream) (void)cudaStreamDestroy(ctx->halo_stream);
     if (ctx->ev_boundary) (void)cudaEventDestroy(ctx->ev_boundary);
     if (ctx->ev_pushed) (void)cudaEventDestroy(ctx->ev_pushed);
@@ -827,6 +831,51 @@ SDFGPU_API int sdfgpu_resample_box(sdfgpu_ctx* ctx, const float box[6], uint64_t
         CK(ctx, cudaStreamSynchronize(ctx->stream));
         *voxels_touched = n;
     }
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_voxel_positions(const sdfgpu_ctx* ctx, uint64_t first_flat, uint64_t count, float* xyz) {
+    if (!ctx || (!xyz && count)) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL argument");
+    const uint64_t W = ctx->dims[0], H = ctx->dims[1], D = ctx->dims[2];
+    if (first_flat + count > W * H * D || first_flat + count < first_flat)
+        return fail(nullptr, SDFGPU_ERR_INVALID, "voxel range out of the grid");
+    for (uint64_t i = 0; i < count; ++i) {  // flat = (z*H + y)*W + x, scene/sdf/mod.rs:177; position :179-182
+        const uint64_t f = first_flat + i;
+        xyz[3 * i + 0] = ctx->px[f % W];
+        xyz[3 * i + 1] = ctx->py[(f / W) % H];
+        xyz[3 * i + 2] = ctx->pz[f / (W * H)];
+    }
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_ingest_samples(sdfgpu_ctx* ctx, uint64_t first_flat, uint64_t count, const void* samples) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (count == 0) return SDFGPU_OK;
+    if (!samples) return fail(ctx, SDFGPU_ERR_INVALID, "samples is NULL");
+    const uint64_t slice = (uint64_t)ctx->dims[0] * ctx->dims[1];
+    const uint64_t lo = (uint64_t)ctx->z_lo * slice, hi = (uint64_t)ctx->z_hi * slice;
+    if (first_flat < lo || first_flat + count > hi || first_flat + count < first_flat)
+        return fail(ctx, SDFGPU_ERR_INVALID, "voxel range [%llu,+%llu) is outside the slices this handle stores",
+                    (unsigned long long)first_flat, (unsigned long long)count);
+    set_device(ctx);
+    if (!ctx->lut_dev) {
+        CK(ctx, cudaMalloc(&ctx->lut_dev, sizeof ctx->lut));
+        CK(ctx, cudaMemcpyAsync(ctx->lut_dev, ctx->lut, sizeof ctx->lut, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const size_t bytes = (size_t)count * 7 * sizeof(float);
+    if (bytes > ctx->ingest_cap) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        (void)cudaFree(ctx->ingest_dev);
+        ctx->ingest_dev = nullptr; ctx->ingest_cap = 0;
+        CK(ctx, cudaMalloc(&ctx->ingest_dev, bytes));
+        ctx->ingest_cap = bytes;
+    }
+    CK(ctx, cudaMemcpyAsync(ctx->ingest_dev, samples, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, launch_ingest(ctx->tex0, ctx->tex1, ctx->ingest_dev, (size_t)(first_flat - lo), (size_t)count, ctx->lut_dev,
+                          air_dist_value(), ctx->sm_count * 8, ctx->stream));
+    ctx->launches++;
+    // the staging buffer is reused by the next call: wait until the kernel has consumed it
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
     return SDFGPU_OK;
 }
 

@@ -20,6 +20,26 @@ __global__ void __launch_bounds__(256) set_const_kernel(float4* __restrict__ dst
         dst[i] = val;
 }
 
+// Batched ingest of samples computed elsewhere (a CPU / WASM SDFSurface::sample):
+// `samples` holds n SDFSample records (7 floats, src/sdf/mod.rs:104-118) for the n voxels that
+// start at flat index `first` of the stored slab; applies the store rules of scene/sdf/mod.rs:196-208.
+__global__ void __launch_bounds__(256) ingest_kernel(float4* __restrict__ tex0, float4* __restrict__ tex1,
+                                                     const float* __restrict__ samples, size_t first, size_t n,
+                                                     const float* __restrict__ lut, float air_dist) {
+    __shared__ float s_lut[256];
+    s_lut[threadIdx.x] = lut[threadIdx.x];
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float* r = samples + 7 * i;
+        dev::Smp s;
+        s.d = r[0]; s.r = r[1]; s.g = r[2]; s.b = r[3]; s.m = r[4]; s.ro = r[5]; s.o = r[6];
+        float4 t0, t1;
+        dev::store_rules(s, s_lut, air_dist, t0, t1);
+        tex0[first + i] = t0;
+        tex1[first + i] = t1;
+    }
+}
+
 typedef void (*fill_fn)(const FillParams);
 
 fill_fn pick(int V, int program) {
@@ -62,6 +82,13 @@ cudaError_t launch_fill(const FillParams& p, int V, int program, int grid, size_
     fill_fn f = pick(V, program);
     if (!f) return cudaErrorInvalidValue;
     f<<<grid, FILL_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ingest(float4* tex0, float4* tex1, const float* samples_dev, size_t first, size_t n,
+                          const float* lut_dev, float air_dist, int grid, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    ingest_kernel<<<grid, 256, 0, s>>>(tex0, tex1, samples_dev, first, n, lut_dev, air_dist);
     return cudaGetLastError();
 }
 

@@ -184,6 +184,22 @@ __device__ __forceinline__ void stack_load(const float* st, Smp& s) {
     s.m = st[4 * NT]; s.ro = st[5 * NT]; s.o = st[6 * NT];
 }
 
+// The store rules of scene/sdf/mod.rs:196-208 for one sample: tex0 = (clamp(0.1 + d, 0, 1),
+// linear rgb of the u8-quantised colour, grey if the colour is exactly black), tex1 = (metallic,
+// roughness, occlusion or 1 if <= 0, AIR_DIST -- never written by the reference, :76).
+__device__ __forceinline__ void store_rules(Smp s, const float* lut, float air_dist, float4& t0, float4& t1) {
+    t0.x = fminf(fmaxf(1e-1f + s.d, 0.0f), 1.0f);  // f32::clamp; NaN stays NaN below
+    if (s.d != s.d) t0.x = s.d;
+    if (s.r == 0.0f && s.g == 0.0f && s.b == 0.0f) { s.r = 0.5f; s.g = 0.5f; s.b = 0.5f; }
+    t0.y = lut[f32_to_u8_sat(s.r)];
+    t0.z = lut[f32_to_u8_sat(s.g)];
+    t0.w = lut[f32_to_u8_sat(s.b)];
+    t1.x = s.m;
+    t1.y = s.ro;
+    t1.z = (s.o <= 0.0f) ? 1.0f : s.o;
+    t1.w = air_dist;
+}
+
 // ------------------------------------------------------------ tape machine
 // Machine model of include/sdfgpu_tape.h for V voxels at once: A accumulator, T top of the sample
 // stack (registers; deeper levels in shared memory), q the position register.
@@ -330,6 +346,84 @@ __device__ __forceinline__ void exec_op(const uint4 I, Machine<V>& M, const Env&
     SDFGPU_STEP(DOP_PRIM + 0 * 6 + SDFT_SHAPE_SPHERE * 3 + SDFT_MAT_NORMAL, 2)                               \
     SDFGPU_STEP(DOP_POP_DEMO_DIFF, 3)
 
+// One tile for one thread: V voxels at (lx, ly, lz0 .. lz0 + V - 1) of the lattice.  FULL: the tile
+// lies entirely inside the lattice and the pass is unconditional -- no per-voxel predicates at all.
+template <int V, int PROG, bool FULL>
+__device__ __forceinline__ void tile_body(const FillParams& P, const Env& E, const uint4* s_instr, const float* s_lut,
+                                          const float* s_px, const float* s_py, const float* s_pz, uint32_t lx,
+                                          uint32_t ly, uint32_t lz0, size_t slice, size_t vstride,
+                                          uint32_t& touched_local) {
+    const bool row_ok = FULL || (lx < P.nx && ly < P.ny);
+    const uint32_t gx = P.rx0 + lx * P.step, gy = P.ry0 + ly * P.step, gz0 = P.rz0 + lz0 * P.step;
+    const size_t flat0 = row_ok ? (size_t)(gz0 - P.z_lo) * slice + (size_t)gy * P.W + gx : 0;
+
+    Machine<V> M;
+    M.posx = s_px[FULL ? gx : min(gx, P.W - 1u)];
+    M.posy = s_py[FULL ? gy : min(gy, P.H - 1u)];
+    bool act[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        act[v] = FULL || (row_ok && lz0 + v < P.nz);
+        M.posz[v] = s_pz[FULL ? gz0 + v * P.step : min(gz0 + v * P.step, P.D - 1u)];
+    }
+    if (!FULL && P.conditional) {  // scene/sdf/mod.rs:184-190
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            if (act[v]) {
+                bool need = __ldg(reinterpret_cast<const float*>(P.tex0 + flat0 + v * vstride)) == P.air_dist;
+                if (P.has_box)
+                    need = need || (M.posx >= P.box[0] && M.posx <= P.box[3] && M.posy >= P.box[1] &&
+                                    M.posy <= P.box[4] && M.posz[v] >= P.box[2] && M.posz[v] <= P.box[5]);
+                act[v] = need;
+            }
+        }
+        // nothing to sample in this warp's row (passes over an already loaded region)
+        bool any = false;
+#pragma unroll
+        for (int v = 0; v < V; ++v) { any = any || act[v]; touched_local += act[v] ? 1u : 0u; }
+        if (!__any_sync(0xffffffffu, any)) return;
+    }
+
+    // ---- run the lowered tape
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        M.A[v].d = M.A[v].r = M.A[v].g = M.A[v].b = M.A[v].m = M.A[v].ro = M.A[v].o = 0.0f;
+        M.T[v] = M.A[v];
+        M.qx[v] = M.posx; M.qy[v] = M.posy; M.qz[v] = M.posz[v];
+    }
+    if constexpr (PROG == PROG_JIT) {
+        SDFGPU_JIT_BODY
+    } else if constexpr (PROG == PROG_DEMO) {
+        SDFGPU_DEMO_BODY
+    } else {
+        for (uint32_t pc = 0;; ++pc) {
+            const uint4 I = s_instr[pc];
+            if (I.x == DOP_END) break;
+#define C(n) case n: exec_op<V, n>(I, M, E); break;
+            switch (I.x) {
+                C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16) C(17) C(18)
+                C(19) C(20) C(21) C(22) C(23) C(24) C(25) C(26) C(27) C(28) C(29) C(30) C(31) C(32) C(33) C(34)
+                C(35) C(36) C(37) C(38)
+                default: break;
+            }
+#undef C
+        }
+    }
+
+    // ---- the stores of scene/sdf/mod.rs:196-208
+    float4* const out0 = P.tex0 + flat0;
+    float4* const out1 = P.tex1 + flat0;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        if (FULL || act[v]) {
+            float4 t0, t1;
+            store_rules(M.A[v], s_lut, P.air_dist, t0, t1);
+            store_texel(out0 + v * vstride, t0);
+            store_texel(out1 + v * vstride, t1);
+        }
+    }
+}
+
 // V = voxels per thread along z (lattice units).
 template <int V, int PROG>
 __device__ __forceinline__ void fill_body(const FillParams& P) {
@@ -465,85 +559,11 @@ __device__ __forceinline__ void fill_body(const FillParams& P) {
         if (tx >= P.tiles_x) { tx -= P.tiles_x; ++ty; }
         if (ty >= P.tiles_y) { ty -= P.tiles_y; ++tz; }
 
-        const bool row_ok = lx < P.nx && ly < P.ny;
-        const uint32_t gx = P.rx0 + lx * P.step, gy = P.ry0 + ly * P.step, gz0 = P.rz0 + lz0 * P.step;
-        const size_t flat0 = row_ok ? (size_t)(gz0 - P.z_lo) * slice + (size_t)gy * P.W + gx : 0;
-
-        Machine<V> M;
-        M.posx = s_px[min(gx, P.W - 1u)];
-        M.posy = s_py[min(gy, P.H - 1u)];
-        bool act[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            act[v] = row_ok && lz0 + v < P.nz;
-            M.posz[v] = s_pz[min(gz0 + v * P.step, P.D - 1u)];
-        }
-        if (P.conditional) {  // scene/sdf/mod.rs:184-190
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                if (act[v]) {
-                    bool need = __ldg(reinterpret_cast<const float*>(P.tex0 + flat0 + v * vstride)) == P.air_dist;
-                    if (P.has_box)
-                        need = need || (M.posx >= P.box[0] && M.posx <= P.box[3] && M.posy >= P.box[1] &&
-                                        M.posy <= P.box[4] && M.posz[v] >= P.box[2] && M.posz[v] <= P.box[5]);
-                    act[v] = need;
-                }
-            }
-            // nothing to sample in this warp's row (passes over an already loaded region)
-            bool any = false;
-#pragma unroll
-            for (int v = 0; v < V; ++v) { any = any || act[v]; touched_local += act[v] ? 1u : 0u; }
-            if (!__any_sync(0xffffffffu, any)) continue;
-        }
-
-        // ---- run the lowered tape
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            M.A[v].d = M.A[v].r = M.A[v].g = M.A[v].b = M.A[v].m = M.A[v].ro = M.A[v].o = 0.0f;
-            M.T[v] = M.A[v];
-            M.qx[v] = M.posx; M.qy[v] = M.posy; M.qz[v] = M.posz[v];
-        }
-        if constexpr (PROG == PROG_JIT) {
-            SDFGPU_JIT_BODY
-        } else if constexpr (PROG == PROG_DEMO) {
-            SDFGPU_DEMO_BODY
-        } else {
-            for (uint32_t pc = 0;; ++pc) {
-                const uint4 I = s_instr[pc];
-                if (I.x == DOP_END) break;
-#define C(n) case n: exec_op<V, n>(I, M, E); break;
-                switch (I.x) {
-                    C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16) C(17) C(18)
-                    C(19) C(20) C(21) C(22) C(23) C(24) C(25) C(26) C(27) C(28) C(29) C(30) C(31) C(32) C(33) C(34)
-                    C(35) C(36) C(37) C(38)
-                    default: break;
-                }
-#undef C
-            }
-        }
-
-        // ---- the stores of scene/sdf/mod.rs:196-208
-        float4* const out0 = P.tex0 + flat0;
-        float4* const out1 = P.tex1 + flat0;
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-            if (act[v]) {
-                Smp s = M.A[v];
-                float4 t0, t1;
-                t0.x = fminf(fmaxf(1e-1f + s.d, 0.0f), 1.0f);  // f32::clamp; NaN stays NaN below
-                if (s.d != s.d) t0.x = s.d;
-                if (s.r == 0.0f && s.g == 0.0f && s.b == 0.0f) { s.r = 0.5f; s.g = 0.5f; s.b = 0.5f; }
-                t0.y = s_lut[f32_to_u8_sat(s.r)];
-                t0.z = s_lut[f32_to_u8_sat(s.g)];
-                t0.w = s_lut[f32_to_u8_sat(s.b)];
-                t1.x = s.m;
-                t1.y = s.ro;
-                t1.z = (s.o <= 0.0f) ? 1.0f : s.o;
-                t1.w = P.air_dist;  // never written by the reference: keeps its initial value (:76)
-                store_texel(out0 + v * vstride, t0);
-                store_texel(out1 + v * vstride, t1);
-            }
-        }
+        // a tile that lies entirely inside the lattice needs no per-voxel predicates (CTA-uniform test)
+        const bool full = !P.conditional && (lx - lane) + FILL_TILE_X <= P.nx && (ly - warp) + FILL_TILE_Y <= P.ny &&
+                          lz0 + V <= P.nz;
+        if (full) tile_body<V, PROG, true>(P, E, s_instr, s_lut, s_px, s_py, s_pz, lx, ly, lz0, slice, vstride, touched_local);
+        else tile_body<V, PROG, false>(P, E, s_instr, s_lut, s_px, s_py, s_pz, lx, ly, lz0, slice, vstride, touched_local);
     }
 
     if (P.touched) {

@@ -60,6 +60,8 @@ bool jit_get(int device, int cc_major, int cc_minor, const std::vector<uint32_t>
              size_t smem_bytes, void** fn_out, int* max_ctas_per_sm, std::string* err);
 bool jit_launch(void* fn, const FillParams& p, int grid, size_t smem, cudaStream_t s, std::string* err);
 
+cudaError_t launch_ingest(float4* tex0, float4* tex1, const float* samples_dev, size_t first, size_t n,
+                          const float* lut_dev, float air_dist, int grid, cudaStream_t s);
 cudaError_t launch_set_const(float4* dst, size_t n_texels, float v, int grid_ctas, cudaStream_t s);
 cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s);
 cudaError_t launch_keys_unpack(const unsigned long long* keys, uint32_t n, uint8_t* rgba8, float* depth,

@@ -178,6 +178,18 @@ class SDFViewer:
         check(self._lib.sdfgpu_resample_box(self._h, _f6(box), C.byref(n) if count else None), self._h)
         return n.value if count else None
 
+    def voxel_positions(self, first_flat, count):
+        """Positions (count, 3) of the voxels [first_flat, first_flat + count) in flat order."""
+        xyz = np.empty((int(count), 3), np.float32)
+        check(self._lib.sdfgpu_voxel_positions(self._h, int(first_flat), int(count), _host_ptr(xyz)), self._h)
+        return xyz
+
+    def ingest_samples(self, first_flat, samples):
+        """Batched ingest of host-computed `SDFSample` records ((n, 7) float32) for the voxels that start
+        at flat index `first_flat` (SDFs without a tape, e.g. any existing .wasm SDFSurface)."""
+        s = np.ascontiguousarray(samples, np.float32).reshape(-1, 7)
+        check(self._lib.sdfgpu_ingest_samples(self._h, int(first_flat), len(s), _host_ptr(s)), self._h)
+
     def commit(self):  # scene/sdf/mod.rs:220-239
         check(self._lib.sdfgpu_commit(self._h), self._h)
 

@@ -304,6 +304,38 @@ def test_empty_and_degenerate_grids(S, oracle):
     assert same.all() and np.array_equal(bits(t1), bits(o.tex1))
 
 
+def test_batched_ingest_of_host_samples(S, oracle):
+    """an SDF without a tape is sampled on the host in batches (here: the oracle's
+    SDFDemo::sample standing in for a WASM guest) at the positions the library reports; the GPU applies
+    the store rules.  The volume equals the oracle's; odd records (black, NaN, out-of-range colours,
+    negative occlusion) follow scene/sdf/mod.rs:196-208 exactly."""
+    dims = (21, 13, 9)
+    n = dims[0] * dims[1] * dims[2]
+    o = oracle.Viewer(BB, dims, 1)
+    o.fill_all(oracle.Sampler())
+    with S.SDFViewer.new_voxels(dims, BB, 1) as v:
+        pos = v.voxel_positions(0, n)
+        want_pos = np.array([o.voxel_pos(x, y, z) for z in range(dims[2]) for y in range(dims[1]) for x in range(dims[0])], np.float32)
+        assert np.array_equal(bits(pos), bits(want_pos))
+        for first in range(0, n, 1000):  # batches, as a host loop would send them
+            chunk = pos[first:first + 1000]
+            v.ingest_samples(first, oracle.demo_sample(chunk))
+        t0, t1 = v.download()
+        assert_same_volume(t0, t1, o.tex0, o.tex1)
+        odd = np.array([[0.3, 0, 0, 0, 0.1, 0.2, 0.0], [np.nan, 1.5, -0.2, np.nan, 2.0, -1.0, -3.0],
+                        [-5.0, 0.5, 0.6, 0.7, 0.5, 0.0, 0.25], [7.0, 1.0, 1.0, 1.0, 0, 0, 1e-30]], np.float32)
+        v.ingest_samples(5, odd)
+        t0, t1 = v.download()
+    lut = (oracle.C.c_float * 256)(); oracle.lib().orc_srgb_lut(lut)
+    f0, f1 = t0.reshape(-1, 4)[5:9], t1.reshape(-1, 4)[5:9]
+    assert tuple(f0[0]) == (np.float32(0.1) + np.float32(0.3), lut[127], lut[127], lut[127]) and f1[0][2] == 1.0
+    assert np.isnan(f0[1][0]) and tuple(f0[1][1:]) == (lut[255], lut[0], lut[0]) and tuple(f1[1][:3]) == (2.0, -1.0, 1.0)
+    assert f0[2][0] == 0.0 and f0[3][0] == 1.0 and f1[2][2] == np.float32(0.25) and f1[3][2] == np.float32(1e-30)
+    with S.SDFViewer.new_voxels(dims, BB, 1, z_range=(3, 6)) as v:
+        with pytest.raises(S.SdfGpuError):
+            v.ingest_samples(0, odd)  # slice 0 is not stored by this slab
+
+
 def test_errors(S):
     import ctypes as C
     lib = S.viewer._lib.load()
