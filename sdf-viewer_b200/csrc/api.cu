@@ -83,6 +83,10 @@ struct sdfgpu_ctx {
     bool has_changed_box = false;
     float changed_box[6];
     bool changed_box_while_loading = false;
+    // What is known about the volume without reading it: 0 = every stored voxel holds AIR_DIST (fresh /
+    // reset); s > 0 = exactly the lattice points of step s (power of two) have been sampled, the rest hold
+    // AIR_DIST; 1 = every voxel has been sampled; -1 = unknown (the conditional passes read tex0.r).
+    int64_t known_step = 0;
     float lod = 1.0f;            // SDFViewerMaterial::lod_dist_between_samples, material.rs:27
     bool filter_linear = false;  // GL filter state: NEAREST until a commit at lod == 1 (mod.rs:110-111,227-238)
     // tape
@@ -189,8 +193,8 @@ int default_vpt(const sdfgpu_ctx* ctx) {
 }
 
 // one fill launch over lattice {r0 + i*step} restricted to the index box [lo, hi) per axis
-int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_t hi[3], bool conditional,
-             unsigned long long* touched) {
+int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_t hi[3], uint32_t conditional,
+             unsigned long long* touched, uint32_t known_step = 0) {
     if (!ctx->has_tape) return fail(ctx, SDFGPU_ERR_STATE, "no tape set (call sdfgpu_set_tape first)");
     FillParams p;
     memset(&p, 0, sizeof p);
@@ -212,7 +216,8 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
     p.tiles_x = (n[0] + FILL_TILE_X - 1) / FILL_TILE_X;
     p.tiles_y = (n[1] + FILL_TILE_Y - 1) / FILL_TILE_Y;
     p.tiles_z = (n[2] + V - 1) / V;
-    p.conditional = conditional ? 1u : 0u;
+    p.conditional = conditional;
+    p.known_step = known_step;
     p.has_box = ctx->has_changed_box ? 1u : 0u;
     if (ctx->has_changed_box) memcpy(p.box, ctx->changed_box, sizeof p.box);
     p.air_dist = air_dist_value();
@@ -737,8 +742,42 @@ SDFGPU_API int sdfgpu_update(sdfgpu_ctx* ctx, const float* changed_box, uint32_t
     fill_z_range(ctx, &za, &zb);
     uint32_t done = 0;
     while (ctx->lm.step_size != 0 && (max_passes == 0 || done < max_passes)) {  // :173-215, one pass per launch
-        const uint32_t lo[3] = {0, 0, za}, hi[3] = {ctx->dims[0], ctx->dims[1], zb};
-        const int rc = run_fill(ctx, (uint32_t)ctx->lm.step_size, lo, hi, true, nullptr);
+        const uint32_t step = (uint32_t)ctx->lm.step_size;
+        uint32_t lo[3] = {0, 0, za}, hi[3] = {ctx->dims[0], ctx->dims[1], zb};
+        // The rule "sample iff tex0.r == AIR_DIST or position in box" (:184-190) needs no read when the
+        // host knows which voxels hold AIR_DIST (re-sampling a voxel whose stored value merely equals
+        // AIR_DIST is idempotent: sample() is pure, src/sdf/mod.rs:43).
+        int rc = SDFGPU_OK;
+        const int64_t k = ctx->known_step;
+        if (!ctx->has_changed_box && k == 0) {
+            rc = run_fill(ctx, step, lo, hi, FILL_ALL, nullptr);                       // everything is AIR_DIST
+            ctx->known_step = step;
+        } else if (!ctx->has_changed_box && k == 1) {
+            // nothing holds AIR_DIST: the pass samples nothing
+        } else if (!ctx->has_changed_box && k > 1 && k % step == 0) {
+            rc = run_fill(ctx, step, lo, hi, FILL_SKIP_KNOWN, nullptr, (uint32_t)k);   // skip the coarser lattice
+            ctx->known_step = step;
+        } else if (ctx->has_changed_box && k == 1) {
+            // only the voxels inside the box: restrict the launch to its index AABB
+            bool empty = false;
+            const std::vector<float>* tab[3] = {&ctx->px, &ctx->py, &ctx->pz};
+            for (int a = 0; a < 3 && !empty; ++a) {
+                uint32_t first = 0xffffffffu, last = 0;
+                const std::vector<float>& t = *tab[a];
+                for (uint32_t i = 0; i < t.size(); ++i)
+                    if (t[i] >= ctx->changed_box[a] && t[i] <= ctx->changed_box[3 + a]) {
+                        if (first == 0xffffffffu) first = i;
+                        last = i;
+                    }
+                if (first == 0xffffffffu) { empty = true; break; }
+                if (first > lo[a]) lo[a] = first;
+                if (last + 1 < hi[a]) hi[a] = last + 1;
+            }
+            if (!empty) rc = run_fill(ctx, step, lo, hi, FILL_BOX_ONLY, nullptr);
+        } else {
+            rc = run_fill(ctx, step, lo, hi, FILL_READ, nullptr);
+            ctx->known_step = step == 1 ? 1 : -1;  // after a full step-1 pass no voxel holds AIR_DIST
+        }
         if (rc != SDFGPU_OK) return rc;
         ctx->lm.finish_pass();
         ++done;
@@ -767,20 +806,21 @@ SDFGPU_API int sdfgpu_fill_all(sdfgpu_ctx* ctx) {
         }
         const uint32_t lo0[3] = {0, 0, ctx->z_begin}, hi0[3] = {ctx->dims[0], ctx->dims[1], ctx->z_begin + 1};
         const uint32_t lo1[3] = {0, 0, ctx->z_end - 1}, hi1[3] = {ctx->dims[0], ctx->dims[1], ctx->z_end};
-        if ((rc = run_fill(ctx, 1, lo0, hi0, false, nullptr)) != SDFGPU_OK) return rc;
-        if ((rc = run_fill(ctx, 1, lo1, hi1, false, nullptr)) != SDFGPU_OK) return rc;
+        if ((rc = run_fill(ctx, 1, lo0, hi0, FILL_ALL, nullptr)) != SDFGPU_OK) return rc;
+        if ((rc = run_fill(ctx, 1, lo1, hi1, FILL_ALL, nullptr)) != SDFGPU_OK) return rc;
         CK(ctx, cudaEventRecord(ctx->ev_boundary, ctx->stream));
         CK(ctx, cudaStreamWaitEvent(ctx->halo_stream, ctx->ev_boundary, 0));
         if ((rc = push_halos(ctx, ctx->halo_stream)) != SDFGPU_OK) return rc;
         CK(ctx, cudaEventRecord(ctx->ev_pushed, ctx->halo_stream));
         const uint32_t lo[3] = {0, 0, ctx->z_begin + 1}, hi[3] = {ctx->dims[0], ctx->dims[1], ctx->z_end - 1};
-        if ((rc = run_fill(ctx, 1, lo, hi, false, nullptr)) != SDFGPU_OK) return rc;
+        if ((rc = run_fill(ctx, 1, lo, hi, FILL_ALL, nullptr)) != SDFGPU_OK) return rc;
         CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_pushed, 0));
     } else {
         const uint32_t lo[3] = {0, 0, za}, hi[3] = {ctx->dims[0], ctx->dims[1], zb};
-        if ((rc = run_fill(ctx, 1, lo, hi, false, nullptr)) != SDFGPU_OK) return rc;
+        if ((rc = run_fill(ctx, 1, lo, hi, FILL_ALL, nullptr)) != SDFGPU_OK) return rc;
         if (has_peers(ctx) && (rc = push_halos(ctx, ctx->stream)) != SDFGPU_OK) return rc;
     }
+    ctx->known_step = 1;
     while (ctx->lm.step_size != 0) ctx->lm.finish_pass();
     return SDFGPU_OK;
 }
@@ -820,7 +860,9 @@ SDFGPU_API int sdfgpu_resample_box(sdfgpu_ctx* ctx, const float box[6], uint64_t
         cudaError_t e = cudaMemsetAsync(ctx->touched_dev, 0, sizeof(unsigned long long), ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, SDFGPU_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
     }
-    if (rc == SDFGPU_OK) rc = run_fill(ctx, 1, lo, hi, true, voxels_touched ? ctx->touched_dev : nullptr);
+    if (rc == SDFGPU_OK)
+        rc = run_fill(ctx, 1, lo, hi, ctx->known_step == 1 ? FILL_BOX_ONLY : FILL_READ, voxels_touched ? ctx->touched_dev : nullptr);
+    if (ctx->known_step != 1) ctx->known_step = -1;
     ctx->has_changed_box = saved_has;
     memcpy(ctx->changed_box, saved, sizeof saved);
     if (rc == SDFGPU_OK && has_peers(ctx)) rc = push_halos(ctx, ctx->stream);
@@ -874,6 +916,7 @@ SDFGPU_API int sdfgpu_ingest_samples(sdfgpu_ctx* ctx, uint64_t first_flat, uint6
     CK(ctx, launch_ingest(ctx->tex0, ctx->tex1, ctx->ingest_dev, (size_t)(first_flat - lo), (size_t)count, ctx->lut_dev,
                           air_dist_value(), ctx->sm_count * 8, ctx->stream));
     ctx->launches++;
+    if (ctx->known_step != 1) ctx->known_step = -1;
     // the staging buffer is reused by the next call: wait until the kernel has consumed it
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     return SDFGPU_OK;
@@ -902,6 +945,7 @@ SDFGPU_API int sdfgpu_reset(sdfgpu_ctx* ctx, uint32_t loading_passes) {
     const int rc = reset_volumes(ctx);
     if (rc != SDFGPU_OK) return rc;
     ctx->lm.reset(loading_passes);
+    ctx->known_step = 0;
     ctx->has_changed_box = false;
     ctx->changed_box_while_loading = false;
     ctx->lod = 1.0f;
@@ -1243,6 +1287,7 @@ SDFGPU_API int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value
         if (value < 0 || value > 32) return fail(ctx, SDFGPU_ERR_INVALID, "fill_ctas_per_sm out of range");
         ctx->opt_ctas = (int)value;
     } else if (!strcmp(key, "fill_halo")) {
+        if (ctx->opt_fill_halo != (value != 0) && ctx->known_step != 0) ctx->known_step = -1;  // the filled z range changes
         ctx->opt_fill_halo = value != 0;
     } else if (!strcmp(key, "trace_max_steps")) {
         if (value < 2 || value > 65536) return fail(ctx, SDFGPU_ERR_INVALID, "trace_max_steps out of range");

@@ -367,13 +367,18 @@ __device__ __forceinline__ void tile_body(const FillParams& P, const Env& E, con
         M.posz[v] = s_pz[FULL ? gz0 + v * P.step : min(gz0 + v * P.step, P.D - 1u)];
     }
     if (!FULL && P.conditional) {  // scene/sdf/mod.rs:184-190
+        const bool in_xy = P.has_box && M.posx >= P.box[0] && M.posx <= P.box[3] && M.posy >= P.box[1] && M.posy <= P.box[4];
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             if (act[v]) {
-                bool need = __ldg(reinterpret_cast<const float*>(P.tex0 + flat0 + v * vstride)) == P.air_dist;
-                if (P.has_box)
-                    need = need || (M.posx >= P.box[0] && M.posx <= P.box[3] && M.posy >= P.box[1] &&
-                                    M.posy <= P.box[4] && M.posz[v] >= P.box[2] && M.posz[v] <= P.box[5]);
+                bool need;
+                if (P.conditional == FILL_SKIP_KNOWN) {  // sampled so far: exactly the multiples of known_step
+                    need = ((gx | gy | (gz0 + v * P.step)) & (P.known_step - 1u)) != 0u;
+                } else {
+                    need = P.conditional == FILL_READ &&
+                           __ldg(reinterpret_cast<const float*>(P.tex0 + flat0 + v * vstride)) == P.air_dist;
+                    need = need || (in_xy && M.posz[v] >= P.box[2] && M.posz[v] <= P.box[5]);
+                }
                 act[v] = need;
             }
         }
