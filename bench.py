@@ -125,6 +125,33 @@ def cpu_fill_sample(orc, tape, dims, threads, target_s=6.0):
                     f"({n} samples, {dt:.2f} s wall, {threads} threads)")
 
 
+def cpu_reference_order_rate(orc, tape, side=96):
+    """The reference's own configuration: ONE thread, LoadingManager visit order, 2 passes
+    (scene/sdf/mod.rs:173-215 is single-threaded); a small grid bounds the run."""
+    v = orc.Viewer(BB, (side, side, side), 2)
+    s = orc.Sampler(tape=tape)
+    t = time.perf_counter(); it = v.update(s); dt = time.perf_counter() - t
+    return side ** 3 / dt, f"{side}^3 grid, 2 passes, {it} iterations, reference visit order, 1 thread, {dt:.2f} s"
+
+
+def cpu_trace_sample(orc, S, tape, dims, W, H, threads, rows=48):
+    """Oracle trace (the restated fragment shader) of a band of rows of the same frame; rays/s."""
+    v = orc.Viewer(BB, dims, 1)
+    v.fill_all(orc.Sampler(tape=tape), threads=threads)
+    cam = S.default_camera(W, H)
+    P = orc.trace_params(S.camera_rays(cam, W, H), BB, dims, lod=1.0, filter_linear=1)
+    r0 = max(0, H // 2 - rows // 2)
+    t = time.perf_counter()
+    orc.trace(P, v.tex0, v.tex1, W, H, rows=(r0, r0 + rows), gbuf=False, threads=threads)
+    dt = time.perf_counter() - t
+    return W * rows / dt, f"rows [{r0},{r0 + rows}) of the {W}x{H} frame ({W * rows} rays, {dt:.2f} s, {threads} threads)"
+
+
+def workload_name(workload, dims, W, H):
+    return (f"{'demo_sdf' if workload == 'demo' else 'csg_1k'} {dims[0]}x{dims[1]}x{dims[2]} "
+            f"grid fill + {W}x{H} sphere trace, default scene camera")
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path.  The Rust/wasmer build cannot
     be produced here (no cargo/rustc), so this is the C++ restatement in oracle/ (kind "port"), on all
@@ -145,12 +172,19 @@ def run_reference(args, rank, world):
             rates.append(r)
     val = sum(rates) / len(rates)
     n_vox = dims[0] * dims[1] * dims[2]
+    import sdf_viewer_b200 as S
+    one_thread, one_thread_sample = cpu_reference_order_rate(orc, tape)
+    cpu_dims = tuple(min(d, 256) for d in dims)  # the CPU trace sample marches a volume the host can hold
+    rays, rays_sample = cpu_trace_sample(orc, S, tape, cpu_dims, args.width, args.height, threads)
     print(json.dumps({
         "impl": "reference", "metric": "sdf_samples_per_sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_vox / val, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"demo_sdf {dims[0]}x{dims[1]}x{dims[2]} grid fill (CPU port of the reference loop)"},
-        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name("demo", dims, args.width, args.height),
+                   "step": "bounded sample of the grid fill on the host cores (C++ port of the reference loop, OpenMP over z)"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
+                         "reference_order_1_thread": one_thread, "reference_order_sample": one_thread_sample,
+                         "rays_per_sec": rays, "rays_sample": rays_sample + f", {cpu_dims[0]}^3 volume"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -281,8 +315,7 @@ def main():
         "metric": "sdf_samples_per_sec", "value": total_voxels / (fill_ms * 1e-3), "unit": "samples/s",
         "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{'demo_sdf' if args.workload == 'demo' else 'csg_1k'} {dims[0]}x{dims[1]}x{dims[2]} "
-                               f"grid fill + {W}x{H} sphere trace, default scene camera",
+        "config": {"workload": workload_name(args.workload, dims, W, H),
                    "sharding": (f"z-slabs x{n_gpus}, halo exchange: " + ("fused: boundary slices pushed by DMA over NVLink (CUDA IPC) while the interior fills"
                                 if sv.fused else "NCCL send/recv after the fill")) if n_gpus > 1 else "single GPU",
                    "l2": "volume (32 B/voxel) exceeds the 126 MB L2, no flush needed" if own_voxels * 32 > 2.5e8 else "volume fits L2",
@@ -307,7 +340,12 @@ def main():
         orc.build()
         threads = orc.lib().orc_max_threads()
         val, sample = cpu_fill_sample(orc, tape, dims, threads, target_s=8.0)
-        out["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample}
+        one_thread, one_thread_sample = cpu_reference_order_rate(orc, tape)
+        cpu_dims = tuple(min(d, 256) for d in dims)
+        rays, rays_sample = cpu_trace_sample(orc, S, tape, cpu_dims, W, H, threads)
+        out["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
+                               "reference_order_1_thread": one_thread, "reference_order_sample": one_thread_sample,
+                               "rays_per_sec": rays, "rays_sample": rays_sample + f", {cpu_dims[0]}^3 volume"}
     print(json.dumps(out))
     if dist: dist.destroy_process_group()
 
