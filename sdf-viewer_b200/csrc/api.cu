@@ -205,7 +205,9 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
         if (r0[a] >= hi[a]) return SDFGPU_OK;
         n[a] = (hi[a] - r0[a] + step - 1) / step;
     }
-    const int V = default_vpt(ctx);
+    int V = default_vpt(ctx);
+    if (!ctx->opt_vpt)  // thin launches (a boundary slice, a dirty box): do not pad the z extent of a tile with idle voxels
+        while (V > 1 && (uint32_t)V > n[2]) V >>= 1;
     p.tex0 = ctx->tex0; p.tex1 = ctx->tex1;
     p.tape_img = ctx->img_dev; p.tape_img_bytes = (uint32_t)ctx->img_host.size();
     p.W = ctx->dims[0]; p.H = ctx->dims[1]; p.D = ctx->dims[2];

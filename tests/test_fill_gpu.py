@@ -336,6 +336,39 @@ def test_batched_ingest_of_host_samples(S, oracle):
             v.ingest_samples(0, odd)  # slice 0 is not stored by this slab
 
 
+def test_known_state_tracking_mixed_calls(S, oracle):
+    """The read-free passes rely on what the host knows about the volume; calls that break that
+    knowledge (ingest / resample in the middle of a load) must fall back to reading tex0.r.  Expected
+    volume built by hand from the rule of scene/sdf/mod.rs:184-190."""
+    dims = (24, 16, 12)
+    n = dims[0] * dims[1] * dims[2]
+    tapeA, tapeB = S.tape.demo_tape(), S.tape.demo_tape(cube_half_side=0.6, sphere_radius=0.7)
+    a = oracle.Viewer(BB, dims, 1); a.fill_all(oracle.Sampler(tape=tapeA))
+    b = oracle.Viewer(BB, dims, 1); b.fill_all(oracle.Sampler(tape=tapeB))
+    air = np.float32(oracle.lib().orc_air_dist())
+    with S.SDFViewer.new_voxels(dims, BB, 2) as v:
+        v.set_tape(tapeA)
+        assert v.update(None, max_passes=1) == S.loading.pass_items(dims, 2)      # coarse lattice, no read
+        pos = v.voxel_positions(100, 700)
+        v.ingest_samples(100, oracle.tape_sample(tapeB, pos))                      # knowledge lost
+        assert v.update(None) == n                                                # fine pass must read
+        t0, t1 = v.download()
+        want0, want1 = a.tex0.copy().reshape(-1, 4), a.tex1.copy().reshape(-1, 4)
+        want0[100:800], want1[100:800] = b.tex0.reshape(-1, 4)[100:800], b.tex1.reshape(-1, 4)[100:800]
+        # the coarse lattice was sampled with tape A before the ingest overwrote part of it; ingested voxels
+        # whose stored distance happens to equal AIR_DIST would be re-sampled (none here)
+        assert not np.any(b.tex0.reshape(-1, 4)[100:800, 0] == air)
+        assert_same_volume(t0, t1, want0.reshape(t0.shape), want1.reshape(t1.shape))
+        # now fully sampled: a box pass touches only the box, a plain pass nothing
+        v.set_tape(tapeB)
+        assert v.resample_box((-0.3, -0.3, -0.3, 0.3, 0.3, 0.3), count=True) > 0
+        assert v.update(None) == 0
+        v.reset(2)                                                                # all AIR_DIST again
+        assert v.update(None) == S.loading.pass_items(dims, 2) + n
+        t0, t1 = v.download()
+        assert_same_volume(t0, t1, b.tex0, b.tex1)
+
+
 def test_errors(S):
     import ctypes as C
     lib = S.viewer._lib.load()
