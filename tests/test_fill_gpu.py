@@ -193,6 +193,69 @@ def test_deep_stack_tape(S, oracle, program):
         assert_same_volume(t0, t1, o.tex0, o.tex1)
 
 
+def random_tape(T, rng):
+    """A random valid tape: random primitives, every opcode class, balanced stack (depth <= 8)."""
+    t = T.TapeBuilder()
+    n_prims = int(rng.integers(1, 40))
+    prims = [t.prim(int(rng.integers(0, 2)), rng.uniform(-0.9, 0.9, 3), float(rng.uniform(0.05, 0.8)),
+                    int(rng.integers(0, 3)), color=rng.uniform(-0.2, 1.3, 3), metallic=float(rng.uniform(0, 1)),
+                    roughness=float(rng.uniform(0, 1)), occlusion=float(rng.uniform(-0.5, 1)),
+                    air_skip=float(rng.choice([0.05, 0.1, 0.5, np.inf]))) for _ in range(n_prims)]
+    consts = t.const(rng.uniform(-0.5, 0.9, 16))
+    depth = 0
+    t.emit(T.OP_PRIM, int(rng.integers(0, n_prims)))
+    for _ in range(int(rng.integers(3, 40))):
+        r = rng.random()
+        if r < 0.25:
+            t.emit(int(rng.choice([T.OP_PRIM, T.OP_UNION_PRIM, T.OP_INTER_PRIM])), int(rng.integers(0, n_prims)))
+        elif r < 0.32:
+            a = int(rng.integers(0, n_prims)); b = int(rng.integers(1, n_prims - a + 1))
+            t.emit(T.OP_UNION_RANGE, a, b)
+        elif r < 0.47 and depth < 8:
+            t.emit(T.OP_PUSH); depth += 1
+            t.emit(T.OP_PRIM, int(rng.integers(0, n_prims)))
+        elif r < 0.62 and depth > 0:
+            op = int(rng.choice([T.OP_POP_UNION, T.OP_POP_INTER, T.OP_POP_DEMO_DIFF]))
+            t.emit(op, int(rng.integers(0, 9)) if op == T.OP_POP_DEMO_DIFF else 0); depth -= 1
+        elif r < 0.77:
+            op = int(rng.choice([T.OP_D_NEG, T.OP_D_ABS, T.OP_D_ADD, T.OP_D_MUL, T.OP_D_MAX, T.OP_D_MIN]))
+            t.emit(op, imm=float(rng.uniform(-0.5, 1.5)))
+        elif r < 0.83:
+            t.emit(T.OP_M_SET, int(rng.integers(0, 10)))
+        else:
+            op = int(rng.choice([T.OP_P_RESET, T.OP_P_SUB, T.OP_P_MUL, T.OP_P_ABS]))
+            t.emit(op, int(rng.integers(0, 8)) if op == T.OP_P_ABS else int(rng.integers(0, 13)), imm=float(rng.uniform(0.5, 2.0)))
+    while depth > 0:
+        t.emit(int(rng.choice([T.OP_POP_UNION, T.OP_POP_INTER]))); depth -= 1
+    if rng.random() < 0.7:
+        t.emit(T.OP_END)
+    return t.build()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_tapes(S, oracle, seed):
+    """Fuzz: random tapes on random ragged grids and boxes; interpreter and specialised kernel both equal
+    the oracle's interpreter bit for bit."""
+    rng = np.random.default_rng(1000 + seed)
+    tape = random_tape(S.tape, rng)
+    dims = tuple(int(x) for x in rng.integers(1, 40, 3))
+    lo = rng.uniform(-1.5, -0.2, 3); hi = lo + rng.uniform(0.3, 3.0, 3)
+    bb = (tuple(float(x) for x in lo), tuple(float(x) for x in hi))
+    o = oracle.Viewer(bb, dims, 1)
+    with np.errstate(all="ignore"):
+        o.fill_all(oracle.Sampler(tape=tape))
+    for program in ("interpreter", "jit"):
+        with S.SDFViewer.new_voxels(dims, bb, 1) as v:
+            v.set_option("fill_program", PROGRAMS[program][0])
+            v.set_option("fill_voxels_per_thread", int(rng.choice([0, 1, 2, 4, 8])))
+            v.set_tape(tape)
+            v.fill_all()
+            t0, t1 = v.download()
+        ok0 = (bits(t0) == bits(o.tex0)) | (np.isnan(t0) & np.isnan(o.tex0))
+        ok1 = (bits(t1) == bits(o.tex1)) | (np.isnan(t1) & np.isnan(o.tex1))
+        assert ok0.all() and ok1.all(), (program, seed, int((~ok0).sum()), int((~ok1).sum()))
+
+
 def test_changed_box_state_machine(S, oracle):
     """sdf.changed() -> merged pending box -> 3-pass re-sample of the voxels inside it
     (scene/sdf/mod.rs:131-154,184-190), while and after loading.  The GPU runs whole passes; the
