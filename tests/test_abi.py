@@ -106,3 +106,52 @@ def test_specialised_kernel_compiles_for_sm100a(S):
     with pytest.raises(S.SdfGpuError) as e:
         S.jit_check(b"\0" * 40, 2)
     assert e.value.code == -3
+
+
+C_CLIENT = r"""
+#include "sdfgpu.h"
+#include "sdfgpu_tape.h"
+#include <stdio.h>
+int main(void) {
+    float bb[6] = {-1, -1, -1, 1, 2, 0.5f};
+    uint32_t d[3];
+    sdfgpu_camera cam;
+    sdfgpu_rays rays;
+    sdfgpu_ctx* ctx = 0;
+    int rc = sdfgpu_dims_from_bb(bb, 64, d);
+    sdfgpu_camera_default(&cam, 640, 480);
+    rc |= sdfgpu_camera_rays(&cam, 640, 480, &rays);
+    printf("%d %u %u %u %zu %zu %zu %zu %.9g\n", rc, d[0], d[1], d[2], sizeof(sdft_header), sizeof(sdft_instr),
+           sizeof(sdft_prim), sizeof(sdfgpu_camera), (double)sdfgpu_air_dist());
+    rc = sdfgpu_create(bb, 64, 2, 0, &ctx);   /* fails without a device: no CPU fallback */
+    printf("%d %s\n", rc, sdfgpu_last_error(ctx));
+    sdfgpu_destroy(ctx);
+    return 0;
+}
+"""
+
+
+def test_plain_c_client_links_against_the_abi(S, tmp_path):
+    """include/*.h are C99 headers and libsdfgpu.so is a plain C ABI: a C program compiled with gcc
+    -std=c99 -pedantic links and calls it (what a cgo / Rust `extern "C"` binding does)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    src = tmp_path / "client.c"
+    src.write_text(C_CLIENT)
+    exe = tmp_path / "client"
+    libdir = os.path.join(ROOT, "sdf-viewer_b200")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-o", str(exe), "-L", libdir, "-lsdfgpu", f"-Wl,-rpath,{libdir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines()
+    f = out[0].split()
+    assert f[:4] == ["0", "42", "64", "32"]                      # from_bb: sizes (2, 3, 1.5) -> (64*2/3 truncated, 64, 64*1.5/3)
+    assert f[4:8] == ["32", "16", "48", "180"]                   # struct sizes of the tape format and the camera
+    assert abs(float(f[8]) - 0.101234004) < 1e-9
+    import torch
+    if not torch.cuda.is_available():
+        assert out[1].startswith("-2 ") and "no CPU fallback" in out[1]
+    else:
+        assert out[1].startswith("0 ")
