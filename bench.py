@@ -11,7 +11,6 @@ stream); `e2e` is the same through the host-buffer C-ABI calls (tape H2D, frame 
 timed region).  Prints ONE JSON line on rank 0.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -212,7 +211,6 @@ def main():
         run_reference(args, rank, world)
         return
 
-    import numpy as np
     import torch
     import sdf_viewer_b200 as S
 

@@ -32,17 +32,16 @@ def main():
         for prog, vpt, ctas, streaming in [(p, a, b, c) for p in (1, 2, 3) for a in (1, 2, 4, 8) for b in (0, 1, 2, 3) for c in (1,)]:
             if workload != "demo" and prog == 2:
                 continue
-            for _ in (0,):
-                for _ in (0,):
-                    v.set_option("fill_program", prog)
-                    v.set_option("fill_voxels_per_thread", vpt)
-                    v.set_option("fill_ctas_per_sm", ctas)
-                    try:
-                        ms = time_fill(v, stream, reps=5 if workload == "demo" else 2)
-                    except Exception as e:
-                        print("fail", vpt, ctas, streaming, e); continue
-                    rows.append((ms, vpt, ctas, streaming, prog))
-                    print(f"prog={prog} vpt={vpt} ctas={ctas} streaming={streaming}: {ms:.3f} ms  {nvox/ms/1e6:.1f} Gsamples/s  {nvox*32/ms/1e6:.0f} GB/s", flush=True)
+            v.set_option("fill_program", prog)
+            v.set_option("fill_voxels_per_thread", vpt)
+            v.set_option("fill_ctas_per_sm", ctas)
+            try:
+                ms = time_fill(v, stream, reps=5 if workload == "demo" else 2)
+            except Exception as e:
+                print("fail", vpt, ctas, e)
+                continue
+            rows.append((ms, vpt, ctas, streaming, prog))
+            print(f"prog={prog} vpt={vpt} ctas={ctas}: {ms:.3f} ms  {nvox/ms/1e6:.1f} Gsamples/s  {nvox*32/ms/1e6:.0f} GB/s", flush=True)
         rows.sort()
         print("best:", rows[:5])
         ms, vpt, ctas, streaming, prog = rows[0]
