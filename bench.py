@@ -98,6 +98,23 @@ def ncu_traffic():
         return None
 
 
+def trace_profile():
+    """L1/TEX and L2 hit rates and DRAM traffic of the trace kernel from the committed ncu capture."""
+    keys = {"l1tex__t_sector_hit_rate.pct": "l1tex_hit_pct", "lts__t_sector_hit_rate.pct": "l2_hit_pct",
+            "dram__bytes_read.sum": "dram_read", "gpu__time_duration.sum": "ncu_duration_us"}
+    out = {}
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "r01_trace_ncu_summary.txt")):
+            k, _, v = line.partition(" = ")
+            if k in keys:
+                num, unit = (v.split() + [""])[:2]
+                out[keys[k]] = float(num) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3}.get(unit, 1)
+        out["source"] = "profiles/r01_trace_ncu_summary.txt (ncu --set full; 512^3 volume, 1920x1080, default camera)"
+        return out
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -328,6 +345,7 @@ def main():
                 "h2d_bytes_per_step": len(tape) + 256, "d2h_bytes_per_step": W * H * 8,
                 "what": "set_tape (H2D) + fill + commit + trace + frame RGBA8+depth D2H into pinned host memory"},
         "gpu_launches": int(launches), "clocks": clocks, "host_ms_per_step": wall_ms,
+        "trace_profile": trace_profile() if (n_gpus == 1 and args.grid == 512 and args.workload == "demo") else None,
     }
     if n_gpus > 1:
         out["e2e"]["d2h_bytes_per_step"] = W * H * 8
