@@ -109,6 +109,10 @@ struct sdfgpu_ctx {
     float* ingest_dev = nullptr;  // staging for sdfgpu_ingest_samples: records, then the LUT
     size_t ingest_cap = 0;
     float* lut_dev = nullptr;
+    float* dist_dev = nullptr;  // optional distance-only volume for the tracer (option trace_distance_volume)
+    bool dist_valid = false;
+    bool peers_ever = false;  // a neighbour may hold an IPC mapping of this handle's volumes
+    int opt_dist_volume = 0;
     unsigned long long* touched_dev = nullptr;
     // neighbours' volumes opened with cudaIpcOpenMemHandle (fused halo exchange)
     float4* peer_tex0[2] = {nullptr, nullptr};
@@ -264,6 +268,7 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
         CK(ctx, launch_fill(p, V, program, (int)grid, smem, ctx->stream));
     }
     ctx->last_program = program; ctx->last_ctas = per_sm; ctx->last_vpt = V;
+    ctx->dist_valid = false;
     ctx->launches++;
     return SDFGPU_OK;
 }
@@ -300,6 +305,7 @@ int alloc_volumes(sdfgpu_ctx* ctx) {
 }
 
 int reset_volumes(sdfgpu_ctx* ctx) {  // new_voxels, scene/sdf/mod.rs:76-77: AIR_DIST in all 4 channels of both
+    ctx->dist_valid = false;
     const int grid = ctx->sm_count * 8;
     CK(ctx, launch_set_const(ctx->tex0, ctx->stored_texels, air_dist_value(), grid, ctx->stream));
     CK(ctx, launch_set_const(ctx->tex1, ctx->stored_texels, air_dist_value(), grid, ctx->stream));
@@ -442,6 +448,7 @@ SDFGPU_API int sdfgpu_ipc_export(sdfgpu_ctx* ctx, void* handles, size_t handles_
     CK(ctx, cudaIpcGetMemHandle(&h[0], ctx->tex0));
     CK(ctx, cudaIpcGetMemHandle(&h[1], ctx->tex1));
     memcpy(handles, h, sizeof h);
+    ctx->peers_ever = true;
     return SDFGPU_OK;
 }
 
@@ -481,7 +488,7 @@ SDFGPU_API void sdfgpu_destroy(sdfgpu_ctx* ctx) {
     (void)cudaFree(ctx->tex0); (void)cudaFree(ctx->tex1); (void)cudaFree(ctx->img_dev);
     (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
     (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->rgba8_dev); (void)cudaFree(ctx->touched_dev);
-    (void)cudaFree(ctx->ingest_dev); (void)cudaFree(ctx->lut_dev);
+    (void)cudaFree(ctx->ingest_dev); (void)cudaFree(ctx->lut_dev); (void)cudaFree(ctx->dist_dev);
     if (ctx->halo_stream) (void)cudaStreamDestroy(ctx->halo_stream);
     if (ctx->ev_boundary) (void)cudaEventDestroy(ctx->ev_boundary);
     if (ctx->ev_pushed) (void)cudaEventDestroy(ctx->ev_pushed);
@@ -918,6 +925,7 @@ SDFGPU_API int sdfgpu_ingest_samples(sdfgpu_ctx* ctx, uint64_t first_flat, uint6
     CK(ctx, launch_ingest(ctx->tex0, ctx->tex1, ctx->ingest_dev, (size_t)(first_flat - lo), (size_t)count, ctx->lut_dev,
                           air_dist_value(), ctx->sm_count * 8, ctx->stream));
     ctx->launches++;
+    ctx->dist_valid = false;
     if (ctx->known_step != 1) ctx->known_step = -1;
     // the staging buffer is reused by the next call: wait until the kernel has consumed it
     CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1055,6 +1063,17 @@ int fill_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t w, uin
     tp->tone_mapping = cam->tone_mapping; tp->color_mapping = cam->color_mapping;
     tp->gamma = cam->gamma;
     memcpy(tp->ambient, cam->ambient, 12);
+    // optional distance-only volume (4 B per voxel) for the march: built here after any change of tex0;
+    // not with IPC neighbours, whose halo pushes this handle cannot observe
+    if (ctx->opt_dist_volume && ctx->stored_texels && !has_peers(ctx) && !ctx->peers_ever) {
+        if (!ctx->dist_dev) CK(ctx, cudaMalloc(&ctx->dist_dev, ctx->stored_texels * sizeof(float)));
+        if (!ctx->dist_valid) {
+            CK(ctx, launch_extract_dist(ctx->tex0, ctx->dist_dev, ctx->stored_texels, ctx->sm_count * 8, ctx->stream));
+            ctx->launches++;
+            ctx->dist_valid = true;
+        }
+        tp->dist = ctx->dist_dev;
+    }
     tp->width = w; tp->height = h;
     tp->max_steps = (uint32_t)ctx->opt_max_steps;
     // screen rectangle of the projected clip box (a convex box projects inside the bounding rectangle of
@@ -1291,6 +1310,8 @@ SDFGPU_API int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value
     } else if (!strcmp(key, "fill_halo")) {
         if (ctx->opt_fill_halo != (value != 0) && ctx->known_step != 0) ctx->known_step = -1;  // the filled z range changes
         ctx->opt_fill_halo = value != 0;
+    } else if (!strcmp(key, "trace_distance_volume")) {
+        ctx->opt_dist_volume = value != 0;
     } else if (!strcmp(key, "trace_max_steps")) {
         if (value < 2 || value > 65536) return fail(ctx, SDFGPU_ERR_INVALID, "trace_max_steps out of range");
         ctx->opt_max_steps = (int)value;

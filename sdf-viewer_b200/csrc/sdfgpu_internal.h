@@ -15,6 +15,7 @@ namespace sdfgpu {
 struct TraceParams {
     const float4* tex0;
     const float4* tex1;
+    const float* dist;  // optional: tex0.r of every stored texel as a dense array (null = march reads tex0)
     float origin[3], base[3], dx[3], dy[3], bvp[16];
     float bmin[3], bmax[3];          // sdfBoundsMin/Max
     float clip_min[3], clip_max[3];  // == bounds on one GPU; the slab's sub-box for sort-last
@@ -64,6 +65,7 @@ cudaError_t launch_ingest(float4* tex0, float4* tex1, const float* samples_dev, 
                           const float* lut_dev, float air_dist, int grid, cudaStream_t s);
 cudaError_t launch_set_const(float4* dst, size_t n_texels, float v, int grid_ctas, cudaStream_t s);
 cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s);
+cudaError_t launch_extract_dist(const float4* tex0, float* dist, size_t n, int grid, cudaStream_t s);
 cudaError_t launch_keys_unpack(const unsigned long long* keys, uint32_t n, uint8_t* rgba8, float* depth,
                                cudaStream_t s);
 

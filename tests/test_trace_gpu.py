@@ -105,11 +105,22 @@ def test_trace_variants_identical(S):
                             (200, 300, ((4.0, 0.5, 0.2), (0, 3.0, 0)))):
             c = S.default_camera(w, h) if cam is None else S.look_at_camera(cam[0], cam[1], w, h)
             frames = []
-            for variant in (0, 1):
+            for variant, dist_volume in ((0, 0), (1, 0), (0, 1)):
                 v.set_option("trace_variant", variant)
+                v.set_option("trace_distance_volume", dist_volume)  # distance-only copy of tex0.r for the march
                 frames.append(v.trace(c, w, h, gbuf=True))
-            for a, b in zip(*frames):
-                assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+            for other in frames[1:]:
+                for a, b in zip(frames[0], other):
+                    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        # the copy follows every change of the volume
+        v.set_tape(S.tape.demo_tape(sphere_radius=0.8))
+        v.fill_all()
+        c = S.default_camera(320, 240)
+        with_copy = v.trace(c, 320, 240, gbuf=True)
+        v.set_option("trace_distance_volume", 0)
+        without = v.trace(c, 320, 240, gbuf=True)
+        for a, b in zip(with_copy, without):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
         v.set_option("trace_variant", 0)
 
 

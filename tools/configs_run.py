@@ -74,10 +74,10 @@ def main():
                       f"steps mean(entered) {steps[entered].mean():.1f} p50 {np.percentile(steps[entered],50):.0f} "
                       f"p90 {np.percentile(steps[entered],90):.0f} p99 {np.percentile(steps[entered],99):.0f} max {steps.max():.0f}, "
                       f"out-of-steps {(code==-1).sum()}", flush=True)
-                for variant in (1, 0):
-                  v.set_option("trace_variant", variant)
+                for variant, dv in ((1, 0), (0, 0), (0, 1)):
+                  v.set_option("trace_variant", variant); v.set_option("trace_distance_volume", dv)
                   ms = timed(v, stream, lambda: v.trace_device(cam, 1920, 1080), 20)
-                  print(f"trace {name} variant={variant} 1920x1080 LINEAR: {ms:.3f} ms {1920*1080/ms/1e6:.2f} Grays/s; total steps {steps.sum():.3e} -> {steps.sum()/ms/1e6:.1f} Gsteps/s", flush=True)
+                  print(f"trace {name} variant={variant} dist_volume={dv} 1920x1080 LINEAR: {ms:.3f} ms {1920*1080/ms/1e6:.2f} Grays/s; total steps {steps.sum():.3e} -> {steps.sum()/ms/1e6:.1f} Gsteps/s", flush=True)
 
 
 if __name__ == "__main__":
