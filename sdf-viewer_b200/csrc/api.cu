@@ -1065,7 +1065,7 @@ int fill_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t w, uin
     memcpy(tp->ambient, cam->ambient, 12);
     // optional distance-only volume (4 B per voxel) for the march: built here after any change of tex0;
     // not with IPC neighbours, whose halo pushes this handle cannot observe
-    if (ctx->opt_dist_volume && ctx->stored_texels && !has_peers(ctx) && !ctx->peers_ever) {
+    if (ctx->opt_dist_volume && ctx->opt_trace_variant == 0 && ctx->stored_texels && !has_peers(ctx) && !ctx->peers_ever) {
         if (!ctx->dist_dev) CK(ctx, cudaMalloc(&ctx->dist_dev, ctx->stored_texels * sizeof(float)));
         if (!ctx->dist_valid) {
             CK(ctx, launch_extract_dist(ctx->tex0, ctx->dist_dev, ctx->stored_texels, ctx->sm_count * 8, ctx->stream));

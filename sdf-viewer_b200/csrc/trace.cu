@@ -118,7 +118,7 @@ struct CellCache {
     float c000, c100, c010, c110, c001, c101, c011, c111;
 };
 
-template <bool SNAP>
+template <bool SNAP, bool DIST>
 __device__ __forceinline__ float sample_dist_cached(const TraceParams& P, const Vol& v, float px, float py, float pz,
                                                     CellCache& cc) {
     float ax, ay, az;
@@ -127,7 +127,7 @@ __device__ __forceinline__ float sample_dist_cached(const TraceParams& P, const 
     const float fx0 = floorf(ux), fy0 = floorf(uy), fz0 = floorf(uz);
     if (fx0 != cc.x0 || fy0 != cc.y0 || fz0 != cc.z0) {
         const Taps t = linear_taps(v, ax, ay, az);
-        if (P.dist) {  // optional distance-only copy of tex0.r: 4 B per voxel instead of 16, same values
+        if (DIST) {  // optional distance-only copy of tex0.r: 4 B per voxel instead of 16, same values
             cc.c000 = __ldg(P.dist + t.i000); cc.c100 = __ldg(P.dist + t.i100); cc.c010 = __ldg(P.dist + t.i010);
             cc.c110 = __ldg(P.dist + t.i110); cc.c001 = __ldg(P.dist + t.i001); cc.c101 = __ldg(P.dist + t.i101);
             cc.c011 = __ldg(P.dist + t.i011); cc.c111 = __ldg(P.dist + t.i111);
@@ -235,7 +235,7 @@ __device__ __forceinline__ void write_outside(const TraceParams& P, size_t px) {
     if (P.rgba8) P.rgba8[px] = 0u;
 }
 
-template <bool SNAP, bool LINEAR>
+template <bool SNAP, bool LINEAR, bool DIST = false>
 __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, uint32_t j) {
     const size_t px = (size_t)j * P.width + i;
 
@@ -289,7 +289,7 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, ui
             steps = it;
             if (it >= max_steps - 1) { code = -1.0f; break; }                                          // :99-102
             if (oob_dist(P.clip_min, P.clip_max, hx, hy, hz) > 1e-4f) { code = -2.0f; break; }  // :106-109
-            if (LINEAR) s0x = sample_dist_cached<SNAP>(P, v0, hx, hy, hz, cell);                   // :112
+            if (LINEAR) s0x = sample_dist_cached<SNAP, DIST>(P, v0, hx, hy, hz, cell);             // :112
             else s0x = sample_dist<SNAP, LINEAR>(P, v0, hx, hy, hz);
             const float dist = s0x - 1e-1f;                                                  // :59
             if (dist < 1e-5f) { code = t; hit = true; break; }                               // :117-121
@@ -356,7 +356,7 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, ui
 // inside the screen rectangle of the projected clip box come first: the long marches start at
 // once and the cheap outside tiles fill in behind them.  Small CTAs release their SM slot as soon
 // as their own rays end instead of waiting for the slowest of 8 warps.
-template <bool SNAP, bool LINEAR>
+template <bool SNAP, bool LINEAR, bool DIST = false>
 __global__ void __launch_bounds__(64) trace_tiles_kernel(const __grid_constant__ TraceParams P) {
     const uint32_t rw = P.rect[2] - P.rect[0], rh = P.rect[3] - P.rect[1];
     const uint32_t n_heavy = rw * rh;
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(64) trace_tiles_kernel(const __grid_constant__
     const uint32_t i = tx * 8u + (threadIdx.x & 7u), j = ty * 8u + (threadIdx.x >> 3);
     if (i >= P.width || j >= P.height) return;
     if (outside) write_outside(P, (size_t)j * P.width + i);
-    else trace_pixel<SNAP, LINEAR>(P, i, j);
+    else trace_pixel<SNAP, LINEAR, DIST>(P, i, j);
 }
 
 // Variant 1: plain 2-D grid, 8 warps per CTA, each an 8 x 4 pixel tile; CTA tile = 32 x 8 pixels
@@ -418,8 +418,10 @@ cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s) {
     const bool snap = p.lod != 1.0f, lin = p.filter_linear != 0;
     if (variant == 0) {
         const unsigned grid = p.tiles_x * p.tiles_y;
-        if (!snap && lin) trace_tiles_kernel<false, true><<<grid, 64, 0, s>>>(p);
+        if (!snap && lin && p.dist) trace_tiles_kernel<false, true, true><<<grid, 64, 0, s>>>(p);
+        else if (!snap && lin) trace_tiles_kernel<false, true><<<grid, 64, 0, s>>>(p);
         else if (!snap && !lin) trace_tiles_kernel<false, false><<<grid, 64, 0, s>>>(p);
+        else if (snap && lin && p.dist) trace_tiles_kernel<true, true, true><<<grid, 64, 0, s>>>(p);
         else if (snap && lin) trace_tiles_kernel<true, true><<<grid, 64, 0, s>>>(p);
         else trace_tiles_kernel<true, false><<<grid, 64, 0, s>>>(p);
     } else {
