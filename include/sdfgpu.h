@@ -137,6 +137,49 @@ int sdfgpu_resample_box(sdfgpu_ctx* ctx, const float box[6], uint64_t* voxels_to
 int sdfgpu_voxel_positions(const sdfgpu_ctx* ctx, uint64_t first_flat, uint64_t count, float* xyz);
 int sdfgpu_ingest_samples(sdfgpu_ctx* ctx, uint64_t first_flat, uint64_t count, const void* samples);
 
+/* ------------------------------------------------ update from an SDFSurface */
+
+/* The `SDFSurface` trait (src/sdf/mod.rs:33-101) as a table of C callbacks -- the same four
+ * functions the WASM ABI exposes (src/sdf/wasm/mod.rs:5-37; host side src/sdf/wasm/native.rs:163-217,
+ * 463-483), so a host that already holds a `Box<dyn SDFSurface>` (a WasmerSDF, the built-in demo,
+ * anything else) passes thin trampolines.  `self` is handed back to every callback.
+ *   bounding_box : SDFSurface::bounding_box (:37), {min.xyz, max.xyz}; may be NULL (update never calls it)
+ *   sample       : SDFSurface::sample (:43) for one point; out = the 7 floats of SDFSample
+ *                  (:104-118: distance, r, g, b, metallic, roughness, occlusion)
+ *   sample_batch : optional batched form (the reference's "TODO: Batched sampling", :39): n points
+ *                  xyz[3n] -> out[7n]; used instead of `sample` when not NULL
+ *   changed      : SDFSurface::changed (:87): returns non-zero and fills out_box when Some(box); may be NULL
+ *   tape         : optional GPU capability, not in the reference: bytes of a tape (sdfgpu_tape.h)
+ *                  equivalent to sample(p, false), valid until the next call on this surface; returns
+ *                  non-zero when the surface has one.  NULL or zero => the surface is sampled on the
+ *                  host through sample / sample_batch and the results are ingested.
+ *   sample_threads : how many host threads may call sample / sample_batch concurrently (0 or 1 =
+ *                  only the calling thread, which is what the reference does, scene/sdf/mod.rs:174;
+ *                  WasmerSDF serialises on a Mutex anyway, native.rs:189). */
+typedef struct sdfgpu_surface {
+    void* self;
+    void (*bounding_box)(void* self, float out_bb[6]);
+    void (*sample)(void* self, const float p[3], int distance_only, float out_sample[7]);
+    void (*sample_batch)(void* self, const float* xyz, uint64_t n, int distance_only, float* out_samples);
+    int (*changed)(void* self, float out_box[6]);
+    int (*tape)(void* self, const void** bytes, size_t* len);
+    uint32_t sample_threads;
+} sdfgpu_surface;
+
+/* SDFViewer::update(&mut self, sdf: impl SDFSurface, max_delta_time) -> usize
+ * (src/app/scene/sdf/mod.rs:128-217) with the trait object itself: polls sdf.changed(), runs the
+ * changed-box state machine (:131-154) and then
+ *  - a surface WITH a tape: re-sends the tape when it is new or reported a change and runs every
+ *    pending LoadingManager pass on the GPU (sdfgpu_update; a pass is far below max_delta_time);
+ *  - a surface WITHOUT a tape (any existing .wasm SDF): walks the LoadingManager in the reference's
+ *    order (loading.rs:50-76) for at most `max_delta_seconds` (at least one iteration, :173), decides
+ *    `update_required` per voxel (:184-190), calls sample for the required voxels on the host,
+ *    and scatters the results into the volumes with the store rules of :196-208 applied on the GPU.
+ *    A pass may stop half way and continue in the next call, exactly like the reference.
+ * `iterations` receives the LoadingManager iterations performed (the return value of update). */
+int sdfgpu_update_surface(sdfgpu_ctx* ctx, const sdfgpu_surface* sdf, double max_delta_seconds,
+                          uint64_t* iterations);
+
 /* SDFViewer::commit (src/app/scene/sdf/mod.rs:220-239): no upload is needed
  * (the volumes already live in HBM); latches
  * lod_dist_between_samples = 2^passes_left for the tracer (:226). */
@@ -146,6 +189,23 @@ int sdfgpu_commit(sdfgpu_ctx* ctx);
  * (src/app/scene/sdf/loading.rs:80-105; read by scene/mod.rs:153,229-239). */
 int sdfgpu_loading_state(const sdfgpu_ctx* ctx, uint64_t* len, uint64_t* total_iterations,
                          uint32_t* passes_left, uint32_t* passes);
+
+/* The LoadingManager itself (src/app/scene/sdf/loading.rs:5-115) as a device-free object: the same
+ * counters and cursor a handle keeps internally, for hosts that want the visit order (progress bars,
+ * their own batching) and for the tests ported from loading.rs:117-171.
+ *   next     : Iterator::next (:50-76): returns 1 and the index, or 0 when loading is done
+ *   next_run : up to max_iters consecutive next() results that share one x row: they are
+ *              (first[0] + i * *step, first[1], first[2]) for i < the returned count (0 = done)
+ *   len / total_iterations / passes_left : :80-105 */
+typedef struct sdfgpu_loading sdfgpu_loading;
+int sdfgpu_loading_create(const uint32_t limits[3], uint32_t passes, sdfgpu_loading** out);
+void sdfgpu_loading_destroy(sdfgpu_loading* lm);
+void sdfgpu_loading_reset(sdfgpu_loading* lm, uint32_t passes);
+int sdfgpu_loading_next(sdfgpu_loading* lm, uint32_t out_index[3]);
+uint64_t sdfgpu_loading_next_run(sdfgpu_loading* lm, uint64_t max_iters, uint32_t first[3], uint32_t* step);
+uint64_t sdfgpu_loading_len(const sdfgpu_loading* lm);
+uint64_t sdfgpu_loading_total_iterations(const sdfgpu_loading* lm);
+uint32_t sdfgpu_loading_passes_left(const sdfgpu_loading* lm);
 
 /* Reset both volumes to AIR_DIST and restart loading with `loading_passes`
  * (what set_sdf does by rebuilding the viewer, scene/mod.rs:154-155). */

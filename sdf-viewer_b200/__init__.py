@@ -6,7 +6,7 @@ Import as `sdf_viewer_b200` (shim at the repo root).  Nothing here imports `orac
 """
 from . import tape, loading, sdf  # noqa: F401
 from .sdf import SDFSurface, SDFDemo, TapeSDF  # noqa: F401
-from .loading import LoadingManager  # noqa: F401
+from .loading import LoadingManager, NativeLoadingManager  # noqa: F401
 from .viewer import (  # noqa: F401
     SDFViewer, Camera, Rays, SdfGpuError, GBUF_FLOATS, dims_from_bb, default_camera, look_at_camera, camera_rays,
     jit_check,

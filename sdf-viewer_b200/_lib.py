@@ -49,6 +49,25 @@ class Rays(C.Structure):  # sdfgpu_rays
     ]
 
 
+BOUNDING_BOX_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_float))
+SAMPLE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float))
+SAMPLE_BATCH_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_float), C.c_uint64, C.c_int, C.POINTER(C.c_float))
+CHANGED_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float))
+TAPE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t))
+
+
+class Surface(C.Structure):  # sdfgpu_surface
+    _fields_ = [
+        ("self", C.c_void_p),
+        ("bounding_box", BOUNDING_BOX_FN),
+        ("sample", SAMPLE_FN),
+        ("sample_batch", SAMPLE_BATCH_FN),
+        ("changed", CHANGED_FN),
+        ("tape", TAPE_FN),
+        ("sample_threads", C.c_uint32),
+    ]
+
+
 _vp = C.c_void_p
 _u32 = C.c_uint32
 _u64 = C.c_uint64
@@ -74,12 +93,21 @@ SIGNATURES = {
     "sdfgpu_set_tape": (C.c_int, [_vp, _vp, C.c_size_t]),
     "sdfgpu_jit_check": (C.c_int, [_vp, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]),
     "sdfgpu_update": (C.c_int, [_vp, _fp, _u32, _u64p]),
+    "sdfgpu_update_surface": (C.c_int, [_vp, C.POINTER(Surface), C.c_double, _u64p]),
     "sdfgpu_fill_all": (C.c_int, [_vp]),
     "sdfgpu_resample_box": (C.c_int, [_vp, _fp, _u64p]),
     "sdfgpu_voxel_positions": (C.c_int, [_vp, _u64, _u64, _vp]),
     "sdfgpu_ingest_samples": (C.c_int, [_vp, _u64, _u64, _vp]),
     "sdfgpu_commit": (C.c_int, [_vp]),
     "sdfgpu_loading_state": (C.c_int, [_vp, _u64p, _u64p, _u32p, _u32p]),
+    "sdfgpu_loading_create": (C.c_int, [_u32p, _u32, _vpp]),
+    "sdfgpu_loading_destroy": (None, [_vp]),
+    "sdfgpu_loading_reset": (None, [_vp, _u32]),
+    "sdfgpu_loading_next": (C.c_int, [_vp, _u32p]),
+    "sdfgpu_loading_next_run": (_u64, [_vp, _u64, _u32p, _u32p]),
+    "sdfgpu_loading_len": (_u64, [_vp]),
+    "sdfgpu_loading_total_iterations": (_u64, [_vp]),
+    "sdfgpu_loading_passes_left": (_u32, [_vp]),
     "sdfgpu_reset": (C.c_int, [_vp, _u32]),
     "sdfgpu_download": (C.c_int, [_vp, _vp, _vp]),
     "sdfgpu_device_ptrs": (C.c_int, [_vp, _vpp, _vpp]),

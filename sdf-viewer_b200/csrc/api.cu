@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sdfgpu_internal.h"
@@ -35,13 +37,15 @@ struct LoadingState {  // LoadingManager at pass granularity, loading.rs:5-19
     uint64_t limits[3] = {0, 0, 0};
     uint64_t passes = 0;
     uint64_t step_size = 0;
-    uint64_t iterations = 0;  // always 0 between passes
+    uint64_t next[3] = {0, 0, 0};  // next_index: only the host-sampled path stops inside a pass
+    uint64_t iterations = 0;       // iterations done in the current pass (0 between passes)
     uint64_t total_iterations = 0;
 
     void reset(uint64_t p) {  // :37-43
         passes = p;
         const uint32_t e = (uint32_t)(p > 1 ? p : 1) - 1;
         step_size = e < 63 ? (uint64_t)1 << e : (uint64_t)1 << 62;
+        next[0] = next[1] = next[2] = 0;
         iterations = 0;
         total_iterations = 0;
     }
@@ -60,9 +64,41 @@ struct LoadingState {  // LoadingManager at pass granularity, loading.rs:5-19
         if (step_size == 0) return 0;
         return (uint32_t)log2f((float)step_size) + 1;
     }
-    void finish_pass() {  // the tail of next(), :67-71
-        total_iterations += pass_items(step_size);
+    // Up to `max_iters` consecutive iterations of next() (:50-76) that lie in one x row: they visit
+    // (x0 + i * step, y, z) for i < take.  Returns take (0 when loading is done) and advances the
+    // cursor and the counters exactly as `take` calls of next() would; *pass_end is set when the last
+    // of them ended the pass (step_size is then already the next pass's).
+    uint64_t next_row(uint64_t max_iters, uint64_t* x0, uint64_t* y, uint64_t* z, uint64_t* step, bool* pass_end) {
+        *pass_end = false;
+        if (step_size == 0 || max_iters == 0) return 0;
+        const uint64_t s = step_size;
+        *x0 = next[0]; *y = next[1]; *z = next[2]; *step = s;
+        // next() yields next_index even when it lies outside the limits (an empty axis): one iteration
+        const uint64_t row_left = next[0] < limits[0] ? (limits[0] - next[0] + s - 1) / s : 1;
+        const uint64_t take = row_left < max_iters ? row_left : max_iters;
+        iterations += take;
+        total_iterations += take;
+        next[0] += take * s;
+        if (next[0] >= limits[0]) {
+            next[0] = 0;
+            next[1] += s;
+            if (next[1] >= limits[1]) {
+                next[1] = 0;
+                next[2] += s;
+                if (next[2] >= limits[2]) {
+                    step_size = prev_power_of_2((uint32_t)(s - 1));
+                    next[0] = next[1] = next[2] = 0;
+                    iterations = 0;
+                    *pass_end = true;
+                }
+            }
+        }
+        return take;
+    }
+    void finish_pass() {  // the rest of the current pass at once, then the tail of next(), :67-71
+        total_iterations += pass_items(step_size) - iterations;
         step_size = prev_power_of_2((uint32_t)(step_size - 1));
+        next[0] = next[1] = next[2] = 0;
         iterations = 0;
     }
 };
@@ -108,6 +144,21 @@ struct sdfgpu_ctx {
     uint32_t* rgba8_dev = nullptr;
     float* ingest_dev = nullptr;  // staging for sdfgpu_ingest_samples: records, then the LUT
     size_t ingest_cap = 0;
+    // sdfgpu_update_surface, host-sampled path: two pinned staging buffers (records + texel indices) with
+    // their device copies, so that sampling chunk i+1 overlaps the transfer and scatter of chunk i
+    struct HostStage {
+        float* rec = nullptr; uint32_t* idx = nullptr;          // pinned host
+        float* rec_dev = nullptr; uint32_t* idx_dev = nullptr;  // device
+        size_t cap = 0;                                         // voxels
+        cudaEvent_t done = nullptr;
+        bool in_flight = false;
+    } stage[2];
+    uint64_t stage_turn = 0;
+    float* gather_host = nullptr;  // pinned: tex0.r of a chunk's candidates when the state is unknown
+    float* gather_dev = nullptr;
+    size_t gather_cap = 0;
+    int64_t pass_known = 0;        // known_step when the current (partially walked) host pass began
+    std::vector<unsigned char> tape_bytes;  // the public tape last given to sdfgpu_set_tape (change detection)
     float* lut_dev = nullptr;
     float* dist_dev = nullptr;  // optional distance-only volume for the tracer (option trace_distance_volume)
     bool dist_valid = false;
@@ -489,6 +540,11 @@ SDFGPU_API void sdfgpu_destroy(sdfgpu_ctx* ctx) {
     (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
     (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->rgba8_dev); (void)cudaFree(ctx->touched_dev);
     (void)cudaFree(ctx->ingest_dev); (void)cudaFree(ctx->lut_dev); (void)cudaFree(ctx->dist_dev);
+    for (auto& st : ctx->stage) {
+        (void)cudaFreeHost(st.rec); (void)cudaFreeHost(st.idx); (void)cudaFree(st.rec_dev); (void)cudaFree(st.idx_dev);
+        if (st.done) (void)cudaEventDestroy(st.done);
+    }
+    (void)cudaFreeHost(ctx->gather_host); (void)cudaFree(ctx->gather_dev);
     if (ctx->halo_stream) (void)cudaStreamDestroy(ctx->halo_stream);
     if (ctx->ev_boundary) (void)cudaEventDestroy(ctx->ev_boundary);
     if (ctx->ev_pushed) (void)cudaEventDestroy(ctx->ev_pushed);
@@ -698,6 +754,7 @@ SDFGPU_API int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_by
                                  DOP_PRIM + 0 * 6 + SDFT_SHAPE_SPHERE * 3 + SDFT_MAT_NORMAL, DOP_POP_DEMO_DIFF, DOP_END};
     ctx->structure_is_demo = ctx->opcodes.size() == 5 && !memcmp(ctx->opcodes.data(), demo_ops, sizeof demo_ops);
     ctx->has_tape = true;
+    ctx->tape_bytes.assign((const unsigned char*)tape, (const unsigned char*)tape + tape_bytes);
     return SDFGPU_OK;
 }
 
@@ -720,13 +777,14 @@ SDFGPU_API int sdfgpu_jit_check(const void* tape, size_t tape_bytes, int voxels_
 
 // -------------------------------------------------------------------- fill
 
-SDFGPU_API int sdfgpu_update(sdfgpu_ctx* ctx, const float* changed_box, uint32_t max_passes, uint64_t* iterations) {
-    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
-    if (iterations) *iterations = 0;
-    if (!ctx->has_tape) return fail(ctx, SDFGPU_ERR_STATE, "no tape set (call sdfgpu_set_tape first)");
-    set_device(ctx);
+namespace {
+
+// The head of SDFViewer::update: merge the reported box into the pending one (scene/sdf/mod.rs:131-139;
+// merge_bounding_boxes, src/sdf/defaults.rs:59-72) and, when nothing is loading, start the 3-pass
+// re-sample (:144-154).
+void changed_box_state_machine(sdfgpu_ctx* ctx, const float* changed_box) {
     bool just_changed_box = false;
-    if (changed_box) {  // scene/sdf/mod.rs:131-139; merge_bounding_boxes, src/sdf/defaults.rs:59-72
+    if (changed_box) {
         if (ctx->has_changed_box) {
             for (int i = 0; i < 3; ++i) {
                 ctx->changed_box[i] = fminf(ctx->changed_box[i], changed_box[i]);
@@ -739,25 +797,45 @@ SDFGPU_API int sdfgpu_update(sdfgpu_ctx* ctx, const float* changed_box, uint32_t
         ctx->changed_box_while_loading = ctx->lm.len() > 0 || ctx->changed_box_while_loading;
         just_changed_box = true;
     }
-    if (ctx->has_changed_box && ctx->lm.len() == 0) {  // :144-154
+    if (ctx->has_changed_box && ctx->lm.len() == 0) {
         ctx->lm.reset(3);
         if (!just_changed_box) {
             if (!ctx->changed_box_while_loading) ctx->has_changed_box = false;
             ctx->changed_box_while_loading = false;
         }
     }
+}
+
+// index range [first, last] of table entries inside [lo, hi] (closed, float compare, :187-189)
+bool index_range_in(const std::vector<float>& t, float lo, float hi, uint32_t* first, uint32_t* last) {
+    uint32_t f = 0xffffffffu, l = 0;
+    for (uint32_t i = 0; i < t.size(); ++i)
+        if (t[i] >= lo && t[i] <= hi) {
+            if (f == 0xffffffffu) f = i;
+            l = i;
+        }
+    if (f == 0xffffffffu) return false;
+    *first = f; *last = l;
+    return true;
+}
+
+// The loop of SDFViewer::update (:173-215) for a surface that has a tape: one LoadingManager pass per
+// kernel launch, until nothing is pending or `max_passes` (0 = no limit) have run.  The launches
+// are asynchronous and a pass takes well under a millisecond, so max_delta_time has nothing to bound.
+int gpu_passes(sdfgpu_ctx* ctx, uint32_t max_passes, uint64_t* iterations) {
     const uint64_t start_iter = ctx->lm.total_iterations;
     uint32_t za, zb;
     fill_z_range(ctx, &za, &zb);
     uint32_t done = 0;
-    while (ctx->lm.step_size != 0 && (max_passes == 0 || done < max_passes)) {  // :173-215, one pass per launch
+    while (ctx->lm.step_size != 0 && (max_passes == 0 || done < max_passes)) {
         const uint32_t step = (uint32_t)ctx->lm.step_size;
         uint32_t lo[3] = {0, 0, za}, hi[3] = {ctx->dims[0], ctx->dims[1], zb};
         // The rule "sample iff tex0.r == AIR_DIST or position in box" (:184-190) needs no read when the
         // host knows which voxels hold AIR_DIST (re-sampling a voxel whose stored value merely equals
         // AIR_DIST is idempotent: sample() is pure, src/sdf/mod.rs:43).
         int rc = SDFGPU_OK;
-        const int64_t k = ctx->known_step;
+        // a pass the host-sampled path left half way: its voxels are a mix, read tex0.r
+        const int64_t k = ctx->lm.iterations ? -1 : ctx->known_step;
         if (!ctx->has_changed_box && k == 0) {
             rc = run_fill(ctx, step, lo, hi, FILL_ALL, nullptr);                       // everything is AIR_DIST
             ctx->known_step = step;
@@ -771,14 +849,8 @@ SDFGPU_API int sdfgpu_update(sdfgpu_ctx* ctx, const float* changed_box, uint32_t
             bool empty = false;
             const std::vector<float>* tab[3] = {&ctx->px, &ctx->py, &ctx->pz};
             for (int a = 0; a < 3 && !empty; ++a) {
-                uint32_t first = 0xffffffffu, last = 0;
-                const std::vector<float>& t = *tab[a];
-                for (uint32_t i = 0; i < t.size(); ++i)
-                    if (t[i] >= ctx->changed_box[a] && t[i] <= ctx->changed_box[3 + a]) {
-                        if (first == 0xffffffffu) first = i;
-                        last = i;
-                    }
-                if (first == 0xffffffffu) { empty = true; break; }
+                uint32_t first, last;
+                if (!index_range_in(*tab[a], ctx->changed_box[a], ctx->changed_box[3 + a], &first, &last)) { empty = true; break; }
                 if (first > lo[a]) lo[a] = first;
                 if (last + 1 < hi[a]) hi[a] = last + 1;
             }
@@ -797,6 +869,220 @@ SDFGPU_API int sdfgpu_update(sdfgpu_ctx* ctx, const float* changed_box, uint32_t
     }
     if (iterations) *iterations = ctx->lm.total_iterations - start_iter;  // :216
     return SDFGPU_OK;
+}
+
+int ensure_lut_dev(sdfgpu_ctx* ctx) {
+    if (!ctx->lut_dev) {
+        CK(ctx, cudaMalloc(&ctx->lut_dev, sizeof ctx->lut));
+        CK(ctx, cudaMemcpyAsync(ctx->lut_dev, ctx->lut, sizeof ctx->lut, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return SDFGPU_OK;
+}
+
+int ensure_stage(sdfgpu_ctx* ctx, sdfgpu_ctx::HostStage& st, size_t voxels) {
+    if (!st.done) CK(ctx, cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+    if (st.in_flight) {  // the previous chunk that used this buffer must have been consumed
+        CK(ctx, cudaEventSynchronize(st.done));
+        st.in_flight = false;
+    }
+    if (voxels <= st.cap) return SDFGPU_OK;
+    size_t cap = st.cap ? st.cap : 4096;
+    while (cap < voxels) cap *= 2;
+    (void)cudaFreeHost(st.rec); (void)cudaFreeHost(st.idx); (void)cudaFree(st.rec_dev); (void)cudaFree(st.idx_dev);
+    st.rec = nullptr; st.idx = nullptr; st.rec_dev = nullptr; st.idx_dev = nullptr; st.cap = 0;
+    CK(ctx, cudaMallocHost(&st.rec, cap * 7 * sizeof(float)));
+    CK(ctx, cudaMallocHost(&st.idx, cap * sizeof(uint32_t)));
+    CK(ctx, cudaMalloc(&st.rec_dev, cap * 7 * sizeof(float)));
+    CK(ctx, cudaMalloc(&st.idx_dev, cap * sizeof(uint32_t)));
+    st.cap = cap;
+    return SDFGPU_OK;
+}
+
+// sdf.sample(pos, false) for n positions (:193), on up to sdf->sample_threads host threads
+void sample_on_host(const sdfgpu_surface* sdf, const float* xyz, size_t n, float* out) {
+    auto run = [&](size_t a, size_t b) {
+        if (sdf->sample_batch) {
+            if (b > a) sdf->sample_batch(sdf->self, xyz + 3 * a, (uint64_t)(b - a), 0, out + 7 * a);
+        } else {
+            for (size_t i = a; i < b; ++i) sdf->sample(sdf->self, xyz + 3 * i, 0, out + 7 * i);
+        }
+    };
+    size_t threads = sdf->sample_threads > 1 ? sdf->sample_threads : 1;
+    if (threads > n / 256 + 1) threads = n / 256 + 1;
+    if (threads <= 1) { run(0, n); return; }
+    std::vector<std::thread> pool;
+    const size_t per = (n + threads - 1) / threads;
+    for (size_t t = 1; t < threads; ++t) {
+        const size_t a = t * per < n ? t * per : n, b = (t + 1) * per < n ? (t + 1) * per : n;
+        pool.emplace_back(run, a, b);
+    }
+    run(0, per < n ? per : n);
+    for (auto& th : pool) th.join();
+}
+
+// The loop of SDFViewer::update (:173-215) for a surface WITHOUT a tape: the LoadingManager is walked
+// on the host in the reference's order, in chunks; per chunk the voxels that need an update are
+// sampled through the callbacks and scattered into the volumes by ingest_scatter_kernel.
+int host_sampled_passes(sdfgpu_ctx* ctx, const sdfgpu_surface* sdf, double max_seconds, uint64_t* iterations) {
+    LoadingState& lm = ctx->lm;
+    const uint64_t start_iter = lm.total_iterations;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
+    const uint64_t W = ctx->dims[0], H = ctx->dims[1], D = ctx->dims[2];
+    const uint64_t slice = W * H;
+    uint32_t za, zb;
+    fill_z_range(ctx, &za, &zb);
+    const float air = air_dist_value();
+    int rc;
+    if ((rc = ensure_lut_dev(ctx)) != SDFGPU_OK) return rc;
+    if (W * H * D == 0) {  // an empty grid has nothing to visit
+        while (lm.step_size != 0) lm.finish_pass();
+        return SDFGPU_OK;
+    }
+    std::vector<float> xyz;
+    std::vector<uint32_t> cand;
+    std::vector<unsigned char> cand_in_box;
+    bool first = true, pass_finished = false;
+    uint64_t chunk = max_seconds > 0.0 ? 256 : 1;  // iterations walked before the clock is read again
+    while (lm.step_size != 0 && (first || elapsed() < max_seconds)) {
+        first = false;
+        const uint64_t step = lm.step_size;
+        if (lm.iterations == 0) ctx->pass_known = ctx->known_step;
+        // while a pass is half done the volume is a mix the other entry points cannot describe
+        const int64_t k = ctx->pass_known;
+        ctx->known_step = -1;
+        const bool has_box = ctx->has_changed_box;
+        const float* box = ctx->changed_box;
+        // ---- walk up to `chunk` iterations of this pass from the cursor (loading.rs:50-76)
+        xyz.clear(); cand.clear(); cand_in_box.clear();
+        uint64_t walked = 0;
+        bool pass_end = false;
+        while (walked < chunk && !pass_end) {
+            uint64_t x0, y, z, st_;
+            const uint64_t take = lm.next_row(chunk - walked, &x0, &y, &z, &st_, &pass_end);
+            if (!take) break;
+            walked += take;
+            if (x0 >= W || y >= H || z >= D) continue;  // cannot happen on a non-empty grid
+            const bool stored = z >= za && z < zb;  // a slab handle skips the other ranks' slices
+            const bool row_in_box = has_box && ctx->py[y] >= box[1] && ctx->py[y] <= box[4] && ctx->pz[z] >= box[2] &&
+                                    ctx->pz[z] <= box[5];
+            // without a read: k == 0 everything is AIR_DIST; k == 1 nothing is (only the box matters);
+            // k = 2^j exactly the multiples of k have been sampled
+            if (stored && (k != 1 || row_in_box)) {
+                for (uint64_t i = 0; i < take; ++i) {
+                    const uint64_t x = x0 + i * step;
+                    const bool in_box = row_in_box && ctx->px[x] >= box[0] && ctx->px[x] <= box[3];
+                    const bool is_air = k == 0 || (k > 1 && ((x | y | z) & (uint64_t)(k - 1)) != 0);
+                    if (k == -1 || in_box || is_air) {
+                        cand.push_back((uint32_t)((z - ctx->z_lo) * slice + y * W + x));
+                        cand_in_box.push_back(in_box ? 1 : 0);
+                        xyz.push_back(ctx->px[x]); xyz.push_back(ctx->py[y]); xyz.push_back(ctx->pz[z]);
+                    }
+                }
+            }
+        }
+        // ---- unknown state: read tex0.r of the candidates and keep those that hold AIR_DIST or lie in the box
+        size_t n = cand.size();
+        if (k == -1 && n) {
+            if (n > ctx->gather_cap) {
+                CK(ctx, cudaStreamSynchronize(ctx->stream));
+                (void)cudaFreeHost(ctx->gather_host); (void)cudaFree(ctx->gather_dev);
+                ctx->gather_host = nullptr; ctx->gather_dev = nullptr; ctx->gather_cap = 0;
+                size_t cap = 4096;
+                while (cap < n) cap *= 2;
+                CK(ctx, cudaMallocHost(&ctx->gather_host, cap * sizeof(float)));
+                CK(ctx, cudaMalloc(&ctx->gather_dev, cap * sizeof(float)));
+                ctx->gather_cap = cap;
+            }
+            sdfgpu_ctx::HostStage& st = ctx->stage[ctx->stage_turn & 1];
+            if ((rc = ensure_stage(ctx, st, n)) != SDFGPU_OK) return rc;
+            memcpy(st.idx, cand.data(), n * sizeof(uint32_t));
+            CK(ctx, cudaMemcpyAsync(st.idx_dev, st.idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+            CK(ctx, launch_gather_dist(ctx->tex0, st.idx_dev, n, ctx->gather_dev, ctx->sm_count * 8, ctx->stream));
+            ctx->launches++;
+            CK(ctx, cudaMemcpyAsync(ctx->gather_host, ctx->gather_dev, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(ctx, cudaStreamSynchronize(ctx->stream));
+            size_t m = 0;
+            for (size_t i = 0; i < n; ++i)
+                if (ctx->gather_host[i] == air || cand_in_box[i]) {
+                    cand[m] = cand[i];
+                    xyz[3 * m] = xyz[3 * i]; xyz[3 * m + 1] = xyz[3 * i + 1]; xyz[3 * m + 2] = xyz[3 * i + 2];
+                    ++m;
+                }
+            n = m;
+        }
+        // ---- sample on the host, scatter on the GPU
+        if (n) {
+            sdfgpu_ctx::HostStage& st = ctx->stage[ctx->stage_turn & 1];
+            ++ctx->stage_turn;
+            if ((rc = ensure_stage(ctx, st, n)) != SDFGPU_OK) return rc;
+            memcpy(st.idx, cand.data(), n * sizeof(uint32_t));
+            sample_on_host(sdf, xyz.data(), n, st.rec);
+            CK(ctx, cudaMemcpyAsync(st.idx_dev, st.idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+            CK(ctx, cudaMemcpyAsync(st.rec_dev, st.rec, n * 7 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+            CK(ctx, launch_ingest_scatter(ctx->tex0, ctx->tex1, st.rec_dev, st.idx_dev, n, ctx->lut_dev, air,
+                                          ctx->sm_count * 8, ctx->stream));
+            CK(ctx, cudaEventRecord(st.done, ctx->stream));
+            st.in_flight = true;
+            ctx->launches++;
+            ctx->dist_valid = false;
+        }
+        if (pass_end) {
+            // sampled so far: what was known before this pass plus the lattice of `step`
+            if (k == -1) ctx->known_step = step == 1 ? 1 : -1;
+            else if (k == 0) ctx->known_step = (int64_t)step;
+            else ctx->known_step = k < (int64_t)step ? k : (int64_t)step;
+            pass_finished = true;
+        }
+        // next chunk: as many iterations as the measured rate fits into what is left of the budget
+        const double el = elapsed();
+        const uint64_t done_now = lm.total_iterations - start_iter;
+        if (el > 0.0 && max_seconds > el) {
+            const double want = (double)done_now / el * (max_seconds - el) * 0.5;
+            chunk = want < 256.0 ? 256 : want > 1048576.0 ? 1048576 : (uint64_t)want;
+        } else {
+            chunk = 256;
+        }
+    }
+    if (pass_finished && has_peers(ctx)) {
+        if ((rc = push_halos(ctx, ctx->stream)) != SDFGPU_OK) return rc;
+    }
+    if (iterations) *iterations = lm.total_iterations - start_iter;  // :216
+    return SDFGPU_OK;
+}
+
+}  // namespace
+
+SDFGPU_API int sdfgpu_update(sdfgpu_ctx* ctx, const float* changed_box, uint32_t max_passes, uint64_t* iterations) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (iterations) *iterations = 0;
+    if (!ctx->has_tape) return fail(ctx, SDFGPU_ERR_STATE, "no tape set (call sdfgpu_set_tape first)");
+    set_device(ctx);
+    changed_box_state_machine(ctx, changed_box);
+    return gpu_passes(ctx, max_passes, iterations);
+}
+
+SDFGPU_API int sdfgpu_update_surface(sdfgpu_ctx* ctx, const sdfgpu_surface* sdf, double max_delta_seconds,
+                                     uint64_t* iterations) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (iterations) *iterations = 0;
+    if (!sdf) return fail(ctx, SDFGPU_ERR_INVALID, "sdf is NULL");
+    if (max_delta_seconds != max_delta_seconds) return fail(ctx, SDFGPU_ERR_INVALID, "max_delta_seconds is NaN");
+    const void* tape = nullptr;
+    size_t tape_len = 0;
+    const bool has_tape = sdf->tape && sdf->tape(sdf->self, &tape, &tape_len) && tape && tape_len;
+    if (!has_tape && !sdf->sample && !sdf->sample_batch)
+        return fail(ctx, SDFGPU_ERR_INVALID, "the surface has neither a tape nor a sample callback");
+    set_device(ctx);
+    float box[6];
+    const bool changed = sdf->changed && sdf->changed(sdf->self, box);  // :130
+    if (has_tape && (!ctx->has_tape || ctx->tape_bytes.size() != tape_len || memcmp(ctx->tape_bytes.data(), tape, tape_len))) {
+        const int rc = sdfgpu_set_tape(ctx, tape, tape_len);
+        if (rc != SDFGPU_OK) return rc;
+    }
+    changed_box_state_machine(ctx, changed ? box : nullptr);
+    if (has_tape) return gpu_passes(ctx, 0, iterations);
+    return host_sampled_passes(ctx, sdf, max_delta_seconds, iterations);
 }
 
 SDFGPU_API int sdfgpu_fill_all(sdfgpu_ctx* ctx) {
@@ -948,6 +1234,48 @@ SDFGPU_API int sdfgpu_loading_state(const sdfgpu_ctx* ctx, uint64_t* len, uint64
     if (passes) *passes = (uint32_t)ctx->lm.passes;
     return SDFGPU_OK;
 }
+
+// ---- the LoadingManager as a device-free object (same LoadingState the handles use)
+struct sdfgpu_loading {
+    LoadingState lm;
+};
+
+SDFGPU_API int sdfgpu_loading_create(const uint32_t limits[3], uint32_t passes, sdfgpu_loading** out) {
+    if (!out) return fail(nullptr, SDFGPU_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!limits) return fail(nullptr, SDFGPU_ERR_INVALID, "limits is NULL");
+    sdfgpu_loading* l = new (std::nothrow) sdfgpu_loading();
+    if (!l) return fail(nullptr, SDFGPU_ERR_INVALID, "out of host memory");
+    for (int a = 0; a < 3; ++a) l->lm.limits[a] = limits[a];
+    l->lm.reset(passes);
+    *out = l;
+    return SDFGPU_OK;
+}
+
+SDFGPU_API void sdfgpu_loading_destroy(sdfgpu_loading* l) { delete l; }
+
+SDFGPU_API void sdfgpu_loading_reset(sdfgpu_loading* l, uint32_t passes) {
+    if (l) l->lm.reset(passes);
+}
+
+SDFGPU_API uint64_t sdfgpu_loading_next_run(sdfgpu_loading* l, uint64_t max_iters, uint32_t first[3], uint32_t* step) {
+    if (!l) return 0;
+    uint64_t x0 = 0, y = 0, z = 0, s = 0;
+    bool pass_end;
+    const uint64_t n = l->lm.next_row(max_iters, &x0, &y, &z, &s, &pass_end);
+    if (n && first) { first[0] = (uint32_t)x0; first[1] = (uint32_t)y; first[2] = (uint32_t)z; }
+    if (n && step) *step = (uint32_t)s;
+    return n;
+}
+
+SDFGPU_API int sdfgpu_loading_next(sdfgpu_loading* l, uint32_t out_index[3]) {
+    uint32_t step;
+    return sdfgpu_loading_next_run(l, 1, out_index, &step) ? 1 : 0;
+}
+
+SDFGPU_API uint64_t sdfgpu_loading_len(const sdfgpu_loading* l) { return l ? l->lm.len() : 0; }
+SDFGPU_API uint64_t sdfgpu_loading_total_iterations(const sdfgpu_loading* l) { return l ? l->lm.total_iterations : 0; }
+SDFGPU_API uint32_t sdfgpu_loading_passes_left(const sdfgpu_loading* l) { return l ? l->lm.passes_left() : 0; }
 
 SDFGPU_API int sdfgpu_reset(sdfgpu_ctx* ctx, uint32_t loading_passes) {
     if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");

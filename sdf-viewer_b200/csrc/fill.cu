@@ -40,6 +40,37 @@ __global__ void __launch_bounds__(256) ingest_kernel(float4* __restrict__ tex0, 
     }
 }
 
+// Scattered form of the ingest for the reference's interlaced visit order (loading.rs:50-76): record
+// i belongs to the stored texel idx[i].  Records are read 28 contiguous bytes per thread; the two
+// 16-byte stores per voxel are strided by the pass's step, which is what the visit order dictates.
+__global__ void __launch_bounds__(256) ingest_scatter_kernel(float4* __restrict__ tex0, float4* __restrict__ tex1,
+                                                             const float* __restrict__ samples,
+                                                             const uint32_t* __restrict__ idx, size_t n,
+                                                             const float* __restrict__ lut, float air_dist) {
+    __shared__ float s_lut[256];
+    s_lut[threadIdx.x] = lut[threadIdx.x];
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float* r = samples + 7 * i;
+        dev::Smp s;
+        s.d = r[0]; s.r = r[1]; s.g = r[2]; s.b = r[3]; s.m = r[4]; s.ro = r[5]; s.o = r[6];
+        float4 t0, t1;
+        dev::store_rules(s, s_lut, air_dist, t0, t1);
+        const uint32_t t = idx[i];
+        tex0[t] = t0;
+        tex1[t] = t1;
+    }
+}
+
+// tex0.r of the stored texels idx[0..n): the `tex0[flat][0] == AIR_DIST` test of scene/sdf/mod.rs:184
+// when the host does not know which voxels were sampled
+__global__ void __launch_bounds__(256) gather_dist_kernel(const float4* __restrict__ tex0,
+                                                          const uint32_t* __restrict__ idx, size_t n,
+                                                          float* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = reinterpret_cast<const float*>(tex0 + idx[i])[0];
+}
+
 typedef void (*fill_fn)(const FillParams);
 
 fill_fn pick(int V, int program) {
@@ -89,6 +120,23 @@ cudaError_t launch_ingest(float4* tex0, float4* tex1, const float* samples_dev, 
                           const float* lut_dev, float air_dist, int grid, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     ingest_kernel<<<grid, 256, 0, s>>>(tex0, tex1, samples_dev, first, n, lut_dev, air_dist);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ingest_scatter(float4* tex0, float4* tex1, const float* samples_dev, const uint32_t* idx_dev,
+                                  size_t n, const float* lut_dev, float air_dist, int grid, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const size_t blocks = (n + 255) / 256;
+    ingest_scatter_kernel<<<(int)(blocks < (size_t)grid ? blocks : (size_t)grid), 256, 0, s>>>(tex0, tex1, samples_dev,
+                                                                                            idx_dev, n, lut_dev, air_dist);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_dist(const float4* tex0, const uint32_t* idx_dev, size_t n, float* out_dev, int grid,
+                               cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const size_t blocks = (n + 255) / 256;
+    gather_dist_kernel<<<(int)(blocks < (size_t)grid ? blocks : (size_t)grid), 256, 0, s>>>(tex0, idx_dev, n, out_dev);
     return cudaGetLastError();
 }
 

@@ -63,6 +63,10 @@ bool jit_launch(void* fn, const FillParams& p, int grid, size_t smem, cudaStream
 
 cudaError_t launch_ingest(float4* tex0, float4* tex1, const float* samples_dev, size_t first, size_t n,
                           const float* lut_dev, float air_dist, int grid, cudaStream_t s);
+cudaError_t launch_ingest_scatter(float4* tex0, float4* tex1, const float* samples_dev, const uint32_t* idx_dev,
+                                  size_t n, const float* lut_dev, float air_dist, int grid, cudaStream_t s);
+cudaError_t launch_gather_dist(const float4* tex0, const uint32_t* idx_dev, size_t n, float* out_dev, int grid,
+                               cudaStream_t s);
 cudaError_t launch_set_const(float4* dst, size_t n_texels, float v, int grid_ctas, cudaStream_t s);
 cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s);
 cudaError_t launch_extract_dist(const float4* tex0, float* dist, size_t n, int grid, cudaStream_t s);

@@ -79,3 +79,51 @@ def pass_steps(passes):
         out.append(step)
         step = prev_power_of_2(step - 1)
     return out
+
+
+class NativeLoadingManager:
+    """The library's own LoadingManager object (`sdfgpu_loading_*`, include/sdfgpu.h): the counters and
+    cursor every handle keeps, device-free.  Same interface as `LoadingManager` plus `next_run`."""
+
+    def __init__(self, limits, passes):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib.load()
+        self.limits = tuple(int(v) for v in limits)
+        self.passes = int(passes)
+        h = C.c_void_p()
+        _lib.check(self._lib.sdfgpu_loading_create((C.c_uint32 * 3)(*self.limits), self.passes, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.sdfgpu_loading_destroy(self._h)
+            self._h = None
+
+    def reset(self, passes):
+        self.passes = int(passes)
+        self._lib.sdfgpu_loading_reset(self._h, self.passes)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        out = (self._C.c_uint32 * 3)()
+        if not self._lib.sdfgpu_loading_next(self._h, out):
+            raise StopIteration
+        return tuple(out)
+
+    def next_run(self, max_iters):
+        """(first_index, step, count): up to max_iters consecutive iterations inside one x row."""
+        first, step = (self._C.c_uint32 * 3)(), self._C.c_uint32()
+        n = self._lib.sdfgpu_loading_next_run(self._h, int(max_iters), first, self._C.byref(step))
+        return (tuple(first), step.value, n) if n else None
+
+    def __len__(self):
+        return self._lib.sdfgpu_loading_len(self._h)
+
+    def total_iterations(self):
+        return self._lib.sdfgpu_loading_total_iterations(self._h)
+
+    def passes_left(self):
+        return self._lib.sdfgpu_loading_passes_left(self._h)

@@ -9,11 +9,17 @@ class SDFSurface:
     def bounding_box(self):  # src/sdf/mod.rs:37
         raise NotImplementedError
 
+    def sample(self, points, distance_only=False):  # src/sdf/mod.rs:43, batched
+        """`SDFSample`s (n, 7) float32 -- distance, r, g, b, metallic, roughness, occlusion
+        (src/sdf/mod.rs:104-118) -- for points (n, 3).  Only surfaces without a tape need it."""
+        raise NotImplementedError
+
     def changed(self):  # src/sdf/mod.rs:87 -> Option<[Vector3; 2]>
         return None
 
     def tape(self):
-        """Tape bytes (include/sdfgpu_tape.h) equivalent to `sample(p, false)`."""
+        """Tape bytes (include/sdfgpu_tape.h) equivalent to `sample(p, false)`; a surface that
+        cannot be lowered leaves this unimplemented and is sampled on the host."""
         raise NotImplementedError
 
 

@@ -55,6 +55,73 @@ def camera_rays(cam, width, height):
     return rays
 
 
+def _surface_struct(sdf):
+    """An `sdf.SDFSurface` as the callback table of include/sdfgpu.h (`sdfgpu_surface`).  Exceptions raised
+    by the Python callbacks cannot cross the C ABI: they are kept and re-raised by the caller, and the
+    callback returns the reference's benign value (distance 1.0, src/sdf/wasm/native.rs:202)."""
+    surf = _lib.Surface()
+    error = [None]
+    keep = []
+
+    def bounding_box(_self, out):
+        try:
+            bb = sdf.bounding_box()
+            flat = list(bb[0]) + list(bb[1]) if len(bb) == 2 else list(bb)
+            for i in range(6):
+                out[i] = float(flat[i])
+        except Exception as e:  # noqa: BLE001
+            error[0] = error[0] or e
+
+    def sample_batch(_self, xyz, n, distance_only, out):
+        o = np.ctypeslib.as_array(out, shape=(int(n), 7))
+        try:
+            pts = np.ctypeslib.as_array(xyz, shape=(int(n), 3))
+            o[:] = np.asarray(sdf.sample(pts, bool(distance_only)), np.float32).reshape(int(n), 7)
+        except Exception as e:  # noqa: BLE001
+            error[0] = error[0] or e
+            o[:] = 0.0
+            o[:, 0] = 1.0
+
+    def changed(_self, out):
+        try:
+            bb = sdf.changed()
+        except Exception as e:  # noqa: BLE001
+            error[0] = error[0] or e
+            return 0
+        if bb is None:
+            return 0
+        flat = list(bb[0]) + list(bb[1]) if len(bb) == 2 else list(bb)
+        for i in range(6):
+            out[i] = float(flat[i])
+        return 1
+
+    def tape(_self, bytes_out, len_out):
+        try:
+            t = sdf.tape()
+        except NotImplementedError:
+            return 0
+        except Exception as e:  # noqa: BLE001
+            error[0] = error[0] or e
+            return 0
+        if not t:
+            return 0
+        buf = C.create_string_buffer(bytes(t), len(t))
+        keep.append(buf)
+        bytes_out[0] = C.cast(buf, C.c_void_p).value
+        len_out[0] = len(t)
+        return 1
+
+    surf.self = None
+    surf.bounding_box = _lib.BOUNDING_BOX_FN(bounding_box)
+    surf.sample_batch = _lib.SAMPLE_BATCH_FN(sample_batch)
+    surf.changed = _lib.CHANGED_FN(changed)
+    surf.tape = _lib.TAPE_FN(tape)
+    surf.sample_threads = 1  # Python callbacks hold the GIL
+    surf._py_error = error
+    surf._keep = keep
+    return surf
+
+
 class _LoadingView:
     """`viewer.loading_mgr` as the scene reads it (scene/mod.rs:153,229-239)."""
 
@@ -168,6 +235,20 @@ class SDFViewer:
         it = C.c_uint64()
         box = _f6(changed) if changed is not None else None
         check(self._lib.sdfgpu_update(self._h, box, int(max_passes), C.byref(it)), self._h)
+        return it.value
+
+    def update_surface(self, sdf, max_delta_time=0.030):
+        """SDFViewer::update(sdf, max_delta_time) with the trait object itself (scene/sdf/mod.rs:128-217;
+        the scene passes 30 ms, scene/mod.rs:168).  A surface whose `tape()` returns bytes is evaluated on
+        the GPU; any other surface is sampled on the host through `sample(points)` in the reference's visit
+        order for at most `max_delta_time` seconds and the results are scattered into the volumes.
+        Returns the LoadingManager iterations done."""
+        surf = _surface_struct(sdf)
+        it = C.c_uint64()
+        check(self._lib.sdfgpu_update_surface(self._h, C.byref(surf), float(max_delta_time), C.byref(it)), self._h)
+        err = getattr(surf, "_py_error", None)
+        if err and err[0] is not None:
+            raise err[0]
         return it.value
 
     def fill_all(self):

@@ -1,0 +1,185 @@
+// host_viewer.cpp -- the C++ host side (include/sdfgpu_viewer.hpp) driven the way the reference's
+// scene drives SDFViewer (/root/reference/src/app/scene/mod.rs:154-215), plus the reference's own
+// LoadingManager tests (src/app/scene/sdf/loading.rs:117-171) against sdfgpu::LoadingManager.
+//
+//   host_viewer loading          CPU: the five loading.rs cases
+//   host_viewer tape             CPU: hex dump of sdfgpu::SDFDemo's tape (compared with tape.py's)
+//   host_viewer gpu <out_dir>    GPU: (1) the demo surface with a tape, (2) a surface WITHOUT a tape whose
+//                                sample() is the oracle's SDFDemo::sample; volumes and a frame are
+//                                written to <out_dir> for the Python test to compare with the oracle
+//
+// TEST CODE: links liboracle.so as the stand-in for a user's CPU SDF.
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "sdfgpu_viewer.hpp"
+
+extern "C" {  // oracle/sdf_oracle.cpp
+struct OrcDemoParams {
+    float cube_half_side; uint32_t cube_material; float sphere_radius; uint32_t sphere_material;
+    float max_distance_custom_material; uint32_t disable_sphere;
+};
+void orc_demo_params_default(OrcDemoParams* p);
+void orc_demo_sample(const OrcDemoParams* p, const float* pts, uint64_t n, int distance_only, float* out);
+}
+
+#define REQUIRE(c)                                                                  \
+    do {                                                                            \
+        if (!(c)) { std::fprintf(stderr, "%s:%d: REQUIRE(%s) failed\n", __FILE__, __LINE__, #c); std::exit(1); } \
+    } while (0)
+
+// loading.rs:122-146 `test_loading_manager`
+static void loading_case(std::array<uint32_t, 3> limits) {
+    const uint32_t num_passes = 3;
+    sdfgpu::LoadingManager lm(limits, num_passes);
+    std::vector<int> hits((size_t)limits[0] * limits[1] * limits[2], 0);
+    uint64_t iterations = 0;
+    const uint64_t total = iterations + lm.len();
+    while (auto v = lm.next()) {
+        const size_t flat = (*v)[0] + (size_t)(*v)[1] * limits[0] + (size_t)(*v)[2] * limits[0] * limits[1];
+        hits[flat] += 1;
+        REQUIRE(hits[flat] <= (int)num_passes);
+        iterations += 1;
+        REQUIRE(total == iterations + lm.len());
+    }
+    for (int h : hits) REQUIRE(h >= 1);
+    REQUIRE(lm.passes_left() == 0 && lm.total_iterations() == iterations);
+}
+
+// a user's SDFSurface without a tape: sample() is CPU code the library knows nothing about
+class HostDemo : public sdfgpu::SDFSurface {
+   public:
+    HostDemo() { orc_demo_params_default(&params); }
+    sdfgpu::BoundingBox bounding_box() const override { return {sdfgpu::Vector3{-1, -1, -1}, sdfgpu::Vector3{1, 1, 1}}; }
+    sdfgpu::SDFSample sample(sdfgpu::Vector3 p, bool distance_only) const override {
+        sdfgpu::SDFSample s;
+        const float xyz[3] = {p.x, p.y, p.z};
+        orc_demo_sample(&params, xyz, 1, distance_only, reinterpret_cast<float*>(&s));
+        return s;
+    }
+    unsigned sample_threads() const override { return threads; }
+    OrcDemoParams params;
+    unsigned threads = 1;
+};
+
+static void write_file(const std::string& path, const void* data, size_t bytes) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    REQUIRE(f != nullptr);
+    REQUIRE(std::fwrite(data, 1, bytes, f) == bytes);
+    std::fclose(f);
+}
+
+// SDFViewerAppScene::set_sdf + the load loop of render() (scene/mod.rs:154-155,168-199)
+static size_t load(sdfgpu::SDFViewer& viewer, const sdfgpu::SDFSurface& sdf, std::chrono::milliseconds per_frame,
+                   size_t* frames) {
+    size_t updates = 0;
+    *frames = 0;
+    for (;;) {
+        const size_t cpu_updates = viewer.update(sdf, per_frame);
+        ++*frames;
+        updates += cpu_updates;
+        if (cpu_updates == 0) break;
+        viewer.commit();
+    }
+    viewer.commit();
+    return updates;
+}
+
+static int run_gpu(const std::string& out) {
+    // (1) a surface with a tape: every pass is one kernel
+    {
+        sdfgpu::SDFDemo sdf;
+        auto viewer = sdfgpu::SDFViewer::from_bb(sdf.bounding_box(), 32, 2);
+        REQUIRE(viewer.width() == 32 && viewer.height() == 32 && viewer.depth() == 32);
+        const uint64_t total = viewer.loading_mgr().len();
+        REQUIRE(total == 32 * 32 * 32 + 16 * 16 * 16);
+        size_t frames = 0;
+        REQUIRE(load(viewer, sdf, std::chrono::milliseconds(30), &frames) == total);
+        REQUIRE(viewer.loading_mgr().len() == 0 && viewer.loading_mgr().passes_left() == 0);
+        REQUIRE(viewer.loading_mgr().passes == 2 && viewer.loading_mgr().total_iterations() == total);
+        std::vector<float> t0, t1;
+        viewer.download(&t0, &t1);
+        write_file(out + "/tape_tex0.bin", t0.data(), t0.size() * 4);
+        write_file(out + "/tape_tex1.bin", t1.data(), t1.size() * 4);
+        const sdfgpu::Frame f = viewer.render(sdfgpu::SDFViewer::default_camera(160, 120), 160, 120);
+        write_file(out + "/tape_rgba8.bin", f.rgba8.data(), f.rgba8.size());
+        write_file(out + "/tape_depth.bin", f.depth.data(), f.depth.size() * 4);
+        // a parameter edit: changed() reports the whole box once, the viewer re-samples in 3 passes
+        sdf.sphere_radius = 0.9f;
+        sdf.mark_changed();
+        REQUIRE(load(viewer, sdf, std::chrono::milliseconds(30), &frames) > 0);
+        viewer.download(&t0, &t1);
+        write_file(out + "/tape_changed_tex0.bin", t0.data(), t0.size() * 4);
+        write_file(out + "/tape_changed_tex1.bin", t1.data(), t1.size() * 4);
+    }
+    // (2) a surface without a tape: sampled on the host in the reference's order, a few ms per frame
+    {
+        HostDemo sdf;
+        sdf.threads = 4;
+        auto viewer = sdfgpu::SDFViewer::new_voxels({24, 20, 16}, sdf.bounding_box(), 3);
+        const uint64_t total = viewer.loading_mgr().len();
+        size_t frames = 0;
+        REQUIRE(load(viewer, sdf, std::chrono::milliseconds(1), &frames) == total);
+        REQUIRE(frames >= 2);
+        std::vector<float> t0, t1;
+        viewer.download(&t0, &t1);
+        write_file(out + "/host_tex0.bin", t0.data(), t0.size() * 4);
+        write_file(out + "/host_tex1.bin", t1.data(), t1.size() * 4);
+        std::printf("host-sampled load: %zu iterations in %zu frames\n", (size_t)total, frames);
+    }
+    // (3) error behaviour: an exception in the user's sample() surfaces from update(), nothing aborts
+    {
+        struct Broken : HostDemo {
+            sdfgpu::SDFSample sample(sdfgpu::Vector3, bool) const override { throw std::runtime_error("guest trapped"); }
+        } sdf;
+        auto viewer = sdfgpu::SDFViewer::new_voxels({4, 4, 4}, sdf.bounding_box(), 1);
+        bool thrown = false;
+        try {
+            viewer.update(sdf, std::chrono::seconds(10));
+        } catch (const std::runtime_error& e) {
+            thrown = std::string(e.what()) == "guest trapped";
+        }
+        REQUIRE(thrown);
+        bool rejected = false;
+        try {
+            sdfgpu::SDFViewer::from_bb(sdf.bounding_box(), 8, 1, 4096);  // no such device
+        } catch (const sdfgpu::Error& e) {
+            rejected = e.code() == SDFGPU_ERR_INVALID;
+        }
+        REQUIRE(rejected);
+    }
+    std::printf("gpu ok\n");
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    const std::string mode = argc > 1 ? argv[1] : "";
+    if (mode == "loading") {
+        loading_case({2, 2, 2});     // loading.rs:147-170
+        loading_case({8, 8, 8});
+        loading_case({64, 64, 64});
+        loading_case({11, 11, 11});
+        loading_case({8, 11, 17});
+        std::printf("loading ok\n");
+        return 0;
+    }
+    if (mode == "tape") {
+        sdfgpu::SDFDemo sdf;
+        if (argc > 2) sdf.disable_sphere = true;
+        const auto t = *sdf.tape();
+        for (unsigned char c : t) std::printf("%02x", c);
+        std::printf("\n");
+        return 0;
+    }
+    if (mode == "gpu" && argc > 2) {
+        try {
+            return run_gpu(argv[2]);
+        } catch (const std::exception& e) {
+            std::fprintf(stderr, "exception: %s\n", e.what());
+            return 2;
+        }
+    }
+    std::fprintf(stderr, "usage: host_viewer loading | tape [nosphere] | gpu <out_dir>\n");
+    return 64;
+}

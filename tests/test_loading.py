@@ -78,3 +78,67 @@ def test_pass_structure(S):
     assert first == want and lm.step_size == 1
     for x in (0, 1, 2, 3, 5, 8, 9, 1023, 1024, 2 ** 31 + 5):
         assert L.prev_power_of_2(x) == (0 if x == 0 else 1 << (x.bit_length() - 1))
+
+
+# ---- the library's own LoadingManager object (sdfgpu_loading_*, device-free): the state every handle keeps
+
+@pytest.mark.parametrize("limits", CASES)
+def test_reference_cases_native(S, limits):
+    lm = S.NativeLoadingManager(limits, 3)
+
+    def nxt():
+        try:
+            return next(lm)
+        except StopIteration:
+            return None
+    n = _check(limits, nxt, lambda: len(lm))
+    assert n == lm.total_iterations() and lm.passes_left() == 0
+
+
+@pytest.mark.parametrize("limits,passes", [((5, 3, 7), 0), ((5, 3, 7), 1), ((9, 4, 6), 2), ((16, 16, 3), 4), ((3, 3, 3), 6),
+                                           ((1, 1, 1), 3), ((33, 7, 5), 3)])
+def test_native_equals_oracle_sequence(S, oracle, limits, passes):
+    a, b = oracle.LM(limits, passes), S.NativeLoadingManager(limits, passes)
+    assert a.len() == len(b) and a.passes_left() == b.passes_left()
+    while True:
+        va = a.next()
+        try:
+            vb = next(b)
+        except StopIteration:
+            vb = None
+        assert va == vb
+        assert a.len() == len(b) and a.passes_left() == b.passes_left()
+        assert a.total_iterations() == b.total_iterations()
+        if va is None:
+            break
+
+
+@pytest.mark.parametrize("limits,passes,chunk", [((5, 3, 7), 2, 1), ((9, 4, 6), 3, 2), ((16, 16, 3), 4, 5), ((33, 7, 5), 3, 1000),
+                                                 ((64, 64, 64), 2, 37)])
+def test_native_runs_concatenate_to_the_reference_order(S, limits, passes, chunk):
+    """next_run -- what the host-sampled update walks in chunks (sdfgpu_update_surface) -- yields the
+    same sequence, len() and counters as one next() at a time."""
+    one, run = S.LoadingManager(limits, passes), S.NativeLoadingManager(limits, passes)
+    while True:
+        r = run.next_run(chunk)
+        if r is None:
+            assert len(one) == 0 and run.passes_left() == 0
+            with pytest.raises(StopIteration):
+                next(one)
+            break
+        (x0, y, z), step, n = r
+        assert 1 <= n <= chunk
+        for i in range(n):
+            assert next(one) == (x0 + i * step, y, z)
+        assert len(one) == len(run) and one.total_iterations() == run.total_iterations()
+        assert one.passes_left() == run.passes_left()
+
+
+def test_native_reset(S):
+    lm = S.NativeLoadingManager((4, 4, 4), 2)
+    for _ in range(5):
+        next(lm)
+    lm.reset(3)
+    ref = S.LoadingManager((4, 4, 4), 3)
+    assert len(lm) == len(ref) and lm.total_iterations() == 0 and lm.passes_left() == 3
+    assert [next(lm) for _ in range(len(ref))] == [next(ref) for _ in range(len(ref))]
