@@ -163,6 +163,30 @@ def cpu_trace_sample(orc, S, tape, dims, W, H, threads, rows=48):
     return W * rows / dt, f"rows [{r0},{r0 + rows}) of the {W}x{H} frame ({W * rows} rays, {dt:.2f} s, {threads} threads)"
 
 
+def host_sampled_path(orc, S, threads, side=256):
+    """SURVEY 8f row 1 measured: a surface WITHOUT a tape (what every existing .wasm SDF is) loaded through
+    sdfgpu_update_surface -- the library walks the LoadingManager, calls the surface's sample_batch on the
+    host cores (here the oracle's SDFDemo::sample standing in for the guest, C to C, no Python in the loop)
+    and scatters the results on the GPU.  CPU-bound by construction; reported beside the CPU's own rate."""
+    import ctypes as C
+    from sdf_viewer_b200 import _lib
+    P = orc.demo_params()
+    surf = _lib.Surface()
+    surf.self = C.cast(C.pointer(P), C.c_void_p)
+    surf.sample_batch = C.cast(orc.lib().orc_demo_sample, _lib.SAMPLE_BATCH_FN)
+    surf.sample_threads = threads
+    with S.SDFViewer.new_voxels((side, side, side), BB, 2) as v:
+        it = C.c_uint64()
+        total = len(v.loading_mgr)
+        t = time.perf_counter()
+        while len(v.loading_mgr):
+            S.viewer.check(v._lib.sdfgpu_update_surface(v._h, C.byref(surf), 0.030, C.byref(it)), v._h)
+        v.sync()
+        dt = time.perf_counter() - t
+    return {"value": side ** 3 / dt, "unit": "samples/s", "threads": threads,
+            "sample": f"{side}^3 grid, 2 passes ({total} iterations), 30 ms per update call as the scene does, {dt:.2f} s"}
+
+
 def workload_name(workload, dims, W, H):
     return (f"{'demo_sdf' if workload == 'demo' else 'csg_1k'} {dims[0]}x{dims[1]}x{dims[2]} "
             f"grid fill + {W}x{H} sphere trace, default scene camera")
@@ -364,6 +388,10 @@ def main():
         out["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
                                "reference_order_1_thread": one_thread, "reference_order_sample": one_thread_sample,
                                "rays_per_sec": rays, "rays_sample": rays_sample + f", {cpu_dims[0]}^3 volume"}
+        try:
+            out["host_sampled_path"] = host_sampled_path(orc, S, threads)
+        except Exception as e:  # an extra, never a reason to lose the bench line
+            out["host_sampled_path"] = {"error": str(e)}
     print(json.dumps(out))
     if dist: dist.destroy_process_group()
 
