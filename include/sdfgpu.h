@@ -316,9 +316,12 @@ uint64_t sdfgpu_launch_count(const sdfgpu_ctx* ctx);
 /* Fill-kernel knobs (0 = library default); used by the benchmarks and tests:
  *   "fill_voxels_per_thread" 0|1|2|4|8   "fill_ctas_per_sm" 0..32
  *   "fill_halo" 0|1 (compute halo slices locally; 0 when the host exchanges them)
- *   "trace_distance_volume" 0|1: keep a distance-only copy of tex0.r (4 B / voxel, rebuilt after every
- *                  change) for the march: same values, a quarter of the bytes per fetch; pays off when
- *                  many frames are traced per fill (the interactive viewer), off by default
+ *   "trace_distance_volume" 0..3: where the LINEAR march reads its distances.  0 (default) tex0.r in place;
+ *                  1 a distance-only copy of tex0.r in linear memory (4 B / voxel, rebuilt after every change):
+ *                  same values, a quarter of the bytes per fetch; 2 the copy as an R32F 3-D CUDA array read
+ *                  through a texture object in point mode (TMU + block-linear layout, exact fp32 blend: same
+ *                  frame); 3 the array with hardware LINEAR filtering (one fetch per step, 8-bit weights:
+ *                  a fast mode OUTSIDE the 1e-5 parity bar).  1-3 pay off when many frames are traced per fill
  *   "trace_variant" 0 heavy-first 8x8 tiles (default) | 1 plain 2-D grid
  *   "fill_program" 0 auto (kernel specialised for the tape structure, else built-in demo program,
  *                  else interpreter) | 1 interpreter | 2 built-in or interpreter | 3 specialised or fail */

@@ -158,10 +158,15 @@ struct sdfgpu_ctx {
     float* gather_dev = nullptr;
     size_t gather_cap = 0;
     int64_t pass_known = 0;        // known_step when the current (partially walked) host pass began
+    double host_rate = 1.0e6;      // LoadingManager iterations per second the host-sampled path last ran at
+    bool host_rate_known = false;
     std::vector<unsigned char> tape_bytes;  // the public tape last given to sdfgpu_set_tape (change detection)
     float* lut_dev = nullptr;
-    float* dist_dev = nullptr;  // optional distance-only volume for the tracer (option trace_distance_volume)
-    bool dist_valid = false;
+    float* dist_dev = nullptr;  // optional distance-only volume for the tracer (option trace_distance_volume = 1)
+    cudaArray_t dist_arr = nullptr;  // the same as an R32F 3-D CUDA array (options 2, 3): written through dist_surf,
+    cudaSurfaceObject_t dist_surf = 0;  // read through dist_tex[0] (point filter) or dist_tex[1] (linear filter)
+    cudaTextureObject_t dist_tex[2] = {0, 0};
+    bool dist_valid = false;    // the distance volume the current option uses mirrors tex0.r
     bool peers_ever = false;  // a neighbour may hold an IPC mapping of this handle's volumes
     int opt_dist_volume = 0;
     unsigned long long* touched_dev = nullptr;
@@ -540,6 +545,10 @@ SDFGPU_API void sdfgpu_destroy(sdfgpu_ctx* ctx) {
     (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
     (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->rgba8_dev); (void)cudaFree(ctx->touched_dev);
     (void)cudaFree(ctx->ingest_dev); (void)cudaFree(ctx->lut_dev); (void)cudaFree(ctx->dist_dev);
+    if (ctx->dist_tex[0]) (void)cudaDestroyTextureObject(ctx->dist_tex[0]);
+    if (ctx->dist_tex[1]) (void)cudaDestroyTextureObject(ctx->dist_tex[1]);
+    if (ctx->dist_surf) (void)cudaDestroySurfaceObject(ctx->dist_surf);
+    if (ctx->dist_arr) (void)cudaFreeArray(ctx->dist_arr);
     for (auto& st : ctx->stage) {
         (void)cudaFreeHost(st.rec); (void)cudaFreeHost(st.idx); (void)cudaFree(st.rec_dev); (void)cudaFree(st.idx_dev);
         if (st.done) (void)cudaEventDestroy(st.done);
@@ -898,31 +907,48 @@ int ensure_stage(sdfgpu_ctx* ctx, sdfgpu_ctx::HostStage& st, size_t voxels) {
     return SDFGPU_OK;
 }
 
-// sdf.sample(pos, false) for n positions (:193), on up to sdf->sample_threads host threads
-void sample_on_host(const sdfgpu_surface* sdf, const float* xyz, size_t n, float* out) {
-    auto run = [&](size_t a, size_t b) {
-        if (sdf->sample_batch) {
-            if (b > a) sdf->sample_batch(sdf->self, xyz + 3 * a, (uint64_t)(b - a), 0, out + 7 * a);
-        } else {
-            for (size_t i = a; i < b; ++i) sdf->sample(sdf->self, xyz + 3 * i, 0, out + 7 * i);
-        }
-    };
-    size_t threads = sdf->sample_threads > 1 ? sdf->sample_threads : 1;
-    if (threads > n / 256 + 1) threads = n / 256 + 1;
-    if (threads <= 1) { run(0, n); return; }
+// records + texel indices of a filled staging buffer -> device -> ingest_scatter_kernel
+int scatter_stage(sdfgpu_ctx* ctx, sdfgpu_ctx::HostStage& st, size_t n) {
+    CK(ctx, cudaMemcpyAsync(st.idx_dev, st.idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(st.rec_dev, st.rec, n * 7 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, launch_ingest_scatter(ctx->tex0, ctx->tex1, st.rec_dev, st.idx_dev, n, ctx->lut_dev, air_dist_value(),
+                                  ctx->sm_count * 8, ctx->stream));
+    CK(ctx, cudaEventRecord(st.done, ctx->stream));
+    st.in_flight = true;
+    ctx->launches++;
+    ctx->dist_valid = false;
+    return SDFGPU_OK;
+}
+
+// run fn(t) for t in [0, threads) on that many host threads (the calling thread takes t = 0)
+template <class F>
+void parallel_for_threads(size_t threads, F&& fn) {
+    if (threads <= 1) { fn((size_t)0); return; }
     std::vector<std::thread> pool;
-    const size_t per = (n + threads - 1) / threads;
-    for (size_t t = 1; t < threads; ++t) {
-        const size_t a = t * per < n ? t * per : n, b = (t + 1) * per < n ? (t + 1) * per : n;
-        pool.emplace_back(run, a, b);
-    }
-    run(0, per < n ? per : n);
+    pool.reserve(threads - 1);
+    for (size_t t = 1; t < threads; ++t) pool.emplace_back([&fn, t] { fn(t); });
+    fn((size_t)0);
     for (auto& th : pool) th.join();
 }
 
+// sdf.sample(pos, false) for n positions (:193)
+void sample_range(const sdfgpu_surface* sdf, const float* xyz, size_t n, float* out) {
+    if (!n) return;
+    if (sdf->sample_batch) {
+        sdf->sample_batch(sdf->self, xyz, (uint64_t)n, 0, out);
+    } else {
+        for (size_t i = 0; i < n; ++i) sdf->sample(sdf->self, xyz + 3 * i, 0, out + 7 * i);
+    }
+}
+
+struct RowRun {  // `take` consecutive LoadingManager iterations inside one x row: x0 + i * step, y, z
+    uint32_t x0, y, z, take;
+};
+
 // The loop of SDFViewer::update (:173-215) for a surface WITHOUT a tape: the LoadingManager is walked
 // on the host in the reference's order, in chunks; per chunk the voxels that need an update are
-// sampled through the callbacks and scattered into the volumes by ingest_scatter_kernel.
+// sampled through the callbacks and scattered into the volumes by ingest_scatter_kernel.  Deciding
+// `update_required`, building positions and sampling all run on the surface's sample_threads.
 int host_sampled_passes(sdfgpu_ctx* ctx, const sdfgpu_surface* sdf, double max_seconds, uint64_t* iterations) {
     LoadingState& lm = ctx->lm;
     const uint64_t start_iter = lm.total_iterations;
@@ -939,13 +965,24 @@ int host_sampled_passes(sdfgpu_ctx* ctx, const sdfgpu_surface* sdf, double max_s
         while (lm.step_size != 0) lm.finish_pass();
         return SDFGPU_OK;
     }
+    const size_t max_threads = sdf->sample_threads > 1 ? sdf->sample_threads : 1;
+    std::vector<RowRun> runs;
+    std::vector<size_t> block_first, block_count;  // per thread: first run / candidates
     std::vector<float> xyz;
     std::vector<uint32_t> cand;
     std::vector<unsigned char> cand_in_box;
     bool first = true, pass_finished = false;
-    uint64_t chunk = max_seconds > 0.0 ? 256 : 1;  // iterations walked before the clock is read again
+    // iterations walked before the clock is read again: what the rate seen so far (kept across calls)
+    // fits into half of the budget, at least one iteration when the budget is zero (:173)
+    auto chunk_for = [&](double seconds_left) -> uint64_t {
+        if (!(seconds_left > 0.0)) return 1;
+        const double want = ctx->host_rate * seconds_left * 0.5;
+        return want < 256.0 ? 256 : want > 4194304.0 ? 4194304 : (uint64_t)want;
+    };
+    uint64_t chunk = chunk_for(max_seconds);
     while (lm.step_size != 0 && (first || elapsed() < max_seconds)) {
         first = false;
+        const double t_chunk = elapsed();
         const uint64_t step = lm.step_size;
         if (lm.iterations == 0) ctx->pass_known = ctx->known_step;
         // while a pass is half done the volume is a mix the other entry points cannot describe
@@ -953,8 +990,8 @@ int host_sampled_passes(sdfgpu_ctx* ctx, const sdfgpu_surface* sdf, double max_s
         ctx->known_step = -1;
         const bool has_box = ctx->has_changed_box;
         const float* box = ctx->changed_box;
-        // ---- walk up to `chunk` iterations of this pass from the cursor (loading.rs:50-76)
-        xyz.clear(); cand.clear(); cand_in_box.clear();
+        // ---- walk up to `chunk` iterations of this pass from the cursor (loading.rs:50-76) as row runs
+        runs.clear();
         uint64_t walked = 0;
         bool pass_end = false;
         while (walked < chunk && !pass_end) {
@@ -963,27 +1000,75 @@ int host_sampled_passes(sdfgpu_ctx* ctx, const sdfgpu_surface* sdf, double max_s
             if (!take) break;
             walked += take;
             if (x0 >= W || y >= H || z >= D) continue;  // cannot happen on a non-empty grid
-            const bool stored = z >= za && z < zb;  // a slab handle skips the other ranks' slices
-            const bool row_in_box = has_box && ctx->py[y] >= box[1] && ctx->py[y] <= box[4] && ctx->pz[z] >= box[2] &&
-                                    ctx->pz[z] <= box[5];
-            // without a read: k == 0 everything is AIR_DIST; k == 1 nothing is (only the box matters);
-            // k = 2^j exactly the multiples of k have been sampled
-            if (stored && (k != 1 || row_in_box)) {
-                for (uint64_t i = 0; i < take; ++i) {
-                    const uint64_t x = x0 + i * step;
-                    const bool in_box = row_in_box && ctx->px[x] >= box[0] && ctx->px[x] <= box[3];
-                    const bool is_air = k == 0 || (k > 1 && ((x | y | z) & (uint64_t)(k - 1)) != 0);
-                    if (k == -1 || in_box || is_air) {
-                        cand.push_back((uint32_t)((z - ctx->z_lo) * slice + y * W + x));
-                        cand_in_box.push_back(in_box ? 1 : 0);
-                        xyz.push_back(ctx->px[x]); xyz.push_back(ctx->py[y]); xyz.push_back(ctx->pz[z]);
-                    }
-                }
-            }
+            if (z < za || z >= zb) continue;            // a slab handle skips the other ranks' slices
+            runs.push_back(RowRun{(uint32_t)x0, (uint32_t)y, (uint32_t)z, (uint32_t)take});
         }
-        // ---- unknown state: read tex0.r of the candidates and keep those that hold AIR_DIST or lie in the box
-        size_t n = cand.size();
-        if (k == -1 && n) {
+        // ---- update_required (:184-190) per visited voxel.  Without a read: k == 0 everything is AIR_DIST;
+        // k == 1 nothing is (only the box matters); k = 2^j exactly the multiples of k have been sampled;
+        // k == -1 unknown: every visited voxel is a candidate and tex0.r is read below.
+        auto for_each_candidate = [&](const RowRun& r, auto&& emit) {
+            const bool row_in_box = has_box && ctx->py[r.y] >= box[1] && ctx->py[r.y] <= box[4] && ctx->pz[r.z] >= box[2] &&
+                                    ctx->pz[r.z] <= box[5];
+            if (k == 1 && !row_in_box) return;
+            for (uint32_t i = 0; i < r.take; ++i) {
+                const uint64_t x = r.x0 + (uint64_t)i * step;
+                const bool in_box = row_in_box && ctx->px[x] >= box[0] && ctx->px[x] <= box[3];
+                const bool is_air = k == 0 || (k > 1 && ((x | r.y | r.z) & (uint64_t)(k - 1)) != 0);
+                if (k == -1 || in_box || is_air) emit(x, in_box);
+            }
+        };
+        // contiguous blocks of runs per thread, balanced by iterations
+        size_t threads = max_threads;
+        if (threads > walked / 4096 + 1) threads = (size_t)(walked / 4096 + 1);
+        block_first.assign(threads + 1, runs.size());
+        {
+            uint64_t in_runs = 0;
+            for (const RowRun& r : runs) in_runs += r.take;
+            uint64_t acc = 0;
+            size_t t = 0;
+            for (size_t i = 0; i < runs.size(); ++i) {
+                while (t < threads && acc >= in_runs * t / threads) block_first[t++] = i;
+                acc += runs[i].take;
+            }
+            block_first[0] = 0;
+        }
+        block_count.assign(threads + 1, 0);
+        parallel_for_threads(threads, [&](size_t t) {
+            size_t n = 0;
+            for (size_t i = block_first[t]; i < block_first[t + 1]; ++i) for_each_candidate(runs[i], [&](uint64_t, bool) { ++n; });
+            block_count[t + 1] = n;
+        });
+        for (size_t t = 0; t < threads; ++t) block_count[t + 1] += block_count[t];  // -> offsets
+        size_t n = block_count[threads];
+        auto fill_block = [&](size_t t, uint32_t* idx_out, float* xyz_out, unsigned char* in_box_out) {
+            size_t o = block_count[t];
+            for (size_t i = block_first[t]; i < block_first[t + 1]; ++i) {
+                const RowRun& r = runs[i];
+                const uint32_t row = (uint32_t)((r.z - ctx->z_lo) * slice + (uint64_t)r.y * W);
+                for_each_candidate(r, [&](uint64_t x, bool in_box) {
+                    idx_out[o] = row + (uint32_t)x;
+                    xyz_out[3 * o] = ctx->px[x]; xyz_out[3 * o + 1] = ctx->py[r.y]; xyz_out[3 * o + 2] = ctx->pz[r.z];
+                    if (in_box_out) in_box_out[o] = in_box ? 1 : 0;
+                    ++o;
+                });
+            }
+        };
+        if (n && k != -1) {
+            // ---- known state: positions, samples and texel indices go straight into the pinned staging buffer
+            sdfgpu_ctx::HostStage& st = ctx->stage[ctx->stage_turn & 1];
+            ++ctx->stage_turn;
+            if ((rc = ensure_stage(ctx, st, n)) != SDFGPU_OK) return rc;
+            xyz.resize(3 * n);
+            parallel_for_threads(threads, [&](size_t t) {
+                fill_block(t, st.idx, xyz.data(), nullptr);
+                const size_t a = block_count[t], b = block_count[t + 1];
+                sample_range(sdf, xyz.data() + 3 * a, b - a, st.rec + 7 * a);
+            });
+            if ((rc = scatter_stage(ctx, st, n)) != SDFGPU_OK) return rc;
+        } else if (n) {
+            // ---- unknown state: read tex0.r of the candidates, keep those that hold AIR_DIST or lie in the box
+            cand.resize(n); xyz.resize(3 * n); cand_in_box.resize(n);
+            parallel_for_threads(threads, [&](size_t t) { fill_block(t, cand.data(), xyz.data(), cand_in_box.data()); });
             if (n > ctx->gather_cap) {
                 CK(ctx, cudaStreamSynchronize(ctx->stream));
                 (void)cudaFreeHost(ctx->gather_host); (void)cudaFree(ctx->gather_dev);
@@ -995,6 +1080,7 @@ int host_sampled_passes(sdfgpu_ctx* ctx, const sdfgpu_surface* sdf, double max_s
                 ctx->gather_cap = cap;
             }
             sdfgpu_ctx::HostStage& st = ctx->stage[ctx->stage_turn & 1];
+            ++ctx->stage_turn;
             if ((rc = ensure_stage(ctx, st, n)) != SDFGPU_OK) return rc;
             memcpy(st.idx, cand.data(), n * sizeof(uint32_t));
             CK(ctx, cudaMemcpyAsync(st.idx_dev, st.idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -1005,27 +1091,21 @@ int host_sampled_passes(sdfgpu_ctx* ctx, const sdfgpu_surface* sdf, double max_s
             size_t m = 0;
             for (size_t i = 0; i < n; ++i)
                 if (ctx->gather_host[i] == air || cand_in_box[i]) {
-                    cand[m] = cand[i];
+                    st.idx[m] = cand[i];
                     xyz[3 * m] = xyz[3 * i]; xyz[3 * m + 1] = xyz[3 * i + 1]; xyz[3 * m + 2] = xyz[3 * i + 2];
                     ++m;
                 }
             n = m;
-        }
-        // ---- sample on the host, scatter on the GPU
-        if (n) {
-            sdfgpu_ctx::HostStage& st = ctx->stage[ctx->stage_turn & 1];
-            ++ctx->stage_turn;
-            if ((rc = ensure_stage(ctx, st, n)) != SDFGPU_OK) return rc;
-            memcpy(st.idx, cand.data(), n * sizeof(uint32_t));
-            sample_on_host(sdf, xyz.data(), n, st.rec);
-            CK(ctx, cudaMemcpyAsync(st.idx_dev, st.idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-            CK(ctx, cudaMemcpyAsync(st.rec_dev, st.rec, n * 7 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-            CK(ctx, launch_ingest_scatter(ctx->tex0, ctx->tex1, st.rec_dev, st.idx_dev, n, ctx->lut_dev, air,
-                                          ctx->sm_count * 8, ctx->stream));
-            CK(ctx, cudaEventRecord(st.done, ctx->stream));
-            st.in_flight = true;
-            ctx->launches++;
-            ctx->dist_valid = false;
+            if (n) {
+                size_t th = max_threads;
+                if (th > n / 4096 + 1) th = n / 4096 + 1;
+                const size_t per = (n + th - 1) / th;
+                parallel_for_threads(th, [&](size_t t) {
+                    const size_t a = t * per < n ? t * per : n, b = (t + 1) * per < n ? (t + 1) * per : n;
+                    sample_range(sdf, xyz.data() + 3 * a, b - a, st.rec + 7 * a);
+                });
+                if ((rc = scatter_stage(ctx, st, n)) != SDFGPU_OK) return rc;
+            }
         }
         if (pass_end) {
             // sampled so far: what was known before this pass plus the lattice of `step`
@@ -1034,15 +1114,15 @@ int host_sampled_passes(sdfgpu_ctx* ctx, const sdfgpu_surface* sdf, double max_s
             else ctx->known_step = k < (int64_t)step ? k : (int64_t)step;
             pass_finished = true;
         }
-        // next chunk: as many iterations as the measured rate fits into what is left of the budget
-        const double el = elapsed();
-        const uint64_t done_now = lm.total_iterations - start_iter;
-        if (el > 0.0 && max_seconds > el) {
-            const double want = (double)done_now / el * (max_seconds - el) * 0.5;
-            chunk = want < 256.0 ? 256 : want > 1048576.0 ? 1048576 : (uint64_t)want;
-        } else {
-            chunk = 256;
+        // the rate this chunk ran at (smoothed, kept for the next call) sizes the next chunk
+        const double el = elapsed(), dt = el - t_chunk;
+        if (dt > 0.0 && walked >= 256) {
+            const double r = (double)walked / dt;
+            ctx->host_rate = ctx->host_rate_known ? 0.5 * ctx->host_rate + 0.5 * r : r;
+            ctx->host_rate_known = true;
         }
+        chunk = chunk_for(max_seconds - el);
+        if (chunk < 256 && max_seconds > 0.0) chunk = 256;
     }
     if (pass_finished && has_peers(ctx)) {
         if ((rc = push_halos(ctx, ctx->stream)) != SDFGPU_OK) return rc;
@@ -1391,16 +1471,48 @@ int fill_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t w, uin
     tp->tone_mapping = cam->tone_mapping; tp->color_mapping = cam->color_mapping;
     tp->gamma = cam->gamma;
     memcpy(tp->ambient, cam->ambient, 12);
-    // optional distance-only volume (4 B per voxel) for the march: built here after any change of tex0;
-    // not with IPC neighbours, whose halo pushes this handle cannot observe
+    // optional distance-only volume (4 B per voxel) for the march, rebuilt here after any change of tex0
+    // (not with IPC neighbours, whose halo pushes this handle cannot observe): 1 = dense linear array,
+    // 2 / 3 = R32F 3-D CUDA array behind a texture object with point / hardware-linear filtering
     if (ctx->opt_dist_volume && ctx->opt_trace_variant == 0 && ctx->stored_texels && !has_peers(ctx) && !ctx->peers_ever) {
-        if (!ctx->dist_dev) CK(ctx, cudaMalloc(&ctx->dist_dev, ctx->stored_texels * sizeof(float)));
-        if (!ctx->dist_valid) {
-            CK(ctx, launch_extract_dist(ctx->tex0, ctx->dist_dev, ctx->stored_texels, ctx->sm_count * 8, ctx->stream));
-            ctx->launches++;
-            ctx->dist_valid = true;
+        if (ctx->opt_dist_volume == 1) {
+            if (!ctx->dist_dev) CK(ctx, cudaMalloc(&ctx->dist_dev, ctx->stored_texels * sizeof(float)));
+            if (!ctx->dist_valid) {
+                CK(ctx, launch_extract_dist(ctx->tex0, ctx->dist_dev, ctx->stored_texels, ctx->sm_count * 8, ctx->stream));
+                ctx->launches++;
+                ctx->dist_valid = true;
+            }
+            tp->dist = ctx->dist_dev;
+        } else {
+            const uint32_t Ds = ctx->z_hi - ctx->z_lo;
+            if (!ctx->dist_arr) {
+                const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<float>();
+                CK(ctx, cudaMalloc3DArray(&ctx->dist_arr, &fmt, make_cudaExtent(ctx->dims[0], ctx->dims[1], Ds),
+                                          cudaArraySurfaceLoadStore));
+                cudaResourceDesc res;
+                memset(&res, 0, sizeof res);
+                res.resType = cudaResourceTypeArray;
+                res.res.array.array = ctx->dist_arr;
+                CK(ctx, cudaCreateSurfaceObject(&ctx->dist_surf, &res));
+                for (int lin = 0; lin < 2; ++lin) {
+                    cudaTextureDesc td;
+                    memset(&td, 0, sizeof td);
+                    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+                    td.filterMode = lin ? cudaFilterModeLinear : cudaFilterModePoint;
+                    td.readMode = cudaReadModeElementType;
+                    td.normalizedCoords = 0;
+                    CK(ctx, cudaCreateTextureObject(&ctx->dist_tex[lin], &res, &td, nullptr));
+                }
+            }
+            if (!ctx->dist_valid) {
+                CK(ctx, launch_extract_dist_array(ctx->tex0, (unsigned long long)ctx->dist_surf, ctx->dims[0], ctx->dims[1], Ds,
+                                                  ctx->sm_count * 8, ctx->stream));
+                ctx->launches++;
+                ctx->dist_valid = true;
+            }
+            tp->dist_tex = (unsigned long long)ctx->dist_tex[ctx->opt_dist_volume == 3 ? 1 : 0];
         }
-        tp->dist = ctx->dist_dev;
+        tp->dist_mode = (uint32_t)ctx->opt_dist_volume;
     }
     tp->width = w; tp->height = h;
     tp->max_steps = (uint32_t)ctx->opt_max_steps;
@@ -1639,7 +1751,9 @@ SDFGPU_API int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value
         if (ctx->opt_fill_halo != (value != 0) && ctx->known_step != 0) ctx->known_step = -1;  // the filled z range changes
         ctx->opt_fill_halo = value != 0;
     } else if (!strcmp(key, "trace_distance_volume")) {
-        ctx->opt_dist_volume = value != 0;
+        if (value < 0 || value > 3) return fail(ctx, SDFGPU_ERR_INVALID, "trace_distance_volume must be 0..3");
+        if (ctx->opt_dist_volume != (int)value) ctx->dist_valid = false;  // each form is rebuilt on its first use
+        ctx->opt_dist_volume = (int)value;
     } else if (!strcmp(key, "trace_max_steps")) {
         if (value < 2 || value > 65536) return fail(ctx, SDFGPU_ERR_INVALID, "trace_max_steps out of range");
         ctx->opt_max_steps = (int)value;

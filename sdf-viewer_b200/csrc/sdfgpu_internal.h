@@ -15,7 +15,9 @@ namespace sdfgpu {
 struct TraceParams {
     const float4* tex0;
     const float4* tex1;
-    const float* dist;  // optional: tex0.r of every stored texel as a dense array (null = march reads tex0)
+    const float* dist;  // dist_mode 1: tex0.r of every stored texel as a dense array
+    unsigned long long dist_tex;  // dist_mode 2 / 3: cudaTextureObject_t over an R32F 3-D array (point / linear filter)
+    uint32_t dist_mode;           // where the LINEAR march reads distances: 0 tex0.r, 1 dense array, 2 TMU point, 3 TMU linear
     float origin[3], base[3], dx[3], dy[3], bvp[16];
     float bmin[3], bmax[3];          // sdfBoundsMin/Max
     float clip_min[3], clip_max[3];  // == bounds on one GPU; the slab's sub-box for sort-last
@@ -70,6 +72,8 @@ cudaError_t launch_gather_dist(const float4* tex0, const uint32_t* idx_dev, size
 cudaError_t launch_set_const(float4* dst, size_t n_texels, float v, int grid_ctas, cudaStream_t s);
 cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s);
 cudaError_t launch_extract_dist(const float4* tex0, float* dist, size_t n, int grid, cudaStream_t s);
+cudaError_t launch_extract_dist_array(const float4* tex0, unsigned long long surf, uint32_t W, uint32_t H,
+                                      uint32_t stored_slices, int grid, cudaStream_t s);
 cudaError_t launch_keys_unpack(const unsigned long long* keys, uint32_t n, uint8_t* rgba8, float* depth,
                                cudaStream_t s);
 

@@ -11,6 +11,13 @@
 // marching only the distance lane (.r, 4 B) of each texel is fetched; the full
 // texel is fetched once at the hit.
 //
+// Where the march reads its distances from (TraceParams::dist_mode, option trace_distance_volume):
+//   0  the .r lane of tex0 in place (default)            1  a dense R32F copy of tex0.r in linear memory
+//   2  an R32F 3-D CUDA array read through a texture object in POINT mode: the TMU and its block-linear
+//      layout serve the 8 taps, the trilinear blend stays exact fp32 -- same values, same frame
+//   3  the same array with hardware LINEAR filtering: one fetch per step, 8-bit weights -- a fast mode
+//      that is NOT within the 1e-5 bar and is reported separately (hard part 2)
+//
 // A warp owns an 8 x 4 pixel tile so neighbouring rays share texels; finished
 // lanes drop out and the warp leaves the loop as soon as its ballot is empty.
 // CTAs are 8 x 8 pixel tiles in a 1-D grid ordered heavy-first (tiles inside the
@@ -60,19 +67,25 @@ struct Taps {  // texel indices fit 32 bits: sdfgpu_create rejects volumes of 2^
     float fx, fy, fz;
 };
 
+// the texel coordinates of the two taps per axis of a LINEAR fetch whose lower corner is (x0, y0, z0);
+// z relative to the first stored slice
+__device__ __forceinline__ void tap_coords(const Vol& v, int x0, int y0, int z0, int& xa, int& xb, int& ya, int& yb,
+                                           int& za, int& zb) {
+    mirror_pair(x0, v.W, xa, xb);
+    mirror_pair(y0, v.H, ya, yb);
+    mirror_pair(z0, v.D, za, zb);
+    za = min(max(za, v.z_lo), v.z_hi - 1) - v.z_lo;
+    zb = min(max(zb, v.z_lo), v.z_hi - 1) - v.z_lo;
+}
+
 // texture(sampler3D, p01) with GL_LINEAR: texel centres at (i + 0.5) / N
 __device__ __forceinline__ Taps linear_taps(const Vol& v, float ax, float ay, float az) {
     const float ux = ax * (float)v.W - 0.5f, uy = ay * (float)v.H - 0.5f, uz = az * (float)v.D - 0.5f;
     const float fx0 = floorf(ux), fy0 = floorf(uy), fz0 = floorf(uz);
     Taps t;
     t.fx = ux - fx0; t.fy = uy - fy0; t.fz = uz - fz0;
-    const int x0 = (int)fx0, y0 = (int)fy0, z0 = (int)fz0;
     int xa, xb, ya, yb, za, zb;
-    mirror_pair(x0, v.W, xa, xb);
-    mirror_pair(y0, v.H, ya, yb);
-    mirror_pair(z0, v.D, za, zb);
-    za = min(max(za, v.z_lo), v.z_hi - 1) - v.z_lo;
-    zb = min(max(zb, v.z_lo), v.z_hi - 1) - v.z_lo;
+    tap_coords(v, (int)fx0, (int)fy0, (int)fz0, xa, xb, ya, yb, za, zb);
     const uint32_t ra = ((uint32_t)za * v.H + ya) * v.W, rb = ((uint32_t)za * v.H + yb) * v.W;
     const uint32_t rc = ((uint32_t)zb * v.H + ya) * v.W, rd = ((uint32_t)zb * v.H + yb) * v.W;
     t.i000 = ra + xa; t.i100 = ra + xb; t.i010 = rb + xa; t.i110 = rb + xb;
@@ -118,16 +131,39 @@ struct CellCache {
     float c000, c100, c010, c110, c001, c101, c011, c111;
 };
 
-template <bool SNAP, bool DIST>
+// point fetch of texel (x, y, z) of the R32F 3-D array: unnormalised coordinates, texel centre
+__device__ __forceinline__ float tex_point(cudaTextureObject_t t, int x, int y, int z) {
+    return tex3D<float>(t, (float)x + 0.5f, (float)y + 0.5f, (float)z + 0.5f);
+}
+
+template <bool SNAP, int DIST>
 __device__ __forceinline__ float sample_dist_cached(const TraceParams& P, const Vol& v, float px, float py, float pz,
                                                     CellCache& cc) {
     float ax, ay, az;
     tex_coord<SNAP>(P, v, px, py, pz, ax, ay, az);
+    if (DIST == 3) {
+        // hardware trilinear: with unnormalised coordinates the unit fetches around x - 0.5, which is GL's
+        // u * N - 0.5; clamp addressing equals MIRRORED_REPEAT for every position inside the box
+        return tex3D<float>((cudaTextureObject_t)P.dist_tex, ax * (float)v.W, ay * (float)v.H,
+                            az * (float)v.D - (float)v.z_lo);
+    }
     const float ux = ax * (float)v.W - 0.5f, uy = ay * (float)v.H - 0.5f, uz = az * (float)v.D - 0.5f;
     const float fx0 = floorf(ux), fy0 = floorf(uy), fz0 = floorf(uz);
     if (fx0 != cc.x0 || fy0 != cc.y0 || fz0 != cc.z0) {
+        if (DIST == 2) {  // the same 8 values through the texture unit (point mode, block-linear array)
+            int xa, xb, ya, yb, za, zb;
+            tap_coords(v, (int)fx0, (int)fy0, (int)fz0, xa, xb, ya, yb, za, zb);
+            const cudaTextureObject_t t = (cudaTextureObject_t)P.dist_tex;
+            cc.c000 = tex_point(t, xa, ya, za); cc.c100 = tex_point(t, xb, ya, za);
+            cc.c010 = tex_point(t, xa, yb, za); cc.c110 = tex_point(t, xb, yb, za);
+            cc.c001 = tex_point(t, xa, ya, zb); cc.c101 = tex_point(t, xb, ya, zb);
+            cc.c011 = tex_point(t, xa, yb, zb); cc.c111 = tex_point(t, xb, yb, zb);
+            cc.x0 = fx0; cc.y0 = fy0; cc.z0 = fz0;
+            return trilerp(cc.c000, cc.c100, cc.c010, cc.c110, cc.c001, cc.c101, cc.c011, cc.c111, ux - fx0, uy - fy0,
+                           uz - fz0);
+        }
         const Taps t = linear_taps(v, ax, ay, az);
-        if (DIST) {  // optional distance-only copy of tex0.r: 4 B per voxel instead of 16, same values
+        if (DIST == 1) {  // optional distance-only copy of tex0.r: 4 B per voxel instead of 16, same values
             cc.c000 = __ldg(P.dist + t.i000); cc.c100 = __ldg(P.dist + t.i100); cc.c010 = __ldg(P.dist + t.i010);
             cc.c110 = __ldg(P.dist + t.i110); cc.c001 = __ldg(P.dist + t.i001); cc.c101 = __ldg(P.dist + t.i101);
             cc.c011 = __ldg(P.dist + t.i011); cc.c111 = __ldg(P.dist + t.i111);
@@ -235,7 +271,7 @@ __device__ __forceinline__ void write_outside(const TraceParams& P, size_t px) {
     if (P.rgba8) P.rgba8[px] = 0u;
 }
 
-template <bool SNAP, bool LINEAR, bool DIST = false>
+template <bool SNAP, bool LINEAR, int DIST = 0>
 __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, uint32_t j) {
     const size_t px = (size_t)j * P.width + i;
 
@@ -356,7 +392,7 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, ui
 // inside the screen rectangle of the projected clip box come first: the long marches start at
 // once and the cheap outside tiles fill in behind them.  Small CTAs release their SM slot as soon
 // as their own rays end instead of waiting for the slowest of 8 warps.
-template <bool SNAP, bool LINEAR, bool DIST = false>
+template <bool SNAP, bool LINEAR, int DIST = 0>
 __global__ void __launch_bounds__(64) trace_tiles_kernel(const __grid_constant__ TraceParams P) {
     const uint32_t rw = P.rect[2] - P.rect[0], rh = P.rect[3] - P.rect[1];
     const uint32_t n_heavy = rw * rh;
@@ -402,6 +438,16 @@ __global__ void __launch_bounds__(256) extract_dist_kernel(const float4* __restr
         dist[i] = __ldg(reinterpret_cast<const float*>(tex0 + i));
 }
 
+// the same into an R32F 3-D CUDA array (block-linear, what the texture unit reads) through a surface
+__global__ void __launch_bounds__(256) extract_dist_surf_kernel(const float4* __restrict__ tex0, cudaSurfaceObject_t surf,
+                                                                uint32_t W, uint32_t H, uint32_t Ds) {
+    const size_t n = (size_t)W * H * Ds;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t x = (uint32_t)(i % W), y = (uint32_t)((i / W) % H), z = (uint32_t)(i / ((size_t)W * H));
+        surf3Dwrite(__ldg(reinterpret_cast<const float*>(tex0 + i)), surf, (int)(x * sizeof(float)), (int)y, (int)z);
+    }
+}
+
 __global__ void keys_unpack_kernel(const unsigned long long* __restrict__ keys, uint32_t n, uint8_t* __restrict__ rgba8,
                                    float* __restrict__ depth) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -418,10 +464,15 @@ cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s) {
     const bool snap = p.lod != 1.0f, lin = p.filter_linear != 0;
     if (variant == 0) {
         const unsigned grid = p.tiles_x * p.tiles_y;
-        if (!snap && lin && p.dist) trace_tiles_kernel<false, true, true><<<grid, 64, 0, s>>>(p);
+        const uint32_t mode = lin ? p.dist_mode : 0u;  // the distance volumes serve the LINEAR march only
+        if (!snap && lin && mode == 1) trace_tiles_kernel<false, true, 1><<<grid, 64, 0, s>>>(p);
+        else if (!snap && lin && mode == 2) trace_tiles_kernel<false, true, 2><<<grid, 64, 0, s>>>(p);
+        else if (!snap && lin && mode == 3) trace_tiles_kernel<false, true, 3><<<grid, 64, 0, s>>>(p);
         else if (!snap && lin) trace_tiles_kernel<false, true><<<grid, 64, 0, s>>>(p);
         else if (!snap && !lin) trace_tiles_kernel<false, false><<<grid, 64, 0, s>>>(p);
-        else if (snap && lin && p.dist) trace_tiles_kernel<true, true, true><<<grid, 64, 0, s>>>(p);
+        else if (snap && lin && mode == 1) trace_tiles_kernel<true, true, 1><<<grid, 64, 0, s>>>(p);
+        else if (snap && lin && mode == 2) trace_tiles_kernel<true, true, 2><<<grid, 64, 0, s>>>(p);
+        else if (snap && lin && mode == 3) trace_tiles_kernel<true, true, 3><<<grid, 64, 0, s>>>(p);
         else if (snap && lin) trace_tiles_kernel<true, true><<<grid, 64, 0, s>>>(p);
         else trace_tiles_kernel<true, false><<<grid, 64, 0, s>>>(p);
     } else {
@@ -437,6 +488,13 @@ cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s) {
 cudaError_t launch_extract_dist(const float4* tex0, float* dist, size_t n, int grid, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     extract_dist_kernel<<<grid, 256, 0, s>>>(tex0, dist, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_extract_dist_array(const float4* tex0, unsigned long long surf, uint32_t W, uint32_t H, uint32_t Ds,
+                                      int grid, cudaStream_t s) {
+    if ((size_t)W * H * Ds == 0) return cudaSuccess;
+    extract_dist_surf_kernel<<<grid, 256, 0, s>>>(tex0, (cudaSurfaceObject_t)surf, W, H, Ds);
     return cudaGetLastError();
 }
 

@@ -105,7 +105,7 @@ def test_trace_variants_identical(S):
                             (200, 300, ((4.0, 0.5, 0.2), (0, 3.0, 0)))):
             c = S.default_camera(w, h) if cam is None else S.look_at_camera(cam[0], cam[1], w, h)
             frames = []
-            for variant, dist_volume in ((0, 0), (1, 0), (0, 1)):
+            for variant, dist_volume in ((0, 0), (1, 0), (0, 1), (0, 2)):  # 2: the TMU, point mode
                 v.set_option("trace_variant", variant)
                 v.set_option("trace_distance_volume", dist_volume)  # distance-only copy of tex0.r for the march
                 frames.append(v.trace(c, w, h, gbuf=True))
@@ -122,6 +122,31 @@ def test_trace_variants_identical(S):
         for a, b in zip(with_copy, without):
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
         v.set_option("trace_variant", 0)
+
+
+def test_hardware_linear_filter_fast_mode(S, oracle):
+    """trace_distance_volume = 3 marches through the texture unit's own trilinear filter (one fetch per
+    step).  Its weights have 8 fractional bits, so it is NOT inside the 1e-5 bar and never the default;
+    this pins how far off it is: the same pixels hit (up to a sliver at silhouettes) and hit depths agree
+    to the filter's quantisation of a voxel."""
+    w, h = 320, 240
+    dims = (64, 64, 64)
+    with fill(S, S.tape.demo_tape(), dims) as v:
+        for cam in (S.default_camera(w, h), S.look_at_camera((0.9, 1.1, 1.8), (0, 0, 0), w, h)):
+            exact = v.trace(cam, w, h, gbuf=True)
+            v.set_option("trace_distance_volume", 3)
+            fast = v.trace(cam, w, h, gbuf=True)
+            v.set_option("trace_distance_volume", 0)
+            hit_e, hit_f = exact[2][..., 3] >= 0, fast[2][..., 3] >= 0
+            assert (hit_e != hit_f).mean() < 1e-2
+            both = hit_e & hit_f
+            assert both.sum() > 1000
+            # hit distance along the ray: a small fraction of a voxel for all but grazing rays
+            voxel = 2.0 / dims[0]
+            dt = np.abs(exact[2][..., 3] - fast[2][..., 3])[both]
+            assert np.quantile(dt, 0.9) < voxel / 4
+            assert not np.array_equal(exact[0], fast[0])   # it really is a different (approximate) path
+            assert np.abs(exact[0] - fast[0])[both].mean() < 0.05
 
 
 def test_rgba8_frame(S):

@@ -11,6 +11,8 @@ BB = ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))
 with S.SDFViewer.from_bb(BB, side, 2) as v:
     v.set_tape(S.tape.demo_tape() if workload == "demo" else S.tape.csg_tape())
     cam = S.default_camera(1920, 1080)
+    if os.environ.get("SDFGPU_TRACE_DIST"):  # distance source of the march: 1 dense array, 2 TMU point, 3 TMU linear
+        v.set_option("trace_distance_volume", int(os.environ["SDFGPU_TRACE_DIST"]))
     for _ in range(reps):
         v.fill_all()
         v.commit()
