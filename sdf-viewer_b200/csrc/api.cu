@@ -888,6 +888,8 @@ int ensure_lut_dev(sdfgpu_ctx* ctx) {
     return SDFGPU_OK;
 }
 
+constexpr size_t kMaxHostChunk = 1u << 20;  // LoadingManager iterations walked per chunk at most
+
 int ensure_stage(sdfgpu_ctx* ctx, sdfgpu_ctx::HostStage& st, size_t voxels) {
     if (!st.done) CK(ctx, cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
     if (st.in_flight) {  // the previous chunk that used this buffer must have been consumed
@@ -895,7 +897,9 @@ int ensure_stage(sdfgpu_ctx* ctx, sdfgpu_ctx::HostStage& st, size_t voxels) {
         st.in_flight = false;
     }
     if (voxels <= st.cap) return SDFGPU_OK;
-    size_t cap = st.cap ? st.cap : 4096;
+    // pinned allocations are slow: size the buffer once for the largest chunk this handle can produce
+    size_t cap = ctx->stored_texels < kMaxHostChunk ? ctx->stored_texels : kMaxHostChunk;
+    if (cap < 4096) cap = 4096;
     while (cap < voxels) cap *= 2;
     (void)cudaFreeHost(st.rec); (void)cudaFreeHost(st.idx); (void)cudaFree(st.rec_dev); (void)cudaFree(st.idx_dev);
     st.rec = nullptr; st.idx = nullptr; st.rec_dev = nullptr; st.idx_dev = nullptr; st.cap = 0;
@@ -973,11 +977,11 @@ int host_sampled_passes(sdfgpu_ctx* ctx, const sdfgpu_surface* sdf, double max_s
     std::vector<unsigned char> cand_in_box;
     bool first = true, pass_finished = false;
     // iterations walked before the clock is read again: what the rate seen so far (kept across calls)
-    // fits into half of the budget, at least one iteration when the budget is zero (:173)
+    // fits into three quarters of what is left of the budget, at least one iteration when it is zero (:173)
     auto chunk_for = [&](double seconds_left) -> uint64_t {
         if (!(seconds_left > 0.0)) return 1;
-        const double want = ctx->host_rate * seconds_left * 0.5;
-        return want < 256.0 ? 256 : want > 4194304.0 ? 4194304 : (uint64_t)want;
+        const double want = ctx->host_rate * seconds_left * 0.75;
+        return want < 256.0 ? 256 : want > (double)kMaxHostChunk ? kMaxHostChunk : (uint64_t)want;
     };
     uint64_t chunk = chunk_for(max_seconds);
     while (lm.step_size != 0 && (first || elapsed() < max_seconds)) {
@@ -1073,7 +1077,8 @@ int host_sampled_passes(sdfgpu_ctx* ctx, const sdfgpu_surface* sdf, double max_s
                 CK(ctx, cudaStreamSynchronize(ctx->stream));
                 (void)cudaFreeHost(ctx->gather_host); (void)cudaFree(ctx->gather_dev);
                 ctx->gather_host = nullptr; ctx->gather_dev = nullptr; ctx->gather_cap = 0;
-                size_t cap = 4096;
+                size_t cap = ctx->stored_texels < kMaxHostChunk ? ctx->stored_texels : kMaxHostChunk;
+                if (cap < 4096) cap = 4096;
                 while (cap < n) cap *= 2;
                 CK(ctx, cudaMallocHost(&ctx->gather_host, cap * sizeof(float)));
                 CK(ctx, cudaMalloc(&ctx->gather_dev, cap * sizeof(float)));
@@ -1210,14 +1215,8 @@ SDFGPU_API int sdfgpu_resample_box(sdfgpu_ctx* ctx, const float box[6], uint64_t
     uint32_t lo[3], hi[3];
     const std::vector<float>* tab[3] = {&ctx->px, &ctx->py, &ctx->pz};
     for (int a = 0; a < 3; ++a) {
-        uint32_t first = 0xffffffffu, last = 0;
-        const std::vector<float>& t = *tab[a];
-        for (uint32_t i = 0; i < t.size(); ++i)
-            if (t[i] >= box[a] && t[i] <= box[3 + a]) {
-                if (first == 0xffffffffu) first = i;
-                last = i;
-            }
-        if (first == 0xffffffffu) return SDFGPU_OK;  // nothing inside
+        uint32_t first, last;
+        if (!index_range_in(*tab[a], box[a], box[3 + a], &first, &last)) return SDFGPU_OK;  // nothing inside
         lo[a] = first; hi[a] = last + 1;
     }
     uint32_t za, zb;
@@ -1275,9 +1274,9 @@ SDFGPU_API int sdfgpu_ingest_samples(sdfgpu_ctx* ctx, uint64_t first_flat, uint6
         return fail(ctx, SDFGPU_ERR_INVALID, "voxel range [%llu,+%llu) is outside the slices this handle stores",
                     (unsigned long long)first_flat, (unsigned long long)count);
     set_device(ctx);
-    if (!ctx->lut_dev) {
-        CK(ctx, cudaMalloc(&ctx->lut_dev, sizeof ctx->lut));
-        CK(ctx, cudaMemcpyAsync(ctx->lut_dev, ctx->lut, sizeof ctx->lut, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        const int rc = ensure_lut_dev(ctx);
+        if (rc != SDFGPU_OK) return rc;
     }
     const size_t bytes = (size_t)count * 7 * sizeof(float);
     if (bytes > ctx->ingest_cap) {
