@@ -205,7 +205,7 @@ def run_reference(args, rank, world):
     tape = T.demo_tape()
     threads = orc.lib().orc_max_threads()
     rates, sample = [], ""
-    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    per_step = max(0.5, min(20.0, 90.0 / max(1, args.steps + args.warmup)))  # the whole run: about a minute and a half
     for i in range(args.warmup + args.steps):
         r, sample = cpu_fill_sample(orc, tape, dims, threads, target_s=per_step)
         if i >= args.warmup:
