@@ -263,7 +263,8 @@ int sdfgpu_camera_rays(const sdfgpu_camera* cam, uint32_t width, uint32_t height
 
 /* G-buffer record per pixel, SDFGPU_GBUF_FLOATS floats:
  *  [0..2] hit position  [3] t (distance from ray origin; -1 out of steps,
- *  -2 out of bounds, -3 ray misses the bounding box => no fragment)
+ *  -2 out of bounds, -3 ray misses the bounding box => no fragment,
+ *  -4 exact multi-GPU trace only: a hit that another rank owns and shades)
  *  [4..7] raw tex0 at hit  [8..11] raw tex1 at hit  [12..14] normal  [15] steps */
 #define SDFGPU_GBUF_FLOATS 16
 
@@ -301,6 +302,25 @@ int sdfgpu_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t widt
  * written so that an element-wise MIN over ranks composites the frame. */
 int sdfgpu_trace_slab_keys(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width,
                            uint32_t height, void** keys_dev);
+
+/* Exact multi-GPU trace.  The sort-last trace above restarts every ray at its slab's faces, which moves
+ * hit points by O(1e-5).  The exact form keeps the single-GPU step sequence: every rank holds a copy of the
+ * distance channel of the WHOLE grid (4 bytes per voxel), marches every ray through it, and the rank
+ * that owns a hit -- the one whose own slices hold the lower z tap of the hit's texture fetch -- shades it
+ * from its slab; the other ranks write the miss key, so the same element-wise MIN composites a frame that
+ * equals sdfgpu_trace_rgba8 of one handle holding the whole grid, bit for bit.
+ *   sdfgpu_exact_trace_prepare : (after every change of this handle's volume) allocates the full-grid
+ *       distance volume on first use and extracts this handle's own slices into their place.  Returns the
+ *       device pointer of the volume (W*H*D floats, flat order of :177) and this handle's own range in
+ *       floats, so the host can all-gather in place (NCCL), or stage through
+ *   sdfgpu_dist_volume_read / _write : host copies of a float range of that volume (hosts without NCCL).
+ *   sdfgpu_trace_exact_keys : the trace; the caller has gathered every rank's range beforehand.
+ * Not in the reference (single process). */
+int sdfgpu_exact_trace_prepare(sdfgpu_ctx* ctx, void** dist_dev, uint64_t* own_first, uint64_t* own_count);
+int sdfgpu_dist_volume_read(sdfgpu_ctx* ctx, uint64_t first, uint64_t count, float* host_dst);
+int sdfgpu_dist_volume_write(sdfgpu_ctx* ctx, uint64_t first, uint64_t count, const float* host_src);
+int sdfgpu_trace_exact_keys(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width,
+                            uint32_t height, void** keys_dev);
 
 /* Pack / unpack helpers for the composited keys (device -> host RGBA8 + depth). */
 int sdfgpu_keys_download(sdfgpu_ctx* ctx, const void* keys_dev, uint32_t width,

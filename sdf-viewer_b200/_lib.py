@@ -120,6 +120,10 @@ SIGNATURES = {
     "sdfgpu_trace_device": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, C.c_int, _vpp, _vpp, _vpp]),
     "sdfgpu_trace_params": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, C.c_int, _fp, _fp, _fp, _u32p]),
     "sdfgpu_trace_slab_keys": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, _vpp]),
+    "sdfgpu_exact_trace_prepare": (C.c_int, [_vp, _vpp, _u64p, _u64p]),
+    "sdfgpu_dist_volume_read": (C.c_int, [_vp, _u64, _u64, _vp]),
+    "sdfgpu_dist_volume_write": (C.c_int, [_vp, _u64, _u64, _vp]),
+    "sdfgpu_trace_exact_keys": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, _vpp]),
     "sdfgpu_keys_download": (C.c_int, [_vp, _vp, _u32, _u32, _vp, _vp]),
     "sdfgpu_sync": (C.c_int, [_vp]),
     "sdfgpu_stream": (_vp, [_vp]),

@@ -167,6 +167,8 @@ struct sdfgpu_ctx {
     cudaSurfaceObject_t dist_surf = 0;  // read through dist_tex[0] (point filter) or dist_tex[1] (linear filter)
     cudaTextureObject_t dist_tex[2] = {0, 0};
     bool dist_valid = false;    // the distance volume the current option uses mirrors tex0.r
+    float* dist_full = nullptr;         // exact multi-GPU trace: tex0.r of the WHOLE grid (W*H*D floats), replicated
+    bool dist_full_own_valid = false;   //   this handle's own slices of it mirror tex0.r
     bool peers_ever = false;  // a neighbour may hold an IPC mapping of this handle's volumes
     int opt_dist_volume = 0;
     unsigned long long* touched_dev = nullptr;
@@ -324,7 +326,7 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
         CK(ctx, launch_fill(p, V, program, (int)grid, smem, ctx->stream));
     }
     ctx->last_program = program; ctx->last_ctas = per_sm; ctx->last_vpt = V;
-    ctx->dist_valid = false;
+    ctx->dist_valid = false; ctx->dist_full_own_valid = false;
     ctx->launches++;
     return SDFGPU_OK;
 }
@@ -361,7 +363,7 @@ int alloc_volumes(sdfgpu_ctx* ctx) {
 }
 
 int reset_volumes(sdfgpu_ctx* ctx) {  // new_voxels, scene/sdf/mod.rs:76-77: AIR_DIST in all 4 channels of both
-    ctx->dist_valid = false;
+    ctx->dist_valid = false; ctx->dist_full_own_valid = false;
     const int grid = ctx->sm_count * 8;
     CK(ctx, launch_set_const(ctx->tex0, ctx->stored_texels, air_dist_value(), grid, ctx->stream));
     CK(ctx, launch_set_const(ctx->tex1, ctx->stored_texels, air_dist_value(), grid, ctx->stream));
@@ -545,6 +547,7 @@ SDFGPU_API void sdfgpu_destroy(sdfgpu_ctx* ctx) {
     (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
     (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->rgba8_dev); (void)cudaFree(ctx->touched_dev);
     (void)cudaFree(ctx->ingest_dev); (void)cudaFree(ctx->lut_dev); (void)cudaFree(ctx->dist_dev);
+    (void)cudaFree(ctx->dist_full);
     if (ctx->dist_tex[0]) (void)cudaDestroyTextureObject(ctx->dist_tex[0]);
     if (ctx->dist_tex[1]) (void)cudaDestroyTextureObject(ctx->dist_tex[1]);
     if (ctx->dist_surf) (void)cudaDestroySurfaceObject(ctx->dist_surf);
@@ -920,7 +923,7 @@ int scatter_stage(sdfgpu_ctx* ctx, sdfgpu_ctx::HostStage& st, size_t n) {
     CK(ctx, cudaEventRecord(st.done, ctx->stream));
     st.in_flight = true;
     ctx->launches++;
-    ctx->dist_valid = false;
+    ctx->dist_valid = false; ctx->dist_full_own_valid = false;
     return SDFGPU_OK;
 }
 
@@ -1290,7 +1293,7 @@ SDFGPU_API int sdfgpu_ingest_samples(sdfgpu_ctx* ctx, uint64_t first_flat, uint6
     CK(ctx, launch_ingest(ctx->tex0, ctx->tex1, ctx->ingest_dev, (size_t)(first_flat - lo), (size_t)count, ctx->lut_dev,
                           air_dist_value(), ctx->sm_count * 8, ctx->stream));
     ctx->launches++;
-    ctx->dist_valid = false;
+    ctx->dist_valid = false; ctx->dist_full_own_valid = false;
     if (ctx->known_step != 1) ctx->known_step = -1;
     // the staging buffer is reused by the next call: wait until the kernel has consumed it
     CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1695,6 +1698,71 @@ SDFGPU_API int sdfgpu_trace_slab_keys(sdfgpu_ctx* ctx, const sdfgpu_camera* cam,
     return SDFGPU_OK;
 }
 
+// ---- exact multi-GPU trace: replicated full-grid distance volume + owner shading (include/sdfgpu.h)
+
+SDFGPU_API int sdfgpu_exact_trace_prepare(sdfgpu_ctx* ctx, void** dist_dev, uint64_t* own_first, uint64_t* own_count) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    set_device(ctx);
+    const size_t slice = (size_t)ctx->dims[0] * ctx->dims[1];
+    const size_t total = slice * ctx->dims[2];
+    if (!ctx->dist_full && total) CK(ctx, cudaMalloc(&ctx->dist_full, total * sizeof(float)));
+    const size_t own = slice * (ctx->z_end - ctx->z_begin);
+    if (own && !ctx->dist_full_own_valid) {
+        CK(ctx, launch_extract_dist(ctx->tex0 + (size_t)(ctx->z_begin - ctx->z_lo) * slice,
+                                    ctx->dist_full + (size_t)ctx->z_begin * slice, own, ctx->sm_count * 8, ctx->stream));
+        ctx->launches++;
+    }
+    ctx->dist_full_own_valid = true;
+    if (dist_dev) *dist_dev = ctx->dist_full;
+    if (own_first) *own_first = (uint64_t)ctx->z_begin * slice;
+    if (own_count) *own_count = own;
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_dist_volume_read(sdfgpu_ctx* ctx, uint64_t first, uint64_t count, float* host_dst) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    const uint64_t total = (uint64_t)ctx->dims[0] * ctx->dims[1] * ctx->dims[2];
+    if (!ctx->dist_full) return fail(ctx, SDFGPU_ERR_STATE, "no distance volume (call sdfgpu_exact_trace_prepare first)");
+    if (first + count > total || first + count < first || (!host_dst && count)) return fail(ctx, SDFGPU_ERR_INVALID, "range out of the grid");
+    set_device(ctx);
+    if (count) CK(ctx, cudaMemcpyAsync(host_dst, ctx->dist_full + first, count * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_dist_volume_write(sdfgpu_ctx* ctx, uint64_t first, uint64_t count, const float* host_src) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    const uint64_t total = (uint64_t)ctx->dims[0] * ctx->dims[1] * ctx->dims[2];
+    if (!ctx->dist_full) return fail(ctx, SDFGPU_ERR_STATE, "no distance volume (call sdfgpu_exact_trace_prepare first)");
+    if (first + count > total || first + count < first || (!host_src && count)) return fail(ctx, SDFGPU_ERR_INVALID, "range out of the grid");
+    set_device(ctx);
+    if (count) CK(ctx, cudaMemcpyAsync(ctx->dist_full + first, host_src, count * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));  // the source is the caller's: it may be reused on return
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_trace_exact_keys(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t width, uint32_t height,
+                                       void** keys_dev) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (!cam || !keys_dev) return fail(ctx, SDFGPU_ERR_INVALID, "NULL argument");
+    if (width == 0 || height == 0) return fail(ctx, SDFGPU_ERR_INVALID, "empty frame");
+    if (!ctx->dist_full || !ctx->dist_full_own_valid)
+        return fail(ctx, SDFGPU_ERR_STATE, "the volume changed since sdfgpu_exact_trace_prepare (prepare, gather, then trace)");
+    set_device(ctx);
+    int rc = ensure_frame(ctx, width, height, false, true);
+    if (rc != SDFGPU_OK) return rc;
+    TraceParams tp;
+    if ((rc = fill_trace_params(ctx, cam, width, height, false, &tp)) != SDFGPU_OK) return rc;
+    tp.dist = ctx->dist_full; tp.dist_mode = 0; tp.dist_tex = 0;
+    tp.full_dist = 1;
+    tp.own_z0 = ctx->z_begin; tp.own_z1 = ctx->z_end;
+    tp.keys = ctx->keys_dev;
+    CK(ctx, launch_trace(tp, 0, ctx->stream));
+    ctx->launches++;
+    *keys_dev = ctx->keys_dev;
+    return SDFGPU_OK;
+}
+
 SDFGPU_API int sdfgpu_keys_download(sdfgpu_ctx* ctx, const void* keys_dev, uint32_t width, uint32_t height,
                                     uint8_t* rgba8, float* depth) {
     if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
@@ -1751,7 +1819,7 @@ SDFGPU_API int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value
         ctx->opt_fill_halo = value != 0;
     } else if (!strcmp(key, "trace_distance_volume")) {
         if (value < 0 || value > 3) return fail(ctx, SDFGPU_ERR_INVALID, "trace_distance_volume must be 0..3");
-        if (ctx->opt_dist_volume != (int)value) ctx->dist_valid = false;  // each form is rebuilt on its first use
+        if (ctx->opt_dist_volume != (int)value) ctx->dist_valid = false; ctx->dist_full_own_valid = false;  // each form is rebuilt on its first use
         ctx->opt_dist_volume = (int)value;
     } else if (!strcmp(key, "trace_max_steps")) {
         if (value < 2 || value > 65536) return fail(ctx, SDFGPU_ERR_INVALID, "trace_max_steps out of range");

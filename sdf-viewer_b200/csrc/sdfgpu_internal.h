@@ -17,6 +17,8 @@ struct TraceParams {
     const float4* tex1;
     const float* dist;  // dist_mode 1: tex0.r of every stored texel as a dense array
     unsigned long long dist_tex;  // dist_mode 2 / 3: cudaTextureObject_t over an R32F 3-D array (point / linear filter)
+    uint32_t full_dist;           // exact multi-GPU trace: `dist` covers the WHOLE grid (replicated on every rank)
+    uint32_t own_z0, own_z1;      //   and this rank shades only the hits whose lower z tap lies in [own_z0, own_z1)
     uint32_t dist_mode;           // where the LINEAR march reads distances: 0 tex0.r, 1 dense array, 2 TMU point, 3 TMU linear
     float origin[3], base[3], dx[3], dy[3], bvp[16];
     float bmin[3], bmax[3];          // sdfBoundsMin/Max

@@ -194,6 +194,41 @@ __device__ __forceinline__ float sample_dist(const TraceParams& P, const Vol& v,
     }
 }
 
+// distance lane from a dense R32F array that covers the Vol `v` (the replicated full-grid distance
+// volume of the exact multi-GPU trace): same addressing, same blend as sample_dist
+template <bool SNAP, bool LINEAR>
+__device__ __forceinline__ float sample_dist_array(const TraceParams& P, const Vol& v, float px, float py, float pz) {
+    float ax, ay, az;
+    tex_coord<SNAP>(P, v, px, py, pz, ax, ay, az);
+    if (LINEAR) {
+        const Taps t = linear_taps(v, ax, ay, az);
+        return trilerp(__ldg(P.dist + t.i000), __ldg(P.dist + t.i100), __ldg(P.dist + t.i010), __ldg(P.dist + t.i110),
+                       __ldg(P.dist + t.i001), __ldg(P.dist + t.i101), __ldg(P.dist + t.i011), __ldg(P.dist + t.i111),
+                       t.fx, t.fy, t.fz);
+    } else {
+        const int x = (int)floorf(ax * (float)v.W), y = (int)floorf(ay * (float)v.H), z = (int)floorf(az * (float)v.D);
+        return __ldg(P.dist + texel_index(v, x, y, z));
+    }
+}
+
+// Exact multi-GPU trace: every rank marches every ray through the replicated distance volume, and the
+// rank that OWNS the hit shades it from its slab.  The owner is the rank whose own slices hold the
+// lower z tap of the hit's fetch (its upper tap is then an own or a halo slice), so exactly one rank
+// shades each hit and it reads the same texels a single GPU would.
+template <bool SNAP, bool LINEAR>
+__device__ __forceinline__ bool owns_hit(const TraceParams& P, const Vol& vfull, float px, float py, float pz) {
+    float ax, ay, az;
+    tex_coord<SNAP>(P, vfull, px, py, pz, ax, ay, az);
+    int z;
+    if (LINEAR) {
+        int zb;
+        mirror_pair((int)floorf(az * (float)vfull.D - 0.5f), vfull.D, z, zb);
+    } else {
+        z = mirror_idx((int)floorf(az * (float)vfull.D), vfull.D);
+    }
+    return (uint32_t)z >= P.own_z0 && (uint32_t)z < P.own_z1;
+}
+
 template <bool SNAP, bool LINEAR>
 __device__ __forceinline__ float4 sample_full(const TraceParams& P, const Vol& v, float px, float py, float pz) {
     float ax, ay, az;
@@ -271,12 +306,13 @@ __device__ __forceinline__ void write_outside(const TraceParams& P, size_t px) {
     if (P.rgba8) P.rgba8[px] = 0u;
 }
 
-template <bool SNAP, bool LINEAR, int DIST = 0>
+template <bool SNAP, bool LINEAR, int DIST = 0, bool FULL = false>
 __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, uint32_t j) {
     const size_t px = (size_t)j * P.width + i;
 
     const Vol v0{P.tex0, (int)P.W, (int)P.H, (int)P.D, (int)P.z_lo, (int)P.z_hi};
     const Vol v1{P.tex1, (int)P.W, (int)P.H, (int)P.D, (int)P.z_lo, (int)P.z_hi};
+    const Vol vfull{nullptr, (int)P.W, (int)P.H, (int)P.D, 0, (int)P.D};  // FULL: P.dist covers the whole grid
 
     float g[SDFGPU_GBUF_FLOATS];
 #pragma unroll
@@ -325,7 +361,9 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, ui
             steps = it;
             if (it >= max_steps - 1) { code = -1.0f; break; }                                          // :99-102
             if (oob_dist(P.clip_min, P.clip_max, hx, hy, hz) > 1e-4f) { code = -2.0f; break; }  // :106-109
-            if (LINEAR) s0x = sample_dist_cached<SNAP, DIST>(P, v0, hx, hy, hz, cell);             // :112
+            if (FULL) s0x = LINEAR ? sample_dist_cached<SNAP, 1>(P, vfull, hx, hy, hz, cell)       // :112
+                                   : sample_dist_array<SNAP, LINEAR>(P, vfull, hx, hy, hz);
+            else if (LINEAR) s0x = sample_dist_cached<SNAP, DIST>(P, v0, hx, hy, hz, cell);
             else s0x = sample_dist<SNAP, LINEAR>(P, v0, hx, hy, hz);
             const float dist = s0x - 1e-1f;                                                  // :59
             if (dist < 1e-5f) { code = t; hit = true; break; }                               // :117-121
@@ -334,6 +372,10 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, ui
         }
     }
 
+    if (FULL && hit && !owns_hit<SNAP, LINEAR>(P, vfull, hx, hy, hz)) {
+        hit = false;    // another rank shades this pixel; here it looks like a miss to the MIN composite
+        code = -4.0f;
+    }
     g[0] = hx; g[1] = hy; g[2] = hz; g[3] = code; g[15] = (float)steps;
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
     float depth = 1.0f;
@@ -349,7 +391,9 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, ui
             float nx = 0.f, ny = 0.f, nz = 0.f;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float dq = sample_dist<SNAP, LINEAR>(P, v0, hx + kx[q] * h, hy + ky[q] * h, hz + kz[q] * h) - 1e-1f;
+                const float pxq = hx + kx[q] * h, pyq = hy + ky[q] * h, pzq = hz + kz[q] * h;
+                const float dq = (FULL ? sample_dist_array<SNAP, LINEAR>(P, vfull, pxq, pyq, pzq)
+                                       : sample_dist<SNAP, LINEAR>(P, v0, pxq, pyq, pzq)) - 1e-1f;
                 nx += kx[q] * dq; ny += ky[q] * dq; nz += kz[q] * dq;
             }
             const float ninv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
@@ -392,7 +436,7 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, ui
 // inside the screen rectangle of the projected clip box come first: the long marches start at
 // once and the cheap outside tiles fill in behind them.  Small CTAs release their SM slot as soon
 // as their own rays end instead of waiting for the slowest of 8 warps.
-template <bool SNAP, bool LINEAR, int DIST = 0>
+template <bool SNAP, bool LINEAR, int DIST = 0, bool FULL = false>
 __global__ void __launch_bounds__(64) trace_tiles_kernel(const __grid_constant__ TraceParams P) {
     const uint32_t rw = P.rect[2] - P.rect[0], rh = P.rect[3] - P.rect[1];
     const uint32_t n_heavy = rw * rh;
@@ -418,7 +462,7 @@ __global__ void __launch_bounds__(64) trace_tiles_kernel(const __grid_constant__
     const uint32_t i = tx * 8u + (threadIdx.x & 7u), j = ty * 8u + (threadIdx.x >> 3);
     if (i >= P.width || j >= P.height) return;
     if (outside) write_outside(P, (size_t)j * P.width + i);
-    else trace_pixel<SNAP, LINEAR, DIST>(P, i, j);
+    else trace_pixel<SNAP, LINEAR, DIST, FULL>(P, i, j);
 }
 
 // Variant 1: plain 2-D grid, 8 warps per CTA, each an 8 x 4 pixel tile; CTA tile = 32 x 8 pixels
@@ -465,7 +509,12 @@ cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s) {
     if (variant == 0) {
         const unsigned grid = p.tiles_x * p.tiles_y;
         const uint32_t mode = lin ? p.dist_mode : 0u;  // the distance volumes serve the LINEAR march only
-        if (!snap && lin && mode == 1) trace_tiles_kernel<false, true, 1><<<grid, 64, 0, s>>>(p);
+        if (p.full_dist) {  // exact multi-GPU trace: replicated full-grid distance volume, hits shaded by their owner
+            if (!snap && lin) trace_tiles_kernel<false, true, 1, true><<<grid, 64, 0, s>>>(p);
+            else if (!snap && !lin) trace_tiles_kernel<false, false, 0, true><<<grid, 64, 0, s>>>(p);
+            else if (snap && lin) trace_tiles_kernel<true, true, 1, true><<<grid, 64, 0, s>>>(p);
+            else trace_tiles_kernel<true, false, 0, true><<<grid, 64, 0, s>>>(p);
+        } else if (!snap && lin && mode == 1) trace_tiles_kernel<false, true, 1><<<grid, 64, 0, s>>>(p);
         else if (!snap && lin && mode == 2) trace_tiles_kernel<false, true, 2><<<grid, 64, 0, s>>>(p);
         else if (!snap && lin && mode == 3) trace_tiles_kernel<false, true, 3><<<grid, 64, 0, s>>>(p);
         else if (!snap && lin) trace_tiles_kernel<false, true><<<grid, 64, 0, s>>>(p);

@@ -75,6 +75,22 @@ def exchange_halos(dist, textures, dims, rank, world, group=None):
     return len(ops)
 
 
+def gather_slabs(dist, full, dims, world, floats_per_voxel=1, group=None):
+    """All-gather of a z-sharded, z-major volume in place: `full` is a flat tensor covering the WHOLE grid
+    (W*H*D*floats_per_voxel) in which every rank has filled its own slices; afterwards every rank holds all
+    of them.  One broadcast per non-empty slab, so slabs may be uneven (D not divisible by the world size).
+    Device agnostic (NCCL on GPU, gloo in the CPU tests).  Returns the number of broadcasts."""
+    W, H, D = dims
+    n = W * H * floats_per_voxel
+    ops = 0
+    for r in range(world):
+        zb, ze = slab_range(D, r, world)
+        if ze > zb:
+            dist.broadcast(full[zb * n:ze * n], src=r, group=group)
+            ops += 1
+    return ops
+
+
 class _DevMem:
     """A __cuda_array_interface__ view of library-owned device memory."""
 
@@ -186,6 +202,33 @@ class ShardedViewer:
         if self.world == 1:
             return self.viewer.trace_device(cam, width, height)
         return self._composite(cam, width, height)
+
+    def gather_distance_volume(self):
+        """Replicate the distance channel of the whole grid on every rank (4 bytes per voxel): each rank
+        extracts its own slices, then one broadcast per slab over NCCL.  Needed again after every fill."""
+        t = self._torch
+        ptr, _first, _count = self.viewer.exact_trace_prepare()
+        W, H, D = self.dims
+        full = t.as_tensor(_DevMem(ptr, W * H * D, "<f4"), device=t.device("cuda", self.device))
+        with t.cuda.stream(self._stream):
+            gather_slabs(self.dist, full, self.dims, self.world)
+
+    def trace_exact_host(self, cam, width, height, gather=True):
+        """The frame a single GPU holding the whole grid would trace, bit for bit (RGBA8 + depth): every
+        rank marches every ray through the replicated distance volume, the owner of each hit shades it,
+        an all-reduce(MIN) composites.  `gather=False` re-uses the distance volume of the previous call
+        (the volume has not changed: camera motion only)."""
+        if self.world == 1:
+            return self.viewer.trace_rgba8(cam, width, height)
+        t = self._torch
+        if gather:
+            self.gather_distance_volume()
+        keys = self.viewer.trace_exact_keys(cam, width, height)
+        kt = t.as_tensor(_DevMem(keys, width * height, "<i8"), device=t.device("cuda", self.device))
+        with t.cuda.stream(self._stream):
+            self.dist.all_reduce(kt, op=self.dist.ReduceOp.MIN)
+        self._synced = True
+        return self.viewer.keys_download(keys, width, height)
 
     def trace_host(self, cam, width, height, rgba_out=None, depth_out=None):
         """Frame to host memory.  One GPU: RGBA32F + depth (the shader's outputs).  Sharded: the

@@ -330,6 +330,27 @@ class SDFViewer:
         check(self._lib.sdfgpu_trace_slab_keys(self._h, C.byref(cam), int(width), int(height), C.byref(k)), self._h)
         return k.value
 
+    # ---- exact multi-GPU trace (replicated distance volume, hits shaded by their owner)
+    def exact_trace_prepare(self):
+        """(device pointer of the full-grid distance volume, first float of this handle's own range, count)."""
+        p, first, count = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        check(self._lib.sdfgpu_exact_trace_prepare(self._h, C.byref(p), C.byref(first), C.byref(count)), self._h)
+        return p.value, first.value, count.value
+
+    def dist_volume_read(self, first, count):
+        out = np.empty(int(count), np.float32)
+        check(self._lib.sdfgpu_dist_volume_read(self._h, int(first), int(count), _host_ptr(out)), self._h)
+        return out
+
+    def dist_volume_write(self, first, values):
+        a = np.ascontiguousarray(values, np.float32).reshape(-1)
+        check(self._lib.sdfgpu_dist_volume_write(self._h, int(first), len(a), _host_ptr(a)), self._h)
+
+    def trace_exact_keys(self, cam, width, height):
+        k = C.c_void_p()
+        check(self._lib.sdfgpu_trace_exact_keys(self._h, C.byref(cam), int(width), int(height), C.byref(k)), self._h)
+        return k.value
+
     def keys_download(self, keys_dev, width, height):
         rgba8 = np.empty((height, width, 4), np.uint8)
         depth = np.empty((height, width), np.float32)

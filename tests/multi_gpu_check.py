@@ -72,6 +72,17 @@ def main():
     np.testing.assert_allclose(depth, want_depth, rtol=1e-5)
     hit = depth < 1
     assert 0.05 < hit.mean() < 0.5 and rgba8[hit][:, 3].min() == 255 and rgba8[~hit].max() == 0
+    # exact trace: replicated distance volume (NCCL broadcasts) + owner shading + MIN composite == the frame
+    # of ONE handle that holds the whole grid, bit for bit, for several cameras; camera-only frames re-use
+    # the gathered volume
+    with S.SDFViewer.new_voxels(dims, BB, 2, device=local) as whole:
+        whole.set_tape(sdf.tape()); whole.update(None); whole.commit()
+        for k, c in enumerate((cam, S.look_at_camera((0.3, 0.2, 1.4), (0.0, 0.1, 0.0), w, h),
+                               S.look_at_camera((0.2, 0.1, 0.3), (1, 0.2, -0.4), w, h))):
+            want8, want_d = whole.trace_rgba8(c, w, h)
+            got8, got_d = sv.trace_exact_host(c, w, h, gather=(k == 0))
+            assert np.array_equal(got8, want8), f"rank {rank}: exact sharded trace differs from the single-volume frame"
+            assert np.array_equal(got_d.view(np.uint32), np.clip(want_d, 0, 1).view(np.uint32))
     dist.barrier()
     if rank == 0:
         print(f"multi_gpu_check ok: world {world}, dims {dims}, {its} iterations, {int(hit.sum())} hit pixels")

@@ -41,7 +41,7 @@ def _worker(rank, world, port, dims, q):
     import torch.distributed as dist
     import orc
     import sdf_viewer_b200 as S
-    from sdf_viewer_b200.sharded import slab_range, stored_range, exchange_halos
+    from sdf_viewer_b200.sharded import slab_range, stored_range, exchange_halos, gather_slabs
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -74,6 +74,13 @@ def _worker(rank, world, port, dims, q):
         dist.all_gather(gathered, torch.from_numpy(keys.view(np.int64).copy()))
         want = np.minimum.reduce([g.numpy().view(np.uint64) for g in gathered])
         ok = ok and np.array_equal(kt.numpy().view(np.uint64), want)
+        # exact trace: the distance channel of the whole grid replicated by one broadcast per non-empty slab
+        dist_full = np.ascontiguousarray(full.tex0[..., 0]).reshape(-1)
+        mine = torch.full((W * H * D,), float("nan"), dtype=torch.float32)
+        mine[zb * W * H:ze * W * H] = torch.from_numpy(dist_full[zb * W * H:ze * W * H])
+        n_bcast = gather_slabs(dist, mine, dims, world)
+        ok = ok and n_bcast == sum(1 for r in range(world) if slab_range(D, r, world)[0] < slab_range(D, r, world)[1])
+        ok = ok and bool(torch.equal(mine.view(torch.int32), torch.from_numpy(dist_full).view(torch.int32)))
         q.put((rank, ok, n_ops))
     finally:
         dist.destroy_process_group()

@@ -221,3 +221,62 @@ def test_slab_keys_composite(S, oracle):
     assert agree.mean() > 0.98
     hit = dg < 1
     assert np.median(np.abs(comp_depth[hit] - dg[hit])) < 1e-4
+
+
+@pytest.mark.parametrize("ranges", [((0, 14), (14, 28)), ((0, 9), (9, 10), (10, 10), (10, 28))])
+@pytest.mark.parametrize("state", ["linear", "nearest", "loading"])
+def test_exact_sharded_trace_equals_single_volume(S, oracle, ranges, state):
+    """The exact multi-GPU trace on one device: slab handles (one per would-be rank) each hold a copy of the
+    whole grid's distance channel -- gathered here through the host-staging calls instead of NCCL -- march every
+    ray through it and shade only the hits they own; the element-wise MIN of their keys is the RGBA8 + depth
+    frame of a single handle that holds the whole grid, bit for bit (same step sequence, same texels).
+    Covers a one-slice slab, an empty slab, the LINEAR / NEAREST filter states and a half-loaded volume
+    (lod 2 snapping)."""
+    dims = (32, 24, 28)
+    w, h = 200, 150
+    tape = S.tape.demo_tape()
+
+    def load(v):
+        v.set_tape(tape)
+        if state == "loading":
+            v.update(None, max_passes=1)    # only the coarse pass: lod = 2, NEAREST filter state
+        else:
+            v.fill_all()
+        if state != "nearest":
+            v.commit()
+
+    cams = [S.default_camera(w, h), S.look_at_camera((0.3, 0.2, 1.4), (0.0, 0.1, 0.0), w, h),
+            S.look_at_camera((0.2, 0.1, 0.3), (1, 0.2, -0.4), w, h)]
+    with S.SDFViewer.new_voxels(dims, BB, 2) as single:
+        load(single)
+        want = [single.trace_rgba8(c, w, h) for c in cams]
+    slabs = [S.SDFViewer.new_voxels(dims, BB, 2, z_range=r) for r in ranges]
+    try:
+        parts = []
+        for v in slabs:
+            load(v)
+            _, first, count = v.exact_trace_prepare()
+            parts.append((first, v.dist_volume_read(first, count)))
+        for v in slabs:                                   # the "all-gather"
+            for first, values in parts:
+                v.dist_volume_write(first, values)
+        for cam, (want8, want_depth) in zip(cams, want):
+            keys = []
+            for v in slabs:
+                rgba8, depth = v.keys_download(v.trace_exact_keys(cam, w, h), w, h)
+                keys.append((depth.view(np.uint32).astype(np.uint64) << np.uint64(32)) | rgba8.view(np.uint32)[..., 0])
+            best = np.minimum.reduce(keys)
+            got8 = (best & np.uint64(0xffffffff)).astype(np.uint32).view(np.uint8).reshape(h, w, 4)
+            got_depth = (best >> np.uint64(32)).astype(np.uint32).view(np.float32)
+            assert np.array_equal(got8, want8)
+            assert np.array_equal(got_depth.view(np.uint32), np.clip(want_depth, 0, 1).view(np.uint32))
+            # every hit is shaded by exactly one slab
+            hits = sum(((k >> np.uint64(32)).astype(np.uint32).view(np.float32) < 1.0).astype(int) for k in keys)
+            assert hits.max() <= 1 and (hits == 1).sum() == (want_depth < 1.0).sum() > 0
+        # the volume changed: the trace refuses to run on a stale distance volume
+        slabs[0].fill_all()
+        with pytest.raises(S.SdfGpuError):
+            slabs[0].trace_exact_keys(cams[0], w, h)
+    finally:
+        for v in slabs:
+            v.close()
