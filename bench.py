@@ -243,6 +243,9 @@ def main():
     ap.add_argument("--vpt", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exact-trace", action="store_true",
+                    help="N > 1: trace with the replicated distance volume + owner shading (bit-exact frame) instead of sort-last; "
+                         "the gather of the distance channel after every fill is inside the step")
     ap.add_argument("--no-fused-halo", action="store_true", help="exchange halos with NCCL send/recv instead of in-kernel peer stores")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -285,7 +288,10 @@ def main():
         sv.fill_all()          # fill own slab (+ NCCL halo exchange when world > 1)
         sv.commit()            # SDFViewer::commit: lod = 1 -> LINEAR filtering (scene/sdf/mod.rs:226-238)
         if ev: ev[1].record(stream)
-        sv.trace_device(cam, W, H)  # frame stays in HBM (+ MIN-composite over ranks when world > 1)
+        if args.exact_trace and world > 1:
+            sv.trace_exact_device(cam, W, H)
+        else:
+            sv.trace_device(cam, W, H)  # frame stays in HBM (+ MIN-composite over ranks when world > 1)
         if ev: ev[2].record(stream)
 
     def sync_all():
@@ -360,7 +366,9 @@ def main():
                    "sharding": (f"z-slabs x{n_gpus}, halo exchange: " + ("fused: boundary slices pushed by DMA over NVLink (CUDA IPC) while the interior fills"
                                 if sv.fused else "NCCL send/recv after the fill")) if n_gpus > 1 else "single GPU",
                    "l2": "volume (32 B/voxel) exceeds the 126 MB L2, no flush needed" if own_voxels * 32 > 2.5e8 else "volume fits L2",
-                   "step": "fill_all + commit + trace (lod 1, LINEAR filter, fp32 trilinear)"},
+                   "step": "fill_all + commit + trace (lod 1, LINEAR filter, fp32 trilinear)" +
+                           (", exact sharded trace (distance channel gathered after the fill, owner shading)"
+                            if args.exact_trace and n_gpus > 1 else "")},
         "fill_ms": fill_ms, "trace_ms": trace_ms, "fill_samples_per_sec": total_voxels / (fill_ms * 1e-3),
         "rays_per_sec": W * H / (trace_ms * 1e-3), "hit_fraction": hit_frac,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -245,6 +245,24 @@ void sdfgpu_camera_default(sdfgpu_camera* cam, uint32_t width, uint32_t height);
 void sdfgpu_look_at_rh(const float eye[3], const float center[3], const float up[3], float m[16]);
 void sdfgpu_perspective(float fovy_rad, float aspect, float z_near, float z_far, float m[16]);
 
+/* CUDA <-> OpenGL interop presenter: the frame goes from the trace kernel into the presenter's GL textures
+ * on the device, with no copy through the host (the reference renders straight into the egui/three-d
+ * framebuffer, src/app/frameinput.rs:12-67, src/app/scene/mod.rs:202-224).
+ *   sdfgpu_gl_register : color_texture = a GL_RGBA8 texture of width x height; depth_texture = a GL_R32F
+ *       texture of the same size that receives gl_FragDepth, or 0; gl_target = GL_TEXTURE_2D (0x0DE1).
+ *       The GL context that owns them must be current on the calling thread and live on this handle's
+ *       device.  Replaces an earlier registration.
+ *   sdfgpu_trace_gl    : material.frag main() for every pixel, written into the registered textures (row 0 =
+ *       bottom row, GL's origin); stream-ordered, GL may sample them when the call returns.  The host
+ *       then draws one full-screen quad that copies colour and writes gl_FragDepth under the blend /
+ *       depth state of src/app/scene/sdf/material.rs:75-81.
+ * Without a current GL context registration fails with SDFGPU_ERR_CUDA and the host keeps
+ * sdfgpu_trace_rgba8. */
+int sdfgpu_gl_register(sdfgpu_ctx* ctx, uint32_t color_texture, uint32_t depth_texture, uint32_t gl_target,
+                       uint32_t width, uint32_t height);
+int sdfgpu_gl_unregister(sdfgpu_ctx* ctx);
+int sdfgpu_trace_gl(sdfgpu_ctx* ctx, const sdfgpu_camera* cam);
+
 /* Lower-level ray description derived from the camera (kept public so the
  * parity tests can hand identical numbers to the oracle):
  *   unnormalised direction of pixel (i,j), j = 0 at the BOTTOM row (GL window

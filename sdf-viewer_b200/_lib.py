@@ -120,6 +120,9 @@ SIGNATURES = {
     "sdfgpu_trace_device": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, C.c_int, _vpp, _vpp, _vpp]),
     "sdfgpu_trace_params": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, C.c_int, _fp, _fp, _fp, _u32p]),
     "sdfgpu_trace_slab_keys": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, _vpp]),
+    "sdfgpu_gl_register": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32]),
+    "sdfgpu_gl_unregister": (C.c_int, [_vp]),
+    "sdfgpu_trace_gl": (C.c_int, [_vp, C.POINTER(Camera)]),
     "sdfgpu_exact_trace_prepare": (C.c_int, [_vp, _vpp, _u64p, _u64p]),
     "sdfgpu_dist_volume_read": (C.c_int, [_vp, _u64, _u64, _vp]),
     "sdfgpu_dist_volume_write": (C.c_int, [_vp, _u64, _u64, _vp]),

@@ -21,6 +21,11 @@
 
 using namespace sdfgpu;
 
+// CUDA <-> OpenGL interop lives in cudart; its header wants <GL/gl.h>, which this image does not have
+// (GLuint and GLenum are unsigned int)
+extern "C" cudaError_t cudaGraphicsGLRegisterImage(cudaGraphicsResource** resource, unsigned int image, unsigned int target,
+                                                   unsigned int flags);
+
 #define SDFGPU_API extern "C" __attribute__((visibility("default")))
 
 namespace {
@@ -167,6 +172,9 @@ struct sdfgpu_ctx {
     cudaSurfaceObject_t dist_surf = 0;  // read through dist_tex[0] (point filter) or dist_tex[1] (linear filter)
     cudaTextureObject_t dist_tex[2] = {0, 0};
     bool dist_valid = false;    // the distance volume the current option uses mirrors tex0.r
+    // GL textures of the presenter registered for interop (sdfgpu_gl_register): RGBA8 colour, optional R32F depth
+    cudaGraphicsResource* gl_res[2] = {nullptr, nullptr};
+    uint32_t gl_w = 0, gl_h = 0;
     float* dist_full = nullptr;         // exact multi-GPU trace: tex0.r of the WHOLE grid (W*H*D floats), replicated
     bool dist_full_own_valid = false;   //   this handle's own slices of it mirror tex0.r
     bool peers_ever = false;  // a neighbour may hold an IPC mapping of this handle's volumes
@@ -548,6 +556,7 @@ SDFGPU_API void sdfgpu_destroy(sdfgpu_ctx* ctx) {
     (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->rgba8_dev); (void)cudaFree(ctx->touched_dev);
     (void)cudaFree(ctx->ingest_dev); (void)cudaFree(ctx->lut_dev); (void)cudaFree(ctx->dist_dev);
     (void)cudaFree(ctx->dist_full);
+    (void)sdfgpu_gl_unregister(ctx);
     if (ctx->dist_tex[0]) (void)cudaDestroyTextureObject(ctx->dist_tex[0]);
     if (ctx->dist_tex[1]) (void)cudaDestroyTextureObject(ctx->dist_tex[1]);
     if (ctx->dist_surf) (void)cudaDestroySurfaceObject(ctx->dist_surf);
@@ -1695,6 +1704,80 @@ SDFGPU_API int sdfgpu_trace_slab_keys(sdfgpu_ctx* ctx, const sdfgpu_camera* cam,
     CK(ctx, launch_trace(tp, ctx->stored_texels ? ctx->opt_trace_variant : 0, ctx->stream));
     ctx->launches++;
     *keys_dev = ctx->keys_dev;
+    return SDFGPU_OK;
+}
+
+// ---- CUDA <-> GL interop presenter
+
+SDFGPU_API int sdfgpu_gl_unregister(sdfgpu_ctx* ctx) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    set_device(ctx);
+    for (auto& r : ctx->gl_res)
+        if (r) {
+            if (ctx->stream) (void)cudaStreamSynchronize(ctx->stream);
+            (void)cudaGraphicsUnregisterResource(r);
+            r = nullptr;
+        }
+    (void)cudaGetLastError();
+    ctx->gl_w = ctx->gl_h = 0;
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_gl_register(sdfgpu_ctx* ctx, uint32_t color_texture, uint32_t depth_texture, uint32_t gl_target,
+                                  uint32_t width, uint32_t height) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (width == 0 || height == 0) return fail(ctx, SDFGPU_ERR_INVALID, "empty frame");
+    if (color_texture == 0) return fail(ctx, SDFGPU_ERR_INVALID, "color_texture is 0");
+    (void)sdfgpu_gl_unregister(ctx);
+    set_device(ctx);
+    const uint32_t tex[2] = {color_texture, depth_texture};
+    for (int i = 0; i < 2; ++i) {
+        if (!tex[i]) continue;
+        const cudaError_t e = cudaGraphicsGLRegisterImage(&ctx->gl_res[i], tex[i], gl_target, cudaGraphicsRegisterFlagsWriteDiscard);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            ctx->gl_res[i] = nullptr;
+            (void)sdfgpu_gl_unregister(ctx);
+            return fail(ctx, SDFGPU_ERR_CUDA,
+                        "cudaGraphicsGLRegisterImage(texture %u) failed: %s (is the GL context that owns it current on this thread, "
+                        "on this device?)", tex[i], cudaGetErrorString(e));
+        }
+    }
+    ctx->gl_w = width; ctx->gl_h = height;
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_trace_gl(sdfgpu_ctx* ctx, const sdfgpu_camera* cam) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (!cam) return fail(ctx, SDFGPU_ERR_INVALID, "cam is NULL");
+    if (!ctx->gl_res[0]) return fail(ctx, SDFGPU_ERR_STATE, "no GL texture registered (call sdfgpu_gl_register first)");
+    set_device(ctx);
+    const uint32_t w = ctx->gl_w, h = ctx->gl_h;
+    int rc = ensure_frame(ctx, w, h, false, false);
+    if (rc != SDFGPU_OK) return rc;
+    if (!ctx->rgba8_dev) CK(ctx, cudaMalloc(&ctx->rgba8_dev, (size_t)w * h * sizeof(uint32_t)));
+    TraceParams tp;
+    if ((rc = fill_trace_params(ctx, cam, w, h, false, &tp)) != SDFGPU_OK) return rc;
+    tp.rgba8 = ctx->rgba8_dev; tp.depth = ctx->depth_dev;
+    CK(ctx, launch_trace(tp, ctx->stored_texels ? ctx->opt_trace_variant : 0, ctx->stream));
+    ctx->launches++;
+    // map, copy the frame into the textures' arrays on the device (row 0 = bottom row = GL's origin), unmap:
+    // the frame never visits the host
+    const int n = ctx->gl_res[1] ? 2 : 1;
+    CK(ctx, cudaGraphicsMapResources(n, ctx->gl_res, ctx->stream));
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < n && e == cudaSuccess; ++i) {
+        cudaArray_t arr = nullptr;
+        e = cudaGraphicsSubResourceGetMappedArray(&arr, ctx->gl_res[i], 0, 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DToArrayAsync(arr, 0, 0, i == 0 ? (const void*)ctx->rgba8_dev : (const void*)ctx->depth_dev, (size_t)w * 4,
+                                         (size_t)w * 4, h, cudaMemcpyDeviceToDevice, ctx->stream);
+    }
+    const cudaError_t eu = cudaGraphicsUnmapResources(n, ctx->gl_res, ctx->stream);  // GL may use the textures after this
+    if (e != cudaSuccess || eu != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(ctx, SDFGPU_ERR_CUDA, "copy into the GL textures failed: %s", cudaGetErrorString(e != cudaSuccess ? e : eu));
+    }
     return SDFGPU_OK;
 }
 

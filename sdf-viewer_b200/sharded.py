@@ -213,13 +213,10 @@ class ShardedViewer:
         with t.cuda.stream(self._stream):
             gather_slabs(self.dist, full, self.dims, self.world)
 
-    def trace_exact_host(self, cam, width, height, gather=True):
-        """The frame a single GPU holding the whole grid would trace, bit for bit (RGBA8 + depth): every
-        rank marches every ray through the replicated distance volume, the owner of each hit shades it,
-        an all-reduce(MIN) composites.  `gather=False` re-uses the distance volume of the previous call
-        (the volume has not changed: camera motion only)."""
+    def trace_exact_device(self, cam, width, height, gather=True):
+        """trace_exact_host without the download: returns the device pointer of the composited keys."""
         if self.world == 1:
-            return self.viewer.trace_rgba8(cam, width, height)
+            return self.viewer.trace_device(cam, width, height)
         t = self._torch
         if gather:
             self.gather_distance_volume()
@@ -228,6 +225,16 @@ class ShardedViewer:
         with t.cuda.stream(self._stream):
             self.dist.all_reduce(kt, op=self.dist.ReduceOp.MIN)
         self._synced = True
+        return keys
+
+    def trace_exact_host(self, cam, width, height, gather=True):
+        """The frame a single GPU holding the whole grid would trace, bit for bit (RGBA8 + depth): every
+        rank marches every ray through the replicated distance volume, the owner of each hit shades it,
+        an all-reduce(MIN) composites.  `gather=False` re-uses the distance volume of the previous call
+        (the volume has not changed: camera motion only)."""
+        if self.world == 1:
+            return self.viewer.trace_rgba8(cam, width, height)
+        keys = self.trace_exact_device(cam, width, height, gather)
         return self.viewer.keys_download(keys, width, height)
 
     def trace_host(self, cam, width, height, rgba_out=None, depth_out=None):

@@ -280,3 +280,24 @@ def test_exact_sharded_trace_equals_single_volume(S, oracle, ranges, state):
     finally:
         for v in slabs:
             v.close()
+
+
+def test_gl_presenter_needs_a_gl_context(S):
+    """sdfgpu_gl_register / sdfgpu_trace_gl (CUDA <-> GL interop presenter): on a box without a current GL
+    context registration fails loudly with SDFGPU_ERR_CUDA, trace_gl without a registration is a state
+    error, and the handle keeps working through the host-buffer path."""
+    from sdf_viewer_b200 import _lib
+    w, h = 64, 48
+    with fill(S, S.tape.demo_tape(), (24, 24, 24)) as v:
+        cam = S.default_camera(w, h)
+        lib = v._lib
+        assert lib.sdfgpu_trace_gl(v._h, cam) == _lib.SDFGPU_ERR_STATE
+        assert b"sdfgpu_gl_register" in lib.sdfgpu_last_error(v._h)
+        assert lib.sdfgpu_gl_register(v._h, 0, 0, 0x0DE1, w, h) == _lib.SDFGPU_ERR_INVALID
+        rc = lib.sdfgpu_gl_register(v._h, 1, 0, 0x0DE1, w, h)      # texture 1 of a GL context that does not exist
+        assert rc == _lib.SDFGPU_ERR_CUDA, rc
+        assert b"GL context" in lib.sdfgpu_last_error(v._h)
+        assert lib.sdfgpu_trace_gl(v._h, cam) == _lib.SDFGPU_ERR_STATE
+        assert lib.sdfgpu_gl_unregister(v._h) == 0
+        r8, d = v.trace_rgba8(cam, w, h)
+        assert (d < 1).any() and r8[d < 1][:, 3].min() == 255
