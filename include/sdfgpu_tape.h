@@ -21,7 +21,8 @@
  * fused (the reference is Rust/WASM f32, which never contracts).
  *
  * Layout (little endian):
- *   sdft_header | sdft_instr[n_instr] | sdft_prim[n_prims] | float consts[n_consts]
+ *   sdft_header | sdft_instr[n_instr] | sdft_prim[n_prims] | float consts[n_consts] | sdft_sop[n_sops]
+ * (the last section is optional: n_sops = header.reserved[0], 0 in tapes without scalar programs)
  */
 #ifndef SDFGPU_TAPE_H
 #define SDFGPU_TAPE_H
@@ -38,6 +39,7 @@ extern "C" {
 #define SDFT_MAX_INSTR 4096u
 #define SDFT_MAX_PRIMS 4096u
 #define SDFT_MAX_CONSTS 4096u
+#define SDFT_MAX_SOPS 8192u
 
 typedef struct sdft_header {
     uint32_t magic;    /* SDFT_MAGIC */
@@ -45,7 +47,7 @@ typedef struct sdft_header {
     uint32_t n_instr;
     uint32_t n_prims;
     uint32_t n_consts;
-    uint32_t reserved[3];
+    uint32_t reserved[3]; /* [0] = n_sops (scalar-program section, below); [1], [2] = 0 */
 } sdft_header; /* 32 bytes */
 
 /* One instruction: 16 bytes so the interpreter fetches it with one 128-bit load. */
@@ -76,6 +78,43 @@ typedef struct sdft_prim {
     float air_skip;
     uint32_t kind; /* shape | (material << 8) */
 } sdft_prim;
+
+/*
+ * Scalar programs: arbitrary straight-line arithmetic for SDFs that are not made of the primitives above
+ * (what a `sample` function compiled to WASM lowers to, sdfgpu_wasm_lower).  One op: 16 bytes.  A program is
+ * the run sops[a .. a+b) named by an SDFT_OP_SCALAR instruction; value i of the program is the result of its
+ * i-th op, an untyped 32-bit word (f32 or i32, as the consuming op reads it); operands name EARLIER values
+ * of the same program by their index relative to the program's first op.  Semantics are WebAssembly's
+ * (f32 ops IEEE-754 with one rounding each; min / max propagate NaN and order -0 < +0; nearest rounds half
+ * to even; float -> int conversions saturate, NaN -> 0; shifts use the count modulo 32).
+ */
+typedef struct sdft_sop {
+    uint32_t op; /* sdft_sop_op */
+    uint32_t a, b, c;
+} sdft_sop;
+
+enum sdft_sop_op {
+    SDFT_S_PX = 0, SDFT_S_PY = 1, SDFT_S_PZ = 2, /* the position register P                        */
+    SDFT_S_CONST = 3,      /* bits of consts[a] (ABSOLUTE constant index): runtime data, a parameter edit keeps the kernel */
+    SDFT_S_IMM = 4,        /* the word a itself: part of the program's structure              */
+    /* f32 -> f32 */
+    SDFT_S_FNEG = 8, SDFT_S_FABS = 9, SDFT_S_FSQRT = 10, SDFT_S_FFLOOR = 11, SDFT_S_FCEIL = 12, SDFT_S_FTRUNC = 13,
+    SDFT_S_FNEAREST = 14,
+    SDFT_S_FADD = 16, SDFT_S_FSUB = 17, SDFT_S_FMUL = 18, SDFT_S_FDIV = 19, SDFT_S_FMIN = 20, SDFT_S_FMAX = 21,
+    SDFT_S_FCOPYSIGN = 22,
+    /* f32 x f32 -> 0 / 1 */
+    SDFT_S_FEQ = 24, SDFT_S_FNE = 25, SDFT_S_FLT = 26, SDFT_S_FGT = 27, SDFT_S_FLE = 28, SDFT_S_FGE = 29,
+    /* i32 */
+    SDFT_S_IADD = 32, SDFT_S_ISUB = 33, SDFT_S_IMUL = 34, SDFT_S_IAND = 35, SDFT_S_IOR = 36, SDFT_S_IXOR = 37,
+    SDFT_S_ISHL = 38, SDFT_S_ISHR_U = 39, SDFT_S_ISHR_S = 40,
+    SDFT_S_IEQ = 44, SDFT_S_INE = 45, SDFT_S_ILT_S = 46, SDFT_S_ILT_U = 47, SDFT_S_IGT_S = 48, SDFT_S_IGT_U = 49,
+    SDFT_S_ILE_S = 50, SDFT_S_ILE_U = 51, SDFT_S_IGE_S = 52, SDFT_S_IGE_U = 53, SDFT_S_IEQZ = 54,
+    /* mixed */
+    SDFT_S_SELECT = 56,    /* v[a] != 0 ? v[b] : v[c]                                        */
+    SDFT_S_F_FROM_I_S = 57, SDFT_S_F_FROM_I_U = 58, /* f32.convert_i32_s / _u              */
+    SDFT_S_I_FROM_F_S = 59, SDFT_S_I_FROM_F_U = 60, /* i32.trunc_sat_f32_s / _u            */
+    SDFT_S_OUT = 63        /* A[b] = v[a] as f32; b = 0..6: distance, r, g, b, metallic, roughness, occlusion */
+};
 
 enum sdft_shape {
     SDFT_SHAPE_SPHERE = 0,   /* sqrt(dx^2+dy^2+dz^2) - size   (sphere.rs:39) */
@@ -115,7 +154,11 @@ enum sdft_op {
     SDFT_OP_P_RESET = 32,     /* P = voxel position                               */
     SDFT_OP_P_SUB = 33,       /* P = P - consts[a..a+2]                           */
     SDFT_OP_P_MUL = 34,       /* P = P * imm                                      */
-    SDFT_OP_P_ABS = 35        /* P.i = |P.i| for each axis bit set in a           */
+    SDFT_OP_P_ABS = 35,       /* P.i = |P.i| for each axis bit set in a           */
+    /* ---- scalar program ---- */
+    SDFT_OP_SCALAR = 40       /* run sops[a .. a+b): reads P, its SDFT_S_OUT ops write A (channels it does not write keep
+                                 their value).  Evaluated by the kernel specialised for the tape (NVRTC); a box without
+                                 NVRTC rejects such a tape instead of falling back */
 };
 
 /*

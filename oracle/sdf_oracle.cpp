@@ -190,6 +190,7 @@ struct Tape {
     const sdft_instr* instr;
     const sdft_prim* prims;
     const float* consts;
+    const sdft_sop* sops;  // optional scalar-program section, hdr->reserved[0] ops
 };
 
 bool tape_parse(const void* bytes, size_t len, Tape* t) {
@@ -198,12 +199,105 @@ bool tape_parse(const void* bytes, size_t len, Tape* t) {
     if (h->magic != SDFT_MAGIC || h->version != SDFT_VERSION) return false;
     size_t need = sizeof(sdft_header) + (size_t)h->n_instr * sizeof(sdft_instr) +
                   (size_t)h->n_prims * sizeof(sdft_prim) + (size_t)h->n_consts * 4;
+    need += (size_t)h->reserved[0] * sizeof(sdft_sop);
     if (need > len) return false;
     t->hdr = h;
     t->instr = (const sdft_instr*)((const char*)bytes + sizeof(sdft_header));
     t->prims = (const sdft_prim*)(t->instr + h->n_instr);
     t->consts = (const float*)(t->prims + h->n_prims);
+    t->sops = (const sdft_sop*)(t->consts + h->n_consts);
     return true;
+}
+
+// ---- scalar programs (include/sdfgpu_tape.h): WebAssembly's numeric semantics on untyped 32-bit words
+inline float w2f(uint32_t w) { float f; memcpy(&f, &w, 4); return f; }
+inline uint32_t f2w(float f) { uint32_t w; memcpy(&w, &f, 4); return w; }
+inline float wasm_fmin(float a, float b) {
+    if (a != a || b != b) return w2f(0x7fc00000u);
+    if (a == b) return w2f(f2w(a) | f2w(b));  // -0 < +0
+    return a < b ? a : b;
+}
+inline float wasm_fmax(float a, float b) {
+    if (a != a || b != b) return w2f(0x7fc00000u);
+    if (a == b) return w2f(f2w(a) & f2w(b));
+    return a > b ? a : b;
+}
+inline int32_t wasm_trunc_sat_s(float f) {
+    if (f != f) return 0;
+    if (f <= -2147483648.0f) return INT32_MIN;
+    if (f >= 2147483648.0f) return INT32_MAX;
+    return (int32_t)f;
+}
+inline uint32_t wasm_trunc_sat_u(float f) {
+    if (f != f || f <= 0.0f) return 0u;
+    if (f >= 4294967296.0f) return 0xffffffffu;
+    return (uint32_t)f;
+}
+
+void run_scalar_program(const Tape& t, uint32_t first, uint32_t count, V3 p, Sample& A) {
+    std::vector<uint32_t> v(count);
+    float* out[7] = {&A.d, &A.r, &A.g, &A.b, &A.metallic, &A.roughness, &A.occlusion};
+    for (uint32_t i = 0; i < count; ++i) {
+        const sdft_sop& o = t.sops[first + i];
+        const uint32_t a = o.a < i ? v[o.a] : 0u, b = o.b < i ? v[o.b] : 0u, c = o.c < i ? v[o.c] : 0u;
+        const float fa = w2f(a), fb = w2f(b);
+        uint32_t r = 0;
+        switch (o.op) {
+            case SDFT_S_PX: r = f2w(p.x); break;
+            case SDFT_S_PY: r = f2w(p.y); break;
+            case SDFT_S_PZ: r = f2w(p.z); break;
+            case SDFT_S_CONST: r = f2w(t.consts[o.a]); break;
+            case SDFT_S_IMM: r = o.a; break;
+            case SDFT_S_FNEG: r = a ^ 0x80000000u; break;
+            case SDFT_S_FABS: r = a & 0x7fffffffu; break;
+            case SDFT_S_FSQRT: r = f2w(sqrtf(fa)); break;
+            case SDFT_S_FFLOOR: r = f2w(floorf(fa)); break;
+            case SDFT_S_FCEIL: r = f2w(ceilf(fa)); break;
+            case SDFT_S_FTRUNC: r = f2w(truncf(fa)); break;
+            case SDFT_S_FNEAREST: r = f2w(nearbyintf(fa)); break;  // default rounding mode: half to even
+            case SDFT_S_FADD: r = f2w(fa + fb); break;
+            case SDFT_S_FSUB: r = f2w(fa - fb); break;
+            case SDFT_S_FMUL: r = f2w(fa * fb); break;
+            case SDFT_S_FDIV: r = f2w(fa / fb); break;
+            case SDFT_S_FMIN: r = f2w(wasm_fmin(fa, fb)); break;
+            case SDFT_S_FMAX: r = f2w(wasm_fmax(fa, fb)); break;
+            case SDFT_S_FCOPYSIGN: r = (a & 0x7fffffffu) | (b & 0x80000000u); break;
+            case SDFT_S_FEQ: r = fa == fb; break;
+            case SDFT_S_FNE: r = fa != fb; break;
+            case SDFT_S_FLT: r = fa < fb; break;
+            case SDFT_S_FGT: r = fa > fb; break;
+            case SDFT_S_FLE: r = fa <= fb; break;
+            case SDFT_S_FGE: r = fa >= fb; break;
+            case SDFT_S_IADD: r = a + b; break;
+            case SDFT_S_ISUB: r = a - b; break;
+            case SDFT_S_IMUL: r = a * b; break;
+            case SDFT_S_IAND: r = a & b; break;
+            case SDFT_S_IOR: r = a | b; break;
+            case SDFT_S_IXOR: r = a ^ b; break;
+            case SDFT_S_ISHL: r = a << (b & 31u); break;
+            case SDFT_S_ISHR_U: r = a >> (b & 31u); break;
+            case SDFT_S_ISHR_S: r = (uint32_t)((int32_t)a >> (b & 31u)); break;
+            case SDFT_S_IEQ: r = a == b; break;
+            case SDFT_S_INE: r = a != b; break;
+            case SDFT_S_ILT_S: r = (int32_t)a < (int32_t)b; break;
+            case SDFT_S_ILT_U: r = a < b; break;
+            case SDFT_S_IGT_S: r = (int32_t)a > (int32_t)b; break;
+            case SDFT_S_IGT_U: r = a > b; break;
+            case SDFT_S_ILE_S: r = (int32_t)a <= (int32_t)b; break;
+            case SDFT_S_ILE_U: r = a <= b; break;
+            case SDFT_S_IGE_S: r = (int32_t)a >= (int32_t)b; break;
+            case SDFT_S_IGE_U: r = a >= b; break;
+            case SDFT_S_IEQZ: r = a == 0u; break;
+            case SDFT_S_SELECT: r = a != 0u ? b : c; break;
+            case SDFT_S_F_FROM_I_S: r = f2w((float)(int32_t)a); break;
+            case SDFT_S_F_FROM_I_U: r = f2w((float)a); break;
+            case SDFT_S_I_FROM_F_S: r = (uint32_t)wasm_trunc_sat_s(fa); break;
+            case SDFT_S_I_FROM_F_U: r = wasm_trunc_sat_u(fa); break;
+            case SDFT_S_OUT: if (o.b < 7) *out[o.b] = fa; break;
+            default: break;
+        }
+        v[i] = r;
+    }
 }
 
 inline float prim_distance(const sdft_prim& pr, V3 q) {
@@ -274,6 +368,9 @@ Sample tape_sample(const Tape& t, V3 p0) {
                 if (I.a & 1u) p.x = fabsf(p.x);
                 if (I.a & 2u) p.y = fabsf(p.y);
                 if (I.a & 4u) p.z = fabsf(p.z);
+                break;
+            case SDFT_OP_SCALAR:
+                if ((uint64_t)I.a + I.b <= t.hdr->reserved[0]) run_scalar_program(t, I.a, I.b, p, A);
                 break;
             default: break;
         }

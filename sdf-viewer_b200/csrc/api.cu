@@ -136,7 +136,9 @@ struct sdfgpu_ctx {
     unsigned char* img_dev = nullptr;
     size_t img_dev_cap = 0;
     TapeImageHeader hdr;
-    std::vector<uint32_t> opcodes;  // lowered opcode sequence = the tape's structure (JIT cache key)
+    std::vector<uint32_t> opcodes;  // lowered opcode sequence (+ scalar programs' text) = the tape's structure (JIT cache key)
+    uint32_t n_top_ops = 0;         // opcodes up to and including DOP_END
+    bool has_scalar = false;        // the tape runs scalar programs: only the specialised (NVRTC) kernel evaluates them
     bool structure_is_demo = false; // matches the built-in PROG_DEMO kernel
     std::vector<float> px, py, pz;  // host copies of the position tables
     float lut[256];
@@ -258,7 +260,8 @@ void set_device(sdfgpu_ctx* ctx) { (void)cudaSetDevice(ctx->device); }
 int default_vpt(const sdfgpu_ctx* ctx) {
     if (ctx->opt_vpt) return ctx->opt_vpt;
     if (ctx->opt_program == 1) return 4;
-    if (ctx->opt_program != 2 && ctx->opcodes.size() <= 96 && jit_available(nullptr)) return 8;
+    if (ctx->has_scalar) return 4;  // long straight-line programs: fewer voxels per thread keep the registers in check
+    if (ctx->opt_program != 2 && ctx->n_top_ops <= 96 && jit_available(nullptr)) return 8;
     return ctx->structure_is_demo ? 8 : 4;
 }
 
@@ -306,7 +309,7 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
     int per_sm = 0, program = dev::PROG_INTERPRET;
     if (ctx->opt_program == 0 || ctx->opt_program == 3) {
         std::string why;
-        if (ctx->opcodes.size() > 96) why = "tape longer than 96 instructions";
+        if (ctx->n_top_ops > 96) why = "tape longer than 96 instructions";
         else if (jit_get(ctx->device, ctx->cc_major, ctx->cc_minor, ctx->opcodes, V, smem, &jit_fn, &per_sm, &why))
             program = dev::PROG_JIT;
         if (program != dev::PROG_JIT) {
@@ -314,6 +317,9 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
             if (ctx->opt_program == 3) return fail(ctx, SDFGPU_ERR_CUDA, "JIT kernel unavailable: %s", why.c_str());
         }
     }
+    if (program != dev::PROG_JIT && ctx->has_scalar)
+        return fail(ctx, SDFGPU_ERR_CUDA, "the tape runs scalar programs, which only the specialised kernel evaluates: %s",
+                    ctx->opt_program == 1 || ctx->opt_program == 2 ? "fill_program forces the interpreter" : ctx->jit_note.c_str());
     if (program != dev::PROG_JIT) {
         if ((ctx->opt_program == 0 || ctx->opt_program == 2) && ctx->structure_is_demo) program = dev::PROG_DEMO;
         const size_t prepared_key = smem;
@@ -602,7 +608,12 @@ struct ParsedTape {
     std::vector<sdft_instr> low;  // lowered instructions (DeviceOp), operands kept
     std::vector<sdft_prim> prims;
     std::vector<float> consts;
-    std::vector<uint32_t> opcodes;  // the structure: lowered opcodes up to and including DOP_END
+    std::vector<sdft_sop> sops;     // scalar-program section
+    // the structure: lowered opcodes up to and including DOP_END; when the tape has scalar programs their
+    // text follows: n_programs, {pc, first, count} per program, n_sops, {op, a, b, c} per op
+    std::vector<uint32_t> opcodes;
+    uint32_t n_top_ops = 0;         // opcodes up to and including DOP_END
+    bool has_scalar = false;
     uint32_t max_stack = 0;
     bool cull = false;
     uint32_t cull_first = 0, cull_count = 0;
@@ -620,8 +631,11 @@ int parse_and_lower(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes, Parsed
     if (h.n_instr > SDFT_MAX_INSTR || h.n_prims > SDFT_MAX_PRIMS || h.n_consts > SDFT_MAX_CONSTS)
         return fail(ctx, SDFGPU_ERR_TAPE, "tape exceeds limits (%u instr, %u prims, %u consts)", h.n_instr, h.n_prims,
                     h.n_consts);
+    const uint32_t n_sops = h.reserved[0];
+    if (n_sops > SDFT_MAX_SOPS) return fail(ctx, SDFGPU_ERR_TAPE, "tape exceeds limits (%u scalar ops)", n_sops);
+    if (h.reserved[1] || h.reserved[2]) return fail(ctx, SDFGPU_ERR_TAPE, "reserved header words must be 0");
     const size_t need = sizeof(sdft_header) + (size_t)h.n_instr * sizeof(sdft_instr) +
-                        (size_t)h.n_prims * sizeof(sdft_prim) + (size_t)h.n_consts * 4;
+                        (size_t)h.n_prims * sizeof(sdft_prim) + (size_t)h.n_consts * 4 + (size_t)n_sops * sizeof(sdft_sop);
     if (need > tape_bytes) return fail(ctx, SDFGPU_ERR_TAPE, "tape truncated: %zu bytes needed, %zu given", need, tape_bytes);
     std::vector<sdft_instr> instr(h.n_instr);
     out->prims.resize(h.n_prims);
@@ -633,6 +647,10 @@ int parse_and_lower(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes, Parsed
     if (h.n_prims) memcpy(out->prims.data(), b, prims.size() * sizeof(sdft_prim));
     b += prims.size() * sizeof(sdft_prim);
     if (h.n_consts) memcpy(out->consts.data(), b, out->consts.size() * 4);
+    b += out->consts.size() * 4;
+    out->sops.resize(n_sops);
+    if (n_sops) memcpy(out->sops.data(), b, (size_t)n_sops * sizeof(sdft_sop));
+    std::vector<uint32_t> programs;  // {pc, first, count} per SDFT_OP_SCALAR
 
     for (uint32_t k = 0; k < h.n_prims; ++k) {
         const uint32_t shape = prims[k].kind & 0xffu, mat = (prims[k].kind >> 8) & 0xffu;
@@ -697,11 +715,56 @@ int parse_and_lower(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes, Parsed
                 break;
             case SDFT_OP_P_MUL: I.op = DOP_P_MUL; p_clean = false; break;
             case SDFT_OP_P_ABS: I.op = DOP_P_ABS; p_clean = false; break;
+            case SDFT_OP_SCALAR: {
+                if (S.b < 1 || (uint64_t)S.a + S.b > n_sops)
+                    return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: scalar program [%u,+%u) out of range", pc, S.a, S.b);
+                for (uint32_t i = 0; i < S.b; ++i) {  // operands name earlier values of the same program
+                    const sdft_sop& o = out->sops[S.a + i];
+                    int n_in;
+                    switch (o.op) {
+                        case SDFT_S_PX: case SDFT_S_PY: case SDFT_S_PZ: case SDFT_S_IMM: n_in = 0; break;
+                        case SDFT_S_CONST:
+                            if (o.a >= h.n_consts) return fail(ctx, SDFGPU_ERR_TAPE, "scalar op %u: constant %u out of range", S.a + i, o.a);
+                            n_in = 0;
+                            break;
+                        case SDFT_S_FNEG: case SDFT_S_FABS: case SDFT_S_FSQRT: case SDFT_S_FFLOOR: case SDFT_S_FCEIL:
+                        case SDFT_S_FTRUNC: case SDFT_S_FNEAREST: case SDFT_S_IEQZ: case SDFT_S_F_FROM_I_S:
+                        case SDFT_S_F_FROM_I_U: case SDFT_S_I_FROM_F_S: case SDFT_S_I_FROM_F_U: n_in = 1; break;
+                        case SDFT_S_OUT:
+                            if (o.b > 6) return fail(ctx, SDFGPU_ERR_TAPE, "scalar op %u: output channel %u out of range", S.a + i, o.b);
+                            n_in = 1;
+                            break;
+                        case SDFT_S_SELECT: n_in = 3; break;
+                        default:
+                            if ((o.op >= SDFT_S_FADD && o.op <= SDFT_S_FCOPYSIGN) || (o.op >= SDFT_S_FEQ && o.op <= SDFT_S_FGE) ||
+                                (o.op >= SDFT_S_IADD && o.op <= SDFT_S_ISHR_S) || (o.op >= SDFT_S_IEQ && o.op <= SDFT_S_IGE_U)) {
+                                n_in = 2;
+                                break;
+                            }
+                            return fail(ctx, SDFGPU_ERR_TAPE, "scalar op %u: unknown op %u", S.a + i, o.op);
+                    }
+                    if ((n_in >= 1 && o.a >= i) || (n_in >= 2 && o.b >= i) || (n_in >= 3 && o.c >= i))
+                        return fail(ctx, SDFGPU_ERR_TAPE, "scalar op %u: operand does not name an earlier value", S.a + i);
+                }
+                I.op = DOP_SCALAR;
+                programs.push_back(pc); programs.push_back(S.a); programs.push_back(S.b);
+                break;
+            }
             default: return fail(ctx, SDFGPU_ERR_TAPE, "instr %u: unknown op %u", pc, S.op);
         }
         out->opcodes.push_back(I.op);
     }
     if (!ended) out->opcodes.push_back(DOP_END);
+    out->n_top_ops = (uint32_t)out->opcodes.size();
+    out->has_scalar = !programs.empty();
+    if (out->has_scalar) {  // the programs' text is part of the structure the kernel is specialised for
+        out->opcodes.push_back((uint32_t)programs.size() / 3);
+        out->opcodes.insert(out->opcodes.end(), programs.begin(), programs.end());
+        out->opcodes.push_back(n_sops);
+        for (const sdft_sop& o : out->sops) {
+            out->opcodes.push_back(o.op); out->opcodes.push_back(o.a); out->opcodes.push_back(o.b); out->opcodes.push_back(o.c);
+        }
+    }
     out->max_stack = max_depth;
     out->cull = n_ranges == 1 && cull_ok && out->cull_count >= 16;
     return SDFGPU_OK;
@@ -771,6 +834,8 @@ SDFGPU_API int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_by
     ctx->img_host.swap(img);
     ctx->hdr = ih;
     ctx->opcodes.swap(pt.opcodes);
+    ctx->n_top_ops = pt.n_top_ops;
+    ctx->has_scalar = pt.has_scalar;
     const uint32_t demo_ops[] = {DOP_PRIM + 0 * 6 + SDFT_SHAPE_BOX_LINF * 3 + SDFT_MAT_BRICK, DOP_PUSH_REG,
                                  DOP_PRIM + 0 * 6 + SDFT_SHAPE_SPHERE * 3 + SDFT_MAT_NORMAL, DOP_POP_DEMO_DIFF, DOP_END};
     ctx->structure_is_demo = ctx->opcodes.size() == 5 && !memcmp(ctx->opcodes.data(), demo_ops, sizeof demo_ops);

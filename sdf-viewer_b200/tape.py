@@ -22,7 +22,19 @@ OP_PUSH, OP_POP_UNION, OP_POP_INTER, OP_POP_DEMO_DIFF = 8, 9, 10, 11
 OP_D_NEG, OP_D_ABS, OP_D_ADD, OP_D_MUL, OP_D_MAX, OP_D_MIN = 16, 17, 18, 19, 20, 21
 OP_M_SET = 24
 OP_P_RESET, OP_P_SUB, OP_P_MUL, OP_P_ABS = 32, 33, 34, 35
+OP_SCALAR = 40
 
+# scalar-program ops (enum sdft_sop_op)
+S = {name: code for name, code in dict(
+    PX=0, PY=1, PZ=2, CONST=3, IMM=4,
+    FNEG=8, FABS=9, FSQRT=10, FFLOOR=11, FCEIL=12, FTRUNC=13, FNEAREST=14,
+    FADD=16, FSUB=17, FMUL=18, FDIV=19, FMIN=20, FMAX=21, FCOPYSIGN=22,
+    FEQ=24, FNE=25, FLT=26, FGT=27, FLE=28, FGE=29,
+    IADD=32, ISUB=33, IMUL=34, IAND=35, IOR=36, IXOR=37, ISHL=38, ISHR_U=39, ISHR_S=40,
+    IEQ=44, INE=45, ILT_S=46, ILT_U=47, IGT_S=48, IGT_U=49, ILE_S=50, ILE_U=51, IGE_S=52, IGE_U=53, IEQZ=54,
+    SELECT=56, F_FROM_I_S=57, F_FROM_I_U=58, I_FROM_F_S=59, I_FROM_F_U=60, OUT=63).items()}
+
+SOP_DTYPE = np.dtype([("op", "<u4"), ("a", "<u4"), ("b", "<u4"), ("c", "<u4")])
 INSTR_DTYPE = np.dtype([("op", "<u4"), ("a", "<u4"), ("b", "<u4"), ("imm", "<f4")])
 PRIM_DTYPE = np.dtype(
     [("center", "<f4", 3), ("size", "<f4"), ("color", "<f4", 3), ("metallic", "<f4"), ("roughness", "<f4"),
@@ -38,6 +50,7 @@ class TapeBuilder:
         self.instr = []
         self.prims = []
         self.consts = []
+        self.sops = []
 
     # -- tables
     def prim(self, shape, center, size, material=MAT_FLAT, color=(0.0, 0.0, 0.0), metallic=0.0, roughness=0.0,
@@ -64,12 +77,56 @@ class TapeBuilder:
         self.instr.append((op, a, b, imm))
         return self
 
+    def scalar(self, program):
+        """Append a `ScalarProgram` to the scalar section and emit the SDFT_OP_SCALAR that runs it."""
+        first = len(self.sops)
+        for op, a, b, c in program.ops:
+            if op == S["CONST"]:
+                a = self.const([program.const_values[a]])
+            self.sops.append((op, a, b, c))
+        return self.emit(OP_SCALAR, first, len(program.ops))
+
     def build(self):
         ins = np.array(self.instr, dtype=INSTR_DTYPE) if self.instr else np.zeros(0, INSTR_DTYPE)
         prims = np.array(self.prims, dtype=PRIM_DTYPE) if self.prims else np.zeros(0, PRIM_DTYPE)
         consts = np.array(self.consts, dtype="<f4")
-        hdr = struct.pack("<8I", SDFT_MAGIC, SDFT_VERSION, len(ins), len(prims), len(consts), 0, 0, 0)
-        return hdr + ins.tobytes() + prims.tobytes() + consts.tobytes()
+        sops = np.array(self.sops, dtype=SOP_DTYPE) if self.sops else np.zeros(0, SOP_DTYPE)
+        hdr = struct.pack("<8I", SDFT_MAGIC, SDFT_VERSION, len(ins), len(prims), len(consts), len(sops), 0, 0)
+        return hdr + ins.tobytes() + prims.tobytes() + consts.tobytes() + sops.tobytes()
+
+
+class ScalarProgram:
+    """A straight-line SSA program over untyped 32-bit words (include/sdfgpu_tape.h, `sdft_sop`): each method
+    appends one op and returns the index of its value.  `TapeBuilder.scalar(prog)` places it in a tape."""
+
+    def __init__(self):
+        self.ops = []
+        self.const_values = []
+
+    def op(self, name, a=0, b=0, c=0):
+        self.ops.append((S[name], int(a), int(b), int(c)))
+        return len(self.ops) - 1
+
+    def px(self):
+        return self.op("PX")
+
+    def py(self):
+        return self.op("PY")
+
+    def pz(self):
+        return self.op("PZ")
+
+    def const(self, value):
+        """An f32 constant: runtime data of the tape (a new value keeps the compiled kernel)."""
+        self.const_values.append(float(value))
+        return self.op("CONST", len(self.const_values) - 1)
+
+    def imm(self, word):
+        return self.op("IMM", int(word) & 0xFFFFFFFF)
+
+    def out(self, channel, value):
+        """A[channel] = value; channel 0..6 = distance, r, g, b, metallic, roughness, occlusion."""
+        return self.op("OUT", value, channel)
 
 
 def demo_tape(cube_half_side=0.95, cube_material=MAT_BRICK, sphere_radius=1.05, sphere_material=MAT_NORMAL,

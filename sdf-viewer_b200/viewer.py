@@ -396,7 +396,7 @@ def jit_check(tape_bytes, voxels_per_thread=2):
     """Compile the specialised fill kernel for this tape's structure with NVRTC (no GPU needed).
     Returns the generated translation unit; raises SdfGpuError with the compiler log on failure."""
     buf = (C.c_char * len(tape_bytes)).from_buffer_copy(tape_bytes)
-    log = C.create_string_buffer(1 << 16)
+    log = C.create_string_buffer(1 << 22)  # the generated translation unit: long for scalar programs
     rc = _lib.load().sdfgpu_jit_check(buf, len(tape_bytes), int(voxels_per_thread), log, len(log))
     if rc != 0:
         raise SdfGpuError(rc, log.value.decode("utf-8", "replace") or _lib.load().sdfgpu_last_error(None).decode())
