@@ -103,6 +103,24 @@ int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes);
  * log.  Returns SDFGPU_ERR_CUDA when NVRTC is not installed. */
 int sdfgpu_jit_check(const void* tape, size_t tape_bytes, int voxels_per_thread, char* log, size_t log_cap);
 
+/* Lowers the `sample` export of a WebAssembly SDF module -- the guest ABI of src/sdf/wasm/mod.rs:5-37 that
+ * src/sdf/wasm/native.rs loads -- to a tape, so that an existing .wasm SDF runs on the GPU instead of being
+ * called once per voxel.  Device free.  The module is instantiated (start function, optional `init()`,
+ * native.rs:52-56), `bounding_box(sdf_id)` is executed and its six floats returned in bb_out, and
+ * `sample(sdf_id, x, y, z, 0)` is executed once with SYMBOLIC coordinates: integer work, addresses, allocator
+ * and registry look-ups run concretely and vanish, every f32 / i32 operation on a value that depends on the
+ * position becomes one op of a scalar program (sdfgpu_tape.h), and branches on such values are merged into
+ * selects.  The result is the tape {SDFT_OP_SCALAR, SDFT_OP_END}; its constants are runtime data, so lowering
+ * the module again after a parameter change re-uses the compiled kernel.
+ *   tape_out / tape_cap : receives the tape; *tape_len = bytes needed (call with tape_out = NULL to size it)
+ *   log                 : on success a one-line summary, on failure why this module cannot be lowered
+ * Returns SDFGPU_OK; SDFGPU_ERR_INVALID for a malformed module or one without the required exports
+ * (native.rs:59-63); SDFGPU_ERR_TAPE when the guest does something that has no tape form (an address, loop
+ * bound or call target that depends on the position; 64-bit arithmetic on such values; a host import; SIMD) --
+ * such an SDF is sampled on the host through sdfgpu_update_surface instead. */
+int sdfgpu_wasm_lower(const void* wasm, size_t wasm_bytes, uint32_t sdf_id, void* tape_out, size_t tape_cap,
+                      size_t* tape_len, float bb_out[6], char* log, size_t log_cap);
+
 /* SDFViewer::update (src/app/scene/sdf/mod.rs:128-217).
  *   changed_box : result of sdf.changed() this frame ({min,max}), or NULL for None;
  *                 merged into the pending box as :131-139 does.

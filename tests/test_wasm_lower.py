@@ -1,0 +1,372 @@
+"""sdfgpu_wasm_lower: the `sample` export of a WebAssembly SDF (guest ABI: /root/reference/src/sdf/wasm/mod.rs:5-37,
+host src/sdf/wasm/native.rs:29-98,163-217) lowered to a scalar-program tape.
+
+No WASM toolchain exists in the build image, so the guests are assembled here (tests/wasm_asm.py) in the shapes a
+compiler emits: results in a static buffer or on a shadow stack copied out with memory.copy, parameters loaded from
+data segments, helper calls, call_indirect through a table (trait objects), loops with concrete trip counts,
+br_if / if-else / early returns on values that depend on the position, integer work on truncated coordinates.
+Each lowered tape is evaluated by the oracle's interpreter and compared bit for bit with the same formula written
+in numpy float32; the specialiser's CUDA for it must compile (NVRTC, sm_100a).  The GPU run is marked gpu_next."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from wasm_asm import F32, F64, I32, I64, Module
+
+f32 = np.float32
+OUT, BBP = 1024, 2048
+BB = ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))
+SAMPLE_SIG = ([I32, F32, F32, F32, I32], [I32])
+X, Y, Z = ("local.get", 1), ("local.get", 2), ("local.get", 3)
+
+
+def base_module(bb=(-1, -1, -1, 1, 1, 1), pages=1):
+    m = Module(pages=pages)
+    m.data_at(BBP, struct.pack("<6f", *bb))
+    m.func([I32], [I32], body=[("i32.const", BBP)], export="bounding_box")
+    return m
+
+
+def store_out(k, value_instrs, base=("i32.const", OUT)):
+    return [base] + list(value_instrs) + [("f32.store", 4 * k)]
+
+
+def points(n=300, seed=0):
+    rng = np.random.default_rng(seed)
+    p = rng.uniform(-1, 1, (n, 3)).astype(f32)
+    p[:8] = [[0, 0, 0], [0.5, 0.5, 0.5], [-0.5, 0.5, 0], [1, -1, 1], [0.25, -0.125, 0.0], [-0.0, 0.0, 1.0], [0.3, 0.3, 0.3], [-1, -1, -1]]
+    return p
+
+
+def same(a, b):
+    a, b = np.asarray(a, f32), np.asarray(b, f32)
+    return bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
+def lowered(S, oracle, m, sdf_id=0):
+    tape, bb, summary = S.wasm.lower(m.build(), sdf_id)
+    assert S.jit_check(tape, 4)                       # the generated kernel compiles for sm_100a
+    return tape, bb, summary
+
+
+# ---------------------------------------------------------------------------------------------- guests
+
+def guest_sphere_static():
+    """Result in a static buffer; the radius lives in a data segment (a `static` in the guest)."""
+    m = base_module()
+    m.data_at(512, struct.pack("<f", 0.7))
+    body = store_out(0, [X, X, "f32.mul", Y, Y, "f32.mul", "f32.add", Z, Z, "f32.mul", "f32.add", "f32.sqrt",
+                         ("i32.const", 512), ("f32.load", 0), "f32.sub"])
+    body += store_out(1, [X, "f32.abs"]) + store_out(2, [("f32.const", 0.25)]) + store_out(3, [Y, ("f32.const", 0.0), "f32.max"])
+    body += store_out(4, [("f32.const", 0.0)]) + store_out(5, [("f32.const", 0.5)]) + store_out(6, [("f32.const", 1.0)])
+    m.func(*SAMPLE_SIG, body=body + [("i32.const", OUT)], export="sample")
+    return m
+
+
+def ref_sphere_static(p):
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    o = np.zeros((len(p), 7), f32)
+    o[:, 0] = np.sqrt((x * x + y * y) + z * z) - f32(0.7)
+    o[:, 1] = np.abs(x)
+    o[:, 2] = 0.25
+    o[:, 3] = np.where(y > 0, y, f32(0.0)) + f32(0.0) * 0   # wasm max(y, +0): y for y > 0, +0 otherwise (incl. -0)
+    o[:, 5], o[:, 6] = 0.5, 1.0
+    return o
+
+
+def guest_box_branchy():
+    """max() written with br_if, a bump allocator in a global for the result, and an if / else with a result."""
+    m = base_module()
+    heap = m.global_(I32, 4096)
+    D, P = ("local.get", 5), ("local.get", 6)
+    body = [X, "f32.abs", ("local.set", 5)]
+    for axis in (Y, Z):
+        body += [("block", []), axis, "f32.abs", D, "f32.gt", "i32.eqz", ("br_if", 0), axis, "f32.abs", ("local.set", 5), "end"]
+    body += [D, ("f32.const", 0.5), "f32.sub", ("local.set", 5)]
+    body += [("global.get", heap), ("local.tee", 6), ("i32.const", 32), "i32.add", ("global.set", heap)]
+    body += [P, D, ("f32.store", 0)]
+    body += [P, D, ("f32.const", 0.1), "f32.gt", ("if", [F32]), ("f32.const", 0.0), "else",
+             X, ("f32.const", 4.0), "f32.mul", "f32.floor", ("f32.const", 0.25), "f32.mul", "end", ("f32.store", 4)]
+    for k, c in ((2, 0.2), (3, 0.3), (4, 0.0), (5, 0.9), (6, 1.0)):
+        body += [P, ("f32.const", c), ("f32.store", 4 * k)]
+    m.func(*SAMPLE_SIG, locals=[F32, I32], body=body + [P], export="sample")
+    return m
+
+
+def ref_box_branchy(p):
+    a = np.abs(p)
+    d = a[:, 0].copy()
+    d = np.where(a[:, 1] > d, a[:, 1], d)
+    d = np.where(a[:, 2] > d, a[:, 2], d)
+    d = d - f32(0.5)
+    o = np.zeros((len(p), 7), f32)
+    o[:, 0] = d
+    o[:, 1] = np.where(d > f32(0.1), f32(0.0), np.floor(p[:, 0] * f32(4.0)) * f32(0.25))
+    o[:, 2], o[:, 3], o[:, 5], o[:, 6] = 0.2, 0.3, 0.9, 1.0
+    return o
+
+
+SPHERES = [(0.3, 0.2, -0.1, 0.35, 0.9), (-0.4, -0.3, 0.2, 0.3, 0.5), (0.0, 0.5, 0.5, 0.25, 0.2), (-0.2, 0.1, -0.6, 0.4, 0.7)]
+
+
+def guest_csg_calls():
+    """A union of four spheres read from a table in memory: a loop with a concrete trip count, a helper function,
+    call_indirect through the function table (as a trait object's vtable), the result built on a shadow stack
+    (global stack pointer) and copied to the output buffer with memory.copy; `init()` fills the table's count."""
+    m = base_module()
+    sp = m.global_(I32, 60000)
+    TAB, COUNT = 4096, 4000
+    m.data_at(TAB, b"".join(struct.pack("<5f", *s) for s in SPHERES))
+    m.data_at(3000, struct.pack("<I", 1))  # which material function to call (index into the table)
+    init = m.func([], [], body=[("i32.const", COUNT), ("i32.const", len(SPHERES)), ("i32.store", 0)], export="init")
+    # dist(x, y, z, ptr) -> f32
+    dist = m.func([F32, F32, F32, I32], [F32], locals=[F32, F32, F32], body=[
+        ("local.get", 0), ("local.get", 3), ("f32.load", 0), "f32.sub", ("local.set", 4),
+        ("local.get", 1), ("local.get", 3), ("f32.load", 4), "f32.sub", ("local.set", 5),
+        ("local.get", 2), ("local.get", 3), ("f32.load", 8), "f32.sub", ("local.set", 6),
+        ("local.get", 4), ("local.get", 4), "f32.mul", ("local.get", 5), ("local.get", 5), "f32.mul", "f32.add",
+        ("local.get", 6), ("local.get", 6), "f32.mul", "f32.add", "f32.sqrt", ("local.get", 3), ("f32.load", 12), "f32.sub"])
+    mat0 = m.func([F32], [F32], body=[("local.get", 0), ("f32.const", 0.5), "f32.mul"])
+    mat1 = m.func([F32], [F32], body=[("local.get", 0), "f32.abs"])
+    m.table([mat0, mat1])
+    t_mat = m.type_index([F32], [F32])
+    I, BEST, COL, DI, SP, PTR = (("local.get", k) for k in (5, 6, 7, 8, 9, 10))
+    body = [("global.get", sp), ("i32.const", 32), "i32.sub", ("local.tee", 9), ("global.set", sp),
+            ("f32.const", 1e9), ("local.set", 6), ("f32.const", 0.0), ("local.set", 7), ("i32.const", 0), ("local.set", 5),
+            ("block", []), ("loop", []),
+            I, ("i32.const", COUNT), ("i32.load", 0), "i32.ge_u", ("br_if", 1),
+            ("i32.const", TAB), I, ("i32.const", 20), "i32.mul", "i32.add", ("local.set", 10),
+            X, Y, Z, PTR, ("call", dist), ("local.set", 8),
+            PTR, ("f32.load", 16), COL, DI, BEST, "f32.lt", "select", ("local.set", 7),
+            DI, BEST, DI, BEST, "f32.lt", "select", ("local.set", 6),
+            I, ("i32.const", 1), "i32.add", ("local.set", 5), ("br", 0), "end", "end",
+            SP, BEST, ("f32.store", 0), SP, COL, ("f32.store", 4), SP, COL, COL, "f32.mul", ("f32.store", 8),
+            SP, ("f32.const", 0.1), ("f32.store", 12),
+            SP, BEST, ("i32.const", 3000), ("i32.load", 0), ("call_indirect", t_mat), ("f32.store", 16),
+            SP, ("f32.const", 0.6), ("f32.store", 20), SP, ("f32.const", 1.0), ("f32.store", 24),
+            ("i32.const", OUT), SP, ("i32.const", 28), ("memory.copy",),
+            SP, ("i32.const", 32), "i32.add", ("global.set", sp), ("i32.const", OUT)]
+    m.func(*SAMPLE_SIG, locals=[I32, F32, F32, F32, I32, I32], body=body, export="sample")
+    assert init is not None
+    return m
+
+
+def ref_csg_calls(p):
+    best = np.full(len(p), f32(1e9))
+    col = np.zeros(len(p), f32)
+    for cx, cy, cz, r, c in SPHERES:
+        qx, qy, qz = p[:, 0] - f32(cx), p[:, 1] - f32(cy), p[:, 2] - f32(cz)
+        d = np.sqrt((qx * qx + qy * qy) + qz * qz) - f32(r)
+        col = np.where(d < best, f32(c), col)
+        best = np.where(d < best, d, best)
+    o = np.zeros((len(p), 7), f32)
+    o[:, 0], o[:, 1], o[:, 2], o[:, 3], o[:, 4], o[:, 5], o[:, 6] = best, col, col * col, 0.1, np.abs(best), 0.6, 1.0
+    return o
+
+
+def guest_early_returns():
+    """Nested branches on the position with early `return`s and a br out of two blocks carrying a value."""
+    m = base_module()
+    A, B = 1100, 1200
+    m.data_at(A, struct.pack("<7f", 0.5, 1, 0, 0, 0.1, 0.2, 1.0))
+    m.data_at(B, struct.pack("<7f", -0.25, 0, 1, 0, 0.3, 0.4, 0.5))
+    body = [X, ("f32.const", 0.0), "f32.gt",
+            ("if", []),
+            Y, ("f32.const", 0.0), "f32.gt", ("if", []), ("i32.const", A), "return", "end",
+            Z, ("f32.const", 0.5), "f32.lt", ("if", []), ("i32.const", B), "return", "end",
+            "end",
+            # d = block(result f32) { block { br_if 0 (x+y < 0); br 1 (x*y) }; -(x+y) }
+            ("block", [F32]), ("block", []), X, Y, "f32.add", ("f32.const", 0.0), "f32.lt", ("br_if", 0), X, Y, "f32.mul", ("br", 1), "end",
+            X, Y, "f32.add", "f32.neg", "end", ("local.set", 5)]
+    body += store_out(0, [("local.get", 5)]) + store_out(1, [Z, "f32.nearest"]) + store_out(2, [X, Y, "f32.copysign"])
+    body += store_out(3, [X, Y, "f32.min"]) + store_out(4, [X, "f32.ceil"]) + store_out(5, [Y, "f32.trunc"]) + store_out(6, [X, Y, "f32.div"])
+    m.func(*SAMPLE_SIG, locals=[F32], body=body + [("i32.const", OUT)], export="sample")
+    return m
+
+
+def ref_early_returns(p):
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    with np.errstate(all="ignore"):
+        general = np.zeros((len(p), 7), f32)
+        general[:, 0] = np.where(x + y < 0, -(x + y), x * y)
+        general[:, 1] = np.rint(z)
+        general[:, 2] = np.copysign(x, y)
+        mn = np.where(x == y, (x.view(np.uint32) | y.view(np.uint32)).view(f32), np.minimum(x, y))
+        general[:, 3] = mn
+        general[:, 4] = np.ceil(x)
+        general[:, 5] = np.trunc(y)
+        general[:, 6] = x / y
+    a = np.array([0.5, 1, 0, 0, 0.1, 0.2, 1.0], f32)
+    b = np.array([-0.25, 0, 1, 0, 0.3, 0.4, 0.5], f32)
+    out = general
+    out = np.where(((x > 0) & ~(y > 0) & (z < f32(0.5)))[:, None], b[None, :], out)
+    out = np.where(((x > 0) & (y > 0))[:, None], a[None, :], out)
+    return out.astype(f32)
+
+
+def guest_integer_checker():
+    """Integer arithmetic on truncated coordinates (a checker pattern), shifts and conversions back to float."""
+    m = base_module()
+    cell = lambda axis: [axis, ("f32.const", 8.0), "f32.mul", "f32.floor", ("i32.trunc_sat_f32_s",)]  # noqa: E731
+    body = cell(X) + cell(Y) + ["i32.add"] + cell(Z) + ["i32.add", ("local.tee", 5), ("i32.const", 1), "i32.and", ("local.set", 6)]
+    body += store_out(0, [Y])
+    body += store_out(1, [("f32.const", 0.9), ("f32.const", 0.1), ("local.get", 6), "select"])
+    body += store_out(2, [("local.get", 5), "f32.convert_i32_s", ("f32.const", 0.0625), "f32.mul"])
+    body += store_out(3, [("local.get", 5), ("i32.const", 2), "i32.shl", ("i32.const", 3), "i32.shr_s", ("i32.const", 7), "i32.xor", "f32.convert_i32_s"])
+    body += store_out(4, [X, ("i32.trunc_f32_s",) if False else "i32.trunc_f32_s", "f32.convert_i32_s"])
+    body += store_out(5, [X, "i32.reinterpret_f32", ("i32.const", 0x7FFFFFFF), "i32.and", "f32.reinterpret_i32"])
+    body += store_out(6, [("local.get", 5), ("i32.const", 0), "i32.lt_s", ("if", [F32]), ("f32.const", 0.25), "else", ("f32.const", 1.0), "end"])
+    m.func(*SAMPLE_SIG, locals=[I32, I32], body=body + [("i32.const", OUT)], export="sample")
+    return m
+
+
+def ref_integer_checker(p):
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    c = (np.floor(x * f32(8)).astype(np.int32) + np.floor(y * f32(8)).astype(np.int32) + np.floor(z * f32(8)).astype(np.int32))
+    o = np.zeros((len(p), 7), f32)
+    o[:, 0] = y
+    o[:, 1] = np.where((c & 1) != 0, f32(0.9), f32(0.1))
+    o[:, 2] = c.astype(f32) * f32(0.0625)
+    o[:, 3] = (((c << 2) >> 3) ^ 7).astype(f32)
+    o[:, 4] = np.trunc(x).astype(np.int32).astype(f32)
+    o[:, 5] = np.abs(x)
+    o[:, 6] = np.where(c < 0, f32(0.25), f32(1.0))
+    return o
+
+
+GUESTS = {
+    "sphere_static": (guest_sphere_static, ref_sphere_static),
+    "box_branchy": (guest_box_branchy, ref_box_branchy),
+    "csg_calls": (guest_csg_calls, ref_csg_calls),
+    "early_returns": (guest_early_returns, ref_early_returns),
+    "integer_checker": (guest_integer_checker, ref_integer_checker),
+}
+
+
+@pytest.mark.parametrize("name", list(GUESTS))
+def test_lowered_guest_equals_its_formula(S, oracle, name):
+    make, ref = GUESTS[name]
+    tape, bb, summary = lowered(S, oracle, make())
+    assert bb == BB and summary.startswith("lowered:")
+    p = points()
+    got = oracle.tape_sample(tape, p)
+    want = ref(p)
+    bad = ~((got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want)))
+    assert not bad.any(), (name, np.argwhere(bad)[:5], got[bad][:5], want[bad][:5])
+
+
+def test_parameter_change_keeps_the_structure(S, oracle):
+    """Re-lowering after a guest parameter changed (here: the radius in the data segment) yields the same
+    program with other constants -- the compiled kernel is re-used, as for the hand-written demo tape."""
+    a = guest_sphere_static()
+    b = guest_sphere_static()
+    b.data[1] = (512, struct.pack("<f", 0.55))
+    ta, tb = S.wasm.lower(a.build())[0], S.wasm.lower(b.build())[0]
+    assert len(ta) == len(tb) and ta != tb
+    n_consts = struct.unpack_from("<I", ta, 16)[0]
+    off = 32 + 2 * 16
+    assert ta[:off] == tb[:off] and ta[off + 4 * n_consts:] == tb[off + 4 * n_consts:]      # only constants differ
+    p = points(50)
+    assert same(oracle.tape_sample(tb, p)[:, 0], np.sqrt((p[:, 0] ** 2 + p[:, 1] ** 2) + p[:, 2] ** 2).astype(f32) - f32(0.55))
+
+
+def test_wasm_sdf_surface(S):
+    sdf = S.WasmSDF(guest_box_branchy().build())
+    assert sdf.bounding_box() == BB and sdf.changed() is None
+    assert sdf.tape()[:4] == b"SDFT"
+
+
+def expect_failure(S, m, code, *fragments):
+    with pytest.raises(S.WasmLoweringError) as e:
+        S.wasm.lower(m.build() if isinstance(m, Module) else m)
+    assert e.value.code == code, str(e.value)
+    for f in fragments:
+        assert f in str(e.value), str(e.value)
+
+
+def test_what_cannot_be_lowered_says_why(S):
+    # a loop whose exit depends on the position
+    m = base_module()
+    m.func(*SAMPLE_SIG, locals=[F32], body=[X, ("local.set", 5), ("block", []), ("loop", []), ("local.get", 5), ("f32.const", 1.0), "f32.ge", ("br_if", 1),
+                                            ("local.get", 5), ("f32.const", 0.001), "f32.add", ("local.set", 5), ("br", 0), "end", "end",
+                                            ("i32.const", OUT)], export="sample")
+    expect_failure(S, m, -3, "depend on the position")
+    # an address that depends on the position
+    m = base_module()
+    m.func(*SAMPLE_SIG, body=[("i32.const", OUT), X, ("f32.const", 4.0), "f32.mul", ("i32.trunc_sat_f32_s",), ("i32.const", 4), "i32.mul",
+                              ("f32.load", 4096), ("f32.store", 0), ("i32.const", OUT)], export="sample")
+    expect_failure(S, m, -3, "address that depends on the position")
+    # a host import on the way
+    m = Module()
+    imp = m.import_func("env", "host_noise", [F32], [F32])
+    m.data_at(BBP, struct.pack("<6f", -1, -1, -1, 1, 1, 1))
+    m.func([I32], [I32], body=[("i32.const", BBP)], export="bounding_box")
+    m.func(*SAMPLE_SIG, body=[("i32.const", OUT), X, ("call", imp), ("f32.store", 0), ("i32.const", OUT)], export="sample")
+    expect_failure(S, m, -3, "env.host_noise")
+    # f64 arithmetic on the position
+    m = base_module()
+    m.func(*SAMPLE_SIG, body=[("i32.const", OUT), X, "f64.promote_f32", "f64.sqrt", "f32.demote_f64", ("f32.store", 0), ("i32.const", OUT)], export="sample")
+    expect_failure(S, m, -3, "no 32-bit scalar form")
+    # a guest that traps for every position
+    m = base_module()
+    m.func(*SAMPLE_SIG, body=["unreachable"], export="sample")
+    expect_failure(S, m, -3, "traps")
+    # missing exports, wrong signature, garbage
+    m = Module()
+    m.func([I32], [I32], body=[("i32.const", BBP)], export="bounding_box")
+    expect_failure(S, m, -1, "bounding_box and sample")
+    m = base_module()
+    m.func([I32, F32, F32, F32], [I32], body=[("i32.const", OUT)], export="sample")
+    expect_failure(S, m, -1, "signatures")
+    expect_failure(S, b"\0asm\x01\0\0\0\x01\xff\xff\xff\xff\x0f", -1)
+    expect_failure(S, b"not wasm at all", -1, "WebAssembly")
+
+
+def test_traps_on_one_side_of_a_branch_are_dropped(S, oracle):
+    """`if x < -2 { unreachable }` (a bounds check the compiler left in): the trapping side contributes nothing."""
+    m = base_module()
+    body = [X, ("f32.const", -2.0), "f32.lt", ("if", []), "unreachable", "end"] + store_out(0, [X, Y, "f32.add"])
+    for k in range(1, 7):
+        body += store_out(k, [("f32.const", 0.125 * k)])
+    m.func(*SAMPLE_SIG, body=body + [("i32.const", OUT)], export="sample")
+    tape, _, summary = lowered(S, oracle, m)
+    p = points(40)
+    got = oracle.tape_sample(tape, p)
+    assert same(got[:, 0], p[:, 0] + p[:, 1]) and same(got[:, 3], np.full(len(p), 0.375, f32))
+    assert "1 symbolic branches" in summary
+
+
+def test_sdf_id_is_forwarded(S, oracle):
+    """Every export takes the SDF's id first (0 = root, src/sdf/wasm/mod.rs:8-10): a guest with two children."""
+    m = Module()
+    m.data_at(BBP, struct.pack("<6f", -1, -1, -1, 1, 1, 1) + struct.pack("<6f", -0.5, -0.5, -0.5, 0.5, 0.5, 0.5))
+    m.func([I32], [I32], body=[("i32.const", BBP), ("local.get", 0), ("i32.const", 24), "i32.mul", "i32.add"], export="bounding_box")
+    body = store_out(0, [X, ("local.get", 0), "f32.convert_i32_s", "f32.add"])
+    for k in range(1, 7):
+        body += store_out(k, [("f32.const", 0.0)])
+    m.func(*SAMPLE_SIG, body=body + [("i32.const", OUT)], export="sample")
+    p = points(20)
+    for sdf_id, bb in ((0, BB), (1, ((-0.5, -0.5, -0.5), (0.5, 0.5, 0.5)))):
+        tape, got_bb, _ = lowered(S, oracle, m, sdf_id)
+        assert got_bb == bb
+        assert same(oracle.tape_sample(tape, p)[:, 0], p[:, 0] + f32(sdf_id))
+
+
+@pytest.mark.gpu_next
+def test_lowered_guests_fill_on_gpu(S, oracle):
+    """GPU run of the lowered guests, bit-exact against the oracle's interpretation of the same tape.  Not in
+    `-m gpu` yet (no GPU budget was left when this was written): SDFGPU_RUN_NEXT=1 on a B200."""
+    from test_scalar_programs import _have_gpu
+    if not os.environ.get("SDFGPU_RUN_NEXT") or not _have_gpu(S):
+        pytest.skip("set SDFGPU_RUN_NEXT=1 on a GPU box")
+    dims = (40, 36, 32)
+    for name, (make, _) in GUESTS.items():
+        sdf = S.WasmSDF(make().build())
+        o = oracle.Viewer(BB, dims, 2)
+        o.update(oracle.Sampler(tape=sdf.tape()))
+        with S.SDFViewer.new_voxels(dims, BB, 2) as v:
+            assert v.update_surface(sdf, 0.030) == o.total_iterations()
+            t0, t1 = v.download()
+        assert same(t0, o.tex0) and same(t1, o.tex1), name
