@@ -389,6 +389,37 @@ class SDFDemo : public SDFSurface {
     mutable bool changed_ = false;  // the trait takes &self: interior mutability, as in the reference
 };
 
+// An existing .wasm SDF (the guest ABI of src/sdf/wasm/mod.rs:5-37, loaded by the reference with
+// src/sdf/wasm/native.rs) as a surface with a tape: `sdfgpu_wasm_lower` executes the module once with symbolic
+// coordinates and the GPU evaluates the result.  Throws sdfgpu::Error with the reason when the guest cannot be
+// lowered; the host then wraps its own WASM runtime in an SDFSurface whose sample() calls the guest, and the
+// viewer samples that on the host (the reference's own path, batched).
+class WasmSDF : public SDFSurface {
+   public:
+    WasmSDF(const void* wasm, size_t wasm_bytes, uint32_t sdf_id = 0) {
+        char log[1024];
+        size_t need = 0;
+        float bb[6];
+        int rc = sdfgpu_wasm_lower(wasm, wasm_bytes, sdf_id, nullptr, 0, &need, bb, log, sizeof log);
+        if (rc != SDFGPU_OK) throw Error(rc, log);
+        tape_.resize(need);
+        rc = sdfgpu_wasm_lower(wasm, wasm_bytes, sdf_id, tape_.data(), tape_.size(), &need, bb, log, sizeof log);
+        if (rc != SDFGPU_OK) throw Error(rc, log);
+        bb_ = {Vector3{bb[0], bb[1], bb[2]}, Vector3{bb[3], bb[4], bb[5]}};
+        summary = log;
+    }
+    BoundingBox bounding_box() const override { return bb_; }
+    SDFSample sample(Vector3, bool) const override {
+        throw std::logic_error("sdfgpu::WasmSDF is evaluated on the GPU through tape(); it has no host sample()");
+    }
+    std::optional<std::vector<unsigned char>> tape() const override { return tape_; }
+    std::string summary;  // "lowered: N scalar ops, ..."
+
+   private:
+    std::vector<unsigned char> tape_;
+    BoundingBox bb_;
+};
+
 }  // namespace sdfgpu
 
 #endif  // SDFGPU_VIEWER_HPP

@@ -4,6 +4,7 @@
 //
 //   host_viewer loading          CPU: the five loading.rs cases
 //   host_viewer tape             CPU: hex dump of sdfgpu::SDFDemo's tape (compared with tape.py's)
+//   host_viewer wasm <file>      CPU: sdfgpu::WasmSDF lowers a WebAssembly SDF; prints the summary, bounding box, tape
 //   host_viewer gpu <out_dir>    GPU: (1) the demo surface with a tape, (2) a surface WITHOUT a tape whose
 //                                sample() is the oracle's SDFDemo::sample; volumes and a frame are
 //                                written to <out_dir> for the Python test to compare with the oracle
@@ -180,6 +181,25 @@ int main(int argc, char** argv) {
             return 2;
         }
     }
-    std::fprintf(stderr, "usage: host_viewer loading | tape [nosphere] | gpu <out_dir>\n");
+    if (mode == "wasm" && argc > 2) {  // CPU: lower a .wasm SDF through sdfgpu::WasmSDF, print its tape as hex
+        FILE* f = std::fopen(argv[2], "rb");
+        REQUIRE(f != nullptr);
+        std::vector<unsigned char> bytes;
+        for (int c; (c = std::fgetc(f)) != EOF;) bytes.push_back((unsigned char)c);
+        std::fclose(f);
+        try {
+            sdfgpu::WasmSDF sdf(bytes.data(), bytes.size());
+            const auto bb = sdf.bounding_box();
+            std::printf("%s\n%g %g %g %g %g %g\n", sdf.summary.c_str(), bb[0].x, bb[0].y, bb[0].z, bb[1].x, bb[1].y, bb[1].z);
+            const std::vector<unsigned char> tape = *sdf.tape();
+            for (unsigned char c : tape) std::printf("%02x", c);
+            std::printf("\n");
+            return 0;
+        } catch (const sdfgpu::Error& e) {
+            std::printf("cannot lower (%d): %s\n", e.code(), e.what());
+            return 3;
+        }
+    }
+    std::fprintf(stderr, "usage: host_viewer loading | tape [nosphere] | wasm <file.wasm> | gpu <out_dir>\n");
     return 64;
 }

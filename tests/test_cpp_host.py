@@ -38,6 +38,23 @@ def test_cpp_demo_tape_equals_python_tape(S, host_viewer):
         assert bytes.fromhex(r.stdout.strip()) == want
 
 
+def test_cpp_wasm_sdf_lowers_like_python(S, host_viewer, tmp_path):
+    """sdfgpu::WasmSDF (C++) and sdf_viewer_b200.WasmSDF (Python) are the same call into the library."""
+    import test_wasm_lower as W
+    wasm = W.guest_csg_calls().build()
+    path = tmp_path / "guest.wasm"
+    path.write_bytes(wasm)
+    r = subprocess.run([host_viewer, "wasm", str(path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    summary, bb, tape_hex = r.stdout.strip().split("\n")
+    tape, want_bb, want_summary = S.wasm.lower(wasm)
+    assert summary == want_summary and bytes.fromhex(tape_hex) == tape
+    assert [float(v) for v in bb.split()] == list(want_bb[0]) + list(want_bb[1])
+    path.write_bytes(b"\0asm\x01\0\0\0")            # an empty module: no exports
+    r = subprocess.run([host_viewer, "wasm", str(path)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 3 and "cannot lower (-1)" in r.stdout
+
+
 def test_headers_are_self_contained_cxx(tmp_path):
     src = tmp_path / "tu.cpp"
     src.write_text('#include "sdfgpu_viewer.hpp"\nint main() { return sizeof(sdfgpu::SDFSample) == 28 ? 0 : 1; }\n')
