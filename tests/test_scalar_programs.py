@@ -7,7 +7,8 @@ CPU-side evidence (no GPU in the build container):
     few intrinsics it uses, against the oracle -- this checks the code generator's wiring;
   * NVRTC compiles that text for sm_100a (sdfgpu_jit_check);
   * malformed programs are rejected.
-The GPU run of the same tapes is `test_scalar_tape_fill_on_gpu` (marker gpu_next: not yet run on a B200)."""
+GPU: `test_scalar_tape_sphere_fills_on_gpu` (ran on a B200); the wider sweep `test_scalar_tape_fill_on_gpu` is still
+marked gpu_next (not yet run on a B200)."""
 import ctypes as C
 import os
 import re
@@ -353,6 +354,22 @@ def _have_gpu(S):
         return True
     except S.SdfGpuError:
         return False
+
+
+@pytest.mark.gpu
+def test_scalar_tape_sphere_fills_on_gpu(S, oracle):
+    """A hand-written scalar program evaluated by the specialised fill kernel, bit-exact against the oracle
+    (first run on a B200: profiles/r01_scalar_wasm_first_gpu_run.log)."""
+    dims = (40, 36, 32)
+    _, tape = build_tape(S.tape, sphere_with_bands(S.tape))
+    o = oracle.Viewer(BB, dims, 2)
+    o.update(oracle.Sampler(tape=tape))
+    with S.SDFViewer.new_voxels(dims, BB, 2) as v:
+        v.set_tape(tape)
+        v.update(None)
+        t0, t1 = v.download()
+        assert v.get_info("last_fill_program") == 1
+    assert same_f32(t0, o.tex0) and same_f32(t1, o.tex1)
 
 
 @pytest.mark.gpu_next

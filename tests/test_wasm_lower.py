@@ -354,6 +354,23 @@ def test_sdf_id_is_forwarded(S, oracle):
         assert same(oracle.tape_sample(tape, p)[:, 0], p[:, 0] + f32(sdf_id))
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["csg_calls", "early_returns"])
+def test_lowered_guest_fills_on_gpu(S, oracle, name):
+    """A lowered WebAssembly guest evaluated by the specialised fill kernel: both volumes equal the oracle's
+    interpretation of the same tape bit for bit (first run on a B200: profiles/r01_scalar_wasm_first_gpu_run.log)."""
+    dims = (40, 36, 32)
+    tape = S.wasm.lower(GUESTS[name][0]().build())[0]
+    o = oracle.Viewer(BB, dims, 2)
+    o.update(oracle.Sampler(tape=tape))
+    with S.SDFViewer.new_voxels(dims, BB, 2) as v:
+        v.set_tape(tape)
+        v.update(None)
+        t0, t1 = v.download()
+        assert v.get_info("last_fill_program") == 1
+    assert same(t0, o.tex0) and same(t1, o.tex1)
+
+
 @pytest.mark.gpu_next
 def test_lowered_guests_fill_on_gpu(S, oracle):
     """GPU run of the lowered guests, bit-exact against the oracle's interpretation of the same tape.  Not in
