@@ -18,6 +18,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -875,13 +876,13 @@ struct Lowerer {
         return true;
     }
 
-    // carry `arity` values to `height`
-    static void unwind(State& st, size_t height, uint32_t arity) {
-        if (st.stack.size() >= height + arity) {
-            std::vector<Val> keep(st.stack.end() - arity, st.stack.end());
-            st.stack.resize(height);
-            st.stack.insert(st.stack.end(), keep.begin(), keep.end());
-        }
+    // carry `arity` values to `height`; false (with the error set) when the stack does not hold them
+    bool unwind(State& st, size_t height, uint32_t arity) {
+        if (arity > st.stack.size() || height > st.stack.size() - arity) return fail("stack underflow at a branch or return");
+        std::vector<Val> keep(st.stack.end() - arity, st.stack.end());
+        st.stack.resize(height);
+        st.stack.insert(st.stack.end(), keep.begin(), keep.end());
+        return true;
     }
 
     // returns true when the outermost frame returned
@@ -890,8 +891,8 @@ struct Lowerer {
         if (depth >= fr.labels.size()) { fail("branch depth out of range"); return false; }
         const size_t idx = fr.labels.size() - 1 - depth;
         const Label l = fr.labels[idx];
-        unwind(st, l.height, l.arity);
         if (idx == 0) return do_return(st);
+        if (!unwind(st, l.height, l.arity)) return false;
         if (l.is_loop) {
             fr.labels.resize(idx + 1);
             fr.pc = l.cont_pc;
@@ -904,7 +905,7 @@ struct Lowerer {
     bool do_return(State& st) {
         Frame& fr = st.frames.back();
         const Label l = fr.labels[0];
-        unwind(st, l.height, l.results);
+        if (!unwind(st, l.height, l.results)) return false;
         st.frames.pop_back();
         return st.frames.empty();
     }
@@ -946,6 +947,7 @@ struct Lowerer {
             Func& f = m.funcs[fr.func];
             if (fr.pc >= f.code_len) {  // fell off the end of the body
                 if (do_return(st)) return finish(*this, st);
+                if (!err.empty()) return failed();
                 continue;
             }
             Rd r{f.code + fr.pc, f.code + f.code_len};
@@ -961,6 +963,7 @@ struct Lowerer {
                     uint32_t np, nr;
                     if (!block_arity(bt, &np, &nr)) return failed();
                     ADVANCE();
+                    NEED(np);
                     const BlockInfo& bi = f.blocks[at];
                     Label l;
                     l.is_loop = op == 0x03;
@@ -980,6 +983,7 @@ struct Lowerer {
                     NEED(1);
                     const Val c = st.stack.back();
                     st.stack.pop_back();
+                    NEED(np);
                     const BlockInfo bi = f.blocks[at];
                     Label l;
                     l.height = st.stack.size() - np;
@@ -1012,6 +1016,7 @@ struct Lowerer {
                     ADVANCE();
                     if (fr.labels.size() > 1) fr.labels.pop_back();
                     else if (do_return(st)) return finish(*this, st);
+                    else if (!err.empty()) return failed();
                     break;
                 }
                 case 0x0c: {
@@ -1059,7 +1064,11 @@ struct Lowerer {
                     if (!err.empty()) return failed();
                     break;
                 }
-                case 0x0f: ADVANCE(); if (do_return(st)) return finish(*this, st); break;
+                case 0x0f:
+                    ADVANCE();
+                    if (do_return(st)) return finish(*this, st);
+                    if (!err.empty()) return failed();
+                    break;
                 case 0x10: {
                     const uint32_t fi = r.u32();
                     ADVANCE();
@@ -1315,6 +1324,10 @@ extern "C" __attribute__((visibility("default"))) int sdfgpu_wasm_lower(const vo
     if (tape_len) *tape_len = 0;
     if (!wasm || !wasm_bytes) { put_log(log, log_cap, "wasm is NULL or empty"); return SDFGPU_ERR_INVALID; }
     Lowerer L;
+    if (const char* e = getenv("SDFGPU_WASM_BUDGET")) {  // instructions the partial evaluation may execute (tests)
+        const long long n = atoll(e);
+        if (n > 0) L.budget = (uint64_t)n;
+    }
     if (!L.parse((const uint8_t*)wasm, wasm_bytes)) { put_log(log, log_cap, L.err); return SDFGPU_ERR_INVALID; }
     auto find_func = [&](const char* name, uint32_t* fi) {
         auto it = L.m.exports.find(name);

@@ -6,7 +6,8 @@ compiler emits: results in a static buffer or on a shadow stack copied out with 
 data segments, helper calls, call_indirect through a table (trait objects), loops with concrete trip counts,
 br_if / if-else / early returns on values that depend on the position, integer work on truncated coordinates.
 Each lowered tape is evaluated by the oracle's interpreter and compared bit for bit with the same formula written
-in numpy float32; the specialiser's CUDA for it must compile (NVRTC, sm_100a).  The GPU run is marked gpu_next."""
+in numpy float32; the specialiser's CUDA for it must compile (NVRTC, sm_100a).  Two of the guests also fill a grid on
+the GPU (`-m gpu`, ran on a B200); the sweep over all of them is still marked gpu_next."""
 import os
 import struct
 
@@ -322,6 +323,37 @@ def test_what_cannot_be_lowered_says_why(S):
     expect_failure(S, m, -1, "signatures")
     expect_failure(S, b"\0asm\x01\0\0\0\x01\xff\xff\xff\xff\x0f", -1)
     expect_failure(S, b"not wasm at all", -1, "WebAssembly")
+
+
+def test_mutated_modules_never_crash_the_lowering(S, monkeypatch):
+    """The module is untrusted input: random byte flips, truncations and splices of valid guests must end in
+    SDFGPU_OK or an error code, never in a crash or a hang (the instruction budget bounds every run)."""
+    monkeypatch.setenv("SDFGPU_WASM_BUDGET", "200000")
+    rng = np.random.default_rng(2024)
+    seeds = [make().build() for make, _ in GUESTS.values()]
+    outcomes = {"ok": 0, "invalid": 0, "tape": 0}
+    for it in range(1500):
+        w = bytearray(seeds[it % len(seeds)])
+        kind = it % 4
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                w[int(rng.integers(8, len(w)))] = int(rng.integers(0, 256))
+        elif kind == 1:
+            w = w[:int(rng.integers(8, len(w)))]
+        elif kind == 2:
+            i = int(rng.integers(8, len(w)))
+            w[i] ^= 1 << int(rng.integers(0, 8))
+        else:
+            a, b = sorted(int(v) for v in rng.integers(8, len(w), 2))
+            other = seeds[(it + 1) % len(seeds)]
+            w = w[:a] + other[a:b] + w[b:]
+        try:
+            S.wasm.lower(bytes(w))
+            outcomes["ok"] += 1
+        except S.WasmLoweringError as e:
+            outcomes["invalid" if e.code == -1 else "tape"] += 1
+            assert e.code in (-1, -3) and str(e)
+    assert outcomes["invalid"] > 100 and sum(outcomes.values()) == 1500
 
 
 def test_traps_on_one_side_of_a_branch_are_dropped(S, oracle):
