@@ -97,6 +97,11 @@ int sdfgpu_slab(const sdfgpu_ctx* ctx, uint32_t* z_begin, uint32_t* z_end,
  * (SDFSurface::set_parameter, src/sdf/mod.rs:73). */
 int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes);
 
+/* Device-free validation of a tape (what sdfgpu_set_tape checks before it touches the device): header, section
+ * sizes, operand ranges, stack balance, scalar programs.  SDFGPU_OK or SDFGPU_ERR_TAPE / _INVALID with the
+ * reason in sdfgpu_last_error(NULL). */
+int sdfgpu_tape_validate(const void* tape, size_t tape_bytes);
+
 /* Device-free check of the specialiser: validates `tape`, lowers it and compiles the straight-line
  * fill kernel for its structure with NVRTC for sm_100a (what sdfgpu_set_tape + the first fill do on
  * a GPU box).  On success `log` receives the generated translation unit, on failure the compiler

@@ -91,6 +91,7 @@ SIGNATURES = {
     "sdfgpu_dims": (C.c_int, [_vp, _u32p]),
     "sdfgpu_slab": (C.c_int, [_vp, _u32p, _u32p, _u32p, _u32p]),
     "sdfgpu_set_tape": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "sdfgpu_tape_validate": (C.c_int, [_vp, C.c_size_t]),
     "sdfgpu_jit_check": (C.c_int, [_vp, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]),
     "sdfgpu_wasm_lower": (C.c_int, [_vp, C.c_size_t, _u32, _vp, C.c_size_t, C.POINTER(C.c_size_t), _fp, C.c_char_p, C.c_size_t]),
     "sdfgpu_update": (C.c_int, [_vp, _fp, _u32, _u64p]),

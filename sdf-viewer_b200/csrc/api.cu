@@ -844,6 +844,11 @@ SDFGPU_API int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_by
     return SDFGPU_OK;
 }
 
+SDFGPU_API int sdfgpu_tape_validate(const void* tape, size_t tape_bytes) {
+    ParsedTape pt;
+    return parse_and_lower(nullptr, tape, tape_bytes, &pt);
+}
+
 SDFGPU_API int sdfgpu_jit_check(const void* tape, size_t tape_bytes, int voxels_per_thread, char* log, size_t log_cap) {
     if (log && log_cap) log[0] = '\0';
     ParsedTape pt;

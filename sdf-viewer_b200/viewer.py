@@ -392,6 +392,14 @@ class SDFViewer:
         check(self._lib.sdfgpu_set_option(self._h, key.encode(), int(value)), self._h)
 
 
+def tape_validate(tape_bytes):
+    """Device-free validation of a tape; raises SdfGpuError with the reason."""
+    buf = (C.c_char * len(tape_bytes)).from_buffer_copy(tape_bytes) if len(tape_bytes) else None
+    rc = _lib.load().sdfgpu_tape_validate(buf, len(tape_bytes))
+    if rc != 0:
+        raise SdfGpuError(rc, _lib.load().sdfgpu_last_error(None).decode("utf-8", "replace"))
+
+
 def jit_check(tape_bytes, voxels_per_thread=2):
     """Compile the specialised fill kernel for this tape's structure with NVRTC (no GPU needed).
     Returns the generated translation unit; raises SdfGpuError with the compiler log on failure."""

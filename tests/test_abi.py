@@ -155,3 +155,35 @@ def test_plain_c_client_links_against_the_abi(S, tmp_path):
         assert out[1].startswith("-2 ") and "no CPU fallback" in out[1]
     else:
         assert out[1].startswith("0 ")
+
+
+def test_mutated_tapes_are_rejected_or_accepted_never_crash(S):
+    """Tapes are host input: random corruptions of valid tapes (primitive, CSG and scalar-program ones) go through
+    the validator without crashing; truncations are always rejected."""
+    T = S.tape
+    p = T.ScalarProgram()
+    x = p.px()
+    p.out(0, p.op("FSUB", p.op("FABS", x), p.const(0.5)))
+    t = T.TapeBuilder()
+    t.scalar(p).emit(T.OP_END)
+    seeds = [T.demo_tape(), T.csg_tape(T.csg_primitive_table(20)), t.build()]
+    for s in seeds:
+        S.tape_validate(s)
+    rng = np.random.default_rng(99)
+    rejected = 0
+    for it in range(6000):
+        w = bytearray(seeds[it % 3])
+        if it % 3 == 0:
+            w = w[:int(rng.integers(0, len(w)))]
+        else:
+            for _ in range(int(rng.integers(1, 5))):
+                w[int(rng.integers(0, len(w)))] = int(rng.integers(0, 256))
+        try:
+            S.tape_validate(bytes(w))
+        except S.SdfGpuError as e:
+            rejected += 1
+            assert e.code in (-1, -3)
+            assert it % 3 != 0 or e.code in (-1, -3)
+        else:
+            assert it % 3 != 0, "a truncated tape was accepted"
+    assert rejected > 2500
