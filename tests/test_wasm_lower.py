@@ -237,12 +237,56 @@ def ref_integer_checker(p):
     return o
 
 
+def guest_registry():
+    """What a Rust guest does before any arithmetic: look the sdf_id up in a registry (an i64 hash of the id picks a
+    bucket in memory), dispatch on the entry's kind with br_table, grow the memory for the result on first use,
+    narrow stores / sign-extending loads on the way.  All of it is concrete and must leave no trace in the tape."""
+    m = base_module()
+    BUCKETS = 8192
+    # hash(id) = ((id * 0x9E3779B97F4A7C15) rotl 17) >> 61  -> bucket 0..7; bucket for id 0 holds kind 2, radius 0.6
+    def hash_bucket(i):
+        h = (i * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+        h = ((h << 17) | (h >> 47)) & (2 ** 64 - 1)
+        return h >> 61
+    b0 = hash_bucket(0)
+    m.data_at(BUCKETS + 8 * b0, struct.pack("<hbbf", -2, 2, 0, 0.6))   # i16 tag -2, i8 kind 2, pad, f32 radius
+    ENTRY, PTR, KIND = ("local.get", 5), ("local.get", 6), ("local.get", 7)
+    body = [("local.get", 0), "i64.extend_i32_u", ("i64.const", 0x9E3779B97F4A7C15), "i64.mul", ("i64.const", 17), "i64.rotl",
+            ("i64.const", 61), "i64.shr_u", "i32.wrap_i64", ("i32.const", 8), "i32.mul", ("i32.const", BUCKETS), "i32.add", ("local.set", 5),
+            # the tag must be -2 (sign-extending 16-bit load), else trap
+            ENTRY, ("i32.load16_s", 0), ("i32.const", -2 & 0xFFFFFFFF), "i32.ne", ("if", []), "unreachable", "end",
+            ENTRY, ("i32.load8_u", 2), ("local.set", 7),
+            # result buffer: one fresh page
+            ("i32.const", 1), ("memory.grow",), ("i32.const", 16), "i32.shl", ("local.set", 6),
+            PTR, ("i32.const", 0x55), ("i32.store8", 3), PTR, ("i32.const", 0x1234), ("i32.store16", 0),   # scribbles overwritten below
+            ("block", []), ("block", []), ("block", []), KIND, ("br_table", [0, 1, 2], 0), "end",
+            PTR, ("f32.const", 111.0), ("f32.store", 0), ("br", 1), "end",
+            PTR, ("f32.const", 222.0), ("f32.store", 0), ("br", 0), "end"]
+    # kind 2 lands here with nothing stored yet: the sphere
+    body += [PTR, X, X, "f32.mul", Y, Y, "f32.mul", "f32.add", Z, Z, "f32.mul", "f32.add", "f32.sqrt", ENTRY, ("f32.load", 4), "f32.sub",
+             ("f32.store", 0)]
+    for k in range(1, 7):
+        body += [PTR, ("f32.const", 0.1 * k), ("f32.store", 4 * k)]
+    m.func(*SAMPLE_SIG, locals=[I32, I32, I32], body=body + [PTR], export="sample")
+    return m
+
+
+def ref_registry(p):
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    o = np.zeros((len(p), 7), f32)
+    o[:, 0] = np.sqrt((x * x + y * y) + z * z) - f32(0.6)
+    for k in range(1, 7):
+        o[:, k] = f32(0.1 * k)
+    return o
+
+
 GUESTS = {
     "sphere_static": (guest_sphere_static, ref_sphere_static),
     "box_branchy": (guest_box_branchy, ref_box_branchy),
     "csg_calls": (guest_csg_calls, ref_csg_calls),
     "early_returns": (guest_early_returns, ref_early_returns),
     "integer_checker": (guest_integer_checker, ref_integer_checker),
+    "registry": (guest_registry, ref_registry),
 }
 
 
