@@ -188,7 +188,7 @@ def host_sampled_path(orc, S, threads, side=256):
 
 
 def workload_name(workload, dims, W, H):
-    return (f"{'demo_sdf' if workload == 'demo' else 'csg_1k'} {dims[0]}x{dims[1]}x{dims[2]} "
+    return (f"{ {'demo': 'demo_sdf', 'csg': 'csg_1k', 'wasm': 'wasm guest (4 spheres) lowered to a scalar program'}[workload]} {dims[0]}x{dims[1]}x{dims[2]} "
             f"grid fill + {W}x{H} sphere trace, default scene camera")
 
 
@@ -239,7 +239,9 @@ def main():
     ap.add_argument("--grid", type=int, default=512, help="voxels per side owned by each GPU")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--workload", default="demo", choices=["demo", "csg"])
+    ap.add_argument("--workload", default="demo", choices=["demo", "csg", "wasm"],
+                    help="demo: SDFDemo (the headline); csg: 1000 primitives; wasm: a WebAssembly guest (union of four "
+                         "spheres, assembled by tests/test_wasm_lower.py) lowered to a scalar program by sdfgpu_wasm_lower")
     ap.add_argument("--vpt", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -268,7 +270,11 @@ def main():
     n_gpus = world
     dims = grid_for(n_gpus, args.grid)
     W, H = args.width, args.height
-    tape = S.tape.demo_tape() if args.workload == "demo" else S.tape.csg_tape()
+    if args.workload == "wasm":
+        import test_wasm_lower  # test infrastructure: the guest module is assembled there (no WASM toolchain here)
+        tape, _, lowering = S.wasm.lower(test_wasm_lower.guest_csg_calls().build())
+    else:
+        tape = S.tape.demo_tape() if args.workload == "demo" else S.tape.csg_tape()
     cam = S.default_camera(W, H)
 
     from sdf_viewer_b200.sharded import ShardedViewer

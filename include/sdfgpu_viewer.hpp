@@ -299,6 +299,30 @@ class SDFViewer {
 
 // ---------------------------------------------------------------- tape (include/sdfgpu_tape.h)
 
+// A scalar program (sdft_sop run, include/sdfgpu_tape.h): straight-line SSA arithmetic with WebAssembly's
+// numerics.  Each call appends one op and returns the index of its value; TapeBuilder::scalar places it.
+class ScalarProgram {
+   public:
+    uint32_t op(uint32_t code, uint32_t a = 0, uint32_t b = 0, uint32_t c = 0) {
+        ops_.push_back(sdft_sop{code, a, b, c});
+        return (uint32_t)ops_.size() - 1;
+    }
+    uint32_t px() { return op(SDFT_S_PX); }
+    uint32_t py() { return op(SDFT_S_PY); }
+    uint32_t pz() { return op(SDFT_S_PZ); }
+    uint32_t constant(float v) {  // runtime data of the tape: a new value keeps the compiled kernel
+        consts_.push_back(v);
+        return op(SDFT_S_CONST, (uint32_t)consts_.size() - 1);
+    }
+    uint32_t imm(uint32_t word) { return op(SDFT_S_IMM, word); }
+    uint32_t out(uint32_t channel, uint32_t value) { return op(SDFT_S_OUT, value, channel); }
+
+   private:
+    friend class TapeBuilder;
+    std::vector<sdft_sop> ops_;
+    std::vector<float> consts_;
+};
+
 class TapeBuilder {
    public:
     uint32_t prim(uint32_t shape, Vector3 center, float size, uint32_t material = SDFT_MAT_FLAT,
@@ -322,13 +346,25 @@ class TapeBuilder {
         instr_.push_back(sdft_instr{op, a, b, imm});
         return *this;
     }
+    TapeBuilder& scalar(const ScalarProgram& p) {  // append the program and the SDFT_OP_SCALAR that runs it
+        const uint32_t first = (uint32_t)sops_.size();
+        for (sdft_sop o : p.ops_) {
+            if (o.op == SDFT_S_CONST) {
+                consts_.push_back(p.consts_[o.a]);
+                o.a = (uint32_t)consts_.size() - 1;
+            }
+            sops_.push_back(o);
+        }
+        return emit(SDFT_OP_SCALAR, first, (uint32_t)p.ops_.size());
+    }
     std::vector<unsigned char> build() const {
         sdft_header h;
         std::memset(&h, 0, sizeof h);
         h.magic = SDFT_MAGIC; h.version = SDFT_VERSION;
         h.n_instr = (uint32_t)instr_.size(); h.n_prims = (uint32_t)prims_.size(); h.n_consts = (uint32_t)consts_.size();
+        h.reserved[0] = (uint32_t)sops_.size();
         std::vector<unsigned char> out(sizeof h + instr_.size() * sizeof(sdft_instr) + prims_.size() * sizeof(sdft_prim) +
-                                       consts_.size() * sizeof(float));
+                                       consts_.size() * sizeof(float) + sops_.size() * sizeof(sdft_sop));
         unsigned char* p = out.data();
         std::memcpy(p, &h, sizeof h); p += sizeof h;
         if (!instr_.empty()) std::memcpy(p, instr_.data(), instr_.size() * sizeof(sdft_instr));
@@ -336,6 +372,8 @@ class TapeBuilder {
         if (!prims_.empty()) std::memcpy(p, prims_.data(), prims_.size() * sizeof(sdft_prim));
         p += prims_.size() * sizeof(sdft_prim);
         if (!consts_.empty()) std::memcpy(p, consts_.data(), consts_.size() * sizeof(float));
+        p += consts_.size() * sizeof(float);
+        if (!sops_.empty()) std::memcpy(p, sops_.data(), sops_.size() * sizeof(sdft_sop));
         return out;
     }
 
@@ -343,6 +381,7 @@ class TapeBuilder {
     std::vector<sdft_instr> instr_;
     std::vector<sdft_prim> prims_;
     std::vector<float> consts_;
+    std::vector<sdft_sop> sops_;
 };
 
 // SDFDemo (src/sdf/demo/mod.rs:20-75) as a surface that lowers itself to a tape: an L-inf cube with a

@@ -4,6 +4,7 @@
 //
 //   host_viewer loading          CPU: the five loading.rs cases
 //   host_viewer tape             CPU: hex dump of sdfgpu::SDFDemo's tape (compared with tape.py's)
+//   host_viewer scalar           CPU: hex dump of a scalar-program tape built with sdfgpu::ScalarProgram
 //   host_viewer wasm <file>      CPU: sdfgpu::WasmSDF lowers a WebAssembly SDF; prints the summary, bounding box, tape
 //   host_viewer gpu <out_dir>    GPU: (1) the demo surface with a tape, (2) a surface WITHOUT a tape whose
 //                                sample() is the oracle's SDFDemo::sample; volumes and a frame are
@@ -181,6 +182,39 @@ int main(int argc, char** argv) {
             return 2;
         }
     }
+    if (mode == "scalar") {  // CPU: the banded sphere of tests/test_scalar_programs.py written with sdfgpu::ScalarProgram
+        sdfgpu::ScalarProgram p;
+        const uint32_t x = p.px(), y = p.py(), z = p.pz();
+        // one statement per op: C++ does not order the evaluation of nested call arguments
+        const uint32_t xx = p.op(SDFT_S_FMUL, x, x), yy = p.op(SDFT_S_FMUL, y, y);
+        const uint32_t s2 = p.op(SDFT_S_FADD, xx, yy);
+        const uint32_t zz = p.op(SDFT_S_FMUL, z, z);
+        const uint32_t len = p.op(SDFT_S_FSQRT, p.op(SDFT_S_FADD, s2, zz));
+        const uint32_t radius = p.constant(0.7f);
+        const uint32_t d = p.op(SDFT_S_FSUB, len, radius);
+        const uint32_t eight = p.constant(8.0f);
+        const uint32_t cell = p.op(SDFT_S_I_FROM_F_S, p.op(SDFT_S_FFLOOR, p.op(SDFT_S_FMUL, y, eight)));
+        const uint32_t one = p.imm(1);
+        const uint32_t band = p.op(SDFT_S_IAND, cell, one);
+        p.out(0, d);
+        const uint32_t hi = p.constant(0.9f), lo = p.constant(0.1f);
+        p.out(1, p.op(SDFT_S_SELECT, band, hi, lo));
+        p.out(2, p.op(SDFT_S_FABS, x));
+        const uint32_t zero = p.constant(0.0f);
+        const uint32_t zc = p.op(SDFT_S_FMAX, z, zero);
+        const uint32_t fone = p.constant(1.0f);
+        p.out(3, p.op(SDFT_S_FMIN, zc, fone));
+        p.out(4, p.constant(0.25f));
+        p.out(5, p.constant(0.5f));
+        p.out(6, p.constant(1.0f));
+        sdfgpu::TapeBuilder t;
+        t.scalar(p).emit(SDFT_OP_END);
+        const std::vector<unsigned char> tape = t.build();
+        REQUIRE(sdfgpu_tape_validate(tape.data(), tape.size()) == SDFGPU_OK);
+        for (unsigned char c : tape) std::printf("%02x", c);
+        std::printf("\n");
+        return 0;
+    }
     if (mode == "wasm" && argc > 2) {  // CPU: lower a .wasm SDF through sdfgpu::WasmSDF, print its tape as hex
         FILE* f = std::fopen(argv[2], "rb");
         REQUIRE(f != nullptr);
@@ -200,6 +234,6 @@ int main(int argc, char** argv) {
             return 3;
         }
     }
-    std::fprintf(stderr, "usage: host_viewer loading | tape [nosphere] | wasm <file.wasm> | gpu <out_dir>\n");
+    std::fprintf(stderr, "usage: host_viewer loading | tape [nosphere] | scalar | wasm <file.wasm> | gpu <out_dir>\n");
     return 64;
 }

@@ -38,6 +38,13 @@ def test_cpp_demo_tape_equals_python_tape(S, host_viewer):
         assert bytes.fromhex(r.stdout.strip()) == want
 
 
+def test_cpp_scalar_program_equals_python(S, host_viewer):
+    import test_scalar_programs as P
+    r = subprocess.run([host_viewer, "scalar"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert bytes.fromhex(r.stdout.strip()) == P.build_tape(S.tape, P.sphere_with_bands(S.tape))[1]
+
+
 def test_cpp_wasm_sdf_lowers_like_python(S, host_viewer, tmp_path):
     """sdfgpu::WasmSDF (C++) and sdf_viewer_b200.WasmSDF (Python) are the same call into the library."""
     import test_wasm_lower as W
