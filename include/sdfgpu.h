@@ -126,6 +126,16 @@ int sdfgpu_jit_check(const void* tape, size_t tape_bytes, int voxels_per_thread,
 int sdfgpu_wasm_lower(const void* wasm, size_t wasm_bytes, uint32_t sdf_id, void* tape_out, size_t tape_cap,
                       size_t* tape_len, float bb_out[6], char* log, size_t log_cap);
 
+/* The same for a LIVE instance: `memory` is a copy of the guest's linear memory as the host's runtime holds it
+ * now (wasmer: `memory.view(&store)`), i.e. after `init()` and after whatever `set_parameter` calls were made
+ * (src/sdf/wasm/native.rs:386-460 forwards them to the guest, which keeps its parameters in its own memory).
+ * It replaces instantiation, so the tape reflects the current parameters; after the guest's `changed()`
+ * reports a box (native.rs:463-483), lower again and hand the new tape to the viewer -- same structure, new
+ * constants, same compiled kernel.  memory_bytes must be a multiple of 65536. */
+int sdfgpu_wasm_lower_live(const void* wasm, size_t wasm_bytes, const void* memory, size_t memory_bytes,
+                           uint32_t sdf_id, void* tape_out, size_t tape_cap, size_t* tape_len, float bb_out[6],
+                           char* log, size_t log_cap);
+
 /* SDFViewer::update (src/app/scene/sdf/mod.rs:128-217).
  *   changed_box : result of sdf.changed() this frame ({min,max}), or NULL for None;
  *                 merged into the pending box as :131-139 does.

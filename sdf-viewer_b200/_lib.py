@@ -94,6 +94,8 @@ SIGNATURES = {
     "sdfgpu_tape_validate": (C.c_int, [_vp, C.c_size_t]),
     "sdfgpu_jit_check": (C.c_int, [_vp, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t]),
     "sdfgpu_wasm_lower": (C.c_int, [_vp, C.c_size_t, _u32, _vp, C.c_size_t, C.POINTER(C.c_size_t), _fp, C.c_char_p, C.c_size_t]),
+    "sdfgpu_wasm_lower_live": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t, _u32, _vp, C.c_size_t, C.POINTER(C.c_size_t), _fp,
+                                         C.c_char_p, C.c_size_t]),
     "sdfgpu_update": (C.c_int, [_vp, _fp, _u32, _u64p]),
     "sdfgpu_update_surface": (C.c_int, [_vp, C.POINTER(Surface), C.c_double, _u64p]),
     "sdfgpu_fill_all": (C.c_int, [_vp]),

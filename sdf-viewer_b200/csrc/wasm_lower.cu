@@ -1317,9 +1317,8 @@ void put_log(char* log, size_t cap, const std::string& s) {
 
 }  // namespace
 
-extern "C" __attribute__((visibility("default"))) int sdfgpu_wasm_lower(const void* wasm, size_t wasm_bytes, uint32_t sdf_id,
-                                                                          void* tape_out, size_t tape_cap, size_t* tape_len,
-                                                                          float bb_out[6], char* log, size_t log_cap) {
+static int lower_impl(const void* wasm, size_t wasm_bytes, const void* memory, size_t memory_bytes, uint32_t sdf_id,
+                      void* tape_out, size_t tape_cap, size_t* tape_len, float bb_out[6], char* log, size_t log_cap) {
     if (log && log_cap) log[0] = '\0';
     if (tape_len) *tape_len = 0;
     if (!wasm || !wasm_bytes) { put_log(log, log_cap, "wasm is NULL or empty"); return SDFGPU_ERR_INVALID; }
@@ -1352,12 +1351,24 @@ extern "C" __attribute__((visibility("default"))) int sdfgpu_wasm_lower(const vo
         }
     }
     std::vector<Val> res;
-    // instantiate: start function, then the optional init() (native.rs:52-56)
-    if (L.m.start >= 0 && !L.call_concrete((uint32_t)L.m.start, {}, nullptr)) { put_log(log, log_cap, "start: " + L.err); return SDFGPU_ERR_TAPE; }
-    if (find_func("init", &f_tmp) && L.m.types[L.m.funcs[f_tmp].type].params.empty() &&
-        !L.call_concrete(f_tmp, {}, nullptr)) {
-        put_log(log, log_cap, "init: " + L.err);
-        return SDFGPU_ERR_TAPE;
+    if (memory) {
+        // a live instance's linear memory (after init() and whatever set_parameter calls the host made): it
+        // replaces instantiation.  Globals keep their initial values -- the ones a guest mutates across calls
+        // (the shadow stack pointer) are restored by every export before it returns.
+        if (memory_bytes == 0 || memory_bytes % 65536 || memory_bytes / 65536 > 16384) {
+            put_log(log, log_cap, "the memory snapshot is not a whole number of 64 KiB pages");
+            return SDFGPU_ERR_INVALID;
+        }
+        L.m.base.assign((const uint8_t*)memory, (const uint8_t*)memory + memory_bytes);
+        L.m.mem_pages = (uint32_t)(memory_bytes / 65536);
+    } else {
+        // instantiate: start function, then the optional init() (native.rs:52-56)
+        if (L.m.start >= 0 && !L.call_concrete((uint32_t)L.m.start, {}, nullptr)) { put_log(log, log_cap, "start: " + L.err); return SDFGPU_ERR_TAPE; }
+        if (find_func("init", &f_tmp) && L.m.types[L.m.funcs[f_tmp].type].params.empty() &&
+            !L.call_concrete(f_tmp, {}, nullptr)) {
+            put_log(log, log_cap, "init: " + L.err);
+            return SDFGPU_ERR_TAPE;
+        }
     }
     // bounding_box(sdf_id) -> *[f32; 6] (src/sdf/ffi.rs:42-50, native.rs:163-186)
     if (!L.call_concrete(f_bb, {Lowerer::conc(T_I32, sdf_id)}, &res) || res.size() != 1) {
@@ -1485,4 +1496,21 @@ extern "C" __attribute__((visibility("default"))) int sdfgpu_wasm_lower(const vo
         put_log(log, log_cap, buf);
     }
     return SDFGPU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int sdfgpu_wasm_lower(const void* wasm, size_t wasm_bytes, uint32_t sdf_id,
+                                                                          void* tape_out, size_t tape_cap, size_t* tape_len,
+                                                                          float bb_out[6], char* log, size_t log_cap) {
+    return lower_impl(wasm, wasm_bytes, nullptr, 0, sdf_id, tape_out, tape_cap, tape_len, bb_out, log, log_cap);
+}
+
+extern "C" __attribute__((visibility("default"))) int sdfgpu_wasm_lower_live(const void* wasm, size_t wasm_bytes, const void* memory,
+                                                                               size_t memory_bytes, uint32_t sdf_id, void* tape_out,
+                                                                               size_t tape_cap, size_t* tape_len, float bb_out[6],
+                                                                               char* log, size_t log_cap) {
+    if (!memory) {
+        if (log && log_cap) snprintf(log, log_cap, "memory is NULL");
+        return SDFGPU_ERR_INVALID;
+    }
+    return lower_impl(wasm, wasm_bytes, memory, memory_bytes, sdf_id, tape_out, tape_cap, tape_len, bb_out, log, log_cap);
 }

@@ -317,6 +317,36 @@ def test_parameter_change_keeps_the_structure(S, oracle):
     assert same(oracle.tape_sample(tb, p)[:, 0], np.sqrt((p[:, 0] ** 2 + p[:, 1] ** 2) + p[:, 2] ** 2).astype(f32) - f32(0.55))
 
 
+def test_lowering_a_live_instance(S, oracle):
+    """sdfgpu_wasm_lower_live takes the linear memory of a running instance, so a parameter the host changed
+    through the guest's set_parameter (which lands in guest memory) shows up in the tape.  The "live" memory is
+    built here by applying the module's data segments and then poking the radius, as set_parameter would."""
+    m = guest_sphere_static()
+    wasm = m.build()
+    mem = bytearray(65536)
+    for off, payload in m.data:
+        mem[off:off + len(payload)] = payload
+    fresh = S.wasm.lower(wasm)[0]
+    assert S.wasm.lower(wasm, memory=bytes(mem))[0] == fresh          # an untouched instance lowers like the module
+    mem[512:516] = struct.pack("<f", 0.45)                            # set_parameter(radius = 0.45)
+    tape, bb, _ = S.wasm.lower(wasm, memory=bytes(mem))
+    p = points(60)
+    assert bb == BB and len(tape) == len(fresh)
+    assert same(oracle.tape_sample(tape, p)[:, 0], np.sqrt((p[:, 0] ** 2 + p[:, 1] ** 2) + p[:, 2] ** 2).astype(f32) - f32(0.45))
+    # csg guest: init() already ran in the live instance (the sphere count is in memory), it must not be needed again
+    g = guest_csg_calls()
+    mem = bytearray(65536)
+    for off, payload in g.data:
+        mem[off:off + len(payload)] = payload
+    mem[4000:4004] = struct.pack("<I", 2)                             # a live instance that holds only two spheres
+    tape2 = S.wasm.lower(g.build(), memory=bytes(mem))[0]
+    best = np.minimum(*[np.sqrt(((p[:, 0] - f32(cx)) ** 2 + (p[:, 1] - f32(cy)) ** 2) + (p[:, 2] - f32(cz)) ** 2).astype(f32) - f32(r)
+                        for cx, cy, cz, r, _ in SPHERES[:2]])
+    assert same(oracle.tape_sample(tape2, p)[:, 0], best)
+    with pytest.raises(S.WasmLoweringError):
+        S.wasm.lower(wasm, memory=b"\0" * 1000)                      # not whole pages
+
+
 def test_wasm_sdf_surface(S):
     sdf = S.WasmSDF(guest_box_branchy().build())
     assert sdf.bounding_box() == BB and sdf.changed() is None
