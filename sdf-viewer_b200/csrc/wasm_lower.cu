@@ -199,16 +199,16 @@ struct Lowerer {
             return 0;
         }
         int64_t sleb() {
-            int64_t r = 0;
+            uint64_t r = 0;
             int shift = 0;
             uint8_t b;
             do {
                 b = u8();
-                if (shift < 64) r |= (int64_t)(b & 0x7f) << shift;
+                if (shift < 64) r |= (uint64_t)(b & 0x7f) << shift;
                 shift += 7;
             } while ((b & 0x80) && ok && shift < 77);
-            if (shift < 64 && (b & 0x40)) r |= -((int64_t)1 << shift);
-            return r;
+            if (shift < 64 && (b & 0x40)) r |= ~(uint64_t)0 << shift;
+            return (int64_t)r;
         }
         uint32_t u32() { return (uint32_t)uleb(); }
         std::string name() {
