@@ -15,6 +15,7 @@ N_F, N_I = 5, 3                      # scratch locals: f32 at 5..9, i32 at 10..1
 F_LOCALS = list(range(5, 5 + N_F))
 I_LOCALS = list(range(5 + N_F, 5 + N_F + N_I))
 CONSTS = [0.0, 0.25, 0.5, 1.0, -0.75, 2.0, 3.5, -0.125, 8.0, 0.1]
+SCRATCH = [3000, 3004, 3008, 3012]   # guest memory the statements spill to and the expressions read back
 
 
 class Gen:
@@ -28,7 +29,9 @@ class Gen:
 
     # ---- expressions
     def fexpr(self, d=0):
-        r = self.rng.integers(0, 12 if d < 3 else 4)
+        r = self.rng.integers(0, 13 if d < 3 else 4)
+        if r == 12:
+            return [("i32.const", self.pick(SCRATCH)), ("f32.load", 0)]
         if r == 0:
             return [("local.get", self.pick([1, 2, 3]))]
         if r == 1:
@@ -86,6 +89,8 @@ class Gen:
     def stmt(self, d):
         r = self.rng.integers(0, 10)
         can_fork = self.forks < 7 and d < 3
+        if r == 0:  # spill to guest memory (on this path only, when inside a branch)
+            return [("i32.const", self.pick(SCRATCH))] + self.fexpr() + [("f32.store", 0)]
         if r < 3 or not can_fork and r >= 5:
             return self.fexpr() + [("local.set", self.pick(F_LOCALS))]
         if r == 3:
