@@ -102,6 +102,8 @@ enum sdft_sop_op {
     SDFT_S_FNEAREST = 14,
     SDFT_S_FADD = 16, SDFT_S_FSUB = 17, SDFT_S_FMUL = 18, SDFT_S_FDIV = 19, SDFT_S_FMIN = 20, SDFT_S_FMAX = 21,
     SDFT_S_FCOPYSIGN = 22,
+    SDFT_S_FMOD = 23,      /* C fmodf: the exact remainder of a / b with the sign of a (Rust's `%`, which a WASM guest reaches
+                              through its libm; not a WebAssembly instruction)                                              */
     /* f32 x f32 -> 0 / 1 */
     SDFT_S_FEQ = 24, SDFT_S_FNE = 25, SDFT_S_FLT = 26, SDFT_S_FGT = 27, SDFT_S_FLE = 28, SDFT_S_FGE = 29,
     /* i32 */

@@ -262,6 +262,7 @@ void run_scalar_program(const Tape& t, uint32_t first, uint32_t count, V3 p, Sam
             case SDFT_S_FMIN: r = f2w(wasm_fmin(fa, fb)); break;
             case SDFT_S_FMAX: r = f2w(wasm_fmax(fa, fb)); break;
             case SDFT_S_FCOPYSIGN: r = (a & 0x7fffffffu) | (b & 0x80000000u); break;
+            case SDFT_S_FMOD: r = f2w(fmodf(fa, fb)); break;  // exact by definition (cube.rs:192 `%`)
             case SDFT_S_FEQ: r = fa == fb; break;
             case SDFT_S_FNE: r = fa != fb; break;
             case SDFT_S_FLT: r = fa < fb; break;

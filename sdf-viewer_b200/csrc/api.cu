@@ -736,7 +736,7 @@ int parse_and_lower(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes, Parsed
                             break;
                         case SDFT_S_SELECT: n_in = 3; break;
                         default:
-                            if ((o.op >= SDFT_S_FADD && o.op <= SDFT_S_FCOPYSIGN) || (o.op >= SDFT_S_FEQ && o.op <= SDFT_S_FGE) ||
+                            if ((o.op >= SDFT_S_FADD && o.op <= SDFT_S_FMOD) || (o.op >= SDFT_S_FEQ && o.op <= SDFT_S_FGE) ||
                                 (o.op >= SDFT_S_IADD && o.op <= SDFT_S_ISHR_S) || (o.op >= SDFT_S_IEQ && o.op <= SDFT_S_IGE_U)) {
                                 n_in = 2;
                                 break;

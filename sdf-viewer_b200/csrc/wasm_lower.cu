@@ -10,7 +10,8 @@
 // A branch on a symbolic condition forks the execution; the paths' results (the seven floats each leaves in
 // guest memory) are merged with selects, so the tape is branch free.  What cannot be expressed makes the
 // lowering fail with a message (symbolic addresses or loop bounds, i64 / f64 arithmetic on symbolic values,
-// host imports, SIMD): the caller then samples that SDF on the host (sdfgpu_update_surface).
+// host imports, SIMD): the caller then samples that SDF on the host (sdfgpu_update_surface).  The guest's libm
+// fmodf (what `%` on floats calls) is recognised by what it computes and becomes one op (behaves_like_fmodf).
 //
 // A small, self-contained interpreter of the WebAssembly MVP (+ sign extension, saturating truncation, bulk
 // memory copy / fill) follows; it validates nothing beyond what it needs to run safely.
@@ -129,6 +130,8 @@ struct Lowerer {
     uint32_t leaves = 0;
     uint32_t fork_depth = 0;  // symbolic branches open on the current path (run() recurses once per branch)
     bool malformed = false;
+    std::map<uint32_t, int> libm_class;  // function index -> 0 unknown, 1 behaves exactly like C fmodf
+    uint32_t recognised_calls = 0;
 
     bool fail(const char* fmt, ...) {
         if (err.empty()) {
@@ -912,6 +915,69 @@ struct Lowerer {
 
     typedef Leaf (*FinishFn)(Lowerer&, State&);
 
+    // A guest reaches `%` on floats through its libm's fmodf: an integer loop over the operands' exponents whose
+    // trip count depends on the position, so it cannot be unrolled.  But fmodf is an EXACT function, so a callee
+    // can be recognised by what it computes: a (f32, f32) -> f32 function that returns C's fmodf bit for bit on a
+    // grid of probes (signed zeros, denormals, huge ratios, infinities, NaN) is one, whatever its instructions
+    // are, and a call of it with symbolic arguments becomes one SDFT_S_FMOD op.
+    bool behaves_like_fmodf(const State& at, uint32_t fi) {
+        auto it = libm_class.find(fi);
+        if (it != libm_class.end()) return it->second == 1;
+        static const float xs[] = {0.0f, -0.0f, 1.0f, -1.0f, 0.3f, 5.5f, -7.25f, 1e-3f, 123456.7f, 1e30f, -1e-30f, 1e-40f, 0.75f, 2.5f,
+                                   16777216.0f, -3.4e38f, 0.1f};
+        static const float ys[] = {0.5f, 0.25f, 1.0f, 3.0f, -2.0f, 0.1f, 1e-40f, 1e30f, 0.0f, -0.0f, 7.0f, 1.17549435e-38f};
+        std::vector<std::pair<float, float>> probes;
+        for (float x : xs) for (float y : ys) probes.push_back(std::make_pair(x, y));
+        const float inf = f32_of(0x7f800000u), nan = f32_of(0x7fc00000u);
+        const std::pair<float, float> special[] = {{inf, 1.0f}, {-inf, 2.0f}, {1.0f, inf}, {-2.5f, -inf}, {nan, 1.0f}, {1.0f, nan}, {inf, inf}};
+        for (const auto& pr : special) probes.push_back(pr);
+        // the probes must not disturb the lowering in progress
+        const std::string saved_err = err;
+        const uint64_t saved_budget = budget;
+        const uint32_t saved_leaves = leaves, saved_depth = fork_depth;
+        bool same = true;
+        for (size_t k = 0; k < probes.size() && same; ++k) {
+            State t;
+            t.globals = at.globals;
+            t.mem = at.mem;
+            t.pages = at.pages;
+            t.stack.push_back(conc(T_F32, bits_of(probes[k].first)));
+            t.stack.push_back(conc(T_F32, bits_of(probes[k].second)));
+            err.clear();
+            budget = 200000;  // a real fmodf needs a few thousand instructions at most
+            fork_depth = 0;
+            Leaf l;
+            if (!enter(t, fi)) { same = false; break; }
+            l = run(t, [](Lowerer&, State& s) { Leaf o; o.vals = s.stack; return o; });
+            if (l.st != ST_OK || l.vals.size() != 1 || l.vals[0].sym) { same = false; break; }
+            const float want = fmodf(probes[k].first, probes[k].second);
+            const float got = f32_of(l.vals[0].bits);
+            same = (got != got && want != want) || bits_of(got) == bits_of(want);
+        }
+        err = saved_err;
+        budget = saved_budget;
+        leaves = saved_leaves;
+        fork_depth = saved_depth;
+        libm_class[fi] = same ? 1 : 0;
+        return same;
+    }
+
+    // true when the call was replaced by one op (the two arguments are popped, the result pushed)
+    bool call_as_known_function(State& st, uint32_t fi) {
+        if (fi >= m.funcs.size() || m.funcs[fi].imported) return false;
+        const FuncType& ft = m.types[m.funcs[fi].type];
+        if (ft.params != std::vector<uint8_t>{T_F32, T_F32} || ft.results != std::vector<uint8_t>{T_F32} || st.stack.size() < 2) return false;
+        const Val& b = st.stack[st.stack.size() - 1];
+        const Val& a = st.stack[st.stack.size() - 2];
+        if (!a.sym && !b.sym) return false;  // concrete arguments: just run it
+        if (!behaves_like_fmodf(st, fi)) return false;
+        const uint32_t n = node(SDFT_S_FMOD, node_of(a), node_of(b));
+        st.stack.resize(st.stack.size() - 2);
+        st.stack.push_back(symv(T_F32, n));
+        ++recognised_calls;
+        return true;
+    }
+
     Leaf merge(uint32_t cond_node, const Leaf& a, const Leaf& b) {
         if (a.st == ST_FAIL || b.st == ST_FAIL) { Leaf l; l.st = ST_FAIL; return l; }
         if (a.st == ST_TRAP) return b;  // the guest would have trapped on that side: nothing to preserve
@@ -1072,6 +1138,7 @@ struct Lowerer {
                 case 0x10: {
                     const uint32_t fi = r.u32();
                     ADVANCE();
+                    if (call_as_known_function(st, fi)) break;
                     if (!enter(st, fi)) return failed();
                     break;
                 }
@@ -1089,6 +1156,7 @@ struct Lowerer {
                     if (fi >= m.funcs.size() || ti >= m.types.size()) return trapped();
                     const FuncType &want = m.types[ti], &have = m.types[m.funcs[fi].type];
                     if (want.params != have.params || want.results != have.results) return trapped();
+                    if (call_as_known_function(st, fi)) break;
                     if (!enter(st, fi)) return failed();
                     break;
                 }
@@ -1491,8 +1559,12 @@ static int lower_impl(const void* wasm, size_t wasm_bytes, const void* memory, s
     }
     {
         char buf[200];
-        snprintf(buf, sizeof buf, "lowered: %zu scalar ops, %zu constants, %u symbolic branches merged", sops.size(), used_consts.size(),
-                 L.leaves);
+        if (L.recognised_calls)
+            snprintf(buf, sizeof buf, "lowered: %zu scalar ops, %zu constants, %u symbolic branches merged, %u fmodf calls recognised",
+                     sops.size(), used_consts.size(), L.leaves, L.recognised_calls);
+        else
+            snprintf(buf, sizeof buf, "lowered: %zu scalar ops, %zu constants, %u symbolic branches merged", sops.size(),
+                     used_consts.size(), L.leaves);
         put_log(log, log_cap, buf);
     }
     return SDFGPU_OK;

@@ -28,7 +28,7 @@ OP_SCALAR = 40
 S = {name: code for name, code in dict(
     PX=0, PY=1, PZ=2, CONST=3, IMM=4,
     FNEG=8, FABS=9, FSQRT=10, FFLOOR=11, FCEIL=12, FTRUNC=13, FNEAREST=14,
-    FADD=16, FSUB=17, FMUL=18, FDIV=19, FMIN=20, FMAX=21, FCOPYSIGN=22,
+    FADD=16, FSUB=17, FMUL=18, FDIV=19, FMIN=20, FMAX=21, FCOPYSIGN=22, FMOD=23,
     FEQ=24, FNE=25, FLT=26, FGT=27, FLE=28, FGE=29,
     IADD=32, ISUB=33, IMUL=34, IAND=35, IOR=36, IXOR=37, ISHL=38, ISHR_U=39, ISHR_S=40,
     IEQ=44, INE=45, ILT_S=46, ILT_U=47, IGT_S=48, IGT_U=49, ILE_S=50, ILE_U=51, IGE_S=52, IGE_U=53, IEQZ=54,

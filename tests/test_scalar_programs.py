@@ -72,6 +72,8 @@ def ref_eval(ops, consts, p):
                     r = f2w(min(fa, fb) if name == "FMIN" else max(fa, fb))
             elif name == "FCOPYSIGN":
                 r = (A & 0x7FFFFFFF) | (B & 0x80000000)
+            elif name == "FMOD":
+                r = f2w(np.fmod(fa, fb))
             elif name in ("FEQ", "FNE", "FLT", "FGT", "FLE", "FGE"):
                 r = int({"FEQ": fa == fb, "FNE": fa != fb, "FLT": fa < fb, "FGT": fa > fb, "FLE": fa <= fb, "FGE": fa >= fb}[name])
             elif name == "IADD":
@@ -127,13 +129,13 @@ def _names(S):
 
 UNARY = ["FNEG", "FABS", "FSQRT", "FFLOOR", "FCEIL", "FTRUNC", "FNEAREST", "IEQZ", "F_FROM_I_S", "F_FROM_I_U", "I_FROM_F_S",
          "I_FROM_F_U"]
-BINARY = ["FADD", "FSUB", "FMUL", "FDIV", "FMIN", "FMAX", "FCOPYSIGN", "FEQ", "FNE", "FLT", "FGT", "FLE", "FGE", "IADD", "ISUB",
+BINARY = ["FADD", "FSUB", "FMUL", "FDIV", "FMIN", "FMAX", "FCOPYSIGN", "FMOD", "FEQ", "FNE", "FLT", "FGT", "FLE", "FGE", "IADD", "ISUB",
           "IMUL", "IAND", "IOR", "IXOR", "ISHL", "ISHR_U", "ISHR_S", "IEQ", "INE", "ILT_S", "ILT_U", "IGT_S", "IGT_U", "ILE_S",
           "ILE_U", "IGE_S", "IGE_U"]
 SPECIAL = [0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 1.5, 2.5, -2.5, 3.0e9, -3.0e9, 5.0e9, np.inf, -np.inf, np.nan, 1e-40, 16777217.0]
 
 
-FLOAT_ARITH = {"FSQRT", "FFLOOR", "FCEIL", "FTRUNC", "FNEAREST", "FADD", "FSUB", "FMUL", "FDIV", "FMIN", "FMAX", "F_FROM_I_S",
+FLOAT_ARITH = {"FSQRT", "FFLOOR", "FCEIL", "FTRUNC", "FNEAREST", "FADD", "FSUB", "FMUL", "FDIV", "FMIN", "FMAX", "FMOD", "F_FROM_I_S",
                "F_FROM_I_U"}
 
 

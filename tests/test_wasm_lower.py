@@ -280,6 +280,74 @@ def ref_registry(p):
     return o
 
 
+def add_musl_fmodf(m):
+    """compiler-builtins / musl `fmodf` written out in WebAssembly: what a Rust guest's `a % b` on f32 calls.  Its main
+    loop runs (exponent of x - exponent of y) times, so it cannot be unrolled for a symbolic x."""
+    G = lambda k: ("local.get", k)      # noqa: E731   locals: 0 x, 1 y, 2 uxi, 3 uyi, 4 ex, 5 ey, 6 sx, 7 i
+    S_ = lambda k: ("local.set", k)     # noqa: E731
+    C = lambda v: ("i32.const", v)      # noqa: E731
+    zero_times_x = [("f32.const", 0.0), G(0), "f32.mul", "return"]
+
+    def normalize(u, e):
+        return [G(e), "i32.eqz", ("if", []),
+                G(u), C(9), "i32.shl", S_(7),
+                ("block", []), ("loop", []), G(7), C(31), "i32.shr_u", ("br_if", 1),
+                G(e), C(1), "i32.sub", S_(e), G(7), C(1), "i32.shl", S_(7), ("br", 0), "end", "end",
+                G(u), C(1), G(e), "i32.sub", "i32.shl", S_(u),
+                "else", G(u), C(0x007FFFFF), "i32.and", C(0x00800000), "i32.or", S_(u), "end"]
+
+    def subtract_step():
+        return [G(2), G(3), "i32.sub", S_(7), G(7), C(31), "i32.shr_u", "i32.eqz", ("if", []),
+                G(7), "i32.eqz", ("if", [])] + zero_times_x + ["end", G(7), S_(2), "end"]
+
+    body = [G(0), "i32.reinterpret_f32", S_(2), G(1), "i32.reinterpret_f32", S_(3),
+            G(2), C(23), "i32.shr_u", C(255), "i32.and", S_(4), G(3), C(23), "i32.shr_u", C(255), "i32.and", S_(5),
+            G(2), C(0x80000000), "i32.and", S_(6),
+            G(3), C(1), "i32.shl", "i32.eqz", G(1), G(1), "f32.ne", "i32.or", G(4), C(255), "i32.eq", "i32.or", ("if", []),
+            G(0), G(1), "f32.mul", G(0), G(1), "f32.mul", "f32.div", "return", "end",
+            G(2), C(1), "i32.shl", G(3), C(1), "i32.shl", "i32.le_u", ("if", []),
+            G(2), C(1), "i32.shl", G(3), C(1), "i32.shl", "i32.eq", ("if", [])] + zero_times_x + ["end", G(0), "return", "end"]
+    body += normalize(2, 4) + normalize(3, 5)
+    body += [("block", []), ("loop", []), G(4), G(5), "i32.le_s", ("br_if", 1)] + subtract_step() + \
+            [G(2), C(1), "i32.shl", S_(2), G(4), C(1), "i32.sub", S_(4), ("br", 0), "end", "end"]
+    body += subtract_step()
+    body += [("block", []), ("loop", []), G(2), C(23), "i32.shr_u", ("br_if", 1),
+             G(2), C(1), "i32.shl", S_(2), G(4), C(1), "i32.sub", S_(4), ("br", 0), "end", "end"]
+    body += [G(4), C(0), "i32.gt_s", ("if", []),
+             G(2), C(0x00800000), "i32.sub", G(4), C(23), "i32.shl", "i32.or", S_(2),
+             "else", G(2), C(1), G(4), "i32.sub", "i32.shr_u", S_(2), "end",
+             G(2), G(6), "i32.or", "f32.reinterpret_i32"]
+    return m.func([F32, F32], [F32], locals=[I32] * 6, body=body)
+
+
+def guest_brick_modulo():
+    """`%` on floats, as the reference's brick texture uses it (src/sdf/demo/cube.rs:192), through the guest's own fmodf."""
+    m = base_module()
+    fmod = add_musl_fmodf(m)
+    body = store_out(0, [X, ("f32.const", 0.3), "f32.add", "f32.abs", ("f32.const", 3.0), "f32.mul", ("f32.const", 0.5), ("call", fmod)])
+    body += store_out(1, [Y, ("f32.const", 0.25), ("call", fmod)])
+    body += store_out(2, [("f32.const", 5.625), ("f32.const", 0.5), ("call", fmod)])          # concrete arguments: simply executed
+    body += store_out(3, [Z, ("f32.const", 100.0), "f32.mul", ("f32.const", 0.7), ("call", fmod)])
+    body += store_out(4, [X, Y, ("call", fmod)])
+    body += store_out(5, [Z, ("f32.const", 0.0), ("call", fmod)]) + store_out(6, [("f32.const", 1.0)])
+    m.func(*SAMPLE_SIG, body=body + [("i32.const", OUT)], export="sample")
+    return m
+
+
+def ref_brick_modulo(p):
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    o = np.zeros((len(p), 7), f32)
+    with np.errstate(all="ignore"):
+        o[:, 0] = np.fmod(np.abs(x + f32(0.3)) * f32(3.0), f32(0.5))
+        o[:, 1] = np.fmod(y, f32(0.25))
+        o[:, 2] = np.fmod(f32(5.625), f32(0.5))
+        o[:, 3] = np.fmod(z * f32(100.0), f32(0.7))
+        o[:, 4] = np.fmod(x, y)
+        o[:, 5] = np.fmod(z, f32(0.0))
+    o[:, 6] = 1.0
+    return o
+
+
 GUESTS = {
     "sphere_static": (guest_sphere_static, ref_sphere_static),
     "box_branchy": (guest_box_branchy, ref_box_branchy),
@@ -287,6 +355,7 @@ GUESTS = {
     "early_returns": (guest_early_returns, ref_early_returns),
     "integer_checker": (guest_integer_checker, ref_integer_checker),
     "registry": (guest_registry, ref_registry),
+    "brick_modulo": (guest_brick_modulo, ref_brick_modulo),
 }
 
 
@@ -300,6 +369,23 @@ def test_lowered_guest_equals_its_formula(S, oracle, name):
     want = ref(p)
     bad = ~((got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want)))
     assert not bad.any(), (name, np.argwhere(bad)[:5], got[bad][:5], want[bad][:5])
+
+
+def test_fmodf_is_recognised_by_what_it_computes(S, oracle):
+    """The guest's fmodf (an exponent loop that cannot be unrolled for a symbolic operand) is identified by probing
+    it with concrete arguments and becomes one FMOD op per call; a function that differs from fmodf anywhere on the
+    probe grid is not taken for it (it is inlined, and here fails because its loop depends on the position)."""
+    tape, _, summary = lowered(S, oracle, guest_brick_modulo())
+    assert "5 fmodf calls recognised" in summary and "0 symbolic branches" in summary
+    # the same function with one constant changed (mantissa mask) is no fmodf
+    m = base_module()
+    impostor = add_musl_fmodf(m)
+    t, locs, body = m.funcs[impostor - len(m.imports)]
+    body[body.index(("i32.const", 0x007FFFFF))] = ("i32.const", 0x007FFFFE)
+    m.func(*SAMPLE_SIG, body=store_out(0, [X, ("f32.const", 0.5), ("call", impostor)]) + [("i32.const", OUT)], export="sample")
+    with pytest.raises(S.WasmLoweringError) as e:
+        S.wasm.lower(m.build())
+    assert e.value.code == -3 and "depend on the position" in str(e.value)
 
 
 def test_parameter_change_keeps_the_structure(S, oracle):
