@@ -188,7 +188,7 @@ def host_sampled_path(orc, S, threads, side=256):
 
 
 def workload_name(workload, dims, W, H):
-    return (f"{ {'demo': 'demo_sdf', 'csg': 'csg_1k', 'wasm': 'wasm guest (4 spheres) lowered to a scalar program'}[workload]} {dims[0]}x{dims[1]}x{dims[2]} "
+    return (f"{ {'demo': 'demo_sdf', 'csg': 'csg_1k', 'wasm': 'demo_sdf as a WebAssembly guest lowered to a scalar program'}[workload]} {dims[0]}x{dims[1]}x{dims[2]} "
             f"grid fill + {W}x{H} sphere trace, default scene camera")
 
 
@@ -240,8 +240,8 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--workload", default="demo", choices=["demo", "csg", "wasm"],
-                    help="demo: SDFDemo (the headline); csg: 1000 primitives; wasm: a WebAssembly guest (union of four "
-                         "spheres, assembled by tests/test_wasm_lower.py) lowered to a scalar program by sdfgpu_wasm_lower")
+                    help="demo: SDFDemo (the headline); csg: 1000 primitives; wasm: SDFDemo again, but as a WebAssembly guest "
+                         "(hand-compiled in tests/test_wasm_lower.py) lowered to a scalar program by sdfgpu_wasm_lower")
     ap.add_argument("--vpt", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -272,7 +272,7 @@ def main():
     W, H = args.width, args.height
     if args.workload == "wasm":
         import test_wasm_lower  # test infrastructure: the guest module is assembled there (no WASM toolchain here)
-        tape, _, lowering = S.wasm.lower(test_wasm_lower.guest_csg_calls().build())
+        tape, _, lowering = S.wasm.lower(test_wasm_lower.guest_reference_demo().build())
     else:
         tape = S.tape.demo_tape() if args.workload == "demo" else S.tape.csg_tape()
     cam = S.default_camera(W, H)

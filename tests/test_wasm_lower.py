@@ -348,6 +348,71 @@ def ref_brick_modulo(p):
     return o
 
 
+def guest_reference_demo(half=0.95, radius=1.05, seam=0.05):
+    """The reference's own SDFDemo (src/sdf/demo/mod.rs:51-75: brick cube minus sphere with a seam material; cube.rs:79-89,
+    164-222; sphere.rs:37-47,122-124) hand-compiled to WebAssembly the way the Rust source is structured: one function
+    per `sample`, SDFSample structs in guest memory, the air early-outs, the tri-planar brick texture with `%` (through
+    the guest's fmodf) and `floor`, `normalize`, the struct-valued `if` of the combinator done with memory.copy."""
+    m = base_module()
+    fmod = add_musl_fmodf(m)
+    PAR, BOXS, SPHS = 256, 1200, 1300
+    m.data_at(PAR, struct.pack("<3f", half, radius, seam))
+    G = lambda k: ("local.get", k)      # noqa: E731
+    St = lambda k: ("local.set", k)     # noqa: E731
+    K = lambda v: ("f32.const", v)      # noqa: E731
+
+    def store_fields(ptr, values):  # fields 1..6 of the SDFSample at `ptr` (instruction lists that leave an f32)
+        out = []
+        for k, v in enumerate(values, start=1):
+            out += [ptr] + v + [("f32.store", 4 * k)]
+        return out
+
+    # brick_texture(px, py, pz, nx, ny, nz, dst)   locals: 7 u, 8 v, 9 bx, 10 by, 11 max_cement
+    colour = lambda a, b, c: [[K(a), K(255.0), "f32.div"], [K(b), K(255.0), "f32.div"], [K(c), K(255.0), "f32.div"]]  # noqa: E731
+    brick = m.func([F32] * 6 + [I32], [], locals=[F32] * 5, body=[
+        G(3), "f32.abs", G(4), "f32.abs", "f32.gt", ("if", []),
+        G(3), "f32.abs", G(5), "f32.abs", "f32.gt", ("if", []), G(2), St(7), G(1), St(8), "else", G(0), St(7), G(1), St(8), "end",
+        "else",
+        G(4), "f32.abs", G(5), "f32.abs", "f32.gt", ("if", []), G(2), St(7), G(0), St(8), "else", G(0), St(7), G(1), St(8), "end",
+        "end",
+        G(7), G(8), K(0.25), "f32.div", "f32.floor", K(4.0), "f32.div", "f32.add", "f32.abs", K(0.5), ("call", fmod), St(9),
+        G(8), "f32.abs", K(0.25), ("call", fmod), St(10),
+        K(0.2), K(2.0), "f32.div", K(0.25), "f32.mul", St(11),
+        G(9), G(11), "f32.lt", G(9), K(0.5), G(11), "f32.sub", "f32.gt", "i32.or",
+        G(10), G(11), "f32.lt", "i32.or", G(10), K(0.25), G(11), "f32.sub", "f32.gt", "i32.or",
+        ("if", [])] + store_fields(G(6), colour(56.0, 70.0, 60.0) + [[K(0.4)], [K(0.5)], [K(1.0)]]) + ["else"] +
+        store_fields(G(6), colour(150.0, 24.0, 10.0) + [[K(0.2)], [K(0.8)], [K(0.0)]]) + ["end"])
+    zeros = [[K(0.0)]] * 6
+    HALF = [("i32.const", PAR), ("f32.load", 0)]
+    # cube_sample(x, y, z, dst)   locals: 4 d, 5 nx, 6 ny, 7 nz
+    normal = lambda a, dst: [K(1.0), G(a), "f32.copysign", K(0.0), G(a), "f32.abs"] + HALF + ["f32.gt", "select", St(dst)]  # noqa: E731
+    cube = m.func([F32] * 3 + [I32], [], locals=[F32] * 4, body=[
+        G(0), "f32.abs", G(1), "f32.abs", "f32.max", G(2), "f32.abs", "f32.max"] + HALF + ["f32.sub", St(4),
+        G(3), G(4), ("f32.store", 0),
+        G(4), K(0.1), "f32.gt", ("if", [])] + store_fields(G(3), zeros) + ["else"] +
+        normal(0, 5) + normal(1, 6) + normal(2, 7) + [G(0), G(1), G(2), G(5), G(6), G(7), G(3), ("call", brick), "end"])
+    # sphere_sample(x, y, z, dst)   locals: 4 len, 5 d, 6 inv
+    sphere = m.func([F32] * 3 + [I32], [], locals=[F32] * 3, body=[
+        G(0), G(0), "f32.mul", G(1), G(1), "f32.mul", "f32.add", G(2), G(2), "f32.mul", "f32.add", "f32.sqrt", St(4),
+        G(4), ("i32.const", PAR), ("f32.load", 4), "f32.sub", St(5), G(3), G(5), ("f32.store", 0),
+        G(5), K(0.1), "f32.gt", ("if", [])] + store_fields(G(3), zeros) + ["else",
+        K(1.0), G(4), "f32.div", St(6)] +
+        store_fields(G(3), [[G(0), G(6), "f32.mul", "f32.abs"], [G(1), G(6), "f32.mul", "f32.abs"], [G(2), G(6), "f32.mul", "f32.abs"],
+                            [K(0.0)], [K(0.0)], [K(0.0)]]) + ["end"])
+    # sample   locals: 5 dist, 6 inter
+    BD = [("i32.const", BOXS), ("f32.load", 0)]
+    SD = [("i32.const", SPHS), ("f32.load", 0)]
+    body = [X, Y, Z, ("i32.const", BOXS), ("call", cube), X, Y, Z, ("i32.const", SPHS), ("call", sphere)]
+    body += BD + SD + ["f32.neg", "f32.max", St(5)] + BD + ["f32.abs"] + SD + ["f32.abs", "f32.sub", St(6)]
+    body += [G(6), K(0.0), "f32.lt", ("if", []), ("i32.const", OUT), ("i32.const", BOXS), ("i32.const", 28), ("memory.copy",),
+             "else", ("i32.const", OUT), ("i32.const", SPHS), ("i32.const", 28), ("memory.copy",), "end"]
+    body += [G(6), "f32.abs", ("i32.const", PAR), ("f32.load", 8), "f32.le", ("if", [])] + \
+        store_fields(("i32.const", OUT), [[K(0.5)], [K(0.6)], [K(0.7)], [K(0.5)], [K(0.0)], [K(0.0)]]) + ["end"]
+    body += [("i32.const", OUT), G(5), ("f32.store", 0), ("i32.const", OUT)]
+    m.func(*SAMPLE_SIG, locals=[F32, F32], body=body, export="sample")
+    return m
+
+
 GUESTS = {
     "sphere_static": (guest_sphere_static, ref_sphere_static),
     "box_branchy": (guest_box_branchy, ref_box_branchy),
@@ -357,6 +422,7 @@ GUESTS = {
     "registry": (guest_registry, ref_registry),
     "brick_modulo": (guest_brick_modulo, ref_brick_modulo),
 }
+# guest_reference_demo is checked against the oracle's SDFDemo (test_the_reference_demo_as_a_wasm_guest), not a formula
 
 
 @pytest.mark.parametrize("name", list(GUESTS))
@@ -386,6 +452,39 @@ def test_fmodf_is_recognised_by_what_it_computes(S, oracle):
     with pytest.raises(S.WasmLoweringError) as e:
         S.wasm.lower(m.build())
     assert e.value.code == -3 and "depend on the position" in str(e.value)
+
+
+def test_the_reference_demo_as_a_wasm_guest(S, oracle):
+    """SDFDemo hand-compiled to WebAssembly lowers to a scalar program that reproduces the oracle's direct restatement
+    of `SDFDemo::sample` bit for bit -- on random points, on the voxel positions of a grid (where the seams, brick joints
+    and air early-outs are hit exactly) and with other parameters through a live-memory re-lowering."""
+    m = guest_reference_demo()
+    wasm = m.build()
+    tape, bb, summary = lowered(S, oracle, m)
+    assert bb == BB and "fmodf calls recognised" in summary
+    v = oracle.Viewer(BB, (24, 24, 24), 1)
+    grid = np.array([v.voxel_pos(x, y, z) for z in range(24) for y in range(24) for x in range(24)], f32)
+    pts = np.concatenate([points(4000, seed=3), grid, [[1.0, 0.0, 0.0], [0.95, 0.95, 0.95], [0.0, 0.0, 0.0], [-1.0, 1.0, -1.0]]]).astype(f32)
+    got, want = oracle.tape_sample(tape, pts), oracle.demo_sample(pts)
+    bad = ~((got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want)))
+    assert not bad.any(), (summary, np.argwhere(bad)[:5], pts[np.argwhere(bad)[:3, 0]], got[bad][:5], want[bad][:5])
+    # every branch of the demo is exercised by those points
+    assert (want[:, 4] == f32(0.4)).any() and (want[:, 4] == f32(0.2)).any() and (want[:, 4] == f32(0.5)).any() and (want[:, 1] == 0).any()
+    # set_parameter on the live guest (radius 1.05 -> 0.9, cube 0.95 -> 0.85): same structure, new constants
+    mem = bytearray(65536)
+    for off, payload in m.data:
+        mem[off:off + len(payload)] = payload
+    mem[256:268] = struct.pack("<3f", 0.85, 0.9, 0.05)
+    tape2 = S.wasm.lower(wasm, memory=bytes(mem))[0]
+    assert len(tape2) == len(tape)
+    want2 = oracle.demo_sample(pts, oracle.demo_params(cube_half_side=0.85, sphere_radius=0.9))
+    assert same(oracle.tape_sample(tape2, pts), want2)
+    # (equal constants are shared, so a parameter that lands exactly on another constant of the program -- a cube of
+    # 0.8, the brick's roughness -- gives a program one constant shorter: still correct, compiled once more)
+    mem[256:260] = struct.pack("<f", 0.8)
+    tape3 = S.wasm.lower(wasm, memory=bytes(mem))[0]
+    assert len(tape3) < len(tape)
+    assert same(oracle.tape_sample(tape3, pts), oracle.demo_sample(pts, oracle.demo_params(cube_half_side=0.8, sphere_radius=0.9)))
 
 
 def test_parameter_change_keeps_the_structure(S, oracle):
@@ -571,7 +670,9 @@ def test_lowered_guests_fill_on_gpu(S, oracle):
     if not os.environ.get("SDFGPU_RUN_NEXT") or not _have_gpu(S):
         pytest.skip("set SDFGPU_RUN_NEXT=1 on a GPU box")
     dims = (40, 36, 32)
-    for name, (make, _) in GUESTS.items():
+    makers = {name: make for name, (make, _) in GUESTS.items()}
+    makers["reference_demo"] = guest_reference_demo
+    for name, make in makers.items():
         sdf = S.WasmSDF(make().build())
         o = oracle.Viewer(BB, dims, 2)
         o.update(oracle.Sampler(tape=sdf.tape()))
