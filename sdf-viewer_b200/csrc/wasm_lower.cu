@@ -7,8 +7,9 @@
 // coordinates are symbolic.  Every f32 / i32 operation that touches a symbolic word appends one op to a scalar
 // program (include/sdfgpu_tape.h, `sdft_sop`: WebAssembly's own numeric semantics); everything else --
 // allocator, registry lookups, vtable calls, loops with concrete trip counts -- simply runs and disappears.
-// A branch on a symbolic condition forks the execution; the paths' results (the seven floats each leaves in
-// guest memory) are merged with selects, so the tape is branch free.  What cannot be expressed makes the
+// A branch on a symbolic condition forks the execution; the two sides are merged with selects where they meet
+// again (if-conversion of stack, locals, globals and memory: merge_states), or, when a side leaves for good, at
+// the end of the call (the seven floats each path leaves in guest memory: merge), so the tape is branch free.  What cannot be expressed makes the
 // lowering fail with a message (symbolic addresses or loop bounds, i64 / f64 arithmetic on symbolic values,
 // host imports, SIMD): the caller then samples that SDF on the host (sdfgpu_update_surface).  The guest's libm
 // fmodf (what `%` on floats calls) is recognised by what it computes and becomes one op (behaves_like_fmodf).
@@ -112,7 +113,7 @@ struct Node {
     uint32_t op, a, b, c;
 };
 
-enum Status { ST_OK = 0, ST_TRAP = 1, ST_FAIL = 2 };
+enum Status { ST_OK = 0, ST_TRAP = 1, ST_FAIL = 2, ST_REJOIN = 3 };  // ST_REJOIN: the path stopped at the join point it was given
 
 struct Leaf {
     Status st = ST_OK;
@@ -1003,10 +1004,95 @@ struct Lowerer {
     Leaf failed() { Leaf l; l.st = ST_FAIL; return l; }
     Leaf trapped() { Leaf l; l.st = ST_TRAP; return l; }
 
-    // Run `st` until its outermost frame returns, then hand the state to `finish`.
-    Leaf run(State& st, FinishFn finish) {
+    // Where the two sides of a branch on a symbolic condition meet again: the instruction after the construct,
+    // in the same frame, with the same labels open.
+    struct Stop {
+        size_t depth, pc, labels;
+    };
+
+    static bool same_val(const Val& x, const Val& y) {
+        if (x.sym != y.sym || x.ty != y.ty) return false;
+        return x.sym ? x.node == y.node : x.bits == y.bits;
+    }
+    bool merge_val(uint32_t cond, const Val& x, const Val& y, Val* out) {
+        if (same_val(x, y)) { *out = x; return true; }
+        if (x.ty != y.ty || x.ty == T_I64 || x.ty == T_F64) return false;  // 64-bit values have no select
+        *out = symv(x.ty, node(SDFT_S_SELECT, cond, node_of(x), node_of(y)));
+        return true;
+    }
+    // if-conversion: one state that is `a` where cond holds and `b` where it does not.  Both stopped at the same
+    // join point; false when they differ in something a select cannot express (then the caller keeps them apart).
+    bool merge_states(uint32_t cond, const State& a, const State& b, State* out) {
+        if (a.frames.size() != b.frames.size() || a.stack.size() != b.stack.size() || a.pages != b.pages ||
+            a.globals.size() != b.globals.size())
+            return false;
+        State mrg = a;
+        for (size_t i = 0; i < a.stack.size(); ++i)
+            if (!merge_val(cond, a.stack[i], b.stack[i], &mrg.stack[i])) return false;
+        for (size_t i = 0; i < a.globals.size(); ++i)
+            if (!merge_val(cond, a.globals[i], b.globals[i], &mrg.globals[i])) return false;
+        for (size_t k = 0; k < a.frames.size(); ++k) {
+            const Frame &fa = a.frames[k], &fb = b.frames[k];
+            if (fa.func != fb.func || fa.pc != fb.pc || fa.locals.size() != fb.locals.size() || fa.labels.size() != fb.labels.size())
+                return false;
+            for (size_t i = 0; i < fa.labels.size(); ++i)
+                if (fa.labels[i].height != fb.labels[i].height || fa.labels[i].end_pc != fb.labels[i].end_pc ||
+                    fa.labels[i].cont_pc != fb.labels[i].cont_pc)
+                    return false;
+            for (size_t i = 0; i < fa.locals.size(); ++i)
+                if (!merge_val(cond, fa.locals[i], fb.locals[i], &mrg.frames[k].locals[i])) return false;
+        }
+        // guest memory: words either side wrote since instantiation
+        auto word_node = [&](const State& s, uint32_t addr) -> Cell {
+            auto it = s.mem.find(addr);
+            return it != s.mem.end() ? it->second : Cell{false, base_word(addr)};
+        };
+        for (int side = 0; side < 2; ++side) {
+            const State& s = side ? b : a;
+            for (const auto& kv : s.mem) {
+                const Cell ca = word_node(a, kv.first), cb = word_node(b, kv.first);
+                if (ca.sym == cb.sym && ca.w == cb.w) { mrg.mem[kv.first] = ca; continue; }
+                // a concrete word of memory is data, not structure: a constant of the tape (its bits survive the
+                // float load unchanged), so that guests which differ only in such values share a kernel
+                const uint32_t na = ca.sym ? ca.w : node_of(conc(T_F32, ca.w)), nb = cb.sym ? cb.w : node_of(conc(T_F32, cb.w));
+                mrg.mem[kv.first] = Cell{true, node(SDFT_S_SELECT, cond, na, nb)};
+            }
+        }
+        *out = std::move(mrg);
+        return true;
+    }
+
+    // The two sides of a branch on the symbolic condition `cond` have run until they rejoined (ST_REJOIN, their
+    // states in A / B), finished the whole call (a final leaf) or trapped.  Returns true when execution continues
+    // from `*st` (merged, or the surviving side); otherwise *out is the merged final outcome.
+    bool resolve_fork(uint32_t cond, State& A, Leaf la, State& B, Leaf lb, FinishFn finish, State* st, Leaf* out) {
+        if (la.st == ST_FAIL || lb.st == ST_FAIL) { *out = failed(); return false; }
+        if (la.st == ST_REJOIN && lb.st == ST_REJOIN) {
+            State mrg;
+            if (merge_states(cond, A, B, &mrg)) { *st = std::move(mrg); return true; }
+        }
+        if (la.st == ST_REJOIN && lb.st == ST_TRAP) { *st = std::move(A); return true; }  // the trapping side contributes nothing
+        if (la.st == ST_TRAP && lb.st == ST_REJOIN) { *st = std::move(B); return true; }
+        // one side left the construct for good (return, branch further out, unmergeable state): run whatever
+        // stopped at the join point to the end as well and merge the final outcomes
+        ++fork_depth;
+        if (la.st == ST_REJOIN) la = run(A, finish, nullptr);
+        if (lb.st == ST_REJOIN && la.st != ST_FAIL) lb = run(B, finish, nullptr);
+        --fork_depth;
+        *out = merge(cond, la, lb);
+        return false;
+    }
+
+    // Run `st` until its outermost frame returns, then hand the state to `finish`; with `stop`, also until the
+    // path reaches that join point (ST_REJOIN, the state stays in `st`).
+    Leaf run(State& st, FinishFn finish, const Stop* stop = nullptr) {
         for (;;) {
             if (st.frames.empty()) return finish(*this, st);
+            if (stop && st.frames.size() == stop->depth && st.frames.back().pc == stop->pc && st.frames.back().labels.size() == stop->labels) {
+                Leaf l;
+                l.st = ST_REJOIN;
+                return l;
+            }
             if (budget == 0) { fail("instruction budget exhausted (a loop whose exit depends on the position?)"); return failed(); }
             --budget;
             Frame& fr = st.frames.back();
@@ -1063,14 +1149,17 @@ struct Lowerer {
                     };
                     if (!c.sym) { take(st, (uint32_t)c.bits != 0); break; }
                     if (!fork_ok()) return failed();
-                    State other = st;
-                    take(other, true);
-                    take(st, false);
+                    const Stop join{st.frames.size(), bi.end_pc + 1, fr.labels.size()};
+                    State A = st, B = st;
+                    take(A, true);
+                    take(B, false);
                     ++fork_depth;
-                    const Leaf a = run(other, finish);
-                    const Leaf b = a.st == ST_FAIL ? failed() : run(st, finish);
+                    const Leaf la = run(A, finish, &join);
+                    const Leaf lb = la.st == ST_FAIL ? failed() : run(B, finish, &join);
                     --fork_depth;
-                    return merge(c.node, a, b);
+                    Leaf out;
+                    if (!resolve_fork(c.node, A, la, B, lb, finish, &st, &out)) return out;
+                    break;  // `st` is the merged state at the join point
                 }
                 case 0x05: {  // else reached from the then arm: leave the construct
                     const Label l = fr.labels.back();
@@ -1106,15 +1195,24 @@ struct Lowerer {
                         break;
                     }
                     if (!fork_ok()) return failed();
-                    State other = st;
-                    Leaf a;
+                    if (d >= fr.labels.size()) { fail("branch depth out of range"); return failed(); }
+                    const size_t target = fr.labels.size() - 1 - d;
+                    const bool forward = target != 0 && !fr.labels[target].is_loop;  // a block's end: the sides can meet there
+                    State A = st, B = st;  // A takes the branch
+                    Leaf la, lb;
+                    Stop join{0, 0, 0};
                     ++fork_depth;
-                    if (branch(other, d)) a = finish(*this, other);
-                    else if (!err.empty()) a = failed();
-                    else a = run(other, finish);
-                    const Leaf b = a.st == ST_FAIL ? failed() : run(st, finish);
+                    if (branch(A, d)) la = finish(*this, A);
+                    else if (!err.empty()) la = failed();
+                    else if (forward) {
+                        la.st = ST_REJOIN;  // it is at the join point already
+                        join = Stop{A.frames.size(), A.frames.back().pc, A.frames.back().labels.size()};
+                    } else la = run(A, finish, nullptr);
+                    lb = la.st == ST_FAIL ? failed() : run(B, finish, la.st == ST_REJOIN ? &join : nullptr);
                     --fork_depth;
-                    return merge(c.node, a, b);
+                    Leaf out;
+                    if (!resolve_fork(c.node, A, la, B, lb, finish, &st, &out)) return out;
+                    break;
                 }
                 case 0x0e: {
                     const uint32_t n = r.u32();
