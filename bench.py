@@ -187,6 +187,35 @@ def host_sampled_path(orc, S, threads, side=256):
             "sample": f"{side}^3 grid, 2 passes ({total} iterations), 30 ms per update call as the scene does, {dt:.2f} s"}
 
 
+def trace_modes_live(torch, v, stream, cam, W, H, reps=20):
+    """Trace time for the other distance sources of the march (option trace_distance_volume; the step above uses 0,
+    tex0.r in place): dense R32F copy, the same as a 3-D CUDA array through the TMU in point mode (both give the
+    identical frame), and hardware LINEAR filtering (approximate, outside the 1e-5 bar).  The volume is not
+    re-filled in between, which is the situation these modes are for (many frames per fill)."""
+    out = {}
+    try:
+        for mode, name in ((0, "tex0_in_place_ms"), (1, "dense_r32f_ms"), (2, "tmu_point_ms"), (3, "tmu_hw_linear_approx_ms")):
+            v.set_option("trace_distance_volume", mode)
+            v.trace_device(cam, W, H)  # builds this mode's distance volume
+            v.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                v.trace_device(cam, W, H)
+            e1.record(stream)
+            v.sync()
+            torch.cuda.synchronize()
+            out[name] = e0.elapsed_time(e1) / reps
+    except Exception as e:  # an extra: never a reason to lose the bench line
+        out["error"] = str(e)
+    finally:
+        try:
+            v.set_option("trace_distance_volume", 0)
+        except Exception:
+            pass
+    return out
+
+
 def workload_name(workload, dims, W, H):
     return (f"{ {'demo': 'demo_sdf', 'csg': 'csg_1k', 'wasm': 'demo_sdf as a WebAssembly guest lowered to a scalar program'}[workload]} {dims[0]}x{dims[1]}x{dims[2]} "
             f"grid fill + {W}x{H} sphere trace, default scene camera")
@@ -356,6 +385,7 @@ def main():
         e2e_ms = t.item()
     clocks = clk.stop(wall0, time.time()) if clk else None
     hit_frac = float((depth_h < 1.0).mean())
+    trace_modes = trace_modes_live(torch, v, stream, cam, W, H) if n_gpus == 1 else None
 
     if rank != 0:
         if dist: dist.destroy_process_group()
@@ -385,6 +415,7 @@ def main():
                 "h2d_bytes_per_step": len(tape) + 256, "d2h_bytes_per_step": W * H * 8,
                 "what": "set_tape (H2D) + fill + commit + trace + frame RGBA8+depth D2H into pinned host memory"},
         "gpu_launches": int(launches), "clocks": clocks, "host_ms_per_step": wall_ms,
+        "trace_modes": trace_modes,
         "trace_profile": trace_profile() if (n_gpus == 1 and args.grid == 512 and args.workload == "demo") else None,
     }
     if n_gpus > 1:
