@@ -525,13 +525,26 @@ struct Lowerer {
         *out = addr < m.base.size() ? m.base[addr] : 0;
         return 0;
     }
-    bool write_byte(State& st, uint32_t addr, uint8_t b) {
-        const uint32_t wa = addr & ~3u;
-        auto it = st.mem.find(wa);
-        if (it == st.mem.end()) it = st.mem.insert(std::make_pair(wa, Cell{false, base_word(wa)})).first;
-        if (it->second.sym) { it->second.sym = false; it->second.w = 0; }  // overwritten in part: the rest reads as 0 -- rejected on load
-        const int sh = 8 * (int)(addr & 3u);
-        it->second.w = (it->second.w & ~(0xffu << sh)) | ((uint32_t)b << sh);
+    // concrete bytes into guest memory.  A symbolic word may be overwritten as a whole (zeroing a struct, copying
+    // over a spilled value); overwriting part of one has no 32-bit form and fails.
+    bool write_bytes(State& st, uint32_t addr, const uint8_t* data, uint32_t n) {
+        uint32_t i = 0;
+        while (i < n) {
+            const uint32_t a = addr + i, wa = a & ~3u;
+            auto it = st.mem.find(wa);
+            if (a == wa && n - i >= 4) {  // a whole word
+                const uint32_t w = (uint32_t)data[i] | (uint32_t)data[i + 1] << 8 | (uint32_t)data[i + 2] << 16 | (uint32_t)data[i + 3] << 24;
+                if (it == st.mem.end()) st.mem.insert(std::make_pair(wa, Cell{false, w}));
+                else it->second = Cell{false, w};
+                i += 4;
+                continue;
+            }
+            if (it == st.mem.end()) it = st.mem.insert(std::make_pair(wa, Cell{false, base_word(wa)})).first;
+            if (it->second.sym) return fail("a store overwrites part of a symbolic word at 0x%x", wa);
+            const int sh = 8 * (int)(a & 3u);
+            it->second.w = (it->second.w & ~(0xffu << sh)) | ((uint32_t)data[i] << sh);
+            ++i;
+        }
         return true;
     }
     bool load(State& st, uint64_t addr, uint32_t nbytes, uint64_t* out, bool* is_sym, uint32_t* sym_node) {
@@ -559,8 +572,9 @@ struct Lowerer {
             st.mem[(uint32_t)addr] = Cell{false, (uint32_t)v.bits};
             return true;
         }
-        for (uint32_t i = 0; i < nbytes; ++i) write_byte(st, (uint32_t)(addr + i), (uint8_t)(v.bits >> (8 * i)));
-        return true;
+        uint8_t bytes[8];
+        for (uint32_t i = 0; i < nbytes && i < 8; ++i) bytes[i] = (uint8_t)(v.bits >> (8 * i));
+        return write_bytes(st, (uint32_t)addr, bytes, nbytes);
     }
     void commit(State& st) {  // fold a finished CONCRETE set-up call into the instantiated memory
         for (auto& kv : st.mem) {
@@ -1337,7 +1351,8 @@ struct Lowerer {
                         if (len > (64u << 20)) { fail("memory.copy / fill of more than 64 MiB"); return failed(); }
                         if (sub == 11) {
                             if (s.sym) { fail("memory.fill with a symbolic byte"); return failed(); }
-                            for (uint32_t i = 0; i < len; ++i) write_byte(st, dst + i, (uint8_t)s.bits);
+                            const std::vector<uint8_t> fill(len, (uint8_t)s.bits);
+                            if (!write_bytes(st, dst, fill.data(), len)) return failed();
                         } else if (len && ((dst | src | len) & 3u) == 0) {  // word-wise: symbolic words move as they are
                             std::vector<Cell> tmp(len / 4);
                             for (uint32_t i = 0; i < len / 4; ++i) {
@@ -1349,7 +1364,7 @@ struct Lowerer {
                             std::vector<uint8_t> tmp(len);
                             for (uint32_t i = 0; i < len; ++i)
                                 if (read_byte(st, src + i, &tmp[i])) { fail("an unaligned memory.copy moves a symbolic word"); return failed(); }
-                            for (uint32_t i = 0; i < len; ++i) write_byte(st, dst + i, tmp[i]);
+                            if (!write_bytes(st, dst, tmp.data(), len)) return failed();
                         }
                         break;
                     }

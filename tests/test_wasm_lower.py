@@ -629,6 +629,30 @@ def test_traps_on_one_side_of_a_branch_are_dropped(S, oracle):
     assert "1 symbolic branches" in summary
 
 
+def test_symbolic_words_in_memory_are_overwritten_whole_or_not_at_all(S, oracle):
+    """A struct that held position-dependent values may be zeroed (memory.fill) or overwritten by wider stores and
+    reused; a narrow store INTO such a word has no 32-bit form and is refused."""
+    def guest(extra):
+        m = base_module()
+        body = [("i32.const", 3000), X, ("f32.store", 0), ("i32.const", 3004), Y, ("f32.store", 0)]   # spill x, y
+        body += extra
+        body += store_out(0, [("i32.const", 3000), ("f32.load", 0), ("i32.const", 3004), ("f32.load", 0), "f32.add"])
+        for k in range(1, 7):
+            body += store_out(k, [("f32.const", 0.5)])
+        m.func(*SAMPLE_SIG, body=body + [("i32.const", OUT)], export="sample")
+        return m
+
+    p = points(30)
+    # zero both words with memory.fill, then store z over the first
+    zeroed = guest([("i32.const", 3000), ("i32.const", 0), ("i32.const", 8), ("memory.fill",), ("i32.const", 3000), Z, ("f32.store", 0)])
+    assert same(oracle.tape_sample(S.wasm.lower(zeroed.build())[0], p)[:, 0], p[:, 2] + f32(0.0))
+    # an i64 store over both words
+    wide = guest([("i32.const", 3000), ("i64.const", 0x3F8000003F000000), ("i64.store", 0)])
+    assert same(oracle.tape_sample(S.wasm.lower(wide.build())[0], p)[:, 0], np.full(len(p), 1.5, f32))
+    # one byte into a symbolic word
+    expect_failure(S, guest([("i32.const", 3001), ("i32.const", 7), ("i32.store8", 0)]), -3, "part of a symbolic word")
+
+
 def test_sdf_id_is_forwarded(S, oracle):
     """Every export takes the SDF's id first (0 = root, src/sdf/wasm/mod.rs:8-10): a guest with two children."""
     m = Module()
