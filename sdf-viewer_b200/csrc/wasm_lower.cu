@@ -38,8 +38,10 @@ enum : uint8_t { T_I32 = 0, T_I64 = 1, T_F32 = 2, T_F64 = 3 };
 struct Val {
     uint8_t ty = T_I32;
     bool sym = false;
-    uint64_t bits = 0;  // concrete value (i32 / f32 in the low word)
-    uint32_t node = 0;  // symbolic: index of the SSA node
+    uint64_t bits = 0;     // concrete value (i32 / f32 in the low word)
+    uint32_t node = 0;     // symbolic: index of the SSA node (of the low word for a 64-bit value)
+    uint32_t node_hi = 0;  // symbolic i64 / f64: the node of the high word.  Such a value can only be moved
+                           // (loaded, stored, kept in locals, selected): compilers copy structs of floats that way
 };
 
 struct FuncType {
@@ -175,6 +177,17 @@ struct Lowerer {
         Val v;
         v.ty = ty; v.sym = true; v.node = n;
         return v;
+    }
+    static Val sym64(uint8_t ty, uint32_t lo, uint32_t hi) {
+        Val v;
+        v.ty = ty; v.sym = true; v.node = lo; v.node_hi = hi;
+        return v;
+    }
+    static bool is64(uint8_t ty) { return ty == T_I64 || ty == T_F64; }
+    // the node of one half of a 64-bit value (a concrete half is data of the tape, like any memory word)
+    uint32_t half_node(const Val& v, int hi) {
+        if (v.sym) return hi ? v.node_hi : v.node;
+        return node_of(conc(T_F32, hi ? (v.bits >> 32) : (v.bits & 0xffffffffull)));
     }
     static Val conc(uint8_t ty, uint64_t bits) {
         Val v;
@@ -547,6 +560,19 @@ struct Lowerer {
         }
         return true;
     }
+    Cell cell_at(const State& st, uint32_t wa) const {
+        auto it = st.mem.find(wa);
+        return it != st.mem.end() ? it->second : Cell{false, base_word(wa)};
+    }
+    // an aligned 64-bit load of which at least one word is symbolic: the two halves' nodes
+    bool load_pair(State& st, uint64_t addr, uint32_t* lo, uint32_t* hi) {
+        if (addr & 3u) return false;
+        const Cell a = cell_at(st, (uint32_t)addr), b = cell_at(st, (uint32_t)addr + 4);
+        if (!a.sym && !b.sym) return false;
+        *lo = a.sym ? a.w : node_of(conc(T_F32, a.w));
+        *hi = b.sym ? b.w : node_of(conc(T_F32, b.w));
+        return true;
+    }
     bool load(State& st, uint64_t addr, uint32_t nbytes, uint64_t* out, bool* is_sym, uint32_t* sym_node) {
         *is_sym = false;
         if (nbytes == 4 && (addr & 3u) == 0) {
@@ -563,8 +589,14 @@ struct Lowerer {
         return true;
     }
     bool store(State& st, uint64_t addr, uint32_t nbytes, const Val& v) {
+        if (v.sym && is64(v.ty) && nbytes == 8 && (addr & 3u) == 0) {  // a moved pair of words
+            st.mem[(uint32_t)addr] = Cell{true, v.node};
+            st.mem[(uint32_t)addr + 4] = Cell{true, v.node_hi};
+            return true;
+        }
         if (v.sym) {
-            if (nbytes != 4 || (addr & 3u)) return fail("a symbolic value is stored with %u bytes at 0x%x (only aligned 32-bit stores are lowered)", nbytes, (uint32_t)addr);
+            if (nbytes != 4 || (addr & 3u) || is64(v.ty))
+                return fail("a symbolic value is stored with %u bytes at 0x%x (only aligned 32- and 64-bit stores are lowered)", nbytes, (uint32_t)addr);
             st.mem[(uint32_t)addr] = Cell{true, v.node};
             return true;
         }
@@ -1026,11 +1058,17 @@ struct Lowerer {
 
     static bool same_val(const Val& x, const Val& y) {
         if (x.sym != y.sym || x.ty != y.ty) return false;
-        return x.sym ? x.node == y.node : x.bits == y.bits;
+        if (!x.sym) return x.bits == y.bits;
+        return x.node == y.node && (!is64(x.ty) || x.node_hi == y.node_hi);
     }
     bool merge_val(uint32_t cond, const Val& x, const Val& y, Val* out) {
         if (same_val(x, y)) { *out = x; return true; }
-        if (x.ty != y.ty || x.ty == T_I64 || x.ty == T_F64) return false;  // 64-bit values have no select
+        if (x.ty != y.ty) return false;
+        if (is64(x.ty)) {  // a 64-bit value is a pair of words: select each half
+            *out = sym64(x.ty, node(SDFT_S_SELECT, cond, half_node(x, 0), half_node(y, 0)),
+                         node(SDFT_S_SELECT, cond, half_node(x, 1), half_node(y, 1)));
+            return true;
+        }
         *out = symv(x.ty, node(SDFT_S_SELECT, cond, node_of(x), node_of(y)));
         return true;
     }
@@ -1282,8 +1320,9 @@ struct Lowerer {
                     const Val x = st.stack.back(); st.stack.pop_back();
                     if (!c.sym) { st.stack.push_back((uint32_t)c.bits != 0 ? x : y); break; }
                     if (!x.sym && !y.sym && x.bits == y.bits) { st.stack.push_back(x); break; }
-                    if (x.ty == T_I64 || x.ty == T_F64) { fail("select of 64-bit values on a condition that depends on the position"); return failed(); }
-                    st.stack.push_back(symv(x.ty, node(SDFT_S_SELECT, c.node, node_of(x), node_of(y))));
+                    Val sel;
+                    if (!merge_val(c.node, x, y, &sel)) { fail("select of values of different types"); return failed(); }
+                    st.stack.push_back(sel);
                     break;
                 }
                 case 0x20: { const uint32_t i = r.u32(); ADVANCE(); if (i >= fr.locals.size()) { fail("local out of range"); return failed(); } st.stack.push_back(fr.locals[i]); break; }
@@ -1389,6 +1428,10 @@ struct Lowerer {
                         uint64_t v = 0;
                         bool is_sym = false;
                         uint32_t sn = 0;
+                        if (k == 1 || k == 3) {  // i64.load / f64.load of words that depend on the position: a moved pair
+                            uint32_t lo, hi;
+                            if (load_pair(st, addr, &lo, &hi)) { st.stack.push_back(sym64(ty[k], lo, hi)); break; }
+                        }
                         if (!load(st, addr, nb[k], &v, &is_sym, &sn)) return failed();
                         if (is_sym) {
                             if (k != 0 && k != 2) { fail("a symbolic word is loaded as a 64-bit value"); return failed(); }
@@ -1414,7 +1457,6 @@ struct Lowerer {
                         const uint64_t addr = (uint64_t)(uint32_t)a.bits + off;
                         const uint32_t n = nb[op - 0x36];
                         if (!in_bounds(st, addr, n)) return trapped();
-                        if (v.sym && (v.ty == T_I64 || v.ty == T_F64)) { fail("a symbolic 64-bit store"); return failed(); }
                         if (!store(st, addr, n, v)) return failed();
                         break;
                     }
@@ -1424,6 +1466,12 @@ struct Lowerer {
                             NEED(1);
                             const Val a = st.stack.back();
                             st.stack.pop_back();
+                            if (a.sym && is64(a.ty)) {  // a moved pair: only what keeps it a pair, or takes its low word
+                                if (op == 0xbd || op == 0xbf) { st.stack.push_back(sym64(result_type(op), a.node, a.node_hi)); break; }
+                                if (op == 0xa7) { st.stack.push_back(symv(T_I32, a.node)); break; }  // i32.wrap_i64
+                                fail("64-bit arithmetic (0x%02x) on a value that depends on the position", op);
+                                return failed();
+                            }
                             if (a.sym) {
                                 if (op == 0xbc || op == 0xbe) { st.stack.push_back(symv(result_type(op), a.node)); break; }  // reinterpret
                                 // the trapping truncations: identical to the saturating ones wherever the guest does not
@@ -1444,6 +1492,10 @@ struct Lowerer {
                             NEED(2);
                             const Val b = st.stack.back(); st.stack.pop_back();
                             const Val a = st.stack.back(); st.stack.pop_back();
+                            if ((a.sym && is64(a.ty)) || (b.sym && is64(b.ty))) {
+                                fail("64-bit arithmetic (0x%02x) on a value that depends on the position", op);
+                                return failed();
+                            }
                             if (a.sym || b.sym) {
                                 const uint32_t so = sym_binop(op);
                                 if (so == 0xffffffffu) { fail("instruction 0x%02x on a value that depends on the position has no 32-bit scalar form", op); return failed(); }

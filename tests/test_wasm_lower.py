@@ -653,6 +653,51 @@ def test_symbolic_words_in_memory_are_overwritten_whole_or_not_at_all(S, oracle)
     expect_failure(S, guest([("i32.const", 3001), ("i32.const", 7), ("i32.store8", 0)]), -3, "part of a symbolic word")
 
 
+def test_struct_copies_through_64_bit_moves(S, oracle):
+    """Compilers copy a 28-byte SDFSample with three i64 load / store pairs and one i32: 64-bit values whose words
+    depend on the position can be moved (memory, locals, select, a branch that picks one of two structs) though
+    not computed with."""
+    def guest(tail):
+        m = base_module()
+        A, B = 3000, 3100
+        body = []
+        for k, v in enumerate([[X, Y, "f32.add"], [X, "f32.abs"], [Y, "f32.neg"], [Z], [("f32.const", 0.25)], [X, Z, "f32.mul"], [("f32.const", 1.0)]]):
+            body += [("i32.const", A)] + v + [("f32.store", 4 * k)]
+        for k, v in enumerate([[Z, Y, "f32.sub"], [("f32.const", 0.5)], [Y], [X], [Z, "f32.sqrt"], [("f32.const", 0.0)], [Y, Y, "f32.mul"]]):
+            body += [("i32.const", B)] + v + [("f32.store", 4 * k)]
+        m.func(*SAMPLE_SIG, locals=[I64, I32], body=body + tail + [("i32.const", OUT)], export="sample")
+        return m
+
+    def copy(src, via_local=False):
+        out = []
+        for off in (0, 8, 16):
+            if via_local:
+                out += [("i32.const", src), ("i64.load", off), ("local.set", 5), ("i32.const", OUT), ("local.get", 5), ("i64.store", off)]
+            else:
+                out += [("i32.const", OUT), ("i32.const", src), ("i64.load", off), ("i64.store", off)]
+        return out + [("i32.const", OUT), ("i32.const", src), ("i32.load", 24), ("i32.store", 24)]
+
+    p = points(60)
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    with np.errstate(all="ignore"):
+        a = np.stack([x + y, np.abs(x), -y, z, np.full_like(x, 0.25), x * z, np.ones_like(x)], 1).astype(f32)
+        b = np.stack([z - y, np.full_like(x, 0.5), y, x, np.sqrt(z), np.zeros_like(x), y * y], 1).astype(f32)
+    assert same(oracle.tape_sample(S.wasm.lower(guest(copy(3000)).build())[0], p), a)
+    assert same(oracle.tape_sample(S.wasm.lower(guest(copy(3100, via_local=True)).build())[0], p), b)
+    # `if x > y { *out = a } else { *out = b }` with the copies in the arms
+    picked = guest([X, Y, "f32.gt", ("if", [])] + copy(3000) + ["else"] + copy(3100, via_local=True) + ["end"])
+    assert same(oracle.tape_sample(S.wasm.lower(picked.build())[0], p), np.where((x > y)[:, None], a, b))
+    # select between two 64-bit halves of the structs
+    sel = []
+    for off in (0, 8, 16):
+        sel += [("i32.const", OUT), ("i32.const", 3000), ("i64.load", off), ("i32.const", 3100), ("i64.load", off), X, Y, "f32.gt", "select", ("i64.store", off)]
+    sel += [("i32.const", OUT), ("i32.const", 3000), ("i32.load", 24), ("i32.const", 3100), ("i32.load", 24), X, Y, "f32.gt", "select", ("i32.store", 24)]
+    assert same(oracle.tape_sample(S.wasm.lower(guest(sel).build())[0], p), np.where((x > y)[:, None], a, b))
+    # arithmetic on such a value is refused
+    expect_failure(S, guest([("i32.const", OUT), ("i32.const", 3000), ("i64.load", 0), ("i64.const", 1), "i64.add", ("i64.store", 0)]), -3,
+                   "64-bit arithmetic")
+
+
 def test_sdf_id_is_forwarded(S, oracle):
     """Every export takes the SDF's id first (0 = root, src/sdf/wasm/mod.rs:8-10): a guest with two children."""
     m = Module()
