@@ -187,3 +187,52 @@ def test_mutated_tapes_are_rejected_or_accepted_never_crash(S):
         else:
             assert it % 3 != 0, "a truncated tape was accepted"
     assert rejected > 2500
+
+
+def test_surface_callback_table_from_a_python_surface(S, oracle):
+    """`sdfgpu_surface` built from a Python SDFSurface (viewer._surface_struct): the trampolines marshal points,
+    samples, the changed box and the tape exactly, and park exceptions instead of letting them cross the C ABI
+    (the failing samples take the reference's benign value, src/sdf/wasm/native.rs:202)."""
+    from sdf_viewer_b200 import viewer
+
+    class Host(S.SDFSurface):
+        def bounding_box(self):
+            return ((-1, -2, -3), (1, 2, 3))
+
+        def sample(self, pts, distance_only=False):
+            return oracle.demo_sample(pts)
+
+        def changed(self):
+            return (0, 0, 0, 0.5, 0.25, 1)
+
+    s = viewer._surface_struct(Host())
+    pts = np.random.default_rng(1).uniform(-1, 1, (17, 3)).astype(np.float32)
+    out = np.zeros((17, 7), np.float32)
+    fp = C.POINTER(C.c_float)
+    s.sample_batch(None, pts.ctypes.data_as(fp), 17, 0, out.ctypes.data_as(fp))
+    assert np.array_equal(out.view(np.uint32), oracle.demo_sample(pts).view(np.uint32))
+    box = (C.c_float * 6)()
+    assert s.changed(None, box) == 1 and list(box) == [0, 0, 0, 0.5, 0.25, 1]
+    bb = (C.c_float * 6)()
+    s.bounding_box(None, bb)
+    assert list(bb) == [-1, -2, -3, 1, 2, 3]
+    ptr, n = C.c_void_p(), C.c_size_t()
+    assert s.tape(None, C.byref(ptr), C.byref(n)) == 0 and not bool(s.sample)      # no tape, no single-point form
+    assert s.sample_threads == 1 and s._py_error[0] is None
+    # a surface with a tape hands its bytes over unchanged
+    d = viewer._surface_struct(S.SDFDemo())
+    assert d.tape(None, C.byref(ptr), C.byref(n)) == 1 and C.string_at(ptr.value, n.value) == S.SDFDemo().tape()
+
+    class Broken(Host):
+        def sample(self, pts, distance_only=False):
+            raise RuntimeError("guest trapped")
+
+        def changed(self):
+            raise ValueError("also broken")
+
+    b = viewer._surface_struct(Broken())
+    out[:] = 7
+    b.sample_batch(None, pts.ctypes.data_as(fp), 17, 0, out.ctypes.data_as(fp))
+    assert np.all(out[:, 0] == 1.0) and np.all(out[:, 1:] == 0.0)
+    assert b.changed(None, box) == 0
+    assert isinstance(b._py_error[0], RuntimeError)          # the first exception is the one re-raised by update_surface
