@@ -109,8 +109,10 @@ enum sdft_sop_op {
     /* i32 */
     SDFT_S_IADD = 32, SDFT_S_ISUB = 33, SDFT_S_IMUL = 34, SDFT_S_IAND = 35, SDFT_S_IOR = 36, SDFT_S_IXOR = 37,
     SDFT_S_ISHL = 38, SDFT_S_ISHR_U = 39, SDFT_S_ISHR_S = 40,
+    SDFT_S_IDIV_S = 41, SDFT_S_IDIV_U = 42, SDFT_S_IREM_S = 43, /* where WebAssembly traps (divisor 0, INT_MIN / -1) the result is 0 */
     SDFT_S_IEQ = 44, SDFT_S_INE = 45, SDFT_S_ILT_S = 46, SDFT_S_ILT_U = 47, SDFT_S_IGT_S = 48, SDFT_S_IGT_U = 49,
     SDFT_S_ILE_S = 50, SDFT_S_ILE_U = 51, SDFT_S_IGE_S = 52, SDFT_S_IGE_U = 53, SDFT_S_IEQZ = 54,
+    SDFT_S_IREM_U = 55,
     /* mixed */
     SDFT_S_SELECT = 56,    /* v[a] != 0 ? v[b] : v[c]                                        */
     SDFT_S_F_FROM_I_S = 57, SDFT_S_F_FROM_I_U = 58, /* f32.convert_i32_s / _u              */

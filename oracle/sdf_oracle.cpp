@@ -278,6 +278,10 @@ void run_scalar_program(const Tape& t, uint32_t first, uint32_t count, V3 p, Sam
             case SDFT_S_ISHL: r = a << (b & 31u); break;
             case SDFT_S_ISHR_U: r = a >> (b & 31u); break;
             case SDFT_S_ISHR_S: r = (uint32_t)((int32_t)a >> (b & 31u)); break;
+            case SDFT_S_IDIV_S: r = (b == 0u || (a == 0x80000000u && b == 0xffffffffu)) ? 0u : (uint32_t)((int32_t)a / (int32_t)b); break;
+            case SDFT_S_IDIV_U: r = b == 0u ? 0u : a / b; break;
+            case SDFT_S_IREM_S: r = (b == 0u || b == 0xffffffffu) ? 0u : (uint32_t)((int32_t)a % (int32_t)b); break;
+            case SDFT_S_IREM_U: r = b == 0u ? 0u : a % b; break;
             case SDFT_S_IEQ: r = a == b; break;
             case SDFT_S_INE: r = a != b; break;
             case SDFT_S_ILT_S: r = (int32_t)a < (int32_t)b; break;

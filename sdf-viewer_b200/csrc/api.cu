@@ -737,7 +737,8 @@ int parse_and_lower(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes, Parsed
                         case SDFT_S_SELECT: n_in = 3; break;
                         default:
                             if ((o.op >= SDFT_S_FADD && o.op <= SDFT_S_FMOD) || (o.op >= SDFT_S_FEQ && o.op <= SDFT_S_FGE) ||
-                                (o.op >= SDFT_S_IADD && o.op <= SDFT_S_ISHR_S) || (o.op >= SDFT_S_IEQ && o.op <= SDFT_S_IGE_U)) {
+                                (o.op >= SDFT_S_IADD && o.op <= SDFT_S_IREM_S) || (o.op >= SDFT_S_IEQ && o.op <= SDFT_S_IGE_U) ||
+                                o.op == SDFT_S_IREM_U) {
                                 n_in = 2;
                                 break;
                             }

@@ -703,6 +703,10 @@ struct Lowerer {
             case 0x6a: return SDFT_S_IADD;
             case 0x6b: return SDFT_S_ISUB;
             case 0x6c: return SDFT_S_IMUL;
+            case 0x6d: return SDFT_S_IDIV_S;  // the guest would trap on a zero divisor / overflow: the op yields 0 there
+            case 0x6e: return SDFT_S_IDIV_U;
+            case 0x6f: return SDFT_S_IREM_S;
+            case 0x70: return SDFT_S_IREM_U;
             case 0x71: return SDFT_S_IAND;
             case 0x72: return SDFT_S_IOR;
             case 0x73: return SDFT_S_IXOR;

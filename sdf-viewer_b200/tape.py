@@ -30,8 +30,8 @@ S = {name: code for name, code in dict(
     FNEG=8, FABS=9, FSQRT=10, FFLOOR=11, FCEIL=12, FTRUNC=13, FNEAREST=14,
     FADD=16, FSUB=17, FMUL=18, FDIV=19, FMIN=20, FMAX=21, FCOPYSIGN=22, FMOD=23,
     FEQ=24, FNE=25, FLT=26, FGT=27, FLE=28, FGE=29,
-    IADD=32, ISUB=33, IMUL=34, IAND=35, IOR=36, IXOR=37, ISHL=38, ISHR_U=39, ISHR_S=40,
-    IEQ=44, INE=45, ILT_S=46, ILT_U=47, IGT_S=48, IGT_U=49, ILE_S=50, ILE_U=51, IGE_S=52, IGE_U=53, IEQZ=54,
+    IADD=32, ISUB=33, IMUL=34, IAND=35, IOR=36, IXOR=37, ISHL=38, ISHR_U=39, ISHR_S=40, IDIV_S=41, IDIV_U=42, IREM_S=43,
+    IEQ=44, INE=45, ILT_S=46, ILT_U=47, IGT_S=48, IGT_U=49, ILE_S=50, ILE_U=51, IGE_S=52, IGE_U=53, IEQZ=54, IREM_U=55,
     SELECT=56, F_FROM_I_S=57, F_FROM_I_U=58, I_FROM_F_S=59, I_FROM_F_U=60, OUT=63).items()}
 
 SOP_DTYPE = np.dtype([("op", "<u4"), ("a", "<u4"), ("b", "<u4"), ("c", "<u4")])

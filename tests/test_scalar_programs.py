@@ -94,6 +94,14 @@ def ref_eval(ops, consts, p):
                 r = A >> (B & 31)
             elif name == "ISHR_S":
                 r = (sa >> (B & 31)) & 0xFFFFFFFF
+            elif name == "IDIV_S":
+                r = 0 if (B == 0 or (A == 0x80000000 and B == 0xFFFFFFFF)) else int(abs(sa) // abs(sb) * (1 if (sa < 0) == (sb < 0) else -1)) & 0xFFFFFFFF
+            elif name == "IDIV_U":
+                r = 0 if B == 0 else A // B
+            elif name == "IREM_S":
+                r = 0 if (B == 0 or B == 0xFFFFFFFF) else int((abs(sa) % abs(sb)) * (1 if sa >= 0 else -1)) & 0xFFFFFFFF
+            elif name == "IREM_U":
+                r = 0 if B == 0 else A % B
             elif name in ("IEQ", "INE", "ILT_U", "IGT_U", "ILE_U", "IGE_U"):
                 r = int({"IEQ": A == B, "INE": A != B, "ILT_U": A < B, "IGT_U": A > B, "ILE_U": A <= B, "IGE_U": A >= B}[name])
             elif name in ("ILT_S", "IGT_S", "ILE_S", "IGE_S"):
@@ -130,7 +138,7 @@ def _names(S):
 UNARY = ["FNEG", "FABS", "FSQRT", "FFLOOR", "FCEIL", "FTRUNC", "FNEAREST", "IEQZ", "F_FROM_I_S", "F_FROM_I_U", "I_FROM_F_S",
          "I_FROM_F_U"]
 BINARY = ["FADD", "FSUB", "FMUL", "FDIV", "FMIN", "FMAX", "FCOPYSIGN", "FMOD", "FEQ", "FNE", "FLT", "FGT", "FLE", "FGE", "IADD", "ISUB",
-          "IMUL", "IAND", "IOR", "IXOR", "ISHL", "ISHR_U", "ISHR_S", "IEQ", "INE", "ILT_S", "ILT_U", "IGT_S", "IGT_U", "ILE_S",
+          "IMUL", "IAND", "IOR", "IXOR", "ISHL", "ISHR_U", "ISHR_S", "IDIV_S", "IDIV_U", "IREM_S", "IREM_U", "IEQ", "INE", "ILT_S", "ILT_U", "IGT_S", "IGT_U", "ILE_S",
           "ILE_U", "IGE_S", "IGE_U"]
 SPECIAL = [0.0, -0.0, 1.0, -1.0, 0.5, -0.5, 1.5, 2.5, -2.5, 3.0e9, -3.0e9, 5.0e9, np.inf, -np.inf, np.nan, 1e-40, 16777217.0]
 

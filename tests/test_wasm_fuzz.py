@@ -51,7 +51,10 @@ class Gen:
         return self.fexpr(d + 1) + self.fexpr(d + 1) + [("call", self.helper)]
 
     def iexpr(self, d=0):
-        r = self.rng.integers(0, 8 if d < 3 else 3)
+        r = self.rng.integers(0, 9 if d < 3 else 3)
+        if r == 8:  # division / remainder by 1..8 (a zero divisor would trap in the guest)
+            return self.iexpr(d + 1) + self.iexpr(d + 1) + [("i32.const", 7), "i32.and", ("i32.const", 1), "i32.add",
+                                                            self.pick(["i32.div_s", "i32.div_u", "i32.rem_s", "i32.rem_u"])]
         if r == 0:
             return [("i32.const", int(self.rng.integers(-4, 9)) & 0xFFFFFFFF)]
         if r == 1:

@@ -228,6 +228,13 @@ class Instance:
                 y, x = st.pop() & MASK32, st.pop() & MASK32
                 st.append({"i32.add": x + y, "i32.sub": x - y, "i32.mul": x * y, "i32.and": x & y, "i32.or": x | y, "i32.xor": x ^ y,
                            "i32.shl": x << (y & 31), "i32.shr_u": x >> (y & 31), "i32.shr_s": _s32(x) >> (y & 31)}[op] & MASK32)
+            elif op in ("i32.div_s", "i32.div_u", "i32.rem_s", "i32.rem_u"):
+                y, x = st.pop() & MASK32, st.pop() & MASK32
+                if y == 0 or (op == "i32.div_s" and x == 0x80000000 and y == MASK32):
+                    raise Trap("integer division")
+                sx, sy = _s32(x), _s32(y)
+                q = abs(sx) // abs(sy) * (1 if (sx < 0) == (sy < 0) else -1)
+                st.append({"i32.div_s": q, "i32.div_u": x // y, "i32.rem_s": sx - q * sy, "i32.rem_u": x % y}[op] & MASK32)
             elif op in ("i32.eq", "i32.ne", "i32.lt_u", "i32.gt_u", "i32.le_u", "i32.ge_u"):
                 y, x = st.pop() & MASK32, st.pop() & MASK32
                 st.append(int({"i32.eq": x == y, "i32.ne": x != y, "i32.lt_u": x < y, "i32.gt_u": x > y, "i32.le_u": x <= y, "i32.ge_u": x >= y}[op]))
