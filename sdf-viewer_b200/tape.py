@@ -173,3 +173,48 @@ def csg_tape(table=None, clip_radius=0.98):
                   roughness=0.6, occlusion=1.0)
     t.emit(OP_UNION_RANGE, first, len(table)).emit(OP_INTER_PRIM, clip).emit(OP_END)
     return t.build()
+
+
+def disassemble(tape_bytes):
+    """A readable listing of a tape (instructions, primitives, constants, scalar programs): a debugging aid for
+    hand-written tapes and for what sdfgpu_wasm_lower produces."""
+    magic, version, n_instr, n_prims, n_consts, n_sops = struct.unpack_from("<6I", tape_bytes, 0)
+    if magic != SDFT_MAGIC:
+        raise ValueError("not a tape")
+    off = 32
+    instr = np.frombuffer(tape_bytes, INSTR_DTYPE, n_instr, off); off += 16 * n_instr
+    prims = np.frombuffer(tape_bytes, PRIM_DTYPE, n_prims, off); off += 48 * n_prims
+    consts = np.frombuffer(tape_bytes, "<f4", n_consts, off); off += 4 * n_consts
+    sops = np.frombuffer(tape_bytes, SOP_DTYPE, n_sops, off)
+    op_names = {v: k for k, v in globals().items() if k.startswith("OP_") and isinstance(v, int)}
+    s_names = {v: k for k, v in S.items()}
+    lines = [f"tape v{version}: {n_instr} instructions, {n_prims} primitives, {n_consts} constants, {n_sops} scalar ops"]
+    for pc, i in enumerate(instr):
+        name = op_names.get(int(i["op"]), f"op{int(i['op'])}")
+        lines.append(f"  {pc:3d}  {name:<18s} a={int(i['a'])} b={int(i['b'])} imm={float(i['imm']):g}")
+        if int(i["op"]) == OP_SCALAR:
+            first, count = int(i["a"]), int(i["b"])
+            for k in range(count):
+                o = sops[first + k]
+                n, a, b, c = s_names.get(int(o["op"]), f"s{int(o['op'])}"), int(o["a"]), int(o["b"]), int(o["c"])
+                if n in ("PX", "PY", "PZ"):
+                    text = n.lower()
+                elif n == "CONST":
+                    text = f"const[{a}] = {float(consts[a]):g}" if a < n_consts else f"const[{a}] (out of range)"
+                elif n == "IMM":
+                    text = f"imm 0x{a:08x}"
+                elif n == "OUT":
+                    text = f"A.{('d', 'r', 'g', 'b', 'metallic', 'roughness', 'occlusion')[b] if b < 7 else b} = v{a}"
+                elif n == "SELECT":
+                    text = f"v{a} ? v{b} : v{c}"
+                elif n in ("FNEG", "FABS", "FSQRT", "FFLOOR", "FCEIL", "FTRUNC", "FNEAREST", "IEQZ", "F_FROM_I_S", "F_FROM_I_U",
+                           "I_FROM_F_S", "I_FROM_F_U"):
+                    text = f"{n.lower()} v{a}"
+                else:
+                    text = f"{n.lower()} v{a}, v{b}"
+                lines.append(f"         v{k:<4d} {text}")
+    for k, pr in enumerate(prims):
+        kind = int(pr["kind"])
+        lines.append(f"  prim {k}: {'sphere' if (kind & 0xff) == SHAPE_SPHERE else 'box'} centre {tuple(float(v) for v in pr['center'])} "
+                     f"size {float(pr['size']):g} material {('flat', 'brick', 'normal')[(kind >> 8) & 0xff] if (kind >> 8) & 0xff < 3 else kind >> 8}")
+    return "\n".join(lines)

@@ -409,3 +409,14 @@ def test_scalar_tape_fill_on_gpu(S, oracle):
         v.set_tape(build_tape(T, progs[0])[1])
         with pytest.raises(S.SdfGpuError):
             v.fill_all()
+
+
+def test_disassembler_lists_every_section(S):
+    T = S.tape
+    _, tape = build_tape(T, sphere_with_bands(T))
+    text = T.disassemble(tape)
+    assert "OP_SCALAR" in text and "fsqrt v" in text and "A.d = v" in text and "const[0] = 0.7" in text and "imm 0x00000001" in text
+    demo = T.disassemble(T.demo_tape())
+    assert "OP_POP_DEMO_DIFF" in demo and "box centre" in demo and "material brick" in demo
+    with pytest.raises(ValueError):
+        T.disassemble(b"\0" * 64)
