@@ -135,6 +135,7 @@ struct Lowerer {
     bool malformed = false;
     std::map<uint32_t, int> libm_class;  // function index -> 0 unknown, 1 behaves exactly like C fmodf
     uint32_t recognised_calls = 0;
+    uint32_t skipped_imports = 0;  // calls of void host imports that were skipped
 
     bool fail(const char* fmt, ...) {
         if (err.empty()) {
@@ -911,7 +912,16 @@ struct Lowerer {
     bool enter(State& st, uint32_t fi) {  // arguments are on the stack
         if (fi >= m.funcs.size()) return fail("call of function %u, which does not exist", fi);
         Func& f = m.funcs[fi];
-        if (f.imported) return fail("the guest calls the host import `%s` on the way to its result", f.import_name.c_str());
+        if (f.imported) {
+            // a host function that returns nothing (logging, tracing hooks) cannot influence the result: skipped.
+            // One that returns a value would have to be answered by the host: not lowerable.
+            const FuncType& it = m.types[f.type];
+            if (!it.results.empty()) return fail("the guest calls the host import `%s` on the way to its result", f.import_name.c_str());
+            if (st.stack.size() < it.params.size()) return fail("stack underflow at a call");
+            st.stack.resize(st.stack.size() - it.params.size());
+            ++skipped_imports;
+            return true;
+        }
         if (!scan(f)) return false;
         if (st.frames.size() > 2000) return fail("call depth above 2000");
         const FuncType& ft = m.types[f.type];

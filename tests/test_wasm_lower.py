@@ -565,6 +565,20 @@ def test_what_cannot_be_lowered_says_why(S):
     m.func([I32], [I32], body=[("i32.const", BBP)], export="bounding_box")
     m.func(*SAMPLE_SIG, body=[("i32.const", OUT), X, ("call", imp), ("f32.store", 0), ("i32.const", OUT)], export="sample")
     expect_failure(S, m, -3, "env.host_noise")
+    # ... but a host function that returns nothing (a logging hook) is skipped, in init() and in sample() alike
+    m = Module()
+    log = m.import_func("env", "log_f32", [F32], [])
+    m.data_at(BBP, struct.pack("<6f", -1, -1, -1, 1, 1, 1))
+    m.func([I32], [I32], body=[("i32.const", BBP)], export="bounding_box")
+    m.func([], [], body=[("f32.const", 1.0), ("call", log)], export="init")
+    body = [X, ("call", log)] + store_out(0, [X, Y, "f32.mul"])
+    for k in range(1, 7):
+        body += store_out(k, [("f32.const", 0.0)])
+    m.func(*SAMPLE_SIG, body=body + [("i32.const", OUT)], export="sample")
+    tape = S.wasm.lower(m.build())[0]
+    import orc
+    p = points(10)
+    assert same(orc.tape_sample(tape, p)[:, 0], p[:, 0] * p[:, 1])
     # f64 arithmetic on the position
     m = base_module()
     m.func(*SAMPLE_SIG, body=[("i32.const", OUT), X, "f64.promote_f32", "f64.sqrt", "f32.demote_f64", ("f32.store", 0), ("i32.const", OUT)], export="sample")
