@@ -122,7 +122,7 @@ int sdfgpu_jit_check(const void* tape, size_t tape_bytes, int voxels_per_thread,
  * Returns SDFGPU_OK; SDFGPU_ERR_INVALID for a malformed module or one without the required exports
  * (native.rs:59-63); SDFGPU_ERR_TAPE when the guest does something that has no tape form (an address, loop
  * bound or call target that depends on the position; 64-bit arithmetic on such values; a host import that returns a
- * value -- imports that return nothing, e.g. logging hooks, are skipped; SIMD) --
+ * value -- imports that return nothing, e.g. logging hooks, are skipped and WASI calls answered with errno 0; SIMD) --
  * such an SDF is sampled on the host through sdfgpu_update_surface instead. */
 int sdfgpu_wasm_lower(const void* wasm, size_t wasm_bytes, uint32_t sdf_id, void* tape_out, size_t tape_cap,
                       size_t* tape_len, float bb_out[6], char* log, size_t log_cap);

@@ -914,11 +914,17 @@ struct Lowerer {
         Func& f = m.funcs[fi];
         if (f.imported) {
             // a host function that returns nothing (logging, tracing hooks) cannot influence the result: skipped.
-            // One that returns a value would have to be answered by the host: not lowerable.
+            // One that returns a value would have to be answered by the host: not lowerable, except WASI (below).
             const FuncType& it = m.types[f.type];
-            if (!it.results.empty()) return fail("the guest calls the host import `%s` on the way to its result", f.import_name.c_str());
+            // WASI calls (a wasm32-wasi guest seeds its HashMap with random_get, may query the environment or the
+            // clock while it sets itself up): answered with errno 0 and untouched out-parameters -- "success, nothing
+            // there".  The guest stays self-consistent (it inserts and looks up with the same seeds).
+            const bool wasi = f.import_name.compare(0, 5, "wasi_") == 0 && f.import_name.find(".proc_exit") == std::string::npos;
+            if (!it.results.empty() && !wasi)
+                return fail("the guest calls the host import `%s` on the way to its result", f.import_name.c_str());
             if (st.stack.size() < it.params.size()) return fail("stack underflow at a call");
             st.stack.resize(st.stack.size() - it.params.size());
+            for (uint8_t t : it.results) st.stack.push_back(conc(t, 0));
             ++skipped_imports;
             return true;
         }

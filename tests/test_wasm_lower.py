@@ -579,6 +579,20 @@ def test_what_cannot_be_lowered_says_why(S):
     import orc
     p = points(10)
     assert same(orc.tape_sample(tape, p)[:, 0], p[:, 0] * p[:, 1])
+    # WASI calls during set-up (a wasm32-wasi guest seeds its hasher with random_get) are answered with errno 0
+    m = Module()
+    rnd = m.import_func("wasi_snapshot_preview1", "random_get", [I32, I32], [I32])
+    m.data_at(BBP, struct.pack("<6f", -1, -1, -1, 1, 1, 1))
+    m.func([I32], [I32], body=[("i32.const", BBP)], export="bounding_box")
+    # init: if random_get(5000, 16) != 0 { unreachable }; scale = 2.0 + f32(seed word, left at 0)
+    m.func([], [], body=[("i32.const", 5000), ("i32.const", 16), ("call", rnd), ("if", []), "unreachable", "end",
+                         ("i32.const", 5100), ("f32.const", 2.0), ("i32.const", 5000), ("i32.load", 0), "f32.convert_i32_u", "f32.add",
+                         ("f32.store", 0)], export="init")
+    body = store_out(0, [X, ("i32.const", 5100), ("f32.load", 0), "f32.mul"])
+    for k in range(1, 7):
+        body += store_out(k, [("f32.const", 0.0)])
+    m.func(*SAMPLE_SIG, body=body + [("i32.const", OUT)], export="sample")
+    assert same(orc.tape_sample(S.wasm.lower(m.build())[0], p)[:, 0], p[:, 0] * f32(2.0))
     # f64 arithmetic on the position
     m = base_module()
     m.func(*SAMPLE_SIG, body=[("i32.const", OUT), X, "f64.promote_f32", "f64.sqrt", "f32.demote_f64", ("f32.store", 0), ("i32.const", OUT)], export="sample")
