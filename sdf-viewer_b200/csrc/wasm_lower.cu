@@ -1294,7 +1294,26 @@ struct Lowerer {
                     NEED(1);
                     const Val c = st.stack.back();
                     st.stack.pop_back();
-                    if (c.sym) { fail("br_table on a value that depends on the position"); return failed(); }
+                    if (c.sym) {
+                        // a `match` on a value that depends on the position: every arm is followed to the end of the
+                        // call (the arms leave through different labels, there is no common join point to stop at) and
+                        // the outcomes are chained: index == 0 ? arm 0 : index == 1 ? arm 1 : ... : default
+                        if (n > 64) { fail("br_table with %u position-dependent arms", n); return failed(); }
+                        std::vector<Leaf> arms(n + 1);
+                        ++fork_depth;
+                        for (uint32_t k = 0; k <= n; ++k) {
+                            if (!fork_ok()) { --fork_depth; return failed(); }
+                            State arm = st;
+                            if (branch(arm, targets[k])) arms[k] = finish(*this, arm);
+                            else if (!err.empty()) arms[k] = failed();
+                            else arms[k] = run(arm, finish, nullptr);
+                            if (arms[k].st == ST_FAIL) { --fork_depth; return failed(); }
+                        }
+                        --fork_depth;
+                        Leaf out = arms[n];
+                        for (uint32_t k = n; k-- > 0;) out = merge(node(SDFT_S_IEQ, c.node, node(SDFT_S_IMM, k)), arms[k], out);
+                        return out;
+                    }
                     const uint32_t k = (uint32_t)c.bits;
                     if (branch(st, targets[k < n ? k : n])) return finish(*this, st);
                     if (!err.empty()) return failed();

@@ -90,8 +90,17 @@ class Gen:
         return out
 
     def stmt(self, d):
-        r = self.rng.integers(0, 10)
+        r = self.rng.integers(0, 11)
         can_fork = self.forks < 7 and d < 3
+        if r == 10 and can_fork:  # a `match` on a position-dependent integer: br_table out of nested blocks
+            self.forks += 2
+            n = int(self.rng.integers(2, 4))
+            out = [("block", [])] * (n + 1) + self.iexpr() + [("br_table", list(range(n)), n), "end"]
+            for k in range(n):
+                out += self.stmts(1, d + 1) + [("br", n - 1 - k), "end"]
+            return out
+        if r == 10:
+            r = 1
         if r == 0:  # spill to guest memory (on this path only, when inside a branch)
             return [("i32.const", self.pick(SCRATCH))] + self.fexpr() + [("f32.store", 0)]
         if r < 3 or not can_fork and r >= 5:
