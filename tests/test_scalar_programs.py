@@ -420,3 +420,25 @@ def test_disassembler_lists_every_section(S):
     assert "OP_POP_DEMO_DIFF" in demo and "box centre" in demo and "material brick" in demo
     with pytest.raises(ValueError):
         T.disassemble(b"\0" * 64)
+
+
+def test_every_op_compiles_for_sm100a(S):
+    """One program that uses every scalar op: the specialiser's CUDA for it compiles with NVRTC (sm_100a)."""
+    T = S.tape
+    p = T.ScalarProgram()
+    x, y, z = p.px(), p.py(), p.pz()
+    k, i = p.const(0.75), p.imm(3)
+    vals = [x, y, z, k, i]
+    for name in UNARY:
+        vals.append(p.op(name, vals[len(vals) % 5]))
+    for name in BINARY:
+        vals.append(p.op(name, vals[-1], vals[len(vals) % 7]))
+    vals.append(p.op("SELECT", vals[-1], vals[-2], vals[-3]))
+    for ch in range(7):
+        p.out(ch, vals[-1 - ch])
+    used = {op for op, _, _, _ in p.ops}
+    assert used == set(T.S.values()), sorted(set(T.S.values()) - used)
+    _, tape = build_tape(T, p)
+    for V in (1, 8):
+        src = S.jit_check(tape, V)
+        assert "fmodf(" in src and "sdfw_fmin(" in src and "__float2uint_rz(" in src
