@@ -117,7 +117,8 @@ enum sdft_sop_op {
     SDFT_S_SELECT = 56,    /* v[a] != 0 ? v[b] : v[c]                                        */
     SDFT_S_F_FROM_I_S = 57, SDFT_S_F_FROM_I_U = 58, /* f32.convert_i32_s / _u              */
     SDFT_S_I_FROM_F_S = 59, SDFT_S_I_FROM_F_U = 60, /* i32.trunc_sat_f32_s / _u            */
-    SDFT_S_OUT = 63        /* A[b] = v[a] as f32; b = 0..6: distance, r, g, b, metallic, roughness, occlusion */
+    SDFT_S_OUT = 63        /* A[b] = v[a] as f32; b = 0..6: distance, r, g, b, metallic, roughness, occlusion.
+                            * Yields no value: an operand that names an OUT op is rejected (SDFGPU_ERR_TAPE) */
 };
 
 enum sdft_shape {

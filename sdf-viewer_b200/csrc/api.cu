@@ -746,6 +746,13 @@ int parse_and_lower(sdfgpu_ctx* ctx, const void* tape, size_t tape_bytes, Parsed
                     }
                     if ((n_in >= 1 && o.a >= i) || (n_in >= 2 && o.b >= i) || (n_in >= 3 && o.c >= i))
                         return fail(ctx, SDFGPU_ERR_TAPE, "scalar op %u: operand does not name an earlier value", S.a + i);
+                    // SDFT_S_OUT writes a channel and yields no value: naming it as an operand has no meaning
+                    // (the specialiser emits no register for it)
+                    const uint32_t ins[3] = {o.a, o.b, o.c};
+                    for (int q = 0; q < n_in; ++q)
+                        if (out->sops[S.a + ins[q]].op == SDFT_S_OUT)
+                            return fail(ctx, SDFGPU_ERR_TAPE, "scalar op %u: operand %d names an OUT op, which yields no value",
+                                        S.a + i, q);
                 }
                 I.op = DOP_SCALAR;
                 programs.push_back(pc); programs.push_back(S.a); programs.push_back(S.b);

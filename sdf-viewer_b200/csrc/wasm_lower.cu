@@ -109,7 +109,13 @@ struct State {
     std::vector<Val> globals;
     std::map<uint32_t, Cell> mem;  // overlay over Module::base, keyed by the word's address
     uint32_t pages = 0;
+    // Trap predicate of this path: a node that is non-zero at the positions where the guest would have trapped
+    // before reaching this point (a side of a position-dependent branch that ran into `unreachable` / a failed
+    // bounds check, a zero divisor, a truncation out of range); NO_TRAP = never.  The reference answers a trapped
+    // sample() call with SDFSample::new(1.0, 0) (src/sdf/wasm/native.rs:196-203): the outputs select that there.
+    uint32_t trap = 0xffffffffu;
 };
+constexpr uint32_t NO_TRAP = 0xffffffffu;
 
 struct Node {
     uint32_t op, a, b, c;
@@ -120,6 +126,7 @@ enum Status { ST_OK = 0, ST_TRAP = 1, ST_FAIL = 2, ST_REJOIN = 3 };  // ST_REJOI
 struct Leaf {
     Status st = ST_OK;
     std::vector<Val> vals;
+    uint32_t trap = NO_TRAP;  // State::trap of the path that produced the values
 };
 
 struct Lowerer {
@@ -136,6 +143,8 @@ struct Lowerer {
     std::map<uint32_t, int> libm_class;  // function index -> 0 unknown, 1 behaves exactly like C fmodf
     uint32_t recognised_calls = 0;
     uint32_t skipped_imports = 0;  // calls of void host imports that were skipped
+    uint32_t trap_sides = 0;       // sides of position-dependent branches that end in a trap (folded into the trap predicate)
+    uint32_t trap_ops = 0;         // position-dependent divisions / truncations whose trap condition joined the predicate
 
     bool fail(const char* fmt, ...) {
         if (err.empty()) {
@@ -1045,11 +1054,32 @@ struct Lowerer {
         return true;
     }
 
+    // trap predicates: any non-zero word means "trapped", so OR is the bitwise one
+    uint32_t trap_or(uint32_t t, uint32_t cond) { return t == NO_TRAP ? cond : node(SDFT_S_IOR, t, cond); }
+    uint32_t trap_select(uint32_t cond, uint32_t ta, uint32_t tb) {
+        if (ta == tb) return ta;
+        const uint32_t zero = node(SDFT_S_IMM, 0);
+        return node(SDFT_S_SELECT, cond, ta == NO_TRAP ? zero : ta, tb == NO_TRAP ? zero : tb);
+    }
+
+    // `a` is the outcome where cond_node holds, `b` where it does not
     Leaf merge(uint32_t cond_node, const Leaf& a, const Leaf& b) {
         if (a.st == ST_FAIL || b.st == ST_FAIL) { Leaf l; l.st = ST_FAIL; return l; }
-        if (a.st == ST_TRAP) return b;  // the guest would have trapped on that side: nothing to preserve
-        if (b.st == ST_TRAP) return a;
+        if (a.st == ST_TRAP && b.st == ST_TRAP) return a;
+        if (a.st == ST_TRAP) {  // the guest traps where the condition holds: the other side's values, and the predicate
+            Leaf l = b;
+            l.trap = trap_or(b.trap, cond_node);
+            ++trap_sides;
+            return l;
+        }
+        if (b.st == ST_TRAP) {
+            Leaf l = a;
+            l.trap = trap_or(a.trap, node(SDFT_S_IEQZ, cond_node));
+            ++trap_sides;
+            return l;
+        }
         Leaf out;
+        out.trap = trap_select(cond_node, a.trap, b.trap);
         out.vals.resize(a.vals.size());
         for (size_t i = 0; i < a.vals.size(); ++i) {
             const Val& x = a.vals[i];
@@ -1130,6 +1160,7 @@ struct Lowerer {
                 mrg.mem[kv.first] = Cell{true, node(SDFT_S_SELECT, cond, na, nb)};
             }
         }
+        mrg.trap = trap_select(cond, a.trap, b.trap);
         *out = std::move(mrg);
         return true;
     }
@@ -1143,8 +1174,20 @@ struct Lowerer {
             State mrg;
             if (merge_states(cond, A, B, &mrg)) { *st = std::move(mrg); return true; }
         }
-        if (la.st == ST_REJOIN && lb.st == ST_TRAP) { *st = std::move(A); return true; }  // the trapping side contributes nothing
-        if (la.st == ST_TRAP && lb.st == ST_REJOIN) { *st = std::move(B); return true; }
+        // one side traps: execution continues with the other one, and the positions that took the trapping side
+        // join the trap predicate (A is the side where cond holds)
+        if (la.st == ST_REJOIN && lb.st == ST_TRAP) {
+            A.trap = trap_or(A.trap, node(SDFT_S_IEQZ, cond));
+            ++trap_sides;
+            *st = std::move(A);
+            return true;
+        }
+        if (la.st == ST_TRAP && lb.st == ST_REJOIN) {
+            B.trap = trap_or(B.trap, cond);
+            ++trap_sides;
+            *st = std::move(B);
+            return true;
+        }
         // one side left the construct for good (return, branch further out, unmergeable state): run whatever
         // stopped at the join point to the end as well and merge the final outcomes
         ++fork_depth;
@@ -1515,8 +1558,16 @@ struct Lowerer {
                                 if (op == 0xbc || op == 0xbe) { st.stack.push_back(symv(result_type(op), a.node)); break; }  // reinterpret
                                 // the trapping truncations: identical to the saturating ones wherever the guest does not
                                 // trap (a guest that traps has no defined sample; the reference host substitutes one)
-                                if (op == 0xa8) { st.stack.push_back(symv(T_I32, node(SDFT_S_I_FROM_F_S, a.node))); break; }
-                                if (op == 0xa9) { st.stack.push_back(symv(T_I32, node(SDFT_S_I_FROM_F_U, a.node))); break; }
+                                if (op == 0xa8 || op == 0xa9) {
+                                    // in range (and not NaN): -2^31 <= trunc(x) < 2^31, resp. -1 < x < 2^32
+                                    const uint32_t lo = op == 0xa8 ? node(SDFT_S_FGE, a.node, node_of(conc(T_F32, 0xCF000000u)))   // -2147483648.0f
+                                                                   : node(SDFT_S_FGT, a.node, node_of(conc(T_F32, 0xBF800000u)));  // -1.0f
+                                    const uint32_t hi = node(SDFT_S_FLT, a.node, node_of(conc(T_F32, op == 0xa8 ? 0x4F000000u : 0x4F800000u)));
+                                    st.trap = trap_or(st.trap, node(SDFT_S_IEQZ, node(SDFT_S_IAND, lo, hi)));
+                                    ++trap_ops;
+                                    st.stack.push_back(symv(T_I32, node(op == 0xa8 ? SDFT_S_I_FROM_F_S : SDFT_S_I_FROM_F_U, a.node)));
+                                    break;
+                                }
                                 const uint32_t so = sym_unop(op);
                                 if (so == 0xffffffffu) { fail("instruction 0x%02x on a value that depends on the position has no 32-bit scalar form", op); return failed(); }
                                 st.stack.push_back(symv(result_type(op), node(so, a.node)));
@@ -1538,6 +1589,19 @@ struct Lowerer {
                             if (a.sym || b.sym) {
                                 const uint32_t so = sym_binop(op);
                                 if (so == 0xffffffffu) { fail("instruction 0x%02x on a value that depends on the position has no 32-bit scalar form", op); return failed(); }
+                                if (op >= 0x6d && op <= 0x70) {  // i32.div_s / div_u / rem_s / rem_u trap on a zero divisor, div_s on INT_MIN / -1
+                                    const uint32_t nb_ = node_of(b);
+                                    uint32_t t = node(SDFT_S_IEQZ, nb_);
+                                    if (op == 0x6d)
+                                        t = node(SDFT_S_IOR, t, node(SDFT_S_IAND, node(SDFT_S_IEQ, node_of(a), node(SDFT_S_IMM, 0x80000000u)),
+                                                                     node(SDFT_S_IEQ, nb_, node(SDFT_S_IMM, 0xffffffffu))));
+                                    if (!b.sym) {  // a concrete divisor: the condition is known now
+                                        const uint32_t y = (uint32_t)b.bits;
+                                        if (y == 0) return trapped();
+                                        if (!(op == 0x6d && y == 0xffffffffu)) t = NO_TRAP;
+                                    }
+                                    if (t != NO_TRAP) { st.trap = trap_or(st.trap, t); ++trap_ops; }
+                                }
                                 st.stack.push_back(symv(result_type(op), node(so, node_of(a), node_of(b))));
                                 break;
                             }
@@ -1688,6 +1752,7 @@ static int lower_impl(const void* wasm, size_t wasm_bytes, const void* memory, s
             if (!self.load(s, (uint64_t)p + 4 * i, 4, &v, &is_sym, &sn)) { out.st = ST_FAIL; return out; }
             out.vals.push_back(is_sym ? Lowerer::symv(T_F32, sn) : Lowerer::conc(T_F32, v));
         }
+        out.trap = s.trap;
         return out;
     });
     if (leaf.st == ST_TRAP) { put_log(log, log_cap, "sample traps for every position"); return SDFGPU_ERR_TAPE; }
@@ -1695,7 +1760,13 @@ static int lower_impl(const void* wasm, size_t wasm_bytes, const void* memory, s
 
     // ---- the program: nodes reachable from the seven outputs, in creation (= topological) order
     std::vector<uint32_t> outs(7);
-    for (int i = 0; i < 7; ++i) outs[i] = L.node_of(leaf.vals[i]);
+    for (int i = 0; i < 7; ++i) {
+        outs[i] = L.node_of(leaf.vals[i]);
+        // where the guest would have trapped the reference substitutes SDFSample::new(1.0, zero)
+        // (src/sdf/wasm/native.rs:196-203; src/sdf/mod.rs:121-125): distance 1, everything else 0
+        if (leaf.trap != NO_TRAP)
+            outs[i] = L.node(SDFT_S_SELECT, leaf.trap, L.node_of(Lowerer::conc(T_F32, i == 0 ? 0x3F800000u : 0u)), outs[i]);
+    }
     std::vector<char> live(L.nodes.size(), 0);
     for (uint32_t o : outs) live[o] = 1;
     for (size_t i = L.nodes.size(); i-- > 0;) {
@@ -1762,13 +1833,14 @@ static int lower_impl(const void* wasm, size_t wasm_bytes, const void* memory, s
         return SDFGPU_ERR_INVALID;
     }
     {
-        char buf[200];
-        if (L.recognised_calls)
-            snprintf(buf, sizeof buf, "lowered: %zu scalar ops, %zu constants, %u symbolic branches merged, %u fmodf calls recognised",
-                     sops.size(), used_consts.size(), L.leaves, L.recognised_calls);
-        else
-            snprintf(buf, sizeof buf, "lowered: %zu scalar ops, %zu constants, %u symbolic branches merged", sops.size(),
-                     used_consts.size(), L.leaves);
+        char buf[320];
+        int n = snprintf(buf, sizeof buf, "lowered: %zu scalar ops, %zu constants, %u symbolic branches merged", sops.size(),
+                         used_consts.size(), L.leaves);
+        if (L.recognised_calls) n += snprintf(buf + n, sizeof buf - n, ", %u fmodf calls recognised", L.recognised_calls);
+        if (L.skipped_imports) n += snprintf(buf + n, sizeof buf - n, ", %u void host imports skipped", L.skipped_imports);
+        if (leaf.trap != NO_TRAP)
+            n += snprintf(buf + n, sizeof buf - n, ", position-dependent traps kept (%u branch sides, %u div/trunc ops): those voxels "
+                          "get the reference's fallback sample (1.0, 0)", L.trap_sides, L.trap_ops);
         put_log(log, log_cap, buf);
     }
     return SDFGPU_OK;

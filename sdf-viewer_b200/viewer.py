@@ -221,7 +221,7 @@ class SDFViewer:
     def set_tape(self, tape_bytes):
         buf = (C.c_char * len(tape_bytes)).from_buffer_copy(tape_bytes)
         check(self._lib.sdfgpu_set_tape(self._h, buf, len(tape_bytes)), self._h)
-        self._tape = tape_bytes
+        self._tape = bytes(tape_bytes)
 
     def update(self, sdf, max_passes=0):
         """SDFViewer::update (scene/sdf/mod.rs:128-217).  `sdf` is an `sdf.SDFSurface` (its tape is
@@ -230,8 +230,11 @@ class SDFViewer:
         changed = None
         if sdf is not None:
             changed = sdf.changed()
-            if self._tape is None or changed is not None:
-                self.set_tape(sdf.tape())
+            # the reference samples whatever surface it is handed (scene/sdf/mod.rs:128): another surface, or the
+            # same one with new parameters, must not be evaluated through the previous tape
+            tape = bytes(sdf.tape())
+            if self._tape is None or tape != self._tape:
+                self.set_tape(tape)
         it = C.c_uint64()
         box = _f6(changed) if changed is not None else None
         check(self._lib.sdfgpu_update(self._h, box, int(max_passes), C.byref(it)), self._h)
@@ -276,6 +279,7 @@ class SDFViewer:
 
     def reset(self, loading_passes):
         check(self._lib.sdfgpu_reset(self._h, int(loading_passes)), self._h)
+        self._tape = None  # set_sdf rebuilds the viewer (scene/mod.rs:154-155): the next update sends its surface's tape
 
     def download(self, tex0=True, tex1=True, out0=None, out1=None):
         """The CPU-side `Vec<[f32;4]>` volumes (scene/sdf/mod.rs:23-25) of this handle's own slices,

@@ -11,8 +11,6 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
-    config.addinivalue_line("markers", "gpu_next: needs a CUDA device and has not been run on one yet; skipped unless "
-                                       "SDFGPU_RUN_NEXT=1 (kept out of `-m gpu` until verified)")
 
 
 @pytest.fixture(scope="session")

@@ -35,15 +35,23 @@ def sample_indices(dims, n, rng, z_range=None):
     return np.concatenate([idx, special]).astype(np.uint32)
 
 
-@pytest.mark.parametrize("workload,side", [("demo", 256), ("demo", 512), ("csg", 512)])
+@pytest.mark.parametrize("workload,side", [("demo", 256), ("demo", 512), ("csg", 512), ("wasm", 512)])
 def test_full_size_subset_parity(S, oracle, workload, side):
-    """BASELINE configs 2 / 3 and the bench workload: 256^3 and 512^3, default fill path (specialised kernel)."""
-    tape = S.tape.demo_tape() if workload == "demo" else S.tape.csg_tape()
+    """BASELINE configs 2 / 3 and the bench workload: 256^3 and 512^3, default fill path (specialised kernel).
+    "wasm": the reference's SDFDemo as a WebAssembly guest (hand-compiled, tests/test_wasm_lower.py), lowered to a scalar
+    program by sdfgpu_wasm_lower and filled on the GPU; the expected values come from the oracle's DIRECT restatement
+    of SDFDemo::sample (the hand-written demo tape), not from the lowered tape."""
+    if workload == "wasm":
+        import test_wasm_lower
+        tape, _, _ = S.wasm.lower(test_wasm_lower.guest_reference_demo().build())
+        oracle_tape = S.tape.demo_tape()
+    else:
+        tape = oracle_tape = S.tape.demo_tape() if workload == "demo" else S.tape.csg_tape()
     dims = (side, side, side)
     rng = np.random.default_rng(side)
     idx = sample_indices(dims, 300_000, rng)
     o = oracle.Viewer(BB, dims, 2, alloc=False)
-    want0, want1 = o.sample_voxels(oracle.Sampler(tape=tape), idx)
+    want0, want1 = o.sample_voxels(oracle.Sampler(tape=oracle_tape), idx)
     with S.SDFViewer.from_bb(BB, side, 2) as v:
         v.set_tape(tape)
         v.fill_all()

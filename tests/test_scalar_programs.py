@@ -7,8 +7,9 @@ CPU-side evidence (no GPU in the build container):
     few intrinsics it uses, against the oracle -- this checks the code generator's wiring;
   * NVRTC compiles that text for sm_100a (sdfgpu_jit_check);
   * malformed programs are rejected.
-GPU: `test_scalar_tape_sphere_fills_on_gpu` (ran on a B200); the wider sweep `test_scalar_tape_fill_on_gpu` is still
-marked gpu_next (not yet run on a B200)."""
+GPU (`-m gpu`): `test_scalar_tape_sphere_fills_on_gpu` and the wider sweep `test_scalar_tape_fill_on_gpu` (random
+programs x voxels-per-thread).  The sweep's first B200 run (round 2) caught the compiler folding `__float2uint_rz` of a
+constant NaN word to 1 in the V = 1 kernel; the conversions now spell their special cases out (jit.cu)."""
 import ctypes as C
 import os
 import re
@@ -356,6 +357,29 @@ def test_malformed_scalar_programs_are_rejected(S):
     t.scalar(sphere_with_bands(T)).emit(T.OP_END)
     with pytest.raises(S.SdfGpuError):
         S.jit_check(t.build()[:-16], 2)
+    # an operand that names an OUT op (which yields no value): PX, OUT, FNEG v1, OUT -- the validator used to accept
+    # it and the specialiser then emitted an undefined identifier
+    p = T.ScalarProgram()
+    x = p.px()
+    o = p.out(0, x)
+    p.out(1, p.op("FNEG", o))
+    t = T.TapeBuilder()
+    t.scalar(p).emit(T.OP_END)
+    with pytest.raises(S.SdfGpuError) as e:
+        S.tape_validate(t.build())
+    assert e.value.code == -3 and "OUT" in str(e.value)
+    # every single-operand mutation that points a later op at an OUT is rejected as well
+    base = sphere_with_bands(T)
+    outs = [i for i, o_ in enumerate(base.ops) if o_[0] == T.S["OUT"]]
+    assert outs
+    for i in outs[:-1]:
+        t = T.TapeBuilder()
+        t.scalar(base)
+        t.sops.append((T.S["FNEG"], i, 0, 0))
+        t.instr[0] = (T.OP_SCALAR, 0, len(t.sops), 0.0)
+        t.emit(T.OP_END)
+        with pytest.raises(S.SdfGpuError):
+            S.tape_validate(t.build())
 
 
 def _have_gpu(S):
@@ -382,12 +406,10 @@ def test_scalar_tape_sphere_fills_on_gpu(S, oracle):
     assert same_f32(t0, o.tex0) and same_f32(t1, o.tex1)
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 def test_scalar_tape_fill_on_gpu(S, oracle):
-    """GPU run of scalar-program tapes, bit-exact against the oracle.  NOT part of `-m gpu` yet: written after
-    this round's GPU budget was spent; run with SDFGPU_RUN_NEXT=1 on a B200 and move to the gpu marker."""
-    if not os.environ.get("SDFGPU_RUN_NEXT") or not _have_gpu(S):
-        pytest.skip("set SDFGPU_RUN_NEXT=1 on a GPU box")
+    """GPU run of scalar-program tapes (a hand-written one and random ones, every voxels-per-thread variant),
+    bit-exact against the oracle."""
     T = S.tape
     dims = (40, 36, 32)
     rng = np.random.default_rng(7)

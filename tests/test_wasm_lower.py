@@ -7,7 +7,7 @@ data segments, helper calls, call_indirect through a table (trait objects), loop
 br_if / if-else / early returns on values that depend on the position, integer work on truncated coordinates.
 Each lowered tape is evaluated by the oracle's interpreter and compared bit for bit with the same formula written
 in numpy float32; the specialiser's CUDA for it must compile (NVRTC, sm_100a).  Two of the guests also fill a grid on
-the GPU (`-m gpu`, ran on a B200); the sweep over all of them is still marked gpu_next."""
+the GPU (`-m gpu`, ran on a B200), as does the sweep over all of them."""
 import os
 import struct
 
@@ -643,18 +643,86 @@ def test_mutated_modules_never_crash_the_lowering(S, monkeypatch):
     assert outcomes["invalid"] > 100 and sum(outcomes.values()) == 1500
 
 
-def test_traps_on_one_side_of_a_branch_are_dropped(S, oracle):
-    """`if x < -2 { unreachable }` (a bounds check the compiler left in): the trapping side contributes nothing."""
+TRAP_SAMPLE = np.array([1.0, 0, 0, 0, 0, 0, 0], f32)  # SDFSample::new(1.0, zero), src/sdf/wasm/native.rs:196-203
+
+
+def test_position_dependent_traps_give_the_reference_fallback_sample(S, oracle):
+    """Where the guest would trap, the reference logs the error and uses SDFSample::new(1.0, zero) for that voxel
+    (src/sdf/wasm/native.rs:196-203).  The lowering keeps a trap predicate (the branch conditions that lead to
+    `unreachable`, zero divisors, truncations out of range) and selects that sample where it holds."""
+    # (a) `if x < -0.25 { unreachable }` -- a bounds check the compiler left in
     m = base_module()
-    body = [X, ("f32.const", -2.0), "f32.lt", ("if", []), "unreachable", "end"] + store_out(0, [X, Y, "f32.add"])
+    body = [X, ("f32.const", -0.25), "f32.lt", ("if", []), "unreachable", "end"] + store_out(0, [X, Y, "f32.add"])
     for k in range(1, 7):
         body += store_out(k, [("f32.const", 0.125 * k)])
     m.func(*SAMPLE_SIG, body=body + [("i32.const", OUT)], export="sample")
     tape, _, summary = lowered(S, oracle, m)
-    p = points(40)
+    p = points(200)
     got = oracle.tape_sample(tape, p)
-    assert same(got[:, 0], p[:, 0] + p[:, 1]) and same(got[:, 3], np.full(len(p), 0.375, f32))
-    assert "1 symbolic branches" in summary
+    want = np.tile(np.array([0, 0.125, 0.25, 0.375, 0.5, 0.625, 0.75], f32), (len(p), 1))
+    want[:, 0] = p[:, 0] + p[:, 1]
+    trapped = p[:, 0] < f32(-0.25)
+    assert 20 < trapped.sum() < 180
+    want[trapped] = TRAP_SAMPLE
+    assert same(got, want)
+    assert "1 symbolic branches" in summary and "traps kept (1 branch sides, 0 div/trunc ops)" in summary
+
+    # (b) a trap inside a nested branch, on the else side, with the other sides rejoining
+    m = base_module()
+    body = [X, ("f32.const", 0.0), "f32.gt", ("if", [F32]),
+            Y, ("f32.const", 0.5), "f32.gt", ("if", [F32]), ("f32.const", 2.0), "else", "unreachable", "end",
+            "else", ("f32.const", 3.0), "end", ("local.set", 5)]
+    body += store_out(0, [("local.get", 5)])
+    for k in range(1, 7):
+        body += store_out(k, [Z])
+    m.func(*SAMPLE_SIG, locals=[F32], body=body + [("i32.const", OUT)], export="sample")
+    tape, _, summary = lowered(S, oracle, m)
+    got = oracle.tape_sample(tape, p)
+    want = np.repeat(p[:, 2:3], 7, axis=1).astype(f32)
+    want[:, 0] = np.where(p[:, 0] > 0, f32(2.0), f32(3.0))
+    want[(p[:, 0] > 0) & ~(p[:, 1] > f32(0.5))] = TRAP_SAMPLE
+    assert same(got, want)
+
+    # (c) integer division by a position-dependent divisor: traps where trunc(x * 4) == 0; and INT_MIN / -1
+    m = base_module()
+    q = [X, ("f32.const", 4.0), "f32.mul", ("i32.trunc_sat_f32_s",)]
+    body = store_out(0, [("i32.const", 100)] + q + ["i32.div_s", "f32.convert_i32_s"])
+    body += store_out(1, [("i32.const", 100)] + q + ["i32.rem_u", "f32.convert_i32_u"])
+    body += store_out(2, [("i32.const", -0x80000000), Y, ("f32.const", 0.0), "f32.lt", ("if", [I32]), ("i32.const", -1), "else",
+                          ("i32.const", 7), "end", "i32.div_s", "f32.convert_i32_s"])
+    for k in range(3, 7):
+        body += store_out(k, [Z])
+    m.func(*SAMPLE_SIG, body=body + [("i32.const", OUT)], export="sample")
+    tape, _, summary = lowered(S, oracle, m)
+    got = oracle.tape_sample(tape, p)
+    d = np.trunc(p[:, 0] * f32(4)).astype(np.int64)
+    want = np.repeat(p[:, 2:3], 7, axis=1).astype(f32)
+    dz = np.where(d == 0, 1, d)
+    want[:, 0] = (np.sign(dz) * (100 // np.abs(dz))).astype(f32)
+    want[:, 1] = (100 % (dz & 0xFFFFFFFF)).astype(f32)
+    want[:, 2] = f32(-0x80000000 // 7 + 1)  # truncating division
+    want[(d == 0) | (p[:, 1] < 0)] = TRAP_SAMPLE
+    assert (d == 0).sum() > 10
+    assert same(got, want)
+    assert "div/trunc ops" in summary
+
+    # (d) the trapping truncation: i32.trunc_f32_s(x * 3e9) traps outside [-2^31, 2^31) and on NaN
+    m = base_module()
+    body = store_out(0, [X, ("f32.const", 3.0e9), "f32.mul", "i32.trunc_f32_s", "f32.convert_i32_s"])
+    body += store_out(1, [Y, ("f32.const", 5.0e9), "f32.mul", "i32.trunc_f32_u", "f32.convert_i32_u"])
+    for k in range(2, 7):
+        body += store_out(k, [Z])
+    m.func(*SAMPLE_SIG, body=body + [("i32.const", OUT)], export="sample")
+    tape, _, summary = lowered(S, oracle, m)
+    got = oracle.tape_sample(tape, p)
+    a, b = p[:, 0] * f32(3.0e9), p[:, 1] * f32(5.0e9)
+    ok = (a >= f32(-2147483648.0)) & (a < f32(2147483648.0)) & (b > f32(-1.0)) & (b < f32(4294967296.0))
+    want = np.repeat(p[:, 2:3], 7, axis=1).astype(f32)
+    want[:, 0] = np.where(ok, np.trunc(np.where(ok, a, 0)).astype(np.int64), 0).astype(f32)
+    want[:, 1] = np.where(ok, np.trunc(np.where(ok, b, 0)).astype(np.int64), 0).astype(f32)
+    want[~ok] = TRAP_SAMPLE
+    assert 10 < ok.sum() < len(p) - 10
+    assert same(got, want)
 
 
 def test_symbolic_words_in_memory_are_overwritten_whole_or_not_at_all(S, oracle):
@@ -759,13 +827,10 @@ def test_lowered_guest_fills_on_gpu(S, oracle, name):
     assert same(t0, o.tex0) and same(t1, o.tex1)
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 def test_lowered_guests_fill_on_gpu(S, oracle):
-    """GPU run of the lowered guests, bit-exact against the oracle's interpretation of the same tape.  Not in
-    `-m gpu` yet (no GPU budget was left when this was written): SDFGPU_RUN_NEXT=1 on a B200."""
-    from test_scalar_programs import _have_gpu
-    if not os.environ.get("SDFGPU_RUN_NEXT") or not _have_gpu(S):
-        pytest.skip("set SDFGPU_RUN_NEXT=1 on a GPU box")
+    """GPU run of every lowered guest (incl. the reference's SDFDemo hand-compiled to WebAssembly), bit-exact
+    against the oracle's interpretation of the same tape."""
     dims = (40, 36, 32)
     makers = {name: make for name, (make, _) in GUESTS.items()}
     makers["reference_demo"] = guest_reference_demo
