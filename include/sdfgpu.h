@@ -31,6 +31,8 @@ extern "C" {
 #endif
 
 typedef struct sdfgpu_ctx sdfgpu_ctx;
+struct sdfgpu_camera;  /* defined below (trace) */
+struct sdfgpu_surface; /* defined below (update from an SDFSurface) */
 
 typedef enum sdfgpu_status {
     SDFGPU_OK = 0,
@@ -65,7 +67,8 @@ int sdfgpu_create_voxels(const float bb[6], const uint32_t voxels[3], uint32_t l
 int sdfgpu_create_slab(const float bb[6], const uint32_t voxels[3], uint32_t loading_passes,
                        int device, uint32_t z_begin, uint32_t z_end, sdfgpu_ctx** out);
 
-/* Fused halo exchange between slab handles that live in different processes on one node (one
+/* (Earlier, lower-level form of the halo exchange, kept for hosts that order the ranks themselves; linked handles
+ * -- below -- supersede it.)  Fused halo exchange between slab handles that live in different processes on one node (one
  * process per GPU): a handle exports CUDA IPC handles of its two volumes (2 x 64 bytes:
  * cudaIpcMemHandle_t of tex0, then of tex1); its neighbours attach them (side 0 = the neighbour
  * below this handle, 1 = above; [peer_z_lo, peer_z_hi) = the neighbour's stored slices).  From then
@@ -77,6 +80,78 @@ int sdfgpu_ipc_export(sdfgpu_ctx* ctx, void* handles, size_t handles_bytes);
 int sdfgpu_ipc_attach(sdfgpu_ctx* ctx, int side, const void* handles, size_t handles_bytes,
                       uint32_t peer_z_lo, uint32_t peer_z_hi);
 int sdfgpu_ipc_detach(sdfgpu_ctx* ctx);
+
+/* ------------------------------------------------------- multi-GPU: linked slabs
+ *
+ * Z-sharded operation of slab handles with no collective library and no host synchronisation between ranks.  Not in
+ * the reference (one process, one thread: src/app/scene/mod.rs:22-31,158-225).  Two ways in:
+ *
+ *  (1) ONE PROCESS drives every GPU (what a drop-in for the reference's single-threaded scene needs): sdfgpu_group_*
+ *      below -- sdfgpu_group_create_mask(bb, max_voxels_side, passes, device_mask, ...) is SDFViewer::from_bb over the
+ *      devices of the mask.
+ *  (2) ONE PROCESS PER GPU: every rank creates its slab (sdfgpu_create_slab: the slabs tile [0, D) in rank order, none
+ *      empty), calls sdfgpu_link_export, the SDFGPU_LINK_BLOB_BYTES blobs of all ranks are gathered by any means (they
+ *      hold CUDA IPC handles: same node only), and every rank calls sdfgpu_link_attach with all of them.
+ *
+ * Linking maps the neighbours' volumes and every rank's arena (flags, ray queues, the presenter's frame) into this
+ * handle's address space.  From then on these entry points are COLLECTIVE -- every rank calls them in the same order
+ * with the same arguments: sdfgpu_fill_all, sdfgpu_update, sdfgpu_update_surface, sdfgpu_resample_box, sdfgpu_reset,
+ * sdfgpu_commit, sdfgpu_trace_rgba8 / sdfgpu_trace_linked.
+ *   fill:  one launch; the tiles of the first and last own slice go first, the kernel releases a flag when they are
+ *          complete, and the copy engines push them into the neighbours' halo slices over NVLink while the interior is
+ *          still being filled.  update / resample_box push after their last pass, and only the faces a dirty box touches.
+ *   trace: exact.  A ray marches on the rank that owns the lower z tap of its texture fetch and is handed to the
+ *          neighbour (position, t, step count) when it leaves that rank's slices; `world` rounds of one kernel.  The
+ *          frame equals sdfgpu_trace_rgba8 of ONE handle holding the whole grid bit for bit (RGBA8, depth, and the
+ *          G-buffer but for the normals of hits next to a slab face).  Finished pixels are stored straight into the frame
+ *          of rank 0 (the presenter), which alone receives rgba8 / depth / gbuf; the other ranks pass NULL.
+ * Link a handle right after creating it (volumes still AIR_DIST), use frames of at most max_width * max_height pixels,
+ * and detach every rank before destroying any of them.  SDFGPU_LINK_GBUF reserves a G-buffer frame (tests). */
+#define SDFGPU_LINK_BLOB_BYTES 320
+#define SDFGPU_LINK_GBUF 1u
+int sdfgpu_link_export(sdfgpu_ctx* ctx, uint32_t rank, uint32_t world, uint32_t max_width, uint32_t max_height,
+                       uint32_t flags, void* blob, size_t blob_bytes);
+int sdfgpu_link_attach(sdfgpu_ctx* ctx, const void* blobs, uint32_t world);
+int sdfgpu_link_detach(sdfgpu_ctx* ctx);
+/* The collective trace of a linked handle (sdfgpu_trace_rgba8 forwards here with want_gbuf = 0).  want_gbuf must be
+ * the same on every rank; outputs are written on rank 0 only (any may be NULL). */
+int sdfgpu_trace_linked(sdfgpu_ctx* ctx, const struct sdfgpu_camera* cam, uint32_t width, uint32_t height, int want_gbuf,
+                        uint8_t* rgba8, float* depth, float* gbuf);
+/* The same, enqueued only (no host synchronisation, the counterpart of sdfgpu_trace_device): the frame stays in the
+ * presenter's HBM; rank 0 receives device pointers valid until its next trace, the other ranks NULL. */
+int sdfgpu_trace_linked_device(sdfgpu_ctx* ctx, const struct sdfgpu_camera* cam, uint32_t width, uint32_t height,
+                               int want_gbuf, uint8_t** rgba8_dev, float** depth_dev, float** gbuf_dev);
+
+/* The single-process form: a group owns one linked slab handle per device and runs every collective call on all of
+ * them (round by round for the trace).  `devices` may name a device more than once (the tests shard a grid over
+ * several handles of one GPU).  Mirrors the SDFViewer surface: from_bb / new_voxels, update, commit, the volumes,
+ * and the frame of `volume.render` (scene/mod.rs:168-215). */
+typedef struct sdfgpu_group sdfgpu_group;
+int sdfgpu_group_create(const float bb[6], const uint32_t voxels[3], uint32_t loading_passes, const int* devices,
+                        uint32_t n_devices, uint32_t max_width, uint32_t max_height, uint32_t flags, sdfgpu_group** out);
+int sdfgpu_group_create_mask(const float bb[6], uint32_t max_voxels_side, uint32_t loading_passes, uint32_t device_mask,
+                             uint32_t max_width, uint32_t max_height, sdfgpu_group** out);
+void sdfgpu_group_destroy(sdfgpu_group* g);
+uint32_t sdfgpu_group_size(const sdfgpu_group* g);
+sdfgpu_ctx* sdfgpu_group_rank(sdfgpu_group* g, uint32_t rank); /* a rank's handle: options, info, its own slices */
+const char* sdfgpu_group_last_error(const sdfgpu_group* g);
+int sdfgpu_group_set_tape(sdfgpu_group* g, const void* tape, size_t tape_bytes);
+int sdfgpu_group_update(sdfgpu_group* g, const float* changed_box, uint32_t max_passes, uint64_t* iterations);
+int sdfgpu_group_update_surface(sdfgpu_group* g, const struct sdfgpu_surface* sdf, double max_delta_seconds,
+                                uint64_t* iterations);
+int sdfgpu_group_fill_all(sdfgpu_group* g);
+int sdfgpu_group_resample_box(sdfgpu_group* g, const float box[6], uint64_t* voxels_touched);
+int sdfgpu_group_commit(sdfgpu_group* g);
+int sdfgpu_group_reset(sdfgpu_group* g, uint32_t loading_passes);
+int sdfgpu_group_set_option(sdfgpu_group* g, const char* key, int64_t value);
+int sdfgpu_group_sync(sdfgpu_group* g);
+int sdfgpu_group_loading_state(const sdfgpu_group* g, uint64_t* len, uint64_t* total_iterations,
+                               uint32_t* passes_left, uint32_t* passes);
+int sdfgpu_group_download(sdfgpu_group* g, float* tex0, float* tex1); /* the whole grid, W*H*D texels each */
+int sdfgpu_group_trace_rgba8(sdfgpu_group* g, const struct sdfgpu_camera* cam, uint32_t width, uint32_t height,
+                             uint8_t* rgba8, float* depth);
+int sdfgpu_group_trace(sdfgpu_group* g, const struct sdfgpu_camera* cam, uint32_t width, uint32_t height,
+                       uint8_t* rgba8, float* depth, float* gbuf); /* gbuf needs SDFGPU_LINK_GBUF at creation */
 
 /* Dropping the SDFViewer (scene/mod.rs:154-155 rebuilds it on every set_sdf). */
 void sdfgpu_destroy(sdfgpu_ctx* ctx);
@@ -394,7 +469,9 @@ uint64_t sdfgpu_launch_count(const sdfgpu_ctx* ctx);
  *                  through a texture object in point mode (TMU + block-linear layout, exact fp32 blend: same
  *                  frame); 3 the array with hardware LINEAR filtering (one fetch per step, 8-bit weights:
  *                  a fast mode OUTSIDE the 1e-5 parity bar).  1-3 pay off when many frames are traced per fill
- *   "trace_variant" 0 heavy-first 8x8 tiles (default) | 1 plain 2-D grid
+ *   "trace_variant" 0 heavy-first 8x8 tiles | 1 plain 2-D grid | 2 persistent warps pulling 8x4 tiles from a queue,
+ *                  explicit warp-ballot exit (the kernel linked handles always use); same frame bit for bit
+ *   "link_wait_mode" 0 cuStreamWaitValue32 when the driver has it (default) | 1 spin-wait kernels; before link_attach
  *   "fill_program" 0 auto (kernel specialised for the tape structure, else built-in demo program,
  *                  else interpreter) | 1 interpreter | 2 built-in or interpreter | 3 specialised or fail */
 int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value);

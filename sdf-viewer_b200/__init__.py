@@ -9,6 +9,6 @@ from .sdf import SDFSurface, SDFDemo, TapeSDF  # noqa: F401
 from .loading import LoadingManager, NativeLoadingManager  # noqa: F401
 from .wasm import WasmSDF, WasmLoweringError  # noqa: F401
 from .viewer import (  # noqa: F401
-    SDFViewer, Camera, Rays, SdfGpuError, GBUF_FLOATS, dims_from_bb, default_camera, look_at_camera, camera_rays,
+    SDFViewer, SDFViewerGroup, Camera, Rays, SdfGpuError, GBUF_FLOATS, dims_from_bb, default_camera, look_at_camera, camera_rays,
     jit_check, tape_validate,
 )

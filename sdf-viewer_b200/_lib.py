@@ -17,6 +17,8 @@ SDFGPU_ERR_CUDA = -2
 SDFGPU_ERR_TAPE = -3
 SDFGPU_ERR_STATE = -4
 GBUF_FLOATS = 16
+LINK_BLOB_BYTES = 320
+LINK_GBUF = 1
 
 
 class SdfGpuError(RuntimeError):
@@ -86,6 +88,30 @@ SIGNATURES = {
     "sdfgpu_ipc_export": (C.c_int, [_vp, _vp, C.c_size_t]),
     "sdfgpu_ipc_attach": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, _u32, _u32]),
     "sdfgpu_ipc_detach": (C.c_int, [_vp]),
+    "sdfgpu_link_export": (C.c_int, [_vp, _u32, _u32, _u32, _u32, _u32, _vp, C.c_size_t]),
+    "sdfgpu_link_attach": (C.c_int, [_vp, _vp, _u32]),
+    "sdfgpu_link_detach": (C.c_int, [_vp]),
+    "sdfgpu_trace_linked": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, C.c_int, _vp, _vp, _vp]),
+    "sdfgpu_trace_linked_device": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, C.c_int, _vpp, _vpp, _vpp]),
+    "sdfgpu_group_create": (C.c_int, [_fp, _u32p, _u32, C.POINTER(C.c_int), _u32, _u32, _u32, _u32, _vpp]),
+    "sdfgpu_group_create_mask": (C.c_int, [_fp, _u32, _u32, _u32, _u32, _u32, _vpp]),
+    "sdfgpu_group_destroy": (None, [_vp]),
+    "sdfgpu_group_size": (_u32, [_vp]),
+    "sdfgpu_group_rank": (_vp, [_vp, _u32]),
+    "sdfgpu_group_last_error": (C.c_char_p, [_vp]),
+    "sdfgpu_group_set_tape": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "sdfgpu_group_update": (C.c_int, [_vp, _fp, _u32, _u64p]),
+    "sdfgpu_group_update_surface": (C.c_int, [_vp, C.POINTER(Surface), C.c_double, _u64p]),
+    "sdfgpu_group_fill_all": (C.c_int, [_vp]),
+    "sdfgpu_group_resample_box": (C.c_int, [_vp, _fp, _u64p]),
+    "sdfgpu_group_commit": (C.c_int, [_vp]),
+    "sdfgpu_group_reset": (C.c_int, [_vp, _u32]),
+    "sdfgpu_group_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
+    "sdfgpu_group_sync": (C.c_int, [_vp]),
+    "sdfgpu_group_loading_state": (C.c_int, [_vp, _u64p, _u64p, _u32p, _u32p]),
+    "sdfgpu_group_download": (C.c_int, [_vp, _vp, _vp]),
+    "sdfgpu_group_trace_rgba8": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, _vp, _vp]),
+    "sdfgpu_group_trace": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, _vp, _vp, _vp]),
     "sdfgpu_destroy": (None, [_vp]),
     "sdfgpu_last_error": (C.c_char_p, [_vp]),
     "sdfgpu_dims": (C.c_int, [_vp, _u32p]),
@@ -164,4 +190,10 @@ def load():
 def check(rc, ctx=None):
     if rc != SDFGPU_OK:
         msg = load().sdfgpu_last_error(ctx)
+        raise SdfGpuError(rc, msg.decode("utf-8", "replace") if msg else "")
+
+
+def check_group(rc, group=None):
+    if rc != SDFGPU_OK:
+        msg = load().sdfgpu_group_last_error(group)
         raise SdfGpuError(rc, msg.decode("utf-8", "replace") if msg else "")

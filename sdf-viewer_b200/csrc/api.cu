@@ -17,7 +17,7 @@
 #include <thread>
 #include <vector>
 
-#include "sdfgpu_internal.h"
+#include "sdfgpu_ctx.h"
 
 using namespace sdfgpu;
 
@@ -32,180 +32,9 @@ namespace {
 
 thread_local std::string g_thread_error;
 
-// src/app/scene/sdf/loading.rs:108-115
-uint32_t prev_power_of_2(uint32_t x) {
-    x |= x >> 1; x |= x >> 2; x |= x >> 4; x |= x >> 8; x |= x >> 16;
-    return x - (x >> 1);
-}
-
-struct LoadingState {  // LoadingManager at pass granularity, loading.rs:5-19
-    uint64_t limits[3] = {0, 0, 0};
-    uint64_t passes = 0;
-    uint64_t step_size = 0;
-    uint64_t next[3] = {0, 0, 0};  // next_index: only the host-sampled path stops inside a pass
-    uint64_t iterations = 0;       // iterations done in the current pass (0 between passes)
-    uint64_t total_iterations = 0;
-
-    void reset(uint64_t p) {  // :37-43
-        passes = p;
-        const uint32_t e = (uint32_t)(p > 1 ? p : 1) - 1;
-        step_size = e < 63 ? (uint64_t)1 << e : (uint64_t)1 << 62;
-        next[0] = next[1] = next[2] = 0;
-        iterations = 0;
-        total_iterations = 0;
-    }
-    uint64_t pass_items(uint64_t s) const {
-        return ((limits[0] + s - 1) / s) * ((limits[1] + s - 1) / s) * ((limits[2] + s - 1) / s);
-    }
-    uint64_t len() const {  // :80-89
-        uint64_t s = step_size, it = 0;
-        while (s > 0) {
-            it += pass_items(s);
-            s = prev_power_of_2((uint32_t)(s - 1));
-        }
-        return it - iterations;
-    }
-    uint32_t passes_left() const {  // :99-105
-        if (step_size == 0) return 0;
-        return (uint32_t)log2f((float)step_size) + 1;
-    }
-    // Up to `max_iters` consecutive iterations of next() (:50-76) that lie in one x row: they visit
-    // (x0 + i * step, y, z) for i < take.  Returns take (0 when loading is done) and advances the
-    // cursor and the counters exactly as `take` calls of next() would; *pass_end is set when the last
-    // of them ended the pass (step_size is then already the next pass's).
-    uint64_t next_row(uint64_t max_iters, uint64_t* x0, uint64_t* y, uint64_t* z, uint64_t* step, bool* pass_end) {
-        *pass_end = false;
-        if (step_size == 0 || max_iters == 0) return 0;
-        const uint64_t s = step_size;
-        *x0 = next[0]; *y = next[1]; *z = next[2]; *step = s;
-        // next() yields next_index even when it lies outside the limits (an empty axis): one iteration
-        const uint64_t row_left = next[0] < limits[0] ? (limits[0] - next[0] + s - 1) / s : 1;
-        const uint64_t take = row_left < max_iters ? row_left : max_iters;
-        iterations += take;
-        total_iterations += take;
-        next[0] += take * s;
-        if (next[0] >= limits[0]) {
-            next[0] = 0;
-            next[1] += s;
-            if (next[1] >= limits[1]) {
-                next[1] = 0;
-                next[2] += s;
-                if (next[2] >= limits[2]) {
-                    step_size = prev_power_of_2((uint32_t)(s - 1));
-                    next[0] = next[1] = next[2] = 0;
-                    iterations = 0;
-                    *pass_end = true;
-                }
-            }
-        }
-        return take;
-    }
-    void finish_pass() {  // the rest of the current pass at once, then the tail of next(), :67-71
-        total_iterations += pass_items(step_size) - iterations;
-        step_size = prev_power_of_2((uint32_t)(step_size - 1));
-        next[0] = next[1] = next[2] = 0;
-        iterations = 0;
-    }
-};
-
 }  // namespace
 
-struct sdfgpu_ctx {
-    int device = 0;
-    int sm_count = 0;
-    cudaStream_t stream = nullptr;
-    float bb[6];
-    uint32_t dims[3];
-    uint32_t z_begin = 0, z_end = 0, z_lo = 0, z_hi = 0;
-    float4* tex0 = nullptr;
-    float4* tex1 = nullptr;
-    size_t stored_texels = 0;
-    LoadingState lm;
-    bool has_changed_box = false;
-    float changed_box[6];
-    bool changed_box_while_loading = false;
-    // What is known about the volume without reading it: 0 = every stored voxel holds AIR_DIST (fresh /
-    // reset); s > 0 = exactly the lattice points of step s (power of two) have been sampled, the rest hold
-    // AIR_DIST; 1 = every voxel has been sampled; -1 = unknown (the conditional passes read tex0.r).
-    int64_t known_step = 0;
-    float lod = 1.0f;            // SDFViewerMaterial::lod_dist_between_samples, material.rs:27
-    bool filter_linear = false;  // GL filter state: NEAREST until a commit at lod == 1 (mod.rs:110-111,227-238)
-    // tape
-    bool has_tape = false;
-    std::vector<unsigned char> img_host;
-    unsigned char* img_dev = nullptr;
-    size_t img_dev_cap = 0;
-    TapeImageHeader hdr;
-    std::vector<uint32_t> opcodes;  // lowered opcode sequence (+ scalar programs' text) = the tape's structure (JIT cache key)
-    uint32_t n_top_ops = 0;         // opcodes up to and including DOP_END
-    bool has_scalar = false;        // the tape runs scalar programs: only the specialised (NVRTC) kernel evaluates them
-    bool structure_is_demo = false; // matches the built-in PROG_DEMO kernel
-    std::vector<float> px, py, pz;  // host copies of the position tables
-    float lut[256];
-    // frame
-    uint32_t fw = 0, fh = 0;
-    float4* rgba_dev = nullptr;
-    float* depth_dev = nullptr;
-    float* gbuf_dev = nullptr;
-    unsigned long long* keys_dev = nullptr;
-    uint32_t* rgba8_dev = nullptr;
-    float* ingest_dev = nullptr;  // staging for sdfgpu_ingest_samples: records, then the LUT
-    size_t ingest_cap = 0;
-    // sdfgpu_update_surface, host-sampled path: two pinned staging buffers (records + texel indices) with
-    // their device copies, so that sampling chunk i+1 overlaps the transfer and scatter of chunk i
-    struct HostStage {
-        float* rec = nullptr; uint32_t* idx = nullptr;          // pinned host
-        float* rec_dev = nullptr; uint32_t* idx_dev = nullptr;  // device
-        size_t cap = 0;                                         // voxels
-        cudaEvent_t done = nullptr;
-        bool in_flight = false;
-    } stage[2];
-    uint64_t stage_turn = 0;
-    float* gather_host = nullptr;  // pinned: tex0.r of a chunk's candidates when the state is unknown
-    float* gather_dev = nullptr;
-    size_t gather_cap = 0;
-    int64_t pass_known = 0;        // known_step when the current (partially walked) host pass began
-    double host_rate = 1.0e6;      // LoadingManager iterations per second the host-sampled path last ran at
-    bool host_rate_known = false;
-    std::vector<unsigned char> tape_bytes;  // the public tape last given to sdfgpu_set_tape (change detection)
-    float* lut_dev = nullptr;
-    float* dist_dev = nullptr;  // optional distance-only volume for the tracer (option trace_distance_volume = 1)
-    cudaArray_t dist_arr = nullptr;  // the same as an R32F 3-D CUDA array (options 2, 3): written through dist_surf,
-    cudaSurfaceObject_t dist_surf = 0;  // read through dist_tex[0] (point filter) or dist_tex[1] (linear filter)
-    cudaTextureObject_t dist_tex[2] = {0, 0};
-    bool dist_valid = false;    // the distance volume the current option uses mirrors tex0.r
-    // GL textures of the presenter registered for interop (sdfgpu_gl_register): RGBA8 colour, optional R32F depth
-    cudaGraphicsResource* gl_res[2] = {nullptr, nullptr};
-    uint32_t gl_w = 0, gl_h = 0;
-    float* dist_full = nullptr;         // exact multi-GPU trace: tex0.r of the WHOLE grid (W*H*D floats), replicated
-    bool dist_full_own_valid = false;   //   this handle's own slices of it mirror tex0.r
-    bool peers_ever = false;  // a neighbour may hold an IPC mapping of this handle's volumes
-    int opt_dist_volume = 0;
-    unsigned long long* touched_dev = nullptr;
-    // neighbours' volumes opened with cudaIpcOpenMemHandle (fused halo exchange)
-    float4* peer_tex0[2] = {nullptr, nullptr};
-    float4* peer_tex1[2] = {nullptr, nullptr};
-    uint32_t peer_z_lo[2] = {0, 0};
-    cudaStream_t halo_stream = nullptr;  // DMA pushes of the boundary slices, overlapped with the interior fill
-    cudaEvent_t ev_boundary = nullptr, ev_pushed = nullptr;
-    // options
-    int opt_vpt = 0;        // voxels per thread (0 = default)
-    int opt_ctas = 0;       // CTAs per SM (0 = as many as fit)
-    int opt_fill_halo = 1;  // compute the halo slices locally (0: the host exchanges them)
-    int opt_max_steps = 256;    // maxSteps of sdfRaycast (material.frag:142); other values are for experiments only
-    int opt_trace_variant = 0;  // 0: 8x8 tiles, heavy-first 1-D grid; 1: plain 2-D grid of 32x8 CTAs
-    int opt_program = 0;    // 0 auto (JIT, else built-in, else interpreter), 1 interpreter, 2 built-in, 3 JIT or fail
-    int cc_major = 0, cc_minor = 0;
-    int last_program = -1, last_ctas = 0, last_vpt = 0;
-    std::string jit_note;   // why the JIT was not used (if it was not)
-    size_t smem_prepared[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // [V][interpreter | demo]
-    uint64_t launches = 0;
-    std::string err;
-};
-
-namespace {
-
-int fail(sdfgpu_ctx* ctx, int code, const char* fmt, ...) {
+int sdfgpu::fail(sdfgpu_ctx* ctx, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -216,19 +45,14 @@ int fail(sdfgpu_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
-#define CK(ctx, call)                                                                                  \
-    do {                                                                                               \
-        cudaError_t e_ = (call);                                                                       \
-        if (e_ != cudaSuccess) {                                                                       \
-            (void)cudaGetLastError();                                                                  \
-            return fail((ctx), SDFGPU_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));      \
-        }                                                                                              \
-    } while (0)
-
-float air_dist_value() {  // src/app/scene/sdf/mod.rs:42
+float sdfgpu::air_dist_value() {  // src/app/scene/sdf/mod.rs:42
     volatile float a = 1e-1f, b = 0.001234f;
     return a + b;
 }
+
+void sdfgpu::set_device(sdfgpu_ctx* ctx) { (void)cudaSetDevice(ctx->device); }
+
+namespace {
 
 // three-d-asset Srgba::to_linear_srgb on one u8 channel (call site scene/sdf/mod.rs:201)
 float srgb_u8_to_linear(unsigned v) {
@@ -252,8 +76,6 @@ void build_pos_table(std::vector<float>& t, uint32_t n, float lo, float hi) {  /
 }
 
 uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
-
-void set_device(sdfgpu_ctx* ctx) { (void)cudaSetDevice(ctx->device); }
 
 // voxels per thread: 8 for the straight-line kernels (specialised / built in), 4 for the interpreter
 // (measured on B200, tools/sweep_minb.py)
@@ -297,6 +119,7 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
     if (ctx->has_changed_box) memcpy(p.box, ctx->changed_box, sizeof p.box);
     p.air_dist = air_dist_value();
     p.touched = touched;
+    if (ctx->fill_boundary_first) (void)link_fill_all_fused(ctx, &p);
     const uint32_t n_cull = (ctx->hdr.flags & TAPE_FLAG_CULL) ? ctx->hdr.cull_count : 0u;
     const size_t smem = fill_smem_bytes(p.tape_img_bytes, n_cull, ctx->hdr.max_stack, V, &p.stack_floats);
     if (smem > 227u * 1024u)
@@ -345,14 +168,16 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
     return SDFGPU_OK;
 }
 
-bool has_peers(const sdfgpu_ctx* ctx) { return ctx->peer_tex0[0] || ctx->peer_tex0[1]; }
+}  // namespace
+
+bool sdfgpu::has_peers(const sdfgpu_ctx* ctx) { return ctx->peer_tex0[0] || ctx->peer_tex0[1]; }
 
 // Copy this handle's first / last owned slice (both volumes) into the neighbours' halo slices:
-// device-to-device copies into the IPC-mapped peer volumes, i.e. NVLink DMA by the copy engines.
-int push_halos(sdfgpu_ctx* ctx, cudaStream_t s) {
+// device-to-device copies into the mapped peer volumes, i.e. NVLink DMA by the copy engines.
+int sdfgpu::push_halos(sdfgpu_ctx* ctx, cudaStream_t s, bool lo, bool hi) {
     const size_t slice = (size_t)ctx->dims[0] * ctx->dims[1];
     for (int side = 0; side < 2; ++side) {
-        if (!ctx->peer_tex0[side]) continue;
+        if (!ctx->peer_tex0[side] || !(side == 0 ? lo : hi)) continue;
         const uint32_t z = side == 0 ? ctx->z_begin : ctx->z_end - 1;
         const size_t src = (size_t)(z - ctx->z_lo) * slice, dst = (size_t)(z - ctx->peer_z_lo[side]) * slice;
         CK(ctx, cudaMemcpyAsync(ctx->peer_tex0[side] + dst, ctx->tex0 + src, slice * sizeof(float4), cudaMemcpyDeviceToDevice, s));
@@ -360,6 +185,8 @@ int push_halos(sdfgpu_ctx* ctx, cudaStream_t s) {
     }
     return SDFGPU_OK;
 }
+
+namespace {
 
 void fill_z_range(const sdfgpu_ctx* ctx, uint32_t* za, uint32_t* zb) {
     if (ctx->opt_fill_halo) { *za = ctx->z_lo; *zb = ctx->z_hi; }
@@ -373,6 +200,8 @@ int alloc_volumes(sdfgpu_ctx* ctx) {
         CK(ctx, cudaMalloc(&ctx->tex1, ctx->stored_texels * sizeof(float4)));
     }
     CK(ctx, cudaMalloc(&ctx->touched_dev, sizeof(unsigned long long)));
+    CK(ctx, cudaMalloc(&ctx->trace_counters, 2 * sizeof(uint32_t)));
+    CK(ctx, cudaMemsetAsync(ctx->trace_counters, 0, 2 * sizeof(uint32_t), ctx->stream));
     return SDFGPU_OK;
 }
 
@@ -556,7 +385,9 @@ SDFGPU_API void sdfgpu_destroy(sdfgpu_ctx* ctx) {
     if (!ctx) return;
     set_device(ctx);
     if (ctx->stream) (void)cudaStreamSynchronize(ctx->stream);
+    link_free(ctx);
     (void)sdfgpu_ipc_detach(ctx);
+    (void)cudaFree(ctx->trace_counters);
     (void)cudaFree(ctx->tex0); (void)cudaFree(ctx->tex1); (void)cudaFree(ctx->img_dev);
     (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
     (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->rgba8_dev); (void)cudaFree(ctx->touched_dev);
@@ -962,7 +793,10 @@ int gpu_passes(sdfgpu_ctx* ctx, uint32_t max_passes, uint64_t* iterations) {
         ctx->lm.finish_pass();
         ++done;
     }
-    if (done && has_peers(ctx)) {
+    if (ctx->link.on) {  // collective: every rank signals, whether or not anything was pending
+        const int rc = link_after_fill(ctx, done != 0, done != 0);
+        if (rc != SDFGPU_OK) return rc;
+    } else if (done && has_peers(ctx)) {
         const int rc = push_halos(ctx, ctx->stream);
         if (rc != SDFGPU_OK) return rc;
     }
@@ -1219,7 +1053,10 @@ int host_sampled_passes(sdfgpu_ctx* ctx, const sdfgpu_surface* sdf, double max_s
         chunk = chunk_for(max_seconds - el);
         if (chunk < 256 && max_seconds > 0.0) chunk = 256;
     }
-    if (pass_finished && has_peers(ctx)) {
+    if (ctx->link.on) {
+        // ranks stop at different places of a time-budgeted pass: every call pushes and signals, so the epochs agree
+        if ((rc = link_after_fill(ctx, true, true)) != SDFGPU_OK) return rc;
+    } else if (pass_finished && has_peers(ctx)) {
         if ((rc = push_halos(ctx, ctx->stream)) != SDFGPU_OK) return rc;
     }
     if (iterations) *iterations = lm.total_iterations - start_iter;  // :216
@@ -1266,7 +1103,16 @@ SDFGPU_API int sdfgpu_fill_all(sdfgpu_ctx* ctx) {
     uint32_t za, zb;
     fill_z_range(ctx, &za, &zb);
     int rc;
-    if (has_peers(ctx) && ctx->z_end - ctx->z_begin >= 3) {
+    if (ctx->link.on) {
+        // ONE launch: the tiles of the two boundary slices first; the copy engines push them into the neighbours'
+        // halo slices, behind the kernel's boundary flag, while the interior is being filled (link.cu)
+        const uint32_t lo[3] = {0, 0, ctx->z_begin}, hi[3] = {ctx->dims[0], ctx->dims[1], ctx->z_end};
+        ctx->fill_boundary_first = true;
+        rc = run_fill(ctx, 1, lo, hi, FILL_ALL, nullptr);
+        ctx->fill_boundary_first = false;
+        if (rc != SDFGPU_OK) return rc;
+        if ((rc = link_fill_all_pushed(ctx)) != SDFGPU_OK) return rc;
+    } else if (has_peers(ctx) && ctx->z_end - ctx->z_begin >= 3) {
         // fused halo exchange: fill the boundary slices first, then let the copy engines push them into
         // the neighbours' halo slices over NVLink WHILE the interior is being filled
         if (!ctx->halo_stream) {
@@ -1304,34 +1150,44 @@ SDFGPU_API int sdfgpu_resample_box(sdfgpu_ctx* ctx, const float box[6], uint64_t
     // index AABB of the voxels whose position lies in the closed box (float compare, :187-189)
     uint32_t lo[3], hi[3];
     const std::vector<float>* tab[3] = {&ctx->px, &ctx->py, &ctx->pz};
+    bool empty = false;
     for (int a = 0; a < 3; ++a) {
         uint32_t first, last;
-        if (!index_range_in(*tab[a], box[a], box[3 + a], &first, &last)) return SDFGPU_OK;  // nothing inside
+        if (!index_range_in(*tab[a], box[a], box[3 + a], &first, &last)) { empty = true; break; }  // nothing inside
         lo[a] = first; hi[a] = last + 1;
     }
     uint32_t za, zb;
     fill_z_range(ctx, &za, &zb);
-    if (lo[2] < za) lo[2] = za;
-    if (hi[2] > zb) hi[2] = zb;
-    // temporarily present `box` as the pending box of a conditional pass
-    const bool saved_has = ctx->has_changed_box;
-    float saved[6];
-    memcpy(saved, ctx->changed_box, sizeof saved);
-    ctx->has_changed_box = true;
-    memcpy(ctx->changed_box, box, sizeof saved);
-    int rc = SDFGPU_OK;
-    if (voxels_touched) {
-        cudaError_t e = cudaMemsetAsync(ctx->touched_dev, 0, sizeof(unsigned long long), ctx->stream);
-        if (e != cudaSuccess) rc = fail(ctx, SDFGPU_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+    if (!empty) {
+        if (lo[2] < za) lo[2] = za;
+        if (hi[2] > zb) hi[2] = zb;
+        if (lo[2] >= hi[2]) empty = true;  // the box lies in other ranks' slices
     }
-    if (rc == SDFGPU_OK)
-        rc = run_fill(ctx, 1, lo, hi, ctx->known_step == 1 ? FILL_BOX_ONLY : FILL_READ, voxels_touched ? ctx->touched_dev : nullptr);
-    if (ctx->known_step != 1) ctx->known_step = -1;
-    ctx->has_changed_box = saved_has;
-    memcpy(ctx->changed_box, saved, sizeof saved);
-    if (rc == SDFGPU_OK && has_peers(ctx)) rc = push_halos(ctx, ctx->stream);
+    int rc = SDFGPU_OK;
+    if (!empty) {
+        // temporarily present `box` as the pending box of a conditional pass
+        const bool saved_has = ctx->has_changed_box;
+        float saved[6];
+        memcpy(saved, ctx->changed_box, sizeof saved);
+        ctx->has_changed_box = true;
+        memcpy(ctx->changed_box, box, sizeof saved);
+        if (voxels_touched) {
+            cudaError_t e = cudaMemsetAsync(ctx->touched_dev, 0, sizeof(unsigned long long), ctx->stream);
+            if (e != cudaSuccess) rc = fail(ctx, SDFGPU_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+        }
+        if (rc == SDFGPU_OK)
+            rc = run_fill(ctx, 1, lo, hi, ctx->known_step == 1 ? FILL_BOX_ONLY : FILL_READ, voxels_touched ? ctx->touched_dev : nullptr);
+        if (ctx->known_step != 1) ctx->known_step = -1;
+        ctx->has_changed_box = saved_has;
+        memcpy(ctx->changed_box, saved, sizeof saved);
+    }
+    // a neighbour's halo slice changes only when the box reaches this handle's first / last own slice
+    const bool touch_lo = !empty && lo[2] <= ctx->z_begin && hi[2] > ctx->z_begin;
+    const bool touch_hi = !empty && lo[2] < ctx->z_end && hi[2] >= ctx->z_end;
+    if (rc == SDFGPU_OK && ctx->link.on) rc = link_after_fill(ctx, touch_lo, touch_hi);  // collective: always signals
+    else if (rc == SDFGPU_OK && has_peers(ctx) && (touch_lo || touch_hi)) rc = push_halos(ctx, ctx->stream, touch_lo, touch_hi);
     if (rc != SDFGPU_OK) return rc;
-    if (voxels_touched) {
+    if (voxels_touched && !empty) {
         unsigned long long n = 0;
         CK(ctx, cudaMemcpyAsync(&n, ctx->touched_dev, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1449,7 +1305,22 @@ SDFGPU_API uint32_t sdfgpu_loading_passes_left(const sdfgpu_loading* l) { return
 SDFGPU_API int sdfgpu_reset(sdfgpu_ctx* ctx, uint32_t loading_passes) {
     if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
     set_device(ctx);
-    const int rc = reset_volumes(ctx);
+    int rc;
+    if (ctx->link.on) {
+        // a linked handle's halo slices are written by its neighbours only: reset the own slices and push the two
+        // boundary slices like any fill does (collective: the neighbours do the same to this handle's halo slices).
+        // Resetting the halo slices here would race with a neighbour that has already reset and filled again.
+        ctx->dist_valid = false; ctx->dist_full_own_valid = false;
+        const size_t slice = (size_t)ctx->dims[0] * ctx->dims[1];
+        const size_t off = (size_t)(ctx->z_begin - ctx->z_lo) * slice, n = (size_t)(ctx->z_end - ctx->z_begin) * slice;
+        const int grid = ctx->sm_count * 8;
+        CK(ctx, launch_set_const(ctx->tex0 + off, n, air_dist_value(), grid, ctx->stream));
+        CK(ctx, launch_set_const(ctx->tex1 + off, n, air_dist_value(), grid, ctx->stream));
+        ctx->launches += 2;
+        rc = link_after_fill(ctx, true, true);
+    } else {
+        rc = reset_volumes(ctx);
+    }
     if (rc != SDFGPU_OK) return rc;
     ctx->lm.reset(loading_passes);
     ctx->known_step = 0;
@@ -1505,7 +1376,9 @@ void normalize3(float v[3]) {  // cgmath: v * (1 / |v|)
     v[0] *= inv; v[1] *= inv; v[2] *= inv;
 }
 
-int ensure_frame(sdfgpu_ctx* ctx, uint32_t w, uint32_t h, bool want_gbuf, bool want_keys) {
+}  // namespace
+
+int sdfgpu::ensure_frame(sdfgpu_ctx* ctx, uint32_t w, uint32_t h, bool want_gbuf, bool want_keys) {
     const size_t n = (size_t)w * h;
     if (w != ctx->fw || h != ctx->fh) {
         CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1525,7 +1398,7 @@ int ensure_frame(sdfgpu_ctx* ctx, uint32_t w, uint32_t h, bool want_gbuf, bool w
     return SDFGPU_OK;
 }
 
-int fill_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t w, uint32_t h, bool slab_clip, TraceParams* tp) {
+int sdfgpu::fill_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t w, uint32_t h, bool slab_clip, TraceParams* tp) {
     sdfgpu_rays rays;
     int rc = sdfgpu_camera_rays(cam, w, h, &rays);
     if (rc != SDFGPU_OK) return fail(ctx, rc, "%s", g_thread_error.c_str());
@@ -1640,6 +1513,29 @@ int fill_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t w, uin
     return SDFGPU_OK;
 }
 
+namespace {
+
+// the tracer of an un-linked handle: variant 0 / 1 the per-tile kernels, variant 2 the persistent round kernel
+// (one round, no hand-off; trace.cu trace_rounds_kernel) -- same frame, bit for bit
+int launch_trace_any(sdfgpu_ctx* ctx, const TraceParams& tp) {
+    const int variant = ctx->stored_texels ? ctx->opt_trace_variant : 0;
+    if (variant == 2 && tp.dist_mode == 0 && !tp.full_dist) {
+        LinkParams lp;
+        memset(&lp, 0, sizeof lp);
+        lp.first = 1u;
+        lp.own_z0 = 0; lp.own_z1 = ctx->dims[2];
+        lp.work_head = ctx->trace_counters;
+        lp.ctas_done = ctx->trace_counters + 1;
+        const int per_sm = trace_rounds_max_ctas_per_sm(tp);
+        if (per_sm < 1) return fail(ctx, SDFGPU_ERR_CUDA, "the trace kernel does not fit on an SM");
+        CK(ctx, launch_trace_rounds(tp, lp, ctx->sm_count * per_sm, ctx->stream));
+    } else {
+        CK(ctx, launch_trace(tp, variant == 2 ? 0 : variant, ctx->stream));
+    }
+    ctx->launches++;
+    return SDFGPU_OK;
+}
+
 }  // namespace
 
 SDFGPU_API void sdfgpu_look_at_rh(const float eye[3], const float center[3], const float up[3], float m[16]) {
@@ -1705,6 +1601,9 @@ SDFGPU_API int sdfgpu_trace_device(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, ui
     if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
     if (!cam) return fail(ctx, SDFGPU_ERR_INVALID, "cam is NULL");
     if (width == 0 || height == 0) return fail(ctx, SDFGPU_ERR_INVALID, "empty frame");
+    if (ctx->link.on)
+        return fail(ctx, SDFGPU_ERR_STATE, "a linked handle traces collectively: sdfgpu_trace_rgba8 / sdfgpu_trace_linked "
+                                           "(the frame is composed on rank 0)");
     set_device(ctx);
     int rc = ensure_frame(ctx, width, height, want_gbuf != 0, false);
     if (rc != SDFGPU_OK) return rc;
@@ -1712,8 +1611,7 @@ SDFGPU_API int sdfgpu_trace_device(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, ui
     if ((rc = fill_trace_params(ctx, cam, width, height, false, &tp)) != SDFGPU_OK) return rc;
     tp.rgba = ctx->rgba_dev; tp.depth = ctx->depth_dev;
     tp.gbuf = want_gbuf ? ctx->gbuf_dev : nullptr;
-    CK(ctx, launch_trace(tp, ctx->stored_texels ? ctx->opt_trace_variant : 0, ctx->stream));
-    ctx->launches++;
+    if ((rc = launch_trace_any(ctx, tp)) != SDFGPU_OK) return rc;
     if (rgba_dev) *rgba_dev = ctx->rgba_dev;
     if (depth_dev) *depth_dev = ctx->depth_dev;
     if (gbuf_dev) *gbuf_dev = want_gbuf ? ctx->gbuf_dev : nullptr;
@@ -1738,6 +1636,7 @@ SDFGPU_API int sdfgpu_trace_rgba8(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uin
     if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
     if (!cam) return fail(ctx, SDFGPU_ERR_INVALID, "cam is NULL");
     if (width == 0 || height == 0) return fail(ctx, SDFGPU_ERR_INVALID, "empty frame");
+    if (ctx->link.on) return sdfgpu_trace_linked(ctx, cam, width, height, 0, rgba8, depth, nullptr);
     set_device(ctx);
     int rc = ensure_frame(ctx, width, height, false, false);
     if (rc != SDFGPU_OK) return rc;
@@ -1746,8 +1645,7 @@ SDFGPU_API int sdfgpu_trace_rgba8(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uin
     TraceParams tp;
     if ((rc = fill_trace_params(ctx, cam, width, height, false, &tp)) != SDFGPU_OK) return rc;
     tp.rgba8 = ctx->rgba8_dev; tp.depth = ctx->depth_dev;
-    CK(ctx, launch_trace(tp, ctx->stored_texels ? ctx->opt_trace_variant : 0, ctx->stream));
-    ctx->launches++;
+    if ((rc = launch_trace_any(ctx, tp)) != SDFGPU_OK) return rc;
     if (rgba8) CK(ctx, cudaMemcpyAsync(rgba8, ctx->rgba8_dev, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (depth) CK(ctx, cudaMemcpyAsync(depth, ctx->depth_dev, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1779,8 +1677,7 @@ SDFGPU_API int sdfgpu_trace_slab_keys(sdfgpu_ctx* ctx, const sdfgpu_camera* cam,
     TraceParams tp;
     if ((rc = fill_trace_params(ctx, cam, width, height, true, &tp)) != SDFGPU_OK) return rc;
     tp.keys = ctx->keys_dev;
-    CK(ctx, launch_trace(tp, ctx->stored_texels ? ctx->opt_trace_variant : 0, ctx->stream));
-    ctx->launches++;
+    if ((rc = launch_trace_any(ctx, tp)) != SDFGPU_OK) return rc;
     *keys_dev = ctx->keys_dev;
     return SDFGPU_OK;
 }
@@ -1837,8 +1734,7 @@ SDFGPU_API int sdfgpu_trace_gl(sdfgpu_ctx* ctx, const sdfgpu_camera* cam) {
     TraceParams tp;
     if ((rc = fill_trace_params(ctx, cam, w, h, false, &tp)) != SDFGPU_OK) return rc;
     tp.rgba8 = ctx->rgba8_dev; tp.depth = ctx->depth_dev;
-    CK(ctx, launch_trace(tp, ctx->stored_texels ? ctx->opt_trace_variant : 0, ctx->stream));
-    ctx->launches++;
+    if ((rc = launch_trace_any(ctx, tp)) != SDFGPU_OK) return rc;
     // map, copy the frame into the textures' arrays on the device (row 0 = bottom row = GL's origin), unmap:
     // the frame never visits the host
     const int n = ctx->gl_res[1] ? 2 : 1;
@@ -1986,8 +1882,12 @@ SDFGPU_API int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value
         if (value < 2 || value > 65536) return fail(ctx, SDFGPU_ERR_INVALID, "trace_max_steps out of range");
         ctx->opt_max_steps = (int)value;
     } else if (!strcmp(key, "trace_variant")) {
-        if (value < 0 || value > 1) return fail(ctx, SDFGPU_ERR_INVALID, "trace_variant must be 0 or 1");
+        if (value < 0 || value > 2) return fail(ctx, SDFGPU_ERR_INVALID, "trace_variant must be 0, 1 or 2");
         ctx->opt_trace_variant = (int)value;
+    } else if (!strcmp(key, "link_wait_mode")) {
+        if (value < 0 || value > 1) return fail(ctx, SDFGPU_ERR_INVALID, "link_wait_mode must be 0 or 1");
+        if (ctx->link.on) return fail(ctx, SDFGPU_ERR_STATE, "set link_wait_mode before sdfgpu_link_attach");
+        ctx->opt_link_wait = (int)value;
     } else if (!strcmp(key, "fill_program")) {
         if (value < 0 || value > 3) return fail(ctx, SDFGPU_ERR_INVALID, "fill_program must be 0..3");
         ctx->opt_program = (int)value;
@@ -2006,6 +1906,10 @@ SDFGPU_API int sdfgpu_get_info(const sdfgpu_ctx* ctx, const char* key, int64_t* 
     else if (!strcmp(key, "tape_image_bytes")) *value = (int64_t)ctx->img_host.size();
     else if (!strcmp(key, "tape_culled")) *value = (ctx->hdr.flags & TAPE_FLAG_CULL) ? 1 : 0;
     else if (!strcmp(key, "jit_available")) { std::string why; *value = jit_available(&why) ? 1 : 0; }
+    else if (!strcmp(key, "linked")) *value = ctx->link.on ? 1 : 0;
+    else if (!strcmp(key, "link_memops")) *value = ctx->link.on && ctx->link.memops ? 1 : 0;
+    else if (!strcmp(key, "link_fill_epoch")) *value = ctx->link.fill_epoch;
+    else if (!strcmp(key, "link_round_epoch")) *value = ctx->link.round_epoch;
     else return fail(nullptr, SDFGPU_ERR_INVALID, "unknown info key '%s'", key);
     return SDFGPU_OK;
 }

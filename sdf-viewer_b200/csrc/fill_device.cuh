@@ -481,7 +481,9 @@ __device__ __forceinline__ void fill_body(const FillParams& P) {
     const size_t vstride = (size_t)P.step * slice;
     uint32_t touched_local = 0;
 
-    // tile -> (tx, ty, tz), x fastest; advanced incrementally by gridDim.x per iteration
+    // tile -> (tx, ty, tz), x fastest; advanced incrementally by gridDim.x per iteration.  tz is the tile's place in
+    // the z ORDER: with n_boundary_tiles (multi-GPU fill of a whole slab) the order is first z tile, last z tile, then
+    // the interior, so that the slices the neighbours need are complete early (FillParams)
     uint32_t tx = blockIdx.x % P.tiles_x, ty = (blockIdx.x / P.tiles_x) % P.tiles_y,
              tz = blockIdx.x / (P.tiles_x * P.tiles_y);
     const uint32_t sx = gridDim.x % P.tiles_x, sy = (gridDim.x / P.tiles_x) % P.tiles_y,
@@ -490,9 +492,10 @@ __device__ __forceinline__ void fill_body(const FillParams& P) {
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- per-tile culling of the UNION_RANGE (exact-safe: a primitive is dropped only if
         // its lower bound over the tile exceeds some other primitive's upper bound)
+        const uint32_t tzz = P.n_boundary_tiles ? (tz == 0u ? 0u : (tz == 1u ? P.tiles_z - 1u : tz - 1u)) : tz;
         if (n_cull) {
             __syncthreads();  // previous tile's readers of s_list are done
-            const uint32_t lx0 = tx * FILL_TILE_X, ly0 = ty * FILL_TILE_Y, lz0 = tz * V;
+            const uint32_t lx0 = tx * FILL_TILE_X, ly0 = ty * FILL_TILE_Y, lz0 = tzz * V;
             const uint32_t lx1 = min(lx0 + FILL_TILE_X, P.nx) - 1, ly1 = min(ly0 + FILL_TILE_Y, P.ny) - 1,
                            lz1 = min(lz0 + V, P.nz) - 1;
             const float ax = s_px[P.rx0 + lx0 * P.step], bx = s_px[P.rx0 + lx1 * P.step];
@@ -558,7 +561,7 @@ __device__ __forceinline__ void fill_body(const FillParams& P) {
 
         const uint32_t lx = tx * FILL_TILE_X + lane;
         const uint32_t ly = ty * FILL_TILE_Y + warp;
-        const uint32_t lz0 = tz * V;
+        const uint32_t lz0 = tzz * V;
         // advance to this CTA's next tile (mixed-radix add with carries)
         tx += sx; ty += sy; tz += sz;
         if (tx >= P.tiles_x) { tx -= P.tiles_x; ++ty; }
@@ -569,6 +572,17 @@ __device__ __forceinline__ void fill_body(const FillParams& P) {
                           lz0 + V <= P.nz;
         if (full) tile_body<V, PROG, true>(P, E, s_instr, s_lut, s_px, s_py, s_pz, lx, ly, lz0, slice, vstride, touched_local);
         else tile_body<V, PROG, false>(P, E, s_instr, s_lut, s_px, s_py, s_pz, lx, ly, lz0, slice, vstride, touched_local);
+
+        if (tile < P.n_boundary_tiles) {  // CTA-uniform
+            // the copy engines and the stream's semaphore are outside this GPU's SMs: system-scope fence
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0 && atomicAdd(P.boundary_count, 1u) + 1u == P.n_boundary_tiles) {
+                *P.boundary_count = 0u;  // every boundary tile has been counted: ready for the next launch
+                __threadfence_system();
+                *reinterpret_cast<volatile uint32_t*>(P.boundary_flag) = P.boundary_epoch;
+            }
+        }
     }
 
     if (P.touched) {

@@ -44,6 +44,38 @@ struct TraceParams {
     uint32_t* rgba8;           // may be null: the frame as an RGBA8 framebuffer would hold it (round(clamp(c) * 255))
 };
 
+// What the round kernel of the tracer (trace.cu: trace_rounds_kernel) needs beyond TraceParams.  A frame is traced
+// in `world` rounds.  Round 0 starts every ray whose start position this rank owns; a ray marches while the lower z
+// tap of its texture fetch lies in this rank's own slices [own_z0, own_z1) (the upper tap is then an own or a halo
+// slice), and is handed to the neighbour -- position, t and step count, 24 bytes -- when it leaves them; rounds
+// k >= 1 continue the rays the neighbours handed over in round k - 1.  The step sequence of every ray is the one a
+// single GPU holding the whole grid runs, bit for bit.  With linked == 0 the kernel is the plain single-volume trace.
+struct LinkParams {
+    uint32_t linked;        // 0: single volume, outputs of TraceParams; 1: sharded, finished pixels go to the presenter
+    uint32_t first;         // round 0 of a frame: the work units are 8 x 4 pixel tiles; else 32-entry runs of the in-queues
+    uint32_t is_presenter;  // writes the pixels whose ray never enters the box
+    uint32_t own_z0, own_z1;
+    uint32_t max_pixels;    // capacity of every queue buffer
+    uint32_t* work_head;    // local: next work unit (reset by the last CTA)
+    uint32_t* ctas_done;    // local: CTAs that have finished (reset by the last CTA)
+    // in-queues: what the neighbours appended in the previous round ([0] the neighbour below, its UP entries at
+    // [max_pixels - 1 - i]; [1] the neighbour above, its DOWN entries at [i]); null without a neighbour
+    const uint32_t* in_count[2];
+    const float4* in_pos[2];
+    const uint2* in_id[2];
+    // out-queue of this round (own memory): [0] rays leaving downwards, filled from the front; [1] upwards, from the back
+    uint32_t* out_count;    // two counters
+    float4* out_pos;        // position.xyz, t
+    uint2* out_id;          // pixel index, step count
+    uint32_t* reset_count;  // the counter pair this kernel's last CTA zeroes (ring of 4: the pair of round + 2)
+    unsigned long long* frame_keys;  // presenter's (depth, RGBA8) key frame -- peer memory on the other ranks
+    float* frame_gbuf;               // presenter's G-buffer frame, or null
+    uint32_t* sig_round[2];          // the neighbours' "round done" flags (peer memory), or null
+    uint32_t sig_round_value;
+    uint32_t* sig_frame;             // the presenter's "rank r finished the frame" flag (last round only), or null
+    uint32_t sig_frame_value;
+};
+
 // launchers (fill.cu / trace.cu).  `program`: dev::PROG_INTERPRET or dev::PROG_DEMO (built in)
 cudaError_t launch_fill(const FillParams& p, int voxels_per_thread, int program, int grid_ctas, size_t smem_bytes,
                         cudaStream_t s);
@@ -73,6 +105,10 @@ cudaError_t launch_gather_dist(const float4* tex0, const uint32_t* idx_dev, size
                                cudaStream_t s);
 cudaError_t launch_set_const(float4* dst, size_t n_texels, float v, int grid_ctas, cudaStream_t s);
 cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s);
+cudaError_t launch_trace_rounds(const TraceParams& p, const LinkParams& l, int grid_ctas, cudaStream_t s);
+int trace_rounds_max_ctas_per_sm(const TraceParams& p);
+cudaError_t launch_signal(uint32_t* const* flags, const uint32_t* values, int n, cudaStream_t s);  // fence.sys + stores (peer flags)
+cudaError_t launch_spin_wait(const uint32_t* flag, uint32_t value, uint32_t* timed_out, cudaStream_t s);  // fallback for cuStreamWaitValue32
 cudaError_t launch_extract_dist(const float4* tex0, float* dist, size_t n, int grid, cudaStream_t s);
 cudaError_t launch_extract_dist_array(const float4* tex0, unsigned long long surf, uint32_t W, uint32_t H,
                                       uint32_t stored_slices, int grid, cudaStream_t s);

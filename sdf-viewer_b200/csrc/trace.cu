@@ -475,6 +475,339 @@ __global__ void __launch_bounds__(256) trace_kernel(const __grid_constant__ Trac
     trace_pixel<SNAP, LINEAR>(P, i, j);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Round kernel: persistent warps that pull their work from a queue.  One kernel serves the single-volume
+// trace (linked == 0: one round, every ray runs to its end) and the Z-sharded trace (LinkParams,
+// sdfgpu_internal.h): a ray marches while this rank owns the lower z tap of its fetch and is handed to the
+// neighbour otherwise, so the step sequence -- and with it hit point, step count and pixel -- is the single
+// volume's, bit for bit, with a one-slice halo and no replicated data.
+//
+// Work units are 32 rays: in the first round an 8 x 4 pixel tile (tiles inside the screen rectangle of the
+// projected box first: those hold every long march), later 32 consecutive entries of a neighbour's out-queue.
+// A warp takes the next unit with one atomicAdd as soon as ITS rays are done -- a 255-step grazing ray holds
+// one warp slot, not a CTA -- and leaves the march loop on an explicit warp ballot.
+
+struct Ray {
+    float hx, hy, hz, t;
+    int it;
+};
+
+// ray through pixel (i, j): the fragment the rasterised bounding cube would produce (material.frag:133-139).
+// false: the ray does not enter the clip box (no fragment).
+__device__ __forceinline__ bool ray_setup(const TraceParams& P, uint32_t i, uint32_t j, float& rdx, float& rdy, float& rdz,
+                                          float& rox, float& roy, float& roz) {
+    const float fx = (float)i + 0.5f, fy = (float)j + 0.5f;
+    const float camx = P.origin[0], camy = P.origin[1], camz = P.origin[2];
+    const float dux = (P.base[0] + P.dx[0] * fx) + P.dy[0] * fy;
+    const float duy = (P.base[1] + P.dx[1] * fx) + P.dy[1] * fy;
+    const float duz = (P.base[2] + P.dx[2] * fx) + P.dy[2] * fy;
+    const float ix = 1.0f / dux, iy = 1.0f / duy, iz = 1.0f / duz;
+    const float t1x = (P.clip_min[0] - camx) * ix, t2x = (P.clip_max[0] - camx) * ix;
+    const float t1y = (P.clip_min[1] - camy) * iy, t2y = (P.clip_max[1] - camy) * iy;
+    const float t1z = (P.clip_min[2] - camz) * iz, t2z = (P.clip_max[2] - camz) * iz;
+    const float tmin = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
+    const float tmax = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
+    rdx = rdy = rdz = 0.0f; rox = roy = roz = 0.0f;
+    if (!(tmax >= fmaxf(tmin, 0.0f))) return false;
+    const float tf = (tmin < 0.0f) ? tmax : tmin;
+    const float posx = camx + dux * tf, posy = camy + duy * tf, posz = camz + duz * tf;
+    rdx = posx - camx; rdy = posy - camy; rdz = posz - camz;
+    const float inv = 1.0f / sqrtf(rdx * rdx + rdy * rdy + rdz * rdz);
+    rdx *= inv; rdy *= inv; rdz *= inv;
+    rox = posx; roy = posy; roz = posz;
+    if (oob_dist(P.clip_min, P.clip_max, rox + rdx * 0.2f, roy + rdy * 0.2f, roz + rdz * 0.2f) > 0.0f) {
+        rox = camx + rdx * 0.2f; roy = camy + rdy * 0.2f; roz = camz + rdz * 0.2f;
+    }
+    return true;
+}
+
+// the lower z tap of the fetch at normalised coordinate az (same arithmetic as linear_taps / the NEAREST fetch)
+template <bool LINEAR>
+__device__ __forceinline__ int lower_z_tap(int D, float az) {
+    if (LINEAR) {
+        int a, b;
+        mirror_pair((int)floorf(az * (float)D - 0.5f), D, a, b);
+        return a;
+    }
+    return mirror_idx((int)floorf(az * (float)D), D);
+}
+
+// distance lane at normalised coordinates (what sample_dist_cached / sample_dist compute after tex_coord)
+template <bool LINEAR>
+__device__ __forceinline__ float dist_at(const Vol& v, float ax, float ay, float az, CellCache& cc) {
+    if (LINEAR) {
+        const float ux = ax * (float)v.W - 0.5f, uy = ay * (float)v.H - 0.5f, uz = az * (float)v.D - 0.5f;
+        const float fx0 = floorf(ux), fy0 = floorf(uy), fz0 = floorf(uz);
+        if (fx0 != cc.x0 || fy0 != cc.y0 || fz0 != cc.z0) {
+            const Taps t = linear_taps(v, ax, ay, az);
+            cc.c000 = ldx(v.tex, t.i000); cc.c100 = ldx(v.tex, t.i100); cc.c010 = ldx(v.tex, t.i010);
+            cc.c110 = ldx(v.tex, t.i110); cc.c001 = ldx(v.tex, t.i001); cc.c101 = ldx(v.tex, t.i101);
+            cc.c011 = ldx(v.tex, t.i011); cc.c111 = ldx(v.tex, t.i111);
+            cc.x0 = fx0; cc.y0 = fy0; cc.z0 = fz0;
+        }
+        return trilerp(cc.c000, cc.c100, cc.c010, cc.c110, cc.c001, cc.c101, cc.c011, cc.c111, ux - fx0, uy - fy0,
+                       uz - fz0);
+    }
+    const int x = (int)floorf(ax * (float)v.W), y = (int)floorf(ay * (float)v.H), z = (int)floorf(az * (float)v.D);
+    return ldx(v.tex, texel_index(v, x, y, z));
+}
+
+enum : int { RS_HIT = 0, RS_MISS = 1, RS_DOWN = 2, RS_UP = 3, RS_NONE = 4 };
+
+// shading of a finished ray (material.frag:145-181) and its outputs.  Sharded: the (depth, RGBA8) key and the optional
+// G-buffer record go to the presenter's frame; single volume: the buffers of TraceParams.
+template <bool SNAP, bool LINEAR>
+__device__ __forceinline__ void finish_pixel(const TraceParams& P, const LinkParams& L, const Vol& v0, const Vol& v1,
+                                             uint32_t px, bool hit, float code, const Ray& r) {
+    float g[SDFGPU_GBUF_FLOATS];
+#pragma unroll
+    for (int k = 0; k < SDFGPU_GBUF_FLOATS; ++k) g[k] = 0.0f;
+    const float hx = r.hx, hy = r.hy, hz = r.hz;
+    g[0] = hx; g[1] = hy; g[2] = hz; g[3] = code; g[15] = (float)r.it;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    float depth = 1.0f;
+    float* const gbuf = L.linked ? L.frame_gbuf : P.gbuf;
+    if (hit) {
+        const float4 s0 = sample_full<SNAP, LINEAR>(P, v0, hx, hy, hz);
+        const float4 s1 = sample_full<SNAP, LINEAR>(P, v1, hx, hy, hz);  // :154
+        g[4] = s0.x; g[5] = s0.y; g[6] = s0.z; g[7] = s0.w;
+        g[8] = s1.x; g[9] = s1.y; g[10] = s1.z; g[11] = s1.w;
+        if (gbuf) {  // sdfNormal, :73-80 (dead for the ambient-only light set, kept for the G-buffer)
+            const float lx = (float)P.W / P.lod, ly = (float)P.H / P.lod, lz = (float)P.D / P.lod;
+            const float h = 1.0f / sqrtf(lx * lx + ly * ly + lz * lz);
+            const float kx[4] = {1.f, -1.f, -1.f, 1.f}, ky[4] = {-1.f, -1.f, 1.f, 1.f}, kz[4] = {-1.f, 1.f, -1.f, 1.f};
+            float nx = 0.f, ny = 0.f, nz = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float dq = sample_dist<SNAP, LINEAR>(P, v0, hx + kx[q] * h, hy + ky[q] * h, hz + kz[q] * h) - 1e-1f;
+                nx += kx[q] * dq; ny += ky[q] * dq; nz += kz[q] * dq;
+            }
+            const float ninv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+            g[12] = nx * ninv; g[13] = ny * ninv; g[14] = nz * ninv;
+        }
+        const float al[3] = {s0.y * P.tint[0], s0.z * P.tint[1], s0.w * P.tint[2]};  // :158-173
+        float col[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float mixv = al[c] * (1.0f - s1.x) + 0.0f * s1.x;
+            float x = 0.0f + (s1.z * P.ambient[c]) * mixv;
+            x = tone_mapping(P.tone_mapping, x);
+            x = color_mapping(P.color_mapping, x);
+            if (P.gamma != 0.0f) x = powf(x, P.gamma);
+            col[c] = x;
+        }
+        out = make_float4(col[0], col[1], col[2], P.tint[3]);
+        const float* m = P.bvp;  // :180-181
+        const float z = ((m[2] * hx + m[6] * hy) + m[10] * hz) + m[14];
+        const float w = ((m[3] * hx + m[7] * hy) + m[11] * hz) + m[15];
+        depth = z / w;
+    }
+    if (gbuf) {
+        float4* gp = reinterpret_cast<float4*>(gbuf + (size_t)px * SDFGPU_GBUF_FLOATS);
+        gp[0] = make_float4(g[0], g[1], g[2], g[3]);
+        gp[1] = make_float4(g[4], g[5], g[6], g[7]);
+        gp[2] = make_float4(g[8], g[9], g[10], g[11]);
+        gp[3] = make_float4(g[12], g[13], g[14], g[15]);
+    }
+    if (L.linked) {
+        L.frame_keys[px] = pack_key(depth, out.x, out.y, out.z, out.w);
+        return;
+    }
+    if (P.rgba) P.rgba[px] = out;
+    if (P.depth) P.depth[px] = depth;
+    if (P.keys) P.keys[px] = pack_key(depth, out.x, out.y, out.z, out.w);
+    if (P.rgba8) P.rgba8[px] = (uint32_t)(pack_key(depth, out.x, out.y, out.z, out.w) & 0xffffffffull);
+}
+
+template <bool SNAP, bool LINEAR>
+__global__ void __launch_bounds__(256) trace_rounds_kernel(const __grid_constant__ TraceParams P,
+                                                           const __grid_constant__ LinkParams L) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const Vol v0{P.tex0, (int)P.W, (int)P.H, (int)P.D, (int)P.z_lo, (int)P.z_hi};
+    const Vol v1{P.tex1, (int)P.W, (int)P.H, (int)P.D, (int)P.z_lo, (int)P.z_hi};
+
+    // ---- the work of this round
+    const uint32_t tiles_y4 = (P.height + 3u) / 4u;                              // rows of 8 x 4 tiles
+    const uint32_t rw = P.rect[2] - P.rect[0], ry0 = P.rect[1] * 2u;
+    const uint32_t rh4 = min(P.rect[3] * 2u, tiles_y4) - min(ry0, tiles_y4);
+    const uint32_t n_heavy = rw * rh4;
+    uint32_t n_units, units0 = 0, cnt0 = 0, cnt1 = 0;
+    if (L.first) {
+        // tiles outside the rectangle hold no ray that enters the box: only the presenter has to write them
+        n_units = (!L.linked || L.is_presenter) ? P.tiles_x * tiles_y4 : n_heavy;
+    } else {
+        if (L.in_count[0]) cnt0 = *reinterpret_cast<const volatile uint32_t*>(L.in_count[0]);
+        if (L.in_count[1]) cnt1 = *reinterpret_cast<const volatile uint32_t*>(L.in_count[1]);
+        units0 = (cnt0 + 31u) / 32u;
+        n_units = units0 + (cnt1 + 31u) / 32u;
+    }
+
+    for (;;) {
+        uint32_t unit = 0;
+        if (lane == 0) unit = atomicAdd(L.work_head, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+
+        // ---- this lane's ray
+        Ray r;
+        r.hx = r.hy = r.hz = r.t = 0.0f; r.it = 0;
+        uint32_t px = 0;
+        float rdx = 0.f, rdy = 0.f, rdz = 0.f;
+        int status = RS_NONE;   // RS_NONE: nothing (left) to do for this lane
+        bool marching = false;
+        float code = -3.0f;
+        if (L.first) {
+            uint32_t tx, ty;
+            bool outside = false;
+            if (unit < n_heavy) {
+                tx = P.rect[0] + unit % rw; ty = ry0 + unit / rw;
+            } else {
+                outside = true;
+                uint32_t b = unit - n_heavy;
+                const uint32_t n_top = ry0 * P.tiles_x, side = P.tiles_x - rw;
+                if (b < n_top) {
+                    tx = b % P.tiles_x; ty = b / P.tiles_x;
+                } else if (b - n_top < rh4 * side) {
+                    b -= n_top;
+                    const uint32_t k = b % side;
+                    ty = ry0 + b / side; tx = k < P.rect[0] ? k : k + rw;
+                } else {
+                    b -= n_top + rh4 * side;
+                    tx = b % P.tiles_x; ty = ry0 + rh4 + b / P.tiles_x;
+                }
+            }
+            const uint32_t i = tx * 8u + (lane & 7u), j = ty * 4u + (lane >> 3);
+            if (i < P.width && j < P.height) {
+                px = j * P.width + i;
+                float rox, roy, roz;
+                if (outside || !ray_setup(P, i, j, rdx, rdy, rdz, rox, roy, roz)) {
+                    // no fragment: miss code -3, written by the presenter (every rank sees the same test)
+                    if (!L.linked || L.is_presenter) status = RS_MISS;
+                } else {
+                    r.hx = rox; r.hy = roy; r.hz = roz;
+                    marching = true;
+                }
+            }
+        } else {
+            const uint32_t q = unit < units0 ? 0u : 1u;
+            const uint32_t e = (unit - (q ? units0 : 0u)) * 32u + lane;
+            if (e < (q ? cnt1 : cnt0)) {
+                const uint32_t idx = q ? e : L.max_pixels - 1u - e;
+                const float4 pos = L.in_pos[q][idx];
+                const uint2 id = L.in_id[q][idx];
+                r.hx = pos.x; r.hy = pos.y; r.hz = pos.z; r.t = pos.w;
+                px = id.x; r.it = (int)id.y;
+                float rox, roy, roz;
+                (void)ray_setup(P, px % P.width, px / P.width, rdx, rdy, rdz, rox, roy, roz);  // the direction only
+                marching = true;
+            }
+        }
+
+        // ---- sdfRaycast, material.frag:92-128, maxSteps = 256 (:142).  The warp leaves on an empty ballot.
+        const int max_steps = (int)P.max_steps;
+        CellCache cell;
+        cell.x0 = cell.y0 = cell.z0 = __int_as_float(0x7fc00000);  // NaN: never equal, the first step always fetches
+        cell.c000 = cell.c100 = cell.c010 = cell.c110 = cell.c001 = cell.c101 = cell.c011 = cell.c111 = 0.0f;
+        const bool started_here = L.first != 0u;
+        while (__ballot_sync(0xffffffffu, marching)) {
+            if (marching) {
+                float ax, ay, az;
+                tex_coord<SNAP>(P, v0, r.hx, r.hy, r.hz, ax, ay, az);
+                // who owns this sample: the rank whose own slices hold the lower z tap.  The two termination tests
+                // need no texel, so whichever rank holds the ray applies them first: a position outside the box (whose
+                // taps mirror back to slices of some other rank) ends here instead of travelling on, and inside the box
+                // the lower tap is monotone along the ray -- at most world - 1 hand-offs
+                int go = 0;
+                if (L.linked) {
+                    const int z = lower_z_tap<LINEAR>((int)P.D, az);
+                    go = z < (int)L.own_z0 ? RS_DOWN : (z >= (int)L.own_z1 ? RS_UP : 0);
+                }
+                if (go && started_here && r.it == 0) {
+                    status = RS_NONE; marching = false;   // a ray that STARTS elsewhere is started by its owner
+                } else if (r.it >= max_steps - 1) {                                                  // :99-102
+                    code = -1.0f; status = RS_MISS; marching = false;
+                } else if (oob_dist(P.clip_min, P.clip_max, r.hx, r.hy, r.hz) > 1e-4f) {             // :106-109
+                    code = -2.0f; status = RS_MISS; marching = false;
+                } else if (go) {
+                    status = go; marching = false;
+                } else {
+                    const float dist = dist_at<LINEAR>(v0, ax, ay, az, cell) - 1e-1f;                // :112, :59
+                    if (dist < 1e-5f) {                                                              // :117-121
+                        code = r.t; status = RS_HIT; marching = false;
+                    } else {
+                        r.t += dist;                                                                 // :124
+                        r.hx += rdx * dist; r.hy += rdy * dist; r.hz += rdz * dist;                  // :125
+                        ++r.it;
+                    }
+                }
+            }
+        }
+
+        // ---- finished rays: shade and write; rays that left this rank's slices: append to the out-queue
+        if (status == RS_HIT || status == RS_MISS) finish_pixel<SNAP, LINEAR>(P, L, v0, v1, px, status == RS_HIT, code, r);
+        if (L.linked) {
+#pragma unroll
+            for (int dir = 0; dir < 2; ++dir) {
+                const bool go = status == (dir ? RS_UP : RS_DOWN);
+                const uint32_t m = __ballot_sync(0xffffffffu, go);
+                if (m == 0u) continue;
+                uint32_t base = 0;
+                if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(L.out_count + dir, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                if (go) {
+                    const uint32_t e = base + __popc(m & ((1u << lane) - 1u));
+                    const uint32_t idx = dir ? L.max_pixels - 1u - e : e;
+                    L.out_pos[idx] = make_float4(r.hx, r.hy, r.hz, r.t);
+                    L.out_id[idx] = make_uint2(px, (uint32_t)r.it);
+                }
+            }
+        }
+    }
+
+    // ---- the last CTA to finish resets the counters and tells the neighbours (and, after the last round, the
+    // presenter) that this round's queue entries and pixels are in place
+    if (L.linked) __threadfence_system();  // out-queue entries and the peer stores of finished pixels
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(L.ctas_done, 1u) + 1u == gridDim.x) {
+            *L.work_head = 0u;
+            *L.ctas_done = 0u;
+            if (L.linked) {
+                L.reset_count[0] = 0u; L.reset_count[1] = 0u;
+                __threadfence_system();
+                if (L.sig_round[0]) *reinterpret_cast<volatile uint32_t*>(L.sig_round[0]) = L.sig_round_value;
+                if (L.sig_round[1]) *reinterpret_cast<volatile uint32_t*>(L.sig_round[1]) = L.sig_round_value;
+                if (L.sig_frame) *reinterpret_cast<volatile uint32_t*>(L.sig_frame) = L.sig_frame_value;
+            }
+        }
+    }
+}
+
+// flags in (peer) memory: everything this stream did before is visible system-wide first
+__global__ void signal_kernel(uint32_t* f0, uint32_t v0, uint32_t* f1, uint32_t v1, uint32_t* f2, uint32_t v2, uint32_t* f3,
+                              uint32_t v3) {
+    __threadfence_system();
+    if (f0) *reinterpret_cast<volatile uint32_t*>(f0) = v0;
+    if (f1) *reinterpret_cast<volatile uint32_t*>(f1) = v1;
+    if (f2) *reinterpret_cast<volatile uint32_t*>(f2) = v2;
+    if (f3) *reinterpret_cast<volatile uint32_t*>(f3) = v3;
+}
+
+// fallback for cuStreamWaitValue32: one thread spins until (int)(*flag - value) >= 0, at most ~2 s
+__global__ void spin_wait_kernel(const uint32_t* flag, uint32_t value, uint32_t* timed_out) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        const uint32_t v = *reinterpret_cast<const volatile uint32_t*>(flag);
+        if ((int)(v - value) >= 0) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 2000000000ull) { if (timed_out) *timed_out = 1u; break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
 // tex0.r of every stored texel as a dense float array (the optional distance volume of the tracer)
 __global__ void __launch_bounds__(256) extract_dist_kernel(const float4* __restrict__ tex0, float* __restrict__ dist,
                                                            size_t n) {
@@ -531,6 +864,43 @@ cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s) {
         else if (snap && lin) trace_kernel<true, true><<<grid, 256, 0, s>>>(p);
         else trace_kernel<true, false><<<grid, 256, 0, s>>>(p);
     }
+    return cudaGetLastError();
+}
+
+typedef void (*rounds_fn)(const TraceParams, const LinkParams);
+static rounds_fn pick_rounds(const TraceParams& p) {
+    const bool snap = p.lod != 1.0f, lin = p.filter_linear != 0;
+    return !snap && lin ? trace_rounds_kernel<false, true> : !snap ? trace_rounds_kernel<false, false>
+           : lin ? trace_rounds_kernel<true, true> : trace_rounds_kernel<true, false>;
+}
+
+int trace_rounds_max_ctas_per_sm(const TraceParams& p) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pick_rounds(p), 256, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+cudaError_t launch_trace_rounds(const TraceParams& p, const LinkParams& l, int grid, cudaStream_t s) {
+    if (p.width == 0 || p.height == 0 || grid <= 0) return cudaSuccess;
+    pick_rounds(p)<<<grid, 256, 0, s>>>(p, l);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_signal(uint32_t* const* flags, const uint32_t* values, int n, cudaStream_t s) {
+    for (int i = 0; i < n; i += 4) {
+        uint32_t* f[4] = {nullptr, nullptr, nullptr, nullptr};
+        uint32_t v[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4 && i + k < n; ++k) { f[k] = flags[i + k]; v[k] = values[i + k]; }
+        signal_kernel<<<1, 1, 0, s>>>(f[0], v[0], f[1], v[1], f[2], v[2], f[3], v[3]);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_spin_wait(const uint32_t* flag, uint32_t value, uint32_t* timed_out, cudaStream_t s) {
+    spin_wait_kernel<<<1, 1, 0, s>>>(flag, value, timed_out);
     return cudaGetLastError();
 }
 

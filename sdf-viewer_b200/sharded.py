@@ -1,20 +1,21 @@
-"""Z-slab sharding of the grid across GPUs, one process per GPU (torch.distributed / NCCL).
+"""Z-slab sharding of the grid across GPUs, one process per GPU.
 
 The fill is a pure map over voxels (`sample` depends only on the position,
 /root/reference/src/sdf/mod.rs:43), and the flat index is z-major
 (src/app/scene/sdf/mod.rs:177), so rank g owns the contiguous slices
 [g*D/G, (g+1)*D/G) and no collective is needed to fill them.  The one exchange step is the
-halo: the trilinear / normal taps of the tracer at a slab face read one slice of the neighbour,
-so after a fill each rank sends its first and last owned slice (both textures) to its
-neighbours.  Two implementations, both on the GPU: (a) fused (default): every rank maps its
-neighbours' volumes with CUDA IPC; the library fills the two boundary slices first and the copy
-engines push them into the neighbours' halo slices over NVLink while the interior is still being
-filled; ranks are ordered by a 4-byte stream-ordered NCCL all-reduce after the fill; (b) NCCL
-send/recv of the boundary slices after the fill (used when IPC mapping is unavailable).  (Storing
-the boundary texels straight into peer memory from inside the fill kernel was measured and
-rejected: remote stores into a neighbour whose HBM is saturated by its own fill stall the SMs'
-store pipelines, +0.13 ms on a 0.74 ms kernel)  The trace is sort-last: every rank traces its own
-sub-box into 64-bit (depth, RGBA8) keys and an all-reduce(MIN) composites the frame.
+halo: the trilinear taps of the tracer at a slab face read one slice of the neighbour.
+
+Default (`linked=True`): the slab handles are LINKED through the C ABI (include/sdfgpu.h "linked slabs",
+csrc/link.cu).  `torch.distributed` is used ONCE, at set-up, to gather the 320-byte link blobs (CUDA IPC handles);
+after that every call below is a plain library call -- the fill is one launch whose boundary tiles go first and are
+pushed into the neighbours' halo slices by the copy engines behind a flag, the trace hands rays from rank to rank
+(exact: the frame is the single-volume frame bit for bit) and stores finished pixels straight into rank 0's frame
+over NVLink.  No collective-library call and no host synchronisation between ranks in the frame loop.
+
+Fallback (`linked=False`, or when a rank cannot map its peers): the round-1 path -- halo exchange by CUDA IPC pushes
+ordered with a 4-byte NCCL all-reduce, or NCCL send/recv; sort-last trace composited with all-reduce(MIN) over 64-bit
+(depth, RGBA8) keys (approximate at slab faces: every rank marches its own sub-box).
 
 `torch` is used for the process group, streams and as a view on the library's device memory.
 """
@@ -102,10 +103,12 @@ class _DevMem:
 class ShardedViewer:
     """One rank's part of a Z-sharded SDFViewer.  With world == 1 it is a plain SDFViewer."""
 
-    def __init__(self, dims, bb, loading_passes, rank=0, world=1, device=0, group=None, fused=True):
+    def __init__(self, dims, bb, loading_passes, rank=0, world=1, device=0, group=None, fused=True, linked=True,
+                 max_width=1920, max_height=1080, gbuf=False):
         self.dims, self.bb, self.rank, self.world, self.device = tuple(dims), bb, rank, world, device
         self.dist = group  # the torch.distributed module (None when world == 1)
         self.fused = False
+        self.linked = False
         self._synced = True  # no rank can still be reading a halo slice (nothing has been traced yet)
         if world > 1:
             zr = slab_range(dims[2], rank, world)
@@ -118,13 +121,46 @@ class ShardedViewer:
             n = dims[0] * dims[1] * (self.viewer.z_hi - self.viewer.z_lo) * 4
             self._tex = [torch.as_tensor(_DevMem(p, n, "<f4"), device=torch.device("cuda", device)) for p in (p0, p1)]
             self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", device))
-            if fused:
+            if linked:
+                self._link(max_width, max_height, gbuf)
+            if fused and not self.linked:
                 self._attach_neighbours()
         else:
             self.viewer = SDFViewer.new_voxels(dims, bb, loading_passes, device=device)
 
     def close(self):
+        if self.linked:  # every rank stops using its peers' memory before any of it is unmapped or freed
+            self.viewer.sync()
+            self.dist.barrier()
+            self.viewer.link_detach()
+            self.dist.barrier()
+            self.linked = False
         self.viewer.close()
+
+    def _link(self, max_width, max_height, gbuf):
+        """Set-up only: gather every rank's link blob and attach.  All ranks link, or none does."""
+        v, dist, t = self.viewer, self.dist, self._torch
+        ok, blob = 1, None
+        try:
+            blob = v.link_export(self.rank, self.world, max_width, max_height, gbuf=gbuf)
+        except SdfGpuError:
+            ok = 0
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, blob)
+        if ok and all(b is not None for b in blobs):
+            try:
+                v.link_attach(blobs)
+            except SdfGpuError as e:
+                self.link_error = str(e)
+                ok = 0
+        else:
+            ok = 0
+        flag = t.tensor([ok], dtype=t.int32, device=t.device("cuda", self.device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        self.linked = bool(flag.item())
+        if not self.linked:
+            v.link_detach()
+            v.set_option("fill_halo", 0)
 
     def _attach_neighbours(self):
         """Exchange CUDA IPC handles of the volumes and map the two neighbours' (fused halo exchange).
@@ -160,13 +196,15 @@ class ShardedViewer:
             self.dist.all_reduce(self._flag)
 
     def _before_fill(self):
+        if self.linked:
+            return  # ordered by the library's flags
         # a neighbour may still be reading the halo slices this fill overwrites -- unless the last thing
         # every rank did was a collective that came after its reads (the compositing all-reduce)
         if self.world > 1 and self.fused and not self._synced:
             self._barrier()
 
     def _after_fill(self):
-        if self.world == 1:
+        if self.world == 1 or self.linked:
             return
         if self.fused:
             self._barrier()  # every rank's fill, and with it every halo slice, is complete
@@ -201,7 +239,21 @@ class ShardedViewer:
     def trace_device(self, cam, width, height):
         if self.world == 1:
             return self.viewer.trace_device(cam, width, height)
+        if self.linked:
+            return self.viewer.trace_linked_device(cam, width, height)
         return self._composite(cam, width, height)
+
+    def resample_box(self, box, count=False):
+        self._before_fill()
+        n = self.viewer.resample_box(box, count)
+        self._after_fill()
+        return n
+
+    def reset(self, loading_passes):
+        self._before_fill()
+        self.viewer.reset(loading_passes)
+        if self.world > 1 and not self.linked:
+            self._barrier()
 
     def gather_distance_volume(self):
         """Replicate the distance channel of the whole grid on every rank (4 bytes per voxel): each rank
@@ -250,8 +302,8 @@ class ShardedViewer:
                 out["depth"] = depth_out
             r, d, _ = self.viewer.trace(cam, width, height, out=out)
             return r, d
+        if self.linked:  # the frame lands in rank 0's (pinned) buffers; the other ranks only take part
+            r, d, _ = self.viewer.trace_linked(cam, width, height, rgba_out, depth_out, presenter=(self.rank == 0))
+            return r, d
         keys = self._composite(cam, width, height)
-        rgba8, depth = self.viewer.keys_download(keys, width, height)
-        if depth_out is not None:
-            np.copyto(depth_out, depth)
-        return rgba8, depth
+        return self.viewer.keys_download(keys, width, height, rgba_out, depth_out)

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Camera, Rays, GBUF_FLOATS, SdfGpuError, check  # noqa: F401
+from ._lib import Camera, Rays, GBUF_FLOATS, LINK_BLOB_BYTES, LINK_GBUF, SdfGpuError, check, check_group  # noqa: F401
 
 
 def _f6(bb):
@@ -355,9 +355,10 @@ class SDFViewer:
         check(self._lib.sdfgpu_trace_exact_keys(self._h, C.byref(cam), int(width), int(height), C.byref(k)), self._h)
         return k.value
 
-    def keys_download(self, keys_dev, width, height):
-        rgba8 = np.empty((height, width, 4), np.uint8)
-        depth = np.empty((height, width), np.float32)
+    def keys_download(self, keys_dev, width, height, out_rgba8=None, out_depth=None):
+        """Unpack a (depth, RGBA8) key frame into caller-provided (pinned) buffers, or fresh ones."""
+        rgba8 = out_rgba8 if out_rgba8 is not None and out_rgba8.dtype == np.uint8 else np.empty((height, width, 4), np.uint8)
+        depth = out_depth if out_depth is not None else np.empty((height, width), np.float32)
         check(self._lib.sdfgpu_keys_download(self._h, C.c_void_p(keys_dev), int(width), int(height), _host_ptr(rgba8),
                                              _host_ptr(depth)), self._h)
         return rgba8, depth
@@ -374,6 +375,43 @@ class SDFViewer:
 
     def ipc_detach(self):
         check(self._lib.sdfgpu_ipc_detach(self._h), self._h)
+
+    # ---- linked slabs (multi-GPU behind the C ABI: include/sdfgpu.h "linked slabs")
+    def link_export(self, rank, world, max_width, max_height, gbuf=False):
+        """This rank's link blob (CUDA IPC handles of its volumes and arena); gather the blobs of all ranks."""
+        buf = C.create_string_buffer(LINK_BLOB_BYTES)
+        check(self._lib.sdfgpu_link_export(self._h, int(rank), int(world), int(max_width), int(max_height),
+                                           LINK_GBUF if gbuf else 0, buf, len(buf)), self._h)
+        return buf.raw
+
+    def link_attach(self, blobs):
+        """`blobs`: the link blobs of ranks 0 .. world-1 in rank order.  From here on fills and traces are collective."""
+        raw = b"".join(bytes(b) for b in blobs)
+        buf = C.create_string_buffer(raw, len(raw))
+        check(self._lib.sdfgpu_link_attach(self._h, buf, len(raw) // LINK_BLOB_BYTES), self._h)
+
+    def link_detach(self):
+        check(self._lib.sdfgpu_link_detach(self._h), self._h)
+
+    def trace_linked(self, cam, width, height, out_rgba8=None, out_depth=None, out_gbuf=None, gbuf=False, presenter=True):
+        """The collective exact trace of a linked handle.  Rank 0 (`presenter`) receives the frame; the others pass
+        nothing and get (None, None, None)."""
+        r = d = g = None
+        if presenter:
+            r = out_rgba8 if out_rgba8 is not None else np.empty((height, width, 4), np.uint8)
+            d = out_depth if out_depth is not None else np.empty((height, width), np.float32)
+            if gbuf:
+                g = out_gbuf if out_gbuf is not None else np.empty((height, width, GBUF_FLOATS), np.float32)
+        check(self._lib.sdfgpu_trace_linked(self._h, C.byref(cam), int(width), int(height), int(bool(gbuf)), _host_ptr(r),
+                                            _host_ptr(d), _host_ptr(g)), self._h)
+        return r, d, g
+
+    def trace_linked_device(self, cam, width, height, gbuf=False):
+        """Enqueue the collective trace; device pointers (rgba8, depth, gbuf) on rank 0, None elsewhere."""
+        r, d, g = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(self._lib.sdfgpu_trace_linked_device(self._h, C.byref(cam), int(width), int(height), int(bool(gbuf)),
+                                                   C.byref(r), C.byref(d), C.byref(g)), self._h)
+        return r.value, d.value, g.value
 
     # ---- stream
     def sync(self):
@@ -394,6 +432,147 @@ class SDFViewer:
 
     def set_option(self, key, value):
         check(self._lib.sdfgpu_set_option(self._h, key.encode(), int(value)), self._h)
+
+
+class _RankView(SDFViewer):
+    """A group's handle of one rank: owned by the group (never destroyed from here)."""
+
+    def close(self):
+        self._h = None
+
+
+class SDFViewerGroup:
+    """`SDFViewer` over several GPUs driven by ONE process and one thread, as the reference's scene is
+    (scene/mod.rs:22-31,158-225): the grid is sharded along z over `devices`, every call below runs on all of
+    them, and `trace*` returns the frame of one SDFViewer holding the whole grid (include/sdfgpu.h, sdfgpu_group_*)."""
+
+    def __init__(self, handle, bounding_box):
+        self._lib = _lib.load()
+        self._g = handle
+        self.bounding_box = bounding_box
+        self.size = self._lib.sdfgpu_group_size(self._g)
+        self.ranks = [_RankView(C.c_void_p(self._lib.sdfgpu_group_rank(self._g, r)), bounding_box) for r in range(self.size)]
+        self.dims = self.ranks[0].dims
+        self._tape = None
+
+    @classmethod
+    def new_voxels(cls, voxels, bb, loading_passes, devices, max_width=1920, max_height=1080, gbuf=False):
+        lib = _lib.load()
+        g = C.c_void_p()
+        v = (C.c_uint32 * 3)(*[int(x) for x in voxels])
+        dv = (C.c_int * len(devices))(*[int(d) for d in devices])
+        check_group(lib.sdfgpu_group_create(_f6(bb), v, int(loading_passes), dv, len(devices), int(max_width), int(max_height),
+                                            LINK_GBUF if gbuf else 0, C.byref(g)))
+        return cls(g, bb)
+
+    @classmethod
+    def from_bb(cls, bb, max_voxels_side, loading_passes, device_mask=1, max_width=1920, max_height=1080):
+        lib = _lib.load()
+        g = C.c_void_p()
+        check_group(lib.sdfgpu_group_create_mask(_f6(bb), int(max_voxels_side), int(loading_passes), int(device_mask),
+                                                 int(max_width), int(max_height), C.byref(g)))
+        return cls(g, bb)
+
+    def close(self):
+        if self._g:
+            for r in self.ranks:
+                r._h = None
+            self._lib.sdfgpu_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, rc):
+        check_group(rc, self._g)
+
+    def set_tape(self, tape_bytes):
+        buf = (C.c_char * len(tape_bytes)).from_buffer_copy(tape_bytes)
+        self._ck(self._lib.sdfgpu_group_set_tape(self._g, buf, len(tape_bytes)))
+        self._tape = bytes(tape_bytes)
+
+    def update(self, sdf, max_passes=0):
+        changed = None
+        if sdf is not None:
+            changed = sdf.changed()
+            tape = bytes(sdf.tape())
+            if self._tape is None or tape != self._tape:
+                self.set_tape(tape)
+        it = C.c_uint64()
+        box = _f6(changed) if changed is not None else None
+        self._ck(self._lib.sdfgpu_group_update(self._g, box, int(max_passes), C.byref(it)))
+        return it.value
+
+    def update_surface(self, sdf, max_delta_time=0.030):
+        surf = _surface_struct(sdf)
+        it = C.c_uint64()
+        self._ck(self._lib.sdfgpu_group_update_surface(self._g, C.byref(surf), float(max_delta_time), C.byref(it)))
+        err = getattr(surf, "_py_error", None)
+        if err and err[0] is not None:
+            raise err[0]
+        return it.value
+
+    def fill_all(self):
+        self._ck(self._lib.sdfgpu_group_fill_all(self._g))
+
+    def resample_box(self, box, count=False):
+        n = C.c_uint64()
+        self._ck(self._lib.sdfgpu_group_resample_box(self._g, _f6(box), C.byref(n) if count else None))
+        return n.value if count else None
+
+    def commit(self):
+        self._ck(self._lib.sdfgpu_group_commit(self._g))
+
+    def reset(self, loading_passes):
+        self._ck(self._lib.sdfgpu_group_reset(self._g, int(loading_passes)))
+        self._tape = None
+
+    def set_option(self, key, value):
+        self._ck(self._lib.sdfgpu_group_set_option(self._g, key.encode(), int(value)))
+
+    def sync(self):
+        self._ck(self._lib.sdfgpu_group_sync(self._g))
+
+    def loading_state(self):
+        ln, tot = C.c_uint64(), C.c_uint64()
+        left, passes = C.c_uint32(), C.c_uint32()
+        self._ck(self._lib.sdfgpu_group_loading_state(self._g, C.byref(ln), C.byref(tot), C.byref(left), C.byref(passes)))
+        return ln.value, tot.value, left.value, passes.value
+
+    def download(self, out0=None, out1=None):
+        """The whole grid's volumes, shaped (depth, height, width, 4)."""
+        shape = (self.dims[2], self.dims[1], self.dims[0], 4)
+        a0 = out0 if out0 is not None else np.empty(shape, np.float32)
+        a1 = out1 if out1 is not None else np.empty(shape, np.float32)
+        self._ck(self._lib.sdfgpu_group_download(self._g, _host_ptr(a0), _host_ptr(a1)))
+        return a0, a1
+
+    def trace_rgba8(self, cam, width, height, out_rgba8=None, out_depth=None):
+        r = out_rgba8 if out_rgba8 is not None else np.empty((height, width, 4), np.uint8)
+        d = out_depth if out_depth is not None else np.empty((height, width), np.float32)
+        self._ck(self._lib.sdfgpu_group_trace_rgba8(self._g, C.byref(cam), int(width), int(height), _host_ptr(r), _host_ptr(d)))
+        return r, d
+
+    def trace(self, cam, width, height, gbuf=True):
+        """(rgba8, depth, gbuf); the G-buffer needs a group created with gbuf=True."""
+        r = np.empty((height, width, 4), np.uint8)
+        d = np.empty((height, width), np.float32)
+        g = np.empty((height, width, GBUF_FLOATS), np.float32) if gbuf else None
+        self._ck(self._lib.sdfgpu_group_trace(self._g, C.byref(cam), int(width), int(height), _host_ptr(r), _host_ptr(d), _host_ptr(g)))
+        return r, d, g
+
+    @property
+    def launch_count(self):
+        return sum(r.launch_count for r in self.ranks)
 
 
 def tape_validate(tape_bytes):

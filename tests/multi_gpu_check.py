@@ -1,5 +1,7 @@
-"""Run under torchrun with N >= 2 ranks (one GPU each): Z-sharded fill + NCCL halo exchange +
-sort-last composited trace, checked against the CPU oracle.  tests/test_sharded_gpu.py launches it."""
+"""Run under torchrun with N >= 2 ranks (one GPU each).  First the default path -- slab handles linked through the
+C ABI (flag-ordered halo pushes, exact ray-hand-off trace; no torch.distributed call after set-up) -- checked against
+the CPU oracle (volumes, halos) and against ONE handle holding the whole grid (frames, bit for bit); then the
+fallbacks (NCCL / IPC halo exchange, sort-last and replicated-volume traces).  tests/test_sharded_gpu.py launches it."""
 import os
 import sys
 
@@ -28,6 +30,68 @@ def check_slab(sv, v, full, dims, rank):
             f"rank {rank}: stored slab [{v.z_lo},{v.z_hi}) differs from the oracle (halo exchange, fused={sv.fused})"
 
 
+def check_linked(rank, world, local, dims, w, h, sdf, full, want_its):
+    """The default path.  After ShardedViewer's set-up nothing below calls torch.distributed but the test's own
+    barriers around host-side comparisons."""
+    sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, max_width=w, max_height=h, gbuf=True)
+    assert sv.linked, getattr(sv, "link_error", "linking failed")
+    v = sv.viewer
+    assert v.get_info("linked") == 1
+    its = sv.update(S.SDFDemo())
+    sv.commit()
+    assert its == want_its
+    check_slab(sv, v, full, dims, rank)
+    cams = [S.default_camera(w, h), S.look_at_camera((0.3, 0.2, 1.4), (0.0, 0.1, 0.0), w, h),
+            S.look_at_camera((0.2, 0.1, 0.3), (1, 0.2, -0.4), w, h), S.look_at_camera((0.1, 0.05, -2.6), (0, 0, 0), w, h),
+            S.look_at_camera((0.1, 0.05, 2.6), (0, 0, 0), w, h)]
+    with S.SDFViewer.new_voxels(dims, BB, 2, device=local) as whole:
+        whole.set_tape(sdf.tape()); whole.update(None); whole.commit()
+        for c in cams * 2:
+            got8, got_d = sv.trace_host(c, w, h)
+            if rank == 0:
+                want8, want_d = whole.trace_rgba8(c, w, h)
+                assert np.array_equal(got8, want8), "linked trace differs from the single-volume frame"
+                assert np.array_equal(got_d.view(np.uint32), np.clip(want_d, 0, 1).view(np.uint32))
+        got8, got_d, got_g = v.trace_linked(cams[3], w, h, gbuf=True, presenter=(rank == 0))
+        if rank == 0:
+            _, _, want_g = whole.trace(cams[3], w, h, gbuf=True)
+            cols = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 15]
+            assert np.array_equal(got_g[..., cols].view(np.uint32), want_g[..., cols].view(np.uint32)), "linked G-buffer differs"
+        # reset + one-launch fill_all, then a dirty box that crosses the slab faces, then one inside rank 0's slab
+        sv.reset(1); whole.reset(1)
+        v.set_tape(sdf.tape()); whole.set_tape(sdf.tape())
+        sv.fill_all(); whole.fill_all()
+        sv.commit(); whole.commit()
+        check_slab(sv, v, full, dims, rank)
+        other = S.tape.csg_tape(S.tape.csg_primitive_table(12))
+        for box in ((-0.5, -0.5, -0.6, 0.5, 0.5, 0.6), (-0.3, -0.2, -0.95, 0.4, 0.3, -0.8)):
+            v.set_tape(other); whole.set_tape(other)
+            sv.resample_box(box); whole.resample_box(box)
+            t0, t1 = whole.download()
+            v.sync(); torch.cuda.synchronize(); dist.barrier()
+            for t, want in zip(sv._tex, (t0, t1)):
+                got = t.cpu().numpy().reshape(v.z_hi - v.z_lo, dims[1], dims[0], 4)
+                assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(want[v.z_lo:v.z_hi]).view(np.uint32)), \
+                    f"rank {rank}: stored slab differs from the single handle after resample_box{box}"
+            got8, got_d = sv.trace_host(cams[0], w, h)
+            if rank == 0:
+                want8, want_d = whole.trace_rgba8(cams[0], w, h)
+                assert np.array_equal(got8, want8) and np.array_equal(got_d.view(np.uint32), np.clip(want_d, 0, 1).view(np.uint32))
+        # frames enqueued back to back without host synchronisation (the device-timed loop of bench.py)
+        for c in cams * 3:
+            sv.fill_all()
+            sv.trace_device(c, w, h)
+        got8, got_d = sv.trace_host(cams[1], w, h)
+        if rank == 0:
+            whole.fill_all()
+            want8, want_d = whole.trace_rgba8(cams[1], w, h)
+            assert np.array_equal(got8, want8) and np.array_equal(got_d.view(np.uint32), np.clip(want_d, 0, 1).view(np.uint32))
+    dist.barrier()
+    if rank == 0:
+        print(f"linked path ok: world {world}, memops {v.get_info('link_memops')}, {v.get_info('link_round_epoch')} trace rounds")
+    sv.close()
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -37,9 +101,10 @@ def main():
     sdf = S.SDFDemo()
     full = orc.Viewer(BB, dims, 2)
     want_its = full.update(orc.Sampler(tape=sdf.tape()))
+    check_linked(rank, world, local, dims, w, h, sdf, full, want_its)
     fused_modes = []
     for fused in (False, True):                # NCCL send/recv exchange, then the fused in-kernel P2P exchange
-        sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, fused=fused)
+        sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, fused=fused, linked=False)
         fused_modes.append(sv.fused)
         v = sv.viewer
         its = sv.update(S.SDFDemo())           # both passes + halo exchange
