@@ -7,8 +7,15 @@ weak scaling on N GPUs.
 
 A step = one full fill of the grid (every voxel sampled once through the tape) + one trace of the
 frame.  `value` is voxels / step time with everything resident in HBM (CUDA events on the library's
-stream; the fill kernel alone is `fill_samples_per_sec` and the `roofline` object); `e2e` is the same through the host-buffer C-ABI calls (tape H2D, frame D2H inside the
-timed region).  Prints ONE JSON line on rank 0.
+stream; the fill kernel alone is `fill_samples_per_sec` and the `roofline` object); `e2e` is the same
+through the host-buffer C-ABI calls (tape H2D, frame D2H into pinned memory inside the timed region).
+N > 1: one process per GPU, slab handles linked through the C ABI (include/sdfgpu.h "linked slabs");
+torch.distributed is used at set-up (link blobs) and for the barriers / max-over-ranks of the timing
+contract only -- the step itself makes no collective-library call.  After the timed region every N > 1
+run checks itself (`parity_check`).  Prints ONE JSON line on rank 0.
+
+The other BASELINE.json configs ride along as extra keys (outside the timed region): `csg_1k_512` (C3),
+`dirty_60hz` (C5), `trace_closeup`, `mesh` at N = 1; `c4_trace_2160p` at N > 1.
 """
 import argparse
 import json
@@ -25,6 +32,9 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 
 BB = ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))
 BYTES_PER_SAMPLE = 32  # tex0 + tex1 RGBA32F (scene/sdf/mod.rs:76,196-208)
+PROGRAM_KERNEL = {0: "fill_kernel<interpreter>", 1: "sdfgpu_fill_jit", 2: "fill_kernel<demo>"}
+FILL_CAPTURE = "profiles/r01_fill_ncu_summary.txt"
+TRACE_CAPTURE = "profiles/r01_trace_ncu_summary.txt"
 
 
 def grid_for(n_gpus, side):
@@ -36,6 +46,27 @@ def grid_for(n_gpus, side):
         k //= 2
         axis = (axis - 1) % 3
     return tuple(dims)
+
+
+def host_threads():
+    """Host cores this process may use.  torchrun exports OMP_NUM_THREADS=1; the CPU legs pass this count to
+    the oracle explicitly so that every N is measured against the same number of cores."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def workload_name(workload, dims, W, H):
+    return (f"{ {'demo': 'demo_sdf', 'csg': 'csg_1k', 'wasm': 'demo_sdf as a WebAssembly guest lowered to a scalar program'}[workload]} "
+            f"{dims[0]}x{dims[1]}x{dims[2]} grid fill + {W}x{H} sphere trace, default scene camera")
+
+
+def common_config(args, dims):
+    """Identical in both arms."""
+    return {"workload": workload_name(args.workload, dims, args.width, args.height), "grid": list(dims),
+            "frame": [args.width, args.height], "voxels_per_gpu": args.grid ** 3, "n_gpus": args.gpus,
+            "step": "fill of every voxel + trace of the frame"}
 
 
 class ClockSampler:
@@ -82,37 +113,49 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-def ncu_traffic():
-    """dram bytes read + written per fill launch, from the committed `ncu --set full` capture."""
+CAPTURE_COMMITS = {"profiles/r01_fill_ncu_summary.txt": "7431657 (round 1)", "profiles/r01_trace_ncu_summary.txt": "1e579a6 (round 1)",
+                   "profiles/r02_fill_csg_ncu_summary.txt": "dad1a00 (round 2)"}
+
+
+def capture_commit(path):
+    """The commit that last touched a committed capture (so a stale capture is visible in the line); the GPU box
+    has no .git, there the recorded hash is used."""
+    if not os.path.isdir(os.path.join(ROOT, ".git")):
+        return CAPTURE_COMMITS.get(path)
     try:
-        rd = wr = None
-        for line in open(os.path.join(ROOT, "profiles", "r01_fill_ncu_summary.txt")):
-            k, _, v = line.partition(" = ")
-            if k.startswith("dram__bytes_"):
-                num, unit = v.split()[:2]
-                val = float(num) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
-                if "read" in k: rd = val
-                else: wr = val
-        return rd + wr
+        r = subprocess.run(["git", "-C", ROOT, "log", "-1", "--format=%h %cs", "--", path], capture_output=True, text=True, timeout=10)
+        return r.stdout.strip() or None
     except Exception:
         return None
+
+
+def ncu_metrics(path, keys):
+    out = {}
+    try:
+        for line in open(os.path.join(ROOT, path)):
+            k, _, v = line.partition(" = ")
+            if k in keys:
+                num, unit = (v.split() + [""])[:2]
+                out[keys[k]] = float(num) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+    except Exception:
+        return None
+    return out
+
+
+def ncu_traffic():
+    """dram bytes read + written per fill launch, from the committed `ncu --set full` capture of this kernel."""
+    m = ncu_metrics(FILL_CAPTURE, {"dram__bytes_read.sum": "rd", "dram__bytes_write.sum": "wr"})
+    return m["rd"] + m["wr"] if m and "rd" in m and "wr" in m else None
 
 
 def trace_profile():
     """L1/TEX and L2 hit rates and DRAM traffic of the trace kernel from the committed ncu capture."""
-    keys = {"l1tex__t_sector_hit_rate.pct": "l1tex_hit_pct", "lts__t_sector_hit_rate.pct": "l2_hit_pct",
-            "dram__bytes_read.sum": "dram_read", "gpu__time_duration.sum": "ncu_duration_us"}
-    out = {}
-    try:
-        for line in open(os.path.join(ROOT, "profiles", "r01_trace_ncu_summary.txt")):
-            k, _, v = line.partition(" = ")
-            if k in keys:
-                num, unit = (v.split() + [""])[:2]
-                out[keys[k]] = float(num) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3}.get(unit, 1)
-        out["source"] = "profiles/r01_trace_ncu_summary.txt (ncu --set full; 512^3 volume, 1920x1080, default camera)"
-        return out
-    except Exception:
-        return None
+    out = ncu_metrics(TRACE_CAPTURE, {"l1tex__t_sector_hit_rate.pct": "l1tex_hit_pct", "lts__t_sector_hit_rate.pct": "l2_hit_pct",
+                                      "dram__bytes_read.sum": "dram_read", "gpu__time_duration.sum": "ncu_duration_us"})
+    if out:
+        out["source"] = TRACE_CAPTURE + " (ncu --set full; 512^3 volume, 1920x1080, default camera)"
+        out["capture_commit"] = capture_commit(TRACE_CAPTURE)
+    return out
 
 
 def peaks():
@@ -123,10 +166,18 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_fill_sample(orc, tape, dims, threads, target_s=6.0):
-    """Oracle fill (OpenMP over z, all host threads) on a bounded sample of the same grid; samples/s."""
+# ------------------------------------------------------------------------------------------ CPU legs (oracle)
+
+def cpu_sampler(orc, workload, tape):
+    """The closest stand-in for the reference's native SDFDemo::sample: the oracle's direct restatement
+    (oracle/sdf_oracle.cpp demo_sample); other workloads have no native form and run the oracle's tape evaluator."""
+    return orc.Sampler() if workload == "demo" else orc.Sampler(tape=tape)
+
+
+def cpu_fill_sample(orc, sampler, dims, threads, target_s=6.0):
+    """Oracle fill (OpenMP over z, `threads` host threads) on a bounded sample of the same grid; samples/s."""
     v = orc.Viewer(BB, dims, 1)
-    s = orc.Sampler(tape=tape)
+    s = sampler
     mid = dims[2] // 2
     probe = min(dims[2], max(1, 2 * threads))  # enough slices to occupy every thread
     z0 = max(0, mid - probe // 2)
@@ -141,26 +192,91 @@ def cpu_fill_sample(orc, tape, dims, threads, target_s=6.0):
                     f"({n} samples, {dt:.2f} s wall, {threads} threads)")
 
 
-def cpu_reference_order_rate(orc, tape, side=96):
+def cpu_reference_order_rate(orc, sampler, side=96):
     """The reference's own configuration: ONE thread, LoadingManager visit order, 2 passes
     (scene/sdf/mod.rs:173-215 is single-threaded); a small grid bounds the run."""
     v = orc.Viewer(BB, (side, side, side), 2)
-    s = orc.Sampler(tape=tape)
-    t = time.perf_counter(); it = v.update(s); dt = time.perf_counter() - t
+    t = time.perf_counter(); it = v.update(sampler); dt = time.perf_counter() - t
     return side ** 3 / dt, f"{side}^3 grid, 2 passes, {it} iterations, reference visit order, 1 thread, {dt:.2f} s"
 
 
-def cpu_trace_sample(orc, S, tape, dims, W, H, threads, rows=48):
+def cpu_trace_sample(orc, sampler, dims, W, H, threads, rows=48):
     """Oracle trace (the restated fragment shader) of a band of rows of the same frame; rays/s."""
     v = orc.Viewer(BB, dims, 1)
-    v.fill_all(orc.Sampler(tape=tape), threads=threads)
-    cam = S.default_camera(W, H)
-    P = orc.trace_params(S.camera_rays(cam, W, H), BB, dims, lod=1.0, filter_linear=1)
+    v.fill_all(sampler, threads=threads)
+    P = orc.trace_params(orc.default_rays(W, H), BB, dims, lod=1.0, filter_linear=1)
     r0 = max(0, H // 2 - rows // 2)
     t = time.perf_counter()
     orc.trace(P, v.tex0, v.tex1, W, H, rows=(r0, r0 + rows), gbuf=False, threads=threads)
     dt = time.perf_counter() - t
     return W * rows / dt, f"rows [{r0},{r0 + rows}) of the {W}x{H} frame ({W * rows} rays, {dt:.2f} s, {threads} threads)"
+
+
+def cpu_baseline_block(orc, workload, tape, dims, W, H, threads, target_s):
+    sampler = cpu_sampler(orc, workload, tape)
+    val, sample = cpu_fill_sample(orc, sampler, dims, threads, target_s=target_s)
+    one_thread, one_thread_sample = cpu_reference_order_rate(orc, sampler)
+    cpu_dims = tuple(min(d, 256) for d in dims)  # the CPU trace sample marches a volume the host can hold
+    rays, rays_sample = cpu_trace_sample(orc, sampler, cpu_dims, W, H, threads)
+    return {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
+            "sampler": "direct restatement of SDFDemo::sample (oracle demo_sample)" if workload == "demo" else "oracle tape evaluator",
+            "reference_order_1_thread": one_thread, "reference_order_sample": one_thread_sample,
+            "rays_per_sec": rays, "rays_sample": rays_sample + f", {cpu_dims[0]}^3 volume"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The Rust/wasmer build cannot
+    be produced here (no cargo/rustc), so this is the C++ restatement in oracle/ (kind "port"), on all
+    host cores (the reference loop itself is single-threaded, scene/sdf/mod.rs:174).  Loads oracle/liboracle.so
+    only -- nothing of the product."""
+    if rank != 0:
+        return
+    import orc
+    orc.build()
+    dims = grid_for(args.gpus, args.grid)
+    threads = host_threads()
+    tape = None
+    if args.workload != "demo":
+        raise SystemExit("--impl reference runs the demo workload (the reference's SDFDemo)")
+    rates, sample = [], ""
+    per_step = max(0.5, min(20.0, 90.0 / max(1, args.steps + args.warmup)))  # the whole run: about a minute and a half
+    sampler = cpu_sampler(orc, "demo", tape)
+    for i in range(args.warmup + args.steps):
+        r, sample = cpu_fill_sample(orc, sampler, dims, threads, target_s=per_step)
+        if i >= args.warmup:
+            rates.append(r)
+    val = sum(rates) / len(rates)
+    n_vox = dims[0] * dims[1] * dims[2]
+    one_thread, one_thread_sample = cpu_reference_order_rate(orc, sampler)
+    cpu_dims = tuple(min(d, 256) for d in dims)
+    rays, rays_sample = cpu_trace_sample(orc, sampler, cpu_dims, args.width, args.height, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": "sdf_samples_per_sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_vox / val, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": common_config(args, dims),
+        "detail": {"step": "bounded sample of the grid fill on the host cores (C++ port of the reference loop, OpenMP over z); "
+                           "ms_per_step extrapolates the sample's rate to the whole grid",
+                   "omp_threads": threads, "omp_env": os.environ.get("OMP_NUM_THREADS")},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
+                         "sampler": "direct restatement of SDFDemo::sample (oracle demo_sample)",
+                         "reference_order_1_thread": one_thread, "reference_order_sample": one_thread_sample,
+                         "rays_per_sec": rays, "rays_sample": rays_sample + f", {cpu_dims[0]}^3 volume"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU extras
+
+def timed(torch, v, stream, fn, reps):
+    fn(); v.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream); v.sync(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
 
 
 def host_sampled_path(orc, S, threads, side=256):
@@ -190,73 +306,163 @@ def host_sampled_path(orc, S, threads, side=256):
 def trace_modes_live(torch, v, stream, cam, W, H, reps=20):
     """Trace time for the other distance sources of the march (option trace_distance_volume; the step above uses 0,
     tex0.r in place): dense R32F copy, the same as a 3-D CUDA array through the TMU in point mode (both give the
-    identical frame), and hardware LINEAR filtering (approximate, outside the 1e-5 bar).  The volume is not
-    re-filled in between, which is the situation these modes are for (many frames per fill)."""
+    identical frame), and hardware LINEAR filtering (approximate, outside the 1e-5 bar); and for the persistent-warp
+    kernel (trace_variant 2).  The volume is not re-filled in between (many frames per fill)."""
     out = {}
     try:
         for mode, name in ((0, "tex0_in_place_ms"), (1, "dense_r32f_ms"), (2, "tmu_point_ms"), (3, "tmu_hw_linear_approx_ms")):
             v.set_option("trace_distance_volume", mode)
-            v.trace_device(cam, W, H)  # builds this mode's distance volume
-            v.sync()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for _ in range(reps):
-                v.trace_device(cam, W, H)
-            e1.record(stream)
-            v.sync()
-            torch.cuda.synchronize()
-            out[name] = e0.elapsed_time(e1) / reps
+            out[name] = timed(torch, v, stream, lambda: v.trace_device(cam, W, H), reps)
+        v.set_option("trace_distance_volume", 0)
+        v.set_option("trace_variant", 2)
+        out["persistent_warps_ms"] = timed(torch, v, stream, lambda: v.trace_device(cam, W, H), reps)
     except Exception as e:  # an extra: never a reason to lose the bench line
         out["error"] = str(e)
     finally:
         try:
             v.set_option("trace_distance_volume", 0)
+            v.set_option("trace_variant", 0)
         except Exception:
             pass
     return out
 
 
-def workload_name(workload, dims, W, H):
-    return (f"{ {'demo': 'demo_sdf', 'csg': 'csg_1k', 'wasm': 'demo_sdf as a WebAssembly guest lowered to a scalar program'}[workload]} {dims[0]}x{dims[1]}x{dims[2]} "
-            f"grid fill + {W}x{H} sphere trace, default scene camera")
+def extras_single_gpu(torch, S, v, stream, W, H, side, peak):
+    """BASELINE.json configs C3 and C5 and the close-up trace, on the handle of the bench (refilled afterwards by
+    nobody: this runs after every timed region)."""
+    out = {}
+    try:  # ---- C3: CSG of 1000 random primitives, 512^3 (tape-interpreter stress)
+        v.set_tape(S.tape.csg_tape())
+        ms = timed(torch, v, stream, v.fill_all, 5)
+        prog = v.get_info("last_fill_program")
+        v.commit()
+        cam = S.default_camera(W, H)
+        tms = timed(torch, v, stream, lambda: v.trace_device(cam, W, H), 10)
+        alu = ncu_metrics("profiles/r02_fill_csg_ncu_summary.txt",
+                          {"smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+                           "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
+                           "smsp__inst_executed.sum": "warp_instructions"})
+        out["csg_1k_512"] = {
+            "config": f"BASELINE.json configs[2]: union of 1000 random primitives, {side}^3, {W}x{H}",
+            "fill_ms": ms, "samples_per_sec": side ** 3 / (ms * 1e-3), "kernel": PROGRAM_KERNEL.get(prog, str(prog)),
+            "voxels_per_thread": v.get_info("last_fill_voxels_per_thread"), "tile_culling": bool(v.get_info("tape_culled")),
+            "hbm_frac": side ** 3 * BYTES_PER_SAMPLE / (ms * 1e-3) / 1e9 / peak, "trace_ms": tms,
+            "rays_per_sec": W * H / (tms * 1e-3),
+            "ncu": dict(alu or {}, source="profiles/r02_fill_csg_ncu_summary.txt", capture_commit=capture_commit("profiles/r02_fill_csg_ncu_summary.txt"))}
+        try:
+            st = v.cull_stats()
+            out["csg_1k_512"]["cull_survivors_per_tile"] = st
+        except Exception as e:
+            out["csg_1k_512"]["cull_survivors_per_tile"] = {"error": str(e)}
+    except Exception as e:
+        out["csg_1k_512"] = {"error": str(e)}
+    try:  # ---- C5: animated parameter, whole-bbox change (what the reference demo reports), 3-pass re-sample
+        sdf = S.SDFDemo()
+        v.reset(2)
+        v.update(sdf)
+        v.sync()
+
+        def sweep():
+            sdf.set_parameter("sphere_radius", 1.05 if sdf.params["sphere_radius"] < 1.05 else 1.04)
+            v.update(sdf)
+
+        ms = timed(torch, v, stream, sweep, 10)
+        h = 128 / float(side - 1)
+        box = (-h, -h, -h, h, h, h)
+        n = v.resample_box(box, count=True)
+        us = 1e3 * timed(torch, v, stream, lambda: v.resample_box(box), 50)
+        out["dirty_60hz"] = {
+            "config": f"BASELINE.json configs[4]: sphere_radius edited every frame (demo/sphere.rs:75-84), {side}^3",
+            "whole_bbox_change_ms": ms, "whole_bbox_change_hz": 1e3 / ms,
+            "whole_bbox_what": "set_tape + the 3-pass re-sample of scene/sdf/mod.rs:144-153 (passes 1, 2 conditional)",
+            "frame_budget_fraction_at_60hz": ms / (1e3 / 60.0),
+            "sub_block_voxels": int(n), "sub_block_us": us, "sub_block_samples_per_sec": n / (us * 1e-6),
+            "sub_block_what": "sdfgpu_resample_box of a 128^3 dirty AABB (mod.rs:184-190 restricted to its index range)"}
+    except Exception as e:
+        out["dirty_60hz"] = {"error": str(e)}
+    try:  # ---- the close-up camera (87 % of the rays enter the box)
+        v.set_tape(S.tape.demo_tape()); v.fill_all(); v.commit()
+        cam = S.look_at_camera((0.9, 1.1, 1.8), (0, 0, 0), W, H)
+        res = {}
+        for variant in (0, 2):
+            v.set_option("trace_variant", variant)
+            ms = timed(torch, v, stream, lambda: v.trace_device(cam, W, H), 20)
+            res[f"variant{variant}_ms"] = ms
+            res[f"variant{variant}_rays_per_sec"] = W * H / (ms * 1e-3)
+        v.set_option("trace_variant", 0)
+        out["trace_closeup"] = res
+    except Exception as e:
+        out["trace_closeup"] = {"error": str(e)}
+    try:  # ---- SURVEY 8f-4: isosurface mesh from the resident volume
+        if hasattr(v, "mesh"):
+            cells = (side - 1) ** 3
+            v.mesh(download=False); v.sync()
+            t = time.perf_counter()
+            reps = 5
+            for _ in range(reps):
+                nv, nt = v.mesh(download=False)
+            v.sync()
+            dt = (time.perf_counter() - t) / reps
+            out["mesh"] = {"vertices": int(nv), "triangles": int(nt), "ms": dt * 1e3, "triangles_per_sec": nt / dt,
+                           "cells_per_sec": cells / dt, "what": "marching cubes over the resident distance volume, counts read back"}
+    except Exception as e:
+        out["mesh"] = {"error": str(e)}
+    return out
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path.  The Rust/wasmer build cannot
-    be produced here (no cargo/rustc), so this is the C++ restatement in oracle/ (kind "port"), on all
-    host cores (the reference loop itself is single-threaded, scene/sdf/mod.rs:174)."""
-    if rank != 0:
-        return
-    import orc
-    import sdf_viewer_b200.tape as T
-    orc.build()
-    dims = grid_for(args.gpus, args.grid)
-    tape = T.demo_tape()
-    threads = orc.lib().orc_max_threads()
-    rates, sample = [], ""
-    per_step = max(0.5, min(20.0, 90.0 / max(1, args.steps + args.warmup)))  # the whole run: about a minute and a half
-    for i in range(args.warmup + args.steps):
-        r, sample = cpu_fill_sample(orc, tape, dims, threads, target_s=per_step)
-        if i >= args.warmup:
-            rates.append(r)
-    val = sum(rates) / len(rates)
-    n_vox = dims[0] * dims[1] * dims[2]
-    import sdf_viewer_b200 as S
-    one_thread, one_thread_sample = cpu_reference_order_rate(orc, tape)
-    cpu_dims = tuple(min(d, 256) for d in dims)  # the CPU trace sample marches a volume the host can hold
-    rays, rays_sample = cpu_trace_sample(orc, S, tape, cpu_dims, args.width, args.height, threads)
-    print(json.dumps({
-        "impl": "reference", "metric": "sdf_samples_per_sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_vox / val, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name("demo", dims, args.width, args.height),
-                   "step": "bounded sample of the grid fill on the host cores (C++ port of the reference loop, OpenMP over z)"},
-        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
-                         "reference_order_1_thread": one_thread, "reference_order_sample": one_thread_sample,
-                         "rays_per_sec": rays, "rays_sample": rays_sample + f", {cpu_dims[0]}^3 volume"},
-        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }))
+def parity_check_multi(torch, dist, S, sv, tape, dims, cam, W, H, rank, world, local, rgba_h, depth_h):
+    """After the timed region of an N > 1 run: (1) each halo slice equals the same slice computed locally,
+    (2) random texels of the own slab equal the oracle's point samples, (3) the linked frame equals the frame
+    of ONE handle holding the whole grid (rank 0, when the grid fits beside its slab).  Bit for bit."""
+    import numpy as np
+    from sdf_viewer_b200.sharded import _DevMem
+    v = sv.viewer
+    res = {}
+    ok = True
+    v.sync(); torch.cuda.synchronize(); dist.barrier()
+    n = dims[0] * dims[1] * 4
+    dev = torch.device("cuda", local)
+    halos = 0
+    for z in ([v.z_lo] if v.z_lo < v.z_begin else []) + ([v.z_hi - 1] if v.z_hi > v.z_end else []):
+        with S.SDFViewer.new_voxels(dims, BB, 1, device=local, z_range=(z, z + 1)) as one:
+            one.set_option("fill_halo", 0)
+            one.set_tape(tape); one.fill_all(); one.sync()
+            p0, p1 = one.device_ptrs()
+            off = (z - one.z_lo) * n
+            for p, mine in zip((p0, p1), sv._tex):
+                t = torch.as_tensor(_DevMem(p, (one.z_hi - one.z_lo) * n, "<f4"), device=dev)[off:off + n]
+                ok &= bool(torch.equal(t.view(torch.int32), mine[(z - v.z_lo) * n:(z - v.z_lo + 1) * n].view(torch.int32)))
+            halos += 1
+    res["halo_slices_checked"] = halos
+    try:
+        import orc
+        orc.build()
+        rng = np.random.default_rng(1234 + rank)
+        k = max(1000, 100000 // world)
+        idx = np.stack([rng.integers(0, dims[0], k), rng.integers(0, dims[1], k), rng.integers(v.z_begin, v.z_end, k)], 1).astype(np.uint32)
+        flat = ((idx[:, 2].astype(np.int64) - v.z_lo) * dims[1] + idx[:, 1]) * dims[0] + idx[:, 0]
+        ft = torch.from_numpy(flat).to(dev)
+        o0, o1 = orc.Viewer(BB, dims, 1, alloc=False).sample_voxels(orc.Sampler(tape=tape), idx, threads=1)
+        for mine, want in zip(sv._tex, (o0, o1)):
+            got = mine.view(-1, 4)[ft].cpu().numpy()
+            ok &= bool(np.array_equal(got.view(np.uint32), want.view(np.uint32)))
+        res["texels_vs_oracle"] = k * world
+    except Exception as e:
+        res["texels_vs_oracle"] = f"skipped: {e}"
+    frame = "skipped (the whole grid does not fit beside rank 0's slab)"
+    sv.trace_host(cam, W, H, rgba_h, depth_h)
+    if rank == 0 and dims[0] * dims[1] * dims[2] * BYTES_PER_SAMPLE < 100e9:
+        with S.SDFViewer.new_voxels(dims, BB, 2, device=local) as whole:
+            whole.set_tape(tape); whole.fill_all(); whole.commit()
+            want8, want_d = whole.trace_rgba8(cam, W, H)
+        same = bool(np.array_equal(want8, rgba_h) and np.array_equal(np.clip(want_d, 0, 1).view(np.uint32), depth_h.view(np.uint32)))
+        ok &= same
+        frame = "bit-exact vs one handle holding the whole grid" if same else "DIFFERS from the single-handle frame"
+    res["frame"] = frame
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["status"] = "ok" if flag.item() else "FAILED"
+    return res
 
 
 def main():
@@ -274,10 +480,12 @@ def main():
     ap.add_argument("--vpt", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C3 / C5 / close-up / 2160p legs that follow the timed region")
+    ap.add_argument("--no-linked", action="store_true",
+                    help="N > 1: the round-1 path (IPC halo pushes ordered by NCCL, sort-last trace + all-reduce(MIN)) instead of linked slabs")
     ap.add_argument("--exact-trace", action="store_true",
-                    help="N > 1: trace with the replicated distance volume + owner shading (bit-exact frame) instead of sort-last; "
-                         "the gather of the distance channel after every fill is inside the step")
-    ap.add_argument("--no-fused-halo", action="store_true", help="exchange halos with NCCL send/recv instead of in-kernel peer stores")
+                    help="with --no-linked: trace with the replicated distance volume + owner shading instead of sort-last")
+    ap.add_argument("--no-fused-halo", action="store_true", help="with --no-linked: exchange halos with NCCL send/recv")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -297,6 +505,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
+    args.gpus = n_gpus
     dims = grid_for(n_gpus, args.grid)
     W, H = args.width, args.height
     if args.workload == "wasm":
@@ -307,7 +516,9 @@ def main():
     cam = S.default_camera(W, H)
 
     from sdf_viewer_b200.sharded import ShardedViewer
-    sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, fused=not args.no_fused_halo)
+    want_c4 = world > 1 and not args.no_extras
+    sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, fused=not args.no_fused_halo,
+                       linked=not args.no_linked, max_width=max(W, 3840 if want_c4 else 0), max_height=max(H, 2160 if want_c4 else 0))
     v = sv.viewer
     if args.vpt:
         v.set_option("fill_voxels_per_thread", args.vpt)
@@ -320,13 +531,13 @@ def main():
 
     def step_device(ev=None):
         if ev: ev[0].record(stream)
-        sv.fill_all()          # fill own slab (+ NCCL halo exchange when world > 1)
+        sv.fill_all()          # fill own slab (+ halo exchange when world > 1)
         sv.commit()            # SDFViewer::commit: lod = 1 -> LINEAR filtering (scene/sdf/mod.rs:226-238)
         if ev: ev[1].record(stream)
-        if args.exact_trace and world > 1:
+        if args.exact_trace and world > 1 and not sv.linked:
             sv.trace_exact_device(cam, W, H)
         else:
-            sv.trace_device(cam, W, H)  # frame stays in HBM (+ MIN-composite over ranks when world > 1)
+            sv.trace_device(cam, W, H)  # frame stays in HBM (rank 0's when world > 1)
         if ev: ev[2].record(stream)
 
     def sync_all():
@@ -348,7 +559,6 @@ def main():
         step_device(evs[i])
     sync_all()
     elapsed = time.perf_counter() - t0
-    wall1 = time.time()
     launches = v.launch_count - l0
     fill_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     trace_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
@@ -357,10 +567,13 @@ def main():
         t = torch.tensor([step_ms, fill_ms, trace_ms, elapsed * 1e3 / args.steps], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         step_ms, fill_ms, trace_ms, wall_ms = t.tolist()
+        t = torch.tensor([float(launches)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        launches = int(t.item())
     else:
         wall_ms = elapsed * 1e3 / args.steps
 
-    # ---- end to end through the host-buffer ABI: tape H2D + fill + trace + frame D2H
+    # ---- end to end through the host-buffer ABI: tape H2D + fill + trace + frame D2H into pinned memory (rank 0)
     rgba_h = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory().numpy()  # the reference presents an RGBA8 framebuffer
     depth_h = torch.empty((H, W), dtype=torch.float32).pin_memory().numpy()
     e2e_steps = max(3, min(args.steps, 30))
@@ -371,7 +584,7 @@ def main():
         sv.commit()
         return sv.trace_host(cam, W, H, rgba_h, depth_h)
 
-    for _ in range(2):
+    for _ in range(3):
         step_e2e()
     sync_all()
     t0 = time.perf_counter()
@@ -385,59 +598,107 @@ def main():
         e2e_ms = t.item()
     clocks = clk.stop(wall0, time.time()) if clk else None
     hit_frac = float((depth_h < 1.0).mean())
-    trace_modes = trace_modes_live(torch, v, stream, cam, W, H) if n_gpus == 1 else None
+    program = v.get_info("last_fill_program")
+    peak, peak_src = peaks()
+
+    # ---- after the timed regions
+    parity = None
+    c4 = None
+    if world > 1:
+        if sv.linked:
+            parity = parity_check_multi(torch, dist, S, sv, tape, dims, cam, W, H, rank, world, local, rgba_h, depth_h)
+        if want_c4 and sv.linked:
+            try:
+                cam4 = S.default_camera(3840, 2160)
+                for _ in range(3):
+                    sv.trace_device(cam4, 3840, 2160)
+                sync_all()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(20):
+                    sv.trace_device(cam4, 3840, 2160)
+                e1.record(stream)
+                sync_all()
+                t = torch.tensor([e0.elapsed_time(e1) / 20], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                r4 = torch.empty((2160, 3840, 4), dtype=torch.uint8).pin_memory().numpy()
+                d4 = torch.empty((2160, 3840), dtype=torch.float32).pin_memory().numpy()
+                sv.trace_host(cam4, 3840, 2160, r4, d4)
+                sync_all()
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    sv.trace_host(cam4, 3840, 2160, r4, d4)
+                sync_all()
+                c4 = {"config": f"BASELINE.json configs[3]: {dims[0]}x{dims[1]}x{dims[2]} Z-sharded over {world} GPUs, 3840x2160 raymarch",
+                      "trace_ms": t.item(), "rays_per_sec": 3840 * 2160 / (t.item() * 1e-3),
+                      "e2e_frame_ms": (time.perf_counter() - t0) * 1e3 / 10, "e2e_what": "trace + RGBA8+depth D2H (66 MB) on rank 0",
+                      "hit_fraction": float((d4 < 1.0).mean())}
+            except Exception as e:
+                c4 = {"error": str(e)}
+    trace_modes = extras = None
+    if n_gpus == 1 and not args.no_extras:
+        trace_modes = trace_modes_live(torch, v, stream, cam, W, H)
+        if args.grid == 512:
+            extras = extras_single_gpu(torch, S, v, stream, W, H, args.grid, peak)
 
     if rank != 0:
+        sv.close()
         if dist: dist.destroy_process_group()
         return
-    peak, peak_src = peaks()
     achieved = own_voxels * BYTES_PER_SAMPLE / (fill_ms * 1e-3) / 1e9
+    headline_cfg = n_gpus == 1 and args.grid == 512 and args.workload == "demo"
+    if n_gpus == 1:
+        sharding = "single GPU"
+    elif sv.linked:
+        sharding = (f"z-slabs x{n_gpus}, linked through the C ABI: one fill launch per rank (boundary tiles first, DMA halo push behind a flag), "
+                    f"exact ray-hand-off trace ({n_gpus} rounds), pixels stored into rank 0's frame over NVLink; flags: "
+                    + ("stream memory operations" if v.get_info("link_memops") else "spin-wait kernels"))
+    else:
+        sharding = (f"z-slabs x{n_gpus}, round-1 path: " + ("IPC halo pushes ordered by a 4-byte NCCL all-reduce" if sv.fused else "NCCL send/recv halo exchange")
+                    + ", " + ("exact trace on a replicated distance volume" if args.exact_trace else "sort-last trace + all-reduce(MIN)"))
     out = {
         # value: voxels of the whole job / the time of the whole step (fill + commit + trace), the same
         # K-step interval ms_per_step reports; the fill kernel alone is fill_samples_per_sec / roofline
         "metric": "sdf_samples_per_sec", "value": total_voxels / (step_ms * 1e-3), "unit": "samples/s",
         "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, dims, W, H),
-                   "sharding": (f"z-slabs x{n_gpus}, halo exchange: " + ("fused: boundary slices pushed by DMA over NVLink (CUDA IPC) while the interior fills"
-                                if sv.fused else "NCCL send/recv after the fill")) if n_gpus > 1 else "single GPU",
+        "config": common_config(args, dims),
+        "detail": {"sharding": sharding,
                    "l2": "volume (32 B/voxel) exceeds the 126 MB L2, no flush needed" if own_voxels * 32 > 2.5e8 else "volume fits L2",
-                   "step": "fill_all + commit + trace (lod 1, LINEAR filter, fp32 trilinear)" +
-                           (", exact sharded trace (distance channel gathered after the fill, owner shading)"
-                            if args.exact_trace and n_gpus > 1 else "")},
+                   "step": "fill_all + commit + trace (lod 1, LINEAR filter, fp32 trilinear)"},
         "fill_ms": fill_ms, "trace_ms": trace_ms, "fill_samples_per_sec": total_voxels / (fill_ms * 1e-3),
         "rays_per_sec": W * H / (trace_ms * 1e-3), "hit_fraction": hit_frac,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic() if (n_gpus == 1 and args.grid == 512 and args.workload == "demo") else None,
-                     "traffic_source": "profiles/r01_fill_ncu_summary.txt (ncu --set full, same kernel and grid)", "peak_source": peak_src, "kernel": "fill_kernel",
+                     "traffic": ncu_traffic() if headline_cfg else None,
+                     "traffic_source": f"{FILL_CAPTURE} (ncu --set full, same kernel and grid; capture committed at {capture_commit(FILL_CAPTURE)})"
+                     if headline_cfg else None,
+                     "peak_source": peak_src, "kernel": PROGRAM_KERNEL.get(program, str(program)),
                      "algorithmic_bytes_per_launch": own_voxels * BYTES_PER_SAMPLE},
         "e2e": {"value": total_voxels / (e2e_ms * 1e-3), "unit": "samples/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": len(tape) + 256, "d2h_bytes_per_step": W * H * 8,
-                "what": "set_tape (H2D) + fill + commit + trace + frame RGBA8+depth D2H into pinned host memory"},
+                "h2d_bytes_per_step": (len(tape) + 256) * n_gpus, "d2h_bytes_per_step": W * H * 8,
+                "what": "set_tape (H2D, every rank) + fill + commit + trace + frame RGBA8+depth D2H into pinned host memory (rank 0)"},
         "gpu_launches": int(launches), "clocks": clocks, "host_ms_per_step": wall_ms,
         "trace_modes": trace_modes,
-        "trace_profile": trace_profile() if (n_gpus == 1 and args.grid == 512 and args.workload == "demo") else None,
+        "trace_profile": trace_profile() if headline_cfg else None,
     }
-    if n_gpus > 1:
-        out["e2e"]["d2h_bytes_per_step"] = W * H * 8
-        out["e2e"]["what"] = ("set_tape (H2D) + fill + NCCL halo exchange + slab trace + all-reduce(MIN) composite + "
-                              "frame RGBA8+depth D2H").replace("NCCL halo exchange", "fused halo exchange" if sv.fused else "NCCL halo exchange")
+    if parity is not None:
+        out["parity_check"] = parity["status"]
+        out["parity_detail"] = parity
+    if c4 is not None:
+        out["c4_trace_2160p"] = c4
+    if extras:
+        out.update(extras)
     if not args.no_cpu_baseline and n_gpus == 1:
         import orc
         orc.build()
-        threads = orc.lib().orc_max_threads()
-        val, sample = cpu_fill_sample(orc, tape, dims, threads, target_s=8.0)
-        one_thread, one_thread_sample = cpu_reference_order_rate(orc, tape)
-        cpu_dims = tuple(min(d, 256) for d in dims)
-        rays, rays_sample = cpu_trace_sample(orc, S, tape, cpu_dims, W, H, threads)
-        out["cpu_baseline"] = {"value": val, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample,
-                               "reference_order_1_thread": one_thread, "reference_order_sample": one_thread_sample,
-                               "rays_per_sec": rays, "rays_sample": rays_sample + f", {cpu_dims[0]}^3 volume"}
+        threads = host_threads()
+        out["cpu_baseline"] = cpu_baseline_block(orc, args.workload, tape, dims, W, H, threads, target_s=8.0)
         try:
             out["host_sampled_path"] = host_sampled_path(orc, S, threads)
         except Exception as e:  # an extra, never a reason to lose the bench line
             out["host_sampled_path"] = {"error": str(e)}
     print(json.dumps(out))
+    sv.close()
     if dist: dist.destroy_process_group()
 
 

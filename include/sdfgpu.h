@@ -153,6 +153,35 @@ int sdfgpu_group_trace_rgba8(sdfgpu_group* g, const struct sdfgpu_camera* cam, u
 int sdfgpu_group_trace(sdfgpu_group* g, const struct sdfgpu_camera* cam, uint32_t width, uint32_t height,
                        uint8_t* rgba8, float* depth, float* gbuf); /* gbuf needs SDFGPU_LINK_GBUF at creation */
 
+/* ------------------------------------------------------- sampling at arbitrary positions, mesh export
+ *
+ * sdfgpu_sample_points: SDFSurface::sample(p, false) (src/sdf/mod.rs:43) of the current tape for n positions
+ * (xyz: n x 3 floats) -> out: n x 7 floats (distance, r, g, b, metallic, roughness, occlusion: the SDFSample of
+ * src/sdf/mod.rs:104-118, raw -- none of the volume's store rules applied).
+ *
+ * sdfgpu_mesh: the `mesh` subcommand's pipeline (src/sdf/meshers/mod.rs:66-87) on the GPU, from the volume that is
+ * ALREADY resident instead of re-sampling the SDF: marching cubes over the cells of the lattice (the sign of
+ * tex0.r - 0.1, material.frag:56-60; an SDFViewer of N + 1 voxels per axis holds exactly the (N + 1)^3 samples the
+ * reference's MarchingCubes::new(N) takes, meshers/isosurface.rs:26-29,94-98), one vertex per sign-changing lattice
+ * edge (shared by the triangles around it), then Mesh::postproc (meshers/mesh.rs:22-33) through the tape: colour,
+ * metallic, roughness, occlusion = sample(vertex, false); normal = SDFSurface::normal(vertex, None)
+ * (src/sdf/defaults.rs:49-56).  Vertex records are 12 floats -- position, normal, colour, metallic, roughness,
+ * occlusion (mesh.rs Vertex) -- in the SDF's coordinates; triangles are counter-clockwise seen from outside.  The
+ * volume must be fully loaded and the handle must hold the whole grid.  The `isosurface` crate is not vendored with
+ * the reference: vertex order and the triangulation of ambiguous cells are this library's own (watertight by
+ * construction, see mc_table.py).
+ *
+ * sdfgpu_ply_serialize / sdfgpu_mesh_write_ply: Mesh::serialize_ply (meshers/mesh.rs:38-129): ASCII PLY with the
+ * reference's element / property list, floats in Rust's shortest round-trip `{}` form, colours (c * 255.9999) as u8;
+ * `comment` is the header's comment line (the reference writes "Created with <version>"). */
+int sdfgpu_sample_points(sdfgpu_ctx* ctx, const float* xyz, uint64_t n, float* out);
+int sdfgpu_mesh(sdfgpu_ctx* ctx, uint64_t* n_vertices, uint64_t* n_triangles);
+int sdfgpu_mesh_download(sdfgpu_ctx* ctx, float* vertices, uint32_t* indices);
+int sdfgpu_mesh_device_ptrs(sdfgpu_ctx* ctx, const float** vertices_dev, const uint32_t** indices_dev);
+int sdfgpu_mesh_write_ply(sdfgpu_ctx* ctx, const char* path, const char* comment, uint64_t* bytes_written);
+int sdfgpu_ply_serialize(const float* vertices, uint64_t n_vertices, const uint32_t* indices, uint64_t n_triangles,
+                         const char* comment, const char* path, uint64_t* bytes_written);
+
 /* Dropping the SDFViewer (scene/mod.rs:154-155 rebuilds it on every set_sdf). */
 void sdfgpu_destroy(sdfgpu_ctx* ctx);
 

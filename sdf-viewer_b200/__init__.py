@@ -10,5 +10,5 @@ from .loading import LoadingManager, NativeLoadingManager  # noqa: F401
 from .wasm import WasmSDF, WasmLoweringError  # noqa: F401
 from .viewer import (  # noqa: F401
     SDFViewer, SDFViewerGroup, Camera, Rays, SdfGpuError, GBUF_FLOATS, dims_from_bb, default_camera, look_at_camera, camera_rays,
-    jit_check, tape_validate,
+    jit_check, tape_validate, ply_serialize,
 )

@@ -112,6 +112,12 @@ SIGNATURES = {
     "sdfgpu_group_download": (C.c_int, [_vp, _vp, _vp]),
     "sdfgpu_group_trace_rgba8": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, _vp, _vp]),
     "sdfgpu_group_trace": (C.c_int, [_vp, C.POINTER(Camera), _u32, _u32, _vp, _vp, _vp]),
+    "sdfgpu_sample_points": (C.c_int, [_vp, _vp, _u64, _vp]),
+    "sdfgpu_mesh": (C.c_int, [_vp, _u64p, _u64p]),
+    "sdfgpu_mesh_download": (C.c_int, [_vp, _vp, _vp]),
+    "sdfgpu_mesh_device_ptrs": (C.c_int, [_vp, _vpp, _vpp]),
+    "sdfgpu_mesh_write_ply": (C.c_int, [_vp, C.c_char_p, C.c_char_p, _u64p]),
+    "sdfgpu_ply_serialize": (C.c_int, [_vp, _u64, _vp, _u64, C.c_char_p, C.c_char_p, _u64p]),
     "sdfgpu_destroy": (None, [_vp]),
     "sdfgpu_last_error": (C.c_char_p, [_vp]),
     "sdfgpu_dims": (C.c_int, [_vp, _u32p]),

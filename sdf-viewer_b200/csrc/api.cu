@@ -87,39 +87,11 @@ int default_vpt(const sdfgpu_ctx* ctx) {
     return ctx->structure_is_demo ? 8 : 4;
 }
 
-// one fill launch over lattice {r0 + i*step} restricted to the index box [lo, hi) per axis
-int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_t hi[3], uint32_t conditional,
-             unsigned long long* touched, uint32_t known_step = 0) {
-    if (!ctx->has_tape) return fail(ctx, SDFGPU_ERR_STATE, "no tape set (call sdfgpu_set_tape first)");
-    FillParams p;
-    memset(&p, 0, sizeof p);
-    uint32_t r0[3], n[3];
-    for (int a = 0; a < 3; ++a) {
-        if (hi[a] <= lo[a]) return SDFGPU_OK;
-        r0[a] = ((lo[a] + step - 1) / step) * step;
-        if (r0[a] >= hi[a]) return SDFGPU_OK;
-        n[a] = (hi[a] - r0[a] + step - 1) / step;
-    }
-    int V = default_vpt(ctx);
-    if (!ctx->opt_vpt)  // thin launches (a boundary slice, a dirty box): do not pad the z extent of a tile with idle voxels
-        while (V > 1 && (uint32_t)V > n[2]) V >>= 1;
-    p.tex0 = ctx->tex0; p.tex1 = ctx->tex1;
-    p.tape_img = ctx->img_dev; p.tape_img_bytes = (uint32_t)ctx->img_host.size();
-    p.W = ctx->dims[0]; p.H = ctx->dims[1]; p.D = ctx->dims[2];
-    p.z_lo = ctx->z_lo;
-    p.rx0 = r0[0]; p.ry0 = r0[1]; p.rz0 = r0[2];
-    p.nx = n[0]; p.ny = n[1]; p.nz = n[2];
-    p.step = step;
-    p.tiles_x = (n[0] + FILL_TILE_X - 1) / FILL_TILE_X;
-    p.tiles_y = (n[1] + FILL_TILE_Y - 1) / FILL_TILE_Y;
-    p.tiles_z = (n[2] + V - 1) / V;
-    p.conditional = conditional;
-    p.known_step = known_step;
-    p.has_box = ctx->has_changed_box ? 1u : 0u;
-    if (ctx->has_changed_box) memcpy(p.box, ctx->changed_box, sizeof p.box);
-    p.air_dist = air_dist_value();
-    p.touched = touched;
-    if (ctx->fill_boundary_first) (void)link_fill_all_fused(ctx, &p);
+}  // namespace
+
+// picks the program for a prepared launch (a kernel specialised for this tape structure (NVRTC), the built-in demo
+// program, or the interpreter) and launches it
+int sdfgpu::dispatch_fill(sdfgpu_ctx* ctx, FillParams& p, int V) {
     const uint32_t n_cull = (ctx->hdr.flags & TAPE_FLAG_CULL) ? ctx->hdr.cull_count : 0u;
     const size_t smem = fill_smem_bytes(p.tape_img_bytes, n_cull, ctx->hdr.max_stack, V, &p.stack_floats);
     if (smem > 227u * 1024u)
@@ -163,8 +135,48 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
         CK(ctx, launch_fill(p, V, program, (int)grid, smem, ctx->stream));
     }
     ctx->last_program = program; ctx->last_ctas = per_sm; ctx->last_vpt = V;
-    ctx->dist_valid = false; ctx->dist_full_own_valid = false;
     ctx->launches++;
+    return SDFGPU_OK;
+}
+
+namespace {
+
+// one fill launch over lattice {r0 + i*step} restricted to the index box [lo, hi) per axis
+int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_t hi[3], uint32_t conditional,
+             unsigned long long* touched, uint32_t known_step = 0) {
+    if (!ctx->has_tape) return fail(ctx, SDFGPU_ERR_STATE, "no tape set (call sdfgpu_set_tape first)");
+    FillParams p;
+    memset(&p, 0, sizeof p);
+    uint32_t r0[3], n[3];
+    for (int a = 0; a < 3; ++a) {
+        if (hi[a] <= lo[a]) return SDFGPU_OK;
+        r0[a] = ((lo[a] + step - 1) / step) * step;
+        if (r0[a] >= hi[a]) return SDFGPU_OK;
+        n[a] = (hi[a] - r0[a] + step - 1) / step;
+    }
+    int V = default_vpt(ctx);
+    if (!ctx->opt_vpt)  // thin launches (a boundary slice, a dirty box): do not pad the z extent of a tile with idle voxels
+        while (V > 1 && (uint32_t)V > n[2]) V >>= 1;
+    p.tex0 = ctx->tex0; p.tex1 = ctx->tex1;
+    p.tape_img = ctx->img_dev; p.tape_img_bytes = (uint32_t)ctx->img_host.size();
+    p.W = ctx->dims[0]; p.H = ctx->dims[1]; p.D = ctx->dims[2];
+    p.z_lo = ctx->z_lo;
+    p.rx0 = r0[0]; p.ry0 = r0[1]; p.rz0 = r0[2];
+    p.nx = n[0]; p.ny = n[1]; p.nz = n[2];
+    p.step = step;
+    p.tiles_x = (n[0] + FILL_TILE_X - 1) / FILL_TILE_X;
+    p.tiles_y = (n[1] + FILL_TILE_Y - 1) / FILL_TILE_Y;
+    p.tiles_z = (n[2] + V - 1) / V;
+    p.conditional = conditional;
+    p.known_step = known_step;
+    p.has_box = ctx->has_changed_box ? 1u : 0u;
+    if (ctx->has_changed_box) memcpy(p.box, ctx->changed_box, sizeof p.box);
+    p.air_dist = air_dist_value();
+    p.touched = touched;
+    if (ctx->fill_boundary_first) (void)link_fill_all_fused(ctx, &p);
+    const int rc = dispatch_fill(ctx, p, V);
+    if (rc != SDFGPU_OK) return rc;
+    ctx->dist_valid = false; ctx->dist_full_own_valid = false;
     return SDFGPU_OK;
 }
 
@@ -386,6 +398,7 @@ SDFGPU_API void sdfgpu_destroy(sdfgpu_ctx* ctx) {
     set_device(ctx);
     if (ctx->stream) (void)cudaStreamSynchronize(ctx->stream);
     link_free(ctx);
+    mesh_free(ctx);
     (void)sdfgpu_ipc_detach(ctx);
     (void)cudaFree(ctx->trace_counters);
     (void)cudaFree(ctx->tex0); (void)cudaFree(ctx->tex1); (void)cudaFree(ctx->img_dev);

@@ -346,6 +346,52 @@ __device__ __forceinline__ void exec_op(const uint4 I, Machine<V>& M, const Env&
     SDFGPU_STEP(DOP_PRIM + 0 * 6 + SDFT_SHAPE_SPHERE * 3 + SDFT_MAT_NORMAL, 2)                               \
     SDFGPU_STEP(DOP_POP_DEMO_DIFF, 3)
 
+// The lowered tape for the V positions in M.pos*: the specialised straight-line body, the built-in demo body, or
+// the fetch / dispatch loop.
+template <int V, int PROG>
+__device__ __forceinline__ void run_tape(Machine<V>& M, const Env& E, const uint4* s_instr) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        M.A[v].d = M.A[v].r = M.A[v].g = M.A[v].b = M.A[v].m = M.A[v].ro = M.A[v].o = 0.0f;
+        M.T[v] = M.A[v];
+        M.qx[v] = M.posx; M.qy[v] = M.posy; M.qz[v] = M.posz[v];
+    }
+    if constexpr (PROG == PROG_JIT) {
+        SDFGPU_JIT_BODY
+    } else if constexpr (PROG == PROG_DEMO) {
+        SDFGPU_DEMO_BODY
+    } else {
+        for (uint32_t pc = 0;; ++pc) {
+            const uint4 I = s_instr[pc];
+            if (I.x == DOP_END) break;
+#define C(n) case n: exec_op<V, n>(I, M, E); break;
+            switch (I.x) {
+                C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16) C(17) C(18)
+                C(19) C(20) C(21) C(22) C(23) C(24) C(25) C(26) C(27) C(28) C(29) C(30) C(31) C(32) C(33) C(34)
+                C(35) C(36) C(37) C(38)
+                default: break;
+            }
+#undef C
+        }
+    }
+}
+
+// Point mode (FillParams::points): one arbitrary position per thread, the raw sample out.
+template <int PROG>
+__device__ __forceinline__ void point_body(const FillParams& P, const Env& E, const uint4* s_instr, uint32_t tile) {
+    const uint32_t i = tile * FILL_THREADS + threadIdx.x;
+    const bool ok = i < P.n_points;
+    const uint32_t j = ok ? i : P.n_points - 1u;  // idle lanes of the last tile repeat the last point
+    Machine<1> M;
+    M.posx = P.points[3u * j]; M.posy = P.points[3u * j + 1u]; M.posz[0] = P.points[3u * j + 2u];
+    run_tape<1, PROG>(M, E, s_instr);
+    if (ok) {
+        float* o = P.points_out + 7u * (size_t)i;
+        const Smp& a = M.A[0];
+        o[0] = a.d; o[1] = a.r; o[2] = a.g; o[3] = a.b; o[4] = a.m; o[5] = a.ro; o[6] = a.o;
+    }
+}
+
 // One tile for one thread: V voxels at (lx, ly, lz0 .. lz0 + V - 1) of the lattice.  FULL: the tile
 // lies entirely inside the lattice and the pass is unconditional -- no per-voxel predicates at all.
 template <int V, int PROG, bool FULL>
@@ -389,31 +435,7 @@ __device__ __forceinline__ void tile_body(const FillParams& P, const Env& E, con
         if (!__any_sync(0xffffffffu, any)) return;
     }
 
-    // ---- run the lowered tape
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        M.A[v].d = M.A[v].r = M.A[v].g = M.A[v].b = M.A[v].m = M.A[v].ro = M.A[v].o = 0.0f;
-        M.T[v] = M.A[v];
-        M.qx[v] = M.posx; M.qy[v] = M.posy; M.qz[v] = M.posz[v];
-    }
-    if constexpr (PROG == PROG_JIT) {
-        SDFGPU_JIT_BODY
-    } else if constexpr (PROG == PROG_DEMO) {
-        SDFGPU_DEMO_BODY
-    } else {
-        for (uint32_t pc = 0;; ++pc) {
-            const uint4 I = s_instr[pc];
-            if (I.x == DOP_END) break;
-#define C(n) case n: exec_op<V, n>(I, M, E); break;
-            switch (I.x) {
-                C(1) C(2) C(3) C(4) C(5) C(6) C(7) C(8) C(9) C(10) C(11) C(12) C(13) C(14) C(15) C(16) C(17) C(18)
-                C(19) C(20) C(21) C(22) C(23) C(24) C(25) C(26) C(27) C(28) C(29) C(30) C(31) C(32) C(33) C(34)
-                C(35) C(36) C(37) C(38)
-                default: break;
-            }
-#undef C
-        }
-    }
+    run_tape<V, PROG>(M, E, s_instr);
 
     // ---- the stores of scene/sdf/mod.rs:196-208
     float4* const out0 = P.tex0 + flat0;
@@ -473,7 +495,14 @@ __device__ __forceinline__ void fill_body(const FillParams& P) {
     E.stack = reinterpret_cast<float*>(smem + img_bytes + 16 + 64 + ((n_cull * 4u + 15u) & ~15u)) + threadIdx.x;
     E.list = s_list;
     E.list_n = 0;
-    E.culled = n_cull != 0;
+    E.culled = n_cull != 0 && P.points == nullptr;
+
+    if constexpr (V == 1) {
+        if (P.points) {  // kernel-uniform
+            for (uint32_t tile = blockIdx.x; tile < P.tiles_z; tile += gridDim.x) point_body<PROG>(P, E, s_instr, tile);
+            return;
+        }
+    }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_tiles = P.tiles_x * P.tiles_y * P.tiles_z;

@@ -26,6 +26,7 @@
 //   consumed          (from the presenter) frames 0 .. value - 1 have been unpacked: their key frame may be reused
 #include <unistd.h>
 
+#include <cstdlib>
 #include <new>
 
 #include "sdfgpu_ctx.h"
@@ -121,6 +122,22 @@ int signal_flags(sdfgpu_ctx* ctx, cudaStream_t s, uint32_t* const* flags, const 
 }
 
 ArenaHeader* peer_hdr(sdfgpu_ctx* ctx, int rank) { return hdr_of(ctx->link.peer_arena[rank]); }
+
+bool link_timing() {
+    static const bool on = [] { const char* e = getenv("SDFGPU_LINK_TIMING"); return e && *e && *e != '0'; }();
+    return on;
+}
+
+void timing_mark(sdfgpu_ctx* ctx) {
+    if (!link_timing()) return;
+    LinkState& L = ctx->link;
+    if (L.timing_used == L.timing_events.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        L.timing_events.push_back(e);
+    }
+    (void)cudaEventRecord(L.timing_events[L.timing_used++], ctx->stream);
+}
 
 // tell both neighbours that fill number `epoch` of this rank is in their halo slices
 int signal_halo_in(sdfgpu_ctx* ctx, cudaStream_t s, uint32_t epoch) {
@@ -229,6 +246,8 @@ int sdfgpu::link_trace_begin(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t
     L.cur_w = w; L.cur_h = h; L.cur_round = 0;
     L.cur_gbuf = want_gbuf;
     L.in_frame = true;
+    L.timing_used = 0;
+    timing_mark(ctx);
     return SDFGPU_OK;
 }
 
@@ -244,6 +263,7 @@ int sdfgpu::link_trace_round(sdfgpu_ctx* ctx) {
     int rc;
     for (int side = 0; side < 2; ++side)  // the neighbour has finished round g - 1
         if (L.nb[side] >= 0 && (rc = wait_flag(ctx, ctx->stream, &hd->round_done[side], g)) != SDFGPU_OK) return rc;
+    timing_mark(ctx);
     const ArenaLayout lay = arena_layout(L.max_pixels, L.want_gbuf);
     LinkParams lp;
     memset(&lp, 0, sizeof lp);
@@ -283,6 +303,7 @@ int sdfgpu::link_trace_round(sdfgpu_ctx* ctx) {
     if (per_sm < 1) return fail(ctx, SDFGPU_ERR_CUDA, "the trace kernel does not fit on an SM");
     CK(ctx, launch_trace_rounds(ctx->link_tp, lp, ctx->sm_count * per_sm, ctx->stream));
     ctx->launches++;
+    timing_mark(ctx);
     return SDFGPU_OK;
 }
 
@@ -298,6 +319,7 @@ int sdfgpu::link_trace_end(sdfgpu_ctx* ctx, uint8_t* rgba8, float* depth, float*
         ArenaHeader* hd = hdr_of(L.arena);
         for (uint32_t r = 1; r < L.world; ++r)
             if ((rc = wait_flag(ctx, ctx->stream, &hd->frame_done[r], t + 1u)) != SDFGPU_OK) return rc;
+        timing_mark(ctx);
         const ArenaLayout lay = arena_layout(L.max_pixels, L.want_gbuf);
         const size_t n = (size_t)L.cur_w * L.cur_h;
         CK(ctx, launch_keys_unpack(reinterpret_cast<const unsigned long long*>(L.arena + lay.keys[t & 1u]), (uint32_t)n,
@@ -313,8 +335,20 @@ int sdfgpu::link_trace_end(sdfgpu_ctx* ctx, uint8_t* rgba8, float* depth, float*
         for (uint32_t r = 1; r < L.world; ++r) { flags[m] = &peer_hdr(ctx, (int)r)->consumed; values[m++] = t + 1u; }
         if ((rc = signal_flags(ctx, ctx->stream, flags, values, m)) != SDFGPU_OK) return rc;
     }
+    timing_mark(ctx);
     if (sync) {
         CK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (link_timing() && L.timing_used >= 2) {
+            std::string line = "[sdfgpu link timing] rank " + std::to_string(L.rank) + " frame " + std::to_string(t) + " us:";
+            for (size_t i = 1; i < L.timing_used; ++i) {
+                float ms = 0.0f;
+                (void)cudaEventElapsedTime(&ms, L.timing_events[i - 1], L.timing_events[i]);
+                char b[32];
+                snprintf(b, sizeof b, " %.1f", ms * 1e3f);
+                line += b;
+            }
+            fprintf(stderr, "%s  (per round: wait, kernel; presenter then: wait frame_done, unpack+copies)\n", line.c_str());
+        }
         if (!L.memops) {
             uint32_t to = 0;
             CK(ctx, cudaMemcpy(&to, &hdr_of(L.arena)->timed_out, 4, cudaMemcpyDeviceToHost));
@@ -345,6 +379,7 @@ void sdfgpu::link_free(sdfgpu_ctx* ctx) {
         }
     }
     (void)cudaFree(L.arena);
+    for (cudaEvent_t e : L.timing_events) (void)cudaEventDestroy(e);
     (void)cudaGetLastError();
     L = LinkState();
 }

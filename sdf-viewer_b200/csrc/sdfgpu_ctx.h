@@ -114,6 +114,23 @@ struct LinkState {
     uint32_t cur_w = 0, cur_h = 0, cur_round = 0;
     bool cur_gbuf = false;
     bool in_frame = false;
+    // SDFGPU_LINK_TIMING=1 (development): events around the waits and the kernel of every round, printed to stderr
+    // by a synchronising sdfgpu_trace_linked
+    std::vector<cudaEvent_t> timing_events;
+    size_t timing_used = 0;
+};
+
+// The mesher's device buffers (mesh.cu); `points` / `samples` also stage sdfgpu_sample_points.
+struct MeshState {
+    uint32_t* vert_base = nullptr;      size_t vert_base_cap = 0;      // per lattice point
+    uint32_t* block_counts = nullptr;   size_t block_counts_cap = 0;
+    uint32_t* block_offsets = nullptr;  size_t block_offsets_cap = 0;
+    float* vertices = nullptr;          size_t vertices_cap = 0;       // 12 floats per vertex (mesh.rs Vertex)
+    uint32_t* indices = nullptr;        size_t indices_cap = 0;        // 3 per triangle
+    float* points = nullptr;            size_t points_cap = 0;
+    float* samples = nullptr;           size_t samples_cap = 0;
+    uint64_t n_vertices = 0, n_triangles = 0;
+    bool valid = false;
 };
 
 }  // namespace sdfgpu
@@ -210,6 +227,7 @@ struct sdfgpu_ctx {
     uint64_t launches = 0;
     std::string err;
     sdfgpu::LinkState link;
+    sdfgpu::MeshState mesh;
     sdfgpu::TraceParams link_tp;  // trace parameters of the linked frame in flight
     bool fill_boundary_first = false;  // the next run_fill is the whole-slab launch of a linked fill_all
     int opt_link_wait = 0;             // 0: stream memory operations when the driver has them, 1: spin-wait kernels
@@ -237,6 +255,11 @@ bool has_peers(const sdfgpu_ctx* ctx);
 int push_halos(sdfgpu_ctx* ctx, cudaStream_t s, bool lo = true, bool hi = true);
 int ensure_frame(sdfgpu_ctx* ctx, uint32_t w, uint32_t h, bool want_gbuf, bool want_keys);
 int fill_trace_params(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t w, uint32_t h, bool slab_clip, TraceParams* tp);
+int dispatch_fill(sdfgpu_ctx* ctx, FillParams& p, int V);  // program choice + launch of a prepared fill
+
+// mesh.cu
+int sample_points_device(sdfgpu_ctx* ctx, const float* points_dev, uint32_t n, float* out_dev);  // the tape at n positions
+void mesh_free(sdfgpu_ctx* ctx);
 
 // link.cu
 int link_after_fill(sdfgpu_ctx* ctx, bool touched_lo, bool touched_hi);  // push the boundary slices that changed, signal the neighbours

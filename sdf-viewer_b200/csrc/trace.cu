@@ -626,15 +626,18 @@ __global__ void __launch_bounds__(256) trace_rounds_kernel(const __grid_constant
     const Vol v0{P.tex0, (int)P.W, (int)P.H, (int)P.D, (int)P.z_lo, (int)P.z_hi};
     const Vol v1{P.tex1, (int)P.W, (int)P.H, (int)P.D, (int)P.z_lo, (int)P.z_hi};
 
-    // ---- the work of this round
+    // ---- the work of this round.  First round: one unit per 8 x 4 tile inside the screen rectangle of the box (all
+    // the marching is there), then units of OUTSIDE_RUN tiles outside it (stores only: one queue access per 512 pixels)
+    constexpr uint32_t OUTSIDE_RUN = 16u;
     const uint32_t tiles_y4 = (P.height + 3u) / 4u;                              // rows of 8 x 4 tiles
-    const uint32_t rw = P.rect[2] - P.rect[0], ry0 = P.rect[1] * 2u;
-    const uint32_t rh4 = min(P.rect[3] * 2u, tiles_y4) - min(ry0, tiles_y4);
+    const uint32_t rw = P.rect[2] - P.rect[0], ry0 = min(P.rect[1] * 2u, tiles_y4);
+    const uint32_t rh4 = min(P.rect[3] * 2u, tiles_y4) - ry0;
     const uint32_t n_heavy = rw * rh4;
+    const uint32_t n_outside = P.tiles_x * tiles_y4 - n_heavy;
     uint32_t n_units, units0 = 0, cnt0 = 0, cnt1 = 0;
     if (L.first) {
         // tiles outside the rectangle hold no ray that enters the box: only the presenter has to write them
-        n_units = (!L.linked || L.is_presenter) ? P.tiles_x * tiles_y4 : n_heavy;
+        n_units = n_heavy + ((!L.linked || L.is_presenter) ? (n_outside + OUTSIDE_RUN - 1u) / OUTSIDE_RUN : 0u);
     } else {
         if (L.in_count[0]) cnt0 = *reinterpret_cast<const volatile uint32_t*>(L.in_count[0]);
         if (L.in_count[1]) cnt1 = *reinterpret_cast<const volatile uint32_t*>(L.in_count[1]);
@@ -648,23 +651,13 @@ __global__ void __launch_bounds__(256) trace_rounds_kernel(const __grid_constant
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= n_units) break;
 
-        // ---- this lane's ray
-        Ray r;
-        r.hx = r.hy = r.hz = r.t = 0.0f; r.it = 0;
-        uint32_t px = 0;
-        float rdx = 0.f, rdy = 0.f, rdz = 0.f;
-        int status = RS_NONE;   // RS_NONE: nothing (left) to do for this lane
-        bool marching = false;
-        float code = -3.0f;
-        if (L.first) {
-            uint32_t tx, ty;
-            bool outside = false;
-            if (unit < n_heavy) {
-                tx = P.rect[0] + unit % rw; ty = ry0 + unit / rw;
-            } else {
-                outside = true;
-                uint32_t b = unit - n_heavy;
-                const uint32_t n_top = ry0 * P.tiles_x, side = P.tiles_x - rw;
+        if (L.first && unit >= n_heavy) {  // a run of tiles no ray of which enters the box: miss code -3, no arithmetic
+            const uint32_t b0 = (unit - n_heavy) * OUTSIDE_RUN, b1 = min(b0 + OUTSIDE_RUN, n_outside);
+            const uint32_t n_top = ry0 * P.tiles_x, side = P.tiles_x - rw;
+            Ray none;
+            none.hx = none.hy = none.hz = none.t = 0.0f; none.it = 0;
+            for (uint32_t bb = b0; bb < b1; ++bb) {
+                uint32_t b = bb, tx, ty;
                 if (b < n_top) {
                     tx = b % P.tiles_x; ty = b / P.tiles_x;
                 } else if (b - n_top < rh4 * side) {
@@ -675,12 +668,27 @@ __global__ void __launch_bounds__(256) trace_rounds_kernel(const __grid_constant
                     b -= n_top + rh4 * side;
                     tx = b % P.tiles_x; ty = ry0 + rh4 + b / P.tiles_x;
                 }
+                const uint32_t i = tx * 8u + (lane & 7u), j = ty * 4u + (lane >> 3);
+                if (i < P.width && j < P.height) finish_pixel<SNAP, LINEAR>(P, L, v0, v1, j * P.width + i, false, -3.0f, none);
             }
+            continue;
+        }
+
+        // ---- this lane's ray
+        Ray r;
+        r.hx = r.hy = r.hz = r.t = 0.0f; r.it = 0;
+        uint32_t px = 0;
+        float rdx = 0.f, rdy = 0.f, rdz = 0.f;
+        int status = RS_NONE;   // RS_NONE: nothing (left) to do for this lane
+        bool marching = false;
+        float code = -3.0f;
+        if (L.first) {
+            const uint32_t tx = P.rect[0] + unit % rw, ty = ry0 + unit / rw;
             const uint32_t i = tx * 8u + (lane & 7u), j = ty * 4u + (lane >> 3);
             if (i < P.width && j < P.height) {
                 px = j * P.width + i;
                 float rox, roy, roz;
-                if (outside || !ray_setup(P, i, j, rdx, rdy, rdz, rox, roy, roz)) {
+                if (!ray_setup(P, i, j, rdx, rdy, rdz, rox, roy, roz)) {
                     // no fragment: miss code -3, written by the presenter (every rank sees the same test)
                     if (!L.linked || L.is_presenter) status = RS_MISS;
                 } else {

@@ -376,6 +376,32 @@ class SDFViewer:
     def ipc_detach(self):
         check(self._lib.sdfgpu_ipc_detach(self._h), self._h)
 
+    # ---- SDFSurface::sample at arbitrary positions, mesh export (src/sdf/meshers)
+    def sample_points(self, points):
+        """`sample(p, false)` of the current tape for points (n, 3) -> (n, 7) raw SDFSamples."""
+        pts = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        out = np.empty((len(pts), 7), np.float32)
+        check(self._lib.sdfgpu_sample_points(self._h, _host_ptr(pts), len(pts), _host_ptr(out)), self._h)
+        return out
+
+    def mesh(self, download=True):
+        """Marching cubes over the resident volume + Mesh::postproc through the tape (meshers/mod.rs:66-87).
+        Returns (vertices (n, 12) float32, triangles (m, 3) uint32), or the two counts with download=False."""
+        nv, nt = C.c_uint64(), C.c_uint64()
+        check(self._lib.sdfgpu_mesh(self._h, C.byref(nv), C.byref(nt)), self._h)
+        if not download:
+            return nv.value, nt.value
+        v = np.empty((nv.value, 12), np.float32)
+        t = np.empty((nt.value, 3), np.uint32)
+        check(self._lib.sdfgpu_mesh_download(self._h, _host_ptr(v), _host_ptr(t)), self._h)
+        return v, t
+
+    def mesh_write_ply(self, path, comment="Created with sdf-viewer_b200"):
+        """Mesh::serialize_ply (meshers/mesh.rs:38-129) of the last mesh(); returns the bytes written."""
+        n = C.c_uint64()
+        check(self._lib.sdfgpu_mesh_write_ply(self._h, str(path).encode(), comment.encode() if comment else None, C.byref(n)), self._h)
+        return n.value
+
     # ---- linked slabs (multi-GPU behind the C ABI: include/sdfgpu.h "linked slabs")
     def link_export(self, rank, world, max_width, max_height, gbuf=False):
         """This rank's link blob (CUDA IPC handles of its volumes and arena); gather the blobs of all ranks."""
@@ -573,6 +599,16 @@ class SDFViewerGroup:
     @property
     def launch_count(self):
         return sum(r.launch_count for r in self.ranks)
+
+
+def ply_serialize(vertices, triangles, path, comment="Created with sdf-viewer_b200"):
+    """Mesh::serialize_ply for host arrays: vertices (n, 12) float32, triangles (m, 3) uint32."""
+    v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 12)
+    t = np.ascontiguousarray(triangles, np.uint32).reshape(-1, 3)
+    n = C.c_uint64()
+    check(_lib.load().sdfgpu_ply_serialize(_host_ptr(v), len(v), _host_ptr(t), len(t), comment.encode() if comment else None,
+                                           str(path).encode(), C.byref(n)))
+    return n.value
 
 
 def tape_validate(tape_bytes):

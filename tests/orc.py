@@ -258,3 +258,35 @@ class LM:
 
     def passes_left(self):
         return lib().orc_lm_passes_left(self.h)
+
+
+class RaysOracle:
+    """origin / base / dx / dy / bvp of a camera, as trace_params() takes them (the fields of sdfgpu_rays)."""
+
+
+def camera_rays(eye, center, up, fovy_deg, width, height, z_near=0.1, z_far=1000.0):
+    """Per-pixel ray basis and the biased view-projection matrix from the oracle's own cgmath restatement
+    (orc_look_at_rh / orc_perspective; scene/mod.rs:82-95, material.rs:88-95), in f32: pixel (i, j) looks along
+    base + dx * (i + 0.5) + dy * (j + 0.5).  Independent of the product's sdfgpu_camera_rays (bench.py's reference
+    arm must not load the product; tests compare the two)."""
+    f32 = np.float32
+    V, Pm = (C.c_float * 16)(), (C.c_float * 16)()
+    lib().orc_look_at_rh(_f(eye), _f(center), _f(up), V)
+    lib().orc_perspective(f32(fovy_deg) * f32(np.pi) / f32(180.0), f32(width) / f32(height), z_near, z_far, Pm)
+    V = np.array(list(V), f32); Pm = np.array(list(Pm), f32)
+    s, u, f = V[[0, 4, 8]], V[[1, 5, 9]], -V[[2, 6, 10]]
+    sx, sy = f32(1.0) / Pm[0], f32(1.0) / Pm[5]
+    r = RaysOracle()
+    r.origin = [f32(x) for x in eye]
+    r.base = list((f - s * sx) - u * sy)
+    r.dx = list(s * (f32(2.0) * sx / f32(width)))
+    r.dy = list(u * (f32(2.0) * sy / f32(height)))
+    bias = np.array([0.5, 0, 0, 0, 0, 0.5, 0, 0, 0, 0, 0.5, 0, 0.5, 0.5, 0.5, 1.0], f32).reshape(4, 4).T  # column-major
+    pv = Pm.reshape(4, 4).T @ V.reshape(4, 4).T
+    r.bvp = list((bias @ pv).T.reshape(-1).astype(f32))
+    return r
+
+
+def default_rays(width, height):
+    """The scene's default camera (scene/mod.rs:89-94): eye (2.5, 3, 5), target origin, 45 degrees."""
+    return camera_rays((2.5, 3.0, 5.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 45.0, width, height)

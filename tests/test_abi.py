@@ -236,3 +236,15 @@ def test_surface_callback_table_from_a_python_surface(S, oracle):
     assert np.all(out[:, 0] == 1.0) and np.all(out[:, 1:] == 0.0)
     assert b.changed(None, box) == 0
     assert isinstance(b._py_error[0], RuntimeError)          # the first exception is the one re-raised by update_surface
+
+
+def test_camera_rays_match_the_oracles_own_derivation(S, oracle):
+    """sdfgpu_camera_rays against the ray basis the oracle derives from its own cgmath restatement (orc.camera_rays):
+    the frame tests hand the product's rays to the oracle, this pins the rays themselves."""
+    for (w, h, eye, target) in ((640, 480, (2.5, 3.0, 5.0), (0, 0, 0)), (1920, 1080, (2.5, 3.0, 5.0), (0, 0, 0)),
+                                (333, 211, (0.2, 0.1, 0.3), (1, 0.2, -0.4))):
+        a = oracle.camera_rays(eye, target, (0, 1, 0), 45.0, w, h)
+        b = S.camera_rays(S.look_at_camera(eye, target, w, h), w, h)
+        for k in ("origin", "base", "dx", "dy", "bvp"):
+            np.testing.assert_allclose(np.array(list(getattr(a, k)), np.float32), np.array(list(getattr(b, k)), np.float32),
+                                       rtol=2e-6, atol=1e-7, err_msg=k)
