@@ -145,3 +145,15 @@ def test_trace_edge_semantics(oracle, S):
     assert (codes == -2).sum() > 0
     assert np.all(g["gbuf"][..., 15][codes == -3] == 0)
     assert g["gbuf"][..., 15].max() <= 255
+
+
+def test_trace_known_answers_derived_by_hand(oracle):
+    """tests/trace_kats.py: hit / miss, w, step count and end position of the centre ray computed on paper from
+    material.frag:27-36,97-126 and the GL filter rules -- independent of how the oracle was written."""
+    import trace_kats as K
+    rays = oracle.camera_rays(K.EYE, K.TARGET, K.UP, K.FOVY, K.W, K.H)
+    for name, dims, r, lod, linear, _exp in K.cases():
+        t0, t1 = K._volume(dims, r)
+        P = oracle.trace_params(rays, K.BB, dims, lod=lod, filter_linear=linear)
+        rgba, depth, gbuf = oracle.trace(P, t0, t1, K.W, K.H)
+        K.check(name, gbuf, depth, rgba)

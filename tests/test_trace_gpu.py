@@ -301,3 +301,22 @@ def test_gl_presenter_needs_a_gl_context(S):
         assert lib.sdfgpu_gl_unregister(v._h) == 0
         r8, d = v.trace_rgba8(cam, w, h)
         assert (d < 1).any() and r8[d < 1][:, 3].min() == 255
+
+
+def test_trace_known_answers_derived_by_hand(S):
+    """tests/trace_kats.py on the CUDA kernels (every trace variant): expectations computed on paper from
+    material.frag:27-36,97-126, not by the oracle.  The volumes go in through sdfgpu_ingest_samples."""
+    import trace_kats as K
+    cam = S.look_at_camera(K.EYE, K.TARGET, K.W, K.H, up=K.UP, fovy_deg=K.FOVY)
+    for name, dims, r, lod, linear, _exp in K.cases():
+        passes = 1 if lod == 1.0 else 2
+        with S.SDFViewer.new_voxels(dims, K.BB, passes) as v:
+            v.set_tape(S.tape.demo_tape())
+            v.update(None, max_passes=1)            # lod 1: loaded; lod 2: the coarse pass of two
+            v.ingest_samples(0, K.records(dims, r))  # then the whole volume is replaced by the KAT's
+            v.commit()
+            assert v.trace_params(cam, K.W, K.H)[2:] == (lod, linear), name
+            for variant in (0, 1, 2):
+                v.set_option("trace_variant", variant)
+                rgba, depth, gbuf = v.trace(cam, K.W, K.H, gbuf=True)
+                K.check(name, gbuf, depth, rgba)
