@@ -50,19 +50,22 @@ struct ArenaHeader {
     uint32_t pad[6];
     uint32_t frame_done[LINK_MAX_WORLD];
     uint32_t out_count[4][2];
-    uint32_t pad2[24];
+    uint32_t in_count[2][2];  // [round parity][0 from below | 1 from above], written by the neighbours
+    uint32_t pad2[20];
 };
 static_assert(sizeof(ArenaHeader) == 256, "arena header is 256 bytes");
 
 struct ArenaLayout {
-    size_t pos[2], id[2], keys[2], gbuf, total;
+    size_t pos[2][2], id[2][2], keys[2], gbuf, total;  // in-queues [round parity][0 from below | 1 from above]
 };
 ArenaLayout arena_layout(uint32_t max_pixels, bool want_gbuf) {
     ArenaLayout a;
     size_t off = sizeof(ArenaHeader);
     const size_t n = ((size_t)max_pixels + 31u) & ~(size_t)31u;
-    for (int p = 0; p < 2; ++p) { a.pos[p] = off; off += n * sizeof(float4); }
-    for (int p = 0; p < 2; ++p) { a.id[p] = off; off += n * sizeof(uint2); }
+    for (int p = 0; p < 2; ++p)
+        for (int q = 0; q < 2; ++q) { a.pos[p][q] = off; off += n * sizeof(float4); }
+    for (int p = 0; p < 2; ++p)
+        for (int q = 0; q < 2; ++q) { a.id[p][q] = off; off += n * sizeof(uint2); }
     for (int p = 0; p < 2; ++p) { a.keys[p] = off; off += n * sizeof(unsigned long long); }
     a.gbuf = want_gbuf ? off : 0;
     if (want_gbuf) off += n * SDFGPU_GBUF_FLOATS * sizeof(float);
@@ -277,17 +280,22 @@ int sdfgpu::link_trace_round(sdfgpu_ctx* ctx) {
     if (k > 0) {
         const uint32_t pg = g - 1u;  // the round whose out-queues are this round's in-queues
         for (int q = 0; q < 2; ++q) {
-            const int nb = L.nb[q];
-            if (nb < 0) continue;
-            unsigned char* a = L.peer_arena[nb];
-            lp.in_count[q] = &hdr_of(a)->out_count[pg & 3u][q == 0 ? 1 : 0];  // below: its UP queue; above: its DOWN queue
-            lp.in_pos[q] = reinterpret_cast<const float4*>(a + lay.pos[pg & 1u]);
-            lp.in_id[q] = reinterpret_cast<const uint2*>(a + lay.id[pg & 1u]);
+            if (L.nb[q] < 0) continue;
+            lp.in_count[q] = &hd->in_count[pg & 1u][q];
+            lp.in_pos[q] = reinterpret_cast<const float4*>(L.arena + lay.pos[pg & 1u][q]);
+            lp.in_id[q] = reinterpret_cast<const uint2*>(L.arena + lay.id[pg & 1u][q]);
         }
     }
     lp.out_count = hd->out_count[g & 3u];
-    lp.out_pos = reinterpret_cast<float4*>(L.arena + lay.pos[g & 1u]);
-    lp.out_id = reinterpret_cast<uint2*>(L.arena + lay.id[g & 1u]);
+    for (int dir = 0; dir < 2; ++dir) {  // dir 0: down, into the lower neighbour's "from above" queue; 1: up
+        const int nb = L.nb[dir];
+        if (nb < 0) continue;
+        unsigned char* a = L.peer_arena[nb];
+        const int q = 1 - dir;
+        lp.out_pos[dir] = reinterpret_cast<float4*>(a + lay.pos[g & 1u][q]);
+        lp.out_id[dir] = reinterpret_cast<uint2*>(a + lay.id[g & 1u][q]);
+        lp.out_publish[dir] = &hdr_of(a)->in_count[g & 1u][q];
+    }
     lp.reset_count = hd->out_count[(g + 2u) & 3u];
     unsigned char* pa = L.peer_arena[0];
     lp.frame_keys = reinterpret_cast<unsigned long long*>(pa + lay.keys[t & 1u]);

@@ -50,6 +50,8 @@ struct TraceParams {
 // slice), and is handed to the neighbour -- position, t and step count, 24 bytes -- when it leaves them; rounds
 // k >= 1 continue the rays the neighbours handed over in round k - 1.  The step sequence of every ray is the one a
 // single GPU holding the whole grid runs, bit for bit.  With linked == 0 the kernel is the plain single-volume trace.
+// Hand-over is PUSH: a rank stores the entries into its neighbour's in-queue and publishes the count there, so every
+// kernel reads its work from local memory.
 struct LinkParams {
     uint32_t linked;        // 0: single volume, outputs of TraceParams; 1: sharded, finished pixels go to the presenter
     uint32_t first;         // round 0 of a frame: the work units are 8 x 4 pixel tiles; else 32-entry runs of the in-queues
@@ -58,16 +60,18 @@ struct LinkParams {
     uint32_t max_pixels;    // capacity of every queue buffer
     uint32_t* work_head;    // local: next work unit (reset by the last CTA)
     uint32_t* ctas_done;    // local: CTAs that have finished (reset by the last CTA)
-    // in-queues: what the neighbours appended in the previous round ([0] the neighbour below, its UP entries at
-    // [max_pixels - 1 - i]; [1] the neighbour above, its DOWN entries at [i]); null without a neighbour
+    // in-queues (OWN memory: the neighbours PUSH): what they appended in the previous round, [0] the neighbour below
+    // (rays travelling up), [1] the neighbour above (rays travelling down); counts published by their last CTA
     const uint32_t* in_count[2];
     const float4* in_pos[2];
     const uint2* in_id[2];
-    // out-queue of this round (own memory): [0] rays leaving downwards, filled from the front; [1] upwards, from the back
-    uint32_t* out_count;    // two counters
-    float4* out_pos;        // position.xyz, t
-    uint2* out_id;          // pixel index, step count
-    uint32_t* reset_count;  // the counter pair this kernel's last CTA zeroes (ring of 4: the pair of round + 2)
+    // out-queues of this round: [0] rays leaving downwards, [1] upwards -- each in the in-queue of that neighbour
+    // (peer memory: stores over NVLink, no load ever crosses it); null without a neighbour
+    uint32_t* out_count;      // own memory: two reservation counters
+    float4* out_pos[2];       // position.xyz, t
+    uint2* out_id[2];         // pixel index, step count
+    uint32_t* out_publish[2]; // the neighbours' in_count words for this round (written by the last CTA)
+    uint32_t* reset_count;    // the counter pair this kernel's last CTA zeroes (ring of 4: the pair of round + 2)
     unsigned long long* frame_keys;  // presenter's (depth, RGBA8) key frame -- peer memory on the other ranks
     float* frame_gbuf;               // presenter's G-buffer frame, or null
     uint32_t* sig_round[2];          // the neighbours' "round done" flags (peer memory), or null

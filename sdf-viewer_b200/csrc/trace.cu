@@ -700,9 +700,8 @@ __global__ void __launch_bounds__(256) trace_rounds_kernel(const __grid_constant
             const uint32_t q = unit < units0 ? 0u : 1u;
             const uint32_t e = (unit - (q ? units0 : 0u)) * 32u + lane;
             if (e < (q ? cnt1 : cnt0)) {
-                const uint32_t idx = q ? e : L.max_pixels - 1u - e;
-                const float4 pos = L.in_pos[q][idx];
-                const uint2 id = L.in_id[q][idx];
+                const float4 pos = L.in_pos[q][e];
+                const uint2 id = L.in_id[q][e];
                 r.hx = pos.x; r.hy = pos.y; r.hz = pos.z; r.t = pos.w;
                 px = id.x; r.it = (int)id.y;
                 float rox, roy, roz;
@@ -764,9 +763,8 @@ __global__ void __launch_bounds__(256) trace_rounds_kernel(const __grid_constant
                 base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
                 if (go) {
                     const uint32_t e = base + __popc(m & ((1u << lane) - 1u));
-                    const uint32_t idx = dir ? L.max_pixels - 1u - e : e;
-                    L.out_pos[idx] = make_float4(r.hx, r.hy, r.hz, r.t);
-                    L.out_id[idx] = make_uint2(px, (uint32_t)r.it);
+                    L.out_pos[dir][e] = make_float4(r.hx, r.hy, r.hz, r.t);
+                    L.out_id[dir][e] = make_uint2(px, (uint32_t)r.it);
                 }
             }
         }
@@ -781,6 +779,9 @@ __global__ void __launch_bounds__(256) trace_rounds_kernel(const __grid_constant
             *L.work_head = 0u;
             *L.ctas_done = 0u;
             if (L.linked) {
+                // every CTA has finished: the reservation counters are final -- publish them in the neighbours' arenas
+                if (L.out_publish[0]) *reinterpret_cast<volatile uint32_t*>(L.out_publish[0]) = L.out_count[0];
+                if (L.out_publish[1]) *reinterpret_cast<volatile uint32_t*>(L.out_publish[1]) = L.out_count[1];
                 L.reset_count[0] = 0u; L.reset_count[1] = 0u;
                 __threadfence_system();
                 if (L.sig_round[0]) *reinterpret_cast<volatile uint32_t*>(L.sig_round[0]) = L.sig_round_value;
