@@ -645,10 +645,11 @@ __global__ void __launch_bounds__(256) trace_rounds_kernel(const __grid_constant
         n_units = units0 + (cnt1 + 31u) / 32u;
     }
 
+    // every warp's first unit is its own index -- a round with little or no work costs no queue access at all -- the
+    // rest are handed out by the queue
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     for (;;) {
-        uint32_t unit = 0;
-        if (lane == 0) unit = atomicAdd(L.work_head, 1u);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= n_units) break;
 
         if (L.first && unit >= n_heavy) {  // a run of tiles no ray of which enters the box: miss code -3, no arithmetic
@@ -671,6 +672,8 @@ __global__ void __launch_bounds__(256) trace_rounds_kernel(const __grid_constant
                 const uint32_t i = tx * 8u + (lane & 7u), j = ty * 4u + (lane >> 3);
                 if (i < P.width && j < P.height) finish_pixel<SNAP, LINEAR>(P, L, v0, v1, j * P.width + i, false, -3.0f, none);
             }
+            if (lane == 0) unit = n_warps + atomicAdd(L.work_head, 1u);
+            unit = __shfl_sync(0xffffffffu, unit, 0);
             continue;
         }
 
@@ -768,13 +771,17 @@ __global__ void __launch_bounds__(256) trace_rounds_kernel(const __grid_constant
                 }
             }
         }
+        if (lane == 0) unit = n_warps + atomicAdd(L.work_head, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
     }
 
     // ---- the last CTA to finish resets the counters and tells the neighbours (and, after the last round, the
     // presenter) that this round's queue entries and pixels are in place
-    if (L.linked) __threadfence_system();  // out-queue entries and the peer stores of finished pixels
+    // out-queue entries and the peer stores of finished pixels: the CTA's writes are ordered before thread 0's fence by
+    // the barrier (fences are cumulative), so one system-scope fence per CTA is enough
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (L.linked) __threadfence_system();
         if (atomicAdd(L.ctas_done, 1u) + 1u == gridDim.x) {
             *L.work_head = 0u;
             *L.ctas_done = 0u;
