@@ -434,6 +434,21 @@ def parity_check_multi(torch, dist, S, sv, tape, dims, cam, W, H, rank, world, l
                 ok &= bool(torch.equal(t.view(torch.int32), mine[(z - v.z_lo) * n:(z - v.z_lo + 1) * n].view(torch.int32)))
             halos += 1
     res["halo_slices_checked"] = halos
+    # (1b) each halo slice equals the neighbour's actual boundary slice (fetched with NCCL here, outside any timed region)
+    ops, got = [], []
+    for nb, z_send, z_halo in ((rank - 1, v.z_begin, v.z_lo), (rank + 1, v.z_end - 1, v.z_hi - 1)):
+        if nb < 0 or nb >= world:
+            continue
+        for tex in sv._tex:
+            buf = torch.empty(n, dtype=torch.float32, device=dev)
+            ops += [dist.P2POp(dist.isend, tex[(z_send - v.z_lo) * n:(z_send - v.z_lo + 1) * n].clone(), nb), dist.P2POp(dist.irecv, buf, nb)]
+            got.append((buf, tex[(z_halo - v.z_lo) * n:(z_halo - v.z_lo + 1) * n]))
+    for r in dist.batch_isend_irecv(ops) if ops else []:
+        r.wait()
+    torch.cuda.synchronize()
+    for buf, mine in got:
+        ok &= bool(torch.equal(buf.view(torch.int32), mine.view(torch.int32)))
+    res["halo_slices_vs_neighbour"] = len(got)
     try:
         import orc
         orc.build()
@@ -465,6 +480,41 @@ def parity_check_multi(torch, dist, S, sv, tape, dims, cam, W, H, rank, world, l
     return res
 
 
+def alt_modes_multi(torch, dist, ShardedViewer, dims, tape, cam, W, H, rank, world, local, steps=20):
+    """N > 1, after the timed region: the same step with the halo slices PUSHED by the neighbours and the trace in
+    ROUNDS (the two alternatives the default replaces), so that every scaling run carries the comparison."""
+    out = {}
+    for name, kw in (("halo_push_stream_trace", {"halo_push": True}), ("halo_local_rounds_trace", {"trace_mode": 1})):
+        sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, max_width=W, max_height=H, **kw)
+        try:
+            if not sv.linked:
+                out[name] = {"error": getattr(sv, "link_error", "not linked")}
+                continue
+            v = sv.viewer
+            v.set_tape(tape)
+            stream = torch.cuda.ExternalStream(v.stream, device=torch.device("cuda", local))
+            for _ in range(3):
+                sv.fill_all(); sv.commit(); sv.trace_device(cam, W, H)
+            v.sync(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+            for e in evs:
+                e[0].record(stream)
+                sv.fill_all(); sv.commit()
+                e[1].record(stream)
+                sv.trace_device(cam, W, H)
+                e[2].record(stream)
+            v.sync(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            t = torch.tensor([evs[0][0].elapsed_time(evs[-1][2]) / steps, sum(e[0].elapsed_time(e[1]) for e in evs) / steps,
+                              sum(e[1].elapsed_time(e[2]) for e in evs) / steps], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out[name] = {"ms_per_step": t[0].item(), "fill_ms": t[1].item(), "trace_ms": t[2].item(), "steps": steps}
+        except Exception as e:  # an extra, never a reason to lose the bench line
+            out[name] = {"error": str(e)}
+        finally:
+            sv.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -483,6 +533,10 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the C3 / C5 / close-up / 2160p legs that follow the timed region")
     ap.add_argument("--no-linked", action="store_true",
                     help="N > 1: the round-1 path (IPC halo pushes ordered by NCCL, sort-last trace + all-reduce(MIN)) instead of linked slabs")
+    ap.add_argument("--halo-push", action="store_true",
+                    help="N > 1, linked: the neighbours push the halo slices over NVLink (default: every rank fills its own)")
+    ap.add_argument("--trace-rounds", action="store_true",
+                    help="N > 1, linked: trace in `world` rounds of one kernel (default: one streaming kernel per rank)")
     ap.add_argument("--exact-trace", action="store_true",
                     help="with --no-linked: trace with the replicated distance volume + owner shading instead of sort-last")
     ap.add_argument("--no-fused-halo", action="store_true", help="with --no-linked: exchange halos with NCCL send/recv")
@@ -518,7 +572,8 @@ def main():
     from sdf_viewer_b200.sharded import ShardedViewer
     want_c4 = world > 1 and not args.no_extras
     sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, fused=not args.no_fused_halo,
-                       linked=not args.no_linked, max_width=max(W, 3840 if want_c4 else 0), max_height=max(H, 2160 if want_c4 else 0))
+                       linked=not args.no_linked, max_width=max(W, 3840 if want_c4 else 0), max_height=max(H, 2160 if want_c4 else 0),
+                       halo_push=args.halo_push, trace_mode=1 if args.trace_rounds else 0)
     v = sv.viewer
     if args.vpt:
         v.set_option("fill_voxels_per_thread", args.vpt)
@@ -635,6 +690,9 @@ def main():
                       "hit_fraction": float((d4 < 1.0).mean())}
             except Exception as e:
                 c4 = {"error": str(e)}
+    alt = None
+    if world > 1 and sv.linked and not args.no_extras and not args.halo_push and not args.trace_rounds:
+        alt = alt_modes_multi(torch, dist, ShardedViewer, dims, tape, cam, W, H, rank, world, local)
     trace_modes = extras = None
     if n_gpus == 1 and not args.no_extras:
         trace_modes = trace_modes_live(torch, v, stream, cam, W, H)
@@ -650,8 +708,13 @@ def main():
     if n_gpus == 1:
         sharding = "single GPU"
     elif sv.linked:
-        sharding = (f"z-slabs x{n_gpus}, linked through the C ABI: one fill launch per rank (boundary tiles first, DMA halo push behind a flag), "
-                    f"exact ray-hand-off trace ({n_gpus} rounds), pixels stored into rank 0's frame over NVLink; flags: "
+        sharding = (f"z-slabs x{n_gpus}, linked through the C ABI: one fill launch per rank, "
+                    + ("boundary tiles first, DMA halo push behind a flag" if v.get_info("link_halo_push")
+                       else "halo slices filled by their holder (no exchange: sample() is a pure function of the position)")
+                    + ", exact ray-hand-off trace ("
+                    + ("one streaming kernel per rank, rays pushed into the neighbour's queue over NVLink" if v.get_info("link_trace_stream")
+                       else f"{n_gpus} rounds")
+                    + "), pixels stored into rank 0's frame over NVLink; flags: "
                     + ("stream memory operations" if v.get_info("link_memops") else "spin-wait kernels"))
     else:
         sharding = (f"z-slabs x{n_gpus}, round-1 path: " + ("IPC halo pushes ordered by a 4-byte NCCL all-reduce" if sv.fused else "NCCL send/recv halo exchange")
@@ -686,6 +749,8 @@ def main():
         out["parity_detail"] = parity
     if c4 is not None:
         out["c4_trace_2160p"] = c4
+    if alt is not None:
+        out["alternatives"] = alt
     if extras:
         out.update(extras)
     if not args.no_cpu_baseline and n_gpus == 1:

@@ -93,15 +93,24 @@ int sdfgpu_ipc_detach(sdfgpu_ctx* ctx);
  *      empty), calls sdfgpu_link_export, the SDFGPU_LINK_BLOB_BYTES blobs of all ranks are gathered by any means (they
  *      hold CUDA IPC handles: same node only), and every rank calls sdfgpu_link_attach with all of them.
  *
- * Linking maps the neighbours' volumes and every rank's arena (flags, ray queues, the presenter's frame) into this
- * handle's address space.  From then on these entry points are COLLECTIVE -- every rank calls them in the same order
+ * Linking maps every rank's arena (flags, ray queues, the presenter's frame) -- and, with SDFGPU_LINK_HALO_PUSH, the
+ * neighbours' volumes -- into this handle's address space.  From then on these entry points are COLLECTIVE -- every rank calls them in the same order
  * with the same arguments: sdfgpu_fill_all, sdfgpu_update, sdfgpu_update_surface, sdfgpu_resample_box, sdfgpu_reset,
- * sdfgpu_commit, sdfgpu_trace_rgba8 / sdfgpu_trace_linked.
- *   fill:  one launch; the tiles of the first and last own slice go first, the kernel releases a flag when they are
- *          complete, and the copy engines push them into the neighbours' halo slices over NVLink while the interior is
- *          still being filled.  update / resample_box push after their last pass, and only the faces a dirty box touches.
+ * sdfgpu_commit, sdfgpu_trace_rgba8 / sdfgpu_trace_linked.  Options read by sdfgpu_link_export: "link_halo_push",
+ * "link_trace_mode" (0 auto, 1 rounds, 2 stream), "link_timeout_ms" (how long a streaming trace waits for a neighbour).
+ *   fill:  no exchange.  Every rank fills its stored slices, the one halo slice per interior face included:
+ *          SDFSurface::sample is a pure function of the position between changed() events (src/sdf/mod.rs:43), so the
+ *          halo slices equal the neighbours' boundary slices bit for bit and cost 2 of D/world slices of extra work.
+ *          With SDFGPU_LINK_HALO_PUSH the neighbours push them instead: one launch, the tiles of the first and last own
+ *          slice go first, the kernel releases a flag when they are complete, and the copy engines push them into the
+ *          neighbours' halo slices over NVLink while the interior is still being filled; update / resample_box push
+ *          after their last pass, and only the faces a dirty box touches.  (Measured: the pushes are slow while both
+ *          HBMs are saturated by the fills -- DESIGN.md section 5.)
  *   trace: exact.  A ray marches on the rank that owns the lower z tap of its texture fetch and is handed to the
- *          neighbour (position, t, step count) when it leaves that rank's slices; `world` rounds of one kernel.  The
+ *          neighbour (position, t, step count) when it leaves that rank's slices.  With every rank on a device of its
+ *          own this is ONE kernel per rank and frame: its persistent warps trace the rank's own rays, then poll the
+ *          in-queue the neighbours store into over NVLink, so the ranks form a pipeline along z.  Ranks that share a
+ *          device (tests), or SDFGPU_LINK_ROUNDS, take turns instead: `world` rounds of one kernel.  Either way the
  *          frame equals sdfgpu_trace_rgba8 of ONE handle holding the whole grid bit for bit (RGBA8, depth, and the
  *          G-buffer but for the normals of hits next to a slab face).  Finished pixels are stored straight into the frame
  *          of rank 0 (the presenter), which alone receives rgba8 / depth / gbuf; the other ranks pass NULL.
@@ -109,6 +118,9 @@ int sdfgpu_ipc_detach(sdfgpu_ctx* ctx);
  * and detach every rank before destroying any of them.  SDFGPU_LINK_GBUF reserves a G-buffer frame (tests). */
 #define SDFGPU_LINK_BLOB_BYTES 320
 #define SDFGPU_LINK_GBUF 1u
+#define SDFGPU_LINK_HALO_PUSH 2u /* halo slices pushed by the neighbours (below) instead of filled by their holder */
+#define SDFGPU_LINK_ROUNDS 4u    /* trace in `world` rounds even when every rank has a device of its own */
+#define SDFGPU_LINK_STREAM 8u    /* insist on the one-launch trace: attach fails when ranks share a device */
 int sdfgpu_link_export(sdfgpu_ctx* ctx, uint32_t rank, uint32_t world, uint32_t max_width, uint32_t max_height,
                        uint32_t flags, void* blob, size_t blob_bytes);
 int sdfgpu_link_attach(sdfgpu_ctx* ctx, const void* blobs, uint32_t world);
@@ -501,12 +513,15 @@ uint64_t sdfgpu_launch_count(const sdfgpu_ctx* ctx);
  *   "trace_variant" 0 heavy-first 8x8 tiles | 1 plain 2-D grid | 2 persistent warps pulling 8x4 tiles from a queue,
  *                  explicit warp-ballot exit (the kernel linked handles always use); same frame bit for bit
  *   "link_wait_mode" 0 cuStreamWaitValue32 when the driver has it (default) | 1 spin-wait kernels; before link_attach
+ *   "link_halo_push" 0|1 and "link_trace_mode" 0 auto | 1 rounds | 2 stream: the SDFGPU_LINK_* flags as options, read by
+ *                  sdfgpu_link_export;  "link_timeout_ms" (default 20000): how long a streaming trace kernel waits
+ *                  for rays of a neighbour that never arrives before the frame fails with SDFGPU_ERR_STATE
  *   "fill_program" 0 auto (kernel specialised for the tape structure, else built-in demo program,
  *                  else interpreter) | 1 interpreter | 2 built-in or interpreter | 3 specialised or fail */
 int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value);
 /* Introspection: "last_fill_program" (0 interpreter, 1 specialised/JIT, 2 built-in demo),
  * "last_fill_ctas_per_sm", "last_fill_voxels_per_thread", "sm_count", "tape_image_bytes",
- * "tape_culled", "jit_available". */
+ * "tape_culled", "jit_available", "device", "linked", "link_memops", "link_halo_push", "link_trace_stream". */
 int sdfgpu_get_info(const sdfgpu_ctx* ctx, const char* key, int64_t* value);
 
 #ifdef __cplusplus

@@ -19,6 +19,9 @@ SDFGPU_ERR_STATE = -4
 GBUF_FLOATS = 16
 LINK_BLOB_BYTES = 320
 LINK_GBUF = 1
+LINK_HALO_PUSH = 2
+LINK_ROUNDS = 4
+LINK_STREAM = 8
 
 
 class SdfGpuError(RuntimeError):

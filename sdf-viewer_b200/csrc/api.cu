@@ -1116,7 +1116,7 @@ SDFGPU_API int sdfgpu_fill_all(sdfgpu_ctx* ctx) {
     uint32_t za, zb;
     fill_z_range(ctx, &za, &zb);
     int rc;
-    if (ctx->link.on) {
+    if (ctx->link.on && ctx->link.halo_push) {
         // ONE launch: the tiles of the two boundary slices first; the copy engines push them into the neighbours'
         // halo slices, behind the kernel's boundary flag, while the interior is being filled (link.cu)
         const uint32_t lo[3] = {0, 0, ctx->z_begin}, hi[3] = {ctx->dims[0], ctx->dims[1], ctx->z_end};
@@ -1125,7 +1125,7 @@ SDFGPU_API int sdfgpu_fill_all(sdfgpu_ctx* ctx) {
         ctx->fill_boundary_first = false;
         if (rc != SDFGPU_OK) return rc;
         if ((rc = link_fill_all_pushed(ctx)) != SDFGPU_OK) return rc;
-    } else if (has_peers(ctx) && ctx->z_end - ctx->z_begin >= 3) {
+    } else if (!ctx->link.on && has_peers(ctx) && ctx->z_end - ctx->z_begin >= 3) {
         // fused halo exchange: fill the boundary slices first, then let the copy engines push them into
         // the neighbours' halo slices over NVLink WHILE the interior is being filled
         if (!ctx->halo_stream) {
@@ -1147,7 +1147,9 @@ SDFGPU_API int sdfgpu_fill_all(sdfgpu_ctx* ctx) {
     } else {
         const uint32_t lo[3] = {0, 0, za}, hi[3] = {ctx->dims[0], ctx->dims[1], zb};
         if ((rc = run_fill(ctx, 1, lo, hi, FILL_ALL, nullptr)) != SDFGPU_OK) return rc;
-        if (has_peers(ctx) && (rc = push_halos(ctx, ctx->stream)) != SDFGPU_OK) return rc;
+        if (ctx->link.on) rc = link_after_fill(ctx, true, true);  // halo slices filled above: counts the fill, nothing to exchange
+        else if (has_peers(ctx)) rc = push_halos(ctx, ctx->stream);
+        if (rc != SDFGPU_OK) return rc;
     }
     ctx->known_step = 1;
     while (ctx->lm.step_size != 0) ctx->lm.finish_pass();
@@ -1188,8 +1190,20 @@ SDFGPU_API int sdfgpu_resample_box(sdfgpu_ctx* ctx, const float box[6], uint64_t
             cudaError_t e = cudaMemsetAsync(ctx->touched_dev, 0, sizeof(unsigned long long), ctx->stream);
             if (e != cudaSuccess) rc = fail(ctx, SDFGPU_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
         }
-        if (rc == SDFGPU_OK)
-            rc = run_fill(ctx, 1, lo, hi, ctx->known_step == 1 ? FILL_BOX_ONLY : FILL_READ, voxels_touched ? ctx->touched_dev : nullptr);
+        // voxels_touched counts the slab's OWN voxels: halo slices that are filled here too (fill_halo) go into launches
+        // of their own, without the counter
+        const uint32_t mode = ctx->known_step == 1 ? FILL_BOX_ONLY : FILL_READ;
+        const uint32_t own_lo = lo[2] > ctx->z_begin ? lo[2] : ctx->z_begin, own_hi = hi[2] < ctx->z_end ? hi[2] : ctx->z_end;
+        if (rc == SDFGPU_OK && voxels_touched && (lo[2] < own_lo || hi[2] > own_hi)) {
+            const uint32_t parts[3][2] = {{lo[2], own_lo < hi[2] ? own_lo : hi[2]}, {own_lo, own_hi}, {own_hi > lo[2] ? own_hi : lo[2], hi[2]}};
+            for (int k = 0; k < 3 && rc == SDFGPU_OK; ++k) {
+                if (parts[k][0] >= parts[k][1]) continue;
+                const uint32_t plo[3] = {lo[0], lo[1], parts[k][0]}, phi[3] = {hi[0], hi[1], parts[k][1]};
+                rc = run_fill(ctx, 1, plo, phi, mode, k == 1 ? ctx->touched_dev : nullptr);
+            }
+        } else if (rc == SDFGPU_OK) {
+            rc = run_fill(ctx, 1, lo, hi, mode, voxels_touched ? ctx->touched_dev : nullptr);
+        }
         if (ctx->known_step != 1) ctx->known_step = -1;
         ctx->has_changed_box = saved_has;
         memcpy(ctx->changed_box, saved, sizeof saved);
@@ -1319,7 +1333,7 @@ SDFGPU_API int sdfgpu_reset(sdfgpu_ctx* ctx, uint32_t loading_passes) {
     if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
     set_device(ctx);
     int rc;
-    if (ctx->link.on) {
+    if (ctx->link.on && ctx->link.halo_push) {
         // a linked handle's halo slices are written by its neighbours only: reset the own slices and push the two
         // boundary slices like any fill does (collective: the neighbours do the same to this handle's halo slices).
         // Resetting the halo slices here would race with a neighbour that has already reset and filled again.
@@ -1901,6 +1915,18 @@ SDFGPU_API int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value
         if (value < 0 || value > 1) return fail(ctx, SDFGPU_ERR_INVALID, "link_wait_mode must be 0 or 1");
         if (ctx->link.on) return fail(ctx, SDFGPU_ERR_STATE, "set link_wait_mode before sdfgpu_link_attach");
         ctx->opt_link_wait = (int)value;
+    } else if (!strcmp(key, "link_halo_push")) {
+        if (value < 0 || value > 1) return fail(ctx, SDFGPU_ERR_INVALID, "link_halo_push must be 0 or 1");
+        if (ctx->link.arena) return fail(ctx, SDFGPU_ERR_STATE, "set link_halo_push before sdfgpu_link_export");
+        ctx->opt_link_halo_push = (int)value;
+    } else if (!strcmp(key, "link_trace_mode")) {
+        if (value < 0 || value > 2) return fail(ctx, SDFGPU_ERR_INVALID, "link_trace_mode must be 0 (auto), 1 (rounds) or 2 (stream)");
+        if (ctx->link.arena) return fail(ctx, SDFGPU_ERR_STATE, "set link_trace_mode before sdfgpu_link_export");
+        ctx->opt_link_trace_mode = (int)value;
+    } else if (!strcmp(key, "link_timeout_ms")) {
+        if (value < 1 || value > 3600000) return fail(ctx, SDFGPU_ERR_INVALID, "link_timeout_ms out of range");
+        ctx->opt_link_timeout_ms = (int)value;
+        ctx->link.timeout_ms = (uint32_t)value;
     } else if (!strcmp(key, "fill_program")) {
         if (value < 0 || value > 3) return fail(ctx, SDFGPU_ERR_INVALID, "fill_program must be 0..3");
         ctx->opt_program = (int)value;
@@ -1916,11 +1942,14 @@ SDFGPU_API int sdfgpu_get_info(const sdfgpu_ctx* ctx, const char* key, int64_t* 
     else if (!strcmp(key, "last_fill_ctas_per_sm")) *value = ctx->last_ctas;
     else if (!strcmp(key, "last_fill_voxels_per_thread")) *value = ctx->last_vpt;
     else if (!strcmp(key, "sm_count")) *value = ctx->sm_count;
+    else if (!strcmp(key, "device")) *value = ctx->device;
     else if (!strcmp(key, "tape_image_bytes")) *value = (int64_t)ctx->img_host.size();
     else if (!strcmp(key, "tape_culled")) *value = (ctx->hdr.flags & TAPE_FLAG_CULL) ? 1 : 0;
     else if (!strcmp(key, "jit_available")) { std::string why; *value = jit_available(&why) ? 1 : 0; }
     else if (!strcmp(key, "linked")) *value = ctx->link.on ? 1 : 0;
     else if (!strcmp(key, "link_memops")) *value = ctx->link.on && ctx->link.memops ? 1 : 0;
+    else if (!strcmp(key, "link_halo_push")) *value = ctx->link.on && ctx->link.halo_push ? 1 : 0;
+    else if (!strcmp(key, "link_trace_stream")) *value = ctx->link.on && ctx->link.stream ? 1 : 0;
     else if (!strcmp(key, "link_fill_epoch")) *value = ctx->link.fill_epoch;
     else if (!strcmp(key, "link_round_epoch")) *value = ctx->link.round_epoch;
     else return fail(nullptr, SDFGPU_ERR_INVALID, "unknown info key '%s'", key);

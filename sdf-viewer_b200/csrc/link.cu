@@ -26,6 +26,7 @@
 //   consumed          (from the presenter) frames 0 .. value - 1 have been unpacked: their key frame may be reused
 #include <unistd.h>
 
+#include <cstddef>
 #include <cstdlib>
 #include <new>
 
@@ -47,25 +48,35 @@ struct ArenaHeader {
     uint32_t work_head;
     uint32_t ctas_done;
     uint32_t timed_out;
-    uint32_t pad[6];
+    uint32_t tiles_done;      // stream trace: tile units finished
+    uint32_t pad0;
+    uint32_t in_head[2];      // stream trace: in-queue units claimed [0 from below | 1 from above]
+    uint32_t in_done[2];      //   ... and finished
     uint32_t frame_done[LINK_MAX_WORLD];
     uint32_t out_count[4][2];
     uint32_t in_count[2][2];  // [round parity][0 from below | 1 from above], written by the neighbours
-    uint32_t pad2[20];
+    uint32_t sent_final[2];   // stream trace: this rank has closed its out-queue [0 down | 1 up]
+    unsigned long long in_final[2][2];  // stream trace, [frame parity][from below | above], written by the neighbours:
+                                        // frame tag << 32 | entries in that in-queue (the queue is closed)
+    uint32_t pad2[10];
 };
 static_assert(sizeof(ArenaHeader) == 256, "arena header is 256 bytes");
+static_assert(offsetof(ArenaHeader, in_final) % 8 == 0, "64-bit words are aligned");
 
 struct ArenaLayout {
-    size_t pos[2][2], id[2][2], keys[2], gbuf, total;  // in-queues [round parity][0 from below | 1 from above]
+    // in-queues [round / frame parity][0 from below | 1 from above], 32 bytes per entry: the round kernel keeps
+    // float4 positions at pos and uint2 ids at id, the stream kernel two tagged float4 per entry from pos on
+    size_t pos[2][2], id[2][2], keys[2], gbuf, total;
 };
 ArenaLayout arena_layout(uint32_t max_pixels, bool want_gbuf) {
     ArenaLayout a;
     size_t off = sizeof(ArenaHeader);
     const size_t n = ((size_t)max_pixels + 31u) & ~(size_t)31u;
     for (int p = 0; p < 2; ++p)
-        for (int q = 0; q < 2; ++q) { a.pos[p][q] = off; off += n * sizeof(float4); }
-    for (int p = 0; p < 2; ++p)
-        for (int q = 0; q < 2; ++q) { a.id[p][q] = off; off += n * sizeof(uint2); }
+        for (int q = 0; q < 2; ++q) {
+            a.pos[p][q] = off; off += n * sizeof(float4);
+            a.id[p][q] = off; off += n * sizeof(float4);
+        }
     for (int p = 0; p < 2; ++p) { a.keys[p] = off; off += n * sizeof(unsigned long long); }
     a.gbuf = want_gbuf ? off : 0;
     if (want_gbuf) off += n * SDFGPU_GBUF_FLOATS * sizeof(float);
@@ -81,6 +92,7 @@ struct LinkBlob {  // what a rank publishes (SDFGPU_LINK_BLOB_BYTES)
     uint64_t arena_bytes;
     uint64_t p_tex0, p_tex1, p_arena;
     cudaIpcMemHandle_t h_tex0, h_tex1, h_arena;
+    unsigned char uuid[16];  // of the device: ranks that share a GPU cannot run the stream trace
 };
 static_assert(sizeof(LinkBlob) <= SDFGPU_LINK_BLOB_BYTES, "blob fits");
 constexpr uint32_t LINK_MAGIC = 0x4b4c4453u;  // "SDLK"
@@ -184,6 +196,7 @@ int sdfgpu::link_after_fill(sdfgpu_ctx* ctx, bool touched_lo, bool touched_hi) {
     if (!L.on) return SDFGPU_OK;
     int rc;
     const uint32_t f = ++L.fill_epoch;
+    if (!L.halo_push) return SDFGPU_OK;  // the halo slices were filled here like the own ones
     if ((rc = wait_neighbours_idle(ctx, ctx->stream, touched_lo, touched_hi)) != SDFGPU_OK) return rc;
     if ((rc = push_halos(ctx, ctx->stream, touched_lo, touched_hi)) != SDFGPU_OK) return rc;
     return signal_halo_in(ctx, ctx->stream, f);
@@ -191,7 +204,7 @@ int sdfgpu::link_after_fill(sdfgpu_ctx* ctx, bool touched_lo, bool touched_hi) {
 
 int sdfgpu::link_fill_all_fused(sdfgpu_ctx* ctx, FillParams* p) {
     LinkState& L = ctx->link;
-    if (!L.on || (L.nb[0] < 0 && L.nb[1] < 0)) return SDFGPU_OK;
+    if (!L.on || !L.halo_push || (L.nb[0] < 0 && L.nb[1] < 0)) return SDFGPU_OK;
     ArenaHeader* h = hdr_of(L.arena);
     const uint32_t bz = p->tiles_z < 2u ? p->tiles_z : 2u;
     p->n_boundary_tiles = p->tiles_x * p->tiles_y * bz;
@@ -205,7 +218,7 @@ int sdfgpu::link_fill_all_pushed(sdfgpu_ctx* ctx) {
     LinkState& L = ctx->link;
     if (!L.on) return SDFGPU_OK;
     const uint32_t f = ++L.fill_epoch;
-    if (L.nb[0] < 0 && L.nb[1] < 0) return SDFGPU_OK;
+    if (!L.halo_push || (L.nb[0] < 0 && L.nb[1] < 0)) return SDFGPU_OK;
     int rc;
     if ((rc = ensure_halo_stream(ctx)) != SDFGPU_OK) return rc;
     // the copy engines wait for the fill kernel's boundary flag (epochs are unique: no event needed), not for the kernel
@@ -239,7 +252,7 @@ int sdfgpu::link_trace_begin(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t
     ctx->link_tp.dist = nullptr; ctx->link_tp.dist_mode = 0; ctx->link_tp.dist_tex = 0;
     const uint32_t t = L.frame_epoch++;
     ArenaHeader* hd = hdr_of(L.arena);
-    for (int side = 0; side < 2; ++side)  // the neighbours' boundary slices of the last fill are in my halo slices
+    for (int side = 0; side < 2 && L.halo_push; ++side)  // the neighbours' boundary slices of the last fill are in my halo slices
         if (L.nb[side] >= 0 && (rc = wait_flag(ctx, ctx->stream, &hd->halo_in[side], L.fill_epoch)) != SDFGPU_OK) return rc;
     if (L.rank != 0) {
         // the presenter's key frame of this parity was last used by frame t - 2 (the single G-buffer frame by t - 1)
@@ -315,6 +328,75 @@ int sdfgpu::link_trace_round(sdfgpu_ctx* ctx) {
     return SDFGPU_OK;
 }
 
+// The whole frame of this rank in one launch (LinkState::stream): the kernels of the ranks run side by side and feed
+// each other's in-queues; nothing here waits for a neighbour -- the kernel does.
+int sdfgpu::link_trace_stream(sdfgpu_ctx* ctx) {
+    LinkState& L = ctx->link;
+    if (!L.on || !L.in_frame) return fail(ctx, SDFGPU_ERR_STATE, "no linked frame in flight");
+    if (!L.stream) return fail(ctx, SDFGPU_ERR_STATE, "the link traces in rounds");
+    if (L.cur_round != 0) return fail(ctx, SDFGPU_ERR_STATE, "the frame has been issued");
+    set_device(ctx);
+    L.cur_round = L.world;
+    const uint32_t g = L.round_epoch++;
+    const uint32_t t = L.frame_epoch - 1u;
+    ArenaHeader* hd = hdr_of(L.arena);
+    const ArenaLayout lay = arena_layout(L.max_pixels, L.want_gbuf);
+    LinkParams lp;
+    memset(&lp, 0, sizeof lp);
+    lp.linked = 1u;
+    lp.first = 1u;
+    lp.is_presenter = L.rank == 0 ? 1u : 0u;
+    lp.own_z0 = ctx->z_begin; lp.own_z1 = ctx->z_end;
+    lp.max_pixels = L.max_pixels;
+    lp.work_head = &hd->work_head;
+    lp.ctas_done = &hd->ctas_done;
+    lp.epoch = t + 1u;
+    lp.timeout_ms = L.timeout_ms;
+    lp.tiles_done = &hd->tiles_done;
+    lp.in_head = hd->in_head;
+    lp.in_done = hd->in_done;
+    lp.sent_final = hd->sent_final;
+    lp.timed_out = L.timed_out_host;
+    lp.out_count = hd->out_count[0];
+    const uint32_t par = t & 1u;
+    for (int q = 0; q < 2; ++q) {  // q 0: the neighbour below feeds my "from below" queue; dir 0: I feed ITS "from above" queue
+        const int nb = L.nb[q];
+        if (nb < 0) continue;
+        lp.in_q[q] = reinterpret_cast<const float4*>(L.arena + lay.pos[par][q]);
+        lp.in_final[q] = &hd->in_final[par][q];
+        unsigned char* a = L.peer_arena[nb];
+        lp.out_q[q] = reinterpret_cast<float4*>(a + lay.pos[par][1 - q]);
+        lp.out_final[q] = &hdr_of(a)->in_final[par][1 - q];
+    }
+    unsigned char* pa = L.peer_arena[0];
+    lp.frame_keys = reinterpret_cast<unsigned long long*>(pa + lay.keys[par]);
+    lp.frame_gbuf = L.cur_gbuf ? reinterpret_cast<float*>(pa + lay.gbuf) : nullptr;
+    for (int side = 0; side < 2; ++side)
+        if (L.nb[side] >= 0) lp.sig_round[side] = &peer_hdr(ctx, L.nb[side])->round_done[1 - side];
+    lp.sig_round_value = g + 1u;
+    if (L.rank != 0) {
+        lp.sig_frame = &hdr_of(pa)->frame_done[L.rank];
+        lp.sig_frame_value = t + 1u;
+    }
+    const int per_sm = trace_stream_max_ctas_per_sm(ctx->link_tp);
+    if (per_sm < 1) return fail(ctx, SDFGPU_ERR_CUDA, "the trace kernel does not fit on an SM");
+    timing_mark(ctx);
+    CK(ctx, launch_trace_stream(ctx->link_tp, lp, ctx->sm_count * per_sm, ctx->stream));
+    ctx->launches++;
+    timing_mark(ctx);
+    return SDFGPU_OK;
+}
+
+// every round of the frame (or its one streaming launch)
+int sdfgpu::link_trace_issue(sdfgpu_ctx* ctx) {
+    if (ctx->link.stream) return link_trace_stream(ctx);
+    for (uint32_t k = 0; k < ctx->link.world; ++k) {
+        const int rc = link_trace_round(ctx);
+        if (rc != SDFGPU_OK) return rc;
+    }
+    return SDFGPU_OK;
+}
+
 int sdfgpu::link_trace_end(sdfgpu_ctx* ctx, uint8_t* rgba8, float* depth, float* gbuf, bool sync) {
     LinkState& L = ctx->link;
     if (!L.on || !L.in_frame) return fail(ctx, SDFGPU_ERR_STATE, "no linked frame in flight");
@@ -362,6 +444,10 @@ int sdfgpu::link_trace_end(sdfgpu_ctx* ctx, uint8_t* rgba8, float* depth, float*
             CK(ctx, cudaMemcpy(&to, &hdr_of(L.arena)->timed_out, 4, cudaMemcpyDeviceToHost));
             if (to) return fail(ctx, SDFGPU_ERR_STATE, "a wait on another rank's flag timed out (ranks out of step?)");
         }
+        if (L.stream && L.timed_out_host && *reinterpret_cast<volatile uint32_t*>(L.timed_out_host)) {
+            *L.timed_out_host = 0u;
+            return fail(ctx, SDFGPU_ERR_STATE, "the trace kernel waited %u ms for its neighbours' rays and gave up (ranks out of step?)", L.timeout_ms);
+        }
     }
     return SDFGPU_OK;
 }
@@ -387,6 +473,7 @@ void sdfgpu::link_free(sdfgpu_ctx* ctx) {
         }
     }
     (void)cudaFree(L.arena);
+    if (L.timed_out_host) (void)cudaFreeHost(L.timed_out_host);
     for (cudaEvent_t e : L.timing_events) (void)cudaEventDestroy(e);
     (void)cudaGetLastError();
     L = LinkState();
@@ -404,17 +491,34 @@ SDFGPU_API int sdfgpu_link_export(sdfgpu_ctx* ctx, uint32_t rank, uint32_t world
     if (has_peers(ctx)) return fail(ctx, SDFGPU_ERR_STATE, "neighbours already attached with sdfgpu_ipc_attach");
     set_device(ctx);
     LinkState& L = ctx->link;
+    if (flags & ~(SDFGPU_LINK_GBUF | SDFGPU_LINK_HALO_PUSH | SDFGPU_LINK_ROUNDS | SDFGPU_LINK_STREAM))
+        return fail(ctx, SDFGPU_ERR_INVALID, "unknown link flags 0x%x", flags);
+    if (ctx->opt_link_halo_push) flags |= SDFGPU_LINK_HALO_PUSH;
+    if (ctx->opt_link_trace_mode == 1) flags |= SDFGPU_LINK_ROUNDS;
+    if (ctx->opt_link_trace_mode == 2) flags |= SDFGPU_LINK_STREAM;
+    if ((flags & SDFGPU_LINK_ROUNDS) && (flags & SDFGPU_LINK_STREAM)) return fail(ctx, SDFGPU_ERR_INVALID, "SDFGPU_LINK_ROUNDS and SDFGPU_LINK_STREAM exclude each other");
     L.rank = rank; L.world = world;
     L.max_pixels = max_width * max_height;
     L.want_gbuf = (flags & SDFGPU_LINK_GBUF) != 0;
+    L.halo_push = (flags & SDFGPU_LINK_HALO_PUSH) != 0;
+    L.timeout_ms = (uint32_t)ctx->opt_link_timeout_ms;
     const ArenaLayout lay = arena_layout(L.max_pixels, L.want_gbuf);
     CK(ctx, cudaMalloc(&L.arena, lay.total));
     L.arena_bytes = lay.total;
-    CK(ctx, cudaMemsetAsync(L.arena, 0, sizeof(ArenaHeader), ctx->stream));
+    // header and ray queues: the stream trace recognises an entry by its tag, which is never 0
+    CK(ctx, cudaMemsetAsync(L.arena, 0, lay.keys[0], ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaHostAlloc(reinterpret_cast<void**>(&L.timed_out_host), sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+    *L.timed_out_host = 0u;
     LinkBlob b;
     memset(&b, 0, sizeof b);
     b.magic = LINK_MAGIC; b.rank = rank; b.world = world; b.flags = flags;
+    {
+        cudaDeviceProp prop;
+        CK(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+        static_assert(sizeof prop.uuid == sizeof b.uuid, "device uuid is 16 bytes");
+        memcpy(b.uuid, &prop.uuid, sizeof b.uuid);
+    }
     b.pid = (uint64_t)getpid();
     b.device = (uint32_t)ctx->device;
     b.z_begin = ctx->z_begin; b.z_end = ctx->z_end; b.z_lo = ctx->z_lo; b.z_hi = ctx->z_hi;
@@ -449,12 +553,23 @@ SDFGPU_API int sdfgpu_link_attach(sdfgpu_ctx* ctx, const void* blobs, uint32_t w
         if (b.magic != LINK_MAGIC || b.rank != r || b.world != world) return fail(ctx, SDFGPU_ERR_INVALID, "blob %u is not rank %u's", r, r);
         if (b.max_pixels != L.max_pixels || ((b.flags ^ (L.want_gbuf ? SDFGPU_LINK_GBUF : 0u)) & SDFGPU_LINK_GBUF))
             return fail(ctx, SDFGPU_ERR_INVALID, "rank %u was exported with other frame parameters", r);
+        if (((b.flags & SDFGPU_LINK_HALO_PUSH) != 0) != L.halo_push)
+            return fail(ctx, SDFGPU_ERR_INVALID, "rank %u was exported with another halo mode (SDFGPU_LINK_HALO_PUSH)", r);
         if (memcmp(b.dims, ctx->dims, sizeof b.dims)) return fail(ctx, SDFGPU_ERR_INVALID, "rank %u has another grid", r);
         if (b.z_begin != z || b.z_end <= b.z_begin) return fail(ctx, SDFGPU_ERR_INVALID, "the slabs must tile the grid in rank order, none empty (rank %u owns [%u,%u))", r, b.z_begin, b.z_end);
         z = b.z_end;
     }
     if (z != ctx->dims[2]) return fail(ctx, SDFGPU_ERR_INVALID, "the slabs end at slice %u of %u", z, ctx->dims[2]);
     if (bs[L.rank].p_arena != (uint64_t)(uintptr_t)L.arena) return fail(ctx, SDFGPU_ERR_INVALID, "blob %u is not this handle's", L.rank);
+    // the stream trace's kernels wait for each other: every rank needs a device of its own
+    bool distinct = true, any_rounds = false, any_stream = false;
+    for (uint32_t r = 0; r < world; ++r) {
+        any_rounds |= (bs[r].flags & SDFGPU_LINK_ROUNDS) != 0;
+        any_stream |= (bs[r].flags & SDFGPU_LINK_STREAM) != 0;
+        for (uint32_t q = 0; q < r; ++q) distinct &= memcmp(bs[r].uuid, bs[q].uuid, sizeof bs[r].uuid) != 0;
+    }
+    if (any_stream && (!distinct || any_rounds))
+        return fail(ctx, SDFGPU_ERR_INVALID, "SDFGPU_LINK_STREAM needs every rank on a device of its own, and no rank asking for SDFGPU_LINK_ROUNDS");
     const uint64_t pid = (uint64_t)getpid();
     auto map = [&](const LinkBlob& b, uint64_t raw, const cudaIpcMemHandle_t& h, void** out, bool* ipc) -> int {
         *ipc = false;
@@ -487,7 +602,7 @@ SDFGPU_API int sdfgpu_link_attach(sdfgpu_ctx* ctx, const void* blobs, uint32_t w
         rc = map(bs[r], bs[r].p_arena, bs[r].h_arena, &p, &L.peer_arena_ipc[r]);
         L.peer_arena[r] = (unsigned char*)p;
     }
-    for (int side = 0; side < 2 && rc == SDFGPU_OK; ++side) {
+    for (int side = 0; side < 2 && rc == SDFGPU_OK && L.halo_push; ++side) {  // the neighbours' volumes: targets of the halo push
         if (L.nb[side] < 0) continue;
         const LinkBlob& b = bs[L.nb[side]];
         void *p0 = nullptr, *p1 = nullptr;
@@ -501,22 +616,28 @@ SDFGPU_API int sdfgpu_link_attach(sdfgpu_ctx* ctx, const void* blobs, uint32_t w
     }
     if (rc != SDFGPU_OK) {
         const std::string why = ctx->err;
-        const uint32_t rank = L.rank, w = L.world, mp = L.max_pixels;
-        const bool gb = L.want_gbuf;
+        const uint32_t rank = L.rank, w = L.world, mp = L.max_pixels, to = L.timeout_ms;
+        const bool gb = L.want_gbuf, hp = L.halo_push;
         unsigned char* arena = L.arena;
         const size_t ab = L.arena_bytes;
+        uint32_t* toh = L.timed_out_host;
         L.arena = nullptr;  // keep the exported arena: the caller may retry or detach
+        L.timed_out_host = nullptr;
         L.on = true;        // so that link_free clears the neighbour pointers
         link_free(ctx);
-        L.arena = arena; L.arena_bytes = ab; L.rank = rank; L.world = w; L.max_pixels = mp; L.want_gbuf = gb;
+        L.arena = arena; L.arena_bytes = ab; L.rank = rank; L.world = w; L.max_pixels = mp; L.want_gbuf = gb; L.halo_push = hp;
+        L.timed_out_host = toh; L.timeout_ms = to;
         ctx->err = why;
         return rc;
     }
     L.memops = wait32() != nullptr && ctx->opt_link_wait != 1;
+    L.stream = distinct && !any_rounds && world > 1;
     L.on = true;
-    // the slab is filled and traced as [z_begin, z_end); the halo slices come from the neighbours
-    ctx->opt_fill_halo = 0;
-    if (ctx->known_step != 0) ctx->known_step = -1;
+    // push mode: the slab is filled as [z_begin, z_end) and the halo slices come from the neighbours; otherwise every
+    // rank fills its stored slices [z_lo, z_hi), halo slices included
+    const int fill_halo = L.halo_push ? 0 : 1;
+    if (ctx->opt_fill_halo != fill_halo && ctx->known_step != 0) ctx->known_step = -1;
+    ctx->opt_fill_halo = fill_halo;
     return SDFGPU_OK;
 }
 
@@ -532,8 +653,7 @@ SDFGPU_API int sdfgpu_trace_linked(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, ui
     if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
     int rc = link_trace_begin(ctx, cam, width, height, want_gbuf != 0);
     if (rc != SDFGPU_OK) return rc;
-    for (uint32_t k = 0; k < ctx->link.world; ++k)
-        if ((rc = link_trace_round(ctx)) != SDFGPU_OK) { ctx->link.in_frame = false; return rc; }
+    if ((rc = link_trace_issue(ctx)) != SDFGPU_OK) { ctx->link.in_frame = false; return rc; }
     return link_trace_end(ctx, rgba8, depth, gbuf, true);
 }
 
@@ -545,8 +665,7 @@ SDFGPU_API int sdfgpu_trace_linked_device(sdfgpu_ctx* ctx, const sdfgpu_camera* 
     if (gbuf_dev) *gbuf_dev = nullptr;
     int rc = link_trace_begin(ctx, cam, width, height, want_gbuf != 0);
     if (rc != SDFGPU_OK) return rc;
-    for (uint32_t k = 0; k < ctx->link.world; ++k)
-        if ((rc = link_trace_round(ctx)) != SDFGPU_OK) { ctx->link.in_frame = false; return rc; }
+    if ((rc = link_trace_issue(ctx)) != SDFGPU_OK) { ctx->link.in_frame = false; return rc; }
     if ((rc = link_trace_end(ctx, nullptr, nullptr, nullptr, false)) != SDFGPU_OK) return rc;
     if (ctx->link.rank == 0) {
         if (rgba8_dev) *rgba8_dev = reinterpret_cast<uint8_t*>(ctx->rgba8_dev);
@@ -752,11 +871,18 @@ SDFGPU_API int sdfgpu_group_trace(sdfgpu_group* g, const sdfgpu_camera* cam, uin
             return gfail(g, c, rc);
         }
     }
-    for (size_t k = 0; k < g->ranks.size(); ++k)
+    if (g->ranks[0]->link.stream) {  // every rank on its own device: one launch each, side by side
         for (sdfgpu_ctx* c : g->ranks) {
-            const int rc = link_trace_round(c);
+            const int rc = link_trace_stream(c);
             if (rc != SDFGPU_OK) return gfail(g, c, rc);
         }
+    } else {
+        for (size_t k = 0; k < g->ranks.size(); ++k)
+            for (sdfgpu_ctx* c : g->ranks) {
+                const int rc = link_trace_round(c);
+                if (rc != SDFGPU_OK) return gfail(g, c, rc);
+            }
+    }
     for (size_t r = g->ranks.size(); r-- > 0;) {  // the presenter (rank 0) last: its end synchronises
         sdfgpu_ctx* c = g->ranks[r];
         const int rc = link_trace_end(c, rgba8, depth, gbuf, r == 0);

@@ -110,6 +110,15 @@ struct LinkState {
     uint32_t frame_epoch = 0;        // linked traces started
     uint32_t round_epoch = 0;        // global trace rounds started (world rounds per frame)
     bool memops = false;             // cuStreamWaitValue32 usable: waits are stream memory operations, else a spin kernel
+    // halo slices: false (default) -- every rank fills its two halo slices itself (sample() is a pure function of the
+    // position, src/sdf/mod.rs:43, so they equal the neighbours' boundary slices bit for bit and the fill needs no
+    // exchange at all); true (SDFGPU_LINK_HALO_PUSH) -- the neighbours push them over NVLink
+    bool halo_push = false;
+    // trace: true -- one streaming kernel per rank and frame (needs every rank on a device of its own: the kernels
+    // wait for each other); false -- `world` rounds of the round kernel
+    bool stream = false;
+    uint32_t* timed_out_host = nullptr;  // mapped host word the stream kernel sets when it gives up waiting
+    uint32_t timeout_ms = 20000;
     // frame in flight (begin / round / end are separate so that a single-process group can interleave ranks)
     uint32_t cur_w = 0, cur_h = 0, cur_round = 0;
     bool cur_gbuf = false;
@@ -231,6 +240,9 @@ struct sdfgpu_ctx {
     sdfgpu::TraceParams link_tp;  // trace parameters of the linked frame in flight
     bool fill_boundary_first = false;  // the next run_fill is the whole-slab launch of a linked fill_all
     int opt_link_wait = 0;             // 0: stream memory operations when the driver has them, 1: spin-wait kernels
+    int opt_link_halo_push = 0;        // before sdfgpu_link_export: 1 = SDFGPU_LINK_HALO_PUSH
+    int opt_link_trace_mode = 0;       // before sdfgpu_link_export: 0 auto, 1 rounds (SDFGPU_LINK_ROUNDS), 2 stream
+    int opt_link_timeout_ms = 20000;
     uint32_t* trace_counters = nullptr;  // work_head, ctas_done of the round kernel (un-linked handles)
 };
 
@@ -267,6 +279,8 @@ int link_fill_all_fused(sdfgpu_ctx* ctx, FillParams* p);                  // fil
 int link_fill_all_pushed(sdfgpu_ctx* ctx);                                // after that launch: flag-ordered DMA push + signal
 int link_trace_begin(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t w, uint32_t h, bool want_gbuf);
 int link_trace_round(sdfgpu_ctx* ctx);
+int link_trace_stream(sdfgpu_ctx* ctx);  // LinkState::stream: the whole frame of this rank in one launch
+int link_trace_issue(sdfgpu_ctx* ctx);   // every round, or the one streaming launch
 int link_trace_end(sdfgpu_ctx* ctx, uint8_t* rgba8, float* depth, float* gbuf, bool sync);
 void link_free(sdfgpu_ctx* ctx);
 

@@ -78,6 +78,23 @@ struct LinkParams {
     uint32_t sig_round_value;
     uint32_t* sig_frame;             // the presenter's "rank r finished the frame" flag (last round only), or null
     uint32_t sig_frame_value;
+    // ---- stream mode (trace.cu: trace_stream_kernel): ONE launch per rank and frame instead of `world` rounds.  The
+    // warps first work through the tiles, then poll the in-queues, so a handed-over ray continues as soon as it has
+    // arrived instead of at the next round.  A queue entry is two float4 -- (x, y, z, tag), (t, pixel, steps, tag) --
+    // and is complete when both tags equal `epoch`: no fence, no count between producer and consumer.  A rank closes
+    // an out-queue with its final count once nothing can enter it any more: its tiles are done and the in-queue on
+    // the other side (rays keep their z direction) is closed and worked off.
+    uint32_t epoch;                         // tag of this frame's entries (frame number + 1: never 0, the memset value)
+    uint32_t timeout_ms;                    // a rank that waits longer for its neighbours gives up (sets *timed_out)
+    uint32_t* tiles_done;                   // local counters, reset by the last CTA: tile units finished,
+    uint32_t* in_head;                      //   [2] in-queue units claimed,
+    uint32_t* in_done;                      //   [2] in-queue units finished,
+    uint32_t* sent_final;                   //   [2] out-queue closed
+    uint32_t* timed_out;                    // mapped host memory
+    const unsigned long long* in_final[2];  // own memory, written by the neighbour: epoch << 32 | entries of its out-queue
+    unsigned long long* out_final[2];       // the same word of the neighbours (peer memory)
+    const float4* in_q[2];                  // entries, own memory; null without a neighbour on that side
+    float4* out_q[2];                       // peer memory
 };
 
 // launchers (fill.cu / trace.cu).  `program`: dev::PROG_INTERPRET or dev::PROG_DEMO (built in)
@@ -111,6 +128,8 @@ cudaError_t launch_set_const(float4* dst, size_t n_texels, float v, int grid_cta
 cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s);
 cudaError_t launch_trace_rounds(const TraceParams& p, const LinkParams& l, int grid_ctas, cudaStream_t s);
 int trace_rounds_max_ctas_per_sm(const TraceParams& p);
+cudaError_t launch_trace_stream(const TraceParams& p, const LinkParams& l, int grid_ctas, cudaStream_t s);
+int trace_stream_max_ctas_per_sm(const TraceParams& p);
 cudaError_t launch_signal(uint32_t* const* flags, const uint32_t* values, int n, cudaStream_t s);  // fence.sys + stores (peer flags)
 cudaError_t launch_spin_wait(const uint32_t* flag, uint32_t value, uint32_t* timed_out, cudaStream_t s);  // fallback for cuStreamWaitValue32
 cudaError_t launch_extract_dist(const float4* tex0, float* dist, size_t n, int grid, cudaStream_t s);

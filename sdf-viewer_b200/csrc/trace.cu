@@ -799,6 +799,312 @@ __global__ void __launch_bounds__(256) trace_rounds_kernel(const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Stream kernel: the Z-sharded trace in ONE launch per rank.  Same ownership rule, same arithmetic and the same
+// frame as the round kernel, but no round structure: the persistent warps work through this rank's tiles and then
+// poll the in-queues, so a ray that a neighbour hands over continues as soon as its entry has arrived -- the ranks
+// form a pipeline along z instead of taking turns.  Producer and consumer share no counter: an entry is two 16-byte
+// stores, each carrying the frame's tag, and the consumer works on a 32-entry unit when all its tags are there (16-byte
+// stores are not torn on NVLink).  A queue is closed by its producer's final count (LinkParams::out_final).
+
+__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_volatile_f4(float4* p, float x, float y, float z, float w) {
+    asm volatile("st.volatile.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
+// lane 0 of any warp, whenever something completed: close the out-queue of direction `dir` (0 down, 1 up) if nothing
+// can enter it any more.  Rays keep the sign of their z direction, so what leaves downwards started here or came
+// from above (in-queue 1), and the other way round.
+__device__ __forceinline__ void stream_maybe_close(const LinkParams& L, int dir, uint32_t n_tile_units) {
+    if (!L.out_final[dir]) return;
+    if (ld_volatile_u32(L.sent_final + dir)) return;
+    if (ld_volatile_u32(L.tiles_done) != n_tile_units) return;
+    const int src = 1 - dir;
+    if (L.in_q[src]) {
+        const unsigned long long f = ld_volatile_u64(L.in_final[src]);
+        if ((uint32_t)(f >> 32) != L.epoch) return;
+        if (ld_volatile_u32(L.in_done + src) != ((uint32_t)f + 31u) / 32u) return;
+    }
+    // (the counters above were incremented after the units' reservations in out_count had returned)
+    if (atomicExch(L.sent_final + dir, 1u) != 0u) return;
+    const uint32_t c = ld_volatile_u32(L.out_count + dir);
+    *reinterpret_cast<volatile unsigned long long*>(L.out_final[dir]) = ((unsigned long long)L.epoch << 32) | c;
+}
+
+template <bool SNAP, bool LINEAR>
+__global__ void __launch_bounds__(256, 4) trace_stream_kernel(const __grid_constant__ TraceParams P,
+                                                           const __grid_constant__ LinkParams L) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const Vol v0{P.tex0, (int)P.W, (int)P.H, (int)P.D, (int)P.z_lo, (int)P.z_hi};
+    const Vol v1{P.tex1, (int)P.W, (int)P.H, (int)P.D, (int)P.z_lo, (int)P.z_hi};
+
+    // ---- tile units, as in round 0 of the round kernel: 8 x 4 tiles inside the screen rectangle of the box, then
+    // (presenter only) runs of OUTSIDE_RUN tiles outside it
+    constexpr uint32_t OUTSIDE_RUN = 16u;
+    const uint32_t tiles_y4 = (P.height + 3u) / 4u;
+    const uint32_t rw = P.rect[2] - P.rect[0], ry0 = min(P.rect[1] * 2u, tiles_y4);
+    const uint32_t rh4 = min(P.rect[3] * 2u, tiles_y4) - ry0;
+    const uint32_t n_heavy = rw * rh4;
+    const uint32_t n_outside = P.tiles_x * tiles_y4 - n_heavy;
+    const uint32_t n_units = n_heavy + (L.is_presenter ? (n_outside + OUTSIDE_RUN - 1u) / OUTSIDE_RUN : 0u);
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t capacity = (L.max_pixels + 31u) & ~31u;  // entries per queue buffer
+    const uint32_t tag = L.epoch;
+    constexpr uint32_t NO_TICKET = 0xffffffffu;
+
+    uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // tickets held -- a unit of the in-queue from below / from above -- with the lanes of the unit already traced, and
+    // whether the unit has been seen incomplete before
+    uint32_t pend0 = NO_TICKET, pend1 = NO_TICKET, mask0 = 0u, mask1 = 0u;
+    bool seen0 = false, seen1 = false;
+    uint32_t sleep_ns = 32u;
+    unsigned long long idle_since = 0ull;
+
+    for (;;) {
+        Ray r;
+        r.hx = r.hy = r.hz = r.t = 0.0f; r.it = 0;
+        uint32_t px = 0;
+        float rdx = 0.f, rdy = 0.f, rdz = 0.f;
+        int status = RS_NONE;
+        bool marching = false;
+        float code = -3.0f;
+        int src = -1;  // -1: a tile unit; 0 / 1: a unit of the in-queue from below / above
+        uint32_t src_valid = 0xffffffffu;  // lanes of that unit that exist (all, unless the queue is closed within it)
+
+        // ---- the in-queues first: a ray that has already travelled is on some other rank's critical path.  Units are
+        // handed out by TICKET, one atomicAdd (verifying a unit first and claiming it with a compare-and-swap hands out
+        // one unit per memory round trip: measured, 12 ms for a frame whose every ray crosses a slab face).  A warp takes
+        // a ticket where the head unit has begun to arrive, or where the queue is closed and not handed out yet.  It
+        // holds at most one ticket per queue and looks at both, so a ticket for entries that are still far away keeps
+        // it neither from the other queue nor from the tiles: every entry that has arrived belongs to a warp that is
+        // polling or busy with a finite unit.  A complete unit is traced at once; an incomplete one the second time
+        // the warp finds it so (its stragglers must not wait for the queue to close: they are the frame's tail), the
+        // rest of it in a later pass.  A ticket beyond the final count is void.  Lane q looks after queue q.
+        bool got = false, open = false;
+        const bool tile_next = unit < n_units;
+        if (!tile_next || unit < n_heavy) {  // (not between the presenter's store-only runs: they are short)
+            uint32_t cnt = 0, fin = 0, tk = lane ? pend1 : pend0, msk = lane ? mask1 : mask0, op = 0u, pre = 0u, valid = 0xffffffffu;
+            if (lane < 2u && L.in_q[lane]) {
+                const uint32_t q = lane;
+                op = 1u;
+                const unsigned long long f = ld_volatile_u64(L.in_final[q]);
+                fin = (uint32_t)(f >> 32) == tag ? 1u : 0u;
+                cnt = (uint32_t)f;
+                if (tk == NO_TICKET) {
+                    const uint32_t h = ld_volatile_u32(L.in_head + q);
+                    bool take;
+                    if (fin) take = h * 32u < cnt;
+                    else take = h * 32u < capacity && __float_as_uint(ld_volatile_f4(L.in_q[q] + 2u * (size_t)(h * 32u)).w) == tag;
+                    if (take) { tk = atomicAdd(L.in_head + q, 1u); msk = 0u; }
+                    else if (fin) op = 0u;  // closed and handed out
+                }
+                if (tk != NO_TICKET && fin) {
+                    const uint32_t base = tk * 32u;
+                    valid = base >= cnt ? 0u : (cnt - base >= 32u ? 0xffffffffu : (1u << (cnt - base)) - 1u);
+                    if (valid == 0u) {  // void: the head is beyond the count
+                        tk = NO_TICKET; op = 0u;
+                    } else if ((msk & valid) == valid) {  // the queue was closed inside this unit, after its last entry was traced
+                        if (atomicAdd(L.in_done + q, 1u) + 1u == (cnt + 31u) / 32u) stream_maybe_close(L, 1 - (int)q, n_units);
+                        tk = NO_TICKET; msk = 0u;
+                    }
+                }
+                if (tk != NO_TICKET && tk * 32u < capacity)  // the first entry not traced yet: has it arrived?
+                    pre = __float_as_uint(ld_volatile_f4(L.in_q[q] + 2u * (size_t)(tk * 32u + (uint32_t)__ffs((int)~msk) - 1u)).w) == tag ? 1u : 0u;
+            }
+            pend0 = __shfl_sync(0xffffffffu, tk, 0); pend1 = __shfl_sync(0xffffffffu, tk, 1);
+            mask0 = __shfl_sync(0xffffffffu, msk, 0); mask1 = __shfl_sync(0xffffffffu, msk, 1);
+            open = __any_sync(0xffffffffu, op != 0u);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (got || !__shfl_sync(0xffffffffu, pre, q)) continue;
+                const uint32_t t_q = q ? pend1 : pend0, m_q = q ? mask1 : mask0;
+                const uint32_t valid_q = __shfl_sync(0xffffffffu, valid, q);
+                const uint32_t e = t_q * 32u + lane;
+                const bool want = ((valid_q & ~m_q) >> lane) & 1u;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                bool ready = false;
+                if (want) {
+                    a = ld_volatile_f4(L.in_q[q] + 2u * (size_t)e);
+                    b = ld_volatile_f4(L.in_q[q] + 2u * (size_t)e + 1u);
+                    ready = __float_as_uint(a.w) == tag && __float_as_uint(b.w) == tag;
+                }
+                const uint32_t ready_lanes = __ballot_sync(0xffffffffu, ready);
+                const bool complete = __ballot_sync(0xffffffffu, want && !ready) == 0u;
+                const bool seen = q ? seen1 : seen0;
+                if (ready_lanes == 0u) continue;
+                if (!complete && (!seen || (!tile_next && sleep_ns < 512u))) {
+                    // give the rest of the unit until the next look (a warp without tiles: a few looks, about 5 us)
+                    if (q) seen1 = true; else seen0 = true;
+                    continue;
+                }
+                got = true; src = q; src_valid = valid_q;
+                if (q) { mask1 = m_q | ready_lanes; seen1 = false; } else { mask0 = m_q | ready_lanes; seen0 = false; }
+                if (ready) {
+                    r.hx = a.x; r.hy = a.y; r.hz = a.z; r.t = b.x;
+                    px = __float_as_uint(b.y); r.it = (int)__float_as_uint(b.z);
+                    float rox, roy, roz;
+                    (void)ray_setup(P, px % P.width, px / P.width, rdx, rdy, rdz, rox, roy, roz);  // the direction only
+                    marching = true;
+                }
+            }
+        }
+
+        if (got) {
+            sleep_ns = 32u; idle_since = 0ull;
+        } else if (tile_next) {
+            if (unit >= n_heavy) {  // a run of tiles no ray of which enters the box: miss code -3, no arithmetic
+                const uint32_t b0 = (unit - n_heavy) * OUTSIDE_RUN, b1 = min(b0 + OUTSIDE_RUN, n_outside);
+                const uint32_t n_top = ry0 * P.tiles_x, side = P.tiles_x - rw;
+                for (uint32_t bb = b0; bb < b1; ++bb) {
+                    uint32_t b = bb, tx, ty;
+                    if (b < n_top) {
+                        tx = b % P.tiles_x; ty = b / P.tiles_x;
+                    } else if (b - n_top < rh4 * side) {
+                        b -= n_top;
+                        const uint32_t k = b % side;
+                        ty = ry0 + b / side; tx = k < P.rect[0] ? k : k + rw;
+                    } else {
+                        b -= n_top + rh4 * side;
+                        tx = b % P.tiles_x; ty = ry0 + rh4 + b / P.tiles_x;
+                    }
+                    const uint32_t i = tx * 8u + (lane & 7u), j = ty * 4u + (lane >> 3);
+                    if (i < P.width && j < P.height) finish_pixel<SNAP, LINEAR>(P, L, v0, v1, j * P.width + i, false, -3.0f, r);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    if (atomicAdd(L.tiles_done, 1u) + 1u == n_units) { stream_maybe_close(L, 0, n_units); stream_maybe_close(L, 1, n_units); }
+                    unit = n_warps + atomicAdd(L.work_head, 1u);
+                }
+                unit = __shfl_sync(0xffffffffu, unit, 0);
+                continue;
+            }
+            const uint32_t tx = P.rect[0] + unit % rw, ty = ry0 + unit / rw;
+            const uint32_t i = tx * 8u + (lane & 7u), j = ty * 4u + (lane >> 3);
+            if (i < P.width && j < P.height) {
+                px = j * P.width + i;
+                float rox, roy, roz;
+                if (!ray_setup(P, i, j, rdx, rdy, rdz, rox, roy, roz)) {
+                    if (L.is_presenter) status = RS_MISS;  // no fragment: every rank sees the same test, one writes
+                } else {
+                    r.hx = rox; r.hy = roy; r.hz = roz;
+                    marching = true;
+                }
+            }
+        } else {
+            // nothing to do right now.  Every way out of the loop passes the close test: the last warp to learn that an
+            // in-queue is closed (and empty) may be the one that has to close the out-queue behind it
+            if (lane == 0) { stream_maybe_close(L, 0, n_units); stream_maybe_close(L, 1, n_units); }
+            if (!open) break;  // both in-queues are closed and handed out, no ticket pending: this warp is done
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (idle_since == 0ull) idle_since = now;
+            if (now - idle_since > (unsigned long long)L.timeout_ms * 1000000ull) {
+                if (lane == 0) *reinterpret_cast<volatile uint32_t*>(L.timed_out) = 1u;
+                break;
+            }
+            __nanosleep(sleep_ns);
+            if (sleep_ns < 1024u) sleep_ns *= 2u;
+            continue;
+        }
+
+        // ---- sdfRaycast, material.frag:92-128 (the round kernel's loop)
+        const int max_steps = (int)P.max_steps;
+        CellCache cell;
+        cell.x0 = cell.y0 = cell.z0 = __int_as_float(0x7fc00000);
+        cell.c000 = cell.c100 = cell.c010 = cell.c110 = cell.c001 = cell.c101 = cell.c011 = cell.c111 = 0.0f;
+        const bool started_here = src < 0;
+        while (__ballot_sync(0xffffffffu, marching)) {
+            if (marching) {
+                float ax, ay, az;
+                tex_coord<SNAP>(P, v0, r.hx, r.hy, r.hz, ax, ay, az);
+                const int z = lower_z_tap<LINEAR>((int)P.D, az);
+                const int go = z < (int)L.own_z0 ? RS_DOWN : (z >= (int)L.own_z1 ? RS_UP : 0);
+                if (go && started_here && r.it == 0) {
+                    status = RS_NONE; marching = false;   // a ray that STARTS elsewhere is started by its owner
+                } else if (r.it >= max_steps - 1) {                                                  // :99-102
+                    code = -1.0f; status = RS_MISS; marching = false;
+                } else if (oob_dist(P.clip_min, P.clip_max, r.hx, r.hy, r.hz) > 1e-4f) {             // :106-109
+                    code = -2.0f; status = RS_MISS; marching = false;
+                } else if (go) {
+                    status = go; marching = false;
+                } else {
+                    const float dist = dist_at<LINEAR>(v0, ax, ay, az, cell) - 1e-1f;                // :112, :59
+                    if (dist < 1e-5f) {                                                              // :117-121
+                        code = r.t; status = RS_HIT; marching = false;
+                    } else {
+                        r.t += dist;                                                                 // :124
+                        r.hx += rdx * dist; r.hy += rdy * dist; r.hz += rdz * dist;                  // :125
+                        ++r.it;
+                    }
+                }
+            }
+        }
+
+        if (status == RS_HIT || status == RS_MISS) finish_pixel<SNAP, LINEAR>(P, L, v0, v1, px, status == RS_HIT, code, r);
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {
+            const bool go = status == (dir ? RS_UP : RS_DOWN);
+            const uint32_t m = __ballot_sync(0xffffffffu, go);
+            if (m == 0u) continue;
+            uint32_t base = 0;
+            if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(L.out_count + dir, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (go && L.out_q[dir]) {
+                const uint32_t e = base + __popc(m & ((1u << lane) - 1u));
+                float4* dst = L.out_q[dir] + 2u * (size_t)e;
+                st_volatile_f4(dst, r.hx, r.hy, r.hz, __uint_as_float(tag));
+                st_volatile_f4(dst + 1, r.t, __uint_as_float(px), __uint_as_float((uint32_t)r.it), __uint_as_float(tag));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            // (the unit's reservations in out_count have been performed: their return values were used above.  No fence
+            // here -- it would wait for the unit's pixel stores to cross NVLink)
+            if (src < 0) {
+                if (atomicAdd(L.tiles_done, 1u) + 1u == n_units) { stream_maybe_close(L, 0, n_units); stream_maybe_close(L, 1, n_units); }
+                unit = n_warps + atomicAdd(L.work_head, 1u);
+            } else if ((((src ? mask1 : mask0) & src_valid) == src_valid)) {
+                // every entry of the unit has been traced; the unit that completes a closed in-queue closes the out-queue
+                // its rays travel on
+                const uint32_t done = atomicAdd(L.in_done + src, 1u) + 1u;
+                const unsigned long long f = ld_volatile_u64(L.in_final[src]);
+                if ((uint32_t)(f >> 32) == tag && done == ((uint32_t)f + 31u) / 32u) stream_maybe_close(L, 1 - src, n_units);
+            }
+        }
+        if (src < 0) {
+            unit = __shfl_sync(0xffffffffu, unit, 0);
+        } else if (((src ? mask1 : mask0) & src_valid) == src_valid) {  // the ticket is used up
+            if (src) { pend1 = NO_TICKET; mask1 = 0u; } else { pend0 = NO_TICKET; mask0 = 0u; }
+        }
+    }
+
+    // ---- the last CTA to finish resets the counters and tells the neighbours and the presenter.  The CTA's peer
+    // stores of finished pixels are ordered before thread 0's system fence by the barrier.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(L.ctas_done, 1u) + 1u == gridDim.x) {
+            *L.work_head = 0u; *L.ctas_done = 0u; *L.tiles_done = 0u;
+            L.in_head[0] = L.in_head[1] = 0u; L.in_done[0] = L.in_done[1] = 0u;
+            L.sent_final[0] = L.sent_final[1] = 0u; L.out_count[0] = L.out_count[1] = 0u;
+            __threadfence_system();
+            if (L.sig_round[0]) *reinterpret_cast<volatile uint32_t*>(L.sig_round[0]) = L.sig_round_value;
+            if (L.sig_round[1]) *reinterpret_cast<volatile uint32_t*>(L.sig_round[1]) = L.sig_round_value;
+            if (L.sig_frame) *reinterpret_cast<volatile uint32_t*>(L.sig_frame) = L.sig_frame_value;
+        }
+    }
+}
+
 // flags in (peer) memory: everything this stream did before is visible system-wide first
 __global__ void signal_kernel(uint32_t* f0, uint32_t v0, uint32_t* f1, uint32_t v1, uint32_t* f2, uint32_t v2, uint32_t* f3,
                               uint32_t v3) {
@@ -902,6 +1208,27 @@ int trace_rounds_max_ctas_per_sm(const TraceParams& p) {
 cudaError_t launch_trace_rounds(const TraceParams& p, const LinkParams& l, int grid, cudaStream_t s) {
     if (p.width == 0 || p.height == 0 || grid <= 0) return cudaSuccess;
     pick_rounds(p)<<<grid, 256, 0, s>>>(p, l);
+    return cudaGetLastError();
+}
+
+static rounds_fn pick_stream(const TraceParams& p) {
+    const bool snap = p.lod != 1.0f, lin = p.filter_linear != 0;
+    return !snap && lin ? trace_stream_kernel<false, true> : !snap ? trace_stream_kernel<false, false>
+           : lin ? trace_stream_kernel<true, true> : trace_stream_kernel<true, false>;
+}
+
+int trace_stream_max_ctas_per_sm(const TraceParams& p) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pick_stream(p), 256, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+cudaError_t launch_trace_stream(const TraceParams& p, const LinkParams& l, int grid, cudaStream_t s) {
+    if (p.width == 0 || p.height == 0 || grid <= 0) return cudaSuccess;
+    pick_stream(p)<<<grid, 256, 0, s>>>(p, l);
     return cudaGetLastError();
 }
 

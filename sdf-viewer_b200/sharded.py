@@ -104,8 +104,9 @@ class ShardedViewer:
     """One rank's part of a Z-sharded SDFViewer.  With world == 1 it is a plain SDFViewer."""
 
     def __init__(self, dims, bb, loading_passes, rank=0, world=1, device=0, group=None, fused=True, linked=True,
-                 max_width=1920, max_height=1080, gbuf=False):
+                 max_width=1920, max_height=1080, gbuf=False, halo_push=False, trace_mode=0):
         self.dims, self.bb, self.rank, self.world, self.device = tuple(dims), bb, rank, world, device
+        self.halo_push, self.trace_mode = halo_push, trace_mode
         self.dist = group  # the torch.distributed module (None when world == 1)
         self.fused = False
         self.linked = False
@@ -142,7 +143,8 @@ class ShardedViewer:
         v, dist, t = self.viewer, self.dist, self._torch
         ok, blob = 1, None
         try:
-            blob = v.link_export(self.rank, self.world, max_width, max_height, gbuf=gbuf)
+            blob = v.link_export(self.rank, self.world, max_width, max_height, gbuf=gbuf, halo_push=self.halo_push,
+                                 trace_mode=self.trace_mode)
         except SdfGpuError:
             ok = 0
         blobs = [None] * self.world

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Camera, Rays, GBUF_FLOATS, LINK_BLOB_BYTES, LINK_GBUF, SdfGpuError, check, check_group  # noqa: F401
+from ._lib import Camera, Rays, GBUF_FLOATS, LINK_BLOB_BYTES, LINK_GBUF, LINK_HALO_PUSH, LINK_ROUNDS, LINK_STREAM, SdfGpuError, check, check_group  # noqa: F401
 
 
 def _f6(bb):
@@ -403,11 +403,13 @@ class SDFViewer:
         return n.value
 
     # ---- linked slabs (multi-GPU behind the C ABI: include/sdfgpu.h "linked slabs")
-    def link_export(self, rank, world, max_width, max_height, gbuf=False):
-        """This rank's link blob (CUDA IPC handles of its volumes and arena); gather the blobs of all ranks."""
+    def link_export(self, rank, world, max_width, max_height, gbuf=False, halo_push=False, trace_mode=0):
+        """This rank's link blob (CUDA IPC handles of its volumes and arena); gather the blobs of all ranks.
+        `halo_push`: the neighbours push the halo slices (default: every rank fills its own); `trace_mode`: 0 auto,
+        1 rounds, 2 stream (include/sdfgpu.h)."""
         buf = C.create_string_buffer(LINK_BLOB_BYTES)
         check(self._lib.sdfgpu_link_export(self._h, int(rank), int(world), int(max_width), int(max_height),
-                                           LINK_GBUF if gbuf else 0, buf, len(buf)), self._h)
+                                           link_flags(gbuf, halo_push, trace_mode), buf, len(buf)), self._h)
         return buf.raw
 
     def link_attach(self, blobs):
@@ -467,6 +469,11 @@ class _RankView(SDFViewer):
         self._h = None
 
 
+def link_flags(gbuf=False, halo_push=False, trace_mode=0):
+    return ((LINK_GBUF if gbuf else 0) | (LINK_HALO_PUSH if halo_push else 0)
+            | {0: 0, 1: LINK_ROUNDS, 2: LINK_STREAM}[int(trace_mode)])
+
+
 class SDFViewerGroup:
     """`SDFViewer` over several GPUs driven by ONE process and one thread, as the reference's scene is
     (scene/mod.rs:22-31,158-225): the grid is sharded along z over `devices`, every call below runs on all of
@@ -482,13 +489,14 @@ class SDFViewerGroup:
         self._tape = None
 
     @classmethod
-    def new_voxels(cls, voxels, bb, loading_passes, devices, max_width=1920, max_height=1080, gbuf=False):
+    def new_voxels(cls, voxels, bb, loading_passes, devices, max_width=1920, max_height=1080, gbuf=False, halo_push=False,
+                   trace_mode=0):
         lib = _lib.load()
         g = C.c_void_p()
         v = (C.c_uint32 * 3)(*[int(x) for x in voxels])
         dv = (C.c_int * len(devices))(*[int(d) for d in devices])
         check_group(lib.sdfgpu_group_create(_f6(bb), v, int(loading_passes), dv, len(devices), int(max_width), int(max_height),
-                                            LINK_GBUF if gbuf else 0, C.byref(g)))
+                                            link_flags(gbuf, halo_push, trace_mode), C.byref(g)))
         return cls(g, bb)
 
     @classmethod

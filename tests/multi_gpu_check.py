@@ -1,5 +1,6 @@
 """Run under torchrun with N >= 2 ranks (one GPU each).  First the default path -- slab handles linked through the
-C ABI (flag-ordered halo pushes, exact ray-hand-off trace; no torch.distributed call after set-up) -- checked against
+C ABI (halo slices filled by their holder or pushed behind flags, exact ray-hand-off trace streamed or in rounds; no
+torch.distributed call after set-up) -- checked against
 the CPU oracle (volumes, halos) and against ONE handle holding the whole grid (frames, bit for bit); then the
 fallbacks (NCCL / IPC halo exchange, sort-last and replicated-volume traces).  tests/test_sharded_gpu.py launches it."""
 import os
@@ -30,13 +31,16 @@ def check_slab(sv, v, full, dims, rank):
             f"rank {rank}: stored slab [{v.z_lo},{v.z_hi}) differs from the oracle (halo exchange, fused={sv.fused})"
 
 
-def check_linked(rank, world, local, dims, w, h, sdf, full, want_its):
-    """The default path.  After ShardedViewer's set-up nothing below calls torch.distributed but the test's own
-    barriers around host-side comparisons."""
-    sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, max_width=w, max_height=h, gbuf=True)
+def check_linked(rank, world, local, dims, w, h, sdf, full, want_its, halo_push=False, trace_mode=0):
+    """The default path (halo slices filled by their holder, one streaming trace kernel per rank) and its variants
+    (halo slices pushed by the neighbours; trace in rounds).  After ShardedViewer's set-up nothing below calls
+    torch.distributed but the test's own barriers around host-side comparisons."""
+    sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, max_width=w, max_height=h, gbuf=True,
+                       halo_push=halo_push, trace_mode=trace_mode)
     assert sv.linked, getattr(sv, "link_error", "linking failed")
     v = sv.viewer
-    assert v.get_info("linked") == 1
+    assert v.get_info("linked") == 1 and v.get_info("link_halo_push") == int(halo_push)
+    assert v.get_info("link_trace_stream") == (0 if trace_mode == 1 else 1)
     its = sv.update(S.SDFDemo())
     sv.commit()
     assert its == want_its
@@ -88,7 +92,9 @@ def check_linked(rank, world, local, dims, w, h, sdf, full, want_its):
             assert np.array_equal(got8, want8) and np.array_equal(got_d.view(np.uint32), np.clip(want_d, 0, 1).view(np.uint32))
     dist.barrier()
     if rank == 0:
-        print(f"linked path ok: world {world}, memops {v.get_info('link_memops')}, {v.get_info('link_round_epoch')} trace rounds")
+        print(f"linked path ok: world {world}, halo {'pushed' if halo_push else 'filled locally'}, trace "
+              f"{'streamed' if v.get_info('link_trace_stream') else 'in rounds'}, memops {v.get_info('link_memops')}, "
+              f"{v.get_info('link_round_epoch')} trace launches")
     sv.close()
 
 
@@ -101,7 +107,10 @@ def main():
     sdf = S.SDFDemo()
     full = orc.Viewer(BB, dims, 2)
     want_its = full.update(orc.Sampler(tape=sdf.tape()))
-    check_linked(rank, world, local, dims, w, h, sdf, full, want_its)
+    check_linked(rank, world, local, dims, w, h, sdf, full, want_its)                                # the default
+    check_linked(rank, world, local, dims, w, h, sdf, full, want_its, halo_push=True, trace_mode=2)  # pushed halos
+    check_linked(rank, world, local, dims, w, h, sdf, full, want_its, halo_push=True, trace_mode=1)  # ... and rounds
+    check_linked(rank, world, local, dims, w, h, sdf, full, want_its, trace_mode=1)
     fused_modes = []
     for fused in (False, True):                # NCCL send/recv exchange, then the fused in-kernel P2P exchange
         sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, fused=fused, linked=False)

@@ -1,7 +1,7 @@
 """Linked slabs (include/sdfgpu.h "multi-GPU: linked slabs") on ONE device: a group shards the grid along z over
 several handles that all live on GPU 0, so the driver's single-GPU box runs the whole protocol -- one-launch
-boundary-first fill with the flag-ordered halo push, the collective update / resample_box / reset, and the exact
-ray-hand-off trace -- and checks it against ONE handle holding the whole grid: volumes bit for bit, frames bit for
+fill (halo slices filled by their holder, or boundary-first with the flag-ordered halo push), the collective
+update / resample_box / reset, and the exact ray-hand-off trace in rounds -- and checks it against ONE handle holding the whole grid: volumes bit for bit, frames bit for
 bit (RGBA8, depth, G-buffer but for the normals).  tests/multi_gpu_check.py runs the same over real peers.
 
 The reference has no multi-GPU path (src/app/scene/sdf/mod.rs:174); what is pinned here is that sharding changes
@@ -40,8 +40,11 @@ def same_frame(got, want, slab_faces, dims):
     assert np.array_equal(n_g.view(np.uint32), n_w.view(np.uint32)), "normals away from slab faces differ"
 
 
-@pytest.mark.parametrize("n,dims,wait_mode", [(2, (48, 40, 36), 0), (3, (40, 36, 50), 0), (2, (32, 32, 33), 1), (4, (36, 32, 33), 0), (5, (33, 31, 64), 0)])
-def test_group_equals_single_handle(S, n, dims, wait_mode):
+@pytest.mark.parametrize("n,dims,wait_mode,halo_push", [(2, (48, 40, 36), 0, False), (2, (48, 40, 36), 0, True), (3, (40, 36, 50), 0, True),
+                                                        (2, (32, 32, 33), 1, True), (2, (32, 32, 33), 1, False), (4, (36, 32, 33), 0, False),
+                                                        (4, (36, 32, 33), 0, True), (5, (33, 31, 64), 0, False)])
+def test_group_equals_single_handle(S, n, dims, wait_mode, halo_push):
+    """halo_push False (default): every rank fills its halo slices itself; True: the neighbours push them."""
     w, h = 200, 150
     sdf = S.SDFDemo()
     with S.SDFViewer.new_voxels(dims, BB, 3) as whole:
@@ -54,10 +57,11 @@ def test_group_equals_single_handle(S, n, dims, wait_mode):
                 v = S.SDFViewer.new_voxels(dims, BB, 3, z_range=zr)
                 v.set_option("link_wait_mode", 1)
                 ranks.append(v)
-            blobs = [v.link_export(r, n, w, h, gbuf=True) for r, v in enumerate(ranks)]
+            blobs = [v.link_export(r, n, w, h, gbuf=True, halo_push=halo_push) for r, v in enumerate(ranks)]
             for v in ranks:
                 v.link_attach(blobs)
             assert all(v.get_info("linked") == 1 and v.get_info("link_memops") == 0 for v in ranks)
+            assert all(v.get_info("link_halo_push") == int(halo_push) and v.get_info("link_trace_stream") == 0 for v in ranks)
             try:
                 run_by_hand(S, ranks, whole, sdf, dims, w, h)
             finally:
@@ -68,61 +72,68 @@ def test_group_equals_single_handle(S, n, dims, wait_mode):
                 for v in ranks:
                     v.close()
             return
-        with S.SDFViewerGroup.new_voxels(dims, BB, 3, [0] * n, w, h, gbuf=True) as g:
+        with S.SDFViewerGroup.new_voxels(dims, BB, 3, [0] * n, w, h, gbuf=True, halo_push=halo_push) as g:
             assert g.size == n and g.dims == dims
-            faces = [r.z_begin for r in g.ranks[1:]]
-            # pass by pass: volumes and frames (lod 4, 2, 1; NEAREST then LINEAR) equal the single handle's
-            sdf2 = S.SDFDemo()
-            for k in range(3):
-                it_w = whole.update(sdf, max_passes=1)
-                it_g = g.update(sdf2, max_passes=1)
-                assert it_w == it_g
-                whole.commit(); g.commit()
-                t0, t1 = whole.download()
-                g0, g1 = g.download()
-                assert np.array_equal(t0.view(np.uint32), g0.view(np.uint32)), f"tex0 differs after pass {k}"
-                assert np.array_equal(t1.view(np.uint32), g1.view(np.uint32)), f"tex1 differs after pass {k}"
-                for cam in cameras(S, w, h):
-                    want8, want_d = whole.trace_rgba8(cam, w, h)
-                    _, _, want_g = whole.trace(cam, w, h, gbuf=True)
-                    same_frame(g.trace(cam, w, h), (want8, want_d, want_g), faces, dims)
-            assert g.loading_state()[0] == 0
-            # a frame without G-buffer through the rgba8 entry point, several frames back to back (key-frame parity)
-            for cam in cameras(S, w, h) * 2:
-                want8, want_d = whole.trace_rgba8(cam, w, h)
-                same_frame(g.trace_rgba8(cam, w, h) + (None,), (want8, want_d, None), faces, dims)
-            # halo slices hold the neighbours' boundary slices
-            for r in g.ranks:
-                check_halos(r, t0, t1, dims)
-            # fill_all (one launch per rank, boundary tiles first) after a reset
-            g.reset(1); whole.reset(1)
-            g.set_tape(sdf.tape()); whole.set_tape(sdf.tape())
-            g.fill_all(); whole.fill_all()
-            g.commit(); whole.commit()
-            t0, t1 = whole.download()
-            g0, g1 = g.download()
-            assert np.array_equal(t0.view(np.uint32), g0.view(np.uint32)) and np.array_equal(t1.view(np.uint32), g1.view(np.uint32))
-            for r in g.ranks:
-                check_halos(r, t0, t1, dims)
-            cam = cameras(S, w, h)[3]
-            same_frame(g.trace_rgba8(cam, w, h) + (None,), whole.trace_rgba8(cam, w, h) + (None,), faces, dims)
-            # dirty boxes: inside one slab, across a face, touching nothing
-            for box in ((-0.3, -0.2, -0.9, 0.4, 0.3, -0.7), (-0.5, -0.5, -0.5, 0.5, 0.5, 0.5), (3, 3, 3, 4, 4, 4),
-                        (-1, -1, -1, 1, 1, 1)):
-                other = S.tape.demo_tape() if box[0] == 3 else S.tape.csg_tape(S.tape.csg_primitive_table(12))
-                g.set_tape(other); whole.set_tape(other)
-                assert g.resample_box(box, count=True) == whole.resample_box(box, count=True)
-                t0, t1 = whole.download()
-                g0, g1 = g.download()
-                assert np.array_equal(t0.view(np.uint32), g0.view(np.uint32)) and np.array_equal(t1.view(np.uint32), g1.view(np.uint32))
-                for r in g.ranks:
-                    check_halos(r, t0, t1, dims)
-                # few primitives -> long steps: rays leap over whole slabs and out of the box (hand-offs that skip a rank,
-                # positions whose mirrored taps belong to a rank the ray has already left)
-                for c in cameras(S, w, h):
-                    want8, want_d = whole.trace_rgba8(c, w, h)
-                    _, _, want_g = whole.trace(c, w, h, gbuf=True)
-                    same_frame(g.trace(c, w, h), (want8, want_d, want_g), faces, dims)
+            assert all(r.get_info("link_halo_push") == int(halo_push) and r.get_info("link_trace_stream") == 0 for r in g.ranks)
+            group_body(S, whole, g, sdf, dims, w, h)
+
+
+def group_body(S, whole, g, sdf, dims, w, h):
+    """What a group must reproduce of ONE handle `whole` (both freshly created with 3 loading passes); also run over
+    real peers by tests/group_devices_check.py."""
+    faces = [r.z_begin for r in g.ranks[1:]]
+    # pass by pass: volumes and frames (lod 4, 2, 1; NEAREST then LINEAR) equal the single handle's
+    sdf2 = S.SDFDemo()
+    for k in range(3):
+        it_w = whole.update(sdf, max_passes=1)
+        it_g = g.update(sdf2, max_passes=1)
+        assert it_w == it_g
+        whole.commit(); g.commit()
+        t0, t1 = whole.download()
+        g0, g1 = g.download()
+        assert np.array_equal(t0.view(np.uint32), g0.view(np.uint32)), f"tex0 differs after pass {k}"
+        assert np.array_equal(t1.view(np.uint32), g1.view(np.uint32)), f"tex1 differs after pass {k}"
+        for cam in cameras(S, w, h):
+            want8, want_d = whole.trace_rgba8(cam, w, h)
+            _, _, want_g = whole.trace(cam, w, h, gbuf=True)
+            same_frame(g.trace(cam, w, h), (want8, want_d, want_g), faces, dims)
+    assert g.loading_state()[0] == 0
+    # a frame without G-buffer through the rgba8 entry point, several frames back to back (key-frame parity)
+    for cam in cameras(S, w, h) * 2:
+        want8, want_d = whole.trace_rgba8(cam, w, h)
+        same_frame(g.trace_rgba8(cam, w, h) + (None,), (want8, want_d, None), faces, dims)
+    # halo slices hold the neighbours' boundary slices
+    for r in g.ranks:
+        check_halos(r, t0, t1, dims)
+    # fill_all (one launch per rank, boundary tiles first) after a reset
+    g.reset(1); whole.reset(1)
+    g.set_tape(sdf.tape()); whole.set_tape(sdf.tape())
+    g.fill_all(); whole.fill_all()
+    g.commit(); whole.commit()
+    t0, t1 = whole.download()
+    g0, g1 = g.download()
+    assert np.array_equal(t0.view(np.uint32), g0.view(np.uint32)) and np.array_equal(t1.view(np.uint32), g1.view(np.uint32))
+    for r in g.ranks:
+        check_halos(r, t0, t1, dims)
+    cam = cameras(S, w, h)[3]
+    same_frame(g.trace_rgba8(cam, w, h) + (None,), whole.trace_rgba8(cam, w, h) + (None,), faces, dims)
+    # dirty boxes: inside one slab, across a face, touching nothing
+    for box in ((-0.3, -0.2, -0.9, 0.4, 0.3, -0.7), (-0.5, -0.5, -0.5, 0.5, 0.5, 0.5), (3, 3, 3, 4, 4, 4),
+                (-1, -1, -1, 1, 1, 1)):
+        other = S.tape.demo_tape() if box[0] == 3 else S.tape.csg_tape(S.tape.csg_primitive_table(12))
+        g.set_tape(other); whole.set_tape(other)
+        assert g.resample_box(box, count=True) == whole.resample_box(box, count=True)
+        t0, t1 = whole.download()
+        g0, g1 = g.download()
+        assert np.array_equal(t0.view(np.uint32), g0.view(np.uint32)) and np.array_equal(t1.view(np.uint32), g1.view(np.uint32))
+        for r in g.ranks:
+            check_halos(r, t0, t1, dims)
+        # few primitives -> long steps: rays leap over whole slabs and out of the box (hand-offs that skip a rank,
+        # positions whose mirrored taps belong to a rank the ray has already left)
+        for c in cameras(S, w, h):
+            want8, want_d = whole.trace_rgba8(c, w, h)
+            _, _, want_g = whole.trace(c, w, h, gbuf=True)
+            same_frame(g.trace(c, w, h), (want8, want_d, want_g), faces, dims)
 
 
 def check_halos(v, t0, t1, dims):
@@ -133,7 +144,7 @@ def check_halos(v, t0, t1, dims):
     n = dims[0] * dims[1] * 4
     p0, p1 = v.device_ptrs()
     for p, want in ((p0, t0), (p1, t1)):
-        t = torch.as_tensor(_DevMem(p, (v.z_hi - v.z_lo) * n, "<f4"), device=torch.device("cuda", 0))
+        t = torch.as_tensor(_DevMem(p, (v.z_hi - v.z_lo) * n, "<f4"), device=torch.device("cuda", v.get_info("device")))
         got = t.cpu().numpy().reshape(v.z_hi - v.z_lo, dims[1], dims[0], 4)
         assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(want[v.z_lo:v.z_hi]).view(np.uint32)), \
             f"stored slices [{v.z_lo},{v.z_hi}) of the rank owning [{v.z_begin},{v.z_end}) differ (halo exchange)"

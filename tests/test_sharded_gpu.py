@@ -21,3 +21,14 @@ def test_sharded_fill_halo_trace_nccl():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "multi_gpu_check ok" in r.stdout
+
+
+def test_group_over_real_devices_single_process():
+    """sdfgpu_group_* with one device per rank, driven by one host thread (tests/group_devices_check.py)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "group_devices_check.py")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "group_devices_check ok" in r.stdout

@@ -17,12 +17,17 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     side = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+    halo_push = bool(int(sys.argv[2])) if len(sys.argv) > 2 else False
+    trace_mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     dims = [side, side, side]
     k, axis = world, 2
     while k > 1:
         dims[axis] *= 2; k //= 2; axis = (axis - 1) % 3
     W, H = 1920, 1080
-    sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist if world > 1 else None, max_width=W, max_height=H)
+    sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist if world > 1 else None, max_width=W, max_height=H,
+                       halo_push=halo_push, trace_mode=trace_mode)
+    if rank == 0:
+        print(f"== link: halo_push {halo_push}, trace {'stream' if world > 1 and sv.viewer.get_info('link_trace_stream') else 'rounds'}", flush=True)
     v = sv.viewer
     v.set_tape(S.tape.demo_tape())
     sv.fill_all(); sv.commit()
@@ -54,6 +59,21 @@ def main():
                 e1.record(stream); v.sync(); torch.cuda.synchronize()
                 print(f"   variant {variant}: {e0.elapsed_time(e1) / 20:.3f} ms", flush=True)
             v.set_option("trace_variant", 0)
+    # the bench step (fill + commit + trace, enqueued back to back), per rank
+    cam = S.default_camera(W, H)
+    for _ in range(5):
+        sv.fill_all(); sv.commit(); sv.trace_device(cam, W, H)
+    v.sync(); torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    n = 30
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n)]
+    for e in evs:
+        e[0].record(stream); sv.fill_all(); sv.commit(); e[1].record(stream); sv.trace_device(cam, W, H); e[2].record(stream)
+    v.sync(); torch.cuda.synchronize()
+    fill = sum(e[0].elapsed_time(e[1]) for e in evs[5:]) / (n - 5)
+    trace = sum(e[1].elapsed_time(e[2]) for e in evs[5:]) / (n - 5)
+    step = evs[5][0].elapsed_time(evs[-1][2]) / (n - 5)
+    print(f"== step loop rank {rank}: fill {fill:.3f} ms, trace {trace:.3f} ms, step {step:.3f} ms", flush=True)
     sv.close()
     if world > 1:
         dist.destroy_process_group()
