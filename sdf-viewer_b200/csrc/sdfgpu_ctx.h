@@ -221,6 +221,9 @@ struct sdfgpu_ctx {
     float4* peer_tex1[2] = {nullptr, nullptr};
     uint32_t peer_z_lo[2] = {0, 0};
     cudaStream_t halo_stream = nullptr;  // DMA pushes of the boundary slices, overlapped with the interior fill
+    cudaStream_t copy_stream = nullptr;  // frame rows to the host while the next band of the frame is traced
+    std::vector<cudaEvent_t> band_events;
+    int opt_trace_bands = 6;             // sdfgpu_trace_rgba8: bands per frame (1: trace the frame, then copy it)
     cudaEvent_t ev_boundary = nullptr, ev_pushed = nullptr;
     // options
     int opt_vpt = 0;        // voxels per thread (0 = default)

@@ -37,6 +37,7 @@ struct TraceParams {
     uint32_t max_steps;         // sdfRaycast's maxSteps: 256 (material.frag:142)
     uint32_t tiles_x, tiles_y;  // 8 x 8 pixel tiles
     uint32_t rect[4];           // tile rectangle [x0, y0, x1, y1) that contains every pixel whose ray can hit the clip box
+    uint32_t band_ty0, band_ty1;  // tile rows this launch of trace_tiles_kernel covers (the whole frame: 0, tiles_y)
     float4* rgba;              // may be null
     float* depth;              // may be null
     float* gbuf;               // may be null

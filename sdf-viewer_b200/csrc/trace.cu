@@ -438,25 +438,28 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, ui
 // as their own rays end instead of waiting for the slowest of 8 warps.
 template <bool SNAP, bool LINEAR, int DIST = 0, bool FULL = false>
 __global__ void __launch_bounds__(64) trace_tiles_kernel(const __grid_constant__ TraceParams P) {
-    const uint32_t rw = P.rect[2] - P.rect[0], rh = P.rect[3] - P.rect[1];
+    // the launch covers the tile rows [band_ty0, band_ty1) (the whole frame, or one band of a frame whose rows are
+    // copied to the host while the next band is traced); the rectangle is clipped to them
+    const uint32_t ry0 = min(max(P.rect[1], P.band_ty0), P.band_ty1), ry1 = min(max(P.rect[3], P.band_ty0), P.band_ty1);
+    const uint32_t rw = P.rect[2] - P.rect[0], rh = ry1 - ry0;
     const uint32_t n_heavy = rw * rh;
     uint32_t b = blockIdx.x, tx, ty;
     bool outside = false;
     if (b < n_heavy) {
-        tx = P.rect[0] + b % rw; ty = P.rect[1] + b / rw;
+        tx = P.rect[0] + b % rw; ty = ry0 + b / rw;
     } else {
         outside = true;
         b -= n_heavy;
-        const uint32_t n_top = P.rect[1] * P.tiles_x, side = P.tiles_x - rw;
+        const uint32_t n_top = (ry0 - P.band_ty0) * P.tiles_x, side = P.tiles_x - rw;
         if (b < n_top) {
-            tx = b % P.tiles_x; ty = b / P.tiles_x;
+            tx = b % P.tiles_x; ty = P.band_ty0 + b / P.tiles_x;
         } else if (b - n_top < rh * side) {
             b -= n_top;
             const uint32_t k = b % side;
-            ty = P.rect[1] + b / side; tx = k < P.rect[0] ? k : k + rw;
+            ty = ry0 + b / side; tx = k < P.rect[0] ? k : k + rw;
         } else {
             b -= n_top + rh * side;
-            tx = b % P.tiles_x; ty = P.rect[3] + b / P.tiles_x;
+            tx = b % P.tiles_x; ty = ry1 + b / P.tiles_x;
         }
     }
     const uint32_t i = tx * 8u + (threadIdx.x & 7u), j = ty * 8u + (threadIdx.x >> 3);
@@ -1162,7 +1165,8 @@ cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s) {
     if (p.width == 0 || p.height == 0) return cudaSuccess;
     const bool snap = p.lod != 1.0f, lin = p.filter_linear != 0;
     if (variant == 0) {
-        const unsigned grid = p.tiles_x * p.tiles_y;
+        const unsigned grid = p.tiles_x * (p.band_ty1 - p.band_ty0);
+        if (grid == 0) return cudaSuccess;
         const uint32_t mode = lin ? p.dist_mode : 0u;  // the distance volumes serve the LINEAR march only
         if (p.full_dist) {  // exact multi-GPU trace: replicated full-grid distance volume, hits shaded by their owner
             if (!snap && lin) trace_tiles_kernel<false, true, 1, true><<<grid, 64, 0, s>>>(p);

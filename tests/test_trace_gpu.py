@@ -161,6 +161,24 @@ def test_rgba8_frame(S):
     assert np.abs(r8.astype(int) - want.astype(int)).max() <= 1 and (r8 != want).mean() < 1e-3
 
 
+def test_rgba8_frame_in_bands(S):
+    """sdfgpu_trace_rgba8 traces the frame in bands of tile rows and copies each band while the next is traced
+    (option trace_bands): the same pixels for any number of bands, odd frame sizes, bands above / below / across the
+    screen rectangle of the box, more bands than tile rows."""
+    with fill(S, S.tape.demo_tape(), (48, 48, 48)) as v:
+        for (w, h, cam) in ((640, 480, None), (333, 211, None), (64, 19, None), (320, 200, ((0.2, 0.1, 0.3), (1, 0.2, -0.4))),
+                            (200, 300, ((4.0, 0.5, 0.2), (0, 3.0, 0)))):
+            c = S.default_camera(w, h) if cam is None else S.look_at_camera(cam[0], cam[1], w, h)
+            v.set_option("trace_bands", 1)
+            want8, want_d = v.trace_rgba8(c, w, h)
+            assert (want_d < 1).any()
+            for bands in (2, 3, 6, 7, 64):
+                v.set_option("trace_bands", bands)
+                got8, got_d = v.trace_rgba8(c, w, h)
+                assert np.array_equal(got8, want8) and np.array_equal(got_d.view(np.uint32), want_d.view(np.uint32)), (w, h, bands)
+        v.set_option("trace_bands", 6)
+
+
 def test_uncommitted_nearest(S, oracle):
     """Before any commit lod stays 1 and the GL filter is NEAREST (scene/sdf/mod.rs:110-111)."""
     w, h = 256, 192
