@@ -189,6 +189,12 @@ int ensure_halo_stream(sdfgpu_ctx* ctx) {
 
 }  // namespace
 
+bool sdfgpu::stream_wait_value_available() { return wait32() != nullptr; }
+
+bool sdfgpu::stream_wait_value(cudaStream_t s, const uint32_t* flag, uint32_t value) {
+    return wait32() && wait32()(s, (unsigned long long)(uintptr_t)flag, value, 0u /* CU_STREAM_WAIT_VALUE_GEQ */) == 0;
+}
+
 // ------------------------------------------------------------------------------------------------- fill
 
 int sdfgpu::link_after_fill(sdfgpu_ctx* ctx, bool touched_lo, bool touched_hi) {

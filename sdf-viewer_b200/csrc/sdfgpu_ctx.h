@@ -222,7 +222,9 @@ struct sdfgpu_ctx {
     uint32_t peer_z_lo[2] = {0, 0};
     cudaStream_t halo_stream = nullptr;  // DMA pushes of the boundary slices, overlapped with the interior fill
     cudaStream_t copy_stream = nullptr;  // frame rows to the host while the next band of the frame is traced
-    std::vector<cudaEvent_t> band_events;
+    cudaStream_t copy_stream2 = nullptr; //   ... colour on the first, depth on the second
+    uint32_t* band_counters = nullptr;   // 64 per-band CTA counters + 64 per-band flags (trace_tiles_kernel)
+    uint32_t band_epoch = 0;
     int opt_trace_bands = 6;             // sdfgpu_trace_rgba8: bands per frame (1: trace the frame, then copy it)
     cudaEvent_t ev_boundary = nullptr, ev_pushed = nullptr;
     // options
@@ -281,6 +283,8 @@ int link_after_fill(sdfgpu_ctx* ctx, bool touched_lo, bool touched_hi);  // push
 int link_fill_all_fused(sdfgpu_ctx* ctx, FillParams* p);                  // fills in the boundary-first fields of a full-slab launch
 int link_fill_all_pushed(sdfgpu_ctx* ctx);                                // after that launch: flag-ordered DMA push + signal
 int link_trace_begin(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t w, uint32_t h, bool want_gbuf);
+bool stream_wait_value_available();  // cuStreamWaitValue32 resolved
+bool stream_wait_value(cudaStream_t s, const uint32_t* flag, uint32_t value);  // stream continues once *flag >= value
 int link_trace_round(sdfgpu_ctx* ctx);
 int link_trace_stream(sdfgpu_ctx* ctx);  // LinkState::stream: the whole frame of this rank in one launch
 int link_trace_issue(sdfgpu_ctx* ctx);   // every round, or the one streaming launch

@@ -12,6 +12,8 @@
 
 namespace sdfgpu {
 
+constexpr uint32_t TRACE_MAX_BANDS = 32;
+
 struct TraceParams {
     const float4* tex0;
     const float4* tex1;
@@ -37,7 +39,13 @@ struct TraceParams {
     uint32_t max_steps;         // sdfRaycast's maxSteps: 256 (material.frag:142)
     uint32_t tiles_x, tiles_y;  // 8 x 8 pixel tiles
     uint32_t rect[4];           // tile rectangle [x0, y0, x1, y1) that contains every pixel whose ray can hit the clip box
-    uint32_t band_ty0, band_ty1;  // tile rows this launch of trace_tiles_kernel covers (the whole frame: 0, tiles_y)
+    // trace_tiles_kernel can announce the frame band by band (sdfgpu_trace_rgba8: the rows of a finished band cross
+    // PCIe while the others are still being traced): the CTAs come band by band -- band_rows tile rows each, in the
+    // order of band_order -- and the last CTA of a band to finish stores band_epoch into band_flags[band]
+    uint32_t n_bands, band_rows, band_epoch;  // n_bands == 0: one band, no flags
+    uint8_t band_order[TRACE_MAX_BANDS];
+    uint32_t* band_done;                      // n_bands counters (zero between frames)
+    uint32_t* band_flags;                     // n_bands flags, awaited by stream memory operations
     float4* rgba;              // may be null
     float* depth;              // may be null
     float* gbuf;               // may be null

@@ -438,21 +438,28 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, ui
 // as their own rays end instead of waiting for the slowest of 8 warps.
 template <bool SNAP, bool LINEAR, int DIST = 0, bool FULL = false>
 __global__ void __launch_bounds__(64) trace_tiles_kernel(const __grid_constant__ TraceParams P) {
-    // the launch covers the tile rows [band_ty0, band_ty1) (the whole frame, or one band of a frame whose rows are
-    // copied to the host while the next band is traced); the rectangle is clipped to them
-    const uint32_t ry0 = min(max(P.rect[1], P.band_ty0), P.band_ty1), ry1 = min(max(P.rect[3], P.band_ty0), P.band_ty1);
+    // the CTAs come band by band in the order of band_order -- a band is the tile rows [ty0, ty1) -- and within a band
+    // the tiles inside the rectangle (clipped to the band) first
+    uint32_t b = blockIdx.x, tx, ty, band = 0, ty0 = 0, ty1 = P.tiles_y;
+    for (uint32_t k = 0; k < P.n_bands; ++k) {
+        band = P.band_order[k];
+        ty0 = band * P.band_rows; ty1 = min(ty0 + P.band_rows, P.tiles_y);
+        const uint32_t n = P.tiles_x * (ty1 - ty0);
+        if (b < n) break;
+        b -= n;
+    }
+    const uint32_t ry0 = min(max(P.rect[1], ty0), ty1), ry1 = min(max(P.rect[3], ty0), ty1);
     const uint32_t rw = P.rect[2] - P.rect[0], rh = ry1 - ry0;
     const uint32_t n_heavy = rw * rh;
-    uint32_t b = blockIdx.x, tx, ty;
     bool outside = false;
     if (b < n_heavy) {
         tx = P.rect[0] + b % rw; ty = ry0 + b / rw;
     } else {
         outside = true;
         b -= n_heavy;
-        const uint32_t n_top = (ry0 - P.band_ty0) * P.tiles_x, side = P.tiles_x - rw;
+        const uint32_t n_top = (ry0 - ty0) * P.tiles_x, side = P.tiles_x - rw;
         if (b < n_top) {
-            tx = b % P.tiles_x; ty = P.band_ty0 + b / P.tiles_x;
+            tx = b % P.tiles_x; ty = ty0 + b / P.tiles_x;
         } else if (b - n_top < rh * side) {
             b -= n_top;
             const uint32_t k = b % side;
@@ -463,9 +470,21 @@ __global__ void __launch_bounds__(64) trace_tiles_kernel(const __grid_constant__
         }
     }
     const uint32_t i = tx * 8u + (threadIdx.x & 7u), j = ty * 8u + (threadIdx.x >> 3);
-    if (i >= P.width || j >= P.height) return;
-    if (outside) write_outside(P, (size_t)j * P.width + i);
-    else trace_pixel<SNAP, LINEAR, DIST, FULL>(P, i, j);
+    if (i < P.width && j < P.height) {
+        if (outside) write_outside(P, (size_t)j * P.width + i);
+        else trace_pixel<SNAP, LINEAR, DIST, FULL>(P, i, j);
+    }
+    if (P.n_bands) {  // the last CTA of a band of tile rows to finish: every pixel of those rows is in memory
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(P.band_done + band, 1u) + 1u == P.tiles_x * (ty1 - ty0)) {
+                P.band_done[band] = 0u;
+                __threadfence();
+                *reinterpret_cast<volatile uint32_t*>(P.band_flags + band) = P.band_epoch;
+            }
+        }
+    }
 }
 
 // Variant 1: plain 2-D grid, 8 warps per CTA, each an 8 x 4 pixel tile; CTA tile = 32 x 8 pixels
@@ -1165,8 +1184,7 @@ cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s) {
     if (p.width == 0 || p.height == 0) return cudaSuccess;
     const bool snap = p.lod != 1.0f, lin = p.filter_linear != 0;
     if (variant == 0) {
-        const unsigned grid = p.tiles_x * (p.band_ty1 - p.band_ty0);
-        if (grid == 0) return cudaSuccess;
+        const unsigned grid = p.tiles_x * p.tiles_y;
         const uint32_t mode = lin ? p.dist_mode : 0u;  // the distance volumes serve the LINEAR march only
         if (p.full_dist) {  // exact multi-GPU trace: replicated full-grid distance volume, hits shaded by their owner
             if (!snap && lin) trace_tiles_kernel<false, true, 1, true><<<grid, 64, 0, s>>>(p);

@@ -171,8 +171,8 @@ def test_rgba8_frame_in_bands(S):
             c = S.default_camera(w, h) if cam is None else S.look_at_camera(cam[0], cam[1], w, h)
             v.set_option("trace_bands", 1)
             want8, want_d = v.trace_rgba8(c, w, h)
-            assert (want_d < 1).any()
-            for bands in (2, 3, 6, 7, 64):
+            assert cam is not None or (want_d < 1).any()
+            for bands in (2, 3, 6, 7, 32):
                 v.set_option("trace_bands", bands)
                 got8, got_d = v.trace_rgba8(c, w, h)
                 assert np.array_equal(got8, want8) and np.array_equal(got_d.view(np.uint32), want_d.view(np.uint32)), (w, h, bands)
