@@ -494,6 +494,14 @@ int sdfgpu_trace_exact_keys(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t 
 int sdfgpu_keys_download(sdfgpu_ctx* ctx, const void* keys_dev, uint32_t width,
                          uint32_t height, uint8_t* rgba8, float* depth);
 
+/* Statistics of the per-tile culling the fill applies to a UNION_RANGE of >= 16 primitives (exact-safe: a primitive is
+ * dropped from a tile's list only if its lower distance bound over the tile exceeds another primitive's upper bound;
+ * DESIGN.md section 4.1).  Runs ONE fill of every voxel with the current tape (as sdfgpu_fill_all; idempotent) and
+ * returns the number of tiles, the sum and the maximum of the survivors per tile, and the primitives of the range
+ * (0 everywhere when the tape has no culled range).  Not in the reference (no CSG workload there). */
+int sdfgpu_cull_stats(sdfgpu_ctx* ctx, uint64_t* tiles, uint64_t* survivors_sum, uint64_t* survivors_max,
+                      uint32_t* primitives);
+
 /* ------------------------------------------------------------------ stream */
 
 int sdfgpu_sync(sdfgpu_ctx* ctx);

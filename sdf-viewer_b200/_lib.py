@@ -135,6 +135,7 @@ SIGNATURES = {
     "sdfgpu_update_surface": (C.c_int, [_vp, C.POINTER(Surface), C.c_double, _u64p]),
     "sdfgpu_fill_all": (C.c_int, [_vp]),
     "sdfgpu_resample_box": (C.c_int, [_vp, _fp, _u64p]),
+    "sdfgpu_cull_stats": (C.c_int, [_vp, _u64p, _u64p, _u64p, _u32p]),
     "sdfgpu_voxel_positions": (C.c_int, [_vp, _u64, _u64, _vp]),
     "sdfgpu_ingest_samples": (C.c_int, [_vp, _u64, _u64, _vp]),
     "sdfgpu_commit": (C.c_int, [_vp]),

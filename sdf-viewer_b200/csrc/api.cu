@@ -173,6 +173,7 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
     if (ctx->has_changed_box) memcpy(p.box, ctx->changed_box, sizeof p.box);
     p.air_dist = air_dist_value();
     p.touched = touched;
+    p.cull_stats = ctx->cull_stats_dev;  // null unless sdfgpu_cull_stats is running
     if (ctx->fill_boundary_first) (void)link_fill_all_fused(ctx, &p);
     const int rc = dispatch_fill(ctx, p, V);
     if (rc != SDFGPU_OK) return rc;
@@ -1158,6 +1159,37 @@ SDFGPU_API int sdfgpu_fill_all(sdfgpu_ctx* ctx) {
     }
     ctx->known_step = 1;
     while (ctx->lm.step_size != 0) ctx->lm.finish_pass();
+    return SDFGPU_OK;
+}
+
+SDFGPU_API int sdfgpu_cull_stats(sdfgpu_ctx* ctx, uint64_t* tiles, uint64_t* survivors_sum, uint64_t* survivors_max,
+                                 uint32_t* primitives) {
+    if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
+    if (!ctx->has_tape) return fail(ctx, SDFGPU_ERR_STATE, "no tape set (call sdfgpu_set_tape first)");
+    set_device(ctx);
+    if (primitives) *primitives = (ctx->hdr.flags & TAPE_FLAG_CULL) ? ctx->hdr.cull_count : 0u;
+    unsigned long long st[3] = {0, 0, 0};
+    if (ctx->hdr.flags & TAPE_FLAG_CULL) {
+        unsigned long long* dev = nullptr;
+        CK(ctx, cudaMalloc(&dev, sizeof st));
+        cudaError_t e = cudaMemsetAsync(dev, 0, sizeof st, ctx->stream);
+        int rc = e == cudaSuccess ? SDFGPU_OK : fail(ctx, SDFGPU_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+        if (rc == SDFGPU_OK) {
+            ctx->cull_stats_dev = dev;
+            rc = sdfgpu_fill_all(ctx);  // the statistics of one fill of every voxel (idempotent: sample() is pure)
+            ctx->cull_stats_dev = nullptr;
+        }
+        if (rc == SDFGPU_OK) {
+            e = cudaMemcpyAsync(st, dev, sizeof st, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) rc = fail(ctx, SDFGPU_ERR_CUDA, "reading the statistics failed: %s", cudaGetErrorString(e));
+        }
+        (void)cudaFree(dev);
+        if (rc != SDFGPU_OK) return rc;
+    }
+    if (survivors_sum) *survivors_sum = st[0];
+    if (tiles) *tiles = st[1];
+    if (survivors_max) *survivors_max = st[2];
     return SDFGPU_OK;
 }
 

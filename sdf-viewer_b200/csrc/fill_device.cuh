@@ -586,6 +586,11 @@ __device__ __forceinline__ void fill_body(const FillParams& P) {
                 __syncthreads();
             }
             E.list_n = base;
+            if (P.cull_stats && threadIdx.x == 0) {
+                atomicAdd(P.cull_stats, (unsigned long long)base);
+                atomicAdd(P.cull_stats + 1, 1ull);
+                atomicMax(P.cull_stats + 2, (unsigned long long)base);
+            }
         }
 
         const uint32_t lx = tx * FILL_TILE_X + lane;

@@ -220,6 +220,7 @@ struct sdfgpu_ctx {
     float4* peer_tex0[2] = {nullptr, nullptr};
     float4* peer_tex1[2] = {nullptr, nullptr};
     uint32_t peer_z_lo[2] = {0, 0};
+    unsigned long long* cull_stats_dev = nullptr;  // set while sdfgpu_cull_stats runs its fill
     cudaStream_t halo_stream = nullptr;  // DMA pushes of the boundary slices, overlapped with the interior fill
     cudaStream_t copy_stream = nullptr;  // frame rows to the host while the next band of the frame is traced
     cudaStream_t copy_stream2 = nullptr; //   ... colour on the first, depth on the second

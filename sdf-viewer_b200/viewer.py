@@ -402,6 +402,13 @@ class SDFViewer:
         check(self._lib.sdfgpu_mesh_write_ply(self._h, str(path).encode(), comment.encode() if comment else None, C.byref(n)), self._h)
         return n.value
 
+    def cull_stats(self):
+        """Per-tile culling of the current tape's UNION_RANGE over one fill of every voxel (sdfgpu_cull_stats)."""
+        t, s, m, n = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint32()
+        check(self._lib.sdfgpu_cull_stats(self._h, C.byref(t), C.byref(s), C.byref(m), C.byref(n)), self._h)
+        return {"primitives": n.value, "tiles": t.value, "survivors_mean": s.value / t.value if t.value else 0.0,
+                "survivors_max": m.value}
+
     # ---- linked slabs (multi-GPU behind the C ABI: include/sdfgpu.h "linked slabs")
     def link_export(self, rank, world, max_width, max_height, gbuf=False, halo_push=False, trace_mode=0):
         """This rank's link blob (CUDA IPC handles of its volumes and arena); gather the blobs of all ranks.

@@ -127,6 +127,16 @@ def test_csg_tape(S, oracle, n_prims, vpt, program):
         v.fill_all()
         assert v.get_info("last_fill_program") == PROGRAMS[program][1]
         t0, t1 = v.download()
+        # sdfgpu_cull_stats: one more fill of every voxel (same volume), survivors per tile within [1, n_prims]
+        st = v.cull_stats()
+        vz = v.get_info("last_fill_voxels_per_thread")
+        if n_prims >= 16:
+            assert st["primitives"] == n_prims and 1 <= st["survivors_mean"] <= st["survivors_max"] <= n_prims
+            assert st["tiles"] == -(-dims[0] // 32) * -(-dims[1] // 8) * -(-dims[2] // vz)
+        else:
+            assert st == {"primitives": 0, "tiles": 0, "survivors_mean": 0.0, "survivors_max": 0}
+        u0, u1 = v.download()
+        assert_same_volume(u0, u1, t0, t1)
     o = oracle.Viewer(BB, dims, 1)
     o.fill_all(oracle.Sampler(tape=tape))
     assert_same_volume(t0, t1, o.tex0, o.tex1)
