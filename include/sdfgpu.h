@@ -512,6 +512,8 @@ uint64_t sdfgpu_launch_count(const sdfgpu_ctx* ctx);
 /* Fill-kernel knobs (0 = library default); used by the benchmarks and tests:
  *   "fill_voxels_per_thread" 0|1|2|4|8   "fill_ctas_per_sm" 0..32
  *   "fill_halo" 0|1 (compute halo slices locally; 0 when the host exchanges them)
+ *   "fill_cull_cells" 0|1 (default 1): tiles of a culled UNION_RANGE start from the survivors of their 64^3-voxel cell
+ *                  (computed once per set_tape) instead of the whole range; same volume either way
  *   "trace_distance_volume" 0..3: where the LINEAR march reads its distances.  0 (default) tex0.r in place;
  *                  1 a distance-only copy of tex0.r in linear memory (4 B / voxel, rebuilt after every change):
  *                  same values, a quarter of the bytes per fetch; 2 the copy as an R32F 3-D CUDA array read

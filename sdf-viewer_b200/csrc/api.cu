@@ -174,6 +174,10 @@ int run_fill(sdfgpu_ctx* ctx, uint32_t step, const uint32_t lo[3], const uint32_
     p.air_dist = air_dist_value();
     p.touched = touched;
     p.cull_stats = ctx->cull_stats_dev;  // null unless sdfgpu_cull_stats is running
+    if (ctx->cell_lists_valid && ctx->opt_cull_cells) {
+        p.cell_lists = ctx->cell_lists; p.cell_counts = ctx->cell_counts;
+        p.cells_x = ctx->cells[0]; p.cells_y = ctx->cells[1];
+    }
     if (ctx->fill_boundary_first) (void)link_fill_all_fused(ctx, &p);
     const int rc = dispatch_fill(ctx, p, V);
     if (rc != SDFGPU_OK) return rc;
@@ -404,7 +408,7 @@ SDFGPU_API void sdfgpu_destroy(sdfgpu_ctx* ctx) {
     mesh_free(ctx);
     (void)sdfgpu_ipc_detach(ctx);
     (void)cudaFree(ctx->trace_counters);
-    (void)cudaFree(ctx->tex0); (void)cudaFree(ctx->tex1); (void)cudaFree(ctx->img_dev);
+    (void)cudaFree(ctx->tex0); (void)cudaFree(ctx->tex1); (void)cudaFree(ctx->img_dev); (void)cudaFree(ctx->cell_lists);
     (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
     (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->rgba8_dev); (void)cudaFree(ctx->touched_dev);
     (void)cudaFree(ctx->ingest_dev); (void)cudaFree(ctx->lut_dev); (void)cudaFree(ctx->dist_dev);
@@ -689,6 +693,27 @@ SDFGPU_API int sdfgpu_set_tape(sdfgpu_ctx* ctx, const void* tape, size_t tape_by
     // stream-ordered after earlier fills; the source is pageable, so this call returns once it is staged
     CK(ctx, cudaMemcpyAsync(ctx->img_dev, img.data(), img.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->cell_lists_valid = false;
+    if ((ih.flags & TAPE_FLAG_CULL) && ctx->dims[0] && ctx->dims[1] && ctx->dims[2]) {
+        // coarse pre-cull: the survivors of every 64^3-voxel cell, so that a tile culls tens of candidates, not the range
+        const uint32_t C = 1u << CULL_CELL_SHIFT;
+        for (int a = 0; a < 3; ++a) ctx->cells[a] = (ctx->dims[a] + C - 1) / C;
+        const size_t n_cells = (size_t)ctx->cells[0] * ctx->cells[1] * ctx->cells[2];
+        const size_t need = n_cells * ih.cull_count + n_cells;
+        if (need <= (size_t)1 << 28) {  // at most 1 GiB of lists: beyond that the tiles cull the whole range
+            if (need > ctx->cell_lists_cap) {
+                (void)cudaFree(ctx->cell_lists);
+                ctx->cell_lists = nullptr; ctx->cell_lists_cap = 0;
+                CK(ctx, cudaMalloc(&ctx->cell_lists, need * sizeof(uint32_t)));
+                ctx->cell_lists_cap = need;
+            }
+            ctx->cell_counts = ctx->cell_lists + n_cells * ih.cull_count;
+            CK(ctx, launch_cull_cells(ctx->img_dev, ctx->dims, ctx->cells[0], ctx->cells[1], ctx->cells[2], ctx->cell_lists,
+                                      ctx->cell_counts, ctx->stream));
+            ctx->launches++;
+            ctx->cell_lists_valid = true;
+        }
+    }
     ctx->img_host.swap(img);
     ctx->hdr = ih;
     ctx->opcodes.swap(pt.opcodes);
@@ -1997,6 +2022,8 @@ SDFGPU_API int sdfgpu_set_option(sdfgpu_ctx* ctx, const char* key, int64_t value
     } else if (!strcmp(key, "trace_variant")) {
         if (value < 0 || value > 2) return fail(ctx, SDFGPU_ERR_INVALID, "trace_variant must be 0, 1 or 2");
         ctx->opt_trace_variant = (int)value;
+    } else if (!strcmp(key, "fill_cull_cells")) {
+        ctx->opt_cull_cells = value != 0;
     } else if (!strcmp(key, "trace_bands")) {
         if (value < 1 || value > (int64_t)TRACE_MAX_BANDS) return fail(ctx, SDFGPU_ERR_INVALID, "trace_bands must be 1..%u", TRACE_MAX_BANDS);
         ctx->opt_trace_bands = (int)value;

@@ -71,6 +71,31 @@ __global__ void __launch_bounds__(256) gather_dist_kernel(const float4* __restri
         out[i] = reinterpret_cast<const float*>(tex0 + idx[i])[0];
 }
 
+// Coarse pre-cull of a culled UNION_RANGE (FillParams::cell_lists): one CTA per cell of CULL_CELL^3 voxels runs the
+// fill kernel's own cull (dev::cull_box) against the positions of the whole cell, reading the tape image in global
+// memory, and writes the survivors -- ascending -- to the cell's cull_count slots.
+__global__ void __launch_bounds__(FILL_THREADS) cull_cells_kernel(const unsigned char* __restrict__ img, uint32_t W, uint32_t H,
+                                                                  uint32_t D, uint32_t cells_x, uint32_t cells_y,
+                                                                  uint32_t* __restrict__ lists, uint32_t* __restrict__ counts) {
+    __shared__ float s_red[FILL_THREADS / 32];
+    __shared__ uint32_t s_cnt[FILL_THREADS / 32];
+    const TapeImageHeader* hdr = reinterpret_cast<const TapeImageHeader*>(img);
+    const float4* geom = reinterpret_cast<const float4*>(img + hdr->off_geom);
+    const float4* mat1 = reinterpret_cast<const float4*>(img + hdr->off_mat1);
+    const float* px = reinterpret_cast<const float*>(img + hdr->off_px);
+    const float* py = reinterpret_cast<const float*>(img + hdr->off_py);
+    const float* pz = reinterpret_cast<const float*>(img + hdr->off_pz);
+    const uint32_t cell = blockIdx.x, cx = cell % cells_x, cy = (cell / cells_x) % cells_y, cz = cell / (cells_x * cells_y);
+    const uint32_t C = 1u << CULL_CELL_SHIFT;
+    const float ax = px[cx * C], bx = px[min(cx * C + C, W) - 1u];
+    const float ay = py[cy * C], by = py[min(cy * C + C, H) - 1u];
+    const float az = pz[cz * C], bz = pz[min(cz * C + C, D) - 1u];
+    const uint32_t n = dev::cull_box(geom, mat1, nullptr, hdr->cull_first, hdr->cull_count, fminf(ax, bx), fmaxf(ax, bx),
+                                     fminf(ay, by), fmaxf(ay, by), fminf(az, bz), fmaxf(az, bz), s_red, s_cnt,
+                                     lists + (size_t)cell * hdr->cull_count);
+    if (threadIdx.x == 0) counts[cell] = n;
+}
+
 typedef void (*fill_fn)(const FillParams);
 
 fill_fn pick(int V, int program) {
@@ -113,6 +138,13 @@ cudaError_t launch_fill(const FillParams& p, int V, int program, int grid, size_
     fill_fn f = pick(V, program);
     if (!f) return cudaErrorInvalidValue;
     f<<<grid, FILL_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cull_cells(const unsigned char* img_dev, const uint32_t dims[3], uint32_t cells_x, uint32_t cells_y,
+                              uint32_t cells_z, uint32_t* lists, uint32_t* counts, cudaStream_t s) {
+    cull_cells_kernel<<<cells_x * cells_y * cells_z, FILL_THREADS, 0, s>>>(img_dev, dims[0], dims[1], dims[2], cells_x, cells_y,
+                                                                         lists, counts);
     return cudaGetLastError();
 }
 

@@ -451,6 +451,75 @@ __device__ __forceinline__ void tile_body(const FillParams& P, const Env& E, con
     }
 }
 
+// The exact-safe cull of a UNION_RANGE against the position box [lo, hi], by all FILL_THREADS threads of a CTA: of
+// the n_src candidates -- primitive src[k], or first + k when src is null, ascending -- primitive k is dropped only if
+// its lower distance bound over the box (minus a margin) exceeds some candidate's upper bound (plus a margin), so the
+// argmin over the survivors is the argmin over the candidates at every point of the box; their order is kept (ordered
+// ballot compaction), which keeps the lowest-index tie rule.  Survivors to out[], their number returned (CTA-uniform).
+// The caller has made sure that nobody still reads out[], s_red, s_cnt.
+__device__ __forceinline__ uint32_t cull_box(const float4* geom, const float4* mat1, const uint32_t* src, uint32_t first,
+                                             uint32_t n_src, float lox, float hix, float loy, float hiy, float loz,
+                                             float hiz, float* s_red, uint32_t* s_cnt, uint32_t* out) {
+    constexpr int NT = FILL_THREADS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float EPS = 1e-5f;
+    // pass 1: U = min over primitives of the upper bound
+    float umin = __int_as_float(0x7f800000);
+    for (uint32_t k = threadIdx.x; k < n_src; k += NT) {
+        const uint32_t pk = src ? src[k] : first + k;
+        const float4 g = geom[pk];
+        const uint32_t shape = __float_as_uint(mat1[pk].w) & 0xffu;
+        const float fx = fmaxf(fabsf(lox - g.x), fabsf(hix - g.x));
+        const float fy = fmaxf(fabsf(loy - g.y), fabsf(hiy - g.y));
+        const float fz = fmaxf(fabsf(loz - g.z), fabsf(hiz - g.z));
+        float ub = (shape == SDFT_SHAPE_SPHERE) ? sqrtf(fx * fx + fy * fy + fz * fz) : fmaxf(fmaxf(fx, fy), fz);
+        ub = ub - g.w;
+        ub = ub + EPS * (1.0f + fabsf(ub));
+        umin = fminf(umin, ub);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+    if (lane == 0) s_red[warp] = umin;
+    __syncthreads();
+    float U = s_red[0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) U = fminf(U, s_red[w]);
+    // pass 2: ordered compaction of the survivors (index order keeps the tie rule)
+    uint32_t base = 0;
+    for (uint32_t k0 = 0; k0 < n_src; k0 += NT) {
+        const uint32_t k = k0 + threadIdx.x;
+        bool keep = false;
+        uint32_t pk = 0;
+        if (k < n_src) {
+            pk = src ? src[k] : first + k;
+            const float4 g = geom[pk];
+            const uint32_t shape = __float_as_uint(mat1[pk].w) & 0xffu;
+            const float nx_ = fmaxf(fmaxf(lox - g.x, g.x - hix), 0.0f);
+            const float ny_ = fmaxf(fmaxf(loy - g.y, g.y - hiy), 0.0f);
+            const float nz_ = fmaxf(fmaxf(loz - g.z, g.z - hiz), 0.0f);
+            float lb = (shape == SDFT_SHAPE_SPHERE) ? sqrtf(nx_ * nx_ + ny_ * ny_ + nz_ * nz_)
+                                                    : fmaxf(fmaxf(nx_, ny_), nz_);
+            lb = lb - g.w;
+            lb = lb - EPS * (1.0f + fabsf(lb));
+            keep = !(lb > U);  // NaN bounds keep the primitive
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_cnt[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t wbase = base, total = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) {
+            const uint32_t c = s_cnt[w];
+            if (w < warp) wbase += c;
+            total += c;
+        }
+        if (keep) out[wbase + __popc(bal & ((1u << lane) - 1u))] = pk;
+        base += total;
+        __syncthreads();
+    }
+    return base;
+}
+
 // V = voxels per thread along z (lattice units).
 template <int V, int PROG>
 __device__ __forceinline__ void fill_body(const FillParams& P) {
@@ -533,58 +602,20 @@ __device__ __forceinline__ void fill_body(const FillParams& P) {
             const float lox = fminf(ax, bx), hix = fmaxf(ax, bx);
             const float loy = fminf(ay, by), hiy = fmaxf(ay, by);
             const float loz = fminf(az, bz), hiz = fmaxf(az, bz);
-            const float EPS = 1e-5f;
-            // pass 1: U = min over primitives of the upper bound
-            float umin = __int_as_float(0x7f800000);
-            for (uint32_t k = threadIdx.x; k < n_cull; k += NT) {
-                const float4 g = E.geom[cull_first + k];
-                const uint32_t shape = __float_as_uint(E.mat1[cull_first + k].w) & 0xffu;
-                const float fx = fmaxf(fabsf(lox - g.x), fabsf(hix - g.x));
-                const float fy = fmaxf(fabsf(loy - g.y), fabsf(hiy - g.y));
-                const float fz = fmaxf(fabsf(loz - g.z), fabsf(hiz - g.z));
-                float ub = (shape == SDFT_SHAPE_SPHERE) ? sqrtf(fx * fx + fy * fy + fz * fz) : fmaxf(fmaxf(fx, fy), fz);
-                ub = ub - g.w;
-                ub = ub + EPS * (1.0f + fabsf(ub));
-                umin = fminf(umin, ub);
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-            if (lane == 0) s_red[warp] = umin;
-            __syncthreads();
-            float U = s_red[0];
-#pragma unroll
-            for (int w = 1; w < NT / 32; ++w) U = fminf(U, s_red[w]);
-            // pass 2: ordered compaction of the survivors (index order keeps the tie rule)
-            uint32_t base = 0;
-            for (uint32_t k0 = 0; k0 < n_cull; k0 += NT) {
-                const uint32_t k = k0 + threadIdx.x;
-                bool keep = false;
-                if (k < n_cull) {
-                    const float4 g = E.geom[cull_first + k];
-                    const uint32_t shape = __float_as_uint(E.mat1[cull_first + k].w) & 0xffu;
-                    const float nx_ = fmaxf(fmaxf(lox - g.x, g.x - hix), 0.0f);
-                    const float ny_ = fmaxf(fmaxf(loy - g.y, g.y - hiy), 0.0f);
-                    const float nz_ = fmaxf(fmaxf(loz - g.z, g.z - hiz), 0.0f);
-                    float lb = (shape == SDFT_SHAPE_SPHERE) ? sqrtf(nx_ * nx_ + ny_ * ny_ + nz_ * nz_)
-                                                            : fmaxf(fmaxf(nx_, ny_), nz_);
-                    lb = lb - g.w;
-                    lb = lb - EPS * (1.0f + fabsf(lb));
-                    keep = !(lb > U);  // NaN bounds keep the primitive
+            // a tile inside one cell of the coarse pre-cull starts from that cell's survivors, not from the whole range
+            const uint32_t* src = nullptr;
+            uint32_t n_src = n_cull;
+            if (P.cell_lists) {
+                const uint32_t cx0 = (P.rx0 + lx0 * P.step) >> CULL_CELL_SHIFT, cx1 = (P.rx0 + lx1 * P.step) >> CULL_CELL_SHIFT;
+                const uint32_t cy0 = (P.ry0 + ly0 * P.step) >> CULL_CELL_SHIFT, cy1 = (P.ry0 + ly1 * P.step) >> CULL_CELL_SHIFT;
+                const uint32_t cz0 = (P.rz0 + lz0 * P.step) >> CULL_CELL_SHIFT, cz1 = (P.rz0 + lz1 * P.step) >> CULL_CELL_SHIFT;
+                if (cx0 == cx1 && cy0 == cy1 && cz0 == cz1) {
+                    const uint32_t cell = (cz0 * P.cells_y + cy0) * P.cells_x + cx0;
+                    src = P.cell_lists + (size_t)cell * n_cull;
+                    n_src = P.cell_counts[cell];
                 }
-                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-                if (lane == 0) s_cnt[warp] = __popc(bal);
-                __syncthreads();
-                uint32_t wbase = base, total = 0;
-#pragma unroll
-                for (int w = 0; w < NT / 32; ++w) {
-                    const uint32_t c = s_cnt[w];
-                    if (w < warp) wbase += c;
-                    total += c;
-                }
-                if (keep) s_list[wbase + __popc(bal & ((1u << lane) - 1u))] = cull_first + k;
-                base += total;
-                __syncthreads();
             }
+            const uint32_t base = cull_box(E.geom, E.mat1, src, cull_first, n_src, lox, hix, loy, hiy, loz, hiz, s_red, s_cnt, s_list);
             E.list_n = base;
             if (P.cull_stats && threadIdx.x == 0) {
                 atomicAdd(P.cull_stats, (unsigned long long)base);

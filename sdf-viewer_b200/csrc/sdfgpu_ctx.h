@@ -169,6 +169,13 @@ struct sdfgpu_ctx {
     std::vector<unsigned char> img_host;
     unsigned char* img_dev = nullptr;
     size_t img_dev_cap = 0;
+    // coarse pre-cull of the current tape's culled UNION_RANGE (FillParams::cell_lists), rebuilt by every set_tape
+    uint32_t* cell_lists = nullptr;   // cells x cull_count
+    uint32_t* cell_counts = nullptr;  // follows the lists in the same allocation
+    size_t cell_lists_cap = 0;        // in u32
+    uint32_t cells[3] = {0, 0, 0};
+    bool cell_lists_valid = false;
+    int opt_cull_cells = 1;           // 0: every tile culls the whole range (measurement)
     sdfgpu::TapeImageHeader hdr;
     std::vector<uint32_t> opcodes;  // lowered opcode sequence (+ scalar programs' text) = the tape's structure (JIT cache key)
     uint32_t n_top_ops = 0;         // opcodes up to and including DOP_END

@@ -13,6 +13,7 @@
 namespace sdfgpu {
 
 constexpr uint32_t TRACE_MAX_BANDS = 32;
+constexpr uint32_t TRACE_OUTSIDE_RUN = 8;  // tiles without a ray per CTA of trace_tiles_kernel
 
 struct TraceParams {
     const float4* tex0;
@@ -127,6 +128,8 @@ bool jit_get(int device, int cc_major, int cc_minor, const std::vector<uint32_t>
              size_t smem_bytes, void** fn_out, int* max_ctas_per_sm, std::string* err);
 bool jit_launch(void* fn, const FillParams& p, int grid, size_t smem, cudaStream_t s, std::string* err);
 
+cudaError_t launch_cull_cells(const unsigned char* img_dev, const uint32_t dims[3], uint32_t cells_x, uint32_t cells_y,
+                              uint32_t cells_z, uint32_t* lists, uint32_t* counts, cudaStream_t s);
 cudaError_t launch_ingest(float4* tex0, float4* tex1, const float* samples_dev, size_t first, size_t n,
                           const float* lut_dev, float air_dist, int grid, cudaStream_t s);
 cudaError_t launch_ingest_scatter(float4* tex0, float4* tex1, const float* samples_dev, const uint32_t* idx_dev,

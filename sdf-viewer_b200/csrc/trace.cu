@@ -439,46 +439,51 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, ui
 template <bool SNAP, bool LINEAR, int DIST = 0, bool FULL = false>
 __global__ void __launch_bounds__(64) trace_tiles_kernel(const __grid_constant__ TraceParams P) {
     // the CTAs come band by band in the order of band_order -- a band is the tile rows [ty0, ty1) -- and within a band
-    // the tiles inside the rectangle (clipped to the band) first
-    uint32_t b = blockIdx.x, tx, ty, band = 0, ty0 = 0, ty1 = P.tiles_y;
-    for (uint32_t k = 0; k < P.n_bands; ++k) {
-        band = P.band_order[k];
-        ty0 = band * P.band_rows; ty1 = min(ty0 + P.band_rows, P.tiles_y);
-        const uint32_t n = P.tiles_x * (ty1 - ty0);
-        if (b < n) break;
-        b -= n;
-    }
-    const uint32_t ry0 = min(max(P.rect[1], ty0), ty1), ry1 = min(max(P.rect[3], ty0), ty1);
-    const uint32_t rw = P.rect[2] - P.rect[0], rh = ry1 - ry0;
-    const uint32_t n_heavy = rw * rh;
-    bool outside = false;
-    if (b < n_heavy) {
-        tx = P.rect[0] + b % rw; ty = ry0 + b / rw;
-    } else {
-        outside = true;
-        b -= n_heavy;
-        const uint32_t n_top = (ry0 - ty0) * P.tiles_x, side = P.tiles_x - rw;
-        if (b < n_top) {
-            tx = b % P.tiles_x; ty = ty0 + b / P.tiles_x;
-        } else if (b - n_top < rh * side) {
-            b -= n_top;
-            const uint32_t k = b % side;
-            ty = ry0 + b / side; tx = k < P.rect[0] ? k : k + rw;
-        } else {
-            b -= n_top + rh * side;
-            tx = b % P.tiles_x; ty = ry1 + b / P.tiles_x;
+    // first one CTA per tile inside the rectangle (clipped to the band), then one per run of TRACE_OUTSIDE_RUN tiles
+    // outside it (no ray, stores only: a CTA per tile costs more to schedule than its 64 pixels take to write)
+    uint32_t b = blockIdx.x, band = 0, ty0 = 0, ty1 = P.tiles_y, ry0, ry1, rw, n_heavy, n_out, n_ctas;
+    for (uint32_t k = 0;; ++k) {
+        if (P.n_bands) {
+            band = P.band_order[k];
+            ty0 = band * P.band_rows; ty1 = min(ty0 + P.band_rows, P.tiles_y);
         }
+        ry0 = min(max(P.rect[1], ty0), ty1); ry1 = min(max(P.rect[3], ty0), ty1);
+        rw = P.rect[2] - P.rect[0];
+        n_heavy = rw * (ry1 - ry0);
+        n_out = P.tiles_x * (ty1 - ty0) - n_heavy;
+        n_ctas = n_heavy + (n_out + TRACE_OUTSIDE_RUN - 1u) / TRACE_OUTSIDE_RUN;
+        if (b < n_ctas || k + 1u >= P.n_bands) break;
+        b -= n_ctas;
     }
-    const uint32_t i = tx * 8u + (threadIdx.x & 7u), j = ty * 8u + (threadIdx.x >> 3);
-    if (i < P.width && j < P.height) {
-        if (outside) write_outside(P, (size_t)j * P.width + i);
-        else trace_pixel<SNAP, LINEAR, DIST, FULL>(P, i, j);
+    const uint32_t rh = ry1 - ry0;
+    if (b < n_heavy) {
+        const uint32_t tx = P.rect[0] + b % rw, ty = ry0 + b / rw;
+        const uint32_t i = tx * 8u + (threadIdx.x & 7u), j = ty * 8u + (threadIdx.x >> 3);
+        if (i < P.width && j < P.height) trace_pixel<SNAP, LINEAR, DIST, FULL>(P, i, j);
+    } else {
+        const uint32_t o0 = (b - n_heavy) * TRACE_OUTSIDE_RUN, o1 = min(o0 + TRACE_OUTSIDE_RUN, n_out);
+        const uint32_t n_top = (ry0 - ty0) * P.tiles_x, side = P.tiles_x - rw;
+        for (uint32_t o = o0; o < o1; ++o) {
+            uint32_t q = o, tx, ty;
+            if (q < n_top) {
+                tx = q % P.tiles_x; ty = ty0 + q / P.tiles_x;
+            } else if (q - n_top < rh * side) {
+                q -= n_top;
+                const uint32_t k = q % side;
+                ty = ry0 + q / side; tx = k < P.rect[0] ? k : k + rw;
+            } else {
+                q -= n_top + rh * side;
+                tx = q % P.tiles_x; ty = ry1 + q / P.tiles_x;
+            }
+            const uint32_t i = tx * 8u + (threadIdx.x & 7u), j = ty * 8u + (threadIdx.x >> 3);
+            if (i < P.width && j < P.height) write_outside(P, (size_t)j * P.width + i);
+        }
     }
     if (P.n_bands) {  // the last CTA of a band of tile rows to finish: every pixel of those rows is in memory
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
-            if (atomicAdd(P.band_done + band, 1u) + 1u == P.tiles_x * (ty1 - ty0)) {
+            if (atomicAdd(P.band_done + band, 1u) + 1u == n_ctas) {
                 P.band_done[band] = 0u;
                 __threadfence();
                 *reinterpret_cast<volatile uint32_t*>(P.band_flags + band) = P.band_epoch;
@@ -1184,7 +1189,15 @@ cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s) {
     if (p.width == 0 || p.height == 0) return cudaSuccess;
     const bool snap = p.lod != 1.0f, lin = p.filter_linear != 0;
     if (variant == 0) {
-        const unsigned grid = p.tiles_x * p.tiles_y;
+        unsigned grid = 0;  // per band: a CTA per tile inside the rectangle, a CTA per run of tiles outside it
+        for (uint32_t k = 0; k < (p.n_bands ? p.n_bands : 1u); ++k) {
+            const uint32_t ty0 = p.n_bands ? k * p.band_rows : 0u;
+            const uint32_t ty1 = p.n_bands ? (ty0 + p.band_rows < p.tiles_y ? ty0 + p.band_rows : p.tiles_y) : p.tiles_y;
+            const uint32_t ry0 = p.rect[1] < ty0 ? ty0 : (p.rect[1] > ty1 ? ty1 : p.rect[1]);
+            const uint32_t ry1 = p.rect[3] < ty0 ? ty0 : (p.rect[3] > ty1 ? ty1 : p.rect[3]);
+            const uint32_t n_heavy = (p.rect[2] - p.rect[0]) * (ry1 - ry0), n_out = p.tiles_x * (ty1 - ty0) - n_heavy;
+            grid += n_heavy + (n_out + TRACE_OUTSIDE_RUN - 1u) / TRACE_OUTSIDE_RUN;
+        }
         const uint32_t mode = lin ? p.dist_mode : 0u;  // the distance volumes serve the LINEAR march only
         if (p.full_dist) {  // exact multi-GPU trace: replicated full-grid distance volume, hits shaded by their owner
             if (!snap && lin) trace_tiles_kernel<false, true, 1, true><<<grid, 64, 0, s>>>(p);

@@ -142,6 +142,41 @@ def test_csg_tape(S, oracle, n_prims, vpt, program):
     assert_same_volume(t0, t1, o.tex0, o.tex1)
 
 
+@pytest.mark.parametrize("program,vpt", [("jit", 8), ("jit", 2), ("interpreter", 4)])
+def test_csg_coarse_cell_precull(S, oracle, program, vpt):
+    """A culled UNION_RANGE on a grid of several 64^3-voxel cells (ragged in every axis): tiles start from their cell's
+    survivors (option fill_cull_cells, default) -- the same volume as culling the whole range per tile, and as the
+    oracle's plain fold; also through the two-pass progressive load (step-2 lattice tiles straddle cells) and a dirty
+    box that starts off the tile grid."""
+    n_prims = 300
+    table = S.tape.csg_primitive_table(n_prims, seed=11)
+    tape = S.tape.csg_tape(table)
+    dims = (160, 130, 70)
+    o = oracle.Viewer(BB, dims, 2)
+    o.update(oracle.Sampler(tape=tape))
+    vols = []
+    for cells in (1, 0):
+        with S.SDFViewer.new_voxels(dims, BB, 2) as v:
+            v.set_option("fill_voxels_per_thread", vpt)
+            v.set_option("fill_program", PROGRAMS[program][0])
+            v.set_option("fill_cull_cells", cells)
+            v.set_tape(tape)
+            v.update(None)                       # pass of step 2, then step 1
+            t0, t1 = v.download()
+            assert_same_volume(t0, t1, o.tex0, o.tex1)
+            st = v.cull_stats()                  # (one more fill_all)
+            other = S.tape.csg_tape(S.tape.csg_primitive_table(40, seed=5))
+            v.set_tape(other)
+            v.resample_box((-0.37, -0.41, -0.29, 0.53, 0.22, 0.61))
+            vols.append((v.download(), st))
+    (a0, a1), st_cells = vols[0]
+    (b0, b1), st_full = vols[1]
+    assert_same_volume(a0, a1, b0, b1)
+    # the primitive with the least upper bound over a tile is never dropped by its cell (bounds over a larger box are
+    # wider), so the tile's threshold -- and with it the tile's survivors -- are the same with and without the pre-cull
+    assert st_cells == st_full and st_cells["survivors_mean"] >= 1
+
+
 @pytest.mark.parametrize("program", ["interpreter", "jit"])
 def test_generic_ops_tape(S, oracle, program):
     """Every opcode of include/sdfgpu_tape.h at least once."""
