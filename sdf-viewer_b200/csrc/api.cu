@@ -1992,6 +1992,7 @@ SDFGPU_API int sdfgpu_sync(sdfgpu_ctx* ctx) {
     if (!ctx) return fail(nullptr, SDFGPU_ERR_INVALID, "NULL ctx");
     set_device(ctx);
     CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->link.present_stream) CK(ctx, cudaStreamSynchronize(ctx->link.present_stream));  // a presenter's unpack and copies
     return SDFGPU_OK;
 }
 

@@ -143,7 +143,7 @@ bool link_timing() {
     return on;
 }
 
-void timing_mark(sdfgpu_ctx* ctx) {
+void timing_mark(sdfgpu_ctx* ctx, cudaStream_t s = nullptr) {
     if (!link_timing()) return;
     LinkState& L = ctx->link;
     if (L.timing_used == L.timing_events.size()) {
@@ -151,7 +151,7 @@ void timing_mark(sdfgpu_ctx* ctx) {
         if (cudaEventCreate(&e) != cudaSuccess) return;
         L.timing_events.push_back(e);
     }
-    (void)cudaEventRecord(L.timing_events[L.timing_used++], ctx->stream);
+    (void)cudaEventRecord(L.timing_events[L.timing_used++], s ? s : ctx->stream);
 }
 
 // tell both neighbours that fill number `epoch` of this rank is in their halo slices
@@ -264,6 +264,10 @@ int sdfgpu::link_trace_begin(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t
         // the presenter's key frame of this parity was last used by frame t - 2 (the single G-buffer frame by t - 1)
         const uint32_t need = want_gbuf ? t : (t >= 1u ? t - 1u : 0u);
         if ((rc = wait_flag(ctx, ctx->stream, &hd->consumed, need)) != SDFGPU_OK) return rc;
+    } else if (L.present_stream) {
+        // the same for the presenter's own kernel: frame t - 2 (t - 1) has been unpacked on the presenter's stream
+        if (want_gbuf || L.last_gbuf) { if (t >= 1u) CK(ctx, cudaStreamWaitEvent(ctx->stream, L.ev_presented, 0)); }
+        else if (t >= 2u) CK(ctx, cudaStreamWaitEvent(ctx->stream, L.ev_unpacked[t & 1u], 0));
     }
     L.cur_w = w; L.cur_h = h; L.cur_round = 0;
     L.cur_gbuf = want_gbuf;
@@ -412,27 +416,43 @@ int sdfgpu::link_trace_end(sdfgpu_ctx* ctx, uint8_t* rgba8, float* depth, float*
     const uint32_t t = L.frame_epoch - 1u;
     int rc;
     if (L.rank == 0) {
+        if (!L.present_stream) {
+            CK(ctx, cudaStreamCreateWithFlags(&L.present_stream, cudaStreamNonBlocking));
+            CK(ctx, cudaEventCreateWithFlags(&L.ev_traced, cudaEventDisableTiming));
+            CK(ctx, cudaEventCreateWithFlags(&L.ev_unpacked[0], cudaEventDisableTiming));
+            CK(ctx, cudaEventCreateWithFlags(&L.ev_unpacked[1], cudaEventDisableTiming));
+            CK(ctx, cudaEventCreateWithFlags(&L.ev_presented, cudaEventDisableTiming));
+        }
+        cudaStream_t ps = L.present_stream;
+        CK(ctx, cudaEventRecord(L.ev_traced, ctx->stream));
+        CK(ctx, cudaStreamWaitEvent(ps, L.ev_traced, 0));
         ArenaHeader* hd = hdr_of(L.arena);
         for (uint32_t r = 1; r < L.world; ++r)
-            if ((rc = wait_flag(ctx, ctx->stream, &hd->frame_done[r], t + 1u)) != SDFGPU_OK) return rc;
-        timing_mark(ctx);
+            if ((rc = wait_flag(ctx, ps, &hd->frame_done[r], t + 1u)) != SDFGPU_OK) return rc;
+        timing_mark(ctx, ps);
         const ArenaLayout lay = arena_layout(L.max_pixels, L.want_gbuf);
         const size_t n = (size_t)L.cur_w * L.cur_h;
         CK(ctx, launch_keys_unpack(reinterpret_cast<const unsigned long long*>(L.arena + lay.keys[t & 1u]), (uint32_t)n,
-                                   reinterpret_cast<uint8_t*>(ctx->rgba8_dev), ctx->depth_dev, ctx->stream));
+                                   reinterpret_cast<uint8_t*>(ctx->rgba8_dev), ctx->depth_dev, ps));
         ctx->launches++;
-        if (rgba8) CK(ctx, cudaMemcpyAsync(rgba8, ctx->rgba8_dev, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (depth) CK(ctx, cudaMemcpyAsync(depth, ctx->depth_dev, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaEventRecord(L.ev_unpacked[t & 1u], ps));
+        if (rgba8) CK(ctx, cudaMemcpyAsync(rgba8, ctx->rgba8_dev, n * 4, cudaMemcpyDeviceToHost, ps));
+        if (depth) CK(ctx, cudaMemcpyAsync(depth, ctx->depth_dev, n * 4, cudaMemcpyDeviceToHost, ps));
         if (gbuf && L.cur_gbuf)
-            CK(ctx, cudaMemcpyAsync(gbuf, L.arena + lay.gbuf, n * SDFGPU_GBUF_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(ctx, cudaMemcpyAsync(gbuf, L.arena + lay.gbuf, n * SDFGPU_GBUF_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ps));
         uint32_t* flags[LINK_MAX_WORLD];
         uint32_t values[LINK_MAX_WORLD];
         int m = 0;
         for (uint32_t r = 1; r < L.world; ++r) { flags[m] = &peer_hdr(ctx, (int)r)->consumed; values[m++] = t + 1u; }
-        if ((rc = signal_flags(ctx, ctx->stream, flags, values, m)) != SDFGPU_OK) return rc;
+        if ((rc = signal_flags(ctx, ps, flags, values, m)) != SDFGPU_OK) return rc;
+        CK(ctx, cudaEventRecord(L.ev_presented, ps));
+        L.last_gbuf = L.cur_gbuf;
+        timing_mark(ctx, ps);
+    } else {
+        timing_mark(ctx);
     }
-    timing_mark(ctx);
     if (sync) {
+        if (L.present_stream) CK(ctx, cudaStreamSynchronize(L.present_stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
         if (link_timing() && L.timing_used >= 2) {
             std::string line = "[sdfgpu link timing] rank " + std::to_string(L.rank) + " frame " + std::to_string(t) + " us:";
@@ -479,6 +499,9 @@ void sdfgpu::link_free(sdfgpu_ctx* ctx) {
         }
     }
     (void)cudaFree(L.arena);
+    if (L.present_stream) { (void)cudaStreamSynchronize(L.present_stream); (void)cudaStreamDestroy(L.present_stream); }
+    for (cudaEvent_t e : {L.ev_traced, L.ev_unpacked[0], L.ev_unpacked[1], L.ev_presented})
+        if (e) (void)cudaEventDestroy(e);
     if (L.timed_out_host) (void)cudaFreeHost(L.timed_out_host);
     for (cudaEvent_t e : L.timing_events) (void)cudaEventDestroy(e);
     (void)cudaGetLastError();

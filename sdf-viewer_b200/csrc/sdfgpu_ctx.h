@@ -117,6 +117,12 @@ struct LinkState {
     // trace: true -- one streaming kernel per rank and frame (needs every rank on a device of its own: the kernels
     // wait for each other); false -- `world` rounds of the round kernel
     bool stream = false;
+    // presenter (rank 0): what follows its trace kernel -- waiting for the other ranks' pixels, unpacking the key
+    // frame, the copies to the host, telling the ranks -- runs on a stream of its own, so that the handle's stream goes
+    // straight on to the next fill
+    cudaStream_t present_stream = nullptr;
+    cudaEvent_t ev_traced = nullptr, ev_unpacked[2] = {nullptr, nullptr}, ev_presented = nullptr;
+    bool last_gbuf = false;  // the last frame used the (single) G-buffer frame
     uint32_t* timed_out_host = nullptr;  // mapped host word the stream kernel sets when it gives up waiting
     uint32_t timeout_ms = 20000;
     // frame in flight (begin / round / end are separate so that a single-process group can interleave ranks)
