@@ -33,8 +33,8 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 BB = ((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))
 BYTES_PER_SAMPLE = 32  # tex0 + tex1 RGBA32F (scene/sdf/mod.rs:76,196-208)
 PROGRAM_KERNEL = {0: "fill_kernel<interpreter>", 1: "sdfgpu_fill_jit", 2: "fill_kernel<demo>"}
-FILL_CAPTURE = "profiles/r01_fill_ncu_summary.txt"
-TRACE_CAPTURE = "profiles/r01_trace_ncu_summary.txt"
+FILL_CAPTURE = "profiles/r02_final_fill_ncu_summary.txt"
+TRACE_CAPTURE = "profiles/r02_final_trace_ncu_summary.txt"
 
 
 def grid_for(n_gpus, side):
@@ -113,8 +113,8 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
-CAPTURE_COMMITS = {"profiles/r01_fill_ncu_summary.txt": "7431657 (round 1)", "profiles/r01_trace_ncu_summary.txt": "1e579a6 (round 1)",
-                   "profiles/r02_fill_csg_ncu_summary.txt": "dad1a00 (round 2)"}
+CAPTURE_COMMITS = {"profiles/r02_final_fill_ncu_summary.txt": "a405693 (round 2)", "profiles/r02_final_trace_ncu_summary.txt": "a405693 (round 2)",
+                   "profiles/r02_final_fill_csg_ncu_summary.txt": "a405693 (round 2)"}
 
 
 def capture_commit(path):
@@ -338,7 +338,7 @@ def extras_single_gpu(torch, S, v, stream, W, H, side, peak):
         v.commit()
         cam = S.default_camera(W, H)
         tms = timed(torch, v, stream, lambda: v.trace_device(cam, W, H), 10)
-        alu = ncu_metrics("profiles/r02_fill_csg_ncu_summary.txt",
+        alu = ncu_metrics("profiles/r02_final_fill_csg_ncu_summary.txt",
                           {"smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
                            "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
                            "smsp__inst_executed.sum": "warp_instructions"})
@@ -348,7 +348,7 @@ def extras_single_gpu(torch, S, v, stream, W, H, side, peak):
             "voxels_per_thread": v.get_info("last_fill_voxels_per_thread"), "tile_culling": bool(v.get_info("tape_culled")),
             "hbm_frac": side ** 3 * BYTES_PER_SAMPLE / (ms * 1e-3) / 1e9 / peak, "trace_ms": tms,
             "rays_per_sec": W * H / (tms * 1e-3),
-            "ncu": dict(alu or {}, source="profiles/r02_fill_csg_ncu_summary.txt", capture_commit=capture_commit("profiles/r02_fill_csg_ncu_summary.txt"))}
+            "ncu": dict(alu or {}, source="profiles/r02_final_fill_csg_ncu_summary.txt", capture_commit=capture_commit("profiles/r02_final_fill_csg_ncu_summary.txt"))}
         try:
             st = v.cull_stats()
             out["csg_1k_512"]["cull_survivors_per_tile"] = st
