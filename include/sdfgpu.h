@@ -526,7 +526,7 @@ uint64_t sdfgpu_launch_count(const sdfgpu_ctx* ctx);
  *                  band's rows to the host while the next is traced (1: trace, then copy); same pixels
  *   "link_wait_mode" 0 cuStreamWaitValue32 when the driver has it (default) | 1 spin-wait kernels; before link_attach
  *   "link_halo_push" 0|1 and "link_trace_mode" 0 auto | 1 rounds | 2 stream: the SDFGPU_LINK_* flags as options, read by
- *                  sdfgpu_link_export;  "link_timeout_ms" (default 20000): how long a streaming trace kernel waits
+ *                  sdfgpu_link_export;  "link_timeout_ms" (default 8000): how long a streaming trace kernel waits
  *                  for rays of a neighbour that never arrives before the frame fails with SDFGPU_ERR_STATE
  *   "fill_program" 0 auto (kernel specialised for the tape structure, else built-in demo program,
  *                  else interpreter) | 1 interpreter | 2 built-in or interpreter | 3 specialised or fail */

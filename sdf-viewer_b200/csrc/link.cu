@@ -264,10 +264,12 @@ int sdfgpu::link_trace_begin(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t
         // the presenter's key frame of this parity was last used by frame t - 2 (the single G-buffer frame by t - 1)
         const uint32_t need = want_gbuf ? t : (t >= 1u ? t - 1u : 0u);
         if ((rc = wait_flag(ctx, ctx->stream, &hd->consumed, need)) != SDFGPU_OK) return rc;
-    } else if (L.present_stream) {
-        // the same for the presenter's own kernel: frame t - 2 (t - 1) has been unpacked on the presenter's stream
-        if (want_gbuf || L.last_gbuf) { if (t >= 1u) CK(ctx, cudaStreamWaitEvent(ctx->stream, L.ev_presented, 0)); }
-        else if (t >= 2u) CK(ctx, cudaStreamWaitEvent(ctx->stream, L.ev_unpacked[t & 1u], 0));
+    } else if (L.present_stream && t >= 1u) {
+        // The presenter's trace kernel comes after everything its presenter stream still has to do for the previous
+        // frame.  Not for the key frame's sake (that is the frame before): a streaming trace kernel fills every SM and
+        // WAITS for the other ranks, which wait for the `consumed` signal that follows the unpack kernel -- which would
+        // then find no SM to run on.  Between two frames there normally is a fill, during which that work is done.
+        CK(ctx, cudaStreamWaitEvent(ctx->stream, L.ev_presented, 0));
     }
     L.cur_w = w; L.cur_h = h; L.cur_round = 0;
     L.cur_gbuf = want_gbuf;
@@ -419,8 +421,6 @@ int sdfgpu::link_trace_end(sdfgpu_ctx* ctx, uint8_t* rgba8, float* depth, float*
         if (!L.present_stream) {
             CK(ctx, cudaStreamCreateWithFlags(&L.present_stream, cudaStreamNonBlocking));
             CK(ctx, cudaEventCreateWithFlags(&L.ev_traced, cudaEventDisableTiming));
-            CK(ctx, cudaEventCreateWithFlags(&L.ev_unpacked[0], cudaEventDisableTiming));
-            CK(ctx, cudaEventCreateWithFlags(&L.ev_unpacked[1], cudaEventDisableTiming));
             CK(ctx, cudaEventCreateWithFlags(&L.ev_presented, cudaEventDisableTiming));
         }
         cudaStream_t ps = L.present_stream;
@@ -435,7 +435,6 @@ int sdfgpu::link_trace_end(sdfgpu_ctx* ctx, uint8_t* rgba8, float* depth, float*
         CK(ctx, launch_keys_unpack(reinterpret_cast<const unsigned long long*>(L.arena + lay.keys[t & 1u]), (uint32_t)n,
                                    reinterpret_cast<uint8_t*>(ctx->rgba8_dev), ctx->depth_dev, ps));
         ctx->launches++;
-        CK(ctx, cudaEventRecord(L.ev_unpacked[t & 1u], ps));
         if (rgba8) CK(ctx, cudaMemcpyAsync(rgba8, ctx->rgba8_dev, n * 4, cudaMemcpyDeviceToHost, ps));
         if (depth) CK(ctx, cudaMemcpyAsync(depth, ctx->depth_dev, n * 4, cudaMemcpyDeviceToHost, ps));
         if (gbuf && L.cur_gbuf)
@@ -446,7 +445,6 @@ int sdfgpu::link_trace_end(sdfgpu_ctx* ctx, uint8_t* rgba8, float* depth, float*
         for (uint32_t r = 1; r < L.world; ++r) { flags[m] = &peer_hdr(ctx, (int)r)->consumed; values[m++] = t + 1u; }
         if ((rc = signal_flags(ctx, ps, flags, values, m)) != SDFGPU_OK) return rc;
         CK(ctx, cudaEventRecord(L.ev_presented, ps));
-        L.last_gbuf = L.cur_gbuf;
         timing_mark(ctx, ps);
     } else {
         timing_mark(ctx);
@@ -500,7 +498,7 @@ void sdfgpu::link_free(sdfgpu_ctx* ctx) {
     }
     (void)cudaFree(L.arena);
     if (L.present_stream) { (void)cudaStreamSynchronize(L.present_stream); (void)cudaStreamDestroy(L.present_stream); }
-    for (cudaEvent_t e : {L.ev_traced, L.ev_unpacked[0], L.ev_unpacked[1], L.ev_presented})
+    for (cudaEvent_t e : {L.ev_traced, L.ev_presented})
         if (e) (void)cudaEventDestroy(e);
     if (L.timed_out_host) (void)cudaFreeHost(L.timed_out_host);
     for (cudaEvent_t e : L.timing_events) (void)cudaEventDestroy(e);

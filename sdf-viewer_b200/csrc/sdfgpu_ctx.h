@@ -121,10 +121,9 @@ struct LinkState {
     // frame, the copies to the host, telling the ranks -- runs on a stream of its own, so that the handle's stream goes
     // straight on to the next fill
     cudaStream_t present_stream = nullptr;
-    cudaEvent_t ev_traced = nullptr, ev_unpacked[2] = {nullptr, nullptr}, ev_presented = nullptr;
-    bool last_gbuf = false;  // the last frame used the (single) G-buffer frame
+    cudaEvent_t ev_traced = nullptr, ev_presented = nullptr;
     uint32_t* timed_out_host = nullptr;  // mapped host word the stream kernel sets when it gives up waiting
-    uint32_t timeout_ms = 20000;
+    uint32_t timeout_ms = 8000;
     // frame in flight (begin / round / end are separate so that a single-process group can interleave ranks)
     uint32_t cur_w = 0, cur_h = 0, cur_round = 0;
     bool cur_gbuf = false;
@@ -261,7 +260,7 @@ struct sdfgpu_ctx {
     int opt_link_wait = 0;             // 0: stream memory operations when the driver has them, 1: spin-wait kernels
     int opt_link_halo_push = 0;        // before sdfgpu_link_export: 1 = SDFGPU_LINK_HALO_PUSH
     int opt_link_trace_mode = 0;       // before sdfgpu_link_export: 0 auto, 1 rounds (SDFGPU_LINK_ROUNDS), 2 stream
-    int opt_link_timeout_ms = 20000;
+    int opt_link_timeout_ms = 8000;
     uint32_t* trace_counters = nullptr;  // work_head, ctas_done of the round kernel (un-linked handles)
 };
 

@@ -1298,7 +1298,8 @@ cudaError_t launch_extract_dist_array(const float4* tex0, unsigned long long sur
 cudaError_t launch_keys_unpack(const unsigned long long* keys, uint32_t n, uint8_t* rgba8, float* depth,
                                cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    keys_unpack_kernel<<<(n + 255) / 256, 256, 0, s>>>(keys, n, rgba8, depth);
+    // small CTAs: the kernel shares the SMs with the next fill (a few hundred free registers per SM are enough)
+    keys_unpack_kernel<<<(n + 63) / 64, 64, 0, s>>>(keys, n, rgba8, depth);
     return cudaGetLastError();
 }
 

@@ -90,6 +90,14 @@ def check_linked(rank, world, local, dims, w, h, sdf, full, want_its, halo_push=
             whole.fill_all()
             want8, want_d = whole.trace_rgba8(cams[1], w, h)
             assert np.array_equal(got8, want8) and np.array_equal(got_d.view(np.uint32), np.clip(want_d, 0, 1).view(np.uint32))
+        # ... and frames with NOTHING between them: the presenter's unpack of frame t must not be locked out by the
+        # streaming kernel of frame t + 1, which fills every SM and waits for the ranks that wait for that unpack
+        for c in cams * 4:
+            sv.trace_device(c, w, h)
+        got8, got_d = sv.trace_host(cams[2], w, h)
+        if rank == 0:
+            want8, want_d = whole.trace_rgba8(cams[2], w, h)
+            assert np.array_equal(got8, want8) and np.array_equal(got_d.view(np.uint32), np.clip(want_d, 0, 1).view(np.uint32))
     dist.barrier()
     if rank == 0:
         print(f"linked path ok: world {world}, halo {'pushed' if halo_push else 'filled locally'}, trace "
