@@ -996,9 +996,15 @@ struct Lowerer {
     // can be recognised by what it computes: a (f32, f32) -> f32 function that returns C's fmodf bit for bit on a
     // grid of probes (signed zeros, denormals, huge ratios, infinities, NaN) is one, whatever its instructions
     // are, and a call of it with symbolic arguments becomes one SDFT_S_FMOD op.
+    // It must also leave nothing behind: a call that is replaced by one op loses whatever else the callee did.  A probe
+    // run may write below the caller's shadow-stack pointer (global 0 of a Rust / clang guest: the callee's own frame),
+    // nowhere else; it may not change a global, and it may not call a host import.  SDFGPU_WASM_NO_LIBM=1 switches the
+    // recognition off altogether (such a guest is then sampled on the host).
     bool behaves_like_fmodf(const State& at, uint32_t fi) {
         auto it = libm_class.find(fi);
         if (it != libm_class.end()) return it->second == 1;
+        static const bool disabled = [] { const char* e = getenv("SDFGPU_WASM_NO_LIBM"); return e && *e && *e != '0'; }();
+        if (disabled) { libm_class[fi] = 0; return false; }
         static const float xs[] = {0.0f, -0.0f, 1.0f, -1.0f, 0.3f, 5.5f, -7.25f, 1e-3f, 123456.7f, 1e30f, -1e-30f, 1e-40f, 0.75f, 2.5f,
                                    16777216.0f, -3.4e38f, 0.1f};
         static const float ys[] = {0.5f, 0.25f, 1.0f, 3.0f, -2.0f, 0.1f, 1e-40f, 1e30f, 0.0f, -0.0f, 7.0f, 1.17549435e-38f};
@@ -1010,7 +1016,9 @@ struct Lowerer {
         // the probes must not disturb the lowering in progress
         const std::string saved_err = err;
         const uint64_t saved_budget = budget;
-        const uint32_t saved_leaves = leaves, saved_depth = fork_depth;
+        const uint32_t saved_leaves = leaves, saved_depth = fork_depth, saved_imports = skipped_imports;
+        const bool have_sp = !at.globals.empty() && at.globals[0].ty == T_I32 && !at.globals[0].sym;
+        const uint32_t sp0 = have_sp ? (uint32_t)at.globals[0].bits : 0u;
         bool same = true;
         for (size_t k = 0; k < probes.size() && same; ++k) {
             State t;
@@ -1029,7 +1037,17 @@ struct Lowerer {
             const float want = fmodf(probes[k].first, probes[k].second);
             const float got = f32_of(l.vals[0].bits);
             same = (got != got && want != want) || bits_of(got) == bits_of(want);
+            // no side effects: host imports, globals, memory outside the callee's own stack frame
+            if (skipped_imports != saved_imports || t.globals.size() != at.globals.size()) same = false;
+            for (size_t g = 0; g < at.globals.size() && same; ++g)
+                if (t.globals[g].sym != at.globals[g].sym || t.globals[g].bits != at.globals[g].bits || t.globals[g].node != at.globals[g].node) same = false;
+            for (auto c = t.mem.begin(); c != t.mem.end() && same; ++c) {
+                const auto before = at.mem.find(c->first);
+                const bool changed = before == at.mem.end() || before->second.sym != c->second.sym || before->second.w != c->second.w;
+                if (changed && !(have_sp && c->first < sp0 && sp0 - c->first <= 1024u)) same = false;  // a leaf's frame is small
+            }
         }
+        skipped_imports = saved_imports;
         err = saved_err;
         budget = saved_budget;
         leaves = saved_leaves;

@@ -500,3 +500,16 @@ def test_errors(S):
             v.set_option("nope", 1)
     h = C.c_void_p()
     assert lib.sdfgpu_create((C.c_float * 6)(-1, -1, -1, 1, 1, 1), 16, 2, 999, C.byref(h)) == -1
+
+
+def test_jit_cache_is_bounded():
+    """The cache of specialised kernels keeps the most recently used ones and unloads the rest (jit.cu): run with a
+    bound of 2 over 4 tape structures, twice (tests/jit_cache_check.py; the bound is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "jit_cache_check.py")], capture_output=True, text=True,
+                       timeout=600, env=dict(os.environ, SDFGPU_JIT_CACHE="2"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "jit_cache_check ok" in r.stdout

@@ -454,6 +454,34 @@ def test_fmodf_is_recognised_by_what_it_computes(S, oracle):
     assert e.value.code == -3 and "depend on the position" in str(e.value)
 
 
+@pytest.mark.parametrize("effect", ["store", "global", "stack_frame"])
+def test_fmodf_with_a_side_effect_is_not_replaced(S, oracle, effect):
+    """A callee that returns fmodf on every probe but also leaves something behind -- a store to guest memory, a changed
+    global -- is NOT replaced by the one-op fmod (the side effect would be lost); writing into its own shadow-stack frame
+    (below the caller's stack pointer, global 0) is what compiled code does and is accepted."""
+    m = base_module()
+    sp = m.global_(I32, 60000)                    # __stack_pointer
+    counter = m.global_(I32, 0)
+    f = add_musl_fmodf(m)
+    t, locs, body = m.funcs[f - len(m.imports)]
+    if effect == "store":
+        body[0:0] = [("i32.const", 512), ("i32.const", 512), ("i32.load", 0), ("i32.const", 1), "i32.add", ("i32.store", 0)]
+    elif effect == "global":
+        body[0:0] = [("global.get", counter), ("i32.const", 1), "i32.add", ("global.set", counter)]
+    else:
+        body[0:0] = [("global.get", sp), ("i32.const", 16), "i32.sub", ("local.get", 0), ("f32.store", 0)]  # a spill
+    m.func(*SAMPLE_SIG, body=store_out(0, [X, ("f32.const", 0.5), ("call", f)]) + [("i32.const", OUT)], export="sample")
+    if effect == "stack_frame":
+        tape, _, summary = S.wasm.lower(m.build())
+        assert "1 fmodf calls recognised" in summary
+        p = points(200, seed=5)
+        assert same(oracle.tape_sample(tape, p)[:, 0], np.fmod(p[:, 0], f32(0.5)))
+    else:
+        with pytest.raises(S.WasmLoweringError) as e:
+            S.wasm.lower(m.build())
+        assert e.value.code == -3
+
+
 def test_the_reference_demo_as_a_wasm_guest(S, oracle):
     """SDFDemo hand-compiled to WebAssembly lowers to a scalar program that reproduces the oracle's direct restatement
     of `SDFDemo::sample` bit for bit -- on random points, on the voxel positions of a grid (where the seams, brick joints
