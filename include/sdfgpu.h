@@ -114,6 +114,9 @@ int sdfgpu_ipc_detach(sdfgpu_ctx* ctx);
  *          frame equals sdfgpu_trace_rgba8 of ONE handle holding the whole grid bit for bit (RGBA8, depth, and the
  *          G-buffer but for the normals of hits next to a slab face).  Finished pixels are stored straight into the frame
  *          of rank 0 (the presenter), which alone receives rgba8 / depth / gbuf; the other ranks pass NULL.
+ * A streaming trace whose neighbour does not take part within "link_timeout_ms" fails with SDFGPU_ERR_STATE on every
+ * rank that waited; the link's queues are then in an undefined state: detach and link again.  sdfgpu_cull_stats runs a
+ * fill and is therefore collective on a linked handle, too.
  * Link a handle right after creating it (volumes still AIR_DIST), use frames of at most max_width * max_height pixels,
  * and detach every rank before destroying any of them.  SDFGPU_LINK_GBUF reserves a G-buffer frame (tests). */
 #define SDFGPU_LINK_BLOB_BYTES 320

@@ -1471,6 +1471,10 @@ int sdfgpu::ensure_frame(sdfgpu_ctx* ctx, uint32_t w, uint32_t h, bool want_gbuf
     const size_t n = (size_t)w * h;
     if (w != ctx->fw || h != ctx->fh) {
         CK(ctx, cudaStreamSynchronize(ctx->stream));
+        // ... and whoever else may still read the old frame: a linked presenter's unpack and copies, the banded copies
+        if (ctx->link.present_stream) CK(ctx, cudaStreamSynchronize(ctx->link.present_stream));
+        if (ctx->copy_stream) CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        if (ctx->copy_stream2) CK(ctx, cudaStreamSynchronize(ctx->copy_stream2));
         (void)cudaFree(ctx->rgba_dev); (void)cudaFree(ctx->depth_dev); (void)cudaFree(ctx->gbuf_dev);
         (void)cudaFree(ctx->keys_dev); (void)cudaFree(ctx->rgba8_dev);
         ctx->rgba_dev = nullptr; ctx->depth_dev = nullptr; ctx->gbuf_dev = nullptr; ctx->keys_dev = nullptr;
@@ -1773,14 +1777,19 @@ SDFGPU_API int sdfgpu_trace_rgba8(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uin
     if ((rc = launch_trace_any(ctx, tp)) != SDFGPU_OK) return rc;
     for (uint32_t i = 0; i < tp.n_bands; ++i) {
         const uint32_t k = tp.band_order[i];
-        if (!stream_wait_value(ctx->copy_stream, tp.band_flags + k, tp.band_epoch))
+        if (!stream_wait_value(ctx->copy_stream, tp.band_flags + k, tp.band_epoch)) {
+            // nothing may still write the caller's buffers when this returns
+            (void)cudaStreamSynchronize(ctx->stream); (void)cudaStreamSynchronize(ctx->copy_stream); (void)cudaStreamSynchronize(ctx->copy_stream2);
             return fail(ctx, SDFGPU_ERR_CUDA, "cuStreamWaitValue32 failed");
+        }
         const uint32_t y0 = k * tp.band_rows * 8u, y1 = (k + 1) * tp.band_rows * 8u < height ? (k + 1) * tp.band_rows * 8u : height;
         const size_t off = (size_t)y0 * width, cnt = (size_t)(y1 - y0) * width;
         if (rgba8) CK(ctx, cudaMemcpyAsync(rgba8 + off * 4, ctx->rgba8_dev + off, cnt * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
         if (depth) {  // colour and depth on a stream each: the fixed cost of the small copies overlaps
-            if (!stream_wait_value(ctx->copy_stream2, tp.band_flags + k, tp.band_epoch))
+            if (!stream_wait_value(ctx->copy_stream2, tp.band_flags + k, tp.band_epoch)) {
+                (void)cudaStreamSynchronize(ctx->stream); (void)cudaStreamSynchronize(ctx->copy_stream); (void)cudaStreamSynchronize(ctx->copy_stream2);
                 return fail(ctx, SDFGPU_ERR_CUDA, "cuStreamWaitValue32 failed");
+            }
             CK(ctx, cudaMemcpyAsync(depth + off, ctx->depth_dev + off, cnt * 4, cudaMemcpyDeviceToHost, ctx->copy_stream2));
         }
     }
