@@ -229,6 +229,7 @@ class SDFViewer {
     BoundingBox bounding_box;
 
    private:
+    friend class SDFViewerGroup;
     SDFViewer(sdfgpu_ctx* h, const BoundingBox& bb) : bounding_box(bb), h_(h) {}
     static std::array<float, 6> flat(const BoundingBox& bb) {
         return {bb[0].x, bb[0].y, bb[0].z, bb[1].x, bb[1].y, bb[1].z};
@@ -295,6 +296,91 @@ class SDFViewer {
     };
 
     sdfgpu_ctx* h_ = nullptr;
+};
+
+// The same viewer over several GPUs, driven by ONE thread like the reference's scene (scene/mod.rs:22-31,158-225):
+// the grid is sharded along z over the devices, every call runs on all of them, and render() returns the frame of
+// one SDFViewer holding the whole grid, bit for bit (include/sdfgpu.h "linked slabs", sdfgpu_group_*).  Not in the
+// reference.
+class SDFViewerGroup {
+   public:
+    // SDFViewer::from_bb over the devices of `device_mask` (bit d = CUDA device d); frames of at most max_width x max_height
+    static SDFViewerGroup from_bb(const BoundingBox& bb, uint32_t max_voxels_side, uint32_t loading_passes, uint32_t device_mask,
+                                  uint32_t max_width = 1920, uint32_t max_height = 1080) {
+        const std::array<float, 6> b = SDFViewer::flat(bb);
+        sdfgpu_group* g = nullptr;
+        check(sdfgpu_group_create_mask(b.data(), max_voxels_side, loading_passes, device_mask, max_width, max_height, &g));
+        return SDFViewerGroup(g, bb);
+    }
+    // SDFViewer::new_voxels over an explicit device list (a device may appear more than once)
+    static SDFViewerGroup new_voxels(std::array<uint32_t, 3> voxels, const BoundingBox& bb, uint32_t loading_passes,
+                                     const std::vector<int>& devices, uint32_t max_width = 1920, uint32_t max_height = 1080) {
+        const std::array<float, 6> b = SDFViewer::flat(bb);
+        sdfgpu_group* g = nullptr;
+        check(sdfgpu_group_create(b.data(), voxels.data(), loading_passes, devices.data(), (uint32_t)devices.size(), max_width,
+                                  max_height, 0, &g));
+        return SDFViewerGroup(g, bb);
+    }
+    SDFViewerGroup(SDFViewerGroup&& o) noexcept : bounding_box(o.bounding_box), g_(o.g_) { o.g_ = nullptr; }
+    SDFViewerGroup(const SDFViewerGroup&) = delete;
+    SDFViewerGroup& operator=(const SDFViewerGroup&) = delete;
+    ~SDFViewerGroup() { sdfgpu_group_destroy(g_); }
+
+    uint32_t size() const { return sdfgpu_group_size(g_); }
+
+    template <class Rep, class Period>
+    size_t update(const SDFSurface& sdf, std::chrono::duration<Rep, Period> max_delta_time) {  // SDFViewer::update
+        SDFViewer::Trampoline t{&sdf, {}, nullptr};
+        sdfgpu_surface s;
+        std::memset(&s, 0, sizeof s);
+        s.self = &t;
+        s.bounding_box = &SDFViewer::Trampoline::bounding_box;
+        s.sample = &SDFViewer::Trampoline::sample;
+        s.sample_batch = &SDFViewer::Trampoline::sample_batch;
+        s.changed = &SDFViewer::Trampoline::changed;
+        s.tape = &SDFViewer::Trampoline::tape;
+        s.sample_threads = sdf.sample_threads();
+        uint64_t iterations = 0;
+        const int rc = sdfgpu_group_update_surface(g_, &s, std::chrono::duration<double>(max_delta_time).count(), &iterations);
+        if (t.error) std::rethrow_exception(t.error);
+        gcheck(rc);
+        return (size_t)iterations;
+    }
+    void commit() { gcheck(sdfgpu_group_commit(g_)); }
+    uint64_t loading_len() const {
+        uint64_t v = 0;
+        gcheck(sdfgpu_group_loading_state(g_, &v, nullptr, nullptr, nullptr));
+        return v;
+    }
+    std::array<uint32_t, 3> voxels() const {
+        std::array<uint32_t, 3> d{};
+        check(sdfgpu_dims(sdfgpu_group_rank(g_, 0), d.data()));
+        return d;
+    }
+    void download(std::vector<float>* tex0, std::vector<float>* tex1) {  // the whole grid
+        const auto d = voxels();
+        const size_t n = (size_t)d[0] * d[1] * d[2] * 4;
+        if (tex0) tex0->resize(n);
+        if (tex1) tex1->resize(n);
+        gcheck(sdfgpu_group_download(g_, tex0 ? tex0->data() : nullptr, tex1 ? tex1->data() : nullptr));
+    }
+    Frame render(const sdfgpu_camera& camera, uint32_t width, uint32_t height) {  // volume.render(&camera, lights)
+        Frame f;
+        f.width = width; f.height = height;
+        f.rgba8.resize((size_t)width * height * 4);
+        f.depth.resize((size_t)width * height);
+        gcheck(sdfgpu_group_trace_rgba8(g_, &camera, width, height, f.rgba8.data(), f.depth.data()));
+        return f;
+    }
+    sdfgpu_group* handle() { return g_; }
+    BoundingBox bounding_box;
+
+   private:
+    SDFViewerGroup(sdfgpu_group* g, const BoundingBox& bb) : bounding_box(bb), g_(g) {}
+    void gcheck(int rc) const {
+        if (rc != SDFGPU_OK) throw Error(rc, sdfgpu_group_last_error(g_));
+    }
+    sdfgpu_group* g_ = nullptr;
 };
 
 // ---------------------------------------------------------------- tape (include/sdfgpu_tape.h)

@@ -151,6 +151,34 @@ static int run_gpu(const std::string& out) {
         }
         REQUIRE(rejected);
     }
+    // (4) the same viewer as a GROUP of slabs (here three on device 0; one per GPU on a multi-GPU host): one thread drives
+    // all of them, and volumes and frame equal the single viewer's bit for bit
+    {
+        sdfgpu::SDFDemo sdf, sdf2;
+        auto one = sdfgpu::SDFViewer::new_voxels({40, 36, 30}, sdf.bounding_box(), 2);
+        auto group = sdfgpu::SDFViewerGroup::new_voxels({40, 36, 30}, sdf.bounding_box(), 2, {0, 0, 0}, 160, 120);
+        REQUIRE(group.size() == 3 && group.voxels() == one.voxels());
+        size_t frames = 0;
+        const size_t total = load(one, sdf, std::chrono::milliseconds(30), &frames);
+        size_t got = 0;
+        while (group.loading_len() > 0) {
+            got += group.update(sdf2, std::chrono::milliseconds(30));
+            group.commit();
+        }
+        REQUIRE(got == total);
+        std::vector<float> a0, a1, b0, b1;
+        one.download(&a0, &a1);
+        group.download(&b0, &b1);
+        REQUIRE(a0.size() == b0.size() && std::memcmp(a0.data(), b0.data(), a0.size() * 4) == 0);
+        REQUIRE(std::memcmp(a1.data(), b1.data(), a1.size() * 4) == 0);
+        const sdfgpu_camera cam = sdfgpu::SDFViewer::default_camera(160, 120);
+        const sdfgpu::Frame fa = one.render(cam, 160, 120), fb = group.render(cam, 160, 120);
+        REQUIRE(fa.rgba8 == fb.rgba8);
+        REQUIRE(std::memcmp(fa.depth.data(), fb.depth.data(), fa.depth.size() * 4) == 0);
+        auto solo = sdfgpu::SDFViewerGroup::from_bb(sdf.bounding_box(), 16, 1, 1u, 64, 48);  // a mask of one device
+        REQUIRE(solo.size() == 1);
+        std::printf("group of %u slabs == one viewer\n", group.size());
+    }
     std::printf("gpu ok\n");
     return 0;
 }
