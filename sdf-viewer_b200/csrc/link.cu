@@ -49,7 +49,7 @@ struct ArenaHeader {
     uint32_t ctas_done;
     uint32_t timed_out;
     uint32_t tiles_done;      // stream trace: tile units finished
-    uint32_t pad0;
+    uint32_t outside_done;    // stream trace, presenter: units of tiles outside the box's screen rectangle finished
     uint32_t in_head[2];      // stream trace: in-queue units claimed [0 from below | 1 from above]
     uint32_t in_done[2];      //   ... and finished
     uint32_t frame_done[LINK_MAX_WORLD];
@@ -58,7 +58,8 @@ struct ArenaHeader {
     uint32_t sent_final[2];   // stream trace: this rank has closed its out-queue [0 down | 1 up]
     unsigned long long in_final[2][2];  // stream trace, [frame parity][from below | above], written by the neighbours:
                                         // frame tag << 32 | entries in that in-queue (the queue is closed)
-    uint32_t pad2[10];
+    uint32_t outside_flag;    // stream trace, presenter: frame tag of the last frame whose outside tiles are all written
+    uint32_t pad2[9];
 };
 static_assert(sizeof(ArenaHeader) == 256, "arena header is 256 bytes");
 static_assert(offsetof(ArenaHeader, in_final) % 8 == 0, "64-bit words are aligned");
@@ -272,6 +273,7 @@ int sdfgpu::link_trace_begin(sdfgpu_ctx* ctx, const sdfgpu_camera* cam, uint32_t
         CK(ctx, cudaStreamWaitEvent(ctx->stream, L.ev_presented, 0));
     }
     L.cur_w = w; L.cur_h = h; L.cur_round = 0;
+    L.cur_outside_first = false;
     L.cur_gbuf = want_gbuf;
     L.in_frame = true;
     L.timing_used = 0;
@@ -389,7 +391,13 @@ int sdfgpu::link_trace_stream(sdfgpu_ctx* ctx) {
     if (L.rank != 0) {
         lp.sig_frame = &hdr_of(pa)->frame_done[L.rank];
         lp.sig_frame_value = t + 1u;
+    } else if (L.memops) {
+        // the presenter's own tiles outside the box's rectangle: first, and straight into the frame (link_trace_end
+        // copies the rows that hold nothing else to the host while the rest is traced)
+        lp.out_rgba8 = ctx->rgba8_dev; lp.out_depth = ctx->depth_dev;
+        lp.outside_done = &hd->outside_done; lp.outside_flag = &hd->outside_flag;
     }
+    L.cur_outside_first = lp.out_rgba8 != nullptr;
     const int per_sm = trace_stream_max_ctas_per_sm(ctx->link_tp);
     if (per_sm < 1) return fail(ctx, SDFGPU_ERR_CUDA, "the trace kernel does not fit on an SM");
     timing_mark(ctx);
@@ -424,19 +432,43 @@ int sdfgpu::link_trace_end(sdfgpu_ctx* ctx, uint8_t* rgba8, float* depth, float*
             CK(ctx, cudaEventCreateWithFlags(&L.ev_presented, cudaEventDisableTiming));
         }
         cudaStream_t ps = L.present_stream;
+        ArenaHeader* hd = hdr_of(L.arena);
+        const ArenaLayout lay = arena_layout(L.max_pixels, L.want_gbuf);
+        const size_t n = (size_t)L.cur_w * L.cur_h;
+        // pixel rows [y0, y1) hold the tiles inside the screen rectangle of the box; the rows above and below hold only
+        // pixels the presenter's kernel wrote first, straight into the frame (LinkParams::out_rgba8): they cross PCIe
+        // while the frame is still being traced, behind the kernel's outside_flag
+        size_t y0 = 0, y1 = L.cur_h;
+        if (L.cur_outside_first) {
+            const TraceParams& tp = ctx->link_tp;
+            const uint32_t tiles_y4 = (tp.height + 3u) / 4u;
+            const uint32_t ry0 = tp.rect[1] * 2u < tiles_y4 ? tp.rect[1] * 2u : tiles_y4;
+            const uint32_t ry1 = tp.rect[3] * 2u < tiles_y4 ? tp.rect[3] * 2u : tiles_y4;
+            y0 = (size_t)ry0 * 4u;
+            y1 = (size_t)ry1 * 4u < L.cur_h ? (size_t)ry1 * 4u : L.cur_h;
+            if (tp.rect[2] <= tp.rect[0] || y1 <= y0) y0 = y1 = 0;  // no tile inside: every row is an outside row
+            if ((rgba8 || depth) && (y0 > 0 || y1 < L.cur_h)) {
+                if ((rc = wait_flag(ctx, ps, &hd->outside_flag, t + 1u)) != SDFGPU_OK) return rc;
+                const size_t w = L.cur_w, lo = y0 * w, hi = y1 * w;
+                if (rgba8 && lo) CK(ctx, cudaMemcpyAsync(rgba8, ctx->rgba8_dev, lo * 4, cudaMemcpyDeviceToHost, ps));
+                if (depth && lo) CK(ctx, cudaMemcpyAsync(depth, ctx->depth_dev, lo * 4, cudaMemcpyDeviceToHost, ps));
+                if (rgba8 && hi < n) CK(ctx, cudaMemcpyAsync(rgba8 + hi * 4, ctx->rgba8_dev + hi, (n - hi) * 4, cudaMemcpyDeviceToHost, ps));
+                if (depth && hi < n) CK(ctx, cudaMemcpyAsync(depth + hi, ctx->depth_dev + hi, (n - hi) * 4, cudaMemcpyDeviceToHost, ps));
+            }
+        }
         CK(ctx, cudaEventRecord(L.ev_traced, ctx->stream));
         CK(ctx, cudaStreamWaitEvent(ps, L.ev_traced, 0));
-        ArenaHeader* hd = hdr_of(L.arena);
         for (uint32_t r = 1; r < L.world; ++r)
             if ((rc = wait_flag(ctx, ps, &hd->frame_done[r], t + 1u)) != SDFGPU_OK) return rc;
         timing_mark(ctx, ps);
-        const ArenaLayout lay = arena_layout(L.max_pixels, L.want_gbuf);
-        const size_t n = (size_t)L.cur_w * L.cur_h;
-        CK(ctx, launch_keys_unpack(reinterpret_cast<const unsigned long long*>(L.arena + lay.keys[t & 1u]), (uint32_t)n,
-                                   reinterpret_cast<uint8_t*>(ctx->rgba8_dev), ctx->depth_dev, ps));
-        ctx->launches++;
-        if (rgba8) CK(ctx, cudaMemcpyAsync(rgba8, ctx->rgba8_dev, n * 4, cudaMemcpyDeviceToHost, ps));
-        if (depth) CK(ctx, cudaMemcpyAsync(depth, ctx->depth_dev, n * 4, cudaMemcpyDeviceToHost, ps));
+        const size_t lo = y0 * L.cur_w, cnt = (y1 - y0) * L.cur_w;  // the rows that came through the key frame
+        if (cnt) {
+            CK(ctx, launch_keys_unpack(reinterpret_cast<const unsigned long long*>(L.arena + lay.keys[t & 1u]) + lo, (uint32_t)cnt,
+                                       reinterpret_cast<uint8_t*>(ctx->rgba8_dev + lo), ctx->depth_dev + lo, ps));
+            ctx->launches++;
+            if (rgba8) CK(ctx, cudaMemcpyAsync(rgba8 + lo * 4, ctx->rgba8_dev + lo, cnt * 4, cudaMemcpyDeviceToHost, ps));
+            if (depth) CK(ctx, cudaMemcpyAsync(depth + lo, ctx->depth_dev + lo, cnt * 4, cudaMemcpyDeviceToHost, ps));
+        }
         if (gbuf && L.cur_gbuf)
             CK(ctx, cudaMemcpyAsync(gbuf, L.arena + lay.gbuf, n * SDFGPU_GBUF_FLOATS * sizeof(float), cudaMemcpyDeviceToHost, ps));
         uint32_t* flags[LINK_MAX_WORLD];

@@ -127,6 +127,7 @@ struct LinkState {
     // frame in flight (begin / round / end are separate so that a single-process group can interleave ranks)
     uint32_t cur_w = 0, cur_h = 0, cur_round = 0;
     bool cur_gbuf = false;
+    bool cur_outside_first = false;  // this frame's presenter kernel writes the tiles outside the rectangle first, into the frame
     bool in_frame = false;
     // SDFGPU_LINK_TIMING=1 (development): events around the waits and the kernel of every round, printed to stderr
     // by a synchronising sdfgpu_trace_linked

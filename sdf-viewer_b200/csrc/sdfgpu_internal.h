@@ -105,6 +105,14 @@ struct LinkParams {
     unsigned long long* out_final[2];       // the same word of the neighbours (peer memory)
     const float4* in_q[2];                  // entries, own memory; null without a neighbour on that side
     float4* out_q[2];                       // peer memory
+    // presenter only: the tiles outside the screen rectangle of the box (no ray: the presenter alone writes them) come
+    // FIRST and go straight into the RGBA8 / depth frame instead of the key frame; the last of their units raises
+    // outside_flag, on which the presenter's stream waits to copy the rows that hold nothing else to the host while
+    // the frame is still being traced.  Null: the tiles outside come last and go into the key frame like every pixel.
+    uint32_t* out_rgba8;
+    float* out_depth;
+    uint32_t* outside_done;                 // local counter, reset by the last CTA
+    uint32_t* outside_flag;                 // local: epoch of the last frame whose outside tiles are all written
 };
 
 // launchers (fill.cu / trace.cu).  `program`: dev::PROG_INTERPRET or dev::PROG_DEMO (built in)

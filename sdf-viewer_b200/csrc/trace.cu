@@ -883,7 +883,10 @@ __global__ void __launch_bounds__(256, 4) trace_stream_kernel(const __grid_const
     const uint32_t rh4 = min(P.rect[3] * 2u, tiles_y4) - ry0;
     const uint32_t n_heavy = rw * rh4;
     const uint32_t n_outside = P.tiles_x * tiles_y4 - n_heavy;
-    const uint32_t n_units = n_heavy + (L.is_presenter ? (n_outside + OUTSIDE_RUN - 1u) / OUTSIDE_RUN : 0u);
+    const uint32_t n_out_units = L.is_presenter ? (n_outside + OUTSIDE_RUN - 1u) / OUTSIDE_RUN : 0u;
+    const uint32_t n_units = n_heavy + n_out_units;
+    // unit numbers: the tiles inside the rectangle, then the runs outside it -- or, with out_rgba8, the other way round
+    const uint32_t out_first = L.out_rgba8 ? 0u : n_heavy, heavy_first = L.out_rgba8 ? n_out_units : 0u;
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t capacity = (L.max_pixels + 31u) & ~31u;  // entries per queue buffer
     const uint32_t tag = L.epoch;
@@ -919,7 +922,8 @@ __global__ void __launch_bounds__(256, 4) trace_stream_kernel(const __grid_const
         // rest of it in a later pass.  A ticket beyond the final count is void.  Lane q looks after queue q.
         bool got = false, open = false;
         const bool tile_next = unit < n_units;
-        if (!tile_next || unit < n_heavy) {  // (not between the presenter's store-only runs: they are short)
+        const bool outside_next = tile_next && unit >= out_first && unit - out_first < n_out_units;
+        if (!outside_next) {  // (not between the presenter's store-only runs: they are short)
             uint32_t cnt = 0, fin = 0, tk = lane ? pend1 : pend0, msk = lane ? mask1 : mask0, op = 0u, pre = 0u, valid = 0xffffffffu;
             if (lane < 2u && L.in_q[lane]) {
                 const uint32_t q = lane;
@@ -989,8 +993,8 @@ __global__ void __launch_bounds__(256, 4) trace_stream_kernel(const __grid_const
         if (got) {
             sleep_ns = 32u; idle_since = 0ull;
         } else if (tile_next) {
-            if (unit >= n_heavy) {  // a run of tiles no ray of which enters the box: miss code -3, no arithmetic
-                const uint32_t b0 = (unit - n_heavy) * OUTSIDE_RUN, b1 = min(b0 + OUTSIDE_RUN, n_outside);
+            if (outside_next) {  // a run of tiles no ray of which enters the box: miss code -3, no arithmetic
+                const uint32_t b0 = (unit - out_first) * OUTSIDE_RUN, b1 = min(b0 + OUTSIDE_RUN, n_outside);
                 const uint32_t n_top = ry0 * P.tiles_x, side = P.tiles_x - rw;
                 for (uint32_t bb = b0; bb < b1; ++bb) {
                     uint32_t b = bb, tx, ty;
@@ -1005,17 +1009,38 @@ __global__ void __launch_bounds__(256, 4) trace_stream_kernel(const __grid_const
                         tx = b % P.tiles_x; ty = ry0 + rh4 + b / P.tiles_x;
                     }
                     const uint32_t i = tx * 8u + (lane & 7u), j = ty * 4u + (lane >> 3);
-                    if (i < P.width && j < P.height) finish_pixel<SNAP, LINEAR>(P, L, v0, v1, j * P.width + i, false, -3.0f, r);
+                    if (i < P.width && j < P.height) {
+                        const uint32_t opx = j * P.width + i;
+                        // rows of tiles above / below the rectangle go into the frame itself -- depth 1, colour 0, what
+                        // the key of a miss unpacks to --; tiles beside it share their rows with rays: key frame
+                        if (L.out_rgba8 && (ty < ry0 || ty >= ry0 + rh4)) {
+                            L.out_rgba8[opx] = 0u;
+                            L.out_depth[opx] = 1.0f;
+                            if (L.frame_gbuf) {
+                                float4* gp = reinterpret_cast<float4*>(L.frame_gbuf + (size_t)opx * SDFGPU_GBUF_FLOATS);
+                                gp[0] = make_float4(0.f, 0.f, 0.f, -3.0f);
+                                gp[1] = gp[2] = gp[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        } else {
+                            finish_pixel<SNAP, LINEAR>(P, L, v0, v1, opx, false, -3.0f, r);
+                        }
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) {
+                    if (L.out_rgba8) {
+                        __threadfence();  // the run's pixels before the count that may raise the flag
+                        if (atomicAdd(L.outside_done, 1u) + 1u == n_out_units)
+                            *reinterpret_cast<volatile uint32_t*>(L.outside_flag) = L.epoch;
+                    }
                     if (atomicAdd(L.tiles_done, 1u) + 1u == n_units) { stream_maybe_close(L, 0, n_units); stream_maybe_close(L, 1, n_units); }
                     unit = n_warps + atomicAdd(L.work_head, 1u);
                 }
                 unit = __shfl_sync(0xffffffffu, unit, 0);
                 continue;
             }
-            const uint32_t tx = P.rect[0] + unit % rw, ty = ry0 + unit / rw;
+            const uint32_t hu = unit - heavy_first;
+            const uint32_t tx = P.rect[0] + hu % rw, ty = ry0 + hu / rw;
             const uint32_t i = tx * 8u + (lane & 7u), j = ty * 4u + (lane >> 3);
             if (i < P.width && j < P.height) {
                 px = j * P.width + i;
@@ -1122,6 +1147,7 @@ __global__ void __launch_bounds__(256, 4) trace_stream_kernel(const __grid_const
         __threadfence_system();
         if (atomicAdd(L.ctas_done, 1u) + 1u == gridDim.x) {
             *L.work_head = 0u; *L.ctas_done = 0u; *L.tiles_done = 0u;
+            if (L.outside_done) *L.outside_done = 0u;
             L.in_head[0] = L.in_head[1] = 0u; L.in_done[0] = L.in_done[1] = 0u;
             L.sent_final[0] = L.sent_final[1] = 0u; L.out_count[0] = L.out_count[1] = 0u;
             __threadfence_system();
