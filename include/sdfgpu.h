@@ -525,6 +525,9 @@ uint64_t sdfgpu_launch_count(const sdfgpu_ctx* ctx);
  *                  a fast mode OUTSIDE the 1e-5 parity bar).  1-3 pay off when many frames are traced per fill
  *   "trace_variant" 0 heavy-first 8x8 tiles | 1 plain 2-D grid | 2 persistent warps pulling 8x4 tiles from a queue,
  *                  explicit warp-ballot exit (the kernel linked handles always use); same frame bit for bit
+ *   "trace_tile_order" 0 | 1 auto (default) | 2 always: the tile grid starts the tiles whose marches were longest in the
+ *                  previous frame of the same size first, so that a frame does not end on a long march that started
+ *                  late; auto = when the box's screen rectangle holds at least half of the frame's tiles.  Same frame
  *   "trace_bands" 1..32 (default 6): sdfgpu_trace_rgba8 traces the frame in this many bands of tile rows and copies each
  *                  band's rows to the host while the next is traced (1: trace, then copy); same pixels
  *   "link_wait_mode" 0 cuStreamWaitValue32 when the driver has it (default) | 1 spin-wait kernels; before link_attach

@@ -237,6 +237,14 @@ struct sdfgpu_ctx {
     cudaStream_t halo_stream = nullptr;  // DMA pushes of the boundary slices, overlapped with the interior fill
     cudaStream_t copy_stream = nullptr;  // frame rows to the host while the next band of the frame is traced
     cudaStream_t copy_stream2 = nullptr; //   ... colour on the first, depth on the second
+    // per 8x8-pixel tile: the longest march of the frame being traced / of the previous frame; the tile order made of it
+    uint32_t* tile_cost[2] = {nullptr, nullptr};
+    uint32_t* tile_order = nullptr;
+    size_t tile_cap = 0;
+    int cost_cur = 0;
+    bool cost_valid = false;
+    uint32_t cost_w = 0, cost_h = 0;
+    int opt_tile_order = 1;              // 0: the tiles inside the rectangle row by row; 1: auto; 2: always by cost
     uint32_t* band_counters = nullptr;   // 64 per-band CTA counters + 64 per-band flags (trace_tiles_kernel)
     uint32_t band_epoch = 0;
     int opt_trace_bands = 6;             // sdfgpu_trace_rgba8: bands per frame (1: trace the frame, then copy it)

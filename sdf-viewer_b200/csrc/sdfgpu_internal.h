@@ -47,6 +47,10 @@ struct TraceParams {
     uint8_t band_order[TRACE_MAX_BANDS];
     uint32_t* band_done;                      // n_bands counters (zero between frames)
     uint32_t* band_flags;                     // n_bands flags, awaited by stream memory operations
+    // trace_tiles_kernel: the order of the tiles inside the rectangle (tile ids ty * tiles_x + tx, band by band; null:
+    // row by row) and where it records this frame's longest march per tile (null: nowhere) -- see tile_order_kernel
+    const uint32_t* tile_order;
+    uint32_t* tile_cost;
     float4* rgba;              // may be null
     float* depth;              // may be null
     float* gbuf;               // may be null
@@ -146,6 +150,7 @@ cudaError_t launch_gather_dist(const float4* tex0, const uint32_t* idx_dev, size
                                cudaStream_t s);
 cudaError_t launch_set_const(float4* dst, size_t n_texels, float v, int grid_ctas, cudaStream_t s);
 cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s);
+cudaError_t launch_tile_order(const TraceParams& p, const uint32_t* prev_cost, uint32_t* order, cudaStream_t s);
 cudaError_t launch_trace_rounds(const TraceParams& p, const LinkParams& l, int grid_ctas, cudaStream_t s);
 int trace_rounds_max_ctas_per_sm(const TraceParams& p);
 cudaError_t launch_trace_stream(const TraceParams& p, const LinkParams& l, int grid_ctas, cudaStream_t s);

@@ -307,7 +307,7 @@ __device__ __forceinline__ void write_outside(const TraceParams& P, size_t px) {
 }
 
 template <bool SNAP, bool LINEAR, int DIST = 0, bool FULL = false>
-__device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, uint32_t j) {
+__device__ __forceinline__ int trace_pixel(const TraceParams& P, uint32_t i, uint32_t j) {  // returns the ray's steps
     const size_t px = (size_t)j * P.width + i;
 
     const Vol v0{P.tex0, (int)P.W, (int)P.H, (int)P.D, (int)P.z_lo, (int)P.z_hi};
@@ -430,6 +430,7 @@ __device__ __forceinline__ void trace_pixel(const TraceParams& P, uint32_t i, ui
     }
     if (P.keys) P.keys[px] = pack_key(depth, out.x, out.y, out.z, out.w);
     if (P.rgba8) P.rgba8[px] = (uint32_t)(pack_key(depth, out.x, out.y, out.z, out.w) & 0xffffffffull);
+    return steps;
 }
 
 // Variant 0 (default): 1-D grid of 8 x 8 pixel tiles (2 warps of 8 x 4), ordered so that the tiles
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(64) trace_tiles_kernel(const __grid_constant__
     // the CTAs come band by band in the order of band_order -- a band is the tile rows [ty0, ty1) -- and within a band
     // first one CTA per tile inside the rectangle (clipped to the band), then one per run of TRACE_OUTSIDE_RUN tiles
     // outside it (no ray, stores only: a CTA per tile costs more to schedule than its 64 pixels take to write)
-    uint32_t b = blockIdx.x, band = 0, ty0 = 0, ty1 = P.tiles_y, ry0, ry1, rw, n_heavy, n_out, n_ctas;
+    uint32_t b = blockIdx.x, band = 0, ty0 = 0, ty1 = P.tiles_y, ry0, ry1, rw, n_heavy, n_out, n_ctas, heavy_off = 0;
     for (uint32_t k = 0;; ++k) {
         if (P.n_bands) {
             band = P.band_order[k];
@@ -454,12 +455,24 @@ __global__ void __launch_bounds__(64) trace_tiles_kernel(const __grid_constant__
         n_ctas = n_heavy + (n_out + TRACE_OUTSIDE_RUN - 1u) / TRACE_OUTSIDE_RUN;
         if (b < n_ctas || k + 1u >= P.n_bands) break;
         b -= n_ctas;
+        heavy_off += n_heavy;
     }
     const uint32_t rh = ry1 - ry0;
     if (b < n_heavy) {
-        const uint32_t tx = P.rect[0] + b % rw, ty = ry0 + b / rw;
+        // the tiles inside the rectangle: row by row, or -- tile_order -- the ones whose marches were longest in the
+        // previous frame first (tile_order_kernel), so that the frame does not end on a long march that started late
+        uint32_t tx = P.rect[0] + b % rw, ty = ry0 + b / rw;
+        if (P.tile_order) {
+            const uint32_t id = P.tile_order[heavy_off + b];
+            tx = id % P.tiles_x; ty = id / P.tiles_x;
+        }
         const uint32_t i = tx * 8u + (threadIdx.x & 7u), j = ty * 8u + (threadIdx.x >> 3);
-        if (i < P.width && j < P.height) trace_pixel<SNAP, LINEAR, DIST, FULL>(P, i, j);
+        int steps = 0;
+        if (i < P.width && j < P.height) steps = trace_pixel<SNAP, LINEAR, DIST, FULL>(P, i, j);
+        if (P.tile_cost) {  // this frame's cost of the tile: its longest march
+            steps = __reduce_max_sync(0xffffffffu, steps);
+            if ((threadIdx.x & 31u) == 0u) atomicMax(P.tile_cost + ty * P.tiles_x + tx, (uint32_t)steps);
+        }
     } else {
         const uint32_t o0 = (b - n_heavy) * TRACE_OUTSIDE_RUN, o1 = min(o0 + TRACE_OUTSIDE_RUN, n_out);
         const uint32_t n_top = (ry0 - ty0) * P.tiles_x, side = P.tiles_x - rw;
@@ -1210,6 +1223,75 @@ __global__ void keys_unpack_kernel(const unsigned long long* __restrict__ keys, 
 }
 
 }  // namespace
+
+// The tiles inside the screen rectangle of the box, sorted for trace_tiles_kernel: by band (in the order the kernel walks
+// the bands), within a band by the longest march the tile had in the PREVIOUS frame, longest first.  A counting sort
+// by one CTA (the keys are 32 bands x 256 step counts).  Always a permutation of the CURRENT rectangle's tiles -- the old
+// costs only decide the order, so a camera that has moved costs some of the gain, never a pixel.
+namespace {
+__global__ void __launch_bounds__(1024) tile_order_kernel(const __grid_constant__ TraceParams P, const uint32_t* __restrict__ prev,
+                                                          uint32_t* __restrict__ order) {
+    constexpr uint32_t NB = TRACE_MAX_BANDS * 256u;
+    __shared__ uint32_t bins[NB];
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t band_pos[TRACE_MAX_BANDS];
+    const uint32_t tid = threadIdx.x, rw = P.rect[2] - P.rect[0], rh = P.rect[3] - P.rect[1], n = rw * rh;
+    for (uint32_t k = tid; k < NB; k += 1024u) bins[k] = 0u;
+    if (tid < TRACE_MAX_BANDS) band_pos[tid] = 0u;
+    __syncthreads();
+    if (tid < P.n_bands) band_pos[P.band_order[tid]] = tid;
+    __syncthreads();
+    auto key_of = [&](uint32_t i, uint32_t& id) {
+        const uint32_t tx = P.rect[0] + i % rw, ty = P.rect[1] + i / rw;
+        id = ty * P.tiles_x + tx;
+        const uint32_t cost = min(prev[id], 255u);
+        const uint32_t pos = P.n_bands ? band_pos[min(ty / P.band_rows, TRACE_MAX_BANDS - 1u)] : 0u;
+        return pos * 256u + (255u - cost);
+    };
+    for (uint32_t i = tid; i < n; i += 1024u) {
+        uint32_t id;
+        atomicAdd(&bins[key_of(i, id)], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the bins: 8 per thread, then the 1024 partial sums
+    constexpr uint32_t PER = NB / 1024u;
+    uint32_t local[PER], sum = 0u;
+#pragma unroll
+    for (uint32_t k = 0; k < PER; ++k) { local[k] = bins[tid * PER + k]; sum += local[k]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31u) >= (uint32_t)o) incl += v;
+    }
+    if ((tid & 31u) == 31u) warp_sums[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32u) {
+        uint32_t w = warp_sums[tid], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (tid >= (uint32_t)o) wi += v;
+        }
+        warp_sums[tid] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[tid >> 5] + incl - sum;
+#pragma unroll
+    for (uint32_t k = 0; k < PER; ++k) { bins[tid * PER + k] = run; run += local[k]; }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += 1024u) {
+        uint32_t id;
+        const uint32_t key = key_of(i, id);
+        order[atomicAdd(&bins[key], 1u)] = id;
+    }
+}
+}  // namespace
+
+cudaError_t launch_tile_order(const TraceParams& p, const uint32_t* prev_cost, uint32_t* order, cudaStream_t s) {
+    tile_order_kernel<<<1, 1024, 0, s>>>(p, prev_cost, order);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_trace(const TraceParams& p, int variant, cudaStream_t s) {
     if (p.width == 0 || p.height == 0) return cudaSuccess;

@@ -179,6 +179,26 @@ def test_rgba8_frame_in_bands(S):
         v.set_option("trace_bands", 6)
 
 
+def test_tile_order_from_the_previous_frame(S):
+    """The tile grid starts the tiles with the longest marches of the PREVIOUS frame first (option trace_tile_order):
+    whatever the previous frame was -- the same camera, another one, another frame size, a frame in bands -- the
+    pixels are those of the row-by-row order."""
+    with fill(S, S.tape.demo_tape(), (64, 64, 64)) as v:
+        shots = [(640, 480, None), (640, 480, None), (640, 480, ((0.9, 1.1, 1.8), (0, 0, 0))), (640, 480, None),
+                 (333, 211, None), (640, 480, ((0.2, 0.1, 0.3), (1, 0.2, -0.4))), (640, 480, ((0.2, 0.1, 0.3), (1, 0.2, -0.4)))]
+        frames = {}
+        for order in (0, 2):
+            v.set_option("trace_tile_order", order)
+            frames[order] = []
+            for (w, h, cam) in shots:
+                c = S.default_camera(w, h) if cam is None else S.look_at_camera(cam[0], cam[1], w, h)
+                frames[order].append(v.trace(c, w, h, gbuf=True) + v.trace_rgba8(c, w, h))
+        for a, b in zip(frames[0], frames[2]):
+            for x, y in zip(a, b):
+                assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+        v.set_option("trace_tile_order", 1)
+
+
 def test_uncommitted_nearest(S, oracle):
     """Before any commit lod stays 1 and the GL filter is NEAREST (scene/sdf/mod.rs:110-111)."""
     w, h = 256, 192
