@@ -157,3 +157,9 @@ def test_trace_known_answers_derived_by_hand(oracle):
         P = oracle.trace_params(rays, K.BB, dims, lod=lod, filter_linear=linear)
         rgba, depth, gbuf = oracle.trace(P, t0, t1, K.W, K.H)
         K.check(name, gbuf, depth, rgba)
+    for name, eye, dims, r, exp in K.cases_oracle_only():  # the step limit; the ray origin with the camera inside the box
+        t0, t1 = K._volume(dims, r)
+        target = (eye[0], eye[1], eye[2] - 1.0)
+        P = oracle.trace_params(oracle.camera_rays(eye, target, K.UP, K.FOVY, K.W, K.H), K.BB, dims, lod=1.0, filter_linear=1)
+        rgba, depth, gbuf = oracle.trace(P, t0, t1, K.W, K.H)
+        K.check_expectation(name, exp, gbuf, depth, rgba)

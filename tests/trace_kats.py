@@ -33,6 +33,20 @@ KAT 3  NEAREST filter while loading, lod 2 (:27-36), N = 8 slices, tex0.r = 0.4 
        a) solid slice 5: never read (an un-snapped NEAREST fetch would read it at z = 0.4): miss, w = -2, i = 7.
        b) solid slice 6: hit at z = 0.7, i = 1, w = t = 0.3.
        c) solid slice 4: hit at z = 0.1, i = 3, w = t = 0.9.
+
+Two more, checked against the CPU oracle only (tests/test_oracle.py; the kernels are compared with the oracle in these
+regimes by test_trace_gpu.py: cameras inside the box, step counts of every pixel exact):
+
+KAT 4  the step limit (:97-102, maxSteps = 256 at :142): constant volume tex0.r = f32(0.104): sampleDist =
+       f32(0.104) - f32(0.1) = 0.0040000007 (exact: the operands are within a factor of two).  Never < 1e-5, never out of
+       bounds (1 - 255 * 0.004 = -0.02): iterations i = 0 .. 254 each advance the ray, iteration i = 255 returns w = -1
+       before it samples: a MISS with i = 255 at z = 1 - 255 * 0.0040000007 = -0.0200002.
+
+KAT 5  the ray origin with the camera INSIDE the box (:133-139).  Camera (0, 0, 0.5) looking down -z: the front faces
+       of the cube are behind the near plane, the fragment of the centre pixel lies on the back face, pos = (0, 0, -1).
+       pos + 0.2 dir = (0, 0, -1.2) is outside the box, so rayOrigin = cameraPosition + 0.2 dir = (0, 0, 0.3) (:138).
+       Constant volume 0.6 (sampleDist 0.5): z = 0.3, -0.2, -0.7 are sampled, z = -1.2 is out of bounds: miss, w = -2,
+       i = 3, rayPos = (0, 0, -1.2).
 """
 import numpy as np
 
@@ -95,3 +109,21 @@ def check(name, gbuf, depth, rgba):
         assert rgba[PIXEL][3] == 1.0 and depth[PIXEL] < 1.0
     else:
         assert not rgba[PIXEL].any() and depth[PIXEL] == 1.0  # :145-149
+
+
+def cases_oracle_only():
+    """(name, eye, dims, tex0.r per slice, expected) -- KAT 4 and KAT 5 of the module docstring."""
+    d = float(np.float32(0.104) - np.float32(0.1))
+    return [("the step limit: 255 advances, then w = -1", EYE, (4, 4, 4), [0.104] * 4,
+             dict(hit=False, code=-1.0, steps=255, z=1.0 - 255.0 * d)),
+            ("camera inside the box: the ray starts 0.2 in front of it", (0.0, 0.0, 0.5), (4, 4, 4), [0.6] * 4,
+             dict(hit=False, code=-2.0, steps=3, z=-1.2))]
+
+
+def check_expectation(name, exp, gbuf, depth, rgba):
+    g = gbuf[PIXEL]
+    assert (g[3] >= 0) == exp["hit"], (name, g[3])
+    assert int(g[15]) == exp["steps"], (name, "steps", g[15], exp["steps"])
+    np.testing.assert_allclose(g[3], exp["code"], rtol=1e-5, atol=1e-6, err_msg=name)
+    np.testing.assert_allclose(g[0:3], [0.0, 0.0, exp["z"]], rtol=1e-5, atol=2e-6, err_msg=name)
+    assert not rgba[PIXEL].any() and depth[PIXEL] == 1.0
