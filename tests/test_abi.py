@@ -83,6 +83,15 @@ def test_no_cpu_fallback_without_device(S):
     with pytest.raises(S.SdfGpuError) as e:
         S.SDFViewer.from_bb(((-1, -1, -1), (1, 1, 1)), 16, 2)
     assert e.value.code == -2 and "no CPU fallback" in e.value.message
+    # ... the slab and group constructors included (every compute entry point needs a handle they would have made)
+    with pytest.raises(S.SdfGpuError) as e:
+        S.SDFViewer.new_voxels((16, 16, 16), ((-1, -1, -1), (1, 1, 1)), 1, z_range=(0, 8))
+    assert e.value.code == -2
+    for make in (lambda: S.SDFViewerGroup.from_bb(((-1, -1, -1), (1, 1, 1)), 16, 1, device_mask=3),
+                 lambda: S.SDFViewerGroup.new_voxels((16, 16, 16), ((-1, -1, -1), (1, 1, 1)), 1, [0, 0])):
+        with pytest.raises(S.SdfGpuError) as e:
+            make()
+        assert e.value.code == -2 and "no CPU fallback" in e.value.message
 
 
 def test_product_does_not_import_oracle():
