@@ -571,16 +571,19 @@ def main():
 
     from sdf_viewer_b200.sharded import ShardedViewer
     want_c4 = world > 1 and not args.no_extras
-    sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, fused=not args.no_fused_halo,
-                       linked=not args.no_linked, max_width=max(W, 3840 if want_c4 else 0), max_height=max(H, 2160 if want_c4 else 0),
-                       halo_push=args.halo_push, trace_mode=1 if args.trace_rounds else 0)
-    v = sv.viewer
-    if args.vpt:
-        v.set_option("fill_voxels_per_thread", args.vpt)
-    if args.ctas:
-        v.set_option("fill_ctas_per_sm", args.ctas)
-    v.set_tape(tape)
-    stream = torch.cuda.ExternalStream(v.stream, device=torch.device("cuda", local))
+    def make_viewer(trace_mode):
+        sv = ShardedViewer(dims, BB, 2, rank=rank, world=world, device=local, group=dist, fused=not args.no_fused_halo,
+                           linked=not args.no_linked, max_width=max(W, 3840 if want_c4 else 0), max_height=max(H, 2160 if want_c4 else 0),
+                           halo_push=args.halo_push, trace_mode=trace_mode)
+        v = sv.viewer
+        if args.vpt:
+            v.set_option("fill_voxels_per_thread", args.vpt)
+        if args.ctas:
+            v.set_option("fill_ctas_per_sm", args.ctas)
+        v.set_tape(tape)
+        return sv, v, torch.cuda.ExternalStream(v.stream, device=torch.device("cuda", local))
+
+    sv, v, stream = make_viewer(1 if args.trace_rounds else 0)
     own_voxels = dims[0] * dims[1] * (v.z_end - v.z_begin)
     total_voxels = dims[0] * dims[1] * dims[2]
 
@@ -602,8 +605,38 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
+    # The warm-up doubles as the check that the ranks' streaming trace kernels find each other (they wait for one another
+    # inside the kernel and give up after link_timeout_ms).  Should any rank fail here, EVERY rank falls back to the
+    # trace in rounds -- the same frame, no kernel that waits -- rather than lose the line; the line then says so.
+    fallback = None
+    ok, why = 1, ""
+    try:
+        for _ in range(args.warmup):
+            step_device()
+        v.sync()
+        if os.environ.get("SDFGPU_BENCH_FORCE_FALLBACK") and world > 1 and rank == world - 1:
+            raise RuntimeError("forced by SDFGPU_BENCH_FORCE_FALLBACK (test of the fallback)")
+    except Exception as e:
+        ok, why = 0, str(e)
+    if dist:
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        all_ok = bool(flag.item())
+    else:
+        all_ok = bool(ok)
+    if not all_ok:
+        if not (world > 1 and sv.linked and not args.trace_rounds):
+            raise SystemExit(f"bench.py: the warm-up failed: {why or 'on another rank'}")
+        whys = [None] * world
+        dist.all_gather_object(whys, why)
+        fallback = "streaming trace failed in the warm-up (" + "; ".join(f"rank {r}: {w}" for r, w in enumerate(whys) if w) + "): trace in rounds"
+        try:
+            sv.close()
+        except Exception:
+            pass
+        sv, v, stream = make_viewer(1)
+        for _ in range(args.warmup):
+            step_device()
     sync_all()
     l0 = v.launch_count
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
@@ -691,7 +724,7 @@ def main():
             except Exception as e:
                 c4 = {"error": str(e)}
     alt = None
-    if world > 1 and sv.linked and not args.no_extras and not args.halo_push and not args.trace_rounds:
+    if world > 1 and sv.linked and not args.no_extras and not args.halo_push and not args.trace_rounds and not fallback:
         alt = alt_modes_multi(torch, dist, ShardedViewer, dims, tape, cam, W, H, rank, world, local)
     trace_modes = extras = None
     if n_gpus == 1 and not args.no_extras:
@@ -744,6 +777,8 @@ def main():
         "trace_modes": trace_modes,
         "trace_profile": trace_profile() if headline_cfg else None,
     }
+    if fallback:
+        out["fallback"] = fallback
     if parity is not None:
         out["parity_check"] = parity["status"]
         out["parity_detail"] = parity
