@@ -163,3 +163,34 @@ def test_trace_known_answers_derived_by_hand(oracle):
         P = oracle.trace_params(oracle.camera_rays(eye, target, K.UP, K.FOVY, K.W, K.H), K.BB, dims, lod=1.0, filter_linear=1)
         rgba, depth, gbuf = oracle.trace(P, t0, t1, K.W, K.H)
         K.check_expectation(name, exp, gbuf, depth, rgba)
+
+
+def test_oracle_equals_an_independent_numpy_restatement(oracle):
+    """tests/demo_numpy_ref.py -- a second reading of the reference's Rust, written without looking at the C++ oracle --
+    against the oracle: SDFDemo::sample bit for bit on random points and on the voxel positions of a grid (where seams,
+    brick joints and the air early-outs are hit exactly), for the defaults and for other parameters; the stored
+    texels of SDFViewer::update bit for bit except the sRGB decode (glibc's f32 powf: within 5e-7 of the correctly rounded value)."""
+    import demo_numpy_ref as R
+    f32 = np.float32
+    rng = np.random.default_rng(11)
+    dims = (40, 36, 33)
+    grid = R.voxel_positions(dims, BB).reshape(-1, 3)
+    pts = np.concatenate([rng.uniform(-1.2, 1.2, (100000, 3)).astype(f32), grid,
+                          np.array([[1, 0, 0], [0.95, 0.95, 0.95], [0, 0, 0], [-1, 1, -1], [0.25, -0.125, 0.0], [-0.0, 0.0, 1.0]], f32)])
+    for kw in ({}, {"cube_half_side": 0.8, "sphere_radius": 0.9, "max_distance_custom_material": 0.1}):
+        want = R.demo_sample(pts, kw.get("cube_half_side", 0.95), kw.get("sphere_radius", 1.05), kw.get("max_distance_custom_material", 0.05))
+        got = oracle.demo_sample(pts, oracle.demo_params(**kw))
+        same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+        assert same.all(), (kw, np.argwhere(~same)[:5], pts[np.argwhere(~same)[:3, 0]], got[~same][:5], want[~same][:5])
+        # every branch is exercised: cement, brick, seam, sphere material, air
+        assert (want[:, 4] == f32(0.4)).any() and (want[:, 4] == f32(0.2)).any() and (want[:, 4] == f32(0.5)).any()
+        assert ((want[:, 1:4] == 0).all(1)).any() and ((want[:, 4] == 0) & (want[:, 1] > 0)).any()
+    # positions and stored texels of a whole grid
+    o = oracle.Viewer(BB, dims, 1)
+    o.fill_all(oracle.Sampler())
+    assert np.array_equal(np.array([o.voxel_pos(x, 7, 5) for x in range(dims[0])], f32).view(np.uint32),
+                          R.voxel_positions(dims, BB)[5, 7].view(np.uint32))
+    t0, t1 = R.store(R.demo_sample(grid), f32(0.1) + f32(0.001234))
+    o0, o1 = o.tex0.reshape(-1, 4), o.tex1.reshape(-1, 4)
+    assert np.array_equal(t0[:, 0].view(np.uint32), o0[:, 0].view(np.uint32)) and np.array_equal(t1.view(np.uint32), o1.view(np.uint32))
+    np.testing.assert_allclose(t0[:, 1:], o0[:, 1:], rtol=5e-7, atol=0)  # glibc's f32 powf against the correctly rounded value
