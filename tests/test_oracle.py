@@ -194,3 +194,31 @@ def test_oracle_equals_an_independent_numpy_restatement(oracle):
     o0, o1 = o.tex0.reshape(-1, 4), o.tex1.reshape(-1, 4)
     assert np.array_equal(t0[:, 0].view(np.uint32), o0[:, 0].view(np.uint32)) and np.array_equal(t1.view(np.uint32), o1.view(np.uint32))
     np.testing.assert_allclose(t0[:, 1:], o0[:, 1:], rtol=5e-7, atol=0)  # glibc's f32 powf against the correctly rounded value
+
+
+@pytest.mark.parametrize("eye,target,lod,linear", [((2.5, 3.0, 5.0), (0, 0, 0), 1.0, 1), ((0.9, 1.1, 1.8), (0, 0, 0), 1.0, 1),
+                                                     ((0.2, 0.1, 0.3), (1, 0.2, -0.4), 1.0, 1), ((2.5, 3.0, 5.0), (0, 0, 0), 2.0, 0),
+                                                     ((2.5, 3.0, 5.0), (0, 0, 0), 1.0, 0)])
+def test_oracle_trace_equals_an_independent_numpy_restatement(oracle, eye, target, lod, linear):
+    """tests/frag_numpy_ref.py -- material.frag and the GL sampling rules read again, in numpy, without looking at the
+    oracle or the kernel -- against the oracle's G-buffer: hit / miss class, miss code and step count of (nearly) every
+    pixel identical, hit distance and position within 1e-4 (the two differ in operation order, so a grazing ray may
+    take a step more or fewer).  Cameras outside and inside the box; LINEAR, NEAREST and the lod-2 snapped fetch."""
+    import frag_numpy_ref as R
+    dims, w, h = (32, 32, 32), 96, 72
+    o = oracle.Viewer(BB, dims, 1)
+    o.fill_all(oracle.Sampler())  # (the lod-2 case snaps its fetches on a complete volume: it is the fetch that is compared)
+    rays = oracle.camera_rays(eye, target, (0.0, 1.0, 0.0), 45.0, w, h)
+    P = oracle.trace_params(rays, BB, dims, lod=lod, filter_linear=linear)
+    _, _, g = oracle.trace(P, o.tex0, o.tex1, w, h)
+    code, steps, where = R.trace(rays, BB, o.tex0, w, h, lod=lod, linear=bool(linear))
+    ocode, osteps = g[..., 3], g[..., 15].astype(np.int32)
+    cls = lambda c: np.where(c >= 0, 0, c).astype(np.int32)  # noqa: E731   hit, or which miss
+    same_class = cls(code) == cls(ocode)
+    assert same_class.mean() > 0.999, (same_class.mean(), np.argwhere(~same_class)[:5])
+    assert (ocode >= 0).sum() > 200 and (ocode < 0).sum() > 200
+    same_steps = (steps == osteps) & same_class
+    assert same_steps.mean() > 0.995, same_steps.mean()
+    m = same_steps & (ocode > -3)
+    np.testing.assert_allclose(where[m], g[..., 0:3][m], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(code[m], ocode[m], rtol=0, atol=1e-4)
