@@ -10,6 +10,10 @@
 // reference tests are the five LoadingManager invariants
 // (/root/reference/src/app/scene/sdf/loading.rs:117-171), which tests/ port
 // verbatim.  Every function below cites the reference lines it restates.
+// What stands in for reference outputs: known answers worked out on paper from the cited lines (fill: tests/test_oracle.py;
+// trace: tests/trace_kats.py), and two restatements written a second time from the reference alone, in numpy, which this
+// file has to equal -- tests/demo_numpy_ref.py (SDFDemo::sample, positions, store rules: bit for bit) and
+// tests/frag_numpy_ref.py (material.frag + the GL sampling rules: same hit / miss class on every pixel).
 // Arithmetic from the un-vendored crates three-d 0.18.2 / three-d-asset 0.9.2 /
 // cgmath 0.18.0 (Cargo.lock:6596,6613,1054) is restated from their published
 // algorithms and isolated in srgb_u8_to_linear(), calculate_lighting(),
