@@ -22,6 +22,18 @@ def _oob(p, bmin, bmax):
     return np.max(np.maximum(bmin - p, p - bmax), axis=-1)                       # :83-88
 
 
+def sample(tex, p, bmin, bmax, lod, linear):
+    """all four lanes of sdfSampleRawInterp(k, p) at positions p (n, 3) -> (n, 4)"""
+    return np.stack([_sample_r(tex[..., c:c + 1], p, np.asarray(bmin, f32), np.asarray(bmax, f32), lod, linear) for c in range(4)], 1)
+
+
+def frag_depth(bvp, p):
+    """gl_FragDepth = (BVP * vec4(hitPos, 1)).z / .w, :180-181; bvp column-major (16,)"""
+    m = np.asarray(bvp, f32).reshape(4, 4).T
+    q = np.concatenate([p, np.ones((len(p), 1), f32)], 1) @ m.T
+    return (q[:, 2] / q[:, 3]).astype(f32)
+
+
 def _sample_r(tex0, p, bmin, bmax, lod, linear):
     """tex0.r at positions p (n, 3) -- sdfSampleRawInterp(0, p).r"""
     d, h, w = tex0.shape[:3]

@@ -222,3 +222,11 @@ def test_oracle_trace_equals_an_independent_numpy_restatement(oracle, eye, targe
     m = same_steps & (ocode > -3)
     np.testing.assert_allclose(where[m], g[..., 0:3][m], rtol=0, atol=1e-4)
     np.testing.assert_allclose(code[m], ocode[m], rtol=0, atol=1e-4)
+    # at the oracle's own hit points: the raw samples of both textures it recorded (:120, :154) and gl_FragDepth (:180-181)
+    hit = ocode >= 0
+    hp = g[..., 0:3][hit]
+    np.testing.assert_allclose(R.sample(o.tex0, hp, BB[0], BB[1], lod, bool(linear)), g[..., 4:8][hit], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(R.sample(o.tex1, hp, BB[0], BB[1], lod, bool(linear)), g[..., 8:12][hit], rtol=1e-5, atol=2e-6)
+    _, d, _ = oracle.trace(P, o.tex0, o.tex1, w, h)
+    np.testing.assert_allclose(R.frag_depth(rays.bvp, hp), d[hit], rtol=1e-5, atol=1e-6)
+    assert np.all(d[~hit] == 1.0)
